@@ -1,0 +1,67 @@
+"""Pin the oracle against the real reference (only where /root/reference exists)."""
+import pytest
+import torch
+
+import ref_shim
+from oracle import cips3d_oracle as O
+
+pytestmark = [pytest.mark.reference,
+              pytest.mark.skipif(not ref_shim.reference_available(), reason="no /root/reference")]
+
+
+@pytest.fixture(scope="module")
+def ref_G():
+    torch.manual_seed(1234)
+    return ref_shim.build_reference_generator().eval()
+
+
+@pytest.mark.parametrize("noise,kw", [
+    (0.0, {}), (0.7, {}), (0.3, dict(clamp_mode="softplus", last_back=True)),
+    (0.0, dict(white_back=True, hierarchical_sample=False)),
+])
+def test_generator_bitwise_vs_reference(ref_G, noise, kw):
+    import ref_capture
+    G = ref_G
+    sd = {k: v.clone() for k, v in G.state_dict().items()}     # reference-constructor init
+    torch.manual_seed(11)
+    zs = G.get_zs(2)
+    args = dict(ref_shim.G_KWARGS)
+    args.update(kw)
+    log = []
+    with torch.no_grad(), ref_capture.record_draws(log):
+        img, py = G(zs, img_size=12, nerf_noise=noise, return_aux_img=True, **args)
+    draws = ref_capture.draws_from_log(log, hierarchical=args["hierarchical_sample"])
+    draws.setdefault("noise_c", None)
+    draws.setdefault("pdf_u", None)
+    with torch.no_grad():
+        img2, py2 = O.generator_forward(sd, zs, draws, img_size=12, nerf_noise=noise,
+                                        return_aux_img=True, **args)
+    assert (img - img2).abs().max().item() < 1e-6
+    assert torch.equal(py, py2)
+
+
+def test_draw_order_matches_reference(ref_G):
+    """oracle.draw_randoms replays the reference's RNG call sequence (SURVEY.md §7 hard part 4)."""
+    import ref_capture
+    G = ref_G
+    zs = {"z_nerf": torch.zeros(2, 256), "z_inr": torch.zeros(2, 512)}
+    log = []
+    torch.manual_seed(5)
+    with torch.no_grad(), ref_capture.record_draws(log):
+        G(zs, img_size=8, nerf_noise=0.0, **ref_shim.G_KWARGS)
+    d_ref = ref_capture.draws_from_log(log)
+    torch.manual_seed(5)
+    d = O.draw_randoms(2, 8, 12)
+    for k in d:
+        assert torch.equal(d[k], d_ref[k]), k
+
+
+def test_discriminator_vs_reference():
+    torch.manual_seed(3)
+    D = ref_shim.build_reference_discriminator().eval()
+    sd = {k: v.clone() for k, v in D.state_dict().items()}
+    x = torch.randn(4, 3, 32, 32)
+    with torch.no_grad():
+        a = D(x, use_aux_disc=True, alpha=0.6)[0]
+        b = O.discriminator_forward(sd, x, use_aux_disc=True, alpha=0.6)
+    assert (a - b).abs().max().item() < 1e-6
