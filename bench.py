@@ -1,0 +1,256 @@
+#!/usr/bin/env python
+"""bench.py -- generator-forward throughput of the CIPS-3D hot path on N B200s.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...
+
+Metric (BASELINE.json): generator fwd images/sec @ FFHQ r256, 24 samples/ray.  A step is one
+GeneratorNerfINR.forward over a batch of synthetic latents (per-GPU batch fixed -> weak scaling);
+one rank per GPU, no data-path collective.  Prints ONE JSON line.
+"""
+import argparse
+import json
+import math
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+R, BATCH_PER_GPU, NUM_STEPS = 256, 16, 12
+NERF_FLOP_PER_RAY = 1302528.0      # BASELINE.md section 3 (24 points x 54 272)
+CIPS_FLOP_PER_PIXEL = 8964096.0
+METRIC = "generator fwd images/sec @ FFHQ r256, 24 samples/ray"
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return d["bf16_tflops"], d["hbm_gbs"], "measured (MEASURED_PEAKS.json, burst bf16)"
+    return 1590.0, 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler(threading.Thread):
+    Q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, dev):
+        super().__init__(daemon=True)
+        self.dev, self.rows, self.stop_flag = dev, [], False
+
+    def run(self):
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                      "-i", str(self.dev)], capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([c.strip() for c in out.split(",")])
+            except Exception:
+                pass
+            time.sleep(0.2)
+
+    def summary(self):
+        sm = [float(r[1]) for r in self.rows if r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in self.rows if r[2].replace(".", "").isdigit()]
+        reasons = set()
+        for r in self.rows:
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(self.rows)}
+
+
+def cpu_reference_rate(seconds_budget=20.0, threads=None, img_size=R, batch=1):
+    """The reference algorithm (CPU oracle port of exp/cips3d/models/generator.py) on the host cores."""
+    from oracle import cips3d_oracle as O
+    threads = threads or os.cpu_count()
+    torch.set_num_threads(threads)
+    sd = O.synthetic_state_dict(O.generator_template(), seed=1234)
+    kw = dict(O.G_KWARGS)
+    g = torch.Generator().manual_seed(0)
+    zs = {"z_nerf": torch.randn(batch, 256, generator=g), "z_inr": torch.randn(batch, 512, generator=g)}
+
+    def one():
+        draws = O.draw_randoms(batch, img_size, kw["num_steps"], generator=g)
+        with torch.no_grad():
+            O.generator_forward(sd, zs, draws, img_size=img_size, nerf_noise=0.0, **kw)
+
+    t0 = time.perf_counter()
+    one()                                  # warm-up (also sizes the budget)
+    t_one = time.perf_counter() - t0
+    n = max(1, min(8, int(seconds_budget / max(t_one, 1e-3))))
+    t0 = time.perf_counter()
+    for _ in range(n):
+        one()
+    dt = time.perf_counter() - t0
+    return batch * n / dt, threads, f"{n} x (batch {batch}, r{img_size}, 12+12 samples/ray) fp32 torch-CPU oracle port"
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    t0 = time.perf_counter()
+    for _ in range(max(args.warmup, 0)):
+        pass
+    per_step_budget = max(5.0, min(30.0, 150.0 / max(args.steps, 1)))
+    rates = []
+    for _ in range(args.steps):
+        r, cores, sample = cpu_reference_rate(per_step_budget)
+        rates.append(r)
+    val = float(np.mean(rates))
+    line = {"metric": METRIC, "value": val, "unit": "images/s", "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1000.0 / val, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "impl": "reference",
+            "config": {"workload": f"FFHQ r{R} generator forward, 12 coarse + 12 fine samples/ray, 1 image per step sample",
+                       "resolution": R, "samples_per_ray": 24},
+            "cpu_baseline": {"value": val, "unit": "images/s", "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": val, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0, "wall_s": time.perf_counter() - t0}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=BATCH_PER_GPU, help="images per GPU per step")
+    ap.add_argument("--res", type=int, default=R)
+    ap.add_argument("--kernel-impl", default=os.environ.get("C3D_IMPL", "tc"), choices=["tc", "simt"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        return run_reference(args, rank, world)
+
+    import torch.distributed as dist
+    assert torch.cuda.is_available(), "bench.py needs a GPU (no CPU fallback)"
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    import __graft_entry__ as ge
+    if rank == 0:
+        ge.build()
+    if world > 1:
+        dist.barrier()
+    os.environ["C3D_IMPL"] = args.kernel_impl
+    import cips3d_b200
+    from cips3d_b200 import _lib, ops
+    from oracle import cips3d_oracle as O          # weights recipe only (synthetic_state_dict)
+    lib = _lib.load()
+    res, B = args.res, args.batch
+    cfg = {k: (dict(v) if isinstance(v, dict) else v) for k, v in O.G_CFG.items()}
+    G = cips3d_b200.GeneratorNerfINR(**cfg, device=dev).to(dev).eval()
+    G.load_state_dict(O.synthetic_state_dict(O.generator_template(), seed=1234))
+    kw = dict(O.G_KWARGS)
+    torch.manual_seed(1000 + rank)
+    zs_host = {"z_nerf": torch.randn(B, 256).pin_memory(), "z_inr": torch.randn(B, 512).pin_memory()}
+    zs_dev = {k: v.to(dev) for k, v in zs_host.items()}
+    out_host = torch.empty((B, 3, res, res), dtype=torch.float32).pin_memory()
+
+    def step_resident():
+        with torch.no_grad():
+            img, _ = G(zs_dev, img_size=res, nerf_noise=0.0, **kw)
+        return img
+
+    def step_e2e():
+        with torch.no_grad():
+            z = {k: v.to(dev, non_blocking=True) for k, v in zs_host.items()}
+            img, _ = G(z, img_size=res, nerf_noise=0.0, **kw)
+            out_host.copy_(img, non_blocking=True)
+        return img
+
+    def timed(fn, steps, warmup, profile=False):
+        for _ in range(warmup):
+            fn()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        ops.PROFILE = {} if profile else None
+        l0 = lib.c3d_launch_count()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+        launches = lib.c3d_launch_count() - l0
+        prof, ops.PROFILE = ops.PROFILE, None
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dist.barrier()
+            ms = t.item()
+        return ms, launches, prof
+
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    ms, launches, prof = timed(step_resident, args.steps, args.warmup, profile=True)
+    ms_e2e, _, _ = timed(step_e2e, args.steps, max(1, args.warmup // 2))
+    if sampler:
+        sampler.stop_flag = True
+        sampler.join(timeout=2)
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    imgs = B * world * args.steps
+    value = imgs / (ms / 1e3)
+    e2e = imgs / (ms_e2e / 1e3)
+    peak_tf, peak_hbm, peak_src = peaks()
+    roof = {}
+    for key, flop_unit, units in (("cips", CIPS_FLOP_PER_PIXEL, B * res * res), ("ray", NERF_FLOP_PER_RAY, B * res * res)):
+        evs = (prof or {}).get(key, [])
+        if evs:
+            t_ms = float(np.mean([a.elapsed_time(b) for a, b in evs]))
+            ach = flop_unit * units / (t_ms * 1e-3) / 1e12
+            roof[key] = {"bound": "tensor", "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach / peak_tf,
+                         "traffic": None, "kernel_ms": t_ms, "launches_timed": len(evs),
+                         "algorithmic_flop_per_launch": flop_unit * units, "peak_source": peak_src}
+    dominant = max(roof, key=lambda k: roof[k]["kernel_ms"]) if roof else None
+    line = {
+        "metric": METRIC, "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f16-split (fp32-equivalent) ray MLP, f16 CIPS MLP, fp32 accumulate"
+        if args.kernel_impl == "tc" else "f32",
+        "data": "synthetic",
+        "config": {"workload": f"FFHQ r{res} generator forward (GeneratorNerfINR, ffhq_exp.yaml G_cfg_3D2D), "
+                               f"{B} images/GPU/step, 12 coarse + 12 fine samples/ray, nerf_noise 0",
+                   "resolution": res, "batch_per_gpu": B, "global_batch": B * world, "samples_per_ray": 24,
+                   "kernel_impl": args.kernel_impl, "parallelism": f"dp{world} (no data-path collective)",
+                   "l2": "per-step inputs (random draws ~%.0f MB) exceed the 126 MB L2" % (B * res * res * 48 * 4 / 1e6)},
+        "e2e": {"value": e2e, "unit": "images/s", "h2d_bytes_per_step": int(B * (256 + 512) * 4),
+                "d2h_bytes_per_step": int(B * 3 * res * res * 4), "ms_per_step": ms_e2e / args.steps},
+        "gpu_launches": int(launches),
+        "clocks": sampler.summary() if sampler else None,
+    }
+    if dominant:
+        line["roofline"] = dict(roof[dominant], kernel=("c3d_cips_fwd" if dominant == "cips" else "c3d_ray_siren_fwd"))
+        other = "ray" if dominant == "cips" else "cips"
+        if other in roof:
+            line["roofline_secondary"] = dict(roof[other], kernel=("c3d_cips_fwd" if other == "cips" else "c3d_ray_siren_fwd"))
+    if world == 1 and not args.no_cpu_baseline:
+        v, cores, sample = cpu_reference_rate(20.0)
+        line["cpu_baseline"] = {"value": v, "unit": "images/s", "cores": cores, "kind": "port", "sample": sample}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

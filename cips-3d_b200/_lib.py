@@ -1,0 +1,112 @@
+"""ctypes binding of libcips3d_b200.so (C-ABI declared in include/cips3d_b200.h).
+
+There is no CPU implementation and no fallback: if the shared library is missing or the
+device is not sm_100, every op raises.
+"""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libcips3d_b200.so")
+
+IMPL_TC, IMPL_SIMT = 0, 1
+CIPS_MAX_LAYERS = 18
+
+EXPORTS = ("c3d_version", "c3d_last_error", "c3d_device_supported", "c3d_launch_count",
+           "c3d_ray_siren_workspace_bytes",
+           "c3d_ray_siren_fwd", "c3d_cips_workspace_bytes", "c3d_cips_fwd", "c3d_bias_act",
+           "c3d_upfirdn2d", "c3d_selftest_umma")
+
+_fp = C.c_void_p  # device pointers travel as integers
+
+
+class RayParams(C.Structure):
+    _fields_ = [("batch", C.c_int32), ("img_size", C.c_int32), ("num_steps", C.c_int32),
+                ("n_rays", C.c_int32), ("ray_offset", C.c_int32), ("hierarchical", C.c_int32),
+                ("clamp_mode", C.c_int32), ("white_back", C.c_int32), ("last_back", C.c_int32),
+                ("impl", C.c_int32), ("z_cam", C.c_float), ("ray_start", C.c_float),
+                ("ray_end", C.c_float), ("noise_std", C.c_float)]
+
+
+class SirenWeights(C.Structure):
+    _fields_ = [(n, _fp) for n in ("w0", "b0", "w1", "b1", "w_sigma", "b_sigma", "wc", "bc", "wl", "bl",
+                                   "gamma0", "beta0", "gamma1", "beta1", "gammac", "betac")]
+
+
+class RayIO(C.Structure):
+    _fields_ = [(n, _fp) for n in ("cam2world", "ray_idx", "jitter_u", "noise_c", "pdf_u", "noise_f",
+                                   "pixels_fea", "depth", "weights", "dbg_coarse", "dbg_fine", "dbg_all_z")]
+
+
+class CipsParams(C.Structure):
+    _fields_ = [("batch", C.c_int32), ("n_pix", C.c_int32), ("in_dim", C.c_int32), ("hidden", C.c_int32),
+                ("n_blocks", C.c_int32), ("skip_from", C.c_int32), ("rgb_from", C.c_int32),
+                ("impl", C.c_int32)]
+
+
+class CipsWeights(C.Structure):
+    _fields_ = [("w", _fp * CIPS_MAX_LAYERS), ("style1p", _fp * CIPS_MAX_LAYERS),
+                ("demod", _fp * CIPS_MAX_LAYERS), ("rgb_w", _fp * (CIPS_MAX_LAYERS // 2)),
+                ("rgb_b", _fp * (CIPS_MAX_LAYERS // 2))]
+
+
+_lib = None
+
+
+class C3dError(RuntimeError):
+    pass
+
+
+def load():
+    """Load the shared library (once).  Raises if it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise C3dError(f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'`. "
+                       "cips3d_b200 has no CPU or PyTorch fallback.")
+    lib = C.CDLL(LIB_PATH)
+    lib.c3d_version.restype = C.c_int
+    lib.c3d_last_error.restype = C.c_char_p
+    lib.c3d_device_supported.argtypes = [C.c_int]
+    lib.c3d_launch_count.restype = C.c_ulonglong
+    lib.c3d_ray_siren_workspace_bytes.restype = C.c_size_t
+    lib.c3d_ray_siren_workspace_bytes.argtypes = [C.POINTER(RayParams)]
+    lib.c3d_ray_siren_fwd.argtypes = [C.POINTER(RayParams), C.POINTER(SirenWeights), C.POINTER(RayIO),
+                                      _fp, C.c_size_t, _fp]
+    lib.c3d_cips_workspace_bytes.restype = C.c_size_t
+    lib.c3d_cips_workspace_bytes.argtypes = [C.POINTER(CipsParams)]
+    lib.c3d_cips_fwd.argtypes = [C.POINTER(CipsParams), C.POINTER(CipsWeights), _fp, _fp, _fp, _fp,
+                                 C.c_size_t, _fp]
+    lib.c3d_bias_act.argtypes = [_fp, _fp, _fp, _fp, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
+                                 C.c_float, C.c_float, _fp]
+    lib.c3d_upfirdn2d.argtypes = [_fp, _fp, _fp] + [C.c_int32] * 13 + [_fp]
+    lib.c3d_selftest_umma.argtypes = [_fp, _fp, _fp, C.c_int32, C.c_int32, C.c_int32, _fp]
+    _lib = lib
+    return lib
+
+
+def check(code, what):
+    if code != 0:
+        raise C3dError(f"{what} failed ({code}): {load().c3d_last_error().decode()}")
+
+
+def ptr(t):
+    """Device pointer of a CUDA fp32/int32 contiguous tensor (or None)."""
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise C3dError("cips3d_b200 ops need CUDA tensors (there is no CPU path)")
+    if not t.is_contiguous():
+        raise C3dError("cips3d_b200 ops need contiguous tensors")
+    return t.data_ptr()
+
+
+def stream_ptr():
+    import torch
+    return torch.cuda.current_stream().cuda_stream
+
+
+def default_impl():
+    v = os.environ.get("C3D_IMPL", "tc").lower()
+    return IMPL_SIMT if v == "simt" else IMPL_TC

@@ -1,0 +1,95 @@
+"""Camera sampling and look-at matrices: host-side mirror of exp/comm/comm_utils.py:441-581,
+617-641 (O(B) work on tiny tensors).  torch RNG calls keep the reference's shapes and order
+(theta/yaw first, then phi/pitch) so poses match draw for draw."""
+import math
+import random
+
+import torch
+
+
+def normalize_vecs(v):
+    return v / v.norm(dim=-1, keepdim=True)
+
+
+def _truncated_unit_normal(bs, device):
+    """First of 4 N(0,1) candidates inside (-2,2) per element (comm_utils.py:441-448)."""
+    cand = torch.empty((bs, 1, 4), device=device).normal_()
+    first_ok = ((cand < 2) & (cand > -2)).max(-1, keepdim=True)[1]
+    return cand.gather(-1, first_ok).squeeze(-1)
+
+
+def sample_camera_positions(device, bs=1, r=1, horizontal_stddev=1, vertical_stddev=1,
+                            horizontal_mean=math.pi * 0.5, vertical_mean=math.pi * 0.5, mode='normal'):
+    """-> points on the radius-r sphere (bs,3), pitch phi (bs,1) in [0,pi], yaw theta (bs,1).
+    Modes: uniform | normal | gaussian | hybrid | truncated_gaussian | spherical_uniform | mean."""
+    hs, vs, hm, vm = horizontal_stddev, vertical_stddev, horizontal_mean, vertical_mean
+    unif = lambda: torch.rand((bs, 1), device=device) - 0.5
+    gauss = lambda: torch.randn((bs, 1), device=device)
+    if mode == 'hybrid':                                   # coin flip between wide-uniform and gaussian
+        if random.random() < 0.5:
+            theta = unif() * 2 * hs * 2 + hm
+            phi = unif() * 2 * vs * 2 + vm
+        else:
+            theta = gauss() * hs + hm
+            phi = gauss() * vs + vm
+    elif mode == 'uniform':
+        theta = unif() * 2 * hs + hm
+        phi = unif() * 2 * vs + vm
+    elif mode in ('normal', 'gaussian'):
+        theta = gauss() * hs + hm
+        phi = gauss() * vs + vm
+    elif mode == 'truncated_gaussian':
+        theta = _truncated_unit_normal(bs, device) * hs + hm
+        phi = _truncated_unit_normal(bs, device) * vs + vm
+    elif mode == 'spherical_uniform':
+        theta = unif() * 2 * hs + hm
+        v = (unif() * 2 * (vs / math.pi) + vm / math.pi).clamp(1e-5, 1 - 1e-5)
+        phi = torch.arccos(1 - 2 * v)
+    elif mode == 'mean':
+        theta = torch.full((bs, 1), float(hm), device=device)
+        phi = torch.full((bs, 1), float(vm), device=device)
+    else:
+        assert 0
+    phi = phi.clamp(1e-5, math.pi - 1e-5)
+    sin_phi = torch.sin(phi)
+    pts = torch.zeros((bs, 3), device=device)
+    pts[:, 0:1] = r * sin_phi * torch.cos(theta)
+    pts[:, 2:3] = r * sin_phi * torch.sin(theta)
+    pts[:, 1:2] = r * torch.cos(phi)
+    return pts, phi, theta
+
+
+def create_cam2world_matrix(forward_vector, origin, device=None, up_vector=None):
+    """Look-at: columns (-left, up, -forward), then translate to origin (comm_utils.py:538-581)."""
+    fwd = normalize_vecs(forward_vector)
+    n = fwd.shape[0]
+    if up_vector is None:
+        up_vector = torch.tensor([0, 1, 0], dtype=torch.float, device=device).expand_as(fwd)
+    left = normalize_vecs(torch.cross(up_vector, fwd, dim=-1))
+    up = normalize_vecs(torch.cross(fwd, left, dim=-1))
+    rot = torch.eye(4, device=device).unsqueeze(0).repeat(n, 1, 1)
+    rot[:, :3, :3] = torch.stack((-left, up, -fwd), dim=-1)
+    trans = torch.eye(4, device=device).unsqueeze(0).repeat(n, 1, 1)
+    trans[:, :3, 3] = origin
+    return trans @ rot
+
+
+def sample_cam2world(bs, device, h_stddev, v_stddev, h_mean, v_mean, mode, camera_pos=None,
+                     camera_lookup=None, up_vector=None):
+    """Camera part of transform_sampled_points (comm_utils.py:617-641): -> (bs,4,4), pitch, yaw."""
+    if camera_pos is None or camera_lookup is None:
+        origin, pitch, yaw = sample_camera_positions(
+            device, bs=bs, r=1, horizontal_stddev=h_stddev, vertical_stddev=v_stddev,
+            horizontal_mean=h_mean, vertical_mean=v_mean, mode=mode)
+        look = -origin
+    else:
+        origin, look = camera_pos, camera_lookup
+        pitch = yaw = torch.zeros(bs, 1, device=device)
+    return create_cam2world_matrix(look, origin, device=device, up_vector=up_vector), pitch, yaw
+
+
+def scatter_points(idx_grad, points_grad, idx_no_grad, points_no_grad, num_points):
+    """Inverse of the grad / no-grad pixel split (comm_utils.py:240-258)."""
+    out = points_grad.new_zeros(points_grad.shape[0], num_points, points_grad.shape[-1])
+    out = out.index_copy(1, idx_grad, points_grad)
+    return out.index_copy(1, idx_no_grad, points_no_grad.to(out.dtype))

@@ -1,0 +1,96 @@
+// extern "C" entry points of libcips3d_b200.so (see include/cips3d_b200.h) + error plumbing.
+#include <stdarg.h>
+#include <string.h>
+
+#include "c3d_common.cuh"
+
+#include <atomic>
+static thread_local char g_err[512] = "";
+static std::atomic<unsigned long long> g_launches{0};
+void c3d_count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+extern "C" unsigned long long c3d_launch_count(void) { return g_launches.load(); }
+
+void c3d_set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+// implemented in simt_pipeline.cu / ray_siren_tc.cu / cips_tc.cu
+size_t c3d_ray_siren_simt_workspace_bytes(const C3dRayParams* p);
+int c3d_ray_siren_fwd_simt(const C3dRayParams*, const C3dSirenWeights*, const C3dRayIO*, void*, size_t, cudaStream_t);
+size_t c3d_cips_simt_workspace_bytes(const C3dCipsParams* p);
+int c3d_cips_fwd_simt(const C3dCipsParams*, const C3dCipsWeights*, const float*, float*, float*, void*, size_t, cudaStream_t);
+size_t c3d_ray_siren_tc_workspace_bytes(const C3dRayParams* p);
+int c3d_ray_siren_fwd_tc(const C3dRayParams*, const C3dSirenWeights*, const C3dRayIO*, void*, size_t, cudaStream_t);
+size_t c3d_cips_tc_workspace_bytes(const C3dCipsParams* p);
+int c3d_cips_fwd_tc(const C3dCipsParams*, const C3dCipsWeights*, const float*, float*, float*, void*, size_t, cudaStream_t);
+
+extern "C" int c3d_version(void) { return 100; }
+extern "C" const char* c3d_last_error(void) { return g_err; }
+
+extern "C" int c3d_device_supported(int dev) {
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, dev) != cudaSuccess) return 0;
+  return prop.major == 10 ? 1 : 0;
+}
+
+static int check_ray_args(const C3dRayParams* p, const C3dSirenWeights* w, const C3dRayIO* io) {
+  C3D_CHECK_ARG(p && w && io, "ray_siren: null struct pointer");
+  C3D_CHECK_ARG(p->batch >= 0 && p->img_size >= 1 && p->n_rays >= 0, "ray_siren: bad sizes");
+  C3D_CHECK_ARG(p->num_steps >= 3 && p->num_steps <= 32, "ray_siren: num_steps must be in [3,32], got %d", p->num_steps);
+  C3D_CHECK_ARG((long long)p->n_rays <= (long long)p->img_size * p->img_size, "ray_siren: n_rays > img_size^2");
+  C3D_CHECK_ARG(io->ray_idx || (long long)p->ray_offset + p->n_rays <= (long long)p->img_size * p->img_size,
+                "ray_siren: ray_offset + n_rays exceeds the image");
+  C3D_CHECK_ARG(p->clamp_mode == 0 || p->clamp_mode == 1, "ray_siren: clamp_mode must be 0 (relu) or 1 (softplus)");
+  C3D_CHECK_ARG(io->cam2world && io->jitter_u && io->pixels_fea, "ray_siren: null cam2world/jitter_u/pixels_fea");
+  C3D_CHECK_ARG(!p->hierarchical || io->pdf_u, "ray_siren: hierarchical sampling needs pdf_u");
+  C3D_CHECK_ARG(w->w0 && w->b0 && w->w1 && w->b1 && w->w_sigma && w->b_sigma && w->wc && w->bc && w->wl && w->bl,
+                "ray_siren: null weight pointer");
+  C3D_CHECK_ARG(w->gamma0 && w->beta0 && w->gamma1 && w->beta1 && w->gammac && w->betac, "ray_siren: null FiLM pointer");
+  return C3D_OK;
+}
+
+extern "C" size_t c3d_ray_siren_workspace_bytes(const C3dRayParams* p) {
+  if (!p) return 0;
+  return p->impl == C3D_IMPL_SIMT ? c3d_ray_siren_simt_workspace_bytes(p) : c3d_ray_siren_tc_workspace_bytes(p);
+}
+
+extern "C" int c3d_ray_siren_fwd(const C3dRayParams* p, const C3dSirenWeights* w, const C3dRayIO* io,
+                                 void* workspace, size_t workspace_bytes, void* stream) {
+  if (int e = check_ray_args(p, w, io)) return e;
+  if (p->batch == 0 || p->n_rays == 0) return C3D_OK;
+  C3D_CHECK_ARG(workspace || c3d_ray_siren_workspace_bytes(p) == 0, "ray_siren: null workspace");
+  if (p->impl == C3D_IMPL_SIMT) return c3d_ray_siren_fwd_simt(p, w, io, workspace, workspace_bytes, (cudaStream_t)stream);
+  if (p->impl == C3D_IMPL_TC) return c3d_ray_siren_fwd_tc(p, w, io, workspace, workspace_bytes, (cudaStream_t)stream);
+  c3d_set_error("ray_siren: unknown impl %d", p->impl);
+  return C3D_EINVAL;
+}
+
+static int check_cips_args(const C3dCipsParams* p, const C3dCipsWeights* w, const float* x, float* rgb) {
+  C3D_CHECK_ARG(p && w && x && rgb, "cips: null pointer");
+  C3D_CHECK_ARG(p->n_blocks >= 1 && 2 * p->n_blocks <= C3D_CIPS_MAX_LAYERS, "cips: n_blocks must be in [1,9]");
+  C3D_CHECK_ARG(p->in_dim >= 1 && p->hidden >= 1 && p->batch >= 0 && p->n_pix >= 0, "cips: bad sizes");
+  for (int l = 0; l < 2 * p->n_blocks; ++l)
+    C3D_CHECK_ARG(w->w[l] && w->style1p[l] && w->demod[l], "cips: null weight/style/demod for layer %d", l);
+  for (int b = p->rgb_from; b < p->n_blocks; ++b)
+    C3D_CHECK_ARG(b < 0 || (w->rgb_w[b] && w->rgb_b[b]), "cips: null ToRGB weights for block %d", b);
+  return C3D_OK;
+}
+
+extern "C" size_t c3d_cips_workspace_bytes(const C3dCipsParams* p) {
+  if (!p) return 0;
+  return p->impl == C3D_IMPL_SIMT ? c3d_cips_simt_workspace_bytes(p) : c3d_cips_tc_workspace_bytes(p);
+}
+
+extern "C" int c3d_cips_fwd(const C3dCipsParams* p, const C3dCipsWeights* w, const float* x, float* rgb,
+                            float* hidden_out, void* workspace, size_t workspace_bytes, void* stream) {
+  if (int e = check_cips_args(p, w, x, rgb)) return e;
+  if (p->batch == 0 || p->n_pix == 0) return C3D_OK;
+  C3D_CHECK_ARG(workspace || c3d_cips_workspace_bytes(p) == 0, "cips: null workspace");
+  if (p->impl == C3D_IMPL_SIMT) return c3d_cips_fwd_simt(p, w, x, rgb, hidden_out, workspace, workspace_bytes, (cudaStream_t)stream);
+  if (p->impl == C3D_IMPL_TC) return c3d_cips_fwd_tc(p, w, x, rgb, hidden_out, workspace, workspace_bytes, (cudaStream_t)stream);
+  c3d_set_error("cips: unknown impl %d", p->impl);
+  return C3D_EINVAL;
+}

@@ -1,0 +1,145 @@
+// Discriminator element-wise / stencil ops (HBM-bound): fused bias + leaky-ReLU and upfirdn2d.
+// Semantics follow exp/comm/op/fused_bias_act_kernel.cu:19-50 and
+// exp/comm/op/upfirdn2d_kernel.cu:17-50 (generic form) of the reference; the implementation
+// is new: 128-bit vectorised streaming for bias_act, a shared-memory tile for the FIR.
+#include "c3d_common.cuh"
+
+namespace c3d {
+
+__device__ __forceinline__ float bias_act_one(float x, float ref, int act, int grad, float alpha) {
+  // switch (act*10+grad) of fused_bias_act_kernel.cu:34-46
+  if (act == 3) {
+    if (grad == 0) return x > 0.f ? x : x * alpha;
+    if (grad == 1) return ref > 0.f ? x : x * alpha;
+    return 0.f;
+  }
+  return grad == 2 ? 0.f : x;  // act == 1 (linear)
+}
+
+// VEC = 4: size_x % 4 == 0, step_b % 4 == 0 (a float4 never straddles a bias boundary), 16B-aligned
+template <int VEC>
+__global__ void __launch_bounds__(256) bias_act_kernel(const float* __restrict__ x,
+                                                       const float* __restrict__ bias,
+                                                       const float* __restrict__ ref,
+                                                       float* __restrict__ y, long long n_vec,
+                                                       int step_b, int size_b, int act, int grad,
+                                                       float alpha, float scale) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (; i < n_vec; i += stride) {
+    if (VEC == 4) {
+      float4 v = __ldcs(reinterpret_cast<const float4*>(x) + i);
+      float4 r = ref ? __ldcs(reinterpret_cast<const float4*>(ref) + i) : make_float4(0, 0, 0, 0);
+      float b = bias ? __ldg(bias + ((i * 4) / step_b) % size_b) : 0.f;
+      float4 o;
+      o.x = bias_act_one(v.x + b, r.x, act, grad, alpha) * scale;
+      o.y = bias_act_one(v.y + b, r.y, act, grad, alpha) * scale;
+      o.z = bias_act_one(v.z + b, r.z, act, grad, alpha) * scale;
+      o.w = bias_act_one(v.w + b, r.w, act, grad, alpha) * scale;
+      __stcs(reinterpret_cast<float4*>(y) + i, o);
+    } else {
+      float b = bias ? __ldg(bias + (i / step_b) % size_b) : 0.f;
+      float r = ref ? ref[i] : 0.f;
+      y[i] = bias_act_one(x[i] + b, r, act, grad, alpha) * scale;
+    }
+  }
+}
+
+// upfirdn2d: one CTA per (plane, 32x32 output tile); the input footprint of the tile is staged
+// in shared memory once and every tap is read from there.
+constexpr int kTileW = 32, kTileH = 32, kMaxK = 8;
+__global__ void __launch_bounds__(256) upfirdn2d_kernel(
+    const float* __restrict__ x, const float* __restrict__ kernel, float* __restrict__ y, int in_h,
+    int in_w, int out_h, int out_w, int kh, int kw, int up_x, int up_y, int down_x, int down_y,
+    int pad_x0, int pad_y0, int tiles_x) {
+  extern __shared__ float sm[];
+  __shared__ float sk[kMaxK * kMaxK];
+  const int plane = blockIdx.y;
+  const int tx0 = (blockIdx.x % tiles_x) * kTileW, ty0 = (blockIdx.x / tiles_x) * kTileH;
+  if (threadIdx.x < kh * kw) {
+    int ky = threadIdx.x / kw, kx = threadIdx.x % kw;
+    sk[threadIdx.x] = kernel[(kh - 1 - ky) * kw + (kw - 1 - kx)];  // flipped kernel
+  }
+  // footprint in the (virtual) upsampled+padded image: rows ty0*down_y .. +(kTileH-1)*down_y+kh-1
+  const int fw = (kTileW - 1) * down_x + kw, fh = (kTileH - 1) * down_y + kh;
+  const float* xp = x + (size_t)plane * in_h * in_w;
+  for (int i = threadIdx.x; i < fw * fh; i += blockDim.x) {
+    int fy = i / fw, fx = i % fw;
+    int uy = ty0 * down_y + fy - pad_y0, ux = tx0 * down_x + fx - pad_x0;  // upsampled coords
+    float v = 0.f;
+    if (uy >= 0 && ux >= 0 && uy % up_y == 0 && ux % up_x == 0) {
+      int iy = uy / up_y, ix = ux / up_x;
+      if (iy < in_h && ix < in_w) v = __ldg(xp + (size_t)iy * in_w + ix);
+    }
+    sm[i] = v;
+  }
+  __syncthreads();
+  for (int o = threadIdx.x; o < kTileW * kTileH; o += blockDim.x) {
+    int oy = o / kTileW, ox = o % kTileW;
+    int gy = ty0 + oy, gx = tx0 + ox;
+    if (gy >= out_h || gx >= out_w) continue;
+    float acc = 0.f;
+    for (int ky = 0; ky < kh; ++ky)
+      for (int kx = 0; kx < kw; ++kx)
+        acc = fmaf(sm[(oy * down_y + ky) * fw + ox * down_x + kx], sk[ky * kw + kx], acc);
+    y[((size_t)plane * out_h + gy) * out_w + gx] = acc;
+  }
+}
+
+}  // namespace c3d
+
+using namespace c3d;
+
+extern "C" int c3d_bias_act(const float* x, const float* bias, const float* ref, float* y,
+                            int64_t size_x, int32_t step_b, int32_t size_b, int32_t act,
+                            int32_t grad, float alpha, float scale, void* stream) {
+  C3D_CHECK_ARG(x && y, "bias_act: null x/y");
+  C3D_CHECK_ARG(act == 1 || act == 3, "bias_act: act must be 1 (linear) or 3 (lrelu), got %d", act);
+  C3D_CHECK_ARG(grad >= 0 && grad <= 2, "bias_act: grad must be 0..2");
+  C3D_CHECK_ARG(!bias || (step_b > 0 && size_b > 0), "bias_act: bad bias geometry");
+  C3D_CHECK_ARG(grad != 1 || ref, "bias_act: grad=1 needs ref");
+  if (size_x == 0) return C3D_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  bool vec = size_x % 4 == 0 && (!bias || step_b % 4 == 0) && ((uintptr_t)x % 16 == 0) &&
+             ((uintptr_t)y % 16 == 0) && (!ref || (uintptr_t)ref % 16 == 0);
+  const int sms = 148;
+  if (vec) {
+    long long nv = size_x / 4;
+    int grid = (int)(nv / 256 + 1 < (long long)sms * 16 ? nv / 256 + 1 : (long long)sms * 16);
+    bias_act_kernel<4><<<grid, 256, 0, st>>>(x, bias, ref, y, nv, step_b, size_b, act, grad, alpha, scale);
+  } else {
+    int grid = (int)(size_x / 256 + 1 < (long long)sms * 16 ? size_x / 256 + 1 : (long long)sms * 16);
+    bias_act_kernel<1><<<grid, 256, 0, st>>>(x, bias, ref, y, size_x, step_b, size_b, act, grad, alpha, scale);
+  }
+  C3D_LAUNCH_CHECK();
+  return C3D_OK;
+}
+
+extern "C" int c3d_upfirdn2d(const float* x, const float* kernel, float* y, int32_t planes,
+                             int32_t in_h, int32_t in_w, int32_t kh, int32_t kw, int32_t up_x,
+                             int32_t up_y, int32_t down_x, int32_t down_y, int32_t pad_x0,
+                             int32_t pad_x1, int32_t pad_y0, int32_t pad_y1, void* stream) {
+  C3D_CHECK_ARG(x && kernel && y, "upfirdn2d: null pointer");
+  C3D_CHECK_ARG(kh >= 1 && kw >= 1 && kh <= kMaxK && kw <= kMaxK, "upfirdn2d: kernel up to 8x8");
+  C3D_CHECK_ARG(up_x >= 1 && up_y >= 1 && down_x >= 1 && down_y >= 1 && down_x <= 4 && down_y <= 4,
+                "upfirdn2d: bad up/down factors");
+  int out_h = (in_h * up_y + pad_y0 + pad_y1 - kh) / down_y + 1;
+  int out_w = (in_w * up_x + pad_x0 + pad_x1 - kw) / down_x + 1;
+  C3D_CHECK_ARG(out_h > 0 && out_w > 0, "upfirdn2d: empty output");
+  if (planes == 0) return C3D_OK;
+  int tiles_x = c3d_div_up(out_w, kTileW), tiles_y = c3d_div_up(out_h, kTileH);
+  int fw = (kTileW - 1) * down_x + kw, fh = (kTileH - 1) * down_y + kh;
+  size_t smem = (size_t)fw * fh * sizeof(float);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (smem > 48 * 1024)
+    C3D_CUDA(cudaFuncSetAttribute(upfirdn2d_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  for (int p0 = 0; p0 < planes; p0 += 65535) {  // gridDim.y limit
+    int np = planes - p0 < 65535 ? planes - p0 : 65535;
+    dim3 grid(tiles_x * tiles_y, np);
+    upfirdn2d_kernel<<<grid, 256, smem, st>>>(x + (size_t)p0 * in_h * in_w, kernel,
+                                              y + (size_t)p0 * out_h * out_w, in_h, in_w, out_h, out_w,
+                                              kh, kw, up_x, up_y, down_x, down_y, pad_x0, pad_y0, tiles_x);
+    C3D_LAUNCH_CHECK();
+  }
+  return C3D_OK;
+}

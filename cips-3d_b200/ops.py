@@ -1,0 +1,287 @@
+"""Tensor-level entry points over the C-ABI.  Everything here launches hand-written CUDA
+kernels from libcips3d_b200.so on the current torch stream; torch only provides device
+memory.  No CPU path, no PyTorch fallback for the forward ops."""
+import ctypes as C
+import math
+
+import numpy as np
+import torch
+from torch.autograd import Function
+
+from . import _lib
+from ._lib import CipsParams, CipsWeights, RayIO, RayParams, SirenWeights, check, load, ptr, stream_ptr
+
+CLAMP_MODES = {"relu": 0, "softplus": 1}
+# bench.py sets this to a dict to collect CUDA-event pairs around the two hot entry points
+PROFILE = None
+
+
+def _prof_begin(key):
+    if PROFILE is None:
+        return None
+    e = torch.cuda.Event(enable_timing=True)
+    e.record()
+    return e
+
+
+def _prof_end(key, e0):
+    if e0 is not None:
+        e1 = torch.cuda.Event(enable_timing=True)
+        e1.record()
+        PROFILE.setdefault(key, []).append((e0, e1))
+
+
+def _f32c(t, name):
+    if t is None:
+        return None
+    if t.dtype != torch.float32:
+        raise _lib.C3dError(f"{name}: expected float32, got {t.dtype}")
+    return t.contiguous()
+
+
+def z_cam_from_fov(fov):
+    """-1 / tan(fov*pi/360) evaluated like exp/comm/comm_utils.py:396 (fp32 division)."""
+    return float(np.float32(-1.0) / np.float32(np.tan((2 * math.pi * fov / 360) / 2)))
+
+
+# --------------------------------------------------------------------------------------
+# volumetric renderer
+# --------------------------------------------------------------------------------------
+def render_features(siren, film, cam2world, jitter_u, pdf_u=None, noise_c=None, noise_f=None, *,
+                    img_size, fov, ray_start, ray_end, num_steps, hierarchical_sample=True,
+                    clamp_mode="relu", noise_std=0.0, white_back=False, last_back=False,
+                    ray_idx=None, ray_offset=0, n_rays=None, impl=None, debug=False,
+                    want_depth=False, want_weights=False):
+    """Fused rays -> FiLM-SIREN -> resample -> composite (c3d_ray_siren_fwd).
+
+    siren: dict of the NeRFNetwork parameters {w0,b0,w1,b1,w_sigma,b_sigma,wc,bc,wl,bl}
+    film:  dict {gamma0,beta0,gamma1,beta1,gammac,betac}, each (B,C)
+    cam2world (B,4,4); jitter_u (B,R*R,S); pdf_u (B*N,S); noise_c (B,N,S); noise_f (B,N,nS)
+    Returns dict(pixels_fea (B,N,32)[, depth, weights, coarse, fine, all_z])."""
+    lib = load()
+    if clamp_mode not in CLAMP_MODES:
+        raise AssertionError("Need to choose clamp mode")       # pigan_utils.py:252-253
+    B = cam2world.shape[0]
+    S = int(num_steps)
+    HW = img_size * img_size
+    if ray_idx is not None:
+        ray_idx = ray_idx.to(torch.int32).contiguous()
+        N = ray_idx.numel()
+    else:
+        N = HW - ray_offset if n_rays is None else int(n_rays)
+    nS = 2 * S if hierarchical_sample else S
+    dev = cam2world.device
+    p = RayParams(batch=B, img_size=img_size, num_steps=S, n_rays=N, ray_offset=int(ray_offset),
+                  hierarchical=int(bool(hierarchical_sample)), clamp_mode=CLAMP_MODES[clamp_mode],
+                  white_back=int(bool(white_back)), last_back=int(bool(last_back)),
+                  impl=_lib.default_impl() if impl is None else impl,
+                  z_cam=z_cam_from_fov(fov), ray_start=float(ray_start), ray_end=float(ray_end),
+                  noise_std=float(noise_std))
+    keep = []  # keep contiguous copies alive until launch
+
+    def dp(t, name, shape=None):
+        t = _f32c(t, name)
+        if t is not None:
+            if shape is not None and tuple(t.shape) != tuple(shape):
+                raise _lib.C3dError(f"{name}: expected shape {tuple(shape)}, got {tuple(t.shape)}")
+            keep.append(t)
+        return ptr(t)
+
+    w = SirenWeights(
+        w0=dp(siren["w0"], "w0", (128, 3)), b0=dp(siren["b0"], "b0", (128,)),
+        w1=dp(siren["w1"], "w1", (128, 128)), b1=dp(siren["b1"], "b1", (128,)),
+        w_sigma=dp(siren["w_sigma"], "w_sigma", (1, 128)), b_sigma=dp(siren["b_sigma"], "b_sigma", (1,)),
+        wc=dp(siren["wc"], "wc", (64, 128)), bc=dp(siren["bc"], "bc", (64,)),
+        wl=dp(siren["wl"], "wl", (32, 64)), bl=dp(siren["bl"], "bl", (32,)),
+        gamma0=dp(film["gamma0"], "gamma0", (B, 128)), beta0=dp(film["beta0"], "beta0", (B, 128)),
+        gamma1=dp(film["gamma1"], "gamma1", (B, 128)), beta1=dp(film["beta1"], "beta1", (B, 128)),
+        gammac=dp(film["gammac"], "gammac", (B, 64)), betac=dp(film["betac"], "betac", (B, 64)))
+    out = {"pixels_fea": torch.empty((B, N, 32), device=dev, dtype=torch.float32)}
+    if want_depth or debug:
+        out["depth"] = torch.empty((B, N), device=dev, dtype=torch.float32)
+    if want_weights or debug:
+        out["weights"] = torch.empty((B, N, nS), device=dev, dtype=torch.float32)
+    if debug:
+        out["coarse"] = torch.empty((B, N, S, 33), device=dev, dtype=torch.float32)
+        out["all_z"] = torch.empty((B, N, nS), device=dev, dtype=torch.float32)
+        if hierarchical_sample:
+            out["fine"] = torch.empty((B, N, S, 33), device=dev, dtype=torch.float32)
+    if ray_idx is not None:
+        keep.append(ray_idx)
+    io = RayIO(
+        cam2world=dp(cam2world, "cam2world", (B, 4, 4)),
+        ray_idx=ptr(ray_idx) if ray_idx is not None else None,
+        jitter_u=dp(jitter_u, "jitter_u", (B, HW, S)),
+        noise_c=dp(noise_c, "noise_c", (B, N, S)) if (noise_c is not None and noise_std != 0) else None,
+        pdf_u=dp(pdf_u, "pdf_u", (B * N, S)) if hierarchical_sample else None,
+        noise_f=dp(noise_f, "noise_f", (B, N, nS)) if (noise_f is not None and noise_std != 0) else None,
+        pixels_fea=ptr(out["pixels_fea"]), depth=ptr(out.get("depth")), weights=ptr(out.get("weights")),
+        dbg_coarse=ptr(out.get("coarse")), dbg_fine=ptr(out.get("fine")), dbg_all_z=ptr(out.get("all_z")))
+    wsb = lib.c3d_ray_siren_workspace_bytes(C.byref(p))
+    ws = torch.empty((max(wsb, 4) + 3) // 4, device=dev, dtype=torch.float32)
+    ev = _prof_begin("ray")
+    check(lib.c3d_ray_siren_fwd(C.byref(p), C.byref(w), C.byref(io), ptr(ws), wsb, stream_ptr()),
+          "c3d_ray_siren_fwd")
+    _prof_end("ray", ev)
+    return out
+
+
+# --------------------------------------------------------------------------------------
+# per-pixel CIPS MLP
+# --------------------------------------------------------------------------------------
+def cips_forward(x, weights, style1p, demod, rgb_w, rgb_b, *, n_blocks=9, skip_from=4, rgb_from=3,
+                 impl=None, return_hidden=False):
+    """x (B,N,in) -> tanh(rgb) (B,N,3).  weights[l] (in_l,out), style1p[l] (B,in_l),
+    demod[l] (B,out), rgb_w[b] (3,hidden) / rgb_b[b] (3,) (None for blocks < rgb_from)."""
+    lib = load()
+    x = _f32c(x, "x")
+    B, N, in_dim = x.shape
+    hidden = weights[0].shape[1]
+    p = CipsParams(batch=B, n_pix=N, in_dim=in_dim, hidden=hidden, n_blocks=n_blocks, skip_from=skip_from,
+                   rgb_from=rgb_from, impl=_lib.default_impl() if impl is None else impl)
+    keep = []
+    cw = CipsWeights()
+    for l in range(2 * n_blocks):
+        for arr, src, nm in ((cw.w, weights, "w"), (cw.style1p, style1p, "style1p"), (cw.demod, demod, "demod")):
+            t = _f32c(src[l], f"{nm}[{l}]")
+            keep.append(t)
+            arr[l] = ptr(t)
+    for b in range(n_blocks):
+        if b >= rgb_from:
+            tw, tb = _f32c(rgb_w[b], "rgb_w"), _f32c(rgb_b[b], "rgb_b")
+            keep += [tw, tb]
+            cw.rgb_w[b], cw.rgb_b[b] = ptr(tw), ptr(tb)
+    rgb = torch.empty((B, N, 3), device=x.device, dtype=torch.float32)
+    hid = torch.empty((B, N, hidden), device=x.device, dtype=torch.float32) if return_hidden else None
+    wsb = lib.c3d_cips_workspace_bytes(C.byref(p))
+    ws = torch.empty((max(wsb, 4) + 3) // 4, device=x.device, dtype=torch.float32)
+    ev = _prof_begin("cips")
+    check(lib.c3d_cips_fwd(C.byref(p), C.byref(cw), ptr(x), ptr(rgb), ptr(hid), ptr(ws), wsb, stream_ptr()),
+          "c3d_cips_fwd")
+    _prof_end("cips", ev)
+    return (rgb, hid) if return_hidden else rgb
+
+
+# --------------------------------------------------------------------------------------
+# discriminator ops (same call surface as exp/comm/op/{fused_act,upfirdn2d}.py)
+# --------------------------------------------------------------------------------------
+def bias_act(x, bias=None, ref=None, act=3, grad=0, alpha=0.2, scale=2 ** 0.5):
+    """fused.fused_bias_act(input, bias, refer, act, grad, alpha, scale) -- fused_bias_act.cpp:11-20."""
+    lib = load()
+    x = _f32c(x, "x")
+    y = torch.empty_like(x)
+    b = _f32c(bias, "bias") if bias is not None and bias.numel() else None
+    r = _f32c(ref, "ref") if ref is not None and ref.numel() else None
+    step_b = 1
+    for i in range(2, x.dim()):
+        step_b *= x.size(i)                                     # fused_bias_act_kernel.cu:67-69
+    check(lib.c3d_bias_act(ptr(x), ptr(b), ptr(r), ptr(y), x.numel(), step_b,
+                           b.numel() if b is not None else 1, act, grad, alpha, scale, stream_ptr()),
+          "c3d_bias_act")
+    return y
+
+
+class _FusedLeakyReLUBackward(Function):            # fused_act.py:19-49
+    @staticmethod
+    def forward(ctx, grad_output, out, negative_slope, scale):
+        ctx.save_for_backward(out)
+        ctx.negative_slope, ctx.scale = negative_slope, scale
+        grad_input = bias_act(grad_output, None, out, 3, 1, negative_slope, scale)
+        dim = [0] + list(range(2, grad_input.ndim))
+        return grad_input, grad_input.sum(dim).detach()
+
+    @staticmethod
+    def backward(ctx, gradgrad_input, gradgrad_bias):
+        out, = ctx.saved_tensors
+        return bias_act(gradgrad_input.contiguous(), gradgrad_bias, out, 3, 1, ctx.negative_slope,
+                        ctx.scale), None, None, None
+
+
+class _FusedLeakyReLU(Function):                    # fused_act.py:52-70
+    @staticmethod
+    def forward(ctx, input, bias, negative_slope, scale):
+        out = bias_act(input, bias, None, 3, 0, negative_slope, scale)
+        ctx.save_for_backward(out)
+        ctx.negative_slope, ctx.scale = negative_slope, scale
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_output):
+        out, = ctx.saved_tensors
+        gi, gb = _FusedLeakyReLUBackward.apply(grad_output.contiguous(), out, ctx.negative_slope, ctx.scale)
+        return gi, gb, None, None
+
+
+def fused_leaky_relu(input, bias, negative_slope=0.2, scale=2 ** 0.5):
+    return _FusedLeakyReLU.apply(input, bias, negative_slope, scale)
+
+
+def _upfirdn2d_raw(x, kernel, up, down, pad):
+    lib = load()
+    x = _f32c(x, "x")
+    kernel = _f32c(kernel, "kernel")
+    B, Cc, H, W = x.shape
+    kh, kw = kernel.shape
+    out_h = (H * up[1] + pad[2] + pad[3] - kh) // down[1] + 1
+    out_w = (W * up[0] + pad[0] + pad[1] - kw) // down[0] + 1
+    y = torch.empty((B, Cc, out_h, out_w), device=x.device, dtype=torch.float32)
+    check(lib.c3d_upfirdn2d(ptr(x), ptr(kernel), ptr(y), B * Cc, H, W, kh, kw, up[0], up[1], down[0], down[1],
+                            pad[0], pad[1], pad[2], pad[3], stream_ptr()), "c3d_upfirdn2d")
+    return y
+
+
+class _UpFirDn2dBackward(Function):                 # upfirdn2d.py:18-85
+    @staticmethod
+    def forward(ctx, grad_output, kernel, grad_kernel, up, down, pad, g_pad, in_size):
+        grad_input = _upfirdn2d_raw(grad_output, grad_kernel, down, up, g_pad)
+        ctx.save_for_backward(kernel)
+        ctx.up, ctx.down, ctx.pad = up, down, pad
+        assert tuple(grad_input.shape) == tuple(in_size)
+        return grad_input
+
+    @staticmethod
+    def backward(ctx, gradgrad_input):
+        kernel, = ctx.saved_tensors
+        return _upfirdn2d_raw(gradgrad_input.contiguous(), kernel, ctx.up, ctx.down, ctx.pad), \
+            None, None, None, None, None, None, None
+
+
+class _UpFirDn2d(Function):                         # upfirdn2d.py:88-141
+    @staticmethod
+    def forward(ctx, input, kernel, up, down, pad):
+        up_x, up_y = up
+        down_x, down_y = down
+        pad_x0, pad_x1, pad_y0, pad_y1 = pad
+        kh, kw = kernel.shape
+        _, _, in_h, in_w = input.shape
+        out = _upfirdn2d_raw(input, kernel, up, down, pad)
+        out_h, out_w = out.shape[2:]
+        ctx.save_for_backward(kernel, torch.flip(kernel, [0, 1]))
+        ctx.in_size = tuple(input.shape)
+        ctx.up, ctx.down, ctx.pad = up, down, pad
+        ctx.g_pad = (kw - pad_x0 - 1, in_w * up_x - out_w * down_x + pad_x0 - up_x + 1,
+                     kh - pad_y0 - 1, in_h * up_y - out_h * down_y + pad_y0 - up_y + 1)
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_output):
+        kernel, grad_kernel = ctx.saved_tensors
+        gi = _UpFirDn2dBackward.apply(grad_output.contiguous(), kernel, grad_kernel, ctx.up, ctx.down, ctx.pad,
+                                      ctx.g_pad, ctx.in_size)
+        return gi, None, None, None, None
+
+
+def upfirdn2d(input, kernel, up=1, down=1, pad=(0, 0)):
+    """exp/comm/op/upfirdn2d.py:144-149."""
+    return _UpFirDn2d.apply(input, kernel, (up, up), (down, down), (pad[0], pad[1], pad[0], pad[1]))
+
+
+def selftest_umma(a, b, a_in_tmem=False):
+    """D = A @ B^T through one tcgen05 tile (fp16 operands, fp32 accumulate)."""
+    lib = load()
+    a, b = _f32c(a, "a"), _f32c(b, "b")
+    assert a.shape[0] == 128 and a.shape[1] == b.shape[1]
+    d = torch.empty((128, b.shape[0]), device=a.device, dtype=torch.float32)
+    check(lib.c3d_selftest_umma(ptr(a), ptr(b), ptr(d), b.shape[0], a.shape[1], int(a_in_tmem), stream_ptr()),
+          "c3d_selftest_umma")
+    return d

@@ -1,0 +1,173 @@
+/*
+ * cips3d_b200 -- C-ABI of the B200-native CIPS-3D hot path (libcips3d_b200.so).
+ *
+ * The reference has no FFI for this path: its boundary is the Python nn.Module surface
+ * (exp/cips3d/models/generator.py:1158, exp/cips3d/models/discriminator.py:588) plus two
+ * pybind11 ops used by the discriminator.  Every entry point below names the reference
+ * code it replaces.  Conventions (all entry points):
+ *   - plain C: device pointers + sizes, no torch types; the CALLER owns every buffer
+ *     (outputs and workspaces are allocated by the caller, e.g. with torch.empty);
+ *   - all tensors are fp32, contiguous, row-major, in the layouts documented per argument;
+ *   - work is enqueued on `stream` (a cudaStream_t passed as void*), nothing synchronises,
+ *     no hidden allocation, no global state -> safe to call from several host threads;
+ *   - returns 0 on success, a negative C3D_E* code otherwise; c3d_last_error() returns a
+ *     thread-local message for the last failure on the calling thread.
+ */
+#ifndef CIPS3D_B200_H_
+#define CIPS3D_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define C3D_OK 0
+#define C3D_EINVAL (-1)   /* bad argument (null pointer, unsupported size)            */
+#define C3D_ECUDA (-2)    /* a CUDA runtime call / kernel launch failed               */
+#define C3D_EARCH (-3)    /* device is not sm_100 (the tensor-core path needs tcgen05) */
+#define C3D_EWORKSPACE (-4) /* workspace too small                                    */
+
+/* Which kernel generation executes the GEMM-shaped parts.  Both are sm_100a CUDA.
+ *   C3D_IMPL_TC   : fused tcgen05/TMEM kernels (the product path, default)
+ *   C3D_IMPL_SIMT : unfused fp32-FMA kernels; kept as an on-device cross-check only */
+#define C3D_IMPL_TC 0
+#define C3D_IMPL_SIMT 1
+
+int c3d_version(void);
+const char* c3d_last_error(void);
+/* 1 if device `dev` is compute capability 10.x */
+int c3d_device_supported(int dev);
+/* number of kernels this library has launched in this process (monotonic; bench.py's
+ * gpu_launches is the difference across the timed region) */
+unsigned long long c3d_launch_count(void);
+
+/* ------------------------------------------------------------------------------------
+ * Fused volumetric renderer: rays -> FiLM-SIREN -> hierarchical resampling -> composite.
+ * Replaces (reference, paths relative to the checkout):
+ *   exp/comm/comm_utils.py:365-412 get_initial_rays_trig, :416-438 perturb_points,
+ *   :584-679 transform_sampled_points (point/direction transform part),
+ *   exp/cips3d/models/generator.py:260-317 NeRFNetwork.forward_with_frequencies_phase_shifts,
+ *   exp/comm/models/film_layer.py:78-107 FiLMLayer.forward,
+ *   exp/dev/nerf_inr/models/generator_nerf_inr.py:537-598 get_fine_points_and_direction,
+ *   exp/pigan/pigan_utils.py:164-209 sample_pdf, :212-273 fancy_integration,
+ *   exp/cips3d/models/generator.py:1733-1738 (merge/sort of coarse+fine samples).
+ * Random numbers are NOT generated here: the caller draws them with torch in the
+ * reference's order (hard part 4) and passes the tensors.
+ * ---------------------------------------------------------------------------------- */
+typedef struct C3dRayParams {
+  int32_t batch;        /* B images                                                     */
+  int32_t img_size;     /* R: image is R x R, ray index = h*R + w (comm_utils.py:392)   */
+  int32_t num_steps;    /* S coarse samples per ray, 2 <= S <= 32                       */
+  int32_t n_rays;       /* N rays rendered per image (N <= R*R)                         */
+  int32_t ray_offset;   /* when ray_idx == NULL: local ray i is global ray ray_offset+i */
+  int32_t hierarchical; /* 1: S more importance samples, merged and sorted (2S total)   */
+  int32_t clamp_mode;   /* 0 relu, 1 softplus (pigan_utils.py:248-253)                  */
+  int32_t white_back;   /* pigan_utils.py:265-266                                       */
+  int32_t last_back;    /* pigan_utils.py:259-260                                       */
+  int32_t impl;         /* C3D_IMPL_*                                                   */
+  float z_cam;          /* -1/tan(fov*pi/360) (comm_utils.py:396)                       */
+  float ray_start, ray_end;
+  float noise_std;      /* nerf_noise; scales noise_c / noise_f (pigan_utils.py:246)    */
+} C3dRayParams;
+
+typedef struct C3dSirenWeights { /* NeRFNetwork parameters, torch Linear layout (out,in) */
+  const float* w0; const float* b0;         /* network.0.linear            (128,3) (128) */
+  const float* w1; const float* b1;         /* network.1.linear          (128,128) (128) */
+  const float* w_sigma; const float* b_sigma; /* final_layer               (1,128) (1)   */
+  const float* wc; const float* bc;         /* color_layer_sine.linear    (64,128) (64)  */
+  const float* wl; const float* bl;         /* color_layer_linear.0        (32,64) (32)  */
+  /* per-image FiLM parameters, gamma = 15*gain_fc(w)+30, beta = bias_fc(w)
+   * (film_layer.py:59,89-91); computed by the caller (B x style GEMV, not hot).      */
+  const float* gamma0; const float* beta0;  /* (B,128) */
+  const float* gamma1; const float* beta1;  /* (B,128) */
+  const float* gammac; const float* betac;  /* (B,64)  */
+} C3dSirenWeights;
+
+typedef struct C3dRayIO {
+  const float* cam2world;  /* (B,4,4) row-major, create_cam2world_matrix comm_utils.py:538 */
+  const int32_t* ray_idx;  /* (N) global ray indices or NULL (gather_points comm_utils.py:264) */
+  const float* jitter_u;   /* (B,R*R,S) U[0,1), indexed by GLOBAL ray (comm_utils.py:432)  */
+  const float* noise_c;    /* (B,N,S)  N(0,1) or NULL -> 0  (coarse-pass integration)      */
+  const float* pdf_u;      /* (B*N,S)  U[0,1)  (pigan_utils.py:192); NULL iff !hierarchical */
+  const float* noise_f;    /* (B,N,nS) N(0,1) or NULL -> 0, nS = hierarchical ? 2S : S     */
+  float* pixels_fea;       /* out (B,N,32)  integrated feature (rgb_final)                 */
+  float* depth;            /* out (B,N) or NULL                                            */
+  float* weights;          /* out (B,N,nS) or NULL                                         */
+  float* dbg_coarse;       /* out (B,N,S,33) [feature32, sigma] or NULL (parity tests)     */
+  float* dbg_fine;         /* out (B,N,S,33) or NULL                                       */
+  float* dbg_all_z;        /* out (B,N,nS) sorted sample depths or NULL                    */
+} C3dRayIO;
+
+size_t c3d_ray_siren_workspace_bytes(const C3dRayParams* p);
+int c3d_ray_siren_fwd(const C3dRayParams* p, const C3dSirenWeights* w, const C3dRayIO* io,
+                      void* workspace, size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------
+ * Fused per-pixel CIPS synthesis MLP.
+ * Replaces exp/cips3d/models/generator.py:1107-1154 CIPSNet.forward (+ SinBlock :949-974,
+ * ToRGB :983-1006) and exp/comm/models/mod_conv_fc.py:452-496 SinStyleMod.forward_bmm,
+ * using  y = ((x * (s+1)) @ W) * d,  d[b,o] = rsqrt(sum_i (W[i,o](s[b,i]+1))^2 + 1e-8)
+ * so one W per layer serves every image.  s+1 and d are per-image vectors computed by
+ * the caller (B x 512 GEMMs, not hot).
+ * ---------------------------------------------------------------------------------- */
+#define C3D_CIPS_MAX_LAYERS 18
+typedef struct C3dCipsParams {
+  int32_t batch;        /* B                                                    */
+  int32_t n_pix;        /* N pixels per image                                   */
+  int32_t in_dim;       /* 32                                                   */
+  int32_t hidden;       /* 512                                                  */
+  int32_t n_blocks;     /* blocks that run (9; fewer if img_size stops early)   */
+  int32_t skip_from;    /* block idx >= skip_from adds the residual (4)         */
+  int32_t rgb_from;     /* block idx >= rgb_from accumulates ToRGB (3)          */
+  int32_t impl;         /* C3D_IMPL_*                                           */
+} C3dCipsParams;
+
+typedef struct C3dCipsWeights {
+  const float* w[C3D_CIPS_MAX_LAYERS];      /* SinStyleMod.weight[0], (in,out) row-major   */
+  const float* style1p[C3D_CIPS_MAX_LAYERS]; /* (B,in)  modulation(w_inr) + 1               */
+  const float* demod[C3D_CIPS_MAX_LAYERS];  /* (B,out) rsqrt(sum_i (W s1p)^2 + eps)        */
+  const float* rgb_w[C3D_CIPS_MAX_LAYERS / 2]; /* ToRGB.linear.weight (3,hidden) per block  */
+  const float* rgb_b[C3D_CIPS_MAX_LAYERS / 2]; /* ToRGB.linear.bias (3)                     */
+} C3dCipsWeights;
+
+size_t c3d_cips_workspace_bytes(const C3dCipsParams* p);
+/* x (B,N,in_dim) -> rgb (B,N,3) = tanh(sum of ToRGB skips); hidden_out (B,N,hidden) or NULL */
+int c3d_cips_fwd(const C3dCipsParams* p, const C3dCipsWeights* w, const float* x, float* rgb,
+                 float* hidden_out, void* workspace, size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------
+ * Discriminator ops.  Same semantics as the reference's two pybind11 modules:
+ *   fused.fused_bias_act(input, bias, refer, act, grad, alpha, scale)
+ *       exp/comm/op/fused_bias_act.cpp:11-20, fused_bias_act_kernel.cu:19-50
+ *   upfirdn2d.upfirdn2d(input(N,H,W,1), kernel, up_x, up_y, down_x, down_y, pad_x0..pad_y1)
+ *       exp/comm/op/upfirdn2d.cpp:12-22, upfirdn2d_kernel.cu:52-139
+ * ---------------------------------------------------------------------------------- */
+/* y[i] = f(x[i] + b[(i / step_b) % size_b]) * scale;  act: 1 linear, 3 leaky-relu;
+ * grad: 0 forward, 1 first derivative gated on ref (= saved output), 2 -> 0.
+ * bias / ref may be NULL. */
+int c3d_bias_act(const float* x, const float* bias, const float* ref, float* y, int64_t size_x,
+                 int32_t step_b, int32_t size_b, int32_t act, int32_t grad, float alpha,
+                 float scale, void* stream);
+
+/* x: (planes,in_h,in_w) -> y: (planes,out_h,out_w),
+ * out = (in*up + pad0 + pad1 - k) / down + 1; zero-upsample, pad (negative = crop),
+ * correlate with the flipped kernel (kh,kw), decimate. */
+int c3d_upfirdn2d(const float* x, const float* kernel, float* y, int32_t planes, int32_t in_h,
+                  int32_t in_w, int32_t kh, int32_t kw, int32_t up_x, int32_t up_y,
+                  int32_t down_x, int32_t down_y, int32_t pad_x0, int32_t pad_x1, int32_t pad_y0,
+                  int32_t pad_y1, void* stream);
+
+/* ------------------------------------------------------------------------------------
+ * Self-test of the tcgen05 building block (UMMA descriptors, TMEM round trip):
+ * D[128,N] = A[128,K] * B[N,K]^T with fp16 operands / fp32 accumulate, A and B given as
+ * fp32 row-major (K contiguous) and converted on device.  Used by tests/test_umma_gpu.py.
+ * ---------------------------------------------------------------------------------- */
+int c3d_selftest_umma(const float* a, const float* b, float* d, int32_t n, int32_t k,
+                      int32_t a_in_tmem, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CIPS3D_B200_H_ */

@@ -40,3 +40,54 @@ def rel_err(a, b):
     a, b = a.double(), b.double()
     return ((a - b).abs().max() / b.abs().max().clamp_min(1e-30)).item(), \
            ((a - b).norm() / b.norm().clamp_min(1e-30)).item()
+
+
+# ------------------------------------------------------------------ GPU-side helpers
+import contextlib
+
+
+def draws_sequence(draws, hierarchical=True):
+    """The draw tensors in the order GeneratorNerfINR.forward consumes them."""
+    seq = [draws["jitter_u"][..., None], draws["yaw_n"], draws["pitch_n"]]
+    if hierarchical:
+        seq += [draws["noise_c"][..., None], draws["pdf_u"]]
+    seq.append(draws["noise_f"][..., None])
+    return seq
+
+
+@contextlib.contextmanager
+def replay_draws(seq, device):
+    """Make torch.rand / torch.randn return the given tensors in order (so a module forward
+    consumes exactly the draws the reference consumed)."""
+    it = iter(seq)
+    o_rand, o_randn = torch.rand, torch.randn
+
+    def nxt(*a, **k):
+        t = next(it)
+        shape = a[0] if len(a) == 1 and isinstance(a[0], (tuple, list, torch.Size)) else a
+        assert tuple(t.shape) == tuple(shape), (tuple(t.shape), tuple(shape))
+        return t.to(device=device, dtype=torch.float32)
+
+    torch.rand = torch.randn = nxt
+    try:
+        yield
+    finally:
+        torch.rand, torch.randn = o_rand, o_randn
+
+
+def close_frac(a, b, tol):
+    """fraction of rows (last dim reduced by max) whose abs error is within tol * max|b|"""
+    a, b = a.double().cpu(), b.double().cpu()
+    scale = b.abs().max().clamp_min(1e-30)
+    err = (a - b).abs().reshape(-1, a.shape[-1]).amax(-1) / scale
+    return (err <= tol).double().mean().item(), err.max().item()
+
+
+def build_generator(device, sd=None, frozen=False):
+    import cips3d_b200
+    cls = cips3d_b200.GeneratorNerfINR_freeze_NeRF if frozen else cips3d_b200.GeneratorNerfINR
+    cfg = {k: (dict(v) if isinstance(v, dict) else v) for k, v in O.G_CFG.items()}
+    G = cls(**cfg, device=device).to(device).eval()
+    if sd is not None:
+        G.load_state_dict(sd)
+    return G
