@@ -70,7 +70,21 @@ class ClockSampler(threading.Thread):
 def cpu_reference_rate(seconds_budget=20.0, threads=None, img_size=R, batch=1):
     """The reference algorithm (CPU oracle port of exp/cips3d/models/generator.py) on the host cores."""
     from oracle import cips3d_oracle as O
-    threads = threads or os.cpu_count()
+    sd_probe = O.synthetic_state_dict(O.generator_template(), seed=1234)
+    if threads is None:                     # torch-CPU scales badly past a few dozen threads: pick the best
+        best = (0.0, 1)
+        gp = torch.Generator().manual_seed(1)
+        zp = {"z_nerf": torch.randn(1, 256, generator=gp), "z_inr": torch.randn(1, 512, generator=gp)}
+        for th in sorted({min(os.cpu_count(), t) for t in (8, 16, 32, 64, 128)}):
+            torch.set_num_threads(th)
+            dr = O.draw_randoms(1, 64, 12, generator=gp)
+            t0 = time.perf_counter()
+            with torch.no_grad():
+                O.generator_forward(sd_probe, zp, dr, img_size=64, nerf_noise=0.0, **O.G_KWARGS)
+            r = 1.0 / (time.perf_counter() - t0)
+            if r > best[0]:
+                best = (r, th)
+        threads = best[1]
     torch.set_num_threads(threads)
     sd = O.synthetic_state_dict(O.generator_template(), seed=1234)
     kw = dict(O.G_KWARGS)

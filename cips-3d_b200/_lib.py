@@ -107,6 +107,9 @@ def stream_ptr():
     return torch.cuda.current_stream().cuda_stream
 
 
-def default_impl():
-    v = os.environ.get("C3D_IMPL", "tc").lower()
-    return IMPL_SIMT if v == "simt" else IMPL_TC
+def default_impl(kind=None):
+    """Kernel generation: env C3D_IMPL_RAY / C3D_IMPL_CIPS override C3D_IMPL (default "tc")."""
+    v = os.environ.get("C3D_IMPL", "tc")
+    if kind:
+        v = os.environ.get(f"C3D_IMPL_{kind.upper()}", v)
+    return IMPL_SIMT if v.lower() == "simt" else IMPL_TC

@@ -1,0 +1,478 @@
+// Fused per-pixel CIPS synthesis MLP on tcgen05 (C3D_IMPL_TC).
+//
+// One persistent CTA per SM walks 128-pixel tiles (all pixels of a tile belong to one image).
+// For a tile, the whole 18-layer chain  x -> [mod-linear 512x512 + demod + LeakyReLU]x2 (+skip)
+// -> ToRGB ... -> tanh  runs on-chip:
+//   * activations live in shared memory as the fp16 A operand (128 x 512, UMMA K-major
+//     no-swizzle layout, 128 KB) and are overwritten in place by each layer's epilogue;
+//   * the fp32 accumulator (128 x 512) fills all 512 TMEM columns;
+//   * weights are pre-tiled fp16 blobs (64 K x 128 N, 16 KB) streamed through a 5-stage
+//     shared-memory ring by bulk async copies (TMA engine, UBLKCP), optionally multicast to
+//     every CTA of a thread-block cluster so that L2 sees each byte once per cluster;
+//   * warp 0 = weight producer, warp 1 = single-thread tcgen05.mma issuer, warps 4..19 =
+//     epilogue (TMEM -> registers: demod, LeakyReLU, residual, ToRGB, next-layer input scale,
+//     fp16 pack -> shared memory).  The next layer's MMAs start as soon as the epilogue has
+//     produced the K-chunks / drained the accumulator columns they touch ("chase"), so the
+//     tensor pipe idles only for the first quarter of each epilogue.
+// Per-image modulation:  y = ((x * s1p) @ W) * d   (mod_conv_fc.py:452-496 restated, one W for
+// all images).  Only HBM traffic: x (128 B/pixel) in, rgb (12 B/pixel) out; the residual stream
+// of the skip blocks goes through an L2-resident per-CTA scratch (fp32, 256 KB).
+#include "c3d_common.cuh"
+
+namespace c3d {
+namespace cips {
+
+constexpr int kH = 512;            // hidden width
+constexpr int kTileM = 128;        // pixels per tile
+constexpr int kKC = 64;            // K per weight tile
+constexpr int kNC = 128;           // N per weight tile
+constexpr int kWTileBytes = kKC * kNC * 2;              // 16 KB
+constexpr int kStages = 5;
+constexpr int kXBytes = kTileM * kH * 2;                // 128 KB
+constexpr int kLBO = kTileM * 16;                       // 2048: K-direction core-matrix stride (A and B tiles have 128 rows)
+constexpr int kSBO = 128;                               // M/N-direction stride between 8-row groups
+constexpr int kNumEpiWarps = 16;
+constexpr int kThreads = 32 * (4 + kNumEpiWarps);       // 640
+constexpr int kMaxLayers = C3D_CIPS_MAX_LAYERS;
+
+struct Smem {
+  alignas(1024) uint8_t x[kXBytes];
+  alignas(1024) uint8_t w[kStages][kWTileBytes];
+  float rgb_part[4][kTileM][4];
+  alignas(8) uint64_t full[kStages];
+  uint64_t empty[kStages];
+  uint64_t epi_done[4];
+  uint64_t acc_full;
+  uint32_t tmem_base;
+};
+
+struct KArgs {
+  const float* x;            // (B,N,in_dim)
+  float* rgb;                // (B,N,3)
+  float* hidden_out;         // (B,N,512) or null
+  const __half* wtiles;      // prepped weights: layer-major, [kc][nc][16 KB tile]
+  const float* demod;        // (L,B,512)
+  const float* next_scale;   // (L,B,512): s1p of layer l+1 (ones for the last)
+  const float* in_scale;     // (B,in_dim): s1p of layer 0
+  const float4* rgbw;        // (n_blocks,512) float4 (w0,w1,w2,0) ; valid for blocks >= rgb_from
+  const float* rgbb;         // (3) summed ToRGB biases
+  float4* resid;             // (gridDim.x, 128, 128) float4 scratch
+  int B, N, in_dim, n_layers, skip_from, rgb_from, tiles_per_img, total_tiles;
+  int layer_tile_off[kMaxLayers + 1];   // offset (in tiles) of each layer's first weight tile
+  int layer_kc[kMaxLayers];             // number of K chunks of each layer (1 for the padded input layer)
+};
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+template <int CL>
+__device__ __forceinline__ void commit_stage_free(uint64_t* bar) {
+  if (CL == 1) {
+    tc_commit(bar);
+  } else {
+    const uint16_t mask = (uint16_t)((1u << CL) - 1);
+    asm volatile(
+        "tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+            smem_u32(bar)),
+        "h"(mask)
+        : "memory");
+  }
+}
+template <int CL>
+__device__ __forceinline__ void load_w_tile(void* dst, const uint8_t* src, uint64_t* bar, uint32_t rank) {
+  if (CL == 1) {
+    bulk_g2s(dst, src, kWTileBytes, bar);
+  } else {
+    constexpr uint32_t slice = kWTileBytes / CL;
+    const uint16_t mask = (uint16_t)((1u << CL) - 1);
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;"
+        ::"r"(smem_u32((uint8_t*)dst + rank * slice)), "l"(src + rank * slice), "r"(slice), "r"(smem_u32(bar)), "h"(mask)
+        : "memory");
+  }
+}
+
+__device__ __forceinline__ float lrelu02(float v) { return fmaxf(v, 0.2f * v); }
+
+template <int CL>
+__global__ void __launch_bounds__(kThreads, 1) cips_tc_kernel(const KArgs a) {
+  extern __shared__ uint8_t smem_raw[];
+  // identical offset in every CTA of a cluster (multicast lands at the same CTA-relative address)
+  Smem& s = *reinterpret_cast<Smem*>(smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u));
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t crank = CL > 1 ? cluster_ctarank() : 0;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < kStages; ++i) {
+      mbar_init(&s.full[i], 1);
+      mbar_init(&s.empty[i], CL);
+    }
+    for (int i = 0; i < 4; ++i) mbar_init(&s.epi_done[i], kNumEpiWarps);
+    mbar_init(&s.acc_full, 1);
+    fence_mbar_init();
+  }
+  if (warp == 2) tmem_alloc<512>(&s.tmem_base);
+  tc_fence_before();
+  __syncthreads();
+  if (CL > 1) cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem = s.tmem_base;
+
+  const int iters = (a.total_tiles + (int)gridDim.x - 1) / (int)gridDim.x;
+  const int L = a.n_layers;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------ weight producer
+    if (lane == 0) {
+      uint32_t stage = 0, phase = 0;
+      for (int it = 0; it < iters; ++it) {
+        for (int l = 0; l < L; ++l) {
+          const uint8_t* src = reinterpret_cast<const uint8_t*>(a.wtiles) + (size_t)a.layer_tile_off[l] * kWTileBytes;
+          const int ntiles = a.layer_kc[l] * 4;
+          for (int t = 0; t < ntiles; ++t) {
+            mbar_wait(&s.empty[stage], phase ^ 1);
+            mbar_arrive_expect_tx(&s.full[stage], kWTileBytes);
+            load_w_tile<CL>(s.w[stage], src + (size_t)t * kWTileBytes, &s.full[stage], crank);
+            if (++stage == kStages) { stage = 0; phase ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      const uint32_t idesc = umma_idesc_f16(kTileM, kNC);
+      const uint32_t xaddr = smem_u32(s.x);
+      uint32_t stage = 0, phase = 0;
+      for (int it = 0; it < iters; ++it) {
+        for (int l = 0; l < L; ++l) {
+          const uint32_t epar = (uint32_t)(it * L + l) & 1u;   // phase of the epilogue that feeds layer l (staging for l = 0)
+          const int nkc = a.layer_kc[l];
+          int waited = -1;
+          for (int kc = 0; kc < nkc; ++kc) {
+            for (int nc = 0; nc < 4; ++nc) {
+              const int need = max(kc >> 1, nc);       // epilogue chunk that must be complete
+              if (need > waited) {
+                for (int j = waited + 1; j <= need; ++j) mbar_wait(&s.epi_done[j], epar);
+                waited = need;
+                tc_fence_after();
+              }
+              mbar_wait(&s.full[stage], phase);
+              tc_fence_after();
+              const uint32_t waddr = smem_u32(s.w[stage]);
+#pragma unroll
+              for (int k4 = 0; k4 < kKC / 16; ++k4) {
+                const uint64_t ad = umma_desc_kmajor(xaddr + (uint32_t)((kc * kKC + k4 * 16) / 8) * kLBO, kLBO, kSBO);
+                const uint64_t bd = umma_desc_kmajor(waddr + (uint32_t)(k4 * 2) * kLBO, kLBO, kSBO);
+                umma_ss(tmem + (uint32_t)(nc * kNC), ad, bd, idesc, (kc | k4) != 0);
+              }
+              commit_stage_free<CL>(&s.empty[stage]);
+              if (++stage == kStages) { stage = 0; phase ^= 1; }
+            }
+          }
+          tc_commit(&s.acc_full);
+        }
+      }
+    }
+  } else if (warp >= 4) {
+    // ------------------------------------------------------------ epilogue warps
+    const int ew = warp - 4;
+    const int wg = ew >> 2;            // column group 0..3
+    const int q = warp & 3;            // TMEM lane quarter
+    const int row = q * 32 + lane;     // row of the tile this thread owns
+    const uint32_t trow = tmem + ((uint32_t)(q * 32) << 16);
+    float4* resid = a.resid + (size_t)blockIdx.x * (kH / 4) * kTileM;
+    for (int it = 0; it < iters; ++it) {
+      const int tile = it * (int)gridDim.x + (int)blockIdx.x;
+      const bool tile_ok = tile < a.total_tiles;
+      const int img = tile_ok ? tile / a.tiles_per_img : 0;
+      const int pix = tile_ok ? (tile % a.tiles_per_img) * kTileM + row : a.N;
+      const bool row_ok = tile_ok && pix < a.N;
+      float rgb0 = 0.f, rgb1 = 0.f, rgb2 = 0.f;
+      // ---- e = 0: stage the input tile (K padded to 64) as layer 0's A operand
+      {
+        if (wg < 2) {   // 64 columns: wg 0 -> k 0..31, wg 1 -> k 32..63
+          const int k0 = wg * 32;
+          uint32_t pk[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const int k = k0 + 2 * j;
+            float v0 = 0.f, v1 = 0.f;
+            if (row_ok && k < a.in_dim) {
+              const float* xp = a.x + ((size_t)img * a.N + pix) * a.in_dim;
+              v0 = xp[k] * __ldg(a.in_scale + (size_t)img * a.in_dim + k);
+              if (k + 1 < a.in_dim) v1 = xp[k + 1] * __ldg(a.in_scale + (size_t)img * a.in_dim + k + 1);
+            }
+            pk[j] = pack_f16(v0, v1);
+          }
+#pragma unroll
+          for (int g = 0; g < 4; ++g)
+            *reinterpret_cast<uint4*>(s.x + (size_t)(k0 / 8 + g) * kLBO + row * 16) =
+                make_uint4(pk[4 * g], pk[4 * g + 1], pk[4 * g + 2], pk[4 * g + 3]);
+        }
+        fence_proxy_async();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0)
+          for (int j = 0; j < 4; ++j) mbar_arrive(&s.epi_done[j]);
+      }
+      // ---- e = l + 1: epilogue of layer l
+      for (int l = 0; l < L; ++l) {
+        mbar_wait(&s.acc_full, (uint32_t)(it * L + l) & 1u);
+        tc_fence_after();
+        const int blk = l >> 1;
+        const bool second = (l & 1) != 0;
+        const bool last = l == L - 1;
+        const bool add_res = second && blk >= a.skip_from && blk >= 1;      // block input dim == 512 for blk >= 1
+        const bool keep_res = second && (blk + 1 >= a.skip_from) && !last;  // next block will add this output
+        const bool do_rgb = second && blk >= a.rgb_from;
+        const float* dvec = a.demod + ((size_t)l * a.B + img) * kH;
+        const float* svec = a.next_scale + ((size_t)l * a.B + img) * kH;
+        const float4* rw = a.rgbw + (size_t)blk * kH;
+        for (int j = 0; j < 4; ++j) {
+          const int c0 = j * 128 + wg * 32;
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            const int c = c0 + h * 16;
+            uint32_t acc[16];
+            tmem_ld16(trow + (uint32_t)c, acc);
+            float4 rs[4];
+            if (add_res) {
+#pragma unroll
+              for (int g = 0; g < 4; ++g) rs[g] = resid[(size_t)(c / 4 + g) * kTileM + row];
+            }
+            tc_wait_ld();
+            float y[16];
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+              const float4 d4 = __ldg(reinterpret_cast<const float4*>(dvec + c) + g);
+              y[4 * g + 0] = lrelu02(__uint_as_float(acc[4 * g + 0])) * d4.x;
+              y[4 * g + 1] = lrelu02(__uint_as_float(acc[4 * g + 1])) * d4.y;
+              y[4 * g + 2] = lrelu02(__uint_as_float(acc[4 * g + 2])) * d4.z;
+              y[4 * g + 3] = lrelu02(__uint_as_float(acc[4 * g + 3])) * d4.w;
+              if (add_res) {
+                y[4 * g + 0] += rs[g].x; y[4 * g + 1] += rs[g].y; y[4 * g + 2] += rs[g].z; y[4 * g + 3] += rs[g].w;
+              }
+            }
+            if (keep_res) {
+#pragma unroll
+              for (int g = 0; g < 4; ++g)
+                resid[(size_t)(c / 4 + g) * kTileM + row] = make_float4(y[4 * g], y[4 * g + 1], y[4 * g + 2], y[4 * g + 3]);
+            }
+            if (do_rgb) {
+#pragma unroll
+              for (int i = 0; i < 16; ++i) {
+                const float4 w4 = __ldg(rw + c + i);
+                rgb0 = fmaf(y[i], w4.x, rgb0);
+                rgb1 = fmaf(y[i], w4.y, rgb1);
+                rgb2 = fmaf(y[i], w4.z, rgb2);
+              }
+            }
+            if (last) {
+              if (a.hidden_out && row_ok) {
+                float* ho = a.hidden_out + ((size_t)img * a.N + pix) * kH + c;
+#pragma unroll
+                for (int g = 0; g < 4; ++g)
+                  reinterpret_cast<float4*>(ho)[g] = make_float4(y[4 * g], y[4 * g + 1], y[4 * g + 2], y[4 * g + 3]);
+              }
+            } else {
+              uint32_t pk[8];
+#pragma unroll
+              for (int g = 0; g < 4; ++g) {
+                const float4 s4 = __ldg(reinterpret_cast<const float4*>(svec + c) + g);
+                pk[2 * g + 0] = pack_f16(y[4 * g + 0] * s4.x, y[4 * g + 1] * s4.y);
+                pk[2 * g + 1] = pack_f16(y[4 * g + 2] * s4.z, y[4 * g + 3] * s4.w);
+              }
+              *reinterpret_cast<uint4*>(s.x + (size_t)(c / 8) * kLBO + row * 16) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+              *reinterpret_cast<uint4*>(s.x + (size_t)(c / 8 + 1) * kLBO + row * 16) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+            }
+          }
+          // chunk j of this epilogue is complete for this warp
+          fence_proxy_async();
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0 && !last) mbar_arrive(&s.epi_done[j]);
+        }
+      }
+      // ---- tile output: tanh(sum of ToRGB skips)  (generator.py:1139-1153)
+      s.rgb_part[wg][row][0] = rgb0;
+      s.rgb_part[wg][row][1] = rgb1;
+      s.rgb_part[wg][row][2] = rgb2;
+      asm volatile("bar.sync 1, %0;" ::"n"(kNumEpiWarps * 32) : "memory");
+      if (wg == 0 && row_ok) {
+        float o[3];
+#pragma unroll
+        for (int c = 0; c < 3; ++c)
+          o[c] = tanhf(((s.rgb_part[0][row][c] + s.rgb_part[1][row][c]) + (s.rgb_part[2][row][c] + s.rgb_part[3][row][c])) + a.rgbb[c]);
+        float* op = a.rgb + ((size_t)img * a.N + pix) * 3;
+        op[0] = o[0]; op[1] = o[1]; op[2] = o[2];
+      }
+      asm volatile("bar.sync 1, %0;" ::"n"(kNumEpiWarps * 32) : "memory");
+    }
+  }
+  // ------------------------------------------------------------ teardown
+  tc_fence_before();
+  __syncthreads();
+  if (CL > 1) cluster_sync_all();
+  if (warp == 2) tmem_dealloc<512>(tmem);
+}
+
+// fp32 (in,out) weights -> fp16 UMMA-B tiles: tile (kc,nc) holds B[n][k] = W[kc*64+k][nc*128+n]
+// at byte (n%8)*16 + (n/8)*128 + (k/8)*2048 + (k%8)*2.  Rows k >= in_dim are zero (input layer).
+__global__ void cips_prep_weights_kernel(const float* __restrict__ W, int in_dim, __half* __restrict__ out, int nkc) {
+  const int tile = blockIdx.x;             // kc*4 + nc
+  const int kc = tile >> 2, nc = tile & 3;
+  __half* o = out + (size_t)tile * (kWTileBytes / 2);
+  for (int i = threadIdx.x; i < kKC * kNC; i += blockDim.x) {
+    const int k = i / kNC, n = i % kNC;    // n fastest -> coalesced reads of W rows
+    const int gk = kc * kKC + k;
+    const float v = gk < in_dim ? W[(size_t)gk * kH + nc * kNC + n] : 0.f;
+    o[((n % 8) * 16 + (n / 8) * 128 + (k / 8) * kLBO) / 2 + (k % 8)] = __float2half_rn(v);
+  }
+}
+
+// per-(layer,image) epilogue vectors + packed ToRGB weights
+__global__ void cips_prep_consts_kernel(C3dCipsWeights w, int B, int L, int n_blocks, int rgb_from, float* demod,
+                                        float* next_scale, float4* rgbw, float* rgbb) {
+  const int l = blockIdx.x;
+  if (l < L) {
+    for (int i = threadIdx.x; i < B * kH; i += blockDim.x) {
+      demod[(size_t)l * B * kH + i] = w.demod[l][i];
+      next_scale[(size_t)l * B * kH + i] = (l + 1 < L) ? w.style1p[l + 1][i] : 1.f;
+    }
+  } else {
+    const int blk = l - L;
+    if (blk < n_blocks && blk >= rgb_from)
+      for (int n = threadIdx.x; n < kH; n += blockDim.x)
+        rgbw[(size_t)blk * kH + n] = make_float4(w.rgb_w[blk][n], w.rgb_w[blk][kH + n], w.rgb_w[blk][2 * kH + n], 0.f);
+    if (blk == 0 && threadIdx.x < 3) {
+      float sacc = 0.f;
+      for (int b = rgb_from; b < n_blocks; ++b) sacc += w.rgb_b[b][threadIdx.x];   // same order as the reference's skip chain
+      rgbb[threadIdx.x] = sacc;
+    }
+  }
+}
+
+}  // namespace cips
+}  // namespace c3d
+
+using namespace c3d;
+using namespace c3d::cips;
+
+static int cips_grid(const C3dCipsParams* p, int* cl_out) {
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  int cl = 1;
+  if (const char* e = getenv("C3D_CIPS_CLUSTER")) cl = atoi(e);
+  if (cl != 1 && cl != 2 && cl != 4) cl = 1;
+  const int tiles_per_img = (p->n_pix + kTileM - 1) / kTileM;
+  long long total = (long long)p->batch * tiles_per_img;
+  int grid = (int)(total < sms ? total : sms);
+  grid = (grid + cl - 1) / cl * cl;
+  if (grid > sms) grid = sms / cl * cl;
+  *cl_out = cl;
+  return grid;
+}
+
+struct CipsWs {
+  size_t wtiles, demod, next_scale, rgbw, rgbb, resid, total;
+};
+static CipsWs cips_ws_layout(const C3dCipsParams* p) {
+  CipsWs o;
+  const int L = 2 * p->n_blocks;
+  size_t off = 0;
+  auto take = [&](size_t bytes) { size_t r = off; off += (bytes + 255) / 256 * 256; return r; };
+  o.wtiles = take((size_t)(4 + (L - 1) * 32) * kWTileBytes);
+  o.demod = take((size_t)L * p->batch * kH * 4);
+  o.next_scale = take((size_t)L * p->batch * kH * 4);
+  o.rgbw = take((size_t)p->n_blocks * kH * 16);
+  o.rgbb = take(16);
+  o.resid = take((size_t)148 * 2 * (kH / 4) * kTileM * 16);
+  o.total = off;
+  return o;
+}
+
+size_t c3d_cips_tc_workspace_bytes(const C3dCipsParams* p) { return cips_ws_layout(p).total; }
+
+template <int CL>
+static int launch_cips(const KArgs& ka, int grid, cudaStream_t st) {
+  const size_t smem = sizeof(Smem) + 1024;
+  C3D_CUDA(cudaFuncSetAttribute(cips_tc_kernel<CL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CL;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  c3d_count_launch();
+  C3D_CUDA(cudaLaunchKernelEx(&cfg, cips_tc_kernel<CL>, ka));
+  return C3D_OK;
+}
+
+int c3d_cips_fwd_tc(const C3dCipsParams* p, const C3dCipsWeights* w, const float* x, float* rgb, float* hidden_out,
+                    void* workspace, size_t workspace_bytes, cudaStream_t st) {
+  C3D_CHECK_ARG(p->hidden == kH, "cips(tc): hidden must be 512, got %d", p->hidden);
+  C3D_CHECK_ARG(p->in_dim >= 1 && p->in_dim <= kKC, "cips(tc): in_dim must be <= 64, got %d", p->in_dim);
+  C3D_CHECK_ARG(p->skip_from >= 1, "cips(tc): skip_from must be >= 1 (block 0 changes width)");
+  const CipsWs ws = cips_ws_layout(p);
+  if (workspace_bytes < ws.total) {
+    c3d_set_error("cips(tc): workspace too small (%zu < %zu)", workspace_bytes, ws.total);
+    return C3D_EWORKSPACE;
+  }
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (!c3d_device_supported(dev)) {
+    c3d_set_error("cips(tc): device %d is not sm_100 (tcgen05 required)", dev);
+    return C3D_EARCH;
+  }
+  uint8_t* base = (uint8_t*)workspace;
+  const int L = 2 * p->n_blocks;
+  KArgs ka = {};
+  ka.x = x; ka.rgb = rgb; ka.hidden_out = hidden_out;
+  ka.wtiles = (const __half*)(base + ws.wtiles);
+  ka.demod = (const float*)(base + ws.demod);
+  ka.next_scale = (const float*)(base + ws.next_scale);
+  ka.in_scale = w->style1p[0];
+  ka.rgbw = (const float4*)(base + ws.rgbw);
+  ka.rgbb = (const float*)(base + ws.rgbb);
+  ka.resid = (float4*)(base + ws.resid);
+  ka.B = p->batch; ka.N = p->n_pix; ka.in_dim = p->in_dim; ka.n_layers = L;
+  ka.skip_from = p->skip_from; ka.rgb_from = p->rgb_from;
+  ka.tiles_per_img = (p->n_pix + kTileM - 1) / kTileM;
+  ka.total_tiles = p->batch * ka.tiles_per_img;
+  int off = 0;
+  for (int l = 0; l < L; ++l) {
+    ka.layer_tile_off[l] = off;
+    ka.layer_kc[l] = l == 0 ? 1 : kH / kKC;
+    off += ka.layer_kc[l] * 4;
+  }
+  ka.layer_tile_off[L] = off;
+  // ---- prep: weights -> fp16 tiles, per-image epilogue vectors
+  for (int l = 0; l < L; ++l) {
+    cips_prep_weights_kernel<<<ka.layer_kc[l] * 4, 256, 0, st>>>(
+        w->w[l], l == 0 ? p->in_dim : kH, (__half*)(base + ws.wtiles) + (size_t)ka.layer_tile_off[l] * (kWTileBytes / 2),
+        ka.layer_kc[l]);
+    C3D_LAUNCH_CHECK();
+  }
+  cips_prep_consts_kernel<<<L + p->n_blocks, 256, 0, st>>>(*w, p->batch, L, p->n_blocks, p->rgb_from,
+                                                           (float*)(base + ws.demod), (float*)(base + ws.next_scale),
+                                                           (float4*)(base + ws.rgbw), (float*)(base + ws.rgbb));
+  C3D_LAUNCH_CHECK();
+  int cl = 1;
+  const int grid = cips_grid(p, &cl);
+  if (cl == 1) return launch_cips<1>(ka, grid, st);
+  if (cl == 2) return launch_cips<2>(ka, grid, st);
+  return launch_cips<4>(ka, grid, st);
+}

@@ -1,0 +1,446 @@
+// Fused volumetric renderer on tcgen05 (C3D_IMPL_TC): rays -> FiLM-SIREN -> importance
+// resampling -> second FiLM-SIREN pass -> merge/sort -> front-to-back compositing, one kernel,
+// nothing per-sample ever written to HBM.
+//
+// Work unit: a ray group (RG) of G = floor(128 / S) whole rays = one 128-row MMA block (rows =
+// sample points, ray-major).  A persistent CTA owns two independent TMEM "slots"
+// (A operand 128 cols + fp32 accumulator 128 cols each); each slot carries one RG through
+//     coarse:  L0 (FMA pipe: 3->128 FiLM+sin) -> MMA 128x128 -> FiLM+sin -> MMA 128x(64+sigma)
+//              -> FiLM+sin -> MMA 64x32 -> features/sigma to shared memory
+//     sample:  per-ray weights -> pdf/cdf -> inverse-CDF -> fine depths     (ray_math.cuh)
+//     fine:    the same MLP on the resampled points
+//     merge:   per-ray stable sort of the 2S depths, compositing weights
+//     output:  sum_i w_i * feature_i  -> (B,N,32)
+// while the other slot is in a different phase, so tensor pipe, MUFU (sin) and FMA pipes overlap.
+//
+// Numerics: hidden activations are sin() outputs in [-1,1]; both MMA operands are split into
+// fp16 (hi, lo) pairs and every layer is three tcgen05.mma passes (hi*hi + lo*hi + hi*lo), which
+// restores ~fp32 products (hard part 2: single-pass TF32/BF16 misses 1e-3).
+// The A operand never touches shared memory: epilogue threads write it straight into TMEM
+// (tcgen05.st, two fp16 per 32-bit column, row = lane) and the MMAs use the A-from-TMEM form.
+// Weights (fp16 hi/lo, scaled by 2^8 to keep the lo parts normal) sit in shared memory for the
+// whole kernel (112 KB, loaded once per CTA by bulk async copies).
+#include "c3d_common.cuh"
+#include "ray_math.cuh"
+
+namespace c3d {
+namespace rtc {
+
+constexpr int kRows = 128;
+constexpr float kWScale = 256.f, kWInv = 1.f / 256.f;
+constexpr int kN2 = 80;                       // color_layer_sine (64) + sigma head (1) padded to a multiple of 16
+// shared-memory weight blob (bytes); every matrix is UMMA-B K-major no-swizzle:
+//   element (n,k) at (n%8)*16 + (n/8)*128 + (k/8)*(N*16) + (k%8)*2
+constexpr int kW1Bytes = 128 * 128 * 2;       // per hi / lo
+constexpr int kW2Bytes = kN2 * 128 * 2;
+constexpr int kW3Bytes = 32 * 64 * 2;
+constexpr int kOffW1h = 0, kOffW1l = kW1Bytes, kOffW2h = 2 * kW1Bytes, kOffW2l = kOffW2h + kW2Bytes,
+              kOffW3h = kOffW2l + kW2Bytes, kOffW3l = kOffW3h + kW3Bytes, kWBlobBytes = kOffW3l + kW3Bytes;
+static_assert(kWBlobBytes == 114688, "weight blob is 112 KB");
+
+// per-image epilogue constants (prep kernel): FiLM folded with the linear bias and weight scale
+struct ImgConsts {
+  float4 l0[128];      // (g0*s*W0[j][0..2], g0*b0[j] + beta0[j]),  s = 2/0.24 (UniformBoxWarp)
+  float2 l1[128];      // (g1/256, g1*b1 + beta1)
+  float2 lc[64];       // (gc/256, gc*bc + betac)
+};
+
+struct SlotMem {
+  float feat_c[kRows][33];
+  float feat_f[kRows][33];
+  float z_c[kRows], sig_c[kRows], z_f[kRows], sig_f[kRows];
+  float w_all[2 * kRows];
+  int idx_all[2 * kRows];
+  float wsum[16];
+};
+
+struct Smem {
+  alignas(1024) uint8_t w[kWBlobBytes];
+  SlotMem slot[2];
+  alignas(8) uint64_t w_full;
+  uint64_t a_ready[2];
+  uint64_t d_ready[2];
+  uint32_t tmem_base;
+};
+
+struct KArgs {
+  C3dRayParams p;
+  C3dRayIO io;
+  const uint8_t* wblob;       // kWBlobBytes, prepped
+  const ImgConsts* consts;    // (B)
+  const float* b_sigma;       // (1) final_layer bias
+  const float* bl;            // (32) color_layer_linear bias
+  int G;                      // rays per group
+  int groups_per_img, total_groups;
+};
+
+__device__ __forceinline__ float fast_sin(float x) { return __sinf(x); }
+
+// ---- write 16 consecutive K values (fp32) of this thread's row into the TMEM A operand (hi, lo)
+__device__ __forceinline__ void store_a16(uint32_t a_hi_col, uint32_t a_lo_col, const float (&v)[16]) {
+  uint32_t hi[8], lo[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) split_f16(v[2 * j], v[2 * j + 1], hi[j], lo[j]);
+  tmem_st8(a_hi_col, hi);
+  tmem_st8(a_lo_col, lo);
+}
+
+// ---- three-pass split-precision MMA:  D = A_hi*B_hi + A_lo*B_hi + A_hi*B_lo   (A in TMEM)
+__device__ __forceinline__ void mma_split3(uint32_t d_tmem, uint32_t a_hi, uint32_t a_lo, uint32_t b_hi_addr,
+                                           uint32_t b_lo_addr, int N, int K) {
+  const uint32_t idesc = umma_idesc_f16(kRows, N);
+  const uint32_t lbo = (uint32_t)N * 16;
+  bool first = true;
+#pragma unroll 1
+  for (int pass = 0; pass < 3; ++pass) {
+    const uint32_t a = pass == 1 ? a_lo : a_hi;
+    const uint32_t b = pass == 2 ? b_lo_addr : b_hi_addr;
+    for (int k0 = 0; k0 < K; k0 += 16) {
+      const uint64_t bd = umma_desc_kmajor(b + (uint32_t)(k0 / 8) * lbo, lbo, 128);
+      umma_ts(d_tmem, a + (uint32_t)(k0 / 2), bd, idesc, first ? 0u : 1u);
+      first = false;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(640, 1) ray_siren_tc_kernel(const KArgs a) {
+  extern __shared__ uint8_t smem_raw[];
+  Smem& s = *reinterpret_cast<Smem*>(smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u));
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const C3dRayParams& p = a.p;
+  const int S = p.num_steps, G = a.G;
+  const bool hier = p.hierarchical != 0;
+  const int nS = hier ? 2 * S : S;
+  const int mma_phases = hier ? 6 : 3;
+
+  if (threadIdx.x == 0) {
+    mbar_init(&s.w_full, 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&s.a_ready[i], 8);
+      mbar_init(&s.d_ready[i], 1);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 2) tmem_alloc<512>(&s.tmem_base);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = s.tmem_base;
+  const int iters = (a.total_groups + 2 * (int)gridDim.x - 1) / (2 * (int)gridDim.x);
+
+  if (warp == 0) {
+    if (lane == 0) {   // weights: one 112 KB bulk load per CTA
+      mbar_arrive_expect_tx(&s.w_full, kWBlobBytes);
+      for (int off = 0; off < kWBlobBytes; off += 16384) bulk_g2s(s.w + off, a.wblob + off, 16384, &s.w_full);
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      mbar_wait(&s.w_full, 0);
+      const uint32_t wb = smem_u32(s.w);
+      uint32_t par[2] = {0, 0};
+      for (int it = 0; it < iters; ++it) {
+        for (int ph = 0; ph < mma_phases; ++ph) {
+          const int layer = ph % 3;
+          for (int sl = 0; sl < 2; ++sl) {
+            const uint32_t a_hi = tmem + (uint32_t)(sl * 256), a_lo = a_hi + 64, d = a_hi + 128;
+            mbar_wait(&s.a_ready[sl], par[sl]);
+            par[sl] ^= 1;
+            tc_fence_after();
+            if (layer == 0) mma_split3(d, a_hi, a_lo, wb + kOffW1h, wb + kOffW1l, 128, 128);
+            else if (layer == 1) mma_split3(d, a_hi, a_lo, wb + kOffW2h, wb + kOffW2l, kN2, 128);
+            else mma_split3(d, a_hi, a_lo, wb + kOffW3h, wb + kOffW3l, 32, 64);
+            tc_commit(&s.d_ready[sl]);
+          }
+        }
+      }
+    }
+  } else if (warp >= 4) {
+    // ------------------------------------------------------------ slot workers (epilogue + ray math)
+    const int ew = warp - 4;             // 0..15
+    const int sl = (ew >> 2) & 1;        // slot
+    const int half = ew >> 3;            // column half
+    const int q = warp & 3;
+    const int row = q * 32 + lane;       // point row of the group
+    const int stid = half * 128 + row;   // 0..255 within the slot
+    SlotMem& sm = s.slot[sl];
+    const uint32_t lane_sel = (uint32_t)(q * 32) << 16;
+    const uint32_t a_hi = tmem + (uint32_t)(sl * 256) + lane_sel, a_lo = a_hi + 64, dcol = a_hi + 128;
+    const int bar_id = 1 + sl;
+    auto slot_sync = [&]() { asm volatile("bar.sync %0, 256;" ::"r"(bar_id) : "memory"); };
+    uint32_t dpar = 0;
+    auto signal_a = [&]() {
+      tc_wait_st();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&s.a_ready[sl]);
+    };
+    auto wait_d = [&]() {
+      mbar_wait(&s.d_ready[sl], dpar);
+      dpar ^= 1;
+      tc_fence_after();
+    };
+    const int g_row = row / S, s_row = row - g_row * S;   // ray within the group, sample index
+    const bool row_in_group = g_row < G;
+
+    for (int it = 0; it < iters; ++it) {
+      const int grp = (it * (int)gridDim.x + (int)blockIdx.x) * 2 + sl;
+      const bool grp_ok = grp < a.total_groups;
+      const int img = grp_ok ? grp / a.groups_per_img : 0;
+      const int ray0 = grp_ok ? (grp % a.groups_per_img) * G : 0;          // first local ray of the group
+      const int n_valid = grp_ok ? min(G, p.n_rays - ray0) : 0;            // rays of this group that exist
+      const bool pt_ok = row_in_group && g_row < n_valid;
+      const int nloc = ray0 + g_row;                                       // local ray index (output slot)
+      const ImgConsts& ic = a.consts[img];
+      const float* M = a.io.cam2world + (size_t)img * 16;
+      RayFrame fr;
+      int gray = 0;
+      if (pt_ok) {
+        gray = a.io.ray_idx ? a.io.ray_idx[nloc] : p.ray_offset + nloc;
+        fr = make_ray_frame(M, gray, p.img_size, p.z_cam);
+      }
+
+      for (int pass = 0; pass < (hier ? 2 : 1); ++pass) {
+        // ---------------- L0: point position, first FiLM layer (FMA pipe) -> A operand
+        float px = 0.f, py = 0.f, pz = 0.f;
+        if (pt_ok) {
+          if (pass == 0) {
+            const float u = a.io.jitter_u[((size_t)img * p.img_size * p.img_size + gray) * S + s_row];
+            float z;
+            coarse_sample(fr, M, p.ray_start, p.ray_end, S, s_row, u, z, px, py, pz);
+            if (half == 0) sm.z_c[row] = z;
+          } else {
+            fine_sample(fr, sm.z_f[row], px, py, pz);
+          }
+        }
+#pragma unroll 1
+        for (int c = 0; c < 64; c += 16) {
+          float v[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const float4 w4 = __ldg(&ic.l0[half * 64 + c + j]);
+            v[j] = fast_sin(fmaf(w4.x, px, fmaf(w4.y, py, fmaf(w4.z, pz, w4.w))));
+          }
+          store_a16(a_hi + (uint32_t)(half * 32 + c / 2), a_lo + (uint32_t)(half * 32 + c / 2), v);
+        }
+        signal_a();
+        // ---------------- E1: D(128) -> FiLM+sin -> A (h1)
+        wait_d();
+#pragma unroll 1
+        for (int c = 0; c < 64; c += 16) {
+          uint32_t acc[16];
+          tmem_ld16(dcol + (uint32_t)(half * 64 + c), acc);
+          tc_wait_ld();
+          float v[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const float2 g2 = __ldg(&ic.l1[half * 64 + c + j]);
+            v[j] = fast_sin(fmaf(__uint_as_float(acc[j]), g2.x, g2.y));
+          }
+          store_a16(a_hi + (uint32_t)(half * 32 + c / 2), a_lo + (uint32_t)(half * 32 + c / 2), v);
+        }
+        signal_a();
+        // ---------------- E2: D(80): cols 0..63 -> FiLM+sin -> A (h2, K=64); col 64 -> sigma
+        wait_d();
+#pragma unroll 1
+        for (int c = 0; c < 32; c += 16) {
+          uint32_t acc[16];
+          tmem_ld16(dcol + (uint32_t)(half * 32 + c), acc);
+          tc_wait_ld();
+          float v[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const float2 g2 = __ldg(&ic.lc[half * 32 + c + j]);
+            v[j] = fast_sin(fmaf(__uint_as_float(acc[j]), g2.x, g2.y));
+          }
+          store_a16(a_hi + (uint32_t)(half * 16 + c / 2), a_lo + (uint32_t)(half * 16 + c / 2), v);
+        }
+        float sigma = 0.f;
+        if (half == 1) {
+          uint32_t acc[16];
+          tmem_ld16(dcol + 64u, acc);
+          tc_wait_ld();
+          sigma = fmaf(__uint_as_float(acc[0]), kWInv, __ldg(a.b_sigma));
+          (pass == 0 ? sm.sig_c : sm.sig_f)[row] = sigma;
+        }
+        signal_a();
+        // ---------------- E3: D(32) -> + bias -> features to shared memory
+        wait_d();
+        {
+          uint32_t acc[16];
+          tmem_ld16(dcol + (uint32_t)(half * 16), acc);
+          tc_wait_ld();
+          float(*feat)[33] = pass == 0 ? sm.feat_c : sm.feat_f;
+          float* dbg = pass == 0 ? a.io.dbg_coarse : a.io.dbg_fine;
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const float f = fmaf(__uint_as_float(acc[j]), kWInv, __ldg(a.bl + half * 16 + j));
+            feat[row][half * 16 + j] = f;
+            if (dbg && pt_ok) dbg[(((size_t)img * p.n_rays + nloc) * S + s_row) * kOutC + half * 16 + j] = f;
+          }
+          if (dbg && pt_ok && half == 1) dbg[(((size_t)img * p.n_rays + nloc) * S + s_row) * kOutC + kFeat] = sigma;
+        }
+        tc_fence_before();
+        slot_sync();
+        // ---------------- importance resampling (one thread per ray), generator_nerf_inr.py:537-598
+        if (pass == 0 && hier) {
+          if (stid < n_valid) {
+            const int g = stid, r0 = g * S;
+            const size_t ro = (size_t)img * p.n_rays + ray0 + g;
+            const float* nz = a.io.noise_c ? a.io.noise_c + ro * S : nullptr;
+            float w[kMaxS], zz[kMaxS], u[kMaxS], fz[kMaxS];
+            for (int i = 0; i < S; ++i) {
+              zz[i] = sm.z_c[r0 + i];
+              u[i] = a.io.pdf_u[ro * S + i];
+            }
+            const float ns = p.noise_std;
+            integrate_weights(
+                S, p.clamp_mode, [&](int i) { return zz[i]; }, [&](int i) { return sm.sig_c[r0 + i]; },
+                [&](int i) { return nz ? __fmul_rn(nz[i], ns) : 0.f; }, [&](int i, float v) { w[i] = v; });
+            sample_pdf_ray(S, w, zz, u, fz);
+            for (int i = 0; i < S; ++i) sm.z_f[r0 + i] = fz[i];
+          }
+          slot_sync();
+        }
+      }
+      // ---------------- merge + compositing weights (one thread per ray), generator.py:1733-1744
+      if (stid < n_valid) {
+        const int g = stid, r0 = g * S;
+        const size_t ro = (size_t)img * p.n_rays + ray0 + g;
+        float key[kMaxNS];
+        int idx[kMaxNS];
+        if (hier) {
+          for (int i = 0; i < S; ++i) { key[i] = sm.z_f[r0 + i]; idx[i] = i; }
+          for (int i = 0; i < S; ++i) { key[S + i] = sm.z_c[r0 + i]; idx[S + i] = S + i; }
+          sort_keys(nS, key, idx);
+        } else {
+          for (int i = 0; i < S; ++i) { key[i] = sm.z_c[r0 + i]; idx[i] = S + i; }
+        }
+        const float* nz = a.io.noise_f ? a.io.noise_f + ro * nS : nullptr;
+        const float ns = p.noise_std;
+        float wsum = integrate_weights(
+            nS, p.clamp_mode, [&](int i) { return key[i]; },
+            [&](int i) { return idx[i] < S ? sm.sig_f[r0 + idx[i]] : sm.sig_c[r0 + idx[i] - S]; },
+            [&](int i) { return nz ? __fmul_rn(nz[i], ns) : 0.f; },
+            [&](int i, float v) { sm.w_all[g * nS + i] = v; });
+        if (p.last_back) sm.w_all[g * nS + nS - 1] += 1.f - wsum;
+        sm.wsum[g] = wsum;
+        float depth = 0.f;
+        for (int i = 0; i < nS; ++i) {
+          sm.idx_all[g * nS + i] = idx[i];
+          depth = fmaf(sm.w_all[g * nS + i], key[i], depth);
+          if (a.io.weights) a.io.weights[ro * nS + i] = sm.w_all[g * nS + i];
+          if (a.io.dbg_all_z) a.io.dbg_all_z[ro * nS + i] = key[i];
+        }
+        if (a.io.depth) a.io.depth[ro] = depth;
+      }
+      slot_sync();
+      // ---------------- composite: pixels_fea[ray][c] = sum_i w_i * feature_i[c]  (pigan_utils.py:262)
+      for (int o = stid; o < n_valid * kFeat; o += 256) {
+        const int g = o >> 5, c = o & 31, r0 = g * S;
+        float acc = 0.f;
+        for (int i = 0; i < nS; ++i) {
+          const int id = sm.idx_all[g * nS + i];
+          const float f = id < S ? sm.feat_f[r0 + id][c] : sm.feat_c[r0 + id - S][c];
+          acc = fmaf(sm.w_all[g * nS + i], f, acc);
+        }
+        if (p.white_back) acc += 1.f - sm.wsum[g];
+        a.io.pixels_fea[((size_t)img * p.n_rays + ray0 + g) * kFeat + c] = acc;
+      }
+      slot_sync();
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc<512>(tmem);
+}
+
+// ---- prep: fp32 weights -> scaled fp16 (hi, lo) UMMA-B blobs; per-image folded FiLM constants
+__device__ __forceinline__ void put_split(uint8_t* blob, int off_hi, int off_lo, int N, int n, int k, float v) {
+  const __half h = __float2half_rn(v);
+  const __half l = __float2half_rn(v - __half2float(h));
+  const int e = ((n % 8) * 16 + (n / 8) * 128 + (k / 8) * (N * 16)) / 2 + (k % 8);
+  reinterpret_cast<__half*>(blob + off_hi)[e] = h;
+  reinterpret_cast<__half*>(blob + off_lo)[e] = l;
+}
+
+__global__ void ray_prep_kernel(C3dSirenWeights w, int B, uint8_t* blob, ImgConsts* consts) {
+  const int tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
+  for (int i = tid; i < 128 * 128; i += nth) put_split(blob, kOffW1h, kOffW1l, 128, i / 128, i % 128, w.w1[i] * kWScale);
+  for (int i = tid; i < kN2 * 128; i += nth) {
+    const int n = i / 128, k = i % 128;
+    const float v = n < 64 ? w.wc[n * 128 + k] : (n == 64 ? w.w_sigma[k] : 0.f);
+    put_split(blob, kOffW2h, kOffW2l, kN2, n, k, v * kWScale);
+  }
+  for (int i = tid; i < 32 * 64; i += nth) put_split(blob, kOffW3h, kOffW3l, 32, i / 64, i % 64, w.wl[i] * kWScale);
+  const float sc = 2.f / 0.24f;
+  for (int i = tid; i < B * 128; i += nth) {
+    const int b = i / 128, j = i % 128;
+    const float g0 = w.gamma0[i], g1 = w.gamma1[i];
+    consts[b].l0[j] = make_float4(g0 * sc * w.w0[j * 3], g0 * sc * w.w0[j * 3 + 1], g0 * sc * w.w0[j * 3 + 2],
+                                  fmaf(g0, w.b0[j], w.beta0[i]));
+    consts[b].l1[j] = make_float2(g1 * kWInv, fmaf(g1, w.b1[j], w.beta1[i]));
+  }
+  for (int i = tid; i < B * 64; i += nth) {
+    const int b = i / 64, j = i % 64;
+    const float gc = w.gammac[i];
+    consts[b].lc[j] = make_float2(gc * kWInv, fmaf(gc, w.bc[j], w.betac[i]));
+  }
+}
+
+}  // namespace rtc
+}  // namespace c3d
+
+using namespace c3d;
+using namespace c3d::rtc;
+
+struct RayWs {
+  size_t blob, consts, total;
+};
+static RayWs ray_ws_layout(const C3dRayParams* p) {
+  RayWs o;
+  size_t off = 0;
+  auto take = [&](size_t b) { size_t r = off; off += (b + 255) / 256 * 256; return r; };
+  o.blob = take(kWBlobBytes);
+  o.consts = take((size_t)(p->batch > 0 ? p->batch : 1) * sizeof(ImgConsts));
+  o.total = off;
+  return o;
+}
+size_t c3d_ray_siren_tc_workspace_bytes(const C3dRayParams* p) { return ray_ws_layout(p).total; }
+
+int c3d_ray_siren_fwd_tc(const C3dRayParams* p, const C3dSirenWeights* w, const C3dRayIO* io, void* workspace,
+                         size_t workspace_bytes, cudaStream_t st) {
+  const RayWs ws = ray_ws_layout(p);
+  if (workspace_bytes < ws.total) {
+    c3d_set_error("ray_siren(tc): workspace too small (%zu < %zu)", workspace_bytes, ws.total);
+    return C3D_EWORKSPACE;
+  }
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  if (!c3d_device_supported(dev)) {
+    c3d_set_error("ray_siren(tc): device %d is not sm_100 (tcgen05 required)", dev);
+    return C3D_EARCH;
+  }
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  uint8_t* base = (uint8_t*)workspace;
+  ray_prep_kernel<<<64, 256, 0, st>>>(*w, p->batch, base + ws.blob, (ImgConsts*)(base + ws.consts));
+  C3D_LAUNCH_CHECK();
+  KArgs ka = {};
+  ka.p = *p;
+  ka.io = *io;
+  ka.wblob = base + ws.blob;
+  ka.consts = (const ImgConsts*)(base + ws.consts);
+  ka.bl = w->bl;
+  ka.G = kRows / p->num_steps;
+  ka.groups_per_img = (p->n_rays + ka.G - 1) / ka.G;
+  ka.total_groups = p->batch * ka.groups_per_img;
+  ka.b_sigma = w->b_sigma;
+  const size_t smem = sizeof(Smem) + 1024;
+  C3D_CUDA(cudaFuncSetAttribute(ray_siren_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int grid = (ka.total_groups + 1) / 2;
+  if (grid > sms) grid = sms;
+  if (grid < 1) grid = 1;
+  ray_siren_tc_kernel<<<grid, 640, smem, st>>>(ka);
+  C3D_LAUNCH_CHECK();
+  return C3D_OK;
+}

@@ -74,7 +74,7 @@ def render_features(siren, film, cam2world, jitter_u, pdf_u=None, noise_c=None, 
     p = RayParams(batch=B, img_size=img_size, num_steps=S, n_rays=N, ray_offset=int(ray_offset),
                   hierarchical=int(bool(hierarchical_sample)), clamp_mode=CLAMP_MODES[clamp_mode],
                   white_back=int(bool(white_back)), last_back=int(bool(last_back)),
-                  impl=_lib.default_impl() if impl is None else impl,
+                  impl=_lib.default_impl("ray") if impl is None else impl,
                   z_cam=z_cam_from_fov(fov), ray_start=float(ray_start), ray_end=float(ray_end),
                   noise_std=float(noise_std))
     keep = []  # keep contiguous copies alive until launch
@@ -138,7 +138,7 @@ def cips_forward(x, weights, style1p, demod, rgb_w, rgb_b, *, n_blocks=9, skip_f
     B, N, in_dim = x.shape
     hidden = weights[0].shape[1]
     p = CipsParams(batch=B, n_pix=N, in_dim=in_dim, hidden=hidden, n_blocks=n_blocks, skip_from=skip_from,
-                   rgb_from=rgb_from, impl=_lib.default_impl() if impl is None else impl)
+                   rgb_from=rgb_from, impl=_lib.default_impl("cips") if impl is None else impl)
     keep = []
     cw = CipsWeights()
     for l in range(2 * n_blocks):
@@ -170,6 +170,8 @@ def bias_act(x, bias=None, ref=None, act=3, grad=0, alpha=0.2, scale=2 ** 0.5):
     lib = load()
     x = _f32c(x, "x")
     y = torch.empty_like(x)
+    if x.numel() == 0:
+        return y
     b = _f32c(bias, "bias") if bias is not None and bias.numel() else None
     r = _f32c(ref, "ref") if ref is not None and ref.numel() else None
     step_b = 1
