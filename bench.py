@@ -182,7 +182,7 @@ def main():
         with torch.no_grad():
             z = {k: v.to(dev, non_blocking=True) for k, v in zs_host.items()}
             img, _ = G(z, img_size=res, nerf_noise=0.0, **kw)
-            out_host.copy_(img, non_blocking=True)
+            out_host.copy_(img.contiguous(), non_blocking=True)
         return img
 
     def timed(fn, steps, warmup, profile=False):
@@ -231,7 +231,7 @@ def main():
     for key, flop_unit, units in (("cips", CIPS_FLOP_PER_PIXEL, B * res * res), ("ray", NERF_FLOP_PER_RAY, B * res * res)):
         evs = (prof or {}).get(key, [])
         if evs:
-            t_ms = float(np.mean([a.elapsed_time(b) for a, b in evs]))
+            t_ms = float(np.median([a.elapsed_time(b) for a, b in evs]))
             ach = flop_unit * units / (t_ms * 1e-3) / 1e12
             roof[key] = {"bound": "tensor", "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach / peak_tf,
                          "traffic": None, "kernel_ms": t_ms, "launches_timed": len(evs),

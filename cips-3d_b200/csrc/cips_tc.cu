@@ -38,7 +38,11 @@ constexpr int kMaxLayers = C3D_CIPS_MAX_LAYERS;
 struct Smem {
   alignas(1024) uint8_t x[kXBytes];
   alignas(1024) uint8_t w[kStages][kWTileBytes];
-  float rgb_part[4][kTileM][4];
+  alignas(16) float cvec[2][2][kH];      // per-layer epilogue vectors, double-buffered across layers
+  union {                                // ToRGB weights of the current block / per-tile rgb partial sums
+    float4 rgbw[kH];
+    float rgb_part[4][kTileM][4];
+  };
   alignas(8) uint64_t full[kStages];
   uint64_t empty[kStages];
   uint64_t epi_done[4];
@@ -99,6 +103,74 @@ __device__ __forceinline__ void load_w_tile(void* dst, const uint8_t* src, uint6
 
 __device__ __forceinline__ float lrelu02(float v) { return fmaxf(v, 0.2f * v); }
 
+template <int N>
+__device__ __forceinline__ void reg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
+template <int N>
+__device__ __forceinline__ void reg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
+
+struct EpiFlags {
+  bool add_res, keep_res, do_rgb, last;
+};
+
+// One thread, 16 accumulator columns [c, c+16) of its row.
+//   first layer of a block : a = lrelu(acc) * (d * s_next)                       -> fp16 A operand
+//   second layer of a block: y = lrelu(acc) * d (+ residual); ToRGB += y.Wrgb;   a = y * s_next
+template <bool SECOND>
+__device__ __forceinline__ void epi16(const uint32_t (&acc)[16], const float4 (&rs)[4], const float* __restrict__ c0,
+                                      const float* __restrict__ c1, const float4* __restrict__ rgbw, int c, int row,
+                                      uint8_t* xbuf, float4* resid, const EpiFlags f, float& rgb0, float& rgb1,
+                                      float& rgb2, float* hid_out) {
+  float y[16];
+#pragma unroll
+  for (int g = 0; g < 4; ++g) {
+    const float4 d4 = *reinterpret_cast<const float4*>(c0 + c + 4 * g);
+    y[4 * g + 0] = lrelu02(__uint_as_float(acc[4 * g + 0])) * d4.x;
+    y[4 * g + 1] = lrelu02(__uint_as_float(acc[4 * g + 1])) * d4.y;
+    y[4 * g + 2] = lrelu02(__uint_as_float(acc[4 * g + 2])) * d4.z;
+    y[4 * g + 3] = lrelu02(__uint_as_float(acc[4 * g + 3])) * d4.w;
+  }
+  if (SECOND) {
+    if (f.add_res) {
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        y[4 * g + 0] += rs[g].x; y[4 * g + 1] += rs[g].y; y[4 * g + 2] += rs[g].z; y[4 * g + 3] += rs[g].w;
+      }
+    }
+    if (f.keep_res) {
+#pragma unroll
+      for (int g = 0; g < 4; ++g)
+        resid[(size_t)(c / 4 + g) * kTileM + row] = make_float4(y[4 * g], y[4 * g + 1], y[4 * g + 2], y[4 * g + 3]);
+    }
+    if (f.do_rgb) {
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        const float4 w4 = rgbw[c + i];
+        rgb0 = fmaf(y[i], w4.x, rgb0);
+        rgb1 = fmaf(y[i], w4.y, rgb1);
+        rgb2 = fmaf(y[i], w4.z, rgb2);
+      }
+    }
+    if (f.last) {
+      if (hid_out) {
+#pragma unroll
+        for (int g = 0; g < 4; ++g)
+          reinterpret_cast<float4*>(hid_out + c)[g] = make_float4(y[4 * g], y[4 * g + 1], y[4 * g + 2], y[4 * g + 3]);
+      }
+      return;
+    }
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+      const float4 s4 = *reinterpret_cast<const float4*>(c1 + c + 4 * g);
+      y[4 * g + 0] *= s4.x; y[4 * g + 1] *= s4.y; y[4 * g + 2] *= s4.z; y[4 * g + 3] *= s4.w;
+    }
+  }
+  uint32_t pk[8];
+#pragma unroll
+  for (int g = 0; g < 8; ++g) pk[g] = pack_f16(y[2 * g], y[2 * g + 1]);
+  *reinterpret_cast<uint4*>(xbuf + (size_t)(c / 8) * kLBO + row * 16) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+  *reinterpret_cast<uint4*>(xbuf + (size_t)(c / 8 + 1) * kLBO + row * 16) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+}
+
 template <int CL>
 __global__ void __launch_bounds__(kThreads, 1) cips_tc_kernel(const KArgs a) {
   extern __shared__ uint8_t smem_raw[];
@@ -126,6 +198,8 @@ __global__ void __launch_bounds__(kThreads, 1) cips_tc_kernel(const KArgs a) {
   const int iters = (a.total_tiles + (int)gridDim.x - 1) / (int)gridDim.x;
   const int L = a.n_layers;
 
+  if (warp < 4) {
+    reg_dec<56>();  // 128*32 + 512*112 == 640*96: setmaxnreg only recycles this CTA's own registers
   if (warp == 0) {
     // ------------------------------------------------------------ weight producer
     if (lane == 0) {
@@ -147,7 +221,11 @@ __global__ void __launch_bounds__(kThreads, 1) cips_tc_kernel(const KArgs a) {
     // ------------------------------------------------------------ MMA issuer
     if (lane == 0) {
       const uint32_t idesc = umma_idesc_f16(kTileM, kNC);
-      const uint32_t xaddr = smem_u32(s.x);
+      const uint32_t dhi = umma_desc_hi(kSBO);
+      const uint32_t a_lo0 = umma_desc_lo(smem_u32(s.x), kLBO);
+      const uint32_t b_lo0 = umma_desc_lo(smem_u32(s.w[0]), kLBO);
+      constexpr uint32_t kStepK16 = (2 * kLBO) >> 4;       // one K=16 MMA step  = 2 core-matrix columns
+      constexpr uint32_t kStepStage = kWTileBytes >> 4;
       uint32_t stage = 0, phase = 0;
       for (int it = 0; it < iters; ++it) {
         for (int l = 0; l < L; ++l) {
@@ -155,6 +233,8 @@ __global__ void __launch_bounds__(kThreads, 1) cips_tc_kernel(const KArgs a) {
           const int nkc = a.layer_kc[l];
           int waited = -1;
           for (int kc = 0; kc < nkc; ++kc) {
+            const uint32_t a_lo = a_lo0 + (uint32_t)kc * (kStepK16 * (kKC / 16));
+#pragma unroll 1
             for (int nc = 0; nc < 4; ++nc) {
               const int need = max(kc >> 1, nc);       // epilogue chunk that must be complete
               if (need > waited) {
@@ -164,13 +244,12 @@ __global__ void __launch_bounds__(kThreads, 1) cips_tc_kernel(const KArgs a) {
               }
               mbar_wait(&s.full[stage], phase);
               tc_fence_after();
-              const uint32_t waddr = smem_u32(s.w[stage]);
-#pragma unroll
-              for (int k4 = 0; k4 < kKC / 16; ++k4) {
-                const uint64_t ad = umma_desc_kmajor(xaddr + (uint32_t)((kc * kKC + k4 * 16) / 8) * kLBO, kLBO, kSBO);
-                const uint64_t bd = umma_desc_kmajor(waddr + (uint32_t)(k4 * 2) * kLBO, kLBO, kSBO);
-                umma_ss(tmem + (uint32_t)(nc * kNC), ad, bd, idesc, (kc | k4) != 0);
-              }
+              const uint32_t b_lo = b_lo0 + stage * kStepStage;
+              const uint32_t d = tmem + (uint32_t)(nc * kNC);
+              umma_ss_w(d, a_lo, b_lo, dhi, idesc, kc != 0);
+              umma_ss_w(d, a_lo + kStepK16, b_lo + kStepK16, dhi, idesc, 1);
+              umma_ss_w(d, a_lo + 2 * kStepK16, b_lo + 2 * kStepK16, dhi, idesc, 1);
+              umma_ss_w(d, a_lo + 3 * kStepK16, b_lo + 3 * kStepK16, dhi, idesc, 1);
               commit_stage_free<CL>(&s.empty[stage]);
               if (++stage == kStages) { stage = 0; phase ^= 1; }
             }
@@ -179,8 +258,10 @@ __global__ void __launch_bounds__(kThreads, 1) cips_tc_kernel(const KArgs a) {
         }
       }
     }
-  } else if (warp >= 4) {
+  }
+  } else {
     // ------------------------------------------------------------ epilogue warps
+    reg_inc<104>();
     const int ew = warp - 4;
     const int wg = ew >> 2;            // column group 0..3
     const int q = warp & 3;            // TMEM lane quarter
@@ -223,83 +304,60 @@ __global__ void __launch_bounds__(kThreads, 1) cips_tc_kernel(const KArgs a) {
       }
       // ---- e = l + 1: epilogue of layer l
       for (int l = 0; l < L; ++l) {
-        mbar_wait(&s.acc_full, (uint32_t)(it * L + l) & 1u);
-        tc_fence_after();
         const int blk = l >> 1;
         const bool second = (l & 1) != 0;
-        const bool last = l == L - 1;
-        const bool add_res = second && blk >= a.skip_from && blk >= 1;      // block input dim == 512 for blk >= 1
-        const bool keep_res = second && (blk + 1 >= a.skip_from) && !last;  // next block will add this output
-        const bool do_rgb = second && blk >= a.rgb_from;
-        const float* dvec = a.demod + ((size_t)l * a.B + img) * kH;
-        const float* svec = a.next_scale + ((size_t)l * a.B + img) * kH;
-        const float4* rw = a.rgbw + (size_t)blk * kH;
-        for (int j = 0; j < 4; ++j) {
-          const int c0 = j * 128 + wg * 32;
+        EpiFlags f;
+        f.last = l == L - 1;
+        f.add_res = second && blk >= a.skip_from && blk >= 1;      // block input dim == 512 for blk >= 1
+        f.keep_res = second && (blk + 1 >= a.skip_from) && !f.last;  // the next block adds this output
+        f.do_rgb = second && blk >= a.rgb_from;
+        // stage this layer's per-image vectors (and ToRGB weights) in shared memory while the MMAs run
+        float* c0 = s.cvec[l & 1][0];
+        float* c1 = s.cvec[l & 1][1];
+        {
+          const int t = (int)threadIdx.x - 128;   // 0..511
+          const float dv = __ldg(a.demod + ((size_t)l * a.B + img) * kH + t);
+          const float sv = __ldg(a.next_scale + ((size_t)l * a.B + img) * kH + t);
+          c0[t] = second ? dv : dv * sv;
+          c1[t] = sv;
+          if (f.do_rgb) s.rgbw[t] = __ldg(a.rgbw + (size_t)blk * kH + t);
+        }
+        asm volatile("bar.sync 1, %0;" ::"n"(kNumEpiWarps * 32) : "memory");
+        mbar_wait(&s.acc_full, (uint32_t)(it * L + l) & 1u);
+        tc_fence_after();
+        float* hid = (f.last && a.hidden_out && row_ok) ? a.hidden_out + ((size_t)img * a.N + pix) * kH : nullptr;
+        // software pipeline over the 8 x 16-column slices this thread owns (chunk j = i/2)
+        uint32_t accA[16], accB[16];
+        float4 rsA[4], rsB[4];
+        auto col_of = [&](int i) { return (i >> 1) * 128 + wg * 32 + (i & 1) * 16; };
+        auto prefetch = [&](int i, uint32_t (&acc)[16], float4 (&rs)[4]) {
+          const int c = col_of(i);
+          tmem_ld16(trow + (uint32_t)c, acc);
+          if (f.add_res) {
 #pragma unroll
-          for (int h = 0; h < 2; ++h) {
-            const int c = c0 + h * 16;
-            uint32_t acc[16];
-            tmem_ld16(trow + (uint32_t)c, acc);
-            float4 rs[4];
-            if (add_res) {
-#pragma unroll
-              for (int g = 0; g < 4; ++g) rs[g] = resid[(size_t)(c / 4 + g) * kTileM + row];
-            }
-            tc_wait_ld();
-            float y[16];
-#pragma unroll
-            for (int g = 0; g < 4; ++g) {
-              const float4 d4 = __ldg(reinterpret_cast<const float4*>(dvec + c) + g);
-              y[4 * g + 0] = lrelu02(__uint_as_float(acc[4 * g + 0])) * d4.x;
-              y[4 * g + 1] = lrelu02(__uint_as_float(acc[4 * g + 1])) * d4.y;
-              y[4 * g + 2] = lrelu02(__uint_as_float(acc[4 * g + 2])) * d4.z;
-              y[4 * g + 3] = lrelu02(__uint_as_float(acc[4 * g + 3])) * d4.w;
-              if (add_res) {
-                y[4 * g + 0] += rs[g].x; y[4 * g + 1] += rs[g].y; y[4 * g + 2] += rs[g].z; y[4 * g + 3] += rs[g].w;
-              }
-            }
-            if (keep_res) {
-#pragma unroll
-              for (int g = 0; g < 4; ++g)
-                resid[(size_t)(c / 4 + g) * kTileM + row] = make_float4(y[4 * g], y[4 * g + 1], y[4 * g + 2], y[4 * g + 3]);
-            }
-            if (do_rgb) {
-#pragma unroll
-              for (int i = 0; i < 16; ++i) {
-                const float4 w4 = __ldg(rw + c + i);
-                rgb0 = fmaf(y[i], w4.x, rgb0);
-                rgb1 = fmaf(y[i], w4.y, rgb1);
-                rgb2 = fmaf(y[i], w4.z, rgb2);
-              }
-            }
-            if (last) {
-              if (a.hidden_out && row_ok) {
-                float* ho = a.hidden_out + ((size_t)img * a.N + pix) * kH + c;
-#pragma unroll
-                for (int g = 0; g < 4; ++g)
-                  reinterpret_cast<float4*>(ho)[g] = make_float4(y[4 * g], y[4 * g + 1], y[4 * g + 2], y[4 * g + 3]);
-              }
-            } else {
-              uint32_t pk[8];
-#pragma unroll
-              for (int g = 0; g < 4; ++g) {
-                const float4 s4 = __ldg(reinterpret_cast<const float4*>(svec + c) + g);
-                pk[2 * g + 0] = pack_f16(y[4 * g + 0] * s4.x, y[4 * g + 1] * s4.y);
-                pk[2 * g + 1] = pack_f16(y[4 * g + 2] * s4.z, y[4 * g + 3] * s4.w);
-              }
-              *reinterpret_cast<uint4*>(s.x + (size_t)(c / 8) * kLBO + row * 16) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-              *reinterpret_cast<uint4*>(s.x + (size_t)(c / 8 + 1) * kLBO + row * 16) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
-            }
+            for (int g = 0; g < 4; ++g) rs[g] = resid[(size_t)(c / 4 + g) * kTileM + row];
           }
+        };
+        prefetch(0, accA, rsA);
+#pragma unroll 1
+        for (int j = 0; j < 4; ++j) {
+          tc_wait_ld();
+          prefetch(2 * j + 1, accB, rsB);
+          if (second) epi16<true>(accA, rsA, c0, c1, s.rgbw, col_of(2 * j), row, s.x, resid, f, rgb0, rgb1, rgb2, hid);
+          else epi16<false>(accA, rsA, c0, c1, s.rgbw, col_of(2 * j), row, s.x, resid, f, rgb0, rgb1, rgb2, hid);
+          tc_wait_ld();
+          if (j < 3) prefetch(2 * j + 2, accA, rsA);
+          if (second) epi16<true>(accB, rsB, c0, c1, s.rgbw, col_of(2 * j + 1), row, s.x, resid, f, rgb0, rgb1, rgb2, hid);
+          else epi16<false>(accB, rsB, c0, c1, s.rgbw, col_of(2 * j + 1), row, s.x, resid, f, rgb0, rgb1, rgb2, hid);
           // chunk j of this epilogue is complete for this warp
           fence_proxy_async();
           tc_fence_before();
           __syncwarp();
-          if (lane == 0 && !last) mbar_arrive(&s.epi_done[j]);
+          if (lane == 0 && !f.last) mbar_arrive(&s.epi_done[j]);
         }
       }
       // ---- tile output: tanh(sum of ToRGB skips)  (generator.py:1139-1153)
+      asm volatile("bar.sync 1, %0;" ::"n"(kNumEpiWarps * 32) : "memory");   // rgbw (aliased) no longer read
       s.rgb_part[wg][row][0] = rgb0;
       s.rgb_part[wg][row][1] = rgb1;
       s.rgb_part[wg][row][2] = rgb2;

@@ -49,9 +49,16 @@ struct SlotMem {
   float feat_c[kRows][33];
   float feat_f[kRows][33];
   float z_c[kRows], sig_c[kRows], z_f[kRows], sig_f[kRows];
-  float w_all[2 * kRows];
-  int idx_all[2 * kRows];
-  float wsum[16];
+  float wc[kRows];            // coarse compositing weights
+  float cdf[kRows];           // per ray: S-1 cdf entries (stride S)
+  float fbuf[2 * kRows];      // 1 - alpha + 1e-10 per (sorted) sample
+  float abuf[2 * kRows];      // alpha per (sorted) sample
+  float skey[2 * kRows];      // sorted depths, ray g at [g*nS, (g+1)*nS)
+  int sidx[2 * kRows];        // source of each sorted sample: < S fine, >= S coarse
+  float w_all[2 * kRows];     // final compositing weights (sorted order)
+  alignas(16) float4 l0[128]; // image constants of the group's image (ImgConsts)
+  float2 l1[128];
+  float2 lc[64];
 };
 
 struct Smem {
@@ -75,6 +82,21 @@ struct KArgs {
 };
 
 __device__ __forceinline__ float fast_sin(float x) { return __sinf(x); }
+template <int N>
+__device__ __forceinline__ void reg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
+template <int N>
+__device__ __forceinline__ void reg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
+__device__ __forceinline__ bool mbar_test(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred P;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 P, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, P;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
 
 // ---- write 16 consecutive K values (fp32) of this thread's row into the TMEM A operand (hi, lo)
 __device__ __forceinline__ void store_a16(uint32_t a_hi_col, uint32_t a_lo_col, const float (&v)[16]) {
@@ -85,22 +107,26 @@ __device__ __forceinline__ void store_a16(uint32_t a_hi_col, uint32_t a_lo_col, 
   tmem_st8(a_lo_col, lo);
 }
 
-// ---- three-pass split-precision MMA:  D = A_hi*B_hi + A_lo*B_hi + A_hi*B_lo   (A in TMEM)
-__device__ __forceinline__ void mma_split3(uint32_t d_tmem, uint32_t a_hi, uint32_t a_lo, uint32_t b_hi_addr,
-                                           uint32_t b_lo_addr, int N, int K) {
-  const uint32_t idesc = umma_idesc_f16(kRows, N);
-  const uint32_t lbo = (uint32_t)N * 16;
-  bool first = true;
-#pragma unroll 1
-  for (int pass = 0; pass < 3; ++pass) {
-    const uint32_t a = pass == 1 ? a_lo : a_hi;
-    const uint32_t b = pass == 2 ? b_lo_addr : b_hi_addr;
-    for (int k0 = 0; k0 < K; k0 += 16) {
-      const uint64_t bd = umma_desc_kmajor(b + (uint32_t)(k0 / 8) * lbo, lbo, 128);
-      umma_ts(d_tmem, a + (uint32_t)(k0 / 2), bd, idesc, first ? 0u : 1u);
-      first = false;
-    }
-  }
+// ---- three-pass split-precision MMA:  D = A_hi*B_hi + A_lo*B_hi + A_hi*B_lo   (A in TMEM).
+// b_*_lo: low descriptor words of the hi / lo weight matrices (umma_desc_lo); K-step = 2 core columns.
+template <int N, int K>
+__device__ __forceinline__ void mma_split3(uint32_t d_tmem, uint32_t a_hi, uint32_t a_lo, uint32_t b_hi_lo,
+                                           uint32_t b_lo_lo, uint32_t dhi) {
+  constexpr uint32_t idesc = umma_idesc_f16(kRows, N);
+  constexpr uint32_t kstep = (2u * N * 16u) >> 4;
+#pragma unroll
+  for (int k = 0; k < K / 16; ++k) umma_ts_w(d_tmem, a_hi + 8 * k, b_hi_lo + kstep * k, dhi, idesc, k != 0);
+#pragma unroll
+  for (int k = 0; k < K / 16; ++k) umma_ts_w(d_tmem, a_lo + 8 * k, b_hi_lo + kstep * k, dhi, idesc, 1);
+#pragma unroll
+  for (int k = 0; k < K / 16; ++k) umma_ts_w(d_tmem, a_hi + 8 * k, b_lo_lo + kstep * k, dhi, idesc, 1);
+}
+
+// alpha of one sample (pigan_utils.py:246-251): 1 - exp(-delta * clamp(sigma + noise))
+__device__ __forceinline__ float sample_alpha(float delta, float sigma, float noise, int clamp_mode) {
+  const float sn = __fadd_rn(sigma, noise);
+  const float act = clamp_mode == 1 ? softplus_f32(sn) : fmaxf(sn, 0.f);
+  return __fsub_rn(1.f, expf(__fmul_rn(-delta, act)));
 }
 
 __global__ void __launch_bounds__(640, 1) ray_siren_tc_kernel(const KArgs a) {
@@ -128,35 +154,58 @@ __global__ void __launch_bounds__(640, 1) ray_siren_tc_kernel(const KArgs a) {
   const uint32_t tmem = s.tmem_base;
   const int iters = (a.total_groups + 2 * (int)gridDim.x - 1) / (2 * (int)gridDim.x);
 
-  if (warp == 0) {
-    if (lane == 0) {   // weights: one 112 KB bulk load per CTA
-      mbar_arrive_expect_tx(&s.w_full, kWBlobBytes);
-      for (int off = 0; off < kWBlobBytes; off += 16384) bulk_g2s(s.w + off, a.wblob + off, 16384, &s.w_full);
-    }
-  } else if (warp == 1) {
-    // ------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
-      mbar_wait(&s.w_full, 0);
-      const uint32_t wb = smem_u32(s.w);
-      uint32_t par[2] = {0, 0};
-      for (int it = 0; it < iters; ++it) {
-        for (int ph = 0; ph < mma_phases; ++ph) {
-          const int layer = ph % 3;
+  if (warp < 4) {
+    reg_dec<56>();  // 128*32 + 512*112 == 640*96: setmaxnreg only recycles this CTA's own registers
+    if (warp == 0) {
+      if (lane == 0) {   // weights: one 112 KB bulk load per CTA
+        mbar_arrive_expect_tx(&s.w_full, kWBlobBytes);
+        for (int off = 0; off < kWBlobBytes; off += 16384) bulk_g2s(s.w + off, a.wblob + off, 16384, &s.w_full);
+      }
+    } else if (warp == 1) {
+      // ---------------------------------------------------------- MMA issuer: serve whichever slot is ready
+      if (lane == 0) {
+        mbar_wait(&s.w_full, 0);
+        const uint32_t wb = smem_u32(s.w);
+        const uint32_t dhi = umma_desc_hi(128);
+        const uint32_t w1h = umma_desc_lo(wb + kOffW1h, 128 * 16), w1l = umma_desc_lo(wb + kOffW1l, 128 * 16);
+        const uint32_t w2h = umma_desc_lo(wb + kOffW2h, kN2 * 16), w2l = umma_desc_lo(wb + kOffW2l, kN2 * 16);
+        const uint32_t w3h = umma_desc_lo(wb + kOffW3h, 32 * 16), w3l = umma_desc_lo(wb + kOffW3l, 32 * 16);
+        uint32_t par[2] = {0, 0};
+        int done[2] = {0, 0};
+        const int total = iters * mma_phases;
+        uint32_t idle = 0;
+        while (done[0] < total || done[1] < total) {
+          if (++idle > (1u << 28)) {
+            printf("c3d watchdog: ray MMA issuer starved (block %d, done %d/%d of %d)\n", (int)blockIdx.x, done[0], done[1], total);
+            __trap();
+          }
+#pragma unroll
           for (int sl = 0; sl < 2; ++sl) {
-            const uint32_t a_hi = tmem + (uint32_t)(sl * 256), a_lo = a_hi + 64, d = a_hi + 128;
-            mbar_wait(&s.a_ready[sl], par[sl]);
-            par[sl] ^= 1;
-            tc_fence_after();
-            if (layer == 0) mma_split3(d, a_hi, a_lo, wb + kOffW1h, wb + kOffW1l, 128, 128);
-            else if (layer == 1) mma_split3(d, a_hi, a_lo, wb + kOffW2h, wb + kOffW2l, kN2, 128);
-            else mma_split3(d, a_hi, a_lo, wb + kOffW3h, wb + kOffW3l, 32, 64);
-            tc_commit(&s.d_ready[sl]);
+            if (done[sl] < total && mbar_test(&s.a_ready[sl], par[sl])) {
+              par[sl] ^= 1;
+              tc_fence_after();
+              const uint32_t a_hi = tmem + (uint32_t)(sl * 256), a_lo = a_hi + 64, d = a_hi + 128;
+              const int layer = done[sl] % 3;
+              // opaque per-iteration copies: keeps the compiler from hoisting 50+ loop-invariant
+              // descriptor words out of the loop (they would spill and cost an LDL per MMA)
+              uint32_t bh = layer == 0 ? w1h : (layer == 1 ? w2h : w3h);
+              uint32_t bl = layer == 0 ? w1l : (layer == 1 ? w2l : w3l);
+              uint32_t ah = a_hi, al = a_lo;
+              asm volatile("" : "+r"(bh), "+r"(bl), "+r"(ah), "+r"(al));
+              if (layer == 0) mma_split3<128, 128>(d, ah, al, bh, bl, dhi);
+              else if (layer == 1) mma_split3<kN2, 128>(d, ah, al, bh, bl, dhi);
+              else mma_split3<32, 64>(d, ah, al, bh, bl, dhi);
+              tc_commit(&s.d_ready[sl]);
+              ++done[sl];
+              idle = 0;
+            }
           }
         }
       }
     }
-  } else if (warp >= 4) {
+  } else {
     // ------------------------------------------------------------ slot workers (epilogue + ray math)
+    reg_inc<104>();
     const int ew = warp - 4;             // 0..15
     const int sl = (ew >> 2) & 1;        // slot
     const int half = ew >> 3;            // column half
@@ -182,6 +231,8 @@ __global__ void __launch_bounds__(640, 1) ray_siren_tc_kernel(const KArgs a) {
     };
     const int g_row = row / S, s_row = row - g_row * S;   // ray within the group, sample index
     const bool row_in_group = g_row < G;
+    const int g_el = stid / nS, e_el = stid - g_el * nS;  // (ray, element) view used by the merge phases
+    int cur_img = -1;
 
     for (int it = 0; it < iters; ++it) {
       const int grp = (it * (int)gridDim.x + (int)blockIdx.x) * 2 + sl;
@@ -191,8 +242,16 @@ __global__ void __launch_bounds__(640, 1) ray_siren_tc_kernel(const KArgs a) {
       const int n_valid = grp_ok ? min(G, p.n_rays - ray0) : 0;            // rays of this group that exist
       const bool pt_ok = row_in_group && g_row < n_valid;
       const int nloc = ray0 + g_row;                                       // local ray index (output slot)
-      const ImgConsts& ic = a.consts[img];
+      const size_t ro_row = (size_t)img * p.n_rays + nloc;
       const float* M = a.io.cam2world + (size_t)img * 16;
+      if (img != cur_img) {    // (slot-uniform) stage the image's folded FiLM constants
+        const ImgConsts& ic = a.consts[img];
+        if (stid < 128) sm.l0[stid] = __ldg(&ic.l0[stid]);
+        else sm.l1[stid - 128] = __ldg(&ic.l1[stid - 128]);
+        if (stid < 64) sm.lc[stid] = __ldg(&ic.lc[stid]);
+        cur_img = img;
+        slot_sync();
+      }
       RayFrame fr;
       int gray = 0;
       if (pt_ok) {
@@ -218,50 +277,63 @@ __global__ void __launch_bounds__(640, 1) ray_siren_tc_kernel(const KArgs a) {
           float v[16];
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
-            const float4 w4 = __ldg(&ic.l0[half * 64 + c + j]);
+            const float4 w4 = sm.l0[half * 64 + c + j];
             v[j] = fast_sin(fmaf(w4.x, px, fmaf(w4.y, py, fmaf(w4.z, pz, w4.w))));
           }
           store_a16(a_hi + (uint32_t)(half * 32 + c / 2), a_lo + (uint32_t)(half * 32 + c / 2), v);
         }
         signal_a();
-        // ---------------- E1: D(128) -> FiLM+sin -> A (h1)
+        // ---------------- E1: D(128) -> FiLM+sin -> A (h1); TMEM loads double-buffered
         wait_d();
-#pragma unroll 1
-        for (int c = 0; c < 64; c += 16) {
-          uint32_t acc[16];
-          tmem_ld16(dcol + (uint32_t)(half * 64 + c), acc);
-          tc_wait_ld();
-          float v[16];
+        {
+          uint32_t accA[16], accB[16];
+          auto e1 = [&](const uint32_t (&acc)[16], int c) {
+            float v[16];
 #pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            const float2 g2 = __ldg(&ic.l1[half * 64 + c + j]);
-            v[j] = fast_sin(fmaf(__uint_as_float(acc[j]), g2.x, g2.y));
-          }
-          store_a16(a_hi + (uint32_t)(half * 32 + c / 2), a_lo + (uint32_t)(half * 32 + c / 2), v);
+            for (int j = 0; j < 16; ++j) {
+              const float2 g2 = sm.l1[half * 64 + c + j];
+              v[j] = fast_sin(fmaf(__uint_as_float(acc[j]), g2.x, g2.y));
+            }
+            store_a16(a_hi + (uint32_t)(half * 32 + c / 2), a_lo + (uint32_t)(half * 32 + c / 2), v);
+          };
+          tmem_ld16(dcol + (uint32_t)(half * 64), accA);
+          tc_wait_ld();
+          tmem_ld16(dcol + (uint32_t)(half * 64 + 16), accB);
+          e1(accA, 0);
+          tc_wait_ld();
+          tmem_ld16(dcol + (uint32_t)(half * 64 + 32), accA);
+          e1(accB, 16);
+          tc_wait_ld();
+          tmem_ld16(dcol + (uint32_t)(half * 64 + 48), accB);
+          e1(accA, 32);
+          tc_wait_ld();
+          e1(accB, 48);
         }
         signal_a();
         // ---------------- E2: D(80): cols 0..63 -> FiLM+sin -> A (h2, K=64); col 64 -> sigma
         wait_d();
-#pragma unroll 1
-        for (int c = 0; c < 32; c += 16) {
-          uint32_t acc[16];
-          tmem_ld16(dcol + (uint32_t)(half * 32 + c), acc);
-          tc_wait_ld();
-          float v[16];
-#pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            const float2 g2 = __ldg(&ic.lc[half * 32 + c + j]);
-            v[j] = fast_sin(fmaf(__uint_as_float(acc[j]), g2.x, g2.y));
-          }
-          store_a16(a_hi + (uint32_t)(half * 16 + c / 2), a_lo + (uint32_t)(half * 16 + c / 2), v);
-        }
         float sigma = 0.f;
-        if (half == 1) {
-          uint32_t acc[16];
-          tmem_ld16(dcol + 64u, acc);
+        {
+          uint32_t accA[16], accB[16], accS[16];
+          auto e2 = [&](const uint32_t (&acc)[16], int c) {
+            float v[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              const float2 g2 = sm.lc[half * 32 + c + j];
+              v[j] = fast_sin(fmaf(__uint_as_float(acc[j]), g2.x, g2.y));
+            }
+            store_a16(a_hi + (uint32_t)(half * 16 + c / 2), a_lo + (uint32_t)(half * 16 + c / 2), v);
+          };
+          tmem_ld16(dcol + (uint32_t)(half * 32), accA);
+          tmem_ld16(dcol + (uint32_t)(half * 32 + 16), accB);
+          if (half == 1) tmem_ld16(dcol + 64u, accS);
           tc_wait_ld();
-          sigma = fmaf(__uint_as_float(acc[0]), kWInv, __ldg(a.b_sigma));
-          (pass == 0 ? sm.sig_c : sm.sig_f)[row] = sigma;
+          if (half == 1) {
+            sigma = fmaf(__uint_as_float(accS[0]), kWInv, __ldg(a.b_sigma));
+            (pass == 0 ? sm.sig_c : sm.sig_f)[row] = sigma;
+          }
+          e2(accA, 0);
+          e2(accB, 16);
         }
         signal_a();
         // ---------------- E3: D(32) -> + bias -> features to shared memory
@@ -276,76 +348,108 @@ __global__ void __launch_bounds__(640, 1) ray_siren_tc_kernel(const KArgs a) {
           for (int j = 0; j < 16; ++j) {
             const float f = fmaf(__uint_as_float(acc[j]), kWInv, __ldg(a.bl + half * 16 + j));
             feat[row][half * 16 + j] = f;
-            if (dbg && pt_ok) dbg[(((size_t)img * p.n_rays + nloc) * S + s_row) * kOutC + half * 16 + j] = f;
+            if (dbg && pt_ok) dbg[(ro_row * S + s_row) * kOutC + half * 16 + j] = f;
           }
-          if (dbg && pt_ok && half == 1) dbg[(((size_t)img * p.n_rays + nloc) * S + s_row) * kOutC + kFeat] = sigma;
+          if (dbg && pt_ok && half == 1) dbg[(ro_row * S + s_row) * kOutC + kFeat] = sigma;
         }
         tc_fence_before();
         slot_sync();
-        // ---------------- importance resampling (one thread per ray), generator_nerf_inr.py:537-598
+        // ---------------- importance resampling, all threads (generator_nerf_inr.py:537-598, pigan_utils.py:164-209)
         if (pass == 0 && hier) {
-          if (stid < n_valid) {
-            const int g = stid, r0 = g * S;
-            const size_t ro = (size_t)img * p.n_rays + ray0 + g;
-            const float* nz = a.io.noise_c ? a.io.noise_c + ro * S : nullptr;
-            float w[kMaxS], zz[kMaxS], u[kMaxS], fz[kMaxS];
-            for (int i = 0; i < S; ++i) {
-              zz[i] = sm.z_c[r0 + i];
-              u[i] = a.io.pdf_u[ro * S + i];
-            }
-            const float ns = p.noise_std;
-            integrate_weights(
-                S, p.clamp_mode, [&](int i) { return zz[i]; }, [&](int i) { return sm.sig_c[r0 + i]; },
-                [&](int i) { return nz ? __fmul_rn(nz[i], ns) : 0.f; }, [&](int i, float v) { w[i] = v; });
-            sample_pdf_ray(S, w, zz, u, fz);
-            for (int i = 0; i < S; ++i) sm.z_f[r0 + i] = fz[i];
+          const int r0 = g_row * S;
+          float alpha = 0.f;
+          if (half == 0 && pt_ok) {   // A: alpha_i and (1 - alpha_i + 1e-10)
+            const float delta = s_row + 1 < S ? __fsub_rn(sm.z_c[row + 1], sm.z_c[row]) : 1e10f;
+            const float nz = a.io.noise_c ? __fmul_rn(a.io.noise_c[ro_row * S + s_row], p.noise_std) : 0.f;
+            alpha = sample_alpha(delta, sm.sig_c[row], nz, p.clamp_mode);
+            sm.fbuf[row] = __fadd_rn(__fsub_rn(1.f, alpha), 1e-10f);
+          }
+          slot_sync();
+          if (half == 0 && pt_ok) {   // B: T_i = prod_{j<i} f_j (sequential order), w_i = alpha_i * T_i
+            float T = 1.f;
+            for (int j = 0; j < s_row; ++j) T = __fmul_rn(T, sm.fbuf[r0 + j]);
+            sm.wc[row] = __fmul_rn(alpha, T);
+          }
+          slot_sync();
+          if (half == 0 && pt_ok && s_row <= S - 2) {   // C: cdf_j, j = 0..S-2, over weights (w+1e-5)[1:-1]+1e-5
+            float sum = 0.f;
+            for (int j = 0; j < S - 2; ++j) sum += __fadd_rn(__fadd_rn(sm.wc[r0 + j + 1], 1e-5f), 1e-5f);
+            float c = 0.f;
+            for (int j = 0; j < s_row; ++j)
+              c = __fadd_rn(c, __fdiv_rn(__fadd_rn(__fadd_rn(sm.wc[r0 + j + 1], 1e-5f), 1e-5f), sum));
+            sm.cdf[r0 + s_row] = c;
+          }
+          slot_sync();
+          if (half == 0 && pt_ok) {   // D: inverse CDF for u_k, k = s_row
+            const int ns = S - 2;
+            const float uk = a.io.pdf_u[ro_row * S + s_row];
+            int i = 0;
+            while (i <= ns && sm.cdf[r0 + i] < uk) ++i;         // searchsorted(cdf, u, right=False)
+            const int below = max(i - 1, 0), above = min(i, ns);
+            const float cb = sm.cdf[r0 + below], ca = sm.cdf[r0 + above];
+            const float bb = 0.5f * __fadd_rn(sm.z_c[r0 + below], sm.z_c[r0 + below + 1]);
+            const float ba = 0.5f * __fadd_rn(sm.z_c[r0 + above], sm.z_c[r0 + above + 1]);
+            float denom = __fsub_rn(ca, cb);
+            if (denom < 1e-5f) denom = 1.f;
+            sm.z_f[row] = __fadd_rn(bb, __fmul_rn(__fdiv_rn(__fsub_rn(uk, cb), denom), __fsub_rn(ba, bb)));
           }
           slot_sync();
         }
       }
-      // ---------------- merge + compositing weights (one thread per ray), generator.py:1733-1744
-      if (stid < n_valid) {
-        const int g = stid, r0 = g * S;
-        const size_t ro = (size_t)img * p.n_rays + ray0 + g;
-        float key[kMaxNS];
-        int idx[kMaxNS];
-        if (hier) {
-          for (int i = 0; i < S; ++i) { key[i] = sm.z_f[r0 + i]; idx[i] = i; }
-          for (int i = 0; i < S; ++i) { key[S + i] = sm.z_c[r0 + i]; idx[S + i] = S + i; }
-          sort_keys(nS, key, idx);
-        } else {
-          for (int i = 0; i < S; ++i) { key[i] = sm.z_c[r0 + i]; idx[i] = S + i; }
+      // ---------------- merge (stable rank sort of the nS depths of each ray), generator.py:1733-1738
+      const bool el_ok = g_el < n_valid;
+      const int rc0 = g_el * S;           // first row of ray g_el
+      const int base = g_el * nS;
+      const size_t ro_el = (size_t)img * p.n_rays + ray0 + g_el;
+      if (el_ok) {
+        auto key_of = [&](int e) { return hier ? (e < S ? sm.z_f[rc0 + e] : sm.z_c[rc0 + e - S]) : sm.z_c[rc0 + e]; };
+        const float k = key_of(e_el);
+        int rank = 0;
+        for (int e = 0; e < nS; ++e) {
+          const float ke = key_of(e);
+          rank += (ke < k || (ke == k && e < e_el)) ? 1 : 0;
         }
-        const float* nz = a.io.noise_f ? a.io.noise_f + ro * nS : nullptr;
-        const float ns = p.noise_std;
-        float wsum = integrate_weights(
-            nS, p.clamp_mode, [&](int i) { return key[i]; },
-            [&](int i) { return idx[i] < S ? sm.sig_f[r0 + idx[i]] : sm.sig_c[r0 + idx[i] - S]; },
-            [&](int i) { return nz ? __fmul_rn(nz[i], ns) : 0.f; },
-            [&](int i, float v) { sm.w_all[g * nS + i] = v; });
-        if (p.last_back) sm.w_all[g * nS + nS - 1] += 1.f - wsum;
-        sm.wsum[g] = wsum;
-        float depth = 0.f;
-        for (int i = 0; i < nS; ++i) {
-          sm.idx_all[g * nS + i] = idx[i];
-          depth = fmaf(sm.w_all[g * nS + i], key[i], depth);
-          if (a.io.weights) a.io.weights[ro * nS + i] = sm.w_all[g * nS + i];
-          if (a.io.dbg_all_z) a.io.dbg_all_z[ro * nS + i] = key[i];
-        }
-        if (a.io.depth) a.io.depth[ro] = depth;
+        sm.skey[base + rank] = k;
+        sm.sidx[base + rank] = hier ? e_el : S + e_el;
       }
       slot_sync();
-      // ---------------- composite: pixels_fea[ray][c] = sum_i w_i * feature_i[c]  (pigan_utils.py:262)
+      float alpha_el = 0.f;
+      if (el_ok) {       // alpha of sorted position e_el (pigan_utils.py:241-251)
+        const int src = sm.sidx[base + e_el];
+        const float sg = src < S ? sm.sig_f[rc0 + src] : sm.sig_c[rc0 + src - S];
+        const float delta = e_el + 1 < nS ? __fsub_rn(sm.skey[base + e_el + 1], sm.skey[base + e_el]) : 1e10f;
+        const float nz = a.io.noise_f ? __fmul_rn(a.io.noise_f[ro_el * nS + e_el], p.noise_std) : 0.f;
+        alpha_el = sample_alpha(delta, sg, nz, p.clamp_mode);
+        sm.fbuf[base + e_el] = __fadd_rn(__fsub_rn(1.f, alpha_el), 1e-10f);
+      }
+      slot_sync();
+      if (el_ok) {       // transmittance in the reference's cumprod order, weight
+        float T = 1.f;
+        for (int j = 0; j < e_el; ++j) T = __fmul_rn(T, sm.fbuf[base + j]);
+        sm.w_all[base + e_el] = __fmul_rn(alpha_el, T);
+      }
+      slot_sync();
+      // ---------------- composite: pixels_fea[ray][c] = sum_i w_i * feature_i[c]  (pigan_utils.py:255-266)
       for (int o = stid; o < n_valid * kFeat; o += 256) {
-        const int g = o >> 5, c = o & 31, r0 = g * S;
-        float acc = 0.f;
+        const int g = o >> 5, c = o & 31, r0 = g * S, b0 = g * nS;
+        float wsum = 0.f, acc = 0.f, depth = 0.f;
+        for (int i = 0; i < nS; ++i) wsum += sm.w_all[b0 + i];
+        const size_t ro = (size_t)img * p.n_rays + ray0 + g;
         for (int i = 0; i < nS; ++i) {
-          const int id = sm.idx_all[g * nS + i];
+          float w = sm.w_all[b0 + i];
+          if (p.last_back && i == nS - 1) w += 1.f - wsum;
+          const int id = sm.sidx[b0 + i];
           const float f = id < S ? sm.feat_f[r0 + id][c] : sm.feat_c[r0 + id - S][c];
-          acc = fmaf(sm.w_all[g * nS + i], f, acc);
+          acc = fmaf(w, f, acc);
+          if (c == 0) {
+            depth = fmaf(w, sm.skey[b0 + i], depth);
+            if (a.io.weights) a.io.weights[ro * nS + i] = w;
+            if (a.io.dbg_all_z) a.io.dbg_all_z[ro * nS + i] = sm.skey[b0 + i];
+          }
         }
-        if (p.white_back) acc += 1.f - sm.wsum[g];
-        a.io.pixels_fea[((size_t)img * p.n_rays + ray0 + g) * kFeat + c] = acc;
+        if (p.white_back) acc += 1.f - wsum;
+        a.io.pixels_fea[ro * kFeat + c] = acc;
+        if (c == 0 && a.io.depth) a.io.depth[ro] = depth;
       }
       slot_sync();
     }
