@@ -7,7 +7,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libcips3d_b200.so")
+LIB_PATH = os.environ.get("C3D_LIB_PATH", os.path.join(_HERE, "libcips3d_b200.so"))   # override: A/B kernel experiments
 
 IMPL_TC, IMPL_SIMT = 0, 1
 CIPS_MAX_LAYERS = 18

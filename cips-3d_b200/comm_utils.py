@@ -63,8 +63,9 @@ def create_cam2world_matrix(forward_vector, origin, device=None, up_vector=None)
     """Look-at: columns (-left, up, -forward), then translate to origin (comm_utils.py:538-581)."""
     fwd = normalize_vecs(forward_vector)
     n = fwd.shape[0]
-    if up_vector is None:
-        up_vector = torch.tensor([0, 1, 0], dtype=torch.float, device=device).expand_as(fwd)
+    if up_vector is None:      # (0,1,0) built on the device: torch.tensor(list, device='cuda') would synchronise the host
+        up_vector = torch.zeros_like(fwd)
+        up_vector[:, 1] = 1
     left = normalize_vecs(torch.cross(up_vector, fwd, dim=-1))
     up = normalize_vecs(torch.cross(fwd, left, dim=-1))
     rot = torch.eye(4, device=device).unsqueeze(0).repeat(n, 1, 1)

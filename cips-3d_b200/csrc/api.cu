@@ -30,10 +30,26 @@ int c3d_cips_fwd_tc(const C3dCipsParams*, const C3dCipsWeights*, const float*, f
 extern "C" int c3d_version(void) { return 100; }
 extern "C" const char* c3d_last_error(void) { return g_err; }
 
+// cudaGetDeviceProperties costs milliseconds: query each device once (attributes only) and cache.
+static std::atomic<int> g_dev_cc[64];     // 0 = unknown, else major*10+minor
+static std::atomic<int> g_dev_sms[64];
+static void query_device(int dev) {
+  int major = 0, minor = 0, sms = 0;
+  cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev);
+  cudaDeviceGetAttribute(&minor, cudaDevAttrComputeCapabilityMinor, dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  g_dev_sms[dev].store(sms);
+  g_dev_cc[dev].store(major * 10 + minor + 1000);
+}
 extern "C" int c3d_device_supported(int dev) {
-  cudaDeviceProp prop;
-  if (cudaGetDeviceProperties(&prop, dev) != cudaSuccess) return 0;
-  return prop.major == 10 ? 1 : 0;
+  if (dev < 0 || dev >= 64) return 0;
+  if (g_dev_cc[dev].load() == 0) query_device(dev);
+  return (g_dev_cc[dev].load() - 1000) / 10 == 10 ? 1 : 0;
+}
+int c3d_device_sm_count(int dev) {
+  if (dev < 0 || dev >= 64) return 148;
+  if (g_dev_cc[dev].load() == 0) query_device(dev);
+  return g_dev_sms[dev].load();
 }
 
 static int check_ray_args(const C3dRayParams* p, const C3dSirenWeights* w, const C3dRayIO* io) {

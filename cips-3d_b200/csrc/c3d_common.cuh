@@ -31,6 +31,7 @@ void c3d_count_launch();
     C3D_CUDA(cudaGetLastError());  \
   } while (0)
 
+int c3d_device_sm_count(int dev);   // cached (api.cu)
 static inline int c3d_div_up(long long a, long long b) { return (int)((a + b - 1) / b); }
 
 // ---------------------------------------------------------------- PTX wrappers (device)
@@ -71,27 +72,40 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t by
                "r"(bytes)
                : "memory");
 }
+// The suspend-time hint lets a waiting warp sleep in hardware until the phase completes (or the hint
+// expires) instead of re-issuing the probe: spinning waiters otherwise steal issue slots from the warps
+// that share their scheduler (ncu: ~25 % of all executed instructions were wait-loop probes).
+#ifndef C3D_SUSPEND_HINT_NS
+#define C3D_SUSPEND_HINT_NS 20000
+#endif
+constexpr uint32_t kSuspendHintNs = C3D_SUSPEND_HINT_NS;
 __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   uint32_t ok;
   asm volatile(
       "{\n\t.reg .pred P;\n\t"
+#if C3D_SUSPEND_HINT_NS > 0
+      "mbarrier.try_wait.parity.shared::cta.b64 P, [%1], %2, %3;\n\t"
+#else
       "mbarrier.try_wait.parity.shared::cta.b64 P, [%1], %2;\n\t"
+#endif
       "selp.u32 %0, 1, 0, P;\n\t}"
       : "=r"(ok)
-      : "r"(smem_u32(bar)), "r"(parity)
+      : "r"(smem_u32(bar)), "r"(parity), "r"(kSuspendHintNs)
       : "memory");
   return ok != 0;
 }
 // Spin with a watchdog: a protocol bug traps (-> CUDA error at the caller) instead of hanging the GPU.
 #ifndef C3D_WATCHDOG_SPINS
-#define C3D_WATCHDOG_SPINS (1u << 26)
+#define C3D_WATCHDOG_SPINS (1u << 20)   /* x up to 20 us per probe */
 #endif
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
     if (++spins > C3D_WATCHDOG_SPINS) {
+#ifdef C3D_DEBUG_WATCHDOG   // device printf makes every launch of the kernel heavier: debug builds only
       printf("c3d watchdog: mbarrier wait timed out (block %d thread %d bar 0x%x parity %u)\n", (int)blockIdx.x,
              (int)threadIdx.x, smem_u32(bar), parity);
+#endif
       __trap();
     }
   }

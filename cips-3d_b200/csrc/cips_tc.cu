@@ -17,6 +17,8 @@
 // Per-image modulation:  y = ((x * s1p) @ W) * d   (mod_conv_fc.py:452-496 restated, one W for
 // all images).  Only HBM traffic: x (128 B/pixel) in, rgb (12 B/pixel) out; the residual stream
 // of the skip blocks goes through an L2-resident per-CTA scratch (fp32, 256 KB).
+#include <atomic>
+
 #include "c3d_common.cuh"
 
 namespace c3d {
@@ -64,6 +66,11 @@ struct KArgs {
   int B, N, in_dim, n_layers, skip_from, rgb_from, tiles_per_img, total_tiles;
   int layer_tile_off[kMaxLayers + 1];   // offset (in tiles) of each layer's first weight tile
   int layer_kc[kMaxLayers];             // number of K chunks of each layer (1 for the padded input layer)
+  // Issue order of a full layer's 32 weight tiles ("staircase"): entry = kc | nc << 4 | need << 8 where `need`
+  // is the epilogue chunk of the previous layer that must be complete (input K-chunk written, accumulator
+  // columns drained).  Tiles are stored in this order so the producer streams linearly.
+  uint16_t order_full[32];
+  uint16_t order_in[4];
 };
 
 __device__ __forceinline__ uint32_t cluster_ctarank() {
@@ -112,18 +119,20 @@ struct EpiFlags {
   bool add_res, keep_res, do_rgb, last;
 };
 
-// One thread, 16 accumulator columns [c, c+16) of its row.
+// One thread, 16 accumulator columns of its row.  All pointers already address column c:
+//   c0p/c1p: per-layer vectors, rwp: ToRGB weights, xp: the thread's 16-byte slot of K-group c/8 in the A
+//   operand, rp: residual scratch (float4 index c/4, this row).
 //   first layer of a block : a = lrelu(acc) * (d * s_next)                       -> fp16 A operand
 //   second layer of a block: y = lrelu(acc) * d (+ residual); ToRGB += y.Wrgb;   a = y * s_next
 template <bool SECOND>
-__device__ __forceinline__ void epi16(const uint32_t (&acc)[16], const float4 (&rs)[4], const float* __restrict__ c0,
-                                      const float* __restrict__ c1, const float4* __restrict__ rgbw, int c, int row,
-                                      uint8_t* xbuf, float4* resid, const EpiFlags f, float& rgb0, float& rgb1,
-                                      float& rgb2, float* hid_out) {
+__device__ __forceinline__ void epi16(const uint32_t (&acc)[16], const float4 (&rs)[4], const float* __restrict__ c0p,
+                                      const float* __restrict__ c1p, const float4* __restrict__ rwp, uint8_t* xp,
+                                      float4* rp, const EpiFlags f, float& rgb0, float& rgb1, float& rgb2,
+                                      float* hid_out) {
   float y[16];
 #pragma unroll
   for (int g = 0; g < 4; ++g) {
-    const float4 d4 = *reinterpret_cast<const float4*>(c0 + c + 4 * g);
+    const float4 d4 = *reinterpret_cast<const float4*>(c0p + 4 * g);
     y[4 * g + 0] = lrelu02(__uint_as_float(acc[4 * g + 0])) * d4.x;
     y[4 * g + 1] = lrelu02(__uint_as_float(acc[4 * g + 1])) * d4.y;
     y[4 * g + 2] = lrelu02(__uint_as_float(acc[4 * g + 2])) * d4.z;
@@ -138,13 +147,12 @@ __device__ __forceinline__ void epi16(const uint32_t (&acc)[16], const float4 (&
     }
     if (f.keep_res) {
 #pragma unroll
-      for (int g = 0; g < 4; ++g)
-        resid[(size_t)(c / 4 + g) * kTileM + row] = make_float4(y[4 * g], y[4 * g + 1], y[4 * g + 2], y[4 * g + 3]);
+      for (int g = 0; g < 4; ++g) rp[g * kTileM] = make_float4(y[4 * g], y[4 * g + 1], y[4 * g + 2], y[4 * g + 3]);
     }
     if (f.do_rgb) {
 #pragma unroll
       for (int i = 0; i < 16; ++i) {
-        const float4 w4 = rgbw[c + i];
+        const float4 w4 = rwp[i];
         rgb0 = fmaf(y[i], w4.x, rgb0);
         rgb1 = fmaf(y[i], w4.y, rgb1);
         rgb2 = fmaf(y[i], w4.z, rgb2);
@@ -154,21 +162,21 @@ __device__ __forceinline__ void epi16(const uint32_t (&acc)[16], const float4 (&
       if (hid_out) {
 #pragma unroll
         for (int g = 0; g < 4; ++g)
-          reinterpret_cast<float4*>(hid_out + c)[g] = make_float4(y[4 * g], y[4 * g + 1], y[4 * g + 2], y[4 * g + 3]);
+          reinterpret_cast<float4*>(hid_out)[g] = make_float4(y[4 * g], y[4 * g + 1], y[4 * g + 2], y[4 * g + 3]);
       }
       return;
     }
 #pragma unroll
     for (int g = 0; g < 4; ++g) {
-      const float4 s4 = *reinterpret_cast<const float4*>(c1 + c + 4 * g);
+      const float4 s4 = *reinterpret_cast<const float4*>(c1p + 4 * g);
       y[4 * g + 0] *= s4.x; y[4 * g + 1] *= s4.y; y[4 * g + 2] *= s4.z; y[4 * g + 3] *= s4.w;
     }
   }
   uint32_t pk[8];
 #pragma unroll
   for (int g = 0; g < 8; ++g) pk[g] = pack_f16(y[2 * g], y[2 * g + 1]);
-  *reinterpret_cast<uint4*>(xbuf + (size_t)(c / 8) * kLBO + row * 16) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-  *reinterpret_cast<uint4*>(xbuf + (size_t)(c / 8 + 1) * kLBO + row * 16) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+  *reinterpret_cast<uint4*>(xp) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+  *reinterpret_cast<uint4*>(xp + kLBO) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
 }
 
 template <int CL>
@@ -199,10 +207,9 @@ __global__ void __launch_bounds__(kThreads, 1) cips_tc_kernel(const KArgs a) {
   const int L = a.n_layers;
 
   if (warp < 4) {
-    reg_dec<56>();  // 128*32 + 512*112 == 640*96: setmaxnreg only recycles this CTA's own registers
-  if (warp == 0) {
-    // ------------------------------------------------------------ weight producer
-    if (lane == 0) {
+    reg_dec<56>();
+    if (warp == 0) {
+      // ---------------------------------------------------------- weight producer (whole warp converged, one lane issues)
       uint32_t stage = 0, phase = 0;
       for (int it = 0; it < iters; ++it) {
         for (int l = 0; l < L; ++l) {
@@ -210,16 +217,17 @@ __global__ void __launch_bounds__(kThreads, 1) cips_tc_kernel(const KArgs a) {
           const int ntiles = a.layer_kc[l] * 4;
           for (int t = 0; t < ntiles; ++t) {
             mbar_wait(&s.empty[stage], phase ^ 1);
-            mbar_arrive_expect_tx(&s.full[stage], kWTileBytes);
-            load_w_tile<CL>(s.w[stage], src + (size_t)t * kWTileBytes, &s.full[stage], crank);
+            if (elect_one()) {
+              mbar_arrive_expect_tx(&s.full[stage], kWTileBytes);
+              load_w_tile<CL>(s.w[stage], src + (size_t)t * kWTileBytes, &s.full[stage], crank);
+            }
+            __syncwarp();
             if (++stage == kStages) { stage = 0; phase ^= 1; }
           }
         }
       }
-    }
-  } else if (warp == 1) {
-    // ------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
+    } else if (warp == 1) {
+      // ---------------------------------------------------------- MMA issuer (whole warp converged, one lane issues)
       const uint32_t idesc = umma_idesc_f16(kTileM, kNC);
       const uint32_t dhi = umma_desc_hi(kSBO);
       const uint32_t a_lo0 = umma_desc_lo(smem_u32(s.x), kLBO);
@@ -230,35 +238,37 @@ __global__ void __launch_bounds__(kThreads, 1) cips_tc_kernel(const KArgs a) {
       for (int it = 0; it < iters; ++it) {
         for (int l = 0; l < L; ++l) {
           const uint32_t epar = (uint32_t)(it * L + l) & 1u;   // phase of the epilogue that feeds layer l (staging for l = 0)
-          const int nkc = a.layer_kc[l];
+          const int ntiles = a.layer_kc[l] * 4;
+          const uint16_t* order = ntiles == 32 ? a.order_full : a.order_in;
           int waited = -1;
-          for (int kc = 0; kc < nkc; ++kc) {
-            const uint32_t a_lo = a_lo0 + (uint32_t)kc * (kStepK16 * (kKC / 16));
 #pragma unroll 1
-            for (int nc = 0; nc < 4; ++nc) {
-              const int need = max(kc >> 1, nc);       // epilogue chunk that must be complete
-              if (need > waited) {
-                for (int j = waited + 1; j <= need; ++j) mbar_wait(&s.epi_done[j], epar);
-                waited = need;
-                tc_fence_after();
-              }
-              mbar_wait(&s.full[stage], phase);
-              tc_fence_after();
+          for (int t = 0; t < ntiles; ++t) {
+            const uint32_t e = order[t];
+            const uint32_t kc = e & 15u, nc = (e >> 4) & 15u;
+            const int need = (int)(e >> 8);
+            if (need > waited) {
+              for (int j = waited + 1; j <= need; ++j) mbar_wait(&s.epi_done[j], epar);
+              waited = need;
+            }
+            mbar_wait(&s.full[stage], phase);
+            tc_fence_after();
+            if (elect_one()) {
+              const uint32_t a_lo = a_lo0 + kc * (kStepK16 * (kKC / 16));
               const uint32_t b_lo = b_lo0 + stage * kStepStage;
-              const uint32_t d = tmem + (uint32_t)(nc * kNC);
+              const uint32_t d = tmem + nc * kNC;
               umma_ss_w(d, a_lo, b_lo, dhi, idesc, kc != 0);
               umma_ss_w(d, a_lo + kStepK16, b_lo + kStepK16, dhi, idesc, 1);
               umma_ss_w(d, a_lo + 2 * kStepK16, b_lo + 2 * kStepK16, dhi, idesc, 1);
               umma_ss_w(d, a_lo + 3 * kStepK16, b_lo + 3 * kStepK16, dhi, idesc, 1);
               commit_stage_free<CL>(&s.empty[stage]);
-              if (++stage == kStages) { stage = 0; phase ^= 1; }
+              if (t == ntiles - 1) tc_commit(&s.acc_full);
             }
+            __syncwarp();
+            if (++stage == kStages) { stage = 0; phase ^= 1; }
           }
-          tc_commit(&s.acc_full);
         }
       }
     }
-  }
   } else {
     // ------------------------------------------------------------ epilogue warps
     reg_inc<104>();
@@ -326,37 +336,47 @@ __global__ void __launch_bounds__(kThreads, 1) cips_tc_kernel(const KArgs a) {
         mbar_wait(&s.acc_full, (uint32_t)(it * L + l) & 1u);
         tc_fence_after();
         float* hid = (f.last && a.hidden_out && row_ok) ? a.hidden_out + ((size_t)img * a.N + pix) * kH : nullptr;
-        // software pipeline over the 8 x 16-column slices this thread owns (chunk j = i/2)
+        // software pipeline over the 8 x 16-column slices this thread owns (chunk j, halves 0/1);
+        // every address advances by a constant per chunk
         uint32_t accA[16], accB[16];
         float4 rsA[4], rsB[4];
-        auto col_of = [&](int i) { return (i >> 1) * 128 + wg * 32 + (i & 1) * 16; };
-        auto prefetch = [&](int i, uint32_t (&acc)[16], float4 (&rs)[4]) {
-          const int c = col_of(i);
-          tmem_ld16(trow + (uint32_t)c, acc);
-          if (f.add_res) {
+        const int cw = wg * 32;
+        uint32_t tcol = trow + (uint32_t)cw;                    // TMEM column of slice (j, 0)
+        float4* rp = resid + (size_t)(cw / 4) * kTileM + row;   // residual slot of slice (j, 0), g = 0
+        uint8_t* xp = s.x + (size_t)(cw / 8) * kLBO + row * 16;
+        const float* c0p = c0 + cw;
+        const float* c1p = c1 + cw;
+        const float4* rwp = s.rgbw + cw;
+        float* hp = hid ? hid + cw : nullptr;
+        auto load_res = [&](float4 (&rs)[4], const float4* p) {
 #pragma unroll
-            for (int g = 0; g < 4; ++g) rs[g] = resid[(size_t)(c / 4 + g) * kTileM + row];
-          }
+          for (int g = 0; g < 4; ++g) rs[g] = p[g * kTileM];
         };
-        prefetch(0, accA, rsA);
+        tmem_ld16(tcol, accA);
+        if (f.add_res) load_res(rsA, rp);
 #pragma unroll 1
         for (int j = 0; j < 4; ++j) {
           tc_wait_ld();
-          prefetch(2 * j + 1, accB, rsB);
-          if (second) epi16<true>(accA, rsA, c0, c1, s.rgbw, col_of(2 * j), row, s.x, resid, f, rgb0, rgb1, rgb2, hid);
-          else epi16<false>(accA, rsA, c0, c1, s.rgbw, col_of(2 * j), row, s.x, resid, f, rgb0, rgb1, rgb2, hid);
+          tmem_ld16(tcol + 16, accB);
+          if (f.add_res) load_res(rsB, rp + 4 * kTileM);
+          if (second) epi16<true>(accA, rsA, c0p, c1p, rwp, xp, rp, f, rgb0, rgb1, rgb2, hp);
+          else epi16<false>(accA, rsA, c0p, c1p, rwp, xp, rp, f, rgb0, rgb1, rgb2, hp);
           tc_wait_ld();
-          if (j < 3) prefetch(2 * j + 2, accA, rsA);
-          if (second) epi16<true>(accB, rsB, c0, c1, s.rgbw, col_of(2 * j + 1), row, s.x, resid, f, rgb0, rgb1, rgb2, hid);
-          else epi16<false>(accB, rsB, c0, c1, s.rgbw, col_of(2 * j + 1), row, s.x, resid, f, rgb0, rgb1, rgb2, hid);
+          if (j < 3) {
+            tmem_ld16(tcol + 128, accA);
+            if (f.add_res) load_res(rsA, rp + 32 * kTileM);
+          }
+          if (second) epi16<true>(accB, rsB, c0p + 16, c1p + 16, rwp + 16, xp + 2 * kLBO, rp + 4 * kTileM, f, rgb0, rgb1, rgb2, hp ? hp + 16 : nullptr);
+          else epi16<false>(accB, rsB, c0p + 16, c1p + 16, rwp + 16, xp + 2 * kLBO, rp + 4 * kTileM, f, rgb0, rgb1, rgb2, hp ? hp + 16 : nullptr);
           // chunk j of this epilogue is complete for this warp
           fence_proxy_async();
           tc_fence_before();
           __syncwarp();
           if (lane == 0 && !f.last) mbar_arrive(&s.epi_done[j]);
+          tcol += 128; rp += 32 * kTileM; xp += 16 * kLBO; c0p += 128; c1p += 128; rwp += 128;
+          if (hp) hp += 128;
         }
       }
-      // ---- tile output: tanh(sum of ToRGB skips)  (generator.py:1139-1153)
       asm volatile("bar.sync 1, %0;" ::"n"(kNumEpiWarps * 32) : "memory");   // rgbw (aliased) no longer read
       s.rgb_part[wg][row][0] = rgb0;
       s.rgb_part[wg][row][1] = rgb1;
@@ -380,12 +400,26 @@ __global__ void __launch_bounds__(kThreads, 1) cips_tc_kernel(const KArgs a) {
   if (warp == 2) tmem_dealloc<512>(tmem);
 }
 
-// fp32 (in,out) weights -> fp16 UMMA-B tiles: tile (kc,nc) holds B[n][k] = W[kc*64+k][nc*128+n]
-// at byte (n%8)*16 + (n/8)*128 + (k/8)*2048 + (k%8)*2.  Rows k >= in_dim are zero (input layer).
-__global__ void cips_prep_weights_kernel(const float* __restrict__ W, int in_dim, __half* __restrict__ out, int nkc) {
-  const int tile = blockIdx.x;             // kc*4 + nc
-  const int kc = tile >> 2, nc = tile & 3;
-  __half* o = out + (size_t)tile * (kWTileBytes / 2);
+// fp32 (in,out) weights -> fp16 UMMA-B tiles, one launch for all layers.  Block = one 16 KB tile in STREAM
+// order: tile t of layer l is (kc,nc) = order[t]; it holds B[n][k] = W[kc*64+k][nc*128+n] at byte
+// (n%8)*16 + (n/8)*128 + (k/8)*2048 + (k%8)*2.  Rows k >= in_dim are zero (padded input layer).
+struct PrepArgs {
+  const float* w[kMaxLayers];
+  int layer_tile_off[kMaxLayers + 1];
+  int in_dim0, n_layers;
+  uint16_t order_full[32];
+  uint16_t order_in[4];
+};
+__global__ void cips_prep_weights_kernel(const PrepArgs pa, __half* __restrict__ out) {
+  const int gt = blockIdx.x;
+  int l = 0;
+  while (l + 1 < pa.n_layers && gt >= pa.layer_tile_off[l + 1]) ++l;
+  const int t = gt - pa.layer_tile_off[l];
+  const uint32_t e = (pa.layer_tile_off[l + 1] - pa.layer_tile_off[l]) == 32 ? pa.order_full[t] : pa.order_in[t];
+  const int kc = e & 15, nc = (e >> 4) & 15;
+  const int in_dim = l == 0 ? pa.in_dim0 : kH;
+  const float* W = pa.w[l];
+  __half* o = out + (size_t)gt * (kWTileBytes / 2);
   for (int i = threadIdx.x; i < kKC * kNC; i += blockDim.x) {
     const int k = i / kNC, n = i % kNC;    // n fastest -> coalesced reads of W rows
     const int gk = kc * kKC + k;
@@ -423,9 +457,9 @@ using namespace c3d;
 using namespace c3d::cips;
 
 static int cips_grid(const C3dCipsParams* p, int* cl_out) {
-  int dev = 0, sms = 148;
+  int dev = 0;
   cudaGetDevice(&dev);
-  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int sms = c3d_device_sm_count(dev);
   int cl = 1;
   if (const char* e = getenv("C3D_CIPS_CLUSTER")) cl = atoi(e);
   if (cl != 1 && cl != 2 && cl != 4) cl = 1;
@@ -461,7 +495,13 @@ size_t c3d_cips_tc_workspace_bytes(const C3dCipsParams* p) { return cips_ws_layo
 template <int CL>
 static int launch_cips(const KArgs& ka, int grid, cudaStream_t st) {
   const size_t smem = sizeof(Smem) + 1024;
-  C3D_CUDA(cudaFuncSetAttribute(cips_tc_kernel<CL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  static std::atomic<unsigned long long> attr_set{0};     // per device, once
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (!(attr_set.load() >> (dev & 63) & 1ull)) {
+    C3D_CUDA(cudaFuncSetAttribute(cips_tc_kernel<CL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_set.fetch_or(1ull << (dev & 63));
+  }
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(grid);
   cfg.blockDim = dim3(kThreads);
@@ -517,11 +557,29 @@ int c3d_cips_fwd_tc(const C3dCipsParams* p, const C3dCipsWeights* w, const float
     off += ka.layer_kc[l] * 4;
   }
   ka.layer_tile_off[L] = off;
-  // ---- prep: weights -> fp16 tiles, per-image epilogue vectors
-  for (int l = 0; l < L; ++l) {
-    cips_prep_weights_kernel<<<ka.layer_kc[l] * 4, 256, 0, st>>>(
-        w->w[l], l == 0 ? p->in_dim : kH, (__half*)(base + ws.wtiles) + (size_t)ka.layer_tile_off[l] * (kWTileBytes / 2),
-        ka.layer_kc[l]);
+  // ---- staircase issue order (see KArgs::order_full)
+  {
+    bool done[8][4] = {};
+    int n = 0;
+    for (int j = 0; j < 4; ++j)
+      for (int kc = 0; kc < 2 * (j + 1) && kc < 8; ++kc)
+        for (int nc = 0; nc <= j; ++nc)
+          if (!done[kc][nc]) {
+            done[kc][nc] = true;
+            ka.order_full[n++] = (uint16_t)(kc | (nc << 4) | (j << 8));
+          }
+    for (int nc = 0; nc < 4; ++nc) ka.order_in[nc] = (uint16_t)(0 | (nc << 4) | (nc << 8));
+  }
+  // ---- prep: weights -> fp16 tiles (one launch), per-image epilogue vectors
+  {
+    PrepArgs pa = {};
+    for (int l = 0; l < L; ++l) pa.w[l] = w->w[l];
+    for (int l = 0; l <= L; ++l) pa.layer_tile_off[l] = ka.layer_tile_off[l];
+    pa.in_dim0 = p->in_dim;
+    pa.n_layers = L;
+    for (int i = 0; i < 32; ++i) pa.order_full[i] = ka.order_full[i];
+    for (int i = 0; i < 4; ++i) pa.order_in[i] = ka.order_in[i];
+    cips_prep_weights_kernel<<<ka.layer_tile_off[L], 256, 0, st>>>(pa, (__half*)(base + ws.wtiles));
     C3D_LAUNCH_CHECK();
   }
   cips_prep_consts_kernel<<<L + p->n_blocks, 256, 0, st>>>(*w, p->batch, L, p->n_blocks, p->rgb_from,

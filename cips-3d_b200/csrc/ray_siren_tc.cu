@@ -20,6 +20,8 @@
 // (tcgen05.st, two fp16 per 32-bit column, row = lane) and the MMAs use the A-from-TMEM form.
 // Weights (fp16 hi/lo, scaled by 2^8 to keep the lo parts normal) sit in shared memory for the
 // whole kernel (112 KB, loaded once per CTA by bulk async copies).
+#include <atomic>
+
 #include "c3d_common.cuh"
 #include "ray_math.cuh"
 
@@ -162,45 +164,51 @@ __global__ void __launch_bounds__(640, 1) ray_siren_tc_kernel(const KArgs a) {
         for (int off = 0; off < kWBlobBytes; off += 16384) bulk_g2s(s.w + off, a.wblob + off, 16384, &s.w_full);
       }
     } else if (warp == 1) {
-      // ---------------------------------------------------------- MMA issuer: serve whichever slot is ready
-      if (lane == 0) {
-        mbar_wait(&s.w_full, 0);
-        const uint32_t wb = smem_u32(s.w);
-        const uint32_t dhi = umma_desc_hi(128);
-        const uint32_t w1h = umma_desc_lo(wb + kOffW1h, 128 * 16), w1l = umma_desc_lo(wb + kOffW1l, 128 * 16);
-        const uint32_t w2h = umma_desc_lo(wb + kOffW2h, kN2 * 16), w2l = umma_desc_lo(wb + kOffW2l, kN2 * 16);
-        const uint32_t w3h = umma_desc_lo(wb + kOffW3h, 32 * 16), w3l = umma_desc_lo(wb + kOffW3l, 32 * 16);
-        uint32_t par[2] = {0, 0};
-        int done[2] = {0, 0};
-        const int total = iters * mma_phases;
-        uint32_t idle = 0;
-        while (done[0] < total || done[1] < total) {
-          if (++idle > (1u << 28)) {
-            printf("c3d watchdog: ray MMA issuer starved (block %d, done %d/%d of %d)\n", (int)blockIdx.x, done[0], done[1], total);
-            __trap();
-          }
+      // ---------------------------------------------------------- MMA issuer: the whole warp stays converged
+      // (operands live in uniform registers, no per-MMA lane loop); one elected lane issues for whichever slot
+      // is ready.
+      mbar_wait(&s.w_full, 0);
+      const uint32_t wb = smem_u32(s.w);
+      const uint32_t dhi = umma_desc_hi(128);
+      const uint32_t w1h = umma_desc_lo(wb + kOffW1h, 128 * 16), w1l = umma_desc_lo(wb + kOffW1l, 128 * 16);
+      const uint32_t w2h = umma_desc_lo(wb + kOffW2h, kN2 * 16), w2l = umma_desc_lo(wb + kOffW2l, kN2 * 16);
+      const uint32_t w3h = umma_desc_lo(wb + kOffW3h, 32 * 16), w3l = umma_desc_lo(wb + kOffW3l, 32 * 16);
+      uint32_t par[2] = {0, 0};
+      int done[2] = {0, 0};
+      const int total = iters * mma_phases;
+      uint32_t idle = 0;
+      while (done[0] < total || done[1] < total) {
+        if (++idle > (1u << 28)) {
+#ifdef C3D_DEBUG_WATCHDOG
+          if (lane == 0) printf("c3d watchdog: ray MMA issuer starved (block %d, done %d/%d of %d)\n", (int)blockIdx.x, done[0], done[1], total);
+#endif
+          __trap();
+        }
 #pragma unroll
-          for (int sl = 0; sl < 2; ++sl) {
-            if (done[sl] < total && mbar_test(&s.a_ready[sl], par[sl])) {
-              par[sl] ^= 1;
-              tc_fence_after();
-              const uint32_t a_hi = tmem + (uint32_t)(sl * 256), a_lo = a_hi + 64, d = a_hi + 128;
-              const int layer = done[sl] % 3;
-              // opaque per-iteration copies: keeps the compiler from hoisting 50+ loop-invariant
-              // descriptor words out of the loop (they would spill and cost an LDL per MMA)
+        for (int sl = 0; sl < 2; ++sl) {
+          if (done[sl] < total && __all_sync(0xffffffffu, mbar_test(&s.a_ready[sl], par[sl]))) {
+            par[sl] ^= 1;
+            tc_fence_after();
+            const int layer = done[sl] % 3;
+            if (elect_one()) {
+              uint32_t a_hi = tmem + (uint32_t)(sl * 256), a_lo = a_hi + 64;
+              const uint32_t d = a_hi + 128;
+              // opaque per-iteration copies: keeps the compiler from hoisting ~60 loop-invariant descriptor
+              // words out of the loop (they would spill and cost an LDL per MMA)
               uint32_t bh = layer == 0 ? w1h : (layer == 1 ? w2h : w3h);
               uint32_t bl = layer == 0 ? w1l : (layer == 1 ? w2l : w3l);
-              uint32_t ah = a_hi, al = a_lo;
-              asm volatile("" : "+r"(bh), "+r"(bl), "+r"(ah), "+r"(al));
-              if (layer == 0) mma_split3<128, 128>(d, ah, al, bh, bl, dhi);
-              else if (layer == 1) mma_split3<kN2, 128>(d, ah, al, bh, bl, dhi);
-              else mma_split3<32, 64>(d, ah, al, bh, bl, dhi);
+              asm volatile("" : "+r"(bh), "+r"(bl), "+r"(a_hi), "+r"(a_lo));
+              if (layer == 0) mma_split3<128, 128>(d, a_hi, a_lo, bh, bl, dhi);
+              else if (layer == 1) mma_split3<kN2, 128>(d, a_hi, a_lo, bh, bl, dhi);
+              else mma_split3<32, 64>(d, a_hi, a_lo, bh, bl, dhi);
               tc_commit(&s.d_ready[sl]);
-              ++done[sl];
-              idle = 0;
             }
+            __syncwarp();
+            ++done[sl];
+            idle = 0;
           }
         }
+        if (idle) __nanosleep(64);   // nothing ready: yield the issue port to the workers on this scheduler
       }
     }
   } else {
@@ -375,8 +383,9 @@ __global__ void __launch_bounds__(640, 1) ray_siren_tc_kernel(const KArgs a) {
             float sum = 0.f;
             for (int j = 0; j < S - 2; ++j) sum += __fadd_rn(__fadd_rn(sm.wc[r0 + j + 1], 1e-5f), 1e-5f);
             float c = 0.f;
+            const float inv = __fdividef(1.f, sum);      // pdf_j = wt_j / sum (1-2 ulp; cdf only feeds a 2e-4-conditioned inverse)
             for (int j = 0; j < s_row; ++j)
-              c = __fadd_rn(c, __fdiv_rn(__fadd_rn(__fadd_rn(sm.wc[r0 + j + 1], 1e-5f), 1e-5f), sum));
+              c = __fadd_rn(c, __fmul_rn(__fadd_rn(__fadd_rn(sm.wc[r0 + j + 1], 1e-5f), 1e-5f), inv));
             sm.cdf[r0 + s_row] = c;
           }
           slot_sync();
@@ -519,13 +528,13 @@ int c3d_ray_siren_fwd_tc(const C3dRayParams* p, const C3dSirenWeights* w, const 
     c3d_set_error("ray_siren(tc): workspace too small (%zu < %zu)", workspace_bytes, ws.total);
     return C3D_EWORKSPACE;
   }
-  int dev = 0, sms = 148;
+  int dev = 0;
   cudaGetDevice(&dev);
   if (!c3d_device_supported(dev)) {
     c3d_set_error("ray_siren(tc): device %d is not sm_100 (tcgen05 required)", dev);
     return C3D_EARCH;
   }
-  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int sms = c3d_device_sm_count(dev);
   uint8_t* base = (uint8_t*)workspace;
   ray_prep_kernel<<<64, 256, 0, st>>>(*w, p->batch, base + ws.blob, (ImgConsts*)(base + ws.consts));
   C3D_LAUNCH_CHECK();
@@ -540,7 +549,11 @@ int c3d_ray_siren_fwd_tc(const C3dRayParams* p, const C3dSirenWeights* w, const 
   ka.total_groups = p->batch * ka.groups_per_img;
   ka.b_sigma = w->b_sigma;
   const size_t smem = sizeof(Smem) + 1024;
-  C3D_CUDA(cudaFuncSetAttribute(ray_siren_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  static std::atomic<unsigned long long> attr_set{0};     // per device, once
+  if (!(attr_set.load() >> (dev & 63) & 1ull)) {
+    C3D_CUDA(cudaFuncSetAttribute(ray_siren_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_set.fetch_or(1ull << (dev & 63));
+  }
   int grid = (ka.total_groups + 1) / 2;
   if (grid > sms) grid = sms;
   if (grid < 1) grid = 1;
