@@ -82,6 +82,8 @@ def load():
                                  C.c_float, C.c_float, _fp]
     lib.c3d_upfirdn2d.argtypes = [_fp, _fp, _fp] + [C.c_int32] * 13 + [_fp]
     lib.c3d_selftest_umma.argtypes = [_fp, _fp, _fp, C.c_int32, C.c_int32, C.c_int32, _fp]
+    if hasattr(lib, 'c3d_debug_cips_trace'):      # only in -DC3D_TRACE debug builds
+        lib.c3d_debug_cips_trace.argtypes = [C.c_void_p, C.c_int]
     _lib = lib
     return lib
 

@@ -14,8 +14,10 @@
 //     fp16 pack -> shared memory).  The next layer's MMAs start as soon as the epilogue has
 //     produced the K-chunks / drained the accumulator columns they touch ("chase"), so the
 //     tensor pipe idles only for the first quarter of each epilogue.
-// Per-image modulation:  y = ((x * s1p) @ W) * d   (mod_conv_fc.py:452-496 restated, one W for
-// all images).  Only HBM traffic: x (128 B/pixel) in, rgb (12 B/pixel) out; the residual stream
+// Per-image modulation (mod_conv_fc.py:452-496): the prep kernel builds, once per forward and per image,
+// fp16 tiles of  W''[k][n] = s1p[k] * W[k][n] * d[n]  (the reference's modulated + demodulated weight);
+// all 512 pixel tiles of an image stream the same 9.3 MB, so the epilogue needs no per-column constants
+// (they would have to come from shared memory, whose bandwidth the MMA operand fetch already saturates).  Only HBM traffic: x (128 B/pixel) in, rgb (12 B/pixel) out; the residual stream
 // of the skip blocks goes through an L2-resident per-CTA scratch (fp32, 256 KB).
 #include <atomic>
 
@@ -40,7 +42,6 @@ constexpr int kMaxLayers = C3D_CIPS_MAX_LAYERS;
 struct Smem {
   alignas(1024) uint8_t x[kXBytes];
   alignas(1024) uint8_t w[kStages][kWTileBytes];
-  alignas(16) float cvec[2][2][kH];      // per-layer epilogue vectors, double-buffered across layers
   union {                                // ToRGB weights of the current block / per-tile rgb partial sums
     float4 rgbw[kH];
     float rgb_part[4][kTileM][4];
@@ -56,10 +57,8 @@ struct KArgs {
   const float* x;            // (B,N,in_dim)
   float* rgb;                // (B,N,3)
   float* hidden_out;         // (B,N,512) or null
-  const __half* wtiles;      // prepped weights: layer-major, [kc][nc][16 KB tile]
-  const float* demod;        // (L,B,512)
-  const float* next_scale;   // (L,B,512): s1p of layer l+1 (ones for the last)
-  const float* in_scale;     // (B,in_dim): s1p of layer 0
+  const __half* wtiles;      // prepped weights: image-major, then layer-major, tiles in stream order (16 KB each)
+  size_t img_tile_stride;    // tiles per image
   const float4* rgbw;        // (n_blocks,512) float4 (w0,w1,w2,0) ; valid for blocks >= rgb_from
   const float* rgbb;         // (3) summed ToRGB biases
   float4* resid;             // (gridDim.x, 128, 128) float4 scratch
@@ -71,6 +70,7 @@ struct KArgs {
   // columns drained).  Tiles are stored in this order so the producer streams linearly.
   uint16_t order_full[32];
   uint16_t order_in[4];
+  int last_full[2], last_in[2];         // index of the last tile each issuer owns (nc>>1 == issuer)
 };
 
 __device__ __forceinline__ uint32_t cluster_ctarank() {
@@ -110,6 +110,20 @@ __device__ __forceinline__ void load_w_tile(void* dst, const uint8_t* src, uint6
 
 __device__ __forceinline__ float lrelu02(float v) { return fmaxf(v, 0.2f * v); }
 
+#ifdef C3D_TRACE   // debug build: block 0 stamps pipeline events of tile iteration 1 (steady state)
+__device__ unsigned long long g_trace[8192];
+__device__ unsigned int g_trace_n;
+__device__ __forceinline__ void trace_ev(int it, uint32_t tag, uint32_t a0) {
+  if (blockIdx.x == 0 && it == 1) {
+    unsigned int i = atomicAdd(&g_trace_n, 1u);
+    if (i < 8192) g_trace[i] = ((unsigned long long)tag << 56) | ((unsigned long long)(a0 & 0xFFFF) << 40) | (clock64() & 0xFFFFFFFFFFull);
+  }
+}
+#define TRACE(it, tag, a0) trace_ev(it, tag, a0)
+#else
+#define TRACE(it, tag, a0)
+#endif
+
 template <int N>
 __device__ __forceinline__ void reg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
 template <int N>
@@ -119,25 +133,18 @@ struct EpiFlags {
   bool add_res, keep_res, do_rgb, last;
 };
 
-// One thread, 16 accumulator columns of its row.  All pointers already address column c:
-//   c0p/c1p: per-layer vectors, rwp: ToRGB weights, xp: the thread's 16-byte slot of K-group c/8 in the A
-//   operand, rp: residual scratch (float4 index c/4, this row).
-//   first layer of a block : a = lrelu(acc) * (d * s_next)                       -> fp16 A operand
-//   second layer of a block: y = lrelu(acc) * d (+ residual); ToRGB += y.Wrgb;   a = y * s_next
+// One thread, 16 accumulator columns of its row (the per-image scales are already inside the weights).
+//   rwp: ToRGB weights of column c; xp: the thread's 16-byte slot of K-group c/8 in the A operand;
+//   rp: residual scratch (float4 index c/4, this row).
+//   first layer of a block : a = lrelu(acc)
+//   second layer of a block: y = lrelu(acc) (+ residual); ToRGB += y.Wrgb; a = y
 template <bool SECOND>
-__device__ __forceinline__ void epi16(const uint32_t (&acc)[16], const float4 (&rs)[4], const float* __restrict__ c0p,
-                                      const float* __restrict__ c1p, const float4* __restrict__ rwp, uint8_t* xp,
-                                      float4* rp, const EpiFlags f, float& rgb0, float& rgb1, float& rgb2,
+__device__ __forceinline__ void epi16(const uint32_t (&acc)[16], const float4 (&rs)[4], const float4* __restrict__ rwp,
+                                      uint8_t* xp, float4* rp, const EpiFlags f, float& rgb0, float& rgb1, float& rgb2,
                                       float* hid_out) {
   float y[16];
 #pragma unroll
-  for (int g = 0; g < 4; ++g) {
-    const float4 d4 = *reinterpret_cast<const float4*>(c0p + 4 * g);
-    y[4 * g + 0] = lrelu02(__uint_as_float(acc[4 * g + 0])) * d4.x;
-    y[4 * g + 1] = lrelu02(__uint_as_float(acc[4 * g + 1])) * d4.y;
-    y[4 * g + 2] = lrelu02(__uint_as_float(acc[4 * g + 2])) * d4.z;
-    y[4 * g + 3] = lrelu02(__uint_as_float(acc[4 * g + 3])) * d4.w;
-  }
+  for (int i = 0; i < 16; ++i) y[i] = lrelu02(__uint_as_float(acc[i]));
   if (SECOND) {
     if (f.add_res) {
 #pragma unroll
@@ -166,11 +173,6 @@ __device__ __forceinline__ void epi16(const uint32_t (&acc)[16], const float4 (&
       }
       return;
     }
-#pragma unroll
-    for (int g = 0; g < 4; ++g) {
-      const float4 s4 = *reinterpret_cast<const float4*>(c1p + 4 * g);
-      y[4 * g + 0] *= s4.x; y[4 * g + 1] *= s4.y; y[4 * g + 2] *= s4.z; y[4 * g + 3] *= s4.w;
-    }
   }
   uint32_t pk[8];
 #pragma unroll
@@ -193,7 +195,7 @@ __global__ void __launch_bounds__(kThreads, 1) cips_tc_kernel(const KArgs a) {
       mbar_init(&s.empty[i], CL);
     }
     for (int i = 0; i < 4; ++i) mbar_init(&s.epi_done[i], kNumEpiWarps);
-    mbar_init(&s.acc_full, 1);
+    mbar_init(&s.acc_full, 2);   // two MMA issuer warps, each commits once per layer
     fence_mbar_init();
   }
   if (warp == 2) tmem_alloc<512>(&s.tmem_base);
@@ -212,8 +214,11 @@ __global__ void __launch_bounds__(kThreads, 1) cips_tc_kernel(const KArgs a) {
       // ---------------------------------------------------------- weight producer (whole warp converged, one lane issues)
       uint32_t stage = 0, phase = 0;
       for (int it = 0; it < iters; ++it) {
+        const int tile = it * (int)gridDim.x + (int)blockIdx.x;
+        const int img = tile < a.total_tiles ? tile / a.tiles_per_img : 0;     // dummy tiles stream image 0
         for (int l = 0; l < L; ++l) {
-          const uint8_t* src = reinterpret_cast<const uint8_t*>(a.wtiles) + (size_t)a.layer_tile_off[l] * kWTileBytes;
+          const uint8_t* src = reinterpret_cast<const uint8_t*>(a.wtiles) +
+                               ((size_t)img * a.img_tile_stride + (size_t)a.layer_tile_off[l]) * kWTileBytes;
           const int ntiles = a.layer_kc[l] * 4;
           for (int t = 0; t < ntiles; ++t) {
             mbar_wait(&s.empty[stage], phase ^ 1);
@@ -226,8 +231,12 @@ __global__ void __launch_bounds__(kThreads, 1) cips_tc_kernel(const KArgs a) {
           }
         }
       }
-    } else if (warp == 1) {
-      // ---------------------------------------------------------- MMA issuer (whole warp converged, one lane issues)
+    } else if (warp == 1 || warp == 3) {
+      // ---------------------------------------------------------- MMA issuers (whole warp converged, one lane issues).
+      // Two issuer warps share the weight ring: issuer i owns accumulator column blocks nc = 2i, 2i+1 (disjoint
+      // TMEM columns, so the two instruction streams never touch the same accumulator) -- one thread alone
+      // cannot issue 4 MMAs + bookkeeping inside the 256 clk a tile occupies the tensor pipe.
+      const uint32_t me = warp == 1 ? 0u : 1u;
       const uint32_t idesc = umma_idesc_f16(kTileM, kNC);
       const uint32_t dhi = umma_desc_hi(kSBO);
       const uint32_t a_lo0 = umma_desc_lo(smem_u32(s.x), kLBO);
@@ -239,31 +248,38 @@ __global__ void __launch_bounds__(kThreads, 1) cips_tc_kernel(const KArgs a) {
         for (int l = 0; l < L; ++l) {
           const uint32_t epar = (uint32_t)(it * L + l) & 1u;   // phase of the epilogue that feeds layer l (staging for l = 0)
           const int ntiles = a.layer_kc[l] * 4;
-          const uint16_t* order = ntiles == 32 ? a.order_full : a.order_in;
+          const bool full_layer = ntiles == 32;
+          const uint16_t* order = full_layer ? a.order_full : a.order_in;
+          const int my_last = full_layer ? a.last_full[me] : a.last_in[me];
           int waited = -1;
 #pragma unroll 1
           for (int t = 0; t < ntiles; ++t) {
             const uint32_t e = order[t];
             const uint32_t kc = e & 15u, nc = (e >> 4) & 15u;
-            const int need = (int)(e >> 8);
-            if (need > waited) {
-              for (int j = waited + 1; j <= need; ++j) mbar_wait(&s.epi_done[j], epar);
-              waited = need;
+            if ((nc >> 1) == me) {
+              const int need = (int)(e >> 8);
+              if (lane == 0) TRACE(it, 1 + me, (uint32_t)(l << 8 | t));          // tile reached
+              if (need > waited) {
+                for (int j = waited + 1; j <= need; ++j) mbar_wait(&s.epi_done[j], epar);
+                waited = need;
+              }
+              if (lane == 0) TRACE(it, 3 + me, (uint32_t)(l << 8 | t));          // epilogue dependency satisfied
+              mbar_wait(&s.full[stage], phase);
+              if (lane == 0) TRACE(it, 5 + me, (uint32_t)(l << 8 | t));          // weight tile landed
+              tc_fence_after();
+              if (elect_one()) {
+                const uint32_t a_lo = a_lo0 + kc * (kStepK16 * (kKC / 16));
+                const uint32_t b_lo = b_lo0 + stage * kStepStage;
+                const uint32_t d = tmem + nc * kNC;
+                umma_ss_w(d, a_lo, b_lo, dhi, idesc, kc != 0);
+                umma_ss_w(d, a_lo + kStepK16, b_lo + kStepK16, dhi, idesc, 1);
+                umma_ss_w(d, a_lo + 2 * kStepK16, b_lo + 2 * kStepK16, dhi, idesc, 1);
+                umma_ss_w(d, a_lo + 3 * kStepK16, b_lo + 3 * kStepK16, dhi, idesc, 1);
+                commit_stage_free<CL>(&s.empty[stage]);
+                if (t == my_last) tc_commit(&s.acc_full);
+              }
+              __syncwarp();
             }
-            mbar_wait(&s.full[stage], phase);
-            tc_fence_after();
-            if (elect_one()) {
-              const uint32_t a_lo = a_lo0 + kc * (kStepK16 * (kKC / 16));
-              const uint32_t b_lo = b_lo0 + stage * kStepStage;
-              const uint32_t d = tmem + nc * kNC;
-              umma_ss_w(d, a_lo, b_lo, dhi, idesc, kc != 0);
-              umma_ss_w(d, a_lo + kStepK16, b_lo + kStepK16, dhi, idesc, 1);
-              umma_ss_w(d, a_lo + 2 * kStepK16, b_lo + 2 * kStepK16, dhi, idesc, 1);
-              umma_ss_w(d, a_lo + 3 * kStepK16, b_lo + 3 * kStepK16, dhi, idesc, 1);
-              commit_stage_free<CL>(&s.empty[stage]);
-              if (t == ntiles - 1) tc_commit(&s.acc_full);
-            }
-            __syncwarp();
             if (++stage == kStages) { stage = 0; phase ^= 1; }
           }
         }
@@ -296,8 +312,8 @@ __global__ void __launch_bounds__(kThreads, 1) cips_tc_kernel(const KArgs a) {
             float v0 = 0.f, v1 = 0.f;
             if (row_ok && k < a.in_dim) {
               const float* xp = a.x + ((size_t)img * a.N + pix) * a.in_dim;
-              v0 = xp[k] * __ldg(a.in_scale + (size_t)img * a.in_dim + k);
-              if (k + 1 < a.in_dim) v1 = xp[k + 1] * __ldg(a.in_scale + (size_t)img * a.in_dim + k + 1);
+              v0 = xp[k];
+              if (k + 1 < a.in_dim) v1 = xp[k + 1];
             }
             pk[j] = pack_f16(v0, v1);
           }
@@ -321,19 +337,12 @@ __global__ void __launch_bounds__(kThreads, 1) cips_tc_kernel(const KArgs a) {
         f.add_res = second && blk >= a.skip_from && blk >= 1;      // block input dim == 512 for blk >= 1
         f.keep_res = second && (blk + 1 >= a.skip_from) && !f.last;  // the next block adds this output
         f.do_rgb = second && blk >= a.rgb_from;
-        // stage this layer's per-image vectors (and ToRGB weights) in shared memory while the MMAs run
-        float* c0 = s.cvec[l & 1][0];
-        float* c1 = s.cvec[l & 1][1];
-        {
-          const int t = (int)threadIdx.x - 128;   // 0..511
-          const float dv = __ldg(a.demod + ((size_t)l * a.B + img) * kH + t);
-          const float sv = __ldg(a.next_scale + ((size_t)l * a.B + img) * kH + t);
-          c0[t] = second ? dv : dv * sv;
-          c1[t] = sv;
-          if (f.do_rgb) s.rgbw[t] = __ldg(a.rgbw + (size_t)blk * kH + t);
+        if (f.do_rgb) {   // ToRGB weights of this block -> shared memory (overlaps the MMAs)
+          s.rgbw[(int)threadIdx.x - 128] = __ldg(a.rgbw + (size_t)blk * kH + ((int)threadIdx.x - 128));
+          asm volatile("bar.sync 1, %0;" ::"n"(kNumEpiWarps * 32) : "memory");
         }
-        asm volatile("bar.sync 1, %0;" ::"n"(kNumEpiWarps * 32) : "memory");
         mbar_wait(&s.acc_full, (uint32_t)(it * L + l) & 1u);
+        if (threadIdx.x == 128) TRACE(it, 8, (uint32_t)(l << 8));               // accumulator complete
         tc_fence_after();
         float* hid = (f.last && a.hidden_out && row_ok) ? a.hidden_out + ((size_t)img * a.N + pix) * kH : nullptr;
         // software pipeline over the 8 x 16-column slices this thread owns (chunk j, halves 0/1);
@@ -344,8 +353,6 @@ __global__ void __launch_bounds__(kThreads, 1) cips_tc_kernel(const KArgs a) {
         uint32_t tcol = trow + (uint32_t)cw;                    // TMEM column of slice (j, 0)
         float4* rp = resid + (size_t)(cw / 4) * kTileM + row;   // residual slot of slice (j, 0), g = 0
         uint8_t* xp = s.x + (size_t)(cw / 8) * kLBO + row * 16;
-        const float* c0p = c0 + cw;
-        const float* c1p = c1 + cw;
         const float4* rwp = s.rgbw + cw;
         float* hp = hid ? hid + cw : nullptr;
         auto load_res = [&](float4 (&rs)[4], const float4* p) {
@@ -359,21 +366,22 @@ __global__ void __launch_bounds__(kThreads, 1) cips_tc_kernel(const KArgs a) {
           tc_wait_ld();
           tmem_ld16(tcol + 16, accB);
           if (f.add_res) load_res(rsB, rp + 4 * kTileM);
-          if (second) epi16<true>(accA, rsA, c0p, c1p, rwp, xp, rp, f, rgb0, rgb1, rgb2, hp);
-          else epi16<false>(accA, rsA, c0p, c1p, rwp, xp, rp, f, rgb0, rgb1, rgb2, hp);
+          if (second) epi16<true>(accA, rsA, rwp, xp, rp, f, rgb0, rgb1, rgb2, hp);
+          else epi16<false>(accA, rsA, rwp, xp, rp, f, rgb0, rgb1, rgb2, hp);
           tc_wait_ld();
           if (j < 3) {
             tmem_ld16(tcol + 128, accA);
             if (f.add_res) load_res(rsA, rp + 32 * kTileM);
           }
-          if (second) epi16<true>(accB, rsB, c0p + 16, c1p + 16, rwp + 16, xp + 2 * kLBO, rp + 4 * kTileM, f, rgb0, rgb1, rgb2, hp ? hp + 16 : nullptr);
-          else epi16<false>(accB, rsB, c0p + 16, c1p + 16, rwp + 16, xp + 2 * kLBO, rp + 4 * kTileM, f, rgb0, rgb1, rgb2, hp ? hp + 16 : nullptr);
+          if (second) epi16<true>(accB, rsB, rwp + 16, xp + 2 * kLBO, rp + 4 * kTileM, f, rgb0, rgb1, rgb2, hp ? hp + 16 : nullptr);
+          else epi16<false>(accB, rsB, rwp + 16, xp + 2 * kLBO, rp + 4 * kTileM, f, rgb0, rgb1, rgb2, hp ? hp + 16 : nullptr);
           // chunk j of this epilogue is complete for this warp
           fence_proxy_async();
           tc_fence_before();
           __syncwarp();
           if (lane == 0 && !f.last) mbar_arrive(&s.epi_done[j]);
-          tcol += 128; rp += 32 * kTileM; xp += 16 * kLBO; c0p += 128; c1p += 128; rwp += 128;
+          if (lane == 0) TRACE(it, 9, (uint32_t)(l << 8 | (warp - 4) << 2 | j));   // warp finished chunk j
+          tcol += 128; rp += 32 * kTileM; xp += 16 * kLBO; rwp += 128;
           if (hp) hp += 128;
         }
       }
@@ -405,13 +413,16 @@ __global__ void __launch_bounds__(kThreads, 1) cips_tc_kernel(const KArgs a) {
 // (n%8)*16 + (n/8)*128 + (k/8)*2048 + (k%8)*2.  Rows k >= in_dim are zero (padded input layer).
 struct PrepArgs {
   const float* w[kMaxLayers];
+  const float* s1p[kMaxLayers];     // (B,in_l)
+  const float* demod[kMaxLayers];   // (B,512)
   int layer_tile_off[kMaxLayers + 1];
-  int in_dim0, n_layers;
+  int in_dim0, n_layers, B;
   uint16_t order_full[32];
   uint16_t order_in[4];
 };
+// grid = (tiles per image, B): block = one 16 KB tile of one image, in STREAM order
 __global__ void cips_prep_weights_kernel(const PrepArgs pa, __half* __restrict__ out) {
-  const int gt = blockIdx.x;
+  const int gt = blockIdx.x, b = blockIdx.y;
   int l = 0;
   while (l + 1 < pa.n_layers && gt >= pa.layer_tile_off[l + 1]) ++l;
   const int t = gt - pa.layer_tile_off[l];
@@ -419,34 +430,27 @@ __global__ void cips_prep_weights_kernel(const PrepArgs pa, __half* __restrict__
   const int kc = e & 15, nc = (e >> 4) & 15;
   const int in_dim = l == 0 ? pa.in_dim0 : kH;
   const float* W = pa.w[l];
-  __half* o = out + (size_t)gt * (kWTileBytes / 2);
+  const float* sv = pa.s1p[l] + (size_t)b * in_dim;
+  const float* dv = pa.demod[l] + (size_t)b * kH + nc * kNC;
+  __half* o = out + ((size_t)b * pa.layer_tile_off[pa.n_layers] + gt) * (kWTileBytes / 2);
   for (int i = threadIdx.x; i < kKC * kNC; i += blockDim.x) {
     const int k = i / kNC, n = i % kNC;    // n fastest -> coalesced reads of W rows
     const int gk = kc * kKC + k;
-    const float v = gk < in_dim ? W[(size_t)gk * kH + nc * kNC + n] : 0.f;
+    const float v = gk < in_dim ? (sv[gk] * W[(size_t)gk * kH + nc * kNC + n]) * dv[n] : 0.f;
     o[((n % 8) * 16 + (n / 8) * 128 + (k / 8) * kLBO) / 2 + (k % 8)] = __float2half_rn(v);
   }
 }
 
-// per-(layer,image) epilogue vectors + packed ToRGB weights
-__global__ void cips_prep_consts_kernel(C3dCipsWeights w, int B, int L, int n_blocks, int rgb_from, float* demod,
-                                        float* next_scale, float4* rgbw, float* rgbb) {
-  const int l = blockIdx.x;
-  if (l < L) {
-    for (int i = threadIdx.x; i < B * kH; i += blockDim.x) {
-      demod[(size_t)l * B * kH + i] = w.demod[l][i];
-      next_scale[(size_t)l * B * kH + i] = (l + 1 < L) ? w.style1p[l + 1][i] : 1.f;
-    }
-  } else {
-    const int blk = l - L;
-    if (blk < n_blocks && blk >= rgb_from)
-      for (int n = threadIdx.x; n < kH; n += blockDim.x)
-        rgbw[(size_t)blk * kH + n] = make_float4(w.rgb_w[blk][n], w.rgb_w[blk][kH + n], w.rgb_w[blk][2 * kH + n], 0.f);
-    if (blk == 0 && threadIdx.x < 3) {
-      float sacc = 0.f;
-      for (int b = rgb_from; b < n_blocks; ++b) sacc += w.rgb_b[b][threadIdx.x];   // same order as the reference's skip chain
-      rgbb[threadIdx.x] = sacc;
-    }
+// packed ToRGB weights + summed biases
+__global__ void cips_prep_consts_kernel(C3dCipsWeights w, int n_blocks, int rgb_from, float4* rgbw, float* rgbb) {
+  const int blk = blockIdx.x;
+  if (blk < n_blocks && blk >= rgb_from)
+    for (int n = threadIdx.x; n < kH; n += blockDim.x)
+      rgbw[(size_t)blk * kH + n] = make_float4(w.rgb_w[blk][n], w.rgb_w[blk][kH + n], w.rgb_w[blk][2 * kH + n], 0.f);
+  if (blk == 0 && threadIdx.x < 3) {
+    float sacc = 0.f;
+    for (int b = rgb_from; b < n_blocks; ++b) sacc += w.rgb_b[b][threadIdx.x];   // same order as the reference's skip chain
+    rgbb[threadIdx.x] = sacc;
   }
 }
 
@@ -473,24 +477,36 @@ static int cips_grid(const C3dCipsParams* p, int* cl_out) {
 }
 
 struct CipsWs {
-  size_t wtiles, demod, next_scale, rgbw, rgbb, resid, total;
+  size_t wtiles, rgbw, rgbb, resid, total;
 };
 static CipsWs cips_ws_layout(const C3dCipsParams* p) {
   CipsWs o;
   const int L = 2 * p->n_blocks;
   size_t off = 0;
   auto take = [&](size_t bytes) { size_t r = off; off += (bytes + 255) / 256 * 256; return r; };
-  o.wtiles = take((size_t)(4 + (L - 1) * 32) * kWTileBytes);
-  o.demod = take((size_t)L * p->batch * kH * 4);
-  o.next_scale = take((size_t)L * p->batch * kH * 4);
+  o.wtiles = take((size_t)(p->batch > 0 ? p->batch : 1) * (4 + (L - 1) * 32) * kWTileBytes);   // per image
   o.rgbw = take((size_t)p->n_blocks * kH * 16);
   o.rgbb = take(16);
-  o.resid = take((size_t)148 * 2 * (kH / 4) * kTileM * 16);
+  o.resid = take((size_t)160 * (kH / 4) * kTileM * 16);
   o.total = off;
   return o;
 }
 
 size_t c3d_cips_tc_workspace_bytes(const C3dCipsParams* p) { return cips_ws_layout(p).total; }
+
+#ifdef C3D_TRACE
+extern "C" int c3d_debug_cips_trace(unsigned long long* out, int cap) {
+  unsigned int n = 0;
+  cudaDeviceSynchronize();
+  cudaMemcpyFromSymbol(&n, c3d::cips::g_trace_n, sizeof(n));
+  if ((int)n > cap) n = cap;
+  if (n > 8192) n = 8192;
+  cudaMemcpyFromSymbol(out, c3d::cips::g_trace, n * sizeof(unsigned long long));
+  unsigned int zero = 0;
+  cudaMemcpyToSymbol(c3d::cips::g_trace_n, &zero, sizeof(zero));
+  return (int)n;
+}
+#endif
 
 template <int CL>
 static int launch_cips(const KArgs& ka, int grid, cudaStream_t st) {
@@ -540,9 +556,6 @@ int c3d_cips_fwd_tc(const C3dCipsParams* p, const C3dCipsWeights* w, const float
   KArgs ka = {};
   ka.x = x; ka.rgb = rgb; ka.hidden_out = hidden_out;
   ka.wtiles = (const __half*)(base + ws.wtiles);
-  ka.demod = (const float*)(base + ws.demod);
-  ka.next_scale = (const float*)(base + ws.next_scale);
-  ka.in_scale = w->style1p[0];
   ka.rgbw = (const float4*)(base + ws.rgbw);
   ka.rgbb = (const float*)(base + ws.rgbb);
   ka.resid = (float4*)(base + ws.resid);
@@ -557,6 +570,7 @@ int c3d_cips_fwd_tc(const C3dCipsParams* p, const C3dCipsWeights* w, const float
     off += ka.layer_kc[l] * 4;
   }
   ka.layer_tile_off[L] = off;
+  ka.img_tile_stride = (size_t)off;
   // ---- staircase issue order (see KArgs::order_full)
   {
     bool done[8][4] = {};
@@ -569,22 +583,28 @@ int c3d_cips_fwd_tc(const C3dCipsParams* p, const C3dCipsWeights* w, const float
             ka.order_full[n++] = (uint16_t)(kc | (nc << 4) | (j << 8));
           }
     for (int nc = 0; nc < 4; ++nc) ka.order_in[nc] = (uint16_t)(0 | (nc << 4) | (nc << 8));
+    for (int i = 0; i < 32; ++i) ka.last_full[((ka.order_full[i] >> 4) & 15) >> 1] = i;
+    for (int i = 0; i < 4; ++i) ka.last_in[((ka.order_in[i] >> 4) & 15) >> 1] = i;
   }
   // ---- prep: weights -> fp16 tiles (one launch), per-image epilogue vectors
   {
     PrepArgs pa = {};
-    for (int l = 0; l < L; ++l) pa.w[l] = w->w[l];
+    for (int l = 0; l < L; ++l) {
+      pa.w[l] = w->w[l];
+      pa.s1p[l] = w->style1p[l];
+      pa.demod[l] = w->demod[l];
+    }
     for (int l = 0; l <= L; ++l) pa.layer_tile_off[l] = ka.layer_tile_off[l];
     pa.in_dim0 = p->in_dim;
     pa.n_layers = L;
+    pa.B = p->batch;
     for (int i = 0; i < 32; ++i) pa.order_full[i] = ka.order_full[i];
     for (int i = 0; i < 4; ++i) pa.order_in[i] = ka.order_in[i];
-    cips_prep_weights_kernel<<<ka.layer_tile_off[L], 256, 0, st>>>(pa, (__half*)(base + ws.wtiles));
+    cips_prep_weights_kernel<<<dim3(ka.layer_tile_off[L], p->batch), 256, 0, st>>>(pa, (__half*)(base + ws.wtiles));
     C3D_LAUNCH_CHECK();
   }
-  cips_prep_consts_kernel<<<L + p->n_blocks, 256, 0, st>>>(*w, p->batch, L, p->n_blocks, p->rgb_from,
-                                                           (float*)(base + ws.demod), (float*)(base + ws.next_scale),
-                                                           (float4*)(base + ws.rgbw), (float*)(base + ws.rgbb));
+  cips_prep_consts_kernel<<<p->n_blocks, 256, 0, st>>>(*w, p->n_blocks, p->rgb_from, (float4*)(base + ws.rgbw),
+                                                       (float*)(base + ws.rgbb));
   C3D_LAUNCH_CHECK();
   int cl = 1;
   const int grid = cips_grid(p, &cl);

@@ -1,0 +1,46 @@
+"""HBM roofline of the discriminator's two native ops at FFHQ r256 shapes (CUDA events, L2 flushed
+between iterations by a 256 MB write)."""
+import json, os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+import cips3d_b200
+from cips3d_b200 import ops
+dev = "cuda:0"
+peak = json.load(open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "MEASURED_PEAKS.json")))["hbm_gbs"] \
+    if os.path.exists(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "MEASURED_PEAKS.json")) else 6650.0
+flush = torch.empty(64 * 1024 * 1024, device=dev)
+
+
+def timeit(fn, reps=20):
+    for _ in range(5):
+        fn()
+    ts = []
+    for _ in range(reps):
+        flush.fill_(1.0)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); fn(); e1.record(); torch.cuda.synchronize()
+        ts.append(e0.elapsed_time(e1))
+    ts.sort()
+    return ts[len(ts) // 2]
+
+
+out = []
+k = cips3d_b200.discriminator.make_kernel([1, 3, 3, 1]).to(dev)
+for (B, C, H) in [(16, 128, 256), (16, 256, 128), (16, 512, 64)]:
+    x = torch.randn(B, C, H, H, device=dev)
+    b = torch.randn(C, device=dev)
+    ms = timeit(lambda: ops.bias_act(x, b))
+    gb = 2 * x.numel() * 4 / 1e9
+    out.append(dict(op="bias_act fwd", shape=[B, C, H, H], ms=ms, gbs=gb / ms * 1e3, frac=gb / ms * 1e3 / peak))
+    y = ops.bias_act(x, b)
+    ms = timeit(lambda: ops.bias_act(x, None, y, 3, 1))
+    gb = 3 * x.numel() * 4 / 1e9
+    out.append(dict(op="bias_act bwd(grad=1)", shape=[B, C, H, H], ms=ms, gbs=gb / ms * 1e3, frac=gb / ms * 1e3 / peak))
+    for pad in ((2, 2), (1, 1)):
+        ms = timeit(lambda: ops._upfirdn2d_raw(x, k, (1, 1), (1, 1), (pad[0], pad[1], pad[0], pad[1])))
+        Ho = H + pad[0] + pad[1] - 3
+        gb = (x.numel() + B * C * Ho * Ho) * 4 / 1e9
+        out.append(dict(op=f"upfirdn2d blur pad{pad}", shape=[B, C, H, H], ms=ms, gbs=gb / ms * 1e3, frac=gb / ms * 1e3 / peak))
+for r in out:
+    print(json.dumps(r))
+print(json.dumps(dict(hbm_peak_gbs=peak, note="algorithmic bytes (read x + write y [+ read ref]) / CUDA-event median; L2 flushed between reps")))
