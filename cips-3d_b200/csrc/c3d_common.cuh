@@ -102,10 +102,8 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
     if (++spins > C3D_WATCHDOG_SPINS) {
-#ifdef C3D_DEBUG_WATCHDOG   // device printf makes every launch of the kernel heavier: debug builds only
       printf("c3d watchdog: mbarrier wait timed out (block %d thread %d bar 0x%x parity %u)\n", (int)blockIdx.x,
              (int)threadIdx.x, smem_u32(bar), parity);
-#endif
       __trap();
     }
   }

@@ -86,6 +86,73 @@ __global__ void __launch_bounds__(256) upfirdn2d_kernel(
   }
 }
 
+// Fast path for up = down = 1 (every Blur of the discriminator): one CTA = 64 x 16 outputs of one plane.
+// The (16+kh-1) x (64+kw-1) input footprint is staged with coalesced row reads; each thread produces 4
+// vertically adjacent outputs from a sliding window (kh+3 shared-memory rows x kw taps).
+constexpr int kBW = 64, kBH = 16, kBPitch = kBW + kMaxK;   // pitch 72 floats
+// KH/KW > 0: compile-time kernel extent (fully unrolled taps, weights in registers); 0: run-time extent.
+template <int KH, int KW>
+__global__ void __launch_bounds__(256) blur_tile_kernel(const float* __restrict__ x, const float* __restrict__ kernel,
+                                                        float* __restrict__ y, int in_h, int in_w, int out_h,
+                                                        int out_w, int kh_rt, int kw_rt, int pad_x0, int pad_y0) {
+  const int kh = KH > 0 ? KH : kh_rt, kw = KW > 0 ? KW : kw_rt;
+  __shared__ float sm[(kBH + kMaxK - 1) * kBPitch];
+  __shared__ float sk[kMaxK * kMaxK];
+  const int tx = threadIdx.x & 63, ty = threadIdx.x >> 6;      // 64 x 4 threads
+  const int ox0 = blockIdx.x * kBW, oy0 = blockIdx.y * kBH;
+  const float* xp = x + (size_t)blockIdx.z * in_h * in_w;
+  if (threadIdx.x < kh * kw) {
+    const int ky = threadIdx.x / kw, kx = threadIdx.x % kw;
+    sk[threadIdx.x] = kernel[(kh - 1 - ky) * kw + (kw - 1 - kx)];   // flipped kernel (correlation form)
+  }
+  const int fh = kBH + kh - 1, fw = kBW + kw - 1;
+  for (int r = ty; r < fh; r += 4) {
+    const int iy = oy0 + r - pad_y0;
+    const bool row_ok = iy >= 0 && iy < in_h;
+    for (int c = tx; c < fw; c += 64) {
+      const int ix = ox0 + c - pad_x0;
+      sm[r * kBPitch + c] = (row_ok && ix >= 0 && ix < in_w) ? __ldg(xp + (size_t)iy * in_w + ix) : 0.f;
+    }
+  }
+  __syncthreads();
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  const int r0 = ty * 4;
+  if (KH > 0) {
+    float wreg[(KH > 0 ? KH : 1) * (KW > 0 ? KW : 1)];
+#pragma unroll
+    for (int i = 0; i < KH * KW; ++i) wreg[i] = sk[i];
+#pragma unroll
+    for (int r = 0; r < KH + 3; ++r) {
+#pragma unroll
+      for (int kx = 0; kx < KW; ++kx) {
+        const float v = sm[(r0 + r) * kBPitch + tx + kx];
+#pragma unroll
+        for (int o = 0; o < 4; ++o)
+          if (r - o >= 0 && r - o < KH) acc[o] = fmaf(v, wreg[(r - o) * KW + kx], acc[o]);   // resolved at compile time
+      }
+    }
+  } else {
+    for (int r = 0; r < kh + 3; ++r) {
+      for (int kx = 0; kx < kw; ++kx) {
+        const float v = sm[(r0 + r) * kBPitch + tx + kx];
+#pragma unroll
+        for (int o = 0; o < 4; ++o) {
+          const int ky = r - o;
+          if (ky >= 0 && ky < kh) acc[o] = fmaf(v, sk[ky * kw + kx], acc[o]);
+        }
+      }
+    }
+  }
+  const int gx = ox0 + tx;
+  if (gx < out_w) {
+#pragma unroll
+    for (int o = 0; o < 4; ++o) {
+      const int gy = oy0 + r0 + o;
+      if (gy < out_h) y[((size_t)blockIdx.z * out_h + gy) * out_w + gx] = acc[o];
+    }
+  }
+}
+
 }  // namespace c3d
 
 using namespace c3d;
@@ -131,6 +198,20 @@ extern "C" int c3d_upfirdn2d(const float* x, const float* kernel, float* y, int3
   int fw = (kTileW - 1) * down_x + kw, fh = (kTileH - 1) * down_y + kh;
   size_t smem = (size_t)fw * fh * sizeof(float);
   cudaStream_t st = (cudaStream_t)stream;
+  if (up_x == 1 && up_y == 1 && down_x == 1 && down_y == 1) {     // the discriminator's Blur
+    for (int p0 = 0; p0 < planes; p0 += 65535) {
+      int np = planes - p0 < 65535 ? planes - p0 : 65535;
+      dim3 grid(c3d_div_up(out_w, kBW), c3d_div_up(out_h, kBH), np);
+      if (kh == 4 && kw == 4)
+        blur_tile_kernel<4, 4><<<grid, 256, 0, st>>>(x + (size_t)p0 * in_h * in_w, kernel, y + (size_t)p0 * out_h * out_w,
+                                                     in_h, in_w, out_h, out_w, kh, kw, pad_x0, pad_y0);
+      else
+        blur_tile_kernel<0, 0><<<grid, 256, 0, st>>>(x + (size_t)p0 * in_h * in_w, kernel, y + (size_t)p0 * out_h * out_w,
+                                                     in_h, in_w, out_h, out_w, kh, kw, pad_x0, pad_y0);
+      C3D_LAUNCH_CHECK();
+    }
+    return C3D_OK;
+  }
   if (smem > 48 * 1024)
     C3D_CUDA(cudaFuncSetAttribute(upfirdn2d_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   for (int p0 = 0; p0 < planes; p0 += 65535) {  // gridDim.y limit

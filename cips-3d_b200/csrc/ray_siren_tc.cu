@@ -179,9 +179,7 @@ __global__ void __launch_bounds__(640, 1) ray_siren_tc_kernel(const KArgs a) {
       uint32_t idle = 0;
       while (done[0] < total || done[1] < total) {
         if (++idle > (1u << 28)) {
-#ifdef C3D_DEBUG_WATCHDOG
           if (lane == 0) printf("c3d watchdog: ray MMA issuer starved (block %d, done %d/%d of %d)\n", (int)blockIdx.x, done[0], done[1], total);
-#endif
           __trap();
         }
 #pragma unroll
