@@ -236,6 +236,15 @@ def main():
             roof[key] = {"bound": "tensor", "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach / peak_tf,
                          "traffic": None, "kernel_ms": t_ms, "launches_timed": len(evs),
                          "algorithmic_flop_per_launch": flop_unit * units, "peak_source": peak_src}
+    # DRAM traffic per launch from the committed ncu --set full capture of this workload (profiles/traffic.json)
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tpath):
+        tj = json.load(open(tpath))
+        for key, kname in (("cips", "c3d_cips_fwd"), ("ray", "c3d_ray_siren_fwd")):
+            ent = tj.get(kname)
+            if key in roof and ent and ent.get("batch") == B and ent.get("resolution") == res:
+                roof[key]["traffic"] = ent["dram_bytes_per_launch"]
+                roof[key]["traffic_source"] = ent.get("source")
     dominant = max(roof, key=lambda k: roof[k]["kernel_ms"]) if roof else None
     line = {
         "metric": METRIC, "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps,

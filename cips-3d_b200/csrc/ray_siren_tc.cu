@@ -41,15 +41,17 @@ constexpr int kOffW1h = 0, kOffW1l = kW1Bytes, kOffW2h = 2 * kW1Bytes, kOffW2l =
 static_assert(kWBlobBytes == 114688, "weight blob is 112 KB");
 
 // per-image epilogue constants (prep kernel): FiLM folded with the linear bias and weight scale
+constexpr int kW0Bytes = 128 * 16 * 2;   // layer-0 B operand (N=128, K=16) per hi / lo
 struct ImgConsts {
-  float4 l0[128];      // (g0*s*W0[j][0..2], g0*b0[j] + beta0[j]),  s = 2/0.24 (UniformBoxWarp)
+  // layer 0 as a K=16 MMA: A = [x, y, z, 1, 0...], B[j] = [g0*s*W0[j][0..2], g0*b0[j] + beta0[j], 0...]
+  // (s = 2/0.24, UniformBoxWarp), fp16 hi then lo, UMMA K-major layout, unscaled
+  uint8_t w0[2 * kW0Bytes];
   float2 l1[128];      // (g1/256, g1*b1 + beta1)
   float2 lc[64];       // (gc/256, gc*bc + betac)
 };
 
 struct SlotMem {
-  float feat_c[kRows][33];
-  float feat_f[kRows][33];
+  float feat[2][kRows][33];   // [0] fine pass, [1] coarse pass features (padded rows: conflict-free both ways)
   float z_c[kRows], sig_c[kRows], z_f[kRows], sig_f[kRows];
   float wc[kRows];            // coarse compositing weights
   float cdf[kRows];           // per ray: S-1 cdf entries (stride S)
@@ -58,7 +60,9 @@ struct SlotMem {
   float skey[2 * kRows];      // sorted depths, ray g at [g*nS, (g+1)*nS)
   int sidx[2 * kRows];        // source of each sorted sample: < S fine, >= S coarse
   float w_all[2 * kRows];     // final compositing weights (sorted order)
-  alignas(16) float4 l0[128]; // image constants of the group's image (ImgConsts)
+  int frow[2 * kRows];        // row of each sorted sample in feat[0..1] viewed as [2*kRows][33]
+  float wsum[16];             // per ray: sum of weights (before last_back)
+  alignas(128) uint8_t w0[2 * kW0Bytes];  // image constants of the group's image (ImgConsts)
   float2 l1[128];
   float2 lc[64];
 };
@@ -84,6 +88,20 @@ struct KArgs {
 };
 
 __device__ __forceinline__ float fast_sin(float x) { return __sinf(x); }
+
+#ifdef C3D_TRACE   // debug build: block 0 stamps the phases of iteration 3
+__device__ unsigned long long g_rtrace[4096];
+__device__ unsigned int g_rtrace_n;
+__device__ __forceinline__ void rtrace(int it, uint32_t tag, uint32_t a0) {
+  if (blockIdx.x == 0 && it == 3) {
+    unsigned int i = atomicAdd(&g_rtrace_n, 1u);
+    if (i < 4096) g_rtrace[i] = ((unsigned long long)tag << 56) | ((unsigned long long)(a0 & 0xFFFF) << 40) | (clock64() & 0xFFFFFFFFFFull);
+  }
+}
+#define RTRACE(it, tag, a0) rtrace(it, tag, a0)
+#else
+#define RTRACE(it, tag, a0)
+#endif
 template <int N>
 __device__ __forceinline__ void reg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
 template <int N>
@@ -139,7 +157,7 @@ __global__ void __launch_bounds__(640, 1) ray_siren_tc_kernel(const KArgs a) {
   const int S = p.num_steps, G = a.G;
   const bool hier = p.hierarchical != 0;
   const int nS = hier ? 2 * S : S;
-  const int mma_phases = hier ? 6 : 3;
+  const int mma_phases = hier ? 8 : 4;     // per pass: layer 0, layer 1, colour+sigma, colour linear
 
   if (threadIdx.x == 0) {
     mbar_init(&s.w_full, 1);
@@ -187,17 +205,20 @@ __global__ void __launch_bounds__(640, 1) ray_siren_tc_kernel(const KArgs a) {
           if (done[sl] < total && __all_sync(0xffffffffu, mbar_test(&s.a_ready[sl], par[sl]))) {
             par[sl] ^= 1;
             tc_fence_after();
-            const int layer = done[sl] % 3;
+            const int layer = done[sl] & 3;
+            if (lane == 0) RTRACE(done[sl] / mma_phases, 1, (uint32_t)(sl << 8 | (done[sl] % mma_phases)));
             if (elect_one()) {
               uint32_t a_hi = tmem + (uint32_t)(sl * 256), a_lo = a_hi + 64;
               const uint32_t d = a_hi + 128;
               // opaque per-iteration copies: keeps the compiler from hoisting ~60 loop-invariant descriptor
               // words out of the loop (they would spill and cost an LDL per MMA)
-              uint32_t bh = layer == 0 ? w1h : (layer == 1 ? w2h : w3h);
-              uint32_t bl = layer == 0 ? w1l : (layer == 1 ? w2l : w3l);
+              const uint32_t w0h = umma_desc_lo(smem_u32(s.slot[sl].w0), 128 * 16);
+              uint32_t bh = layer == 0 ? w0h : (layer == 1 ? w1h : (layer == 2 ? w2h : w3h));
+              uint32_t bl = layer == 0 ? w0h + (kW0Bytes >> 4) : (layer == 1 ? w1l : (layer == 2 ? w2l : w3l));
               asm volatile("" : "+r"(bh), "+r"(bl), "+r"(a_hi), "+r"(a_lo));
-              if (layer == 0) mma_split3<128, 128>(d, a_hi, a_lo, bh, bl, dhi);
-              else if (layer == 1) mma_split3<kN2, 128>(d, a_hi, a_lo, bh, bl, dhi);
+              if (layer == 0) mma_split3<128, 16>(d, a_hi, a_lo, bh, bl, dhi);
+              else if (layer == 1) mma_split3<128, 128>(d, a_hi, a_lo, bh, bl, dhi);
+              else if (layer == 2) mma_split3<kN2, 128>(d, a_hi, a_lo, bh, bl, dhi);
               else mma_split3<32, 64>(d, a_hi, a_lo, bh, bl, dhi);
               tc_commit(&s.d_ready[sl]);
             }
@@ -235,12 +256,18 @@ __global__ void __launch_bounds__(640, 1) ray_siren_tc_kernel(const KArgs a) {
       dpar ^= 1;
       tc_fence_after();
     };
+    int tr_it = 0, tr_ph = 0;
+    auto stamp = [&](uint32_t tag) { if (stid == 0) RTRACE(tr_it, tag, (uint32_t)(sl << 8 | tr_ph)); ++tr_ph; };
     const int g_row = row / S, s_row = row - g_row * S;   // ray within the group, sample index
     const bool row_in_group = g_row < G;
     const int g_el = stid / nS, e_el = stid - g_el * nS;  // (ray, element) view used by the merge phases
     int cur_img = -1;
+#ifdef C3D_RAY_STAGGER_NS   // start slot 1 half a pass late so its MMA phases fall into slot 0's worker phases
+    if (sl == 1) __nanosleep(C3D_RAY_STAGGER_NS);
+#endif
 
     for (int it = 0; it < iters; ++it) {
+      tr_it = it; tr_ph = 0;
       const int grp = (it * (int)gridDim.x + (int)blockIdx.x) * 2 + sl;
       const bool grp_ok = grp < a.total_groups;
       const int img = grp_ok ? grp / a.groups_per_img : 0;
@@ -252,10 +279,12 @@ __global__ void __launch_bounds__(640, 1) ray_siren_tc_kernel(const KArgs a) {
       const float* M = a.io.cam2world + (size_t)img * 16;
       if (img != cur_img) {    // (slot-uniform) stage the image's folded FiLM constants
         const ImgConsts& ic = a.consts[img];
-        if (stid < 128) sm.l0[stid] = __ldg(&ic.l0[stid]);
-        else sm.l1[stid - 128] = __ldg(&ic.l1[stid - 128]);
-        if (stid < 64) sm.lc[stid] = __ldg(&ic.lc[stid]);
+        reinterpret_cast<uint4*>(sm.w0)[stid] = __ldg(reinterpret_cast<const uint4*>(ic.w0) + stid);           // 8 KB
+        reinterpret_cast<uint4*>(sm.w0)[stid + 256] = __ldg(reinterpret_cast<const uint4*>(ic.w0) + stid + 256);
+        if (stid < 128) sm.l1[stid] = __ldg(&ic.l1[stid]);
+        else if (stid < 192) sm.lc[stid - 128] = __ldg(&ic.lc[stid - 128]);
         cur_img = img;
+        fence_proxy_async();      // w0 is read by the tensor core (async proxy)
         slot_sync();
       }
       RayFrame fr;
@@ -266,7 +295,7 @@ __global__ void __launch_bounds__(640, 1) ray_siren_tc_kernel(const KArgs a) {
       }
 
       for (int pass = 0; pass < (hier ? 2 : 1); ++pass) {
-        // ---------------- L0: point position, first FiLM layer (FMA pipe) -> A operand
+        // ---------------- L0: point position -> A operand [x, y, z, 1] (K = 16) for the layer-0 MMA
         float px = 0.f, py = 0.f, pz = 0.f;
         if (pt_ok) {
           if (pass == 0) {
@@ -278,19 +307,41 @@ __global__ void __launch_bounds__(640, 1) ray_siren_tc_kernel(const KArgs a) {
             fine_sample(fr, sm.z_f[row], px, py, pz);
           }
         }
-#pragma unroll 1
-        for (int c = 0; c < 64; c += 16) {
-          float v[16];
-#pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            const float4 w4 = sm.l0[half * 64 + c + j];
-            v[j] = fast_sin(fmaf(w4.x, px, fmaf(w4.y, py, fmaf(w4.z, pz, w4.w))));
-          }
-          store_a16(a_hi + (uint32_t)(half * 32 + c / 2), a_lo + (uint32_t)(half * 32 + c / 2), v);
+        if (half == 0) {
+          float v[16] = {px, py, pz, 1.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+          store_a16(a_hi, a_lo, v);
         }
+        stamp(2);
+        signal_a();
+        // ---------------- E0: D(128) = g0*(W0 p*s + b0) + beta0  ->  sin  ->  A (h0)
+        wait_d();
+        stamp(3);
+        {
+          uint32_t accA[16], accB[16];
+          auto e0 = [&](const uint32_t (&acc)[16], int c) {
+            float v[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) v[j] = fast_sin(__uint_as_float(acc[j]));
+            store_a16(a_hi + (uint32_t)(half * 32 + c / 2), a_lo + (uint32_t)(half * 32 + c / 2), v);
+          };
+          tmem_ld16(dcol + (uint32_t)(half * 64), accA);
+          tc_wait_ld();
+          tmem_ld16(dcol + (uint32_t)(half * 64 + 16), accB);
+          e0(accA, 0);
+          tc_wait_ld();
+          tmem_ld16(dcol + (uint32_t)(half * 64 + 32), accA);
+          e0(accB, 16);
+          tc_wait_ld();
+          tmem_ld16(dcol + (uint32_t)(half * 64 + 48), accB);
+          e0(accA, 32);
+          tc_wait_ld();
+          e0(accB, 48);
+        }
+        stamp(4);
         signal_a();
         // ---------------- E1: D(128) -> FiLM+sin -> A (h1); TMEM loads double-buffered
         wait_d();
+        stamp(5);
         {
           uint32_t accA[16], accB[16];
           auto e1 = [&](const uint32_t (&acc)[16], int c) {
@@ -315,9 +366,11 @@ __global__ void __launch_bounds__(640, 1) ray_siren_tc_kernel(const KArgs a) {
           tc_wait_ld();
           e1(accB, 48);
         }
+        stamp(6);
         signal_a();
         // ---------------- E2: D(80): cols 0..63 -> FiLM+sin -> A (h2, K=64); col 64 -> sigma
         wait_d();
+        stamp(7);
         float sigma = 0.f;
         {
           uint32_t accA[16], accB[16], accS[16];
@@ -341,14 +394,16 @@ __global__ void __launch_bounds__(640, 1) ray_siren_tc_kernel(const KArgs a) {
           e2(accA, 0);
           e2(accB, 16);
         }
+        stamp(8);
         signal_a();
         // ---------------- E3: D(32) -> + bias -> features to shared memory
         wait_d();
+        stamp(9);
         {
           uint32_t acc[16];
           tmem_ld16(dcol + (uint32_t)(half * 16), acc);
           tc_wait_ld();
-          float(*feat)[33] = pass == 0 ? sm.feat_c : sm.feat_f;
+          float(*feat)[33] = pass == 0 ? sm.feat[1] : sm.feat[0];
           float* dbg = pass == 0 ? a.io.dbg_coarse : a.io.dbg_fine;
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
@@ -360,6 +415,7 @@ __global__ void __launch_bounds__(640, 1) ray_siren_tc_kernel(const KArgs a) {
         }
         tc_fence_before();
         slot_sync();
+        stamp(10);
         // ---------------- importance resampling, all threads (generator_nerf_inr.py:537-598, pigan_utils.py:164-209)
         if (pass == 0 && hier) {
           const int r0 = g_row * S;
@@ -403,6 +459,7 @@ __global__ void __launch_bounds__(640, 1) ray_siren_tc_kernel(const KArgs a) {
           slot_sync();
         }
       }
+      stamp(11);
       // ---------------- merge (stable rank sort of the nS depths of each ray), generator.py:1733-1738
       const bool el_ok = g_el < n_valid;
       const int rc0 = g_el * S;           // first row of ray g_el
@@ -416,8 +473,10 @@ __global__ void __launch_bounds__(640, 1) ray_siren_tc_kernel(const KArgs a) {
           const float ke = key_of(e);
           rank += (ke < k || (ke == k && e < e_el)) ? 1 : 0;
         }
+        const int src = hier ? e_el : S + e_el;
         sm.skey[base + rank] = k;
-        sm.sidx[base + rank] = hier ? e_el : S + e_el;
+        sm.sidx[base + rank] = src;
+        sm.frow[base + rank] = src < S ? rc0 + src : kRows + rc0 + src - S;
       }
       slot_sync();
       float alpha_el = 0.f;
@@ -436,29 +495,41 @@ __global__ void __launch_bounds__(640, 1) ray_siren_tc_kernel(const KArgs a) {
         sm.w_all[base + e_el] = __fmul_rn(alpha_el, T);
       }
       slot_sync();
+      stamp(12);
       // ---------------- composite: pixels_fea[ray][c] = sum_i w_i * feature_i[c]  (pigan_utils.py:255-266)
-      for (int o = stid; o < n_valid * kFeat; o += 256) {
-        const int g = o >> 5, c = o & 31, r0 = g * S, b0 = g * nS;
-        float wsum = 0.f, acc = 0.f, depth = 0.f;
-        for (int i = 0; i < nS; ++i) wsum += sm.w_all[b0 + i];
-        const size_t ro = (size_t)img * p.n_rays + ray0 + g;
-        for (int i = 0; i < nS; ++i) {
-          float w = sm.w_all[b0 + i];
-          if (p.last_back && i == nS - 1) w += 1.f - wsum;
-          const int id = sm.sidx[b0 + i];
-          const float f = id < S ? sm.feat_f[r0 + id][c] : sm.feat_c[r0 + id - S][c];
-          acc = fmaf(w, f, acc);
-          if (c == 0) {
-            depth = fmaf(w, sm.skey[b0 + i], depth);
-            if (a.io.weights) a.io.weights[ro * nS + i] = w;
-            if (a.io.dbg_all_z) a.io.dbg_all_z[ro * nS + i] = sm.skey[b0 + i];
-          }
-        }
-        if (p.white_back) acc += 1.f - wsum;
-        a.io.pixels_fea[ro * kFeat + c] = acc;
-        if (c == 0 && a.io.depth) a.io.depth[ro] = depth;
+      if (el_ok && e_el == 0) {      // per ray: weight sum in the reference's order, last_back folded into the last weight
+        float wsum = 0.f;
+        for (int i = 0; i < nS; ++i) wsum += sm.w_all[base + i];
+        sm.wsum[g_el] = wsum;
+        if (p.last_back) sm.w_all[base + nS - 1] += 1.f - wsum;
       }
       slot_sync();
+      {
+        const int c = stid & 31;
+        const float* featf = &sm.feat[0][0][0];
+        for (int g = stid >> 5; g < n_valid; g += 8) {      // warp = ray, lane = channel
+          const int b0 = g * nS;
+          float acc = 0.f;
+#pragma unroll 4
+          for (int i = 0; i < nS; ++i) acc = fmaf(sm.w_all[b0 + i], featf[sm.frow[b0 + i] * 33 + c], acc);
+          if (p.white_back) acc += 1.f - sm.wsum[g];
+          const size_t ro = (size_t)img * p.n_rays + ray0 + g;
+          a.io.pixels_fea[ro * kFeat + c] = acc;
+          if (c < nS && (a.io.weights || a.io.dbg_all_z)) {     // lanes cover the nS <= 32 fast case, loop otherwise
+            for (int i = c; i < nS; i += 32) {
+              if (a.io.weights) a.io.weights[ro * nS + i] = sm.w_all[b0 + i];
+              if (a.io.dbg_all_z) a.io.dbg_all_z[ro * nS + i] = sm.skey[b0 + i];
+            }
+          }
+          if (c == 0 && a.io.depth) {
+            float depth = 0.f;
+            for (int i = 0; i < nS; ++i) depth = fmaf(sm.w_all[b0 + i], sm.skey[b0 + i], depth);
+            a.io.depth[ro] = depth;
+          }
+        }
+      }
+      slot_sync();
+      stamp(13);
     }
   }
   tc_fence_before();
@@ -488,8 +559,9 @@ __global__ void ray_prep_kernel(C3dSirenWeights w, int B, uint8_t* blob, ImgCons
   for (int i = tid; i < B * 128; i += nth) {
     const int b = i / 128, j = i % 128;
     const float g0 = w.gamma0[i], g1 = w.gamma1[i];
-    consts[b].l0[j] = make_float4(g0 * sc * w.w0[j * 3], g0 * sc * w.w0[j * 3 + 1], g0 * sc * w.w0[j * 3 + 2],
-                                  fmaf(g0, w.b0[j], w.beta0[i]));
+    const float c4[4] = {g0 * sc * w.w0[j * 3], g0 * sc * w.w0[j * 3 + 1], g0 * sc * w.w0[j * 3 + 2],
+                         fmaf(g0, w.b0[j], w.beta0[i])};
+    for (int k = 0; k < 16; ++k) put_split(consts[b].w0, 0, kW0Bytes, 128, j, k, k < 4 ? c4[k] : 0.f);
     consts[b].l1[j] = make_float2(g1 * kWInv, fmaf(g1, w.b1[j], w.beta1[i]));
   }
   for (int i = tid; i < B * 64; i += nth) {
@@ -518,6 +590,20 @@ static RayWs ray_ws_layout(const C3dRayParams* p) {
   return o;
 }
 size_t c3d_ray_siren_tc_workspace_bytes(const C3dRayParams* p) { return ray_ws_layout(p).total; }
+
+#ifdef C3D_TRACE
+extern "C" int c3d_debug_ray_trace(unsigned long long* out, int cap) {
+  unsigned int n = 0;
+  cudaDeviceSynchronize();
+  cudaMemcpyFromSymbol(&n, c3d::rtc::g_rtrace_n, sizeof(n));
+  if ((int)n > cap) n = cap;
+  if (n > 4096) n = 4096;
+  cudaMemcpyFromSymbol(out, c3d::rtc::g_rtrace, n * sizeof(unsigned long long));
+  unsigned int zero = 0;
+  cudaMemcpyToSymbol(c3d::rtc::g_rtrace_n, &zero, sizeof(zero));
+  return (int)n;
+}
+#endif
 
 int c3d_ray_siren_fwd_tc(const C3dRayParams* p, const C3dSirenWeights* w, const C3dRayIO* io, void* workspace,
                          size_t workspace_bytes, cudaStream_t st) {
