@@ -140,6 +140,7 @@ def main():
     ap.add_argument("--res", type=int, default=R)
     ap.add_argument("--kernel-impl", default=os.environ.get("C3D_IMPL", "tc"), choices=["tc", "simt"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-eager", action="store_true", help="skip the eager-torch-on-the-same-GPU comparison")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -186,6 +187,10 @@ def main():
         return img
 
     def timed(fn, steps, warmup, profile=False):
+        t_ramp = time.perf_counter()          # SM clocks ramp from idle (120 MHz) over ~1 s of load: untimed pre-warm
+        while time.perf_counter() - t_ramp < 1.5:
+            fn()
+            torch.cuda.synchronize()
         for _ in range(warmup):
             fn()
         torch.cuda.synchronize()
@@ -267,6 +272,30 @@ def main():
         other = "ray" if dominant == "cips" else "cips"
         if other in roof:
             line["roofline_secondary"] = dict(roof[other], kernel=("c3d_cips_fwd" if other == "cips" else "c3d_ray_siren_fwd"))
+    if world == 1 and not args.no_eager:
+        # the same forward as eager torch CUDA ops (fp32, TF32 off = torch default) on this GPU: what the reference's
+        # PyTorch path executes; chunk the batch if the per-sample tensors would not fit
+        try:
+            G.force_torch_path = True
+            eb = min(B, 4)
+            ze = {k: v[:eb] for k, v in zs_dev.items()}
+            with torch.no_grad():
+                G(ze, img_size=res, nerf_noise=0.0, **kw)
+                torch.cuda.synchronize()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                for _ in range(2):
+                    G(ze, img_size=res, nerf_noise=0.0, **kw)
+                e1.record()
+                torch.cuda.synchronize()
+            line["torch_eager_same_gpu"] = {"value": 2 * eb / (e0.elapsed_time(e1) / 1e3), "unit": "images/s", "batch": eb,
+                                            "note": "identical math as eager torch CUDA ops (cuBLAS fp32, TF32 off) through the same "
+                                                    "module surface; not the product path"}
+        except Exception as ex:  # out of memory etc. -- report, do not fail the bench
+            line["torch_eager_same_gpu"] = {"unavailable": str(ex)[:120]}
+        finally:
+            G.force_torch_path = False
+            torch.cuda.empty_cache()
     if world == 1 and not args.no_cpu_baseline:
         v, cores, sample = cpu_reference_rate(20.0)
         line["cpu_baseline"] = {"value": v, "unit": "images/s", "cores": cores, "kind": "port", "sample": sample}

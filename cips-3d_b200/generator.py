@@ -485,6 +485,9 @@ class GeneratorNerfINR(nn.Module):              # generator.py:1158-1951
         # (pigan_utils.py:246).  Keep the draws (default) so torch's RNG stream stays aligned.
         self.skip_unused_noise_draws = False
         self.impl = None            # None -> env C3D_IMPL / tcgen05 default
+        # measurement hook: run the differentiable torch-CUDA-op restatement even without autograd (the eager
+        # PyTorch path the reference would execute on the same GPU); bench.py reports it beside the fused path
+        self.force_torch_path = False
 
     # ---------------------------------------------------------------- small helpers
     def _nerf_grad_needed(self):
@@ -543,7 +546,7 @@ class GeneratorNerfINR(nn.Module):              # generator.py:1158-1951
         """rays -> (B,N,32) integrated features.  jitter_u (B,HW,S), noise_c (B,N,S), pdf_u (B*N,S),
         noise_f (B,N,nS); ray_idx: LongTensor ray subset or None."""
         _require_cuda(cam2world, "GeneratorNerfINR")
-        if not grad and self.siren.fused_supported():
+        if not grad and not self.force_torch_path and self.siren.fused_supported():
             out = ops.render_features(
                 self.siren.kernel_weights(), self.siren.kernel_film(style_dict), cam2world, jitter_u, pdf_u,
                 noise_c, noise_f, img_size=img_size, fov=fov, ray_start=ray_start, ray_end=ray_end,
@@ -633,7 +636,10 @@ class GeneratorNerfINR(nn.Module):              # generator.py:1158-1951
         return self.whole_grad_forward(forward_points=forward_points, up_vector=up_vector, **common)
 
     def _pixels_to_imgs(self, pixels_fea, style_dict, return_aux_img, img_size, pitch, yaw):
-        inr_img = self.inr_net(pixels_fea, style_dict)                          # generator.py:1754
+        if self.force_torch_path:
+            inr_img = self.inr_net.forward_torch(pixels_fea, style_dict)
+        else:
+            inr_img = self.inr_net(pixels_fea, style_dict)                      # generator.py:1754
         B = inr_img.shape[0]
         inr_img = inr_img.view(B, img_size, img_size, 3).permute(0, 3, 1, 2)
         inr_img = self.filters(inr_img)
