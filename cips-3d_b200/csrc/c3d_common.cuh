@@ -95,16 +95,27 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   return ok != 0;
 }
 // Spin with a watchdog: a protocol bug traps (-> CUDA error at the caller) instead of hanging the GPU.
-#ifndef C3D_WATCHDOG_SPINS
-#define C3D_WATCHDOG_SPINS (1u << 20)   /* x up to 20 us per probe */
+// Time-based (globaltimer), so slow instrumented replays (ncu source counters) do not trip it.
+#ifndef C3D_WATCHDOG_NS
+#define C3D_WATCHDOG_NS 20000000000ull   /* 20 s */
 #endif
+__device__ __forceinline__ unsigned long long c3d_globaltimer() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   uint32_t spins = 0;
+  unsigned long long t0 = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if (++spins > C3D_WATCHDOG_SPINS) {
-      printf("c3d watchdog: mbarrier wait timed out (block %d thread %d bar 0x%x parity %u)\n", (int)blockIdx.x,
-             (int)threadIdx.x, smem_u32(bar), parity);
-      __trap();
+    if ((++spins & 1023u) == 0) {
+      const unsigned long long now = c3d_globaltimer();
+      if (t0 == 0) t0 = now;
+      else if (now - t0 > C3D_WATCHDOG_NS) {
+        printf("c3d watchdog: mbarrier wait timed out (block %d thread %d bar 0x%x parity %u)\n", (int)blockIdx.x,
+               (int)threadIdx.x, smem_u32(bar), parity);
+        __trap();
+      }
     }
   }
 }

@@ -94,6 +94,22 @@ __device__ __forceinline__ void commit_stage_free(uint64_t* bar) {
         : "memory");
   }
 }
+// non-owner issuer: "I have observed this fill" -> one plain arrive on the stage's empty barrier of every CTA
+// that multicasts into it
+template <int CL>
+__device__ __forceinline__ void observe_stage_free(uint64_t* bar) {
+  if (CL == 1) {
+    mbar_arrive(bar);
+  } else {
+#pragma unroll
+    for (uint32_t r = 0; r < (uint32_t)CL; ++r)
+      asm volatile(
+          "{\n\t.reg .b32 ra;\n\tmapa.shared::cluster.u32 ra, %0, %1;\n\t"
+          "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t}" ::"r"(smem_u32(bar)),
+          "r"(r)
+          : "memory");
+  }
+}
 template <int CL>
 __device__ __forceinline__ void load_w_tile(void* dst, const uint8_t* src, uint64_t* bar, uint32_t rank) {
   if (CL == 1) {
@@ -192,7 +208,7 @@ __global__ void __launch_bounds__(kThreads, 1) cips_tc_kernel(const KArgs a) {
   if (threadIdx.x == 0) {
     for (int i = 0; i < kStages; ++i) {
       mbar_init(&s.full[i], 1);
-      mbar_init(&s.empty[i], CL);
+      mbar_init(&s.empty[i], 2 * CL);   // both issuers release every stage (see the issuer loop)
     }
     for (int i = 0; i < 4; ++i) mbar_init(&s.epi_done[i], kNumEpiWarps);
     mbar_init(&s.acc_full, 2);   // two MMA issuer warps, each commits once per layer
@@ -256,7 +272,8 @@ __global__ void __launch_bounds__(kThreads, 1) cips_tc_kernel(const KArgs a) {
           for (int t = 0; t < ntiles; ++t) {
             const uint32_t e = order[t];
             const uint32_t kc = e & 15u, nc = (e >> 4) & 15u;
-            if ((nc >> 1) == me) {
+            const bool mine = (nc >> 1) == me;
+            if (mine) {
               const int need = (int)(e >> 8);
               if (lane == 0) TRACE(it, 1 + me, (uint32_t)(l << 8 | t));          // tile reached
               if (need > waited) {
@@ -264,7 +281,12 @@ __global__ void __launch_bounds__(kThreads, 1) cips_tc_kernel(const KArgs a) {
                 waited = need;
               }
               if (lane == 0) TRACE(it, 3 + me, (uint32_t)(l << 8 | t));          // epilogue dependency satisfied
-              mbar_wait(&s.full[stage], phase);
+            }
+            // BOTH issuers observe every fill of every stage, in ring order, and a stage is released only when
+            // both have (empty count 2): an issuer that skipped the phases of tiles it does not own could see
+            // full[stage] one whole revolution stale (parity aliasing) whenever the epilogue outruns the refill.
+            mbar_wait(&s.full[stage], phase);
+            if (mine) {
               if (lane == 0) TRACE(it, 5 + me, (uint32_t)(l << 8 | t));          // weight tile landed
               tc_fence_after();
               if (elect_one()) {
@@ -278,8 +300,10 @@ __global__ void __launch_bounds__(kThreads, 1) cips_tc_kernel(const KArgs a) {
                 commit_stage_free<CL>(&s.empty[stage]);
                 if (t == my_last) tc_commit(&s.acc_full);
               }
-              __syncwarp();
+            } else if (elect_one()) {
+              observe_stage_free<CL>(&s.empty[stage]);
             }
+            __syncwarp();
             if (++stage == kStages) { stage = 0; phase ^= 1; }
           }
         }

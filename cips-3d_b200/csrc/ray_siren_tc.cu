@@ -195,8 +195,10 @@ __global__ void __launch_bounds__(640, 1) ray_siren_tc_kernel(const KArgs a) {
       int done[2] = {0, 0};
       const int total = iters * mma_phases;
       uint32_t idle = 0;
+      unsigned long long idle_t0 = 0;
       while (done[0] < total || done[1] < total) {
-        if (++idle > (1u << 28)) {
+        if ((++idle & 0xFFFFu) == 0 && (idle_t0 == 0 ? (idle_t0 = c3d_globaltimer(), false)
+                                                      : c3d_globaltimer() - idle_t0 > C3D_WATCHDOG_NS)) {
           if (lane == 0) printf("c3d watchdog: ray MMA issuer starved (block %d, done %d/%d of %d)\n", (int)blockIdx.x, done[0], done[1], total);
           __trap();
         }
@@ -225,6 +227,7 @@ __global__ void __launch_bounds__(640, 1) ray_siren_tc_kernel(const KArgs a) {
             __syncwarp();
             ++done[sl];
             idle = 0;
+            idle_t0 = 0;
           }
         }
         if (idle) __nanosleep(64);   // nothing ready: yield the issue port to the workers on this scheduler
