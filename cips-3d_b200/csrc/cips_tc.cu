@@ -9,11 +9,17 @@
 //   * weights are pre-tiled fp16 blobs (64 K x 128 N, 16 KB) streamed through a 5-stage
 //     shared-memory ring by bulk async copies (TMA engine, UBLKCP), optionally multicast to
 //     every CTA of a thread-block cluster so that L2 sees each byte once per cluster;
-//   * warp 0 = weight producer, warp 1 = single-thread tcgen05.mma issuer, warps 4..19 =
-//     epilogue (TMEM -> registers: demod, LeakyReLU, residual, ToRGB, next-layer input scale,
-//     fp16 pack -> shared memory).  The next layer's MMAs start as soon as the epilogue has
-//     produced the K-chunks / drained the accumulator columns they touch ("chase"), so the
-//     tensor pipe idles only for the first quarter of each epilogue.
+//   * warp 0 = weight producer, warps 1 and 3 = tcgen05.mma issuers (each owns two of the four 128-column
+//     accumulator blocks; one elected lane issues), warps 4..19 = epilogue (TMEM -> registers: LeakyReLU,
+//     residual, ToRGB, fp16 pack -> shared memory).
+//   * software pipeline between layers, in both directions ("staircase"): layer l+1's MMAs start as soon
+//     as the epilogue of layer l has produced the K-chunk they read and drained the accumulator block they
+//     overwrite (epi_done[j]); the epilogue of layer l starts on column chunk j as soon as accumulator
+//     block j is complete and no MMA of layer l still reads A-operand chunk j, which it overwrites in
+//     place (acc_ready[j]).  The tile order inside a layer is chosen to make both happen early.
+//   * both issuers observe every fill of the weight ring and a stage is recycled only when both have
+//     released it (an issuer that skipped the phases of tiles it does not own could alias a whole ring
+//     revolution on the parity wait).
 // Per-image modulation (mod_conv_fc.py:452-496): the prep kernel builds, once per forward and per image,
 // fp16 tiles of  W''[k][n] = s1p[k] * W[k][n] * d[n]  (the reference's modulated + demodulated weight);
 // all 512 pixel tiles of an image stream the same 9.3 MB, so the epilogue needs no per-column constants
@@ -49,7 +55,7 @@ struct Smem {
   alignas(8) uint64_t full[kStages];
   uint64_t empty[kStages];
   uint64_t epi_done[4];
-  uint64_t acc_full;
+  uint64_t acc_ready[4];   // accumulator block j complete AND A-operand chunk j no longer read by this layer's MMAs
   uint32_t tmem_base;
 };
 
@@ -65,12 +71,12 @@ struct KArgs {
   int B, N, in_dim, n_layers, skip_from, rgb_from, tiles_per_img, total_tiles;
   int layer_tile_off[kMaxLayers + 1];   // offset (in tiles) of each layer's first weight tile
   int layer_kc[kMaxLayers];             // number of K chunks of each layer (1 for the padded input layer)
-  // Issue order of a full layer's 32 weight tiles ("staircase"): entry = kc | nc << 4 | need << 8 where `need`
-  // is the epilogue chunk of the previous layer that must be complete (input K-chunk written, accumulator
-  // columns drained).  Tiles are stored in this order so the producer streams linearly.
+  // Issue order of a full layer's 32 weight tiles ("staircase"): entry = kc | nc << 4 | need << 8 | rdy << 12.
+  // `need` is the epilogue chunk of the previous layer that must be complete (input K-chunk written, accumulator
+  // columns drained); bit j of `rdy` says the tile's owner commits acc_ready[j] after it.  Tiles are stored in
+  // this order so the producer streams linearly.
   uint16_t order_full[32];
   uint16_t order_in[4];
-  int last_full[2], last_in[2];         // index of the last tile each issuer owns (nc>>1 == issuer)
 };
 
 __device__ __forceinline__ uint32_t cluster_ctarank() {
@@ -211,7 +217,7 @@ __global__ void __launch_bounds__(kThreads, 1) cips_tc_kernel(const KArgs a) {
       mbar_init(&s.empty[i], 2 * CL);   // both issuers release every stage (see the issuer loop)
     }
     for (int i = 0; i < 4; ++i) mbar_init(&s.epi_done[i], kNumEpiWarps);
-    mbar_init(&s.acc_full, 2);   // two MMA issuer warps, each commits once per layer
+    for (int i = 0; i < 4; ++i) mbar_init(&s.acc_ready[i], 2);   // two MMA issuer warps, each commits once per layer and chunk
     fence_mbar_init();
   }
   if (warp == 2) tmem_alloc<512>(&s.tmem_base);
@@ -266,7 +272,6 @@ __global__ void __launch_bounds__(kThreads, 1) cips_tc_kernel(const KArgs a) {
           const int ntiles = a.layer_kc[l] * 4;
           const bool full_layer = ntiles == 32;
           const uint16_t* order = full_layer ? a.order_full : a.order_in;
-          const int my_last = full_layer ? a.last_full[me] : a.last_in[me];
           int waited = -1;
 #pragma unroll 1
           for (int t = 0; t < ntiles; ++t) {
@@ -274,7 +279,7 @@ __global__ void __launch_bounds__(kThreads, 1) cips_tc_kernel(const KArgs a) {
             const uint32_t kc = e & 15u, nc = (e >> 4) & 15u;
             const bool mine = (nc >> 1) == me;
             if (mine) {
-              const int need = (int)(e >> 8);
+              const int need = (int)((e >> 8) & 15u);
               if (lane == 0) TRACE(it, 1 + me, (uint32_t)(l << 8 | t));          // tile reached
               if (need > waited) {
                 for (int j = waited + 1; j <= need; ++j) mbar_wait(&s.epi_done[j], epar);
@@ -298,7 +303,12 @@ __global__ void __launch_bounds__(kThreads, 1) cips_tc_kernel(const KArgs a) {
                 umma_ss_w(d, a_lo + 2 * kStepK16, b_lo + 2 * kStepK16, dhi, idesc, 1);
                 umma_ss_w(d, a_lo + 3 * kStepK16, b_lo + 3 * kStepK16, dhi, idesc, 1);
                 commit_stage_free<CL>(&s.empty[stage]);
-                if (t == my_last) tc_commit(&s.acc_full);
+                const uint32_t rdy = e >> 12;    // chunks j for which this is the issuer's last tile of S_j
+                if (rdy) {
+#pragma unroll
+                  for (int j = 0; j < 4; ++j)
+                    if (rdy & (1u << j)) tc_commit(&s.acc_ready[j]);
+                }
               }
             } else if (elect_one()) {
               observe_stage_free<CL>(&s.empty[stage]);
@@ -365,9 +375,6 @@ __global__ void __launch_bounds__(kThreads, 1) cips_tc_kernel(const KArgs a) {
           s.rgbw[(int)threadIdx.x - 128] = __ldg(a.rgbw + (size_t)blk * kH + ((int)threadIdx.x - 128));
           asm volatile("bar.sync 1, %0;" ::"n"(kNumEpiWarps * 32) : "memory");
         }
-        mbar_wait(&s.acc_full, (uint32_t)(it * L + l) & 1u);
-        if (threadIdx.x == 128) TRACE(it, 8, (uint32_t)(l << 8));               // accumulator complete
-        tc_fence_after();
         float* hid = (f.last && a.hidden_out && row_ok) ? a.hidden_out + ((size_t)img * a.N + pix) * kH : nullptr;
         // software pipeline over the 8 x 16-column slices this thread owns (chunk j, halves 0/1);
         // every address advances by a constant per chunk
@@ -383,18 +390,32 @@ __global__ void __launch_bounds__(kThreads, 1) cips_tc_kernel(const KArgs a) {
 #pragma unroll
           for (int g = 0; g < 4; ++g) rs[g] = p[g * kTileM];
         };
-        tmem_ld16(tcol, accA);
+        // chunk j starts as soon as accumulator block j is complete and no MMA of this layer still reads
+        // A-operand chunk j (acc_ready[j]); the rest of the layer's MMAs run underneath.
+        const uint32_t apar = (uint32_t)(it * L + l) & 1u;
+        bool have = false;                                      // slice (j, 0) already in flight
         if (f.add_res) load_res(rsA, rp);
 #pragma unroll 1
         for (int j = 0; j < 4; ++j) {
+          if (!have) {
+            mbar_wait(&s.acc_ready[j], apar);
+            if (threadIdx.x == 128) TRACE(it, 8, (uint32_t)(l << 8 | j));       // accumulator block j complete
+            tc_fence_after();
+            tmem_ld16(tcol, accA);
+          }
           tc_wait_ld();
           tmem_ld16(tcol + 16, accB);
           if (f.add_res) load_res(rsB, rp + 4 * kTileM);
           if (second) epi16<true>(accA, rsA, rwp, xp, rp, f, rgb0, rgb1, rgb2, hp);
           else epi16<false>(accA, rsA, rwp, xp, rp, f, rgb0, rgb1, rgb2, hp);
           tc_wait_ld();
+          have = false;
           if (j < 3) {
-            tmem_ld16(tcol + 128, accA);
+            have = __all_sync(0xffffffffu, mbar_test(&s.acc_ready[j + 1], apar)) != 0;
+            if (have) {
+              tc_fence_after();
+              tmem_ld16(tcol + 128, accA);
+            }
             if (f.add_res) load_res(rsA, rp + 32 * kTileM);
           }
           if (second) epi16<true>(accB, rsB, rwp + 16, xp + 2 * kLBO, rp + 4 * kTileM, f, rgb0, rgb1, rgb2, hp ? hp + 16 : nullptr);
@@ -597,18 +618,39 @@ int c3d_cips_fwd_tc(const C3dCipsParams* p, const C3dCipsWeights* w, const float
   ka.img_tile_stride = (size_t)off;
   // ---- staircase issue order (see KArgs::order_full)
   {
-    bool done[8][4] = {};
     int n = 0;
-    for (int j = 0; j < 4; ++j)
-      for (int kc = 0; kc < 2 * (j + 1) && kc < 8; ++kc)
+    // head as below; the tail (everything epilogue chunk 3 unlocks) is ordered so that accumulator block j
+    // completes -- and A-operand chunk j (kc = 2j, 2j+1) is read for the last time -- as early as possible:
+    //   (6,0)(7,0)(0,3)(1,3) | (6,1)(7,1)(2,3)(3,3) | (6,2)(7,2)(4,3)(5,3) | (6,3)(7,3)
+    auto put = [&](int kc, int nc, int need) { ka.order_full[n++] = (uint16_t)(kc | (nc << 4) | (need << 8)); };
+    for (int j = 0; j < 3; ++j)
+      for (int kc = 0; kc < 2 * (j + 1); ++kc)
         for (int nc = 0; nc <= j; ++nc)
-          if (!done[kc][nc]) {
-            done[kc][nc] = true;
-            ka.order_full[n++] = (uint16_t)(kc | (nc << 4) | (j << 8));
+          if (kc >= 2 * j || nc == j) put(kc, nc, j);
+    for (int j = 0; j < 4; ++j) {
+      put(6, j, 3);
+      put(7, j, 3);
+      if (j < 3) { put(2 * j, 3, 3); put(2 * j + 1, 3, 3); }
+    }
+    // commit mask (bits 12..15): tile is its owner's last one in S_j = {nc == j or kc/2 == j}; an issuer without a
+    // tile in S_j commits acc_ready[j] with its first tile
+    auto mark = [&](uint16_t* ord, int cnt) {
+      for (int me = 0; me < 2; ++me)
+        for (int j = 0; j < 4; ++j) {
+          int at = -1, first = -1;
+          for (int i = 0; i < cnt; ++i) {
+            const int kc = ord[i] & 15, nc = (ord[i] >> 4) & 15;
+            if ((nc >> 1) != me) continue;
+            if (first < 0) first = i;
+            if (nc == j || (kc >> 1) == j) at = i;
           }
+          if (at < 0) at = first;
+          ord[at] |= (uint16_t)(1u << (12 + j));
+        }
+    };
     for (int nc = 0; nc < 4; ++nc) ka.order_in[nc] = (uint16_t)(0 | (nc << 4) | (nc << 8));
-    for (int i = 0; i < 32; ++i) ka.last_full[((ka.order_full[i] >> 4) & 15) >> 1] = i;
-    for (int i = 0; i < 4; ++i) ka.last_in[((ka.order_in[i] >> 4) & 15) >> 1] = i;
+    mark(ka.order_full, 32);
+    mark(ka.order_in, 4);
   }
   // ---- prep: weights -> fp16 tiles (one launch), per-image epilogue vectors
   {

@@ -23,30 +23,31 @@ with torch.no_grad():
     n = lib.c3d_debug_cips_trace(buf, 8192)
 ev = [((v >> 56) & 0xFF, (v >> 40) & 0xFFFF, v & 0xFFFFFFFFFF) for v in buf[:n]]
 t0 = min(e[2] for e in ev)
-names = {1: "mma0 reach", 2: "mma1 reach", 3: "mma0 epi-ok", 4: "mma1 epi-ok", 5: "mma0 w-ok", 6: "mma1 w-ok", 8: "acc_full", 9: "chunk-done"}
-# per layer summary
-acc = {}
+# tags: 1/2 issuer reached tile, 3/4 epilogue dependency satisfied, 5/6 weight tile landed (= MMA issue),
+#       8 epilogue saw acc_ready[j] (a0 = layer << 8 | j), 9 epilogue warp finished chunk j (a0 = layer << 8 | warp << 2 | j)
+rdy = collections.defaultdict(dict)
 for tag, a0, t in ev:
     if tag == 8:
-        acc[a0 >> 8] = t - t0
-layers = sorted(acc)
+        rdy[a0 >> 8][a0 & 3] = t - t0
+done = collections.defaultdict(lambda: collections.defaultdict(list))
+for tag, a0, t in ev:
+    if tag == 9:
+        done[a0 >> 8][a0 & 3].append(t - t0)
+issue = collections.defaultdict(dict)
+for tag, a0, t in ev:
+    if tag in (5, 6):
+        issue[a0 >> 8][a0 & 0xFF] = (t - t0, tag - 5)
 print("events", n)
-for l in layers[2:8]:
-    nxt = acc.get(l + 1)
-    chunk = collections.defaultdict(list)
-    for tag, a0, t in ev:
-        if tag == 9 and (a0 >> 8) == l:
-            chunk[a0 & 3].append(t - t0 - acc[l])
-    line = f"layer {l:2d}: acc_full at {acc[l]:8d}; epilogue chunk done (max over warps): " + " ".join(f"c{j}={max(v)}" for j, v in sorted(chunk.items()))
-    line += "  (min: " + " ".join(f"{min(v)}" for j, v in sorted(chunk.items())) + ")"
-    if nxt: line += f"   next acc_full +{nxt - acc[l]}"
+layers = sorted(rdy)
+prev = None
+for l in layers:
+    base = rdy[l].get(0, 0)
+    line = f"layer {l:2d}: ready[0] at {base:8d}"
+    if prev is not None: line += f" (+{base - prev:6d} since previous layer)"
+    prev = base
+    line += "; ready j: " + " ".join(f"{rdy[l].get(j, 0) - base:6d}" for j in range(4))
+    line += "; chunk done (last warp): " + " ".join(f"{max(done[l][j]) - base:6d}" if done[l][j] else "     -" for j in range(4))
     print(line)
-    # MMA tiles of layer l+1 relative to acc[l]
-    for me in (0, 1):
-        tl = []
-        for t_idx in range(32):
-            r = [t for tag, a0, t in ev if tag == 1 + me and a0 == ((l + 1) << 8 | t_idx)]
-            e = [t for tag, a0, t in ev if tag == 3 + me and a0 == ((l + 1) << 8 | t_idx)]
-            w = [t for tag, a0, t in ev if tag == 5 + me and a0 == ((l + 1) << 8 | t_idx)]
-            if r: tl.append((t_idx, r[0] - t0 - acc[l], e[0] - r[0], w[0] - e[0]))
-        print(f"    issuer {me} tiles of layer {l+1} (idx: reach, epi-wait, w-wait): " + " ".join(f"{i}:{a},{b},{c}" for i, a, b, c in tl))
+    if l + 1 in issue and 2 <= l <= 7:
+        print("      layer %d MMA issue times rel. to ready[0] of layer %d (idx:clk/issuer): " % (l + 1, l) +
+              " ".join(f"{i}:{issue[l + 1][i][0] - base}/{issue[l + 1][i][1]}" for i in sorted(issue[l + 1])))
