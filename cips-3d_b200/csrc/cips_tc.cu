@@ -580,6 +580,52 @@ static int launch_cips(const KArgs& ka, int grid, cudaStream_t st) {
   return C3D_OK;
 }
 
+// Issue order of the weight tiles of one layer (see KArgs::order_full).  Host-only; also exported for the
+// CPU protocol test (c3d_debug_cips_tile_order).
+static void build_tile_order(uint16_t* order_full, uint16_t* order_in) {
+  int n = 0;
+  // head: group j (everything epilogue chunk j of the previous layer unlocks) = new K-chunks 2j, 2j+1 for the
+  // accumulator blocks <= j, plus the new accumulator block j for the K-chunks seen so far.
+  // tail (everything chunk 3 unlocks) is ordered so that accumulator block j completes -- and A-operand chunk j
+  // (kc = 2j, 2j+1) is read for the last time -- as early as possible:
+  //   (6,0)(7,0)(0,3)(1,3) | (6,1)(7,1)(2,3)(3,3) | (6,2)(7,2)(4,3)(5,3) | (6,3)(7,3)
+  auto put = [&](int kc, int nc, int need) { order_full[n++] = (uint16_t)(kc | (nc << 4) | (need << 8)); };
+  for (int j = 0; j < 3; ++j)
+    for (int kc = 0; kc < 2 * (j + 1); ++kc)
+      for (int nc = 0; nc <= j; ++nc)
+        if (kc >= 2 * j || nc == j) put(kc, nc, j);
+  for (int j = 0; j < 4; ++j) {
+    put(6, j, 3);
+    put(7, j, 3);
+    if (j < 3) { put(2 * j, 3, 3); put(2 * j + 1, 3, 3); }
+  }
+  // commit mask (bits 12..15): tile is its owner's last one in S_j = {nc == j or kc/2 == j}; an issuer without a
+  // tile in S_j commits acc_ready[j] with its first tile
+  auto mark = [&](uint16_t* ord, int cnt) {
+    for (int me = 0; me < 2; ++me)
+      for (int j = 0; j < 4; ++j) {
+        int at = -1, first = -1;
+        for (int i = 0; i < cnt; ++i) {
+          const int kc = ord[i] & 15, nc = (ord[i] >> 4) & 15;
+          if ((nc >> 1) != me) continue;
+          if (first < 0) first = i;
+          if (nc == j || (kc >> 1) == j) at = i;
+        }
+        if (at < 0) at = first;
+        ord[at] |= (uint16_t)(1u << (12 + j));
+      }
+  };
+  for (int nc = 0; nc < 4; ++nc) order_in[nc] = (uint16_t)(0 | (nc << 4) | (nc << 8));   // padded input layer: K = 64
+  mark(order_full, 32);
+  mark(order_in, 4);
+}
+
+extern "C" int c3d_debug_cips_tile_order(uint16_t* order_full32, uint16_t* order_in4) {
+  if (!order_full32 || !order_in4) return C3D_EINVAL;
+  build_tile_order(order_full32, order_in4);
+  return kStages;
+}
+
 int c3d_cips_fwd_tc(const C3dCipsParams* p, const C3dCipsWeights* w, const float* x, float* rgb, float* hidden_out,
                     void* workspace, size_t workspace_bytes, cudaStream_t st) {
   C3D_CHECK_ARG(p->hidden == kH, "cips(tc): hidden must be 512, got %d", p->hidden);
@@ -616,42 +662,7 @@ int c3d_cips_fwd_tc(const C3dCipsParams* p, const C3dCipsWeights* w, const float
   }
   ka.layer_tile_off[L] = off;
   ka.img_tile_stride = (size_t)off;
-  // ---- staircase issue order (see KArgs::order_full)
-  {
-    int n = 0;
-    // head as below; the tail (everything epilogue chunk 3 unlocks) is ordered so that accumulator block j
-    // completes -- and A-operand chunk j (kc = 2j, 2j+1) is read for the last time -- as early as possible:
-    //   (6,0)(7,0)(0,3)(1,3) | (6,1)(7,1)(2,3)(3,3) | (6,2)(7,2)(4,3)(5,3) | (6,3)(7,3)
-    auto put = [&](int kc, int nc, int need) { ka.order_full[n++] = (uint16_t)(kc | (nc << 4) | (need << 8)); };
-    for (int j = 0; j < 3; ++j)
-      for (int kc = 0; kc < 2 * (j + 1); ++kc)
-        for (int nc = 0; nc <= j; ++nc)
-          if (kc >= 2 * j || nc == j) put(kc, nc, j);
-    for (int j = 0; j < 4; ++j) {
-      put(6, j, 3);
-      put(7, j, 3);
-      if (j < 3) { put(2 * j, 3, 3); put(2 * j + 1, 3, 3); }
-    }
-    // commit mask (bits 12..15): tile is its owner's last one in S_j = {nc == j or kc/2 == j}; an issuer without a
-    // tile in S_j commits acc_ready[j] with its first tile
-    auto mark = [&](uint16_t* ord, int cnt) {
-      for (int me = 0; me < 2; ++me)
-        for (int j = 0; j < 4; ++j) {
-          int at = -1, first = -1;
-          for (int i = 0; i < cnt; ++i) {
-            const int kc = ord[i] & 15, nc = (ord[i] >> 4) & 15;
-            if ((nc >> 1) != me) continue;
-            if (first < 0) first = i;
-            if (nc == j || (kc >> 1) == j) at = i;
-          }
-          if (at < 0) at = first;
-          ord[at] |= (uint16_t)(1u << (12 + j));
-        }
-    };
-    for (int nc = 0; nc < 4; ++nc) ka.order_in[nc] = (uint16_t)(0 | (nc << 4) | (nc << 8));
-    mark(ka.order_full, 32);
-    mark(ka.order_in, 4);
-  }
+  build_tile_order(ka.order_full, ka.order_in);
   // ---- prep: weights -> fp16 tiles (one launch), per-image epilogue vectors
   {
     PrepArgs pa = {};

@@ -5,8 +5,8 @@
 // Work unit: a ray group (RG) of G = floor(128 / S) whole rays = one 128-row MMA block (rows =
 // sample points, ray-major).  A persistent CTA owns two independent TMEM "slots"
 // (A operand 128 cols + fp32 accumulator 128 cols each); each slot carries one RG through
-//     coarse:  L0 (FMA pipe: 3->128 FiLM+sin) -> MMA 128x128 -> FiLM+sin -> MMA 128x(64+sigma)
-//              -> FiLM+sin -> MMA 64x32 -> features/sigma to shared memory
+//     coarse:  MMA K=16 (layer 0: [x,y,z,1] x per-image folded FiLM weights) -> sin -> MMA 128x128
+//              -> FiLM+sin -> MMA 128x(64+sigma) -> FiLM+sin -> MMA 64x32 -> features/sigma to shared memory
 //     sample:  per-ray weights -> pdf/cdf -> inverse-CDF -> fine depths     (ray_math.cuh)
 //     fine:    the same MLP on the resampled points
 //     merge:   per-ray stable sort of the 2S depths, compositing weights

@@ -167,6 +167,16 @@ int c3d_upfirdn2d(const float* x, const float* kernel, float* y, int32_t planes,
 int c3d_selftest_umma(const float* a, const float* b, float* d, int32_t n, int32_t k,
                       int32_t a_in_tmem, void* stream);
 
+/* ------------------------------------------------------------------------------------
+ * Introspection for the CPU-side protocol test (host only, no GPU work): the order in which
+ * c3d_cips_fwd's kernel issues the 32 (K64 x N128) weight tiles of a 512x512 layer and the 4
+ * tiles of the padded input layer.  Entry = kc | nc << 4 | need << 8 | rdy << 12 (see
+ * csrc/cips_tc.cu, KArgs::order_full).  Returns the depth of the weight ring (> 0) or a
+ * negative C3D_E* code.  tests/test_cips_protocol_cpu.py replays the kernel's mbarrier
+ * protocol on it (no parity aliasing, no in-place overwrite of a live operand, no deadlock).
+ * ---------------------------------------------------------------------------------- */
+int c3d_debug_cips_tile_order(uint16_t* order_full32, uint16_t* order_in4);
+
 #ifdef __cplusplus
 }
 #endif
