@@ -66,6 +66,16 @@ def load():
         raise C3dError(f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'`. "
                        "cips3d_b200 has no CPU or PyTorch fallback.")
     lib = C.CDLL(LIB_PATH)
+    if hasattr(lib, "c3d_emulated"):
+        # tools/emu builds the same sources against a CPU emulation of CUDA for the CPU test suite; it must
+        # never stand in for the product library
+        raise C3dError(f"{LIB_PATH} is the CPU emulation build (test infrastructure); cips3d_b200 has no CPU path.")
+    _lib = bind(lib)
+    return _lib
+
+
+def bind(lib):
+    """Declare the C-ABI signatures (include/cips3d_b200.h) on a loaded library."""
     lib.c3d_version.restype = C.c_int
     lib.c3d_last_error.restype = C.c_char_p
     lib.c3d_device_supported.argtypes = [C.c_int]
@@ -84,7 +94,6 @@ def load():
     lib.c3d_selftest_umma.argtypes = [_fp, _fp, _fp, C.c_int32, C.c_int32, C.c_int32, _fp]
     if hasattr(lib, 'c3d_debug_cips_trace'):      # only in -DC3D_TRACE debug builds
         lib.c3d_debug_cips_trace.argtypes = [C.c_void_p, C.c_int]
-    _lib = lib
     return lib
 
 

@@ -7,6 +7,17 @@
 
 #include "../../include/cips3d_b200.h"
 
+// Every kernel launch and every PTX instruction of this library goes through the macros / wrappers of this
+// header, so that a -DC3D_EMU build (g++, tools/emu/c3d_emu.h: functional CPU emulation used by the CPU test
+// suite) can substitute them.  The product build never defines C3D_EMU.
+#ifdef C3D_EMU
+#include "c3d_emu.h"
+#else
+#define C3D_DYN_SMEM(type, name) extern __shared__ type name[]
+#define C3D_DYN_SMEM_ALIGNED(type, name, al) extern __shared__ __align__(al) type name[]
+#define C3D_LAUNCH(kernel, grid, block, smem, stream, ...) kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__)
+#endif
+
 // ---------------------------------------------------------------- host-side error plumbing
 void c3d_set_error(const char* fmt, ...);
 #define C3D_CHECK_ARG(cond, ...)        \
@@ -35,8 +46,11 @@ int c3d_device_sm_count(int dev);   // cached (api.cu)
 static inline int c3d_div_up(long long a, long long b) { return (int)((a + b - 1) / b); }
 
 // ---------------------------------------------------------------- PTX wrappers (device)
-#ifdef __CUDACC__
+#if defined(__CUDACC__) || defined(C3D_EMU)
 namespace c3d {
+#ifdef C3D_EMU
+#include "c3d_emu_ptx.h"
+#else
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));
@@ -106,30 +120,10 @@ __device__ __forceinline__ bool mbar_test(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
-// Spin with a watchdog: a protocol bug traps (-> CUDA error at the caller) instead of hanging the GPU.
-// Time-based (globaltimer), so slow instrumented replays (ncu source counters) do not trip it.
-#ifndef C3D_WATCHDOG_NS
-#define C3D_WATCHDOG_NS 20000000000ull   /* 20 s */
-#endif
 __device__ __forceinline__ unsigned long long c3d_globaltimer() {
   unsigned long long t;
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
   return t;
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  uint32_t spins = 0;
-  unsigned long long t0 = 0;
-  while (!mbar_try_wait(bar, parity)) {
-    if ((++spins & 1023u) == 0) {
-      const unsigned long long now = c3d_globaltimer();
-      if (t0 == 0) t0 = now;
-      else if (now - t0 > C3D_WATCHDOG_NS) {
-        printf("c3d watchdog: mbarrier wait timed out (block %d thread %d bar 0x%x parity %u)\n", (int)blockIdx.x,
-               (int)threadIdx.x, smem_u32(bar), parity);
-        __trap();
-      }
-    }
-  }
 }
 
 // ---- bulk async copy global -> shared (TMA engine, non-tensor form; SASS: UBLKCP)
@@ -174,29 +168,6 @@ __device__ __forceinline__ void tc_commit(uint64_t* bar) {
                : "memory");
 }
 
-// UMMA shared-memory matrix descriptor, K-major, no swizzle ("interleaved" canonical layout,
-// cute/arch/mma_sm100_desc.hpp SmemDescriptor + cute/atom/mma_traits_sm100.hpp:273-303):
-//   element (row r, k) lives at  (r%8)*16 + (r/8)*SBO + (k/8)*LBO + (k%8)*2   [bytes, 16-bit]
-// i.e. 8x(16 B) core matrices of 128 contiguous bytes.
-__device__ __forceinline__ uint64_t umma_desc_kmajor(uint32_t smem_addr, uint32_t lbo_bytes,
-                                                     uint32_t sbo_bytes) {
-  uint64_t d = 0;
-  d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
-  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
-  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
-  d |= (uint64_t)1 << 46;  // descriptor version 1 (Blackwell)
-  // base_offset = 0, lbo_mode = 0, layout_type = SWIZZLE_NONE (0)
-  return d;
-}
-// Instruction descriptor for kind::f16 (cute UMMA::InstrDescriptor): fp16 A/B, fp32 D,
-// both operands K-major, dense, no negate.
-__host__ __device__ constexpr uint32_t umma_idesc_f16(int M, int N) {
-  return (1u << 4)                      // c_format = F32
-         | (0u << 7) | (0u << 10)       // a_format = b_format = F16
-         | (0u << 15) | (0u << 16)      // a_major = b_major = K
-         | ((uint32_t)(N >> 3) << 17)   // n_dim
-         | ((uint32_t)(M >> 4) << 24);  // m_dim
-}
 // D[tmem] (+)= A[smem] * B[smem]^T     (single-thread issue)
 __device__ __forceinline__ void umma_ss(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc,
                                         uint32_t idesc, uint32_t accumulate) {
@@ -207,13 +178,6 @@ __device__ __forceinline__ void umma_ss(uint32_t d_tmem, uint64_t a_desc, uint64
       ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
-// Descriptor words for the hot issue loops: the 64-bit K-major/no-swizzle descriptor is
-//   lo = (addr >> 4) | (LBO >> 4) << 16,   hi = (SBO >> 4) | 1 << 14 (version)
-// so stepping along K or to another ring stage is a 32-bit add on `lo`.
-__device__ __forceinline__ uint32_t umma_desc_lo(uint32_t smem_addr, uint32_t lbo_bytes) {
-  return ((smem_addr >> 4) & 0x3FFF) | (((lbo_bytes >> 4) & 0x3FFF) << 16);
-}
-__device__ __forceinline__ constexpr uint32_t umma_desc_hi(uint32_t sbo_bytes) { return ((sbo_bytes >> 4) & 0x3FFF) | (1u << 14); }
 __device__ __forceinline__ void umma_ss_w(uint32_t d_tmem, uint32_t a_lo, uint32_t b_lo, uint32_t desc_hi, uint32_t idesc,
                                           uint32_t accumulate) {
   asm volatile(
@@ -292,6 +256,108 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&v)[16
       : "memory");
 }
 
+
+// ---- named barriers, register budgets, clusters
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+template <int kId, int kThreads>
+__device__ __forceinline__ void named_bar_sync_c() {
+  asm volatile("bar.sync %0, %1;" ::"n"(kId), "n"(kThreads) : "memory");
+}
+template <int kThreads>
+__device__ __forceinline__ void named_bar_sync_n(int id) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "n"(kThreads) : "memory");
+}
+template <int N>
+__device__ __forceinline__ void reg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
+template <int N>
+__device__ __forceinline__ void reg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// MMA completion -> arrive on the barrier at this offset in every CTA of `mask`
+__device__ __forceinline__ void tc_commit_mc(uint64_t* bar, uint16_t mask) {
+  asm volatile(
+      "tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+          smem_u32(bar)),
+      "h"(mask)
+      : "memory");
+}
+// plain arrive on the barrier at this offset in CTA `rank` of the cluster
+__device__ __forceinline__ void mbar_arrive_cluster(uint64_t* bar, uint32_t rank) {
+  asm volatile(
+      "{\n\t.reg .b32 ra;\n\tmapa.shared::cluster.u32 ra, %0, %1;\n\t"
+      "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t}" ::"r"(smem_u32(bar)),
+      "r"(rank)
+      : "memory");
+}
+// bulk copy multicast to the same offset (data and barrier) of every CTA in `mask`
+__device__ __forceinline__ void bulk_g2s_mc(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar, uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;"
+      ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(bytes), "r"(smem_u32(bar)), "h"(mask)
+      : "memory");
+}
+#endif  // !C3D_EMU  (end of the PTX section; everything below is plain C++ shared with the emulated build)
+
+// Spin with a watchdog: a protocol bug traps (-> CUDA error at the caller) instead of hanging the GPU.
+// Time-based (globaltimer), so slow instrumented replays (ncu source counters) do not trip it.
+#ifndef C3D_WATCHDOG_NS
+#define C3D_WATCHDOG_NS 20000000000ull   /* 20 s */
+#endif
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t spins = 0;
+  unsigned long long t0 = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    if ((++spins & 1023u) == 0) {
+      const unsigned long long now = c3d_globaltimer();
+      if (t0 == 0) t0 = now;
+      else if (now - t0 > C3D_WATCHDOG_NS) {
+        printf("c3d watchdog: mbarrier wait timed out (block %d thread %d bar 0x%x parity %u)\n", (int)blockIdx.x,
+               (int)threadIdx.x, smem_u32(bar), parity);
+        __trap();
+      }
+    }
+  }
+}
+
+
+// UMMA shared-memory matrix descriptor, K-major, no swizzle ("interleaved" canonical layout,
+// cute/arch/mma_sm100_desc.hpp SmemDescriptor + cute/atom/mma_traits_sm100.hpp:273-303):
+//   element (row r, k) lives at  (r%8)*16 + (r/8)*SBO + (k/8)*LBO + (k%8)*2   [bytes, 16-bit]
+// i.e. 8x(16 B) core matrices of 128 contiguous bytes.
+__device__ __forceinline__ uint64_t umma_desc_kmajor(uint32_t smem_addr, uint32_t lbo_bytes,
+                                                     uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;  // descriptor version 1 (Blackwell)
+  // base_offset = 0, lbo_mode = 0, layout_type = SWIZZLE_NONE (0)
+  return d;
+}
+// Instruction descriptor for kind::f16 (cute UMMA::InstrDescriptor): fp16 A/B, fp32 D,
+// both operands K-major, dense, no negate.
+__host__ __device__ constexpr uint32_t umma_idesc_f16(int M, int N) {
+  return (1u << 4)                      // c_format = F32
+         | (0u << 7) | (0u << 10)       // a_format = b_format = F16
+         | (0u << 15) | (0u << 16)      // a_major = b_major = K
+         | ((uint32_t)(N >> 3) << 17)   // n_dim
+         | ((uint32_t)(M >> 4) << 24);  // m_dim
+}
+// Descriptor words for the hot issue loops: the 64-bit K-major/no-swizzle descriptor is
+//   lo = (addr >> 4) | (LBO >> 4) << 16,   hi = (SBO >> 4) | 1 << 14 (version)
+// so stepping along K or to another ring stage is a 32-bit add on `lo`.
+__device__ __forceinline__ uint32_t umma_desc_lo(uint32_t smem_addr, uint32_t lbo_bytes) {
+  return ((smem_addr >> 4) & 0x3FFF) | (((lbo_bytes >> 4) & 0x3FFF) << 16);
+}
+__device__ __forceinline__ constexpr uint32_t umma_desc_hi(uint32_t sbo_bytes) { return ((sbo_bytes >> 4) & 0x3FFF) | (1u << 14); }
 // fp32 -> (hi, lo) fp16 split: hi = rn(x), lo = rn(x - hi); x ~= hi + lo to ~22 bits.
 __device__ __forceinline__ void split_f16(float x0, float x1, uint32_t& hi, uint32_t& lo) {
   __half2 h = __floats2half2_rn(x0, x1);
@@ -306,4 +372,4 @@ __device__ __forceinline__ uint32_t pack_f16(float x0, float x1) {
 }
 
 }  // namespace c3d
-#endif  // __CUDACC__
+#endif  // __CUDACC__ || C3D_EMU

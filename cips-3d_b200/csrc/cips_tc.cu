@@ -79,25 +79,12 @@ struct KArgs {
   uint16_t order_in[4];
 };
 
-__device__ __forceinline__ uint32_t cluster_ctarank() {
-  uint32_t r;
-  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
-  return r;
-}
-__device__ __forceinline__ void cluster_sync_all() {
-  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
 template <int CL>
 __device__ __forceinline__ void commit_stage_free(uint64_t* bar) {
   if (CL == 1) {
     tc_commit(bar);
   } else {
-    const uint16_t mask = (uint16_t)((1u << CL) - 1);
-    asm volatile(
-        "tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
-            smem_u32(bar)),
-        "h"(mask)
-        : "memory");
+    tc_commit_mc(bar, (uint16_t)((1u << CL) - 1));
   }
 }
 // non-owner issuer: "I have observed this fill" -> one plain arrive on the stage's empty barrier of every CTA
@@ -108,12 +95,7 @@ __device__ __forceinline__ void observe_stage_free(uint64_t* bar) {
     mbar_arrive(bar);
   } else {
 #pragma unroll
-    for (uint32_t r = 0; r < (uint32_t)CL; ++r)
-      asm volatile(
-          "{\n\t.reg .b32 ra;\n\tmapa.shared::cluster.u32 ra, %0, %1;\n\t"
-          "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t}" ::"r"(smem_u32(bar)),
-          "r"(r)
-          : "memory");
+    for (uint32_t r = 0; r < (uint32_t)CL; ++r) mbar_arrive_cluster(bar, r);
   }
 }
 template <int CL>
@@ -122,11 +104,7 @@ __device__ __forceinline__ void load_w_tile(void* dst, const uint8_t* src, uint6
     bulk_g2s(dst, src, kWTileBytes, bar);
   } else {
     constexpr uint32_t slice = kWTileBytes / CL;
-    const uint16_t mask = (uint16_t)((1u << CL) - 1);
-    asm volatile(
-        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;"
-        ::"r"(smem_u32((uint8_t*)dst + rank * slice)), "l"(src + rank * slice), "r"(slice), "r"(smem_u32(bar)), "h"(mask)
-        : "memory");
+    bulk_g2s_mc((uint8_t*)dst + rank * slice, src + rank * slice, slice, bar, (uint16_t)((1u << CL) - 1));
   }
 }
 
@@ -145,11 +123,6 @@ __device__ __forceinline__ void trace_ev(int it, uint32_t tag, uint32_t a0) {
 #else
 #define TRACE(it, tag, a0)
 #endif
-
-template <int N>
-__device__ __forceinline__ void reg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
-template <int N>
-__device__ __forceinline__ void reg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
 
 struct EpiFlags {
   bool add_res, keep_res, do_rgb, last;
@@ -205,7 +178,7 @@ __device__ __forceinline__ void epi16(const uint32_t (&acc)[16], const float4 (&
 
 template <int CL>
 __global__ void __launch_bounds__(kThreads, 1) cips_tc_kernel(const KArgs a) {
-  extern __shared__ uint8_t smem_raw[];
+  C3D_DYN_SMEM(uint8_t, smem_raw);
   // identical offset in every CTA of a cluster (multicast lands at the same CTA-relative address)
   Smem& s = *reinterpret_cast<Smem*>(smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u));
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -373,7 +346,7 @@ __global__ void __launch_bounds__(kThreads, 1) cips_tc_kernel(const KArgs a) {
         f.do_rgb = second && blk >= a.rgb_from;
         if (f.do_rgb) {   // ToRGB weights of this block -> shared memory (overlaps the MMAs)
           s.rgbw[(int)threadIdx.x - 128] = __ldg(a.rgbw + (size_t)blk * kH + ((int)threadIdx.x - 128));
-          asm volatile("bar.sync 1, %0;" ::"n"(kNumEpiWarps * 32) : "memory");
+          named_bar_sync_c<1, kNumEpiWarps * 32>();
         }
         float* hid = (f.last && a.hidden_out && row_ok) ? a.hidden_out + ((size_t)img * a.N + pix) * kH : nullptr;
         // software pipeline over the 8 x 16-column slices this thread owns (chunk j, halves 0/1);
@@ -430,11 +403,11 @@ __global__ void __launch_bounds__(kThreads, 1) cips_tc_kernel(const KArgs a) {
           if (hp) hp += 128;
         }
       }
-      asm volatile("bar.sync 1, %0;" ::"n"(kNumEpiWarps * 32) : "memory");   // rgbw (aliased) no longer read
+      named_bar_sync_c<1, kNumEpiWarps * 32>();   // rgbw (aliased) no longer read
       s.rgb_part[wg][row][0] = rgb0;
       s.rgb_part[wg][row][1] = rgb1;
       s.rgb_part[wg][row][2] = rgb2;
-      asm volatile("bar.sync 1, %0;" ::"n"(kNumEpiWarps * 32) : "memory");
+      named_bar_sync_c<1, kNumEpiWarps * 32>();
       if (wg == 0 && row_ok) {
         float o[3];
 #pragma unroll
@@ -443,7 +416,7 @@ __global__ void __launch_bounds__(kThreads, 1) cips_tc_kernel(const KArgs a) {
         float* op = a.rgb + ((size_t)img * a.N + pix) * 3;
         op[0] = o[0]; op[1] = o[1]; op[2] = o[2];
       }
-      asm volatile("bar.sync 1, %0;" ::"n"(kNumEpiWarps * 32) : "memory");
+      named_bar_sync_c<1, kNumEpiWarps * 32>();
     }
   }
   // ------------------------------------------------------------ teardown
@@ -563,6 +536,11 @@ static int launch_cips(const KArgs& ka, int grid, cudaStream_t st) {
     C3D_CUDA(cudaFuncSetAttribute(cips_tc_kernel<CL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_set.fetch_or(1ull << (dev & 63));
   }
+#ifdef C3D_EMU
+  c3d_count_launch();
+  C3D_CUDA(C3D_LAUNCH_CLUSTER(cips_tc_kernel<CL>, grid, kThreads, smem, st, CL, ka));
+  return C3D_OK;
+#else
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(grid);
   cfg.blockDim = dim3(kThreads);
@@ -578,6 +556,7 @@ static int launch_cips(const KArgs& ka, int grid, cudaStream_t st) {
   c3d_count_launch();
   C3D_CUDA(cudaLaunchKernelEx(&cfg, cips_tc_kernel<CL>, ka));
   return C3D_OK;
+#endif
 }
 
 // Issue order of the weight tiles of one layer (see KArgs::order_full).  Host-only; also exported for the
@@ -677,11 +656,11 @@ int c3d_cips_fwd_tc(const C3dCipsParams* p, const C3dCipsWeights* w, const float
     pa.B = p->batch;
     for (int i = 0; i < 32; ++i) pa.order_full[i] = ka.order_full[i];
     for (int i = 0; i < 4; ++i) pa.order_in[i] = ka.order_in[i];
-    cips_prep_weights_kernel<<<dim3(ka.layer_tile_off[L], p->batch), 256, 0, st>>>(pa, (__half*)(base + ws.wtiles));
+    C3D_LAUNCH(cips_prep_weights_kernel, dim3(ka.layer_tile_off[L], p->batch), 256, 0, st, pa, (__half*)(base + ws.wtiles));
     C3D_LAUNCH_CHECK();
   }
-  cips_prep_consts_kernel<<<p->n_blocks, 256, 0, st>>>(*w, p->n_blocks, p->rgb_from, (float4*)(base + ws.rgbw),
-                                                       (float*)(base + ws.rgbb));
+  C3D_LAUNCH(cips_prep_consts_kernel, p->n_blocks, 256, 0, st, *w, p->n_blocks, p->rgb_from, (float4*)(base + ws.rgbw),
+             (float*)(base + ws.rgbb));
   C3D_LAUNCH_CHECK();
   int cl = 1;
   const int grid = cips_grid(p, &cl);

@@ -52,7 +52,7 @@ __global__ void __launch_bounds__(256) upfirdn2d_kernel(
     const float* __restrict__ x, const float* __restrict__ kernel, float* __restrict__ y, int in_h,
     int in_w, int out_h, int out_w, int kh, int kw, int up_x, int up_y, int down_x, int down_y,
     int pad_x0, int pad_y0, int tiles_x) {
-  extern __shared__ float sm[];
+  C3D_DYN_SMEM(float, sm);
   __shared__ float sk[kMaxK * kMaxK];
   const int plane = blockIdx.y;
   const int tx0 = (blockIdx.x % tiles_x) * kTileW, ty0 = (blockIdx.x / tiles_x) * kTileH;
@@ -173,14 +173,17 @@ extern "C" int c3d_bias_act(const float* x, const float* bias, const float* ref,
   if (vec) {
     long long nv = size_x / 4;
     int grid = (int)(nv / 256 + 1 < (long long)sms * 16 ? nv / 256 + 1 : (long long)sms * 16);
-    bias_act_kernel<4><<<grid, 256, 0, st>>>(x, bias, ref, y, nv, step_b, size_b, act, grad, alpha, scale);
+    C3D_LAUNCH(bias_act_kernel<4>, grid, 256, 0, st, x, bias, ref, y, nv, step_b, size_b, act, grad, alpha, scale);
   } else {
     int grid = (int)(size_x / 256 + 1 < (long long)sms * 16 ? size_x / 256 + 1 : (long long)sms * 16);
-    bias_act_kernel<1><<<grid, 256, 0, st>>>(x, bias, ref, y, size_x, step_b, size_b, act, grad, alpha, scale);
+    C3D_LAUNCH(bias_act_kernel<1>, grid, 256, 0, st, x, bias, ref, y, size_x, step_b, size_b, act, grad, alpha, scale);
   }
   C3D_LAUNCH_CHECK();
   return C3D_OK;
 }
+
+static constexpr auto blur44 = blur_tile_kernel<4, 4>;
+static constexpr auto blur00 = blur_tile_kernel<0, 0>;
 
 extern "C" int c3d_upfirdn2d(const float* x, const float* kernel, float* y, int32_t planes,
                              int32_t in_h, int32_t in_w, int32_t kh, int32_t kw, int32_t up_x,
@@ -203,10 +206,10 @@ extern "C" int c3d_upfirdn2d(const float* x, const float* kernel, float* y, int3
       int np = planes - p0 < 65535 ? planes - p0 : 65535;
       dim3 grid(c3d_div_up(out_w, kBW), c3d_div_up(out_h, kBH), np);
       if (kh == 4 && kw == 4)
-        blur_tile_kernel<4, 4><<<grid, 256, 0, st>>>(x + (size_t)p0 * in_h * in_w, kernel, y + (size_t)p0 * out_h * out_w,
+        C3D_LAUNCH(blur44, grid, 256, 0, st, x + (size_t)p0 * in_h * in_w, kernel, y + (size_t)p0 * out_h * out_w,
                                                      in_h, in_w, out_h, out_w, kh, kw, pad_x0, pad_y0);
       else
-        blur_tile_kernel<0, 0><<<grid, 256, 0, st>>>(x + (size_t)p0 * in_h * in_w, kernel, y + (size_t)p0 * out_h * out_w,
+        C3D_LAUNCH(blur00, grid, 256, 0, st, x + (size_t)p0 * in_h * in_w, kernel, y + (size_t)p0 * out_h * out_w,
                                                      in_h, in_w, out_h, out_w, kh, kw, pad_x0, pad_y0);
       C3D_LAUNCH_CHECK();
     }
@@ -217,7 +220,7 @@ extern "C" int c3d_upfirdn2d(const float* x, const float* kernel, float* y, int3
   for (int p0 = 0; p0 < planes; p0 += 65535) {  // gridDim.y limit
     int np = planes - p0 < 65535 ? planes - p0 : 65535;
     dim3 grid(tiles_x * tiles_y, np);
-    upfirdn2d_kernel<<<grid, 256, smem, st>>>(x + (size_t)p0 * in_h * in_w, kernel,
+    C3D_LAUNCH(upfirdn2d_kernel, grid, 256, smem, st, x + (size_t)p0 * in_h * in_w, kernel,
                                               y + (size_t)p0 * out_h * out_w, in_h, in_w, out_h, out_w,
                                               kh, kw, up_x, up_y, down_x, down_y, pad_x0, pad_y0, tiles_x);
     C3D_LAUNCH_CHECK();

@@ -102,21 +102,6 @@ __device__ __forceinline__ void rtrace(int it, uint32_t tag, uint32_t a0) {
 #else
 #define RTRACE(it, tag, a0)
 #endif
-template <int N>
-__device__ __forceinline__ void reg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
-template <int N>
-__device__ __forceinline__ void reg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
-__device__ __forceinline__ bool mbar_test(uint64_t* bar, uint32_t parity) {
-  uint32_t ok;
-  asm volatile(
-      "{\n\t.reg .pred P;\n\t"
-      "mbarrier.test_wait.parity.shared::cta.b64 P, [%1], %2;\n\t"
-      "selp.u32 %0, 1, 0, P;\n\t}"
-      : "=r"(ok)
-      : "r"(smem_u32(bar)), "r"(parity)
-      : "memory");
-  return ok != 0;
-}
 
 // ---- write 16 consecutive K values (fp32) of this thread's row into the TMEM A operand (hi, lo)
 __device__ __forceinline__ void store_a16(uint32_t a_hi_col, uint32_t a_lo_col, const float (&v)[16]) {
@@ -150,7 +135,7 @@ __device__ __forceinline__ float sample_alpha(float delta, float sigma, float no
 }
 
 __global__ void __launch_bounds__(640, 1) ray_siren_tc_kernel(const KArgs a) {
-  extern __shared__ uint8_t smem_raw[];
+  C3D_DYN_SMEM(uint8_t, smem_raw);
   Smem& s = *reinterpret_cast<Smem*>(smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u));
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const C3dRayParams& p = a.p;
@@ -246,7 +231,7 @@ __global__ void __launch_bounds__(640, 1) ray_siren_tc_kernel(const KArgs a) {
     const uint32_t lane_sel = (uint32_t)(q * 32) << 16;
     const uint32_t a_hi = tmem + (uint32_t)(sl * 256) + lane_sel, a_lo = a_hi + 64, dcol = a_hi + 128;
     const int bar_id = 1 + sl;
-    auto slot_sync = [&]() { asm volatile("bar.sync %0, 256;" ::"r"(bar_id) : "memory"); };
+    auto slot_sync = [&]() { named_bar_sync_n<256>(bar_id); };
     uint32_t dpar = 0;
     auto signal_a = [&]() {
       tc_wait_st();
@@ -623,7 +608,7 @@ int c3d_ray_siren_fwd_tc(const C3dRayParams* p, const C3dSirenWeights* w, const 
   }
   const int sms = c3d_device_sm_count(dev);
   uint8_t* base = (uint8_t*)workspace;
-  ray_prep_kernel<<<64, 256, 0, st>>>(*w, p->batch, base + ws.blob, (ImgConsts*)(base + ws.consts));
+  C3D_LAUNCH(ray_prep_kernel, 64, 256, 0, st, *w, p->batch, base + ws.blob, (ImgConsts*)(base + ws.consts));
   C3D_LAUNCH_CHECK();
   KArgs ka = {};
   ka.p = *p;
@@ -644,7 +629,7 @@ int c3d_ray_siren_fwd_tc(const C3dRayParams* p, const C3dSirenWeights* w, const 
   int grid = (ka.total_groups + 1) / 2;
   if (grid > sms) grid = sms;
   if (grid < 1) grid = 1;
-  ray_siren_tc_kernel<<<grid, 640, smem, st>>>(ka);
+  C3D_LAUNCH(ray_siren_tc_kernel, grid, 640, smem, st, ka);
   C3D_LAUNCH_CHECK();
   return C3D_OK;
 }

@@ -90,7 +90,7 @@ __global__ void __launch_bounds__(256) gemm_epi_kernel(GemmArgs a) {
 template <int EPI>
 static int launch_gemm(const GemmArgs& a, cudaStream_t st) {
   dim3 grid(c3d_div_up(a.M, 64), c3d_div_up(a.N, 64));
-  gemm_epi_kernel<EPI><<<grid, 256, 0, st>>>(a);
+  C3D_LAUNCH(gemm_epi_kernel<EPI>, grid, 256, 0, st, a);
   C3D_LAUNCH_CHECK();
   return C3D_OK;
 }
@@ -253,7 +253,7 @@ static int siren_tail(const C3dSirenWeights& w, long long P, int rows_per_img, i
   g.C = h1; g.ldc = 128; g.bias = w.b1; g.g = w.gamma1 + (size_t)b0 * 128; g.b = w.beta1 + (size_t)b0 * 128;
   if (int e = launch_gemm<EPI_FILM_SIN>(g, st)) return e;
   // sigma head -> out33[:, 32]
-  skinny_linear_kernel<<<c3d_div_up(P, 256), 256, 0, st>>>(h1, 128, 128, w.w_sigma, w.b_sigma, 1, out33,
+  C3D_LAUNCH(skinny_linear_kernel, c3d_div_up(P, 256), 256, 0, st, h1, 128, 128, w.w_sigma, w.b_sigma, 1, out33,
                                                           kOutC, kFeat, (int)P, 0, 0);
   C3D_LAUNCH_CHECK();
   // color_layer_sine
@@ -304,25 +304,25 @@ int c3d_ray_siren_fwd_simt(const C3dRayParams* p, const C3dSirenWeights* w, cons
   for (int b0 = 0; b0 < p->batch; b0 += (int)cb) {
     int nb = (int)((p->batch - b0) < cb ? (p->batch - b0) : cb);
     long long P = (long long)nb * N * S, NR = (long long)nb * N;
-    coarse_points_h0_kernel<<<c3d_div_up(P, 8), 256, 0, st>>>(*p, *w, *io, b0, nb, zbuf, h0);
+    C3D_LAUNCH(coarse_points_h0_kernel, c3d_div_up(P, 8), 256, 0, st, *p, *w, *io, b0, nb, zbuf, h0);
     C3D_LAUNCH_CHECK();
     if (int e = siren_tail(*w, P, N * S, b0, h0, h1, h2, c33, st)) return e;
     if (io->dbg_coarse) {
-      copy_rows_kernel<<<c3d_div_up(P * 33, 256), 256, 0, st>>>(c33, io->dbg_coarse + (size_t)b0 * N * S * 33, P * 33);
+      C3D_LAUNCH(copy_rows_kernel, c3d_div_up(P * 33, 256), 256, 0, st, c33, io->dbg_coarse + (size_t)b0 * N * S * 33, P * 33);
       C3D_LAUNCH_CHECK();
     }
     if (p->hierarchical) {
-      fine_z_kernel<<<c3d_div_up(NR, 128), 128, 0, st>>>(*p, *io, b0, nb, zbuf, c33, fzbuf);
+      C3D_LAUNCH(fine_z_kernel, c3d_div_up(NR, 128), 128, 0, st, *p, *io, b0, nb, zbuf, c33, fzbuf);
       C3D_LAUNCH_CHECK();
-      fine_points_h0_kernel<<<c3d_div_up(P, 8), 256, 0, st>>>(*p, *w, *io, b0, nb, fzbuf, h0);
+      C3D_LAUNCH(fine_points_h0_kernel, c3d_div_up(P, 8), 256, 0, st, *p, *w, *io, b0, nb, fzbuf, h0);
       C3D_LAUNCH_CHECK();
       if (int e = siren_tail(*w, P, N * S, b0, h0, h1, h2, f33, st)) return e;
       if (io->dbg_fine) {
-        copy_rows_kernel<<<c3d_div_up(P * 33, 256), 256, 0, st>>>(f33, io->dbg_fine + (size_t)b0 * N * S * 33, P * 33);
+        C3D_LAUNCH(copy_rows_kernel, c3d_div_up(P * 33, 256), 256, 0, st, f33, io->dbg_fine + (size_t)b0 * N * S * 33, P * 33);
         C3D_LAUNCH_CHECK();
       }
     }
-    composite_kernel<<<c3d_div_up(NR, 128), 128, 0, st>>>(*p, *io, b0, nb, zbuf, c33, fzbuf, f33);
+    C3D_LAUNCH(composite_kernel, c3d_div_up(NR, 128), 128, 0, st, *p, *io, b0, nb, zbuf, c33, fzbuf, f33);
     C3D_LAUNCH_CHECK();
   }
   return C3D_OK;
@@ -364,7 +364,7 @@ int c3d_cips_fwd_simt(const C3dCipsParams* p, const C3dCipsWeights* w, const flo
     cur = buf[t2]; cur_dim = H; cur_buf = t2;
     if (blk >= p->rgb_from) {
       bool last = blk == p->n_blocks - 1;
-      skinny_linear_kernel<<<c3d_div_up(M, 256), 256, 0, st>>>(cur, H, H, w->rgb_w[blk], w->rgb_b[blk], 3, rgb, 3, 0,
+      C3D_LAUNCH(skinny_linear_kernel, c3d_div_up(M, 256), 256, 0, st, cur, H, H, w->rgb_w[blk], w->rgb_b[blk], 3, rgb, 3, 0,
                                                               (int)M, rgb_started ? 1 : 0, last ? 1 : 0);
       C3D_LAUNCH_CHECK();
       rgb_started = true;
@@ -372,7 +372,7 @@ int c3d_cips_fwd_simt(const C3dCipsParams* p, const C3dCipsWeights* w, const flo
   }
   if (!rgb_started) C3D_CUDA(cudaMemsetAsync(rgb, 0, (size_t)M * 3 * sizeof(float), st));  // tanh(0)
   if (hidden_out) {
-    copy_rows_kernel<<<c3d_div_up(M * H, 256), 256, 0, st>>>(cur, hidden_out, M * H);
+    C3D_LAUNCH(copy_rows_kernel, c3d_div_up(M * H, 256), 256, 0, st, cur, hidden_out, M * H);
     C3D_LAUNCH_CHECK();
   }
   return C3D_OK;

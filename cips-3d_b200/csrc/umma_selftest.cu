@@ -11,7 +11,7 @@ namespace c3d {
 __global__ void __launch_bounds__(128, 1)
 umma_selftest_kernel(const float* __restrict__ A, const float* __restrict__ B, float* __restrict__ D,
                      int N, int K, int a_in_tmem) {
-  extern __shared__ __align__(1024) uint8_t smem[];
+  C3D_DYN_SMEM_ALIGNED(uint8_t, smem, 1024);
   __shared__ uint64_t bar;
   __shared__ uint32_t tmem_base_s;
   const int tid = threadIdx.x, warp = tid / 32, lane = tid % 32;
@@ -97,7 +97,7 @@ extern "C" int c3d_selftest_umma(const float* a, const float* b, float* d, int32
   C3D_CHECK_ARG(k >= 16 && k <= 256 && k % 16 == 0, "selftest_umma: K must be a multiple of 16 in [16,256]");
   size_t smem = (size_t)(128 + n) * k * 2;
   C3D_CUDA(cudaFuncSetAttribute(c3d::umma_selftest_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  c3d::umma_selftest_kernel<<<1, 128, smem, (cudaStream_t)stream>>>(a, b, d, n, k, a_in_tmem);
+  C3D_LAUNCH(c3d::umma_selftest_kernel, 1, 128, smem, (cudaStream_t)stream, a, b, d, n, k, a_in_tmem);
   C3D_LAUNCH_CHECK();
   return C3D_OK;
 }

@@ -1,0 +1,46 @@
+"""Build libcips3d_b200_emu.so: the product's csrc/*.cu compiled as plain C++ (g++ -DC3D_EMU) against the
+functional CPU emulation of CUDA/PTX in c3d_emu.h.  Test infrastructure only -- never loaded by the package."""
+import glob
+import os
+import subprocess
+import sys
+from concurrent.futures import ThreadPoolExecutor
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+CSRC = os.path.join(ROOT, "cips-3d_b200", "csrc")
+OUT_DIR = os.path.join(HERE, "_build")
+LIB = os.path.join(OUT_DIR, "libcips3d_b200_emu.so")
+CUDA_INC = os.environ.get("CUDA_INC", "/usr/local/cuda/include")
+FLAGS = ["-std=c++17", "-O2", "-g", "-fPIC", "-DC3D_EMU", "-ffp-contract=off", "-fno-strict-aliasing", "-Wno-attributes",
+         "-Wno-unknown-pragmas", "-Wno-unused-value", "-I", HERE, "-I", CUDA_INC]
+
+
+def build(force=False, extra_defs=()):
+    os.makedirs(OUT_DIR, exist_ok=True)
+    srcs = sorted(glob.glob(os.path.join(CSRC, "*.cu"))) + [os.path.join(HERE, "emu_impl.cpp")]
+    deps = srcs + glob.glob(os.path.join(CSRC, "*.cuh")) + glob.glob(os.path.join(HERE, "*.h")) + \
+        glob.glob(os.path.join(ROOT, "include", "*.h")) + [os.path.abspath(__file__)]
+    newest = max(os.path.getmtime(d) for d in deps)
+    if not force and os.path.exists(LIB) and os.path.getmtime(LIB) > newest:
+        return LIB
+    gxx = os.environ.get("CXX", "g++")
+
+    def compile_one(src):
+        obj = os.path.join(OUT_DIR, os.path.basename(src) + ".o")
+        cmd = [gxx] + FLAGS + [f"-D{d}" for d in extra_defs] + ["-x", "c++", "-c", src, "-o", obj]
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError(f"emu build failed for {src}:\n{r.stderr[-6000:]}")
+        return obj
+
+    with ThreadPoolExecutor(max_workers=8) as ex:
+        objs = list(ex.map(compile_one, srcs))
+    r = subprocess.run([gxx, "-shared", "-o", LIB] + objs, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("emu link failed:\n" + r.stderr[-4000:])
+    return LIB
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv))
