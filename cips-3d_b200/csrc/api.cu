@@ -47,6 +47,9 @@ extern "C" int c3d_device_supported(int dev) {
   return (g_dev_cc[dev].load() - 1000) / 10 == 10 ? 1 : 0;
 }
 int c3d_device_sm_count(int dev) {
+#ifdef C3D_EMU
+  return emu::config().sms;      // tests change the emulated SM count between calls
+#endif
   if (dev < 0 || dev >= 64) return 148;
   if (g_dev_cc[dev].load() == 0) query_device(dev);
   return g_dev_sms[dev].load();

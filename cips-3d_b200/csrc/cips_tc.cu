@@ -187,7 +187,11 @@ __global__ void __launch_bounds__(kThreads, 1) cips_tc_kernel(const KArgs a) {
   if (threadIdx.x == 0) {
     for (int i = 0; i < kStages; ++i) {
       mbar_init(&s.full[i], 1);
+#ifdef C3D_INJECT_RING_RACE           // test-only (tests/test_emu_cpu.py): re-creates the round-1 parity-aliasing race
+      mbar_init(&s.empty[i], CL);
+#else
       mbar_init(&s.empty[i], 2 * CL);   // both issuers release every stage (see the issuer loop)
+#endif
     }
     for (int i = 0; i < 4; ++i) mbar_init(&s.epi_done[i], kNumEpiWarps);
     for (int i = 0; i < 4; ++i) mbar_init(&s.acc_ready[i], 2);   // two MMA issuer warps, each commits once per layer and chunk
@@ -263,6 +267,9 @@ __global__ void __launch_bounds__(kThreads, 1) cips_tc_kernel(const KArgs a) {
             // BOTH issuers observe every fill of every stage, in ring order, and a stage is released only when
             // both have (empty count 2): an issuer that skipped the phases of tiles it does not own could see
             // full[stage] one whole revolution stale (parity aliasing) whenever the epilogue outruns the refill.
+#ifdef C3D_INJECT_RING_RACE
+            if (mine)
+#endif
             mbar_wait(&s.full[stage], phase);
             if (mine) {
               if (lane == 0) TRACE(it, 5 + me, (uint32_t)(l << 8 | t));          // weight tile landed
@@ -283,9 +290,12 @@ __global__ void __launch_bounds__(kThreads, 1) cips_tc_kernel(const KArgs a) {
                     if (rdy & (1u << j)) tc_commit(&s.acc_ready[j]);
                 }
               }
-            } else if (elect_one()) {
+            }
+#ifndef C3D_INJECT_RING_RACE
+            else if (elect_one()) {
               observe_stage_free<CL>(&s.empty[stage]);
             }
+#endif
             __syncwarp();
             if (++stage == kStages) { stage = 0; phase ^= 1; }
           }
@@ -486,6 +496,9 @@ static int cips_grid(const C3dCipsParams* p, int* cl_out) {
   if (const char* e = getenv("C3D_CIPS_CLUSTER")) cl = atoi(e);
   if (cl != 1 && cl != 2 && cl != 4) cl = 1;
   const int tiles_per_img = (p->n_pix + kTileM - 1) / kTileM;
+  // the CTAs of a cluster share one multicast weight stream: they must all work on the same image at the same
+  // time, which holds iff clusters never straddle an image boundary (found by the CPU emulation, tools/emu)
+  if (tiles_per_img % cl || sms < cl) cl = 1;
   long long total = (long long)p->batch * tiles_per_img;
   int grid = (int)(total < sms ? total : sms);
   grid = (grid + cl - 1) / cl * cl;

@@ -1,0 +1,184 @@
+"""CPU tests of the CUDA kernels themselves, through the functional emulation in tools/emu.
+
+The product sources (csrc/*.cu) are compiled with g++ -DC3D_EMU; every CUDA thread becomes a fiber, and mbarriers,
+tensor memory, tcgen05.mma (decoded from the real descriptors), bulk copies, named / cluster barriers are emulated
+with asynchronous completion under a seeded schedule (see tools/emu/c3d_emu.h).  The same C-ABI entry points and
+the same Python host layer as on the GPU run here, against the same goldens of the real reference and the same
+oracle -- so layout, descriptor, index and protocol errors in a kernel show up without a GPU.  The emulator itself
+is pinned by the hardware-validated kernels (they must reproduce the goldens) and by a fault-injection case (the
+parity-aliasing race of the round-1 weight ring must be reported)."""
+import ctypes as C
+
+import pytest
+import torch
+
+import _emu
+from _emu import emulated
+from _util import GEN_CASES, build_generator, close_frac, load_gen_case, rel_err
+from oracle import cips3d_oracle as O
+
+TC, SIMT = 0, 1
+MODES = {"eager": 0, "lazy": 1, "random": 2}
+
+
+def test_product_loader_refuses_emulation_build():
+    import cips3d_b200
+    L = cips3d_b200._lib
+    path = _emu.build_emu.build()
+    saved = (L._lib, L.LIB_PATH)
+    L._lib, L.LIB_PATH = None, path
+    try:
+        with pytest.raises(L.C3dError, match="emulation"):
+            L.load()
+    finally:
+        L._lib, L.LIB_PATH = saved
+
+
+def test_emulation_build_exports_the_whole_c_abi():
+    import cips3d_b200
+    lib = _emu.emu_lib()
+    for name in cips3d_b200._lib.EXPORTS:
+        assert hasattr(lib, name), name
+    assert lib.c3d_emulated() == 1
+
+
+@pytest.mark.parametrize("mode", ["eager", "lazy", "random"])
+@pytest.mark.parametrize("n,k,a_in_tmem", [(16, 16, False), (128, 128, True), (80, 128, True), (256, 256, False), (32, 64, True)])
+def test_emu_umma_selftest(mode, n, k, a_in_tmem):
+    g = torch.Generator().manual_seed(n * 1000 + k)
+    a, b = torch.randn(128, k, generator=g), torch.randn(n, k, generator=g)
+    with emulated(async_mode=MODES[mode], seed=n + k) as pkg:
+        d = pkg.ops.selftest_umma(a, b, a_in_tmem=a_in_tmem)
+    ref = a.half().double() @ b.half().double().T
+    assert (d.double() - ref).abs().max().item() < 1e-5 * ref.abs().max().item()
+
+
+def _render(pkg, name, impl):
+    sd, zs, draws, kw, meta, ref = load_gen_case(name)
+    G = build_generator("cpu", sd)
+    R, S, hier = meta["img_size"], kw["num_steps"], kw["hierarchical_sample"]
+    with torch.no_grad():
+        style = G.mapping_network(zs["z_nerf"], zs["z_inr"])
+        origin, _, _ = O.camera_origin(draws["yaw_n"], draws["pitch_n"], kw["h_stddev"], kw["v_stddev"])
+        c2w = O.cam2world(-origin, origin)
+        out = pkg.ops.render_features(
+            G.siren.kernel_weights(), G.siren.kernel_film(style), c2w, draws["jitter_u"],
+            draws["pdf_u"] if hier else None, draws["noise_c"] if hier else None, draws["noise_f"],
+            img_size=R, fov=kw["fov"], ray_start=kw["ray_start"], ray_end=kw["ray_end"], num_steps=S,
+            hierarchical_sample=hier, clamp_mode=kw.get("clamp_mode", "relu"), noise_std=meta["nerf_noise"],
+            white_back=kw.get("white_back", False), last_back=kw.get("last_back", False), impl=impl, debug=True)
+    return out, ref
+
+
+def _check_render(out, ref):
+    # same bounds as tests/test_gpu_parity.py::test_renderer_matches_reference_golden
+    assert rel_err(out["coarse"], ref["coarse"])[0] < 2e-4
+    assert rel_err(out["all_z"], ref["all_z"])[0] < 2e-4
+    frac, worst = close_frac(out["pixels_fea"], ref["pixels_fea"], 1e-3)
+    assert frac >= 0.995, (frac, worst)
+    assert close_frac(out["depth"][..., None], ref["depth"][..., None], 1e-3)[0] >= 0.995
+
+
+@pytest.mark.parametrize("mode", ["lazy", "random"])
+@pytest.mark.parametrize("name", GEN_CASES)
+def test_emu_ray_siren_tc_matches_reference_golden(name, mode):
+    """The fused tcgen05 renderer kernel, executed thread by thread on the CPU, against the REAL reference."""
+    with emulated(async_mode=MODES[mode], seed=11) as pkg:
+        out, ref = _render(pkg, name, TC)
+    _check_render(out, ref)
+
+
+@pytest.mark.parametrize("name", ["r16_trained_noise", "r8_nohier_s24"])
+def test_emu_ray_siren_simt_matches_reference_golden(name):
+    with emulated(async_mode=0) as pkg:
+        out, ref = _render(pkg, name, SIMT)
+    _check_render(out, ref)
+
+
+def _cips_case(pkg, B, N, impl, seed=31, n_blocks=9):
+    sd = O.synthetic_state_dict(O.generator_template(), seed=seed)
+    G = build_generator("cpu", sd)
+    g = torch.Generator().manual_seed(B * 7 + N)
+    x, w = torch.randn(B, N, 32, generator=g), torch.randn(B, 512, generator=g)
+    with torch.no_grad():
+        ref64, hid64 = O.cips_net({k: v.double() for k, v in sd.items()}, x.double(), w.double(), return_hidden=True)
+        ws, s1p, dm, rw, rb = G.inr_net.kernel_inputs({k: w for k in G.inr_net.style_dim_dict}, n_blocks)
+        rgb, hid = pkg.ops.cips_forward(x, ws, s1p, dm, rw, rb, impl=impl, return_hidden=True)
+    return rel_err(hid, hid64.float())[0], rel_err(rgb, ref64.float())[0]
+
+
+@pytest.mark.parametrize("mode", ["eager", "lazy", "random"])
+@pytest.mark.parametrize("B,N", [(1, 128), (3, 200)])
+def test_emu_cips_tc_matches_oracle(B, N, mode):
+    """The fused CIPS tcgen05 kernel (weight ring, dual issuers, staircase pipeline) on the CPU vs the fp64 oracle;
+    (3, 200) has ragged tiles and more tiles than emulated SMs (the persistent loop and the dummy tiles run)."""
+    with emulated(async_mode=MODES[mode], seed=B + N, sms=2) as pkg:
+        e_hid, e_rgb = _cips_case(pkg, B, N, TC)
+    assert e_hid < 1e-3 and e_rgb < 1e-3, (e_hid, e_rgb)
+
+
+@pytest.mark.parametrize("cl", [2, 4])
+def test_emu_cips_tc_cluster_multicast(cl, monkeypatch):
+    """C3D_CIPS_CLUSTER=2|4: weight tiles multicast across a thread-block cluster, remote mbarrier arrives."""
+    monkeypatch.setenv("C3D_CIPS_CLUSTER", str(cl))
+    with emulated(async_mode=2, seed=cl, sms=4) as pkg:
+        e_hid, e_rgb = _cips_case(pkg, 2, 128 * cl, TC)
+        assert e_hid < 1e-3 and e_rgb < 1e-3, (e_hid, e_rgb)
+        # 3 tiles per image: a cluster would straddle two images' weight streams -> the host must fall back to CL = 1
+        e_hid, e_rgb = _cips_case(pkg, 2, 384, TC)
+        assert e_hid < 1e-3 and e_rgb < 1e-3, (e_hid, e_rgb)
+
+
+def test_emu_cips_simt_matches_oracle():
+    with emulated(async_mode=0) as pkg:
+        e_hid, e_rgb = _cips_case(pkg, 1, 128, SIMT)
+    assert e_hid < 1e-3 and e_rgb < 1e-3, (e_hid, e_rgb)
+
+
+def test_emu_detects_the_round1_weight_ring_race():
+    """Fault injection: -DC3D_INJECT_RING_RACE restores the round-1 protocol (an MMA issuer skips the fills of the
+    tiles it does not own).  On hardware it only failed under ncu's replay timing; the emulator must report it
+    whenever asynchronous operations complete late."""
+    path = _emu.build_emu.build(extra_defs=("C3D_INJECT_RING_RACE",), tag="ringrace")
+    good = _emu._cdll
+    bad = C.CDLL(path)
+    bad.c3d_emu_configure.argtypes = [C.c_int, C.c_ulonglong, C.c_int, C.c_int]
+    _emu._cdll = bad
+    try:
+        failures = 0
+        for seed in (1, 2, 3):
+            with emulated(async_mode=MODES["lazy"], seed=seed) as pkg:
+                try:
+                    e_hid, e_rgb = _cips_case(pkg, 1, 256, TC)
+                    failures += int(not (e_hid < 1e-3 and e_rgb < 1e-3))
+                except pkg._lib.C3dError:
+                    failures += 1
+        assert failures == 3, f"the injected race was reported in only {failures} of 3 schedules"
+    finally:
+        _emu._cdll = good
+
+
+@pytest.mark.parametrize("shape", [(3, 5, 8, 8), (2, 7), (4, 6, 5, 3), (2, 3, 1, 1)])
+def test_emu_bias_act(shape):
+    g = torch.Generator().manual_seed(sum(shape))
+    x, b = torch.randn(*shape, generator=g), torch.randn(shape[1], generator=g)
+    with emulated(async_mode=0) as pkg:
+        y = pkg.ops.bias_act(x, b)
+        ref = torch.randn(*shape, generator=g)
+        yg = pkg.ops.bias_act(x, None, ref, act=3, grad=1)
+    assert torch.equal(y, O.bias_act(x, b))
+    assert torch.equal(yg, O.bias_act(x, None, ref, act=3, grad=1))
+
+
+@pytest.mark.parametrize("shape,up,down,pad", [
+    ((2, 3, 9, 11), (1, 1), (1, 1), (2, 2, 2, 2)), ((1, 4, 64, 64), (1, 1), (1, 1), (1, 1, 1, 1)),
+    ((1, 2, 8, 8), (2, 2), (1, 1), (2, 1, 2, 1)), ((2, 2, 16, 12), (1, 1), (2, 2), (1, 1, 1, 1))])
+def test_emu_upfirdn2d(shape, up, down, pad):
+    g = torch.Generator().manual_seed(sum(shape))
+    x = torch.randn(*shape, generator=g)
+    k = torch.tensor([1., 3., 3., 1.])
+    k = (k[None] * k[:, None]) / 64
+    with emulated(async_mode=0) as pkg:
+        y = pkg.ops._upfirdn2d_raw(x, k, up, down, pad)
+    ref = O.upfirdn2d(x, k, up, down, pad)
+    assert y.shape == ref.shape and (y - ref).abs().max().item() < 1e-5

@@ -16,7 +16,14 @@ FLAGS = ["-std=c++17", "-O2", "-g", "-fPIC", "-DC3D_EMU", "-ffp-contract=off", "
          "-Wno-unknown-pragmas", "-Wno-unused-value", "-I", HERE, "-I", CUDA_INC]
 
 
-def build(force=False, extra_defs=()):
+def build(force=False, extra_defs=(), tag=""):
+    """tag: build a variant (e.g. with a fault injected through extra_defs) into its own directory."""
+    global_out = OUT_DIR + ("_" + tag if tag else "")
+    return _build(global_out, force, extra_defs)
+
+
+def _build(OUT_DIR, force, extra_defs):
+    LIB = os.path.join(OUT_DIR, "libcips3d_b200_emu.so")
     os.makedirs(OUT_DIR, exist_ok=True)
     srcs = sorted(glob.glob(os.path.join(CSRC, "*.cu"))) + [os.path.join(HERE, "emu_impl.cpp")]
     deps = srcs + glob.glob(os.path.join(CSRC, "*.cuh")) + glob.glob(os.path.join(HERE, "*.h")) + \

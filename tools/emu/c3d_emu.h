@@ -48,7 +48,7 @@ struct Config {
   uint64_t seed = 1;
   int preempt_permille = 20;  // chance that an emulated primitive yields to another fiber
   int sms = 2;                // what c3d_device_sm_count() reports
-  long long max_steps = 4000000000ll;
+  long long max_steps = 400000000ll;
   int verbose = 0;
 };
 inline Config& config() {
@@ -418,6 +418,7 @@ inline void run_cluster() {
   const int n = (int)l.fibers.size();
   int live = n;
   const int mode = config().async_mode;
+  unsigned passes = 0;
   while (live > 0 && !l.failed) {
     bool progress = false;
     const int start = (int)l.rng.below((uint32_t)n);
@@ -438,6 +439,9 @@ inline void run_cluster() {
       if (++l.steps > config().max_steps) { l.failed = true; l.error = "step budget exhausted (livelock?)"; break; }
       if (mode == 2 && l.rng.below(4) == 0) run_one_async();
     }
+    // lazy mode: asynchronous work completes only when nobody can run -- or, so that polling loops
+    // (test_wait + nanosleep: always "runnable") cannot starve it, every 8th pass over the fibers
+    if (mode == 1 && (++passes & 7) == 0 && run_one_async()) progress = true;
     if (l.failed) break;
     // recount (threads may have been marked done by fail())
     live = 0;
@@ -856,4 +860,4 @@ C3D_EMU_STUB cudaError_t emu_cudaDeviceSynchronize() { return cudaSuccess; }
   emu::launch(#kernel, dim3(grid), dim3(block), (size_t)(smem), 1, [&]() { kernel(__VA_ARGS__); })
 // cudaLaunchKernelEx with a cluster dimension
 #define C3D_LAUNCH_CLUSTER(kernel, grid, block, smem, stream, cluster, ...) \
-  (emu::launch(#kernel, dim3(grid), dim3(block), (size_t)(smem), (cluster), [&]() { kernel(__VA_ARGS__); }) ? cudaErrorLaunchFailure : cudaSuccess)
+  (emu::launch(#kernel, dim3(grid), dim3(block), (size_t)(smem), (cluster), [&]() { kernel(__VA_ARGS__); }) ? (emu::G().last_error = 0, cudaErrorLaunchFailure) : cudaSuccess)
