@@ -304,6 +304,51 @@ __device__ __forceinline__ void bulk_g2s_mc(void* smem_dst, const void* gsrc, ui
       ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(bytes), "r"(smem_u32(bar)), "h"(mask)
       : "memory");
 }
+// ---- tcgen05 cta_group::2 (CTA pair: M = 256 across the two CTAs of a cluster, each CTA holds half of B's N rows)
+template <int kCols>
+__device__ __forceinline__ void tmem_alloc_cg2(uint32_t* smem_result) {  // one full warp in EACH CTA of the pair
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_result)), "n"(kCols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+template <int kCols>
+__device__ __forceinline__ void tmem_dealloc_cg2(uint32_t taddr) {  // one full warp in each CTA
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "n"(kCols) : "memory");
+}
+// issued by ONE thread of the leader CTA (cluster rank 0); descriptors are CTA-relative and apply to both CTAs
+__device__ __forceinline__ void umma_ss_w_cg2(uint32_t d_tmem, uint32_t a_lo, uint32_t b_lo, uint32_t desc_hi, uint32_t idesc,
+                                              uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+      "setp.ne.b32 p, %5, 0;\n\t"
+      "mov.b64 da, {%1, %3};\n\t"
+      "mov.b64 db, {%2, %3};\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %4, p;\n\t}"
+      ::"r"(d_tmem), "r"(a_lo), "r"(b_lo), "r"(desc_hi), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// completion of this thread's earlier cta_group::2 MMAs -> arrive on the barrier at this offset in every CTA of `mask`
+__device__ __forceinline__ void tc_commit_cg2_mc(uint64_t* bar, uint16_t mask) {
+  asm volatile(
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+          smem_u32(bar)),
+      "h"(mask)
+      : "memory");
+}
+// wait on a LOCAL barrier whose arrivals come from another CTA of the cluster (acquire at cluster scope)
+__device__ __forceinline__ bool mbar_try_wait_cluster(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred P;\n\t"
+      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 P, [%1], %2, %3;\n\t"
+      "selp.u32 %0, 1, 0, P;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity), "r"(kSuspendHintNs)
+      : "memory");
+  return ok != 0;
+}
+// generic-proxy writes -> visible to the async proxy, all state spaces (operands another CTA's MMA will read)
+__device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
 #endif  // !C3D_EMU  (end of the PTX section; everything below is plain C++ shared with the emulated build)
 
 // Spin with a watchdog: a protocol bug traps (-> CUDA error at the caller) instead of hanging the GPU.
@@ -327,6 +372,22 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   }
 }
 
+
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
+  uint32_t spins = 0;
+  unsigned long long t0 = 0;
+  while (!mbar_try_wait_cluster(bar, parity)) {
+    if ((++spins & 1023u) == 0) {
+      const unsigned long long now = c3d_globaltimer();
+      if (t0 == 0) t0 = now;
+      else if (now - t0 > C3D_WATCHDOG_NS) {
+        printf("c3d watchdog: cluster mbarrier wait timed out (block %d thread %d bar 0x%x parity %u)\n", (int)blockIdx.x,
+               (int)threadIdx.x, smem_u32(bar), parity);
+        __trap();
+      }
+    }
+  }
+}
 
 // UMMA shared-memory matrix descriptor, K-major, no swizzle ("interleaved" canonical layout,
 // cute/arch/mma_sm100_desc.hpp SmemDescriptor + cute/atom/mma_traits_sm100.hpp:273-303):

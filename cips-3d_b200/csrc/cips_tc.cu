@@ -38,6 +38,14 @@ constexpr int kKC = 64;            // K per weight tile
 constexpr int kNC = 128;           // N per weight tile
 constexpr int kWTileBytes = kKC * kNC * 2;              // 16 KB
 constexpr int kStages = 5;
+// CTA-pair variant (PAIR, tcgen05 cta_group::2): an MMA is M = 256 (128 pixels in each CTA of the pair) x N = 128 and
+// each CTA holds -- and streams from L2 -- only HALF of every weight tile (64 of its 128 N rows, 8 KB), so the ring
+// has twice the stages in the same 80 KB and the L2 -> SM weight traffic per SM is halved.
+template <bool PAIR> struct RingCfg {
+  static constexpr int kStagesP = PAIR ? 2 * kStages : kStages;
+  static constexpr int kStageBytes = PAIR ? kWTileBytes / 2 : kWTileBytes;
+  static constexpr int kLBO_B = PAIR ? (kNC / 2) * 16 : kNC * 16;     // K-direction core-matrix stride of the B tile
+};
 constexpr int kXBytes = kTileM * kH * 2;                // 128 KB
 constexpr int kLBO = kTileM * 16;                       // 2048: K-direction core-matrix stride (A and B tiles have 128 rows)
 constexpr int kSBO = 128;                               // M/N-direction stride between 8-row groups
@@ -45,19 +53,24 @@ constexpr int kNumEpiWarps = 16;
 constexpr int kThreads = 32 * (4 + kNumEpiWarps);       // 640
 constexpr int kMaxLayers = C3D_CIPS_MAX_LAYERS;
 
-struct Smem {
+template <bool PAIR>
+struct SmemT {
+  static constexpr int NS = RingCfg<PAIR>::kStagesP;
   alignas(1024) uint8_t x[kXBytes];
-  alignas(1024) uint8_t w[kStages][kWTileBytes];
+  alignas(1024) uint8_t w[kStages][kWTileBytes];   // PAIR: 10 stages of 8 KB in the same bytes
   union {                                // ToRGB weights of the current block / per-tile rgb partial sums
     float4 rgbw[kH];
     float rgb_part[4][kTileM][4];
   };
-  alignas(8) uint64_t full[kStages];
-  uint64_t empty[kStages];
+  alignas(8) uint64_t full[NS];
+  uint64_t empty[NS];
   uint64_t epi_done[4];
   uint64_t acc_ready[4];   // accumulator block j complete AND A-operand chunk j no longer read by this layer's MMAs
   uint32_t tmem_base;
+  uint32_t pad_;
+  uint64_t peer_full[PAIR ? NS : 1];   // PAIR, leader CTA only: the peer CTA's half of stage s has landed (relayed by the peer)
 };
+using Smem = SmemT<false>;
 
 struct KArgs {
   const float* x;            // (B,N,in_dim)
@@ -176,35 +189,55 @@ __device__ __forceinline__ void epi16(const uint32_t (&acc)[16], const float4 (&
   *reinterpret_cast<uint4*>(xp + kLBO) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
 }
 
-template <int CL>
+// PAIR (CL == 2 only): the two CTAs of a cluster form a tcgen05 CTA pair.  Only the leader (cluster rank 0) issues MMAs
+// (cta_group::2, M = 256: the leader's 128 pixels and the peer's 128 pixels against the same weight tile); each CTA
+// streams HALF of every weight tile into its own ring; the peer relays "my half landed" to the leader (peer_full);
+// both CTAs' epilogue warps report to the leader's epi_done barriers; the leader's commits are multicast to the
+// empty / acc_ready barriers of both CTAs.  Everything else (tile order, staircase, epilogue) is the single-CTA kernel.
+template <int CL, bool PAIR = false>
 __global__ void __launch_bounds__(kThreads, 1) cips_tc_kernel(const KArgs a) {
+  static_assert(!PAIR || CL == 2, "a CTA pair is a cluster of two");
+  using SM = SmemT<PAIR>;
+  using RC = RingCfg<PAIR>;
+  constexpr int NS = RC::kStagesP;
   C3D_DYN_SMEM(uint8_t, smem_raw);
   // identical offset in every CTA of a cluster (multicast lands at the same CTA-relative address)
-  Smem& s = *reinterpret_cast<Smem*>(smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u));
+  SM& s = *reinterpret_cast<SM*>(smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u));
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t crank = CL > 1 ? cluster_ctarank() : 0;
+  const bool leader = !PAIR || crank == 0;
 
   if (threadIdx.x == 0) {
-    for (int i = 0; i < kStages; ++i) {
+    for (int i = 0; i < NS; ++i) {
       mbar_init(&s.full[i], 1);
 #ifdef C3D_INJECT_RING_RACE           // test-only (tests/test_emu_cpu.py): re-creates the round-1 parity-aliasing race
       mbar_init(&s.empty[i], CL);
 #else
-      mbar_init(&s.empty[i], 2 * CL);   // both issuers release every stage (see the issuer loop)
+      mbar_init(&s.empty[i], PAIR ? 2 : 2 * CL);   // both issuers release every stage (see the issuer loop)
 #endif
+      if (PAIR) mbar_init(&s.peer_full[i], 1);
     }
-    for (int i = 0; i < 4; ++i) mbar_init(&s.epi_done[i], kNumEpiWarps);
+    for (int i = 0; i < 4; ++i) mbar_init(&s.epi_done[i], PAIR ? 2 * kNumEpiWarps : kNumEpiWarps);
     for (int i = 0; i < 4; ++i) mbar_init(&s.acc_ready[i], 2);   // two MMA issuer warps, each commits once per layer and chunk
     fence_mbar_init();
   }
-  if (warp == 2) tmem_alloc<512>(&s.tmem_base);
+  if (warp == 2) {
+    if (PAIR) tmem_alloc_cg2<512>(&s.tmem_base);
+    else tmem_alloc<512>(&s.tmem_base);
+  }
   tc_fence_before();
   __syncthreads();
   if (CL > 1) cluster_sync_all();
   tc_fence_after();
   const uint32_t tmem = s.tmem_base;
 
-  const int iters = (a.total_tiles + (int)gridDim.x - 1) / (int)gridDim.x;
+  // tile walked in iteration `it`: PAIR -> the cluster takes two consecutive tiles (same image: tiles_per_img is even)
+  const int grid_units = PAIR ? (int)gridDim.x / 2 : (int)gridDim.x;
+  const int total_units = PAIR ? a.total_tiles / 2 : a.total_tiles;
+  const int iters = (total_units + grid_units - 1) / grid_units;
+  auto tile_of = [&](int it) {
+    return PAIR ? (it * grid_units + (int)blockIdx.x / 2) * 2 + (int)crank : it * (int)gridDim.x + (int)blockIdx.x;
+  };
   const int L = a.n_layers;
 
   if (warp < 4) {
@@ -213,7 +246,7 @@ __global__ void __launch_bounds__(kThreads, 1) cips_tc_kernel(const KArgs a) {
       // ---------------------------------------------------------- weight producer (whole warp converged, one lane issues)
       uint32_t stage = 0, phase = 0;
       for (int it = 0; it < iters; ++it) {
-        const int tile = it * (int)gridDim.x + (int)blockIdx.x;
+        const int tile = tile_of(it);
         const int img = tile < a.total_tiles ? tile / a.tiles_per_img : 0;     // dummy tiles stream image 0
         for (int l = 0; l < L; ++l) {
           const uint8_t* src = reinterpret_cast<const uint8_t*>(a.wtiles) +
@@ -222,13 +255,36 @@ __global__ void __launch_bounds__(kThreads, 1) cips_tc_kernel(const KArgs a) {
           for (int t = 0; t < ntiles; ++t) {
             mbar_wait(&s.empty[stage], phase ^ 1);
             if (elect_one()) {
-              mbar_arrive_expect_tx(&s.full[stage], kWTileBytes);
-              load_w_tile<CL>(s.w[stage], src + (size_t)t * kWTileBytes, &s.full[stage], crank);
+              if (PAIR) {      // this CTA's half (N rows 64*rank .. +63) of the tile
+                mbar_arrive_expect_tx(&s.full[stage], RC::kStageBytes);
+                bulk_g2s(&s.w[0][0] + stage * RC::kStageBytes, src + (size_t)t * kWTileBytes + crank * RC::kStageBytes,
+                         RC::kStageBytes, &s.full[stage]);
+              } else {
+                mbar_arrive_expect_tx(&s.full[stage], kWTileBytes);
+                load_w_tile<CL>(s.w[stage], src + (size_t)t * kWTileBytes, &s.full[stage], crank);
+              }
             }
             __syncwarp();
-            if (++stage == kStages) { stage = 0; phase ^= 1; }
+            if (++stage == NS) { stage = 0; phase ^= 1; }
           }
         }
+      }
+    } else if (PAIR && !leader) {
+      // ---------------------------------------------------------- peer CTA of a pair: warp 1 relays "my half of stage s
+      // has landed" to the leader's peer_full[s] (one remote arrive per fill, in ring order); warp 3 idles.
+      if (warp == 1) {
+        uint32_t stage = 0, phase = 0;
+        for (int it = 0; it < iters; ++it)
+          for (int l = 0; l < L; ++l) {
+            const int ntiles = a.layer_kc[l] * 4;
+#pragma unroll 1
+            for (int t = 0; t < ntiles; ++t) {
+              mbar_wait(&s.full[stage], phase);
+              if (elect_one()) mbar_arrive_cluster(&s.peer_full[stage], 0);
+              __syncwarp();
+              if (++stage == NS) { stage = 0; phase ^= 1; }
+            }
+          }
       }
     } else if (warp == 1 || warp == 3) {
       // ---------------------------------------------------------- MMA issuers (whole warp converged, one lane issues).
@@ -236,12 +292,13 @@ __global__ void __launch_bounds__(kThreads, 1) cips_tc_kernel(const KArgs a) {
       // TMEM columns, so the two instruction streams never touch the same accumulator) -- one thread alone
       // cannot issue 4 MMAs + bookkeeping inside the 256 clk a tile occupies the tensor pipe.
       const uint32_t me = warp == 1 ? 0u : 1u;
-      const uint32_t idesc = umma_idesc_f16(kTileM, kNC);
+      const uint32_t idesc = umma_idesc_f16(PAIR ? 2 * kTileM : kTileM, kNC);
       const uint32_t dhi = umma_desc_hi(kSBO);
       const uint32_t a_lo0 = umma_desc_lo(smem_u32(s.x), kLBO);
-      const uint32_t b_lo0 = umma_desc_lo(smem_u32(s.w[0]), kLBO);
+      const uint32_t b_lo0 = umma_desc_lo(smem_u32(s.w[0]), RC::kLBO_B);
       constexpr uint32_t kStepK16 = (2 * kLBO) >> 4;       // one K=16 MMA step  = 2 core-matrix columns
-      constexpr uint32_t kStepStage = kWTileBytes >> 4;
+      constexpr uint32_t kStepK16B = (2 * RC::kLBO_B) >> 4;
+      constexpr uint32_t kStepStage = RC::kStageBytes >> 4;
       uint32_t stage = 0, phase = 0;
       for (int it = 0; it < iters; ++it) {
         for (int l = 0; l < L; ++l) {
@@ -259,7 +316,10 @@ __global__ void __launch_bounds__(kThreads, 1) cips_tc_kernel(const KArgs a) {
               const int need = (int)((e >> 8) & 15u);
               if (lane == 0) TRACE(it, 1 + me, (uint32_t)(l << 8 | t));          // tile reached
               if (need > waited) {
-                for (int j = waited + 1; j <= need; ++j) mbar_wait(&s.epi_done[j], epar);
+                for (int j = waited + 1; j <= need; ++j) {
+                  if (PAIR) mbar_wait_cluster(&s.epi_done[j], epar);     // half of the arrivals come from the peer CTA
+                  else mbar_wait(&s.epi_done[j], epar);
+                }
                 waited = need;
               }
               if (lane == 0) TRACE(it, 3 + me, (uint32_t)(l << 8 | t));          // epilogue dependency satisfied
@@ -271,6 +331,7 @@ __global__ void __launch_bounds__(kThreads, 1) cips_tc_kernel(const KArgs a) {
             if (mine)
 #endif
             mbar_wait(&s.full[stage], phase);
+            if (PAIR) mbar_wait_cluster(&s.peer_full[stage], phase);             // ... and the peer's half
             if (mine) {
               if (lane == 0) TRACE(it, 5 + me, (uint32_t)(l << 8 | t));          // weight tile landed
               tc_fence_after();
@@ -278,26 +339,37 @@ __global__ void __launch_bounds__(kThreads, 1) cips_tc_kernel(const KArgs a) {
                 const uint32_t a_lo = a_lo0 + kc * (kStepK16 * (kKC / 16));
                 const uint32_t b_lo = b_lo0 + stage * kStepStage;
                 const uint32_t d = tmem + nc * kNC;
-                umma_ss_w(d, a_lo, b_lo, dhi, idesc, kc != 0);
-                umma_ss_w(d, a_lo + kStepK16, b_lo + kStepK16, dhi, idesc, 1);
-                umma_ss_w(d, a_lo + 2 * kStepK16, b_lo + 2 * kStepK16, dhi, idesc, 1);
-                umma_ss_w(d, a_lo + 3 * kStepK16, b_lo + 3 * kStepK16, dhi, idesc, 1);
-                commit_stage_free<CL>(&s.empty[stage]);
+                if (PAIR) {
+                  umma_ss_w_cg2(d, a_lo, b_lo, dhi, idesc, kc != 0);
+                  umma_ss_w_cg2(d, a_lo + kStepK16, b_lo + kStepK16B, dhi, idesc, 1);
+                  umma_ss_w_cg2(d, a_lo + 2 * kStepK16, b_lo + 2 * kStepK16B, dhi, idesc, 1);
+                  umma_ss_w_cg2(d, a_lo + 3 * kStepK16, b_lo + 3 * kStepK16B, dhi, idesc, 1);
+                  tc_commit_cg2_mc(&s.empty[stage], 3);      // stage free in BOTH CTAs
+                } else {
+                  umma_ss_w(d, a_lo, b_lo, dhi, idesc, kc != 0);
+                  umma_ss_w(d, a_lo + kStepK16, b_lo + kStepK16, dhi, idesc, 1);
+                  umma_ss_w(d, a_lo + 2 * kStepK16, b_lo + 2 * kStepK16, dhi, idesc, 1);
+                  umma_ss_w(d, a_lo + 3 * kStepK16, b_lo + 3 * kStepK16, dhi, idesc, 1);
+                  commit_stage_free<CL>(&s.empty[stage]);
+                }
                 const uint32_t rdy = e >> 12;    // chunks j for which this is the issuer's last tile of S_j
                 if (rdy) {
 #pragma unroll
                   for (int j = 0; j < 4; ++j)
-                    if (rdy & (1u << j)) tc_commit(&s.acc_ready[j]);
+                    if (rdy & (1u << j)) {
+                      if (PAIR) tc_commit_cg2_mc(&s.acc_ready[j], 3);
+                      else tc_commit(&s.acc_ready[j]);
+                    }
                 }
               }
             }
 #ifndef C3D_INJECT_RING_RACE
             else if (elect_one()) {
-              observe_stage_free<CL>(&s.empty[stage]);
+              observe_stage_free<CL>(&s.empty[stage]);      // (PAIR: CL == 2 -> one arrive on the barrier of each CTA)
             }
 #endif
             __syncwarp();
-            if (++stage == kStages) { stage = 0; phase ^= 1; }
+            if (++stage == NS) { stage = 0; phase ^= 1; }
           }
         }
       }
@@ -312,7 +384,7 @@ __global__ void __launch_bounds__(kThreads, 1) cips_tc_kernel(const KArgs a) {
     const uint32_t trow = tmem + ((uint32_t)(q * 32) << 16);
     float4* resid = a.resid + (size_t)blockIdx.x * (kH / 4) * kTileM;
     for (int it = 0; it < iters; ++it) {
-      const int tile = it * (int)gridDim.x + (int)blockIdx.x;
+      const int tile = tile_of(it);
       const bool tile_ok = tile < a.total_tiles;
       const int img = tile_ok ? tile / a.tiles_per_img : 0;
       const int pix = tile_ok ? (tile % a.tiles_per_img) * kTileM + row : a.N;
@@ -339,11 +411,15 @@ __global__ void __launch_bounds__(kThreads, 1) cips_tc_kernel(const KArgs a) {
             *reinterpret_cast<uint4*>(s.x + (size_t)(k0 / 8 + g) * kLBO + row * 16) =
                 make_uint4(pk[4 * g], pk[4 * g + 1], pk[4 * g + 2], pk[4 * g + 3]);
         }
-        fence_proxy_async();
+        if (PAIR) fence_proxy_async_all();
+        else fence_proxy_async();
         tc_fence_before();
         __syncwarp();
         if (lane == 0)
-          for (int j = 0; j < 4; ++j) mbar_arrive(&s.epi_done[j]);
+          for (int j = 0; j < 4; ++j) {
+            if (PAIR) mbar_arrive_cluster(&s.epi_done[j], 0);      // the leader's barrier collects both CTAs
+            else mbar_arrive(&s.epi_done[j]);
+          }
       }
       // ---- e = l + 1: epilogue of layer l
       for (int l = 0; l < L; ++l) {
@@ -404,10 +480,14 @@ __global__ void __launch_bounds__(kThreads, 1) cips_tc_kernel(const KArgs a) {
           if (second) epi16<true>(accB, rsB, rwp + 16, xp + 2 * kLBO, rp + 4 * kTileM, f, rgb0, rgb1, rgb2, hp ? hp + 16 : nullptr);
           else epi16<false>(accB, rsB, rwp + 16, xp + 2 * kLBO, rp + 4 * kTileM, f, rgb0, rgb1, rgb2, hp ? hp + 16 : nullptr);
           // chunk j of this epilogue is complete for this warp
-          fence_proxy_async();
+          if (PAIR) fence_proxy_async_all();
+          else fence_proxy_async();
           tc_fence_before();
           __syncwarp();
-          if (lane == 0 && !f.last) mbar_arrive(&s.epi_done[j]);
+          if (lane == 0 && !f.last) {
+            if (PAIR) mbar_arrive_cluster(&s.epi_done[j], 0);
+            else mbar_arrive(&s.epi_done[j]);
+          }
           if (lane == 0) TRACE(it, 9, (uint32_t)(l << 8 | (warp - 4) << 2 | j));   // warp finished chunk j
           tcol += 128; rp += 32 * kTileM; xp += 16 * kLBO; rwp += 128;
           if (hp) hp += 128;
@@ -433,7 +513,10 @@ __global__ void __launch_bounds__(kThreads, 1) cips_tc_kernel(const KArgs a) {
   tc_fence_before();
   __syncthreads();
   if (CL > 1) cluster_sync_all();
-  if (warp == 2) tmem_dealloc<512>(tmem);
+  if (warp == 2) {
+    if (PAIR) tmem_dealloc_cg2<512>(tmem);
+    else tmem_dealloc<512>(tmem);
+  }
 }
 
 // fp32 (in,out) weights -> fp16 UMMA-B tiles, one launch for all layers.  Block = one 16 KB tile in STREAM
@@ -448,7 +531,9 @@ struct PrepArgs {
   uint16_t order_full[32];
   uint16_t order_in[4];
 };
-// grid = (tiles per image, B): block = one 16 KB tile of one image, in STREAM order
+// grid = (tiles per image, B): block = one 16 KB tile of one image, in STREAM order.
+// PAIR: the tile is stored as two 8 KB halves (N rows 0..63, 64..127), each in the canonical layout of a 64-row operand.
+template <bool PAIR>
 __global__ void cips_prep_weights_kernel(const PrepArgs pa, __half* __restrict__ out) {
   const int gt = blockIdx.x, b = blockIdx.y;
   int l = 0;
@@ -465,7 +550,13 @@ __global__ void cips_prep_weights_kernel(const PrepArgs pa, __half* __restrict__
     const int k = i / kNC, n = i % kNC;    // n fastest -> coalesced reads of W rows
     const int gk = kc * kKC + k;
     const float v = gk < in_dim ? (sv[gk] * W[(size_t)gk * kH + nc * kNC + n]) * dv[n] : 0.f;
-    o[((n % 8) * 16 + (n / 8) * 128 + (k / 8) * kLBO) / 2 + (k % 8)] = __float2half_rn(v);
+    if (PAIR) {
+      const int nh = n % (kNC / 2);
+      o[((n / (kNC / 2)) * (kWTileBytes / 2) + (nh % 8) * 16 + (nh / 8) * 128 + (k / 8) * RingCfg<true>::kLBO_B) / 2 + (k % 8)] =
+          __float2half_rn(v);
+    } else {
+      o[((n % 8) * 16 + (n / 8) * 128 + (k / 8) * kLBO) / 2 + (k % 8)] = __float2half_rn(v);
+    }
   }
 }
 
@@ -488,7 +579,7 @@ __global__ void cips_prep_consts_kernel(C3dCipsWeights w, int n_blocks, int rgb_
 using namespace c3d;
 using namespace c3d::cips;
 
-static int cips_grid(const C3dCipsParams* p, int* cl_out) {
+static int cips_grid(const C3dCipsParams* p, int* cl_out, bool* pair_out) {
   int dev = 0;
   cudaGetDevice(&dev);
   const int sms = c3d_device_sm_count(dev);
@@ -496,6 +587,12 @@ static int cips_grid(const C3dCipsParams* p, int* cl_out) {
   if (const char* e = getenv("C3D_CIPS_CLUSTER")) cl = atoi(e);
   if (cl != 1 && cl != 2 && cl != 4) cl = 1;
   const int tiles_per_img = (p->n_pix + kTileM - 1) / kTileM;
+  // C3D_CIPS_PAIR=1: tcgen05 CTA pairs (cta_group::2).  Opt-in until it has been timed on hardware.
+  bool pair = false;
+  if (const char* e = getenv("C3D_CIPS_PAIR")) pair = atoi(e) != 0;
+  if (pair && (tiles_per_img % 2 || sms < 2)) pair = false;     // a pair works on two tiles of ONE image
+  if (pair) cl = 2;
+  *pair_out = pair;
   // the CTAs of a cluster share one multicast weight stream: they must all work on the same image at the same
   // time, which holds iff clusters never straddle an image boundary (found by the CPU emulation, tools/emu)
   if (tiles_per_img % cl || sms < cl) cl = 1;
@@ -539,19 +636,20 @@ extern "C" int c3d_debug_cips_trace(unsigned long long* out, int cap) {
 }
 #endif
 
-template <int CL>
+template <int CL, bool PAIR = false>
 static int launch_cips(const KArgs& ka, int grid, cudaStream_t st) {
-  const size_t smem = sizeof(Smem) + 1024;
+  const size_t smem = sizeof(SmemT<PAIR>) + 1024;
   static std::atomic<unsigned long long> attr_set{0};     // per device, once
   int dev = 0;
   cudaGetDevice(&dev);
+  auto kern = cips_tc_kernel<CL, PAIR>;
   if (!(attr_set.load() >> (dev & 63) & 1ull)) {
-    C3D_CUDA(cudaFuncSetAttribute(cips_tc_kernel<CL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    C3D_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_set.fetch_or(1ull << (dev & 63));
   }
 #ifdef C3D_EMU
   c3d_count_launch();
-  C3D_CUDA(C3D_LAUNCH_CLUSTER(cips_tc_kernel<CL>, grid, kThreads, smem, st, CL, ka));
+  C3D_CUDA(C3D_LAUNCH_CLUSTER(kern, grid, kThreads, smem, st, CL, ka));
   return C3D_OK;
 #else
   cudaLaunchConfig_t cfg = {};
@@ -567,7 +665,7 @@ static int launch_cips(const KArgs& ka, int grid, cudaStream_t st) {
   cfg.attrs = attr;
   cfg.numAttrs = 1;
   c3d_count_launch();
-  C3D_CUDA(cudaLaunchKernelEx(&cfg, cips_tc_kernel<CL>, ka));
+  C3D_CUDA(cudaLaunchKernelEx(&cfg, kern, ka));
   return C3D_OK;
 #endif
 }
@@ -655,6 +753,9 @@ int c3d_cips_fwd_tc(const C3dCipsParams* p, const C3dCipsWeights* w, const float
   ka.layer_tile_off[L] = off;
   ka.img_tile_stride = (size_t)off;
   build_tile_order(ka.order_full, ka.order_in);
+  int cl = 1;
+  bool pair = false;
+  const int grid = cips_grid(p, &cl, &pair);
   // ---- prep: weights -> fp16 tiles (one launch), per-image epilogue vectors
   {
     PrepArgs pa = {};
@@ -669,14 +770,16 @@ int c3d_cips_fwd_tc(const C3dCipsParams* p, const C3dCipsWeights* w, const float
     pa.B = p->batch;
     for (int i = 0; i < 32; ++i) pa.order_full[i] = ka.order_full[i];
     for (int i = 0; i < 4; ++i) pa.order_in[i] = ka.order_in[i];
-    C3D_LAUNCH(cips_prep_weights_kernel, dim3(ka.layer_tile_off[L], p->batch), 256, 0, st, pa, (__half*)(base + ws.wtiles));
+    if (pair)
+      C3D_LAUNCH(cips_prep_weights_kernel<true>, dim3(ka.layer_tile_off[L], p->batch), 256, 0, st, pa, (__half*)(base + ws.wtiles));
+    else
+      C3D_LAUNCH(cips_prep_weights_kernel<false>, dim3(ka.layer_tile_off[L], p->batch), 256, 0, st, pa, (__half*)(base + ws.wtiles));
     C3D_LAUNCH_CHECK();
   }
   C3D_LAUNCH(cips_prep_consts_kernel, p->n_blocks, 256, 0, st, *w, p->n_blocks, p->rgb_from, (float4*)(base + ws.rgbw),
              (float*)(base + ws.rgbb));
   C3D_LAUNCH_CHECK();
-  int cl = 1;
-  const int grid = cips_grid(p, &cl);
+  if (pair) return launch_cips<2, true>(ka, grid, st);
   if (cl == 1) return launch_cips<1>(ka, grid, st);
   if (cl == 2) return launch_cips<2>(ka, grid, st);
   return launch_cips<4>(ka, grid, st);

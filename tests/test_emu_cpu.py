@@ -129,6 +129,27 @@ def test_emu_cips_tc_cluster_multicast(cl, monkeypatch):
         assert e_hid < 1e-3 and e_rgb < 1e-3, (e_hid, e_rgb)
 
 
+@pytest.mark.parametrize("mode", ["eager", "lazy", "random"])
+@pytest.mark.parametrize("B,N,sms", [(1, 256, 2), (2, 512, 2), (3, 256, 4), (2, 200, 2)])
+def test_emu_cips_tc_cta_pair(B, N, sms, mode, monkeypatch):
+    """C3D_CIPS_PAIR=1: tcgen05 cta_group::2 -- the leader CTA issues M = 256 MMAs for both CTAs of a cluster, each
+    CTA streams half of every weight tile, the peer relays its fills and both epilogues report to the leader.
+    (2, 512): four iterations of the persistent loop; (3, 256, sms 4): two pairs, one of them with a dummy tail
+    iteration; (2, 200): ragged second tile.  Not yet run on hardware (opt-in), the emulator's cta_group::2 model
+    follows cute's MMA_Traits<SM100_MMA_F16BF16_2x1SM_SS> operand partitioning."""
+    monkeypatch.setenv("C3D_CIPS_PAIR", "1")
+    with emulated(async_mode=MODES[mode], seed=B * N + sms, sms=sms) as pkg:
+        e_hid, e_rgb = _cips_case(pkg, B, N, TC)
+    assert e_hid < 1e-3 and e_rgb < 1e-3, (e_hid, e_rgb)
+
+
+def test_emu_cips_tc_cta_pair_falls_back_on_odd_tile_counts(monkeypatch):
+    monkeypatch.setenv("C3D_CIPS_PAIR", "1")
+    with emulated(async_mode=2, sms=2) as pkg:
+        e_hid, e_rgb = _cips_case(pkg, 2, 384, TC)       # 3 tiles per image: a pair would straddle two images
+    assert e_hid < 1e-3 and e_rgb < 1e-3, (e_hid, e_rgb)
+
+
 def test_emu_cips_simt_matches_oracle():
     with emulated(async_mode=0) as pkg:
         e_hid, e_rgb = _cips_case(pkg, 1, 128, SIMT)

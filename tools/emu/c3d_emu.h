@@ -147,6 +147,7 @@ struct AsyncOp {
   std::function<void()> run;
   // hazard bookkeeping for MMAs (ranges in TMEM columns; -1 = none)
   int d_col0 = -1, d_col1 = -1, a_col0 = -1, a_col1 = -1;
+  bool both_ctas = false;
   const char* what = "";
 };
 struct AsyncQueue {
@@ -465,6 +466,7 @@ inline int launch(const char* name, dim3 grid, dim3 block, size_t dyn_smem, int 
   l.name = name;
   l.rng.seed(config().seed);
   g.launch = &l;
+  if (config().verbose) fprintf(stderr, "c3d_emu: launch %s grid (%u,%u,%u) block %u cluster %d smem %zu\n", name, grid.x, grid.y, grid.z, block.x, l.cluster, dyn_smem);
   const int nthreads = (int)(block.x * block.y * block.z);
   const long long nblocks = (long long)grid.x * grid.y * grid.z;
   if (grid.x % l.cluster) { fprintf(stderr, "c3d_emu: grid.x %% cluster != 0\n"); abort(); }
@@ -614,8 +616,10 @@ inline void tmem_check_warp(uint32_t taddr, int ncols, const char* what) {
   if (col < 0 || col + ncols > f->cta->tmem_allocated) fail("%s: columns %d..%d outside the allocation (%d columns)", what, col, col + ncols - 1, f->cta->tmem_allocated);
 }
 inline void tmem_hazard(Cta* c, int col0, int col1, bool is_store, const char* what) {
-  for (auto& q : c->queues)
+  for (Cta* oc : L().ctas)
+  for (auto& q : oc->queues)
     for (auto& op : q.q) {
+      if (oc != c && !op.both_ctas) continue;     // a cta_group::2 MMA touches the same columns in both CTAs
       if (op.d_col0 >= 0 && col0 < op.d_col1 && op.d_col0 < col1)
         fail("race: %s of TMEM columns %d..%d while a queued %s still writes columns %d..%d", what, col0, col1 - 1, op.what, op.d_col0, op.d_col1 - 1);
       if (is_store && op.a_col0 >= 0 && col0 < op.a_col1 && op.a_col0 < col1)
@@ -688,7 +692,7 @@ inline InstrDesc decode_idesc(uint32_t id, int cta_group) {
   r.M = (int)(id >> 24 & 0x1Fu) << 4;
   const int m_ok = cta_group == 1 ? 128 : 256;
   if (r.M != m_ok) fail("tcgen05.mma: M = %d not emulated for cta_group::%d (need %d)", r.M, cta_group, m_ok);
-  const int nstep = cta_group == 1 ? 16 : 32;
+  const int nstep = 16;
   if (r.N < nstep || r.N > 256 || r.N % nstep) fail("tcgen05.mma: N = %d invalid for M = %d", r.N, r.M);
   return r;
 }
@@ -766,6 +770,62 @@ inline void mma_issue_cg1(uint32_t d_tmem, bool a_from_tmem, uint64_t a_desc_or_
     mma_execute_cg1(c, d_col, a_from_tmem, a_col, a_base, ad, b_base, bd, N, acc);
   };
   submit_async(c, f->tid, std::move(op));
+  preempt_point();
+}
+// cta_group::2: D_v[128 x N] (+)= A_v[128 x 16] * [B_0; B_1][N x 16]^T in each CTA v of the pair; CTA v holds rows
+// [v*N/2, (v+1)*N/2) of B at the descriptor's address in ITS shared memory (cute MMA_Traits<SM100_MMA_F16BF16_2x1SM_SS>:
+// ALayout / BLayout / CLayout split M, N and M across the two CTAs).
+inline void mma_issue_cg2(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  Fiber* f = cur();
+  Launch& l = L();
+  if (l.ctas.size() != 2) fail("tcgen05.mma.cta_group::2 needs a 2-CTA cluster (have %zu)", l.ctas.size());
+  if (f->cta->rank != 0) fail("tcgen05.mma.cta_group::2 issued by CTA rank %d (only the leader, rank 0, may issue)", f->cta->rank);
+  const InstrDesc id = decode_idesc(idesc, 2);
+  if (d_tmem >> 16) fail("tcgen05.mma: D address names lane %u", d_tmem >> 16);
+  const int d_col = (int)(d_tmem & 0xFFFF), N = id.N, NH = id.N / 2;
+  const SmemDesc ad = decode_desc(a_desc, "tcgen05.mma A"), bd = decode_desc(b_desc, "tcgen05.mma B");
+  uint8_t* a_base[2];
+  uint8_t* b_base[2];
+  uint64_t ha[2], hb[2];
+  for (int v = 0; v < 2; ++v) {
+    Cta* c = l.ctas[v];
+    if (d_col + N > c->tmem_allocated) fail("tcgen05.mma: D columns %d..%d outside CTA %d's allocation", d_col, d_col + N - 1, v);
+    a_base[v] = desc_ptr(c, ad.addr, canon_span(ad, 128), "tcgen05.mma A");
+    b_base[v] = desc_ptr(c, bd.addr, canon_span(bd, NH), "tcgen05.mma B");
+    ha[v] = hash_operand(a_base[v], ad, 128);
+    hb[v] = hash_operand(b_base[v], bd, NH);
+  }
+  Cta* c0 = l.ctas[0];
+  Cta* c1 = l.ctas[1];
+  const bool acc = accumulate != 0;
+  AsyncOp op;
+  op.what = "tcgen05.mma.cta_group::2";
+  op.d_col0 = d_col; op.d_col1 = d_col + N;
+  op.both_ctas = true;
+  op.run = [=]() {
+    Cta* cs[2] = {c0, c1};
+    for (int v = 0; v < 2; ++v) {
+      if (hash_operand(a_base[v], ad, 128) != ha[v]) fail("race: CTA %d's A operand of a cta_group::2 MMA changed between issue and execution", v);
+      if (hash_operand(b_base[v], bd, NH) != hb[v]) fail("race: CTA %d's half of the B operand of a cta_group::2 MMA changed between issue and execution", v);
+    }
+    std::vector<float> B((size_t)N * 16);
+    for (int n = 0; n < N; ++n)
+      for (int k = 0; k < 16; ++k) B[(size_t)n * 16 + k] = h2f(canon_elem(b_base[n / NH], bd, n % NH, k));
+    for (int v = 0; v < 2; ++v)
+      for (int r = 0; r < 128; ++r) {
+        float a[16];
+        for (int k = 0; k < 16; ++k) a[k] = h2f(canon_elem(a_base[v], ad, r, k));
+        for (int n = 0; n < N; ++n) {
+          uint32_t& dw = cs[v]->T(r, d_col + n);
+          float accv = 0.f;
+          if (acc) memcpy(&accv, &dw, 4);
+          const float* b = &B[(size_t)n * 16];
+          for (int k = 0; k < 16; ++k) accv += a[k] * b[k];
+          memcpy(&dw, &accv, 4);
+        }
+      }
+  };
+  submit_async(f->cta, f->tid, std::move(op));
   preempt_point();
 }
 // tcgen05.commit: the arrive happens once every MMA this thread issued before has executed

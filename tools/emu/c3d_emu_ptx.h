@@ -95,3 +95,18 @@ template <int N>
 inline void reg_inc() { emu::syncwarp(); }
 inline uint32_t cluster_ctarank() { return (uint32_t)emu::cur()->cta->rank; }
 inline void cluster_sync_all() { emu::cluster_sync(); }
+
+// ---- tcgen05 cta_group::2
+template <int kCols>
+inline void tmem_alloc_cg2(uint32_t* smem_result) { emu::tmem_do_alloc(smem_result, kCols); }
+template <int kCols>
+inline void tmem_dealloc_cg2(uint32_t taddr) { emu::tmem_do_dealloc(taddr, kCols); }
+inline void umma_ss_w_cg2(uint32_t d_tmem, uint32_t a_lo, uint32_t b_lo, uint32_t desc_hi, uint32_t idesc, uint32_t accumulate) {
+  emu::mma_issue_cg2(d_tmem, (uint64_t)a_lo | (uint64_t)desc_hi << 32, (uint64_t)b_lo | (uint64_t)desc_hi << 32, idesc, accumulate);
+}
+inline void tc_commit_cg2_mc(uint64_t* bar, uint16_t mask) {
+  if (emu::cur()->cta->rank != 0) emu::fail("tcgen05.commit.cta_group::2 issued by CTA rank %d", emu::cur()->cta->rank);
+  tc_commit_mc(bar, mask);
+}
+inline bool mbar_try_wait_cluster(uint64_t* bar, uint32_t parity) { return mbar_try_wait(bar, parity); }
+inline void fence_proxy_async_all() {}
