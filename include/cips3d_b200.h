@@ -160,6 +160,44 @@ int c3d_upfirdn2d(const float* x, const float* kernel, float* y, int32_t planes,
                   int32_t pad_y1, void* stream);
 
 /* ------------------------------------------------------------------------------------
+ * Optimiser tail of the training step, multi-tensor, HBM-bound.
+ * Replaces, per optimiser (exp/cips3d/scripts/train.py:417-438 for D, :468-491 for G):
+ *   torch.nn.utils.clip_grad_norm_(params, grad_clip)         -> c3d_grad_norm
+ *   torch.optim.Adam(..., weight_decay=0).step() [+ zero_grad] -> c3d_adam_ema_step
+ *   comm_model_utils.EMA.update (exp/comm/comm_model_utils.py:99-121, target = target*decay + source*(1-decay))
+ *                                                              -> fused into c3d_adam_ema_step; c3d_ema_update for
+ *                                                                 state_dict entries without optimiser state
+ * The tensor table is a HOST array of device pointers (it travels as a kernel argument).
+ * ---------------------------------------------------------------------------------- */
+#define C3D_OPT_MAX_TENSORS 160   /* per launch; longer tables are processed in groups */
+typedef struct C3dOptTensor {
+  float* param;       /* (n) parameter                                                   */
+  float* grad;        /* (n) gradient (written only when zero_grad != 0)                  */
+  float* exp_avg;     /* (n) Adam first moment  (torch state 'exp_avg')                   */
+  float* exp_avg_sq;  /* (n) Adam second moment (torch state 'exp_avg_sq')                */
+  float* ema;         /* (n) EMA copy of the parameter or NULL                            */
+  int64_t n;
+} C3dOptTensor;
+
+typedef struct C3dAdamParams {   /* doubles: torch holds them as Python floats */
+  double lr, beta1, beta2, eps;
+  double ema_decay;   /* < 0: skip the EMA update this step (itr < start_itr)            */
+  int64_t step;       /* the step count AFTER this update's increment (>= 1)             */
+  int32_t zero_grad;  /* 1: also write zeros into the gradients                          */
+} C3dAdamParams;
+
+size_t c3d_optim_workspace_bytes(void);
+/* norm_out[0] = || all gradients ||_2 ; norm_out[1] = min(1, max_norm / (norm + 1e-6))  (1 if max_norm <= 0).
+ * norm_out: 2 device floats.  Deterministic (fixed summation order for a given device). */
+int c3d_grad_norm(const C3dOptTensor* tensors, int32_t n_tensors, float max_norm, float* norm_out,
+                  void* workspace, size_t workspace_bytes, void* stream);
+/* clip_coef: device pointer to the clip coefficient (norm_out + 1) or NULL (no clipping). */
+int c3d_adam_ema_step(const C3dOptTensor* tensors, int32_t n_tensors, const C3dAdamParams* hp,
+                      const float* clip_coef, void* stream);
+/* ema = ema * decay + param * (1 - decay) for every tensor (param, ema, n used). */
+int c3d_ema_update(const C3dOptTensor* tensors, int32_t n_tensors, double decay, void* stream);
+
+/* ------------------------------------------------------------------------------------
  * Self-test of the tcgen05 building block (UMMA descriptors, TMEM round trip):
  * D[128,N] = A[128,K] * B[N,K]^T with fp16 operands / fp32 accumulate, A and B given as
  * fp32 row-major (K contiguous) and converted on device.  Used by tests/test_umma_gpu.py.

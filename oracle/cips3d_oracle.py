@@ -615,3 +615,40 @@ def generator_template(cfg=G_CFG):
     mapping("mapping_network_inr", cfg["mapping_inr_cfg"])
     t["aux_to_rbg.0.weight"], t["aux_to_rbg.0.bias"] = (3, n["rgb_dim"]), (3,)
     return t
+
+
+# --------------------------------------------------------------------------------------
+# Optimiser tail of the training step:
+#   exp/cips3d/scripts/train.py:417-438 (D) / :468-491 (G)
+#     clip_grad_norm_(parameters, grad_clip)  -- torch/nn/utils/clip_grad.py: norm of the per-tensor L2 norms,
+#                                                clip_coef = max_norm / (total_norm + 1e-6), clamped to 1, grads *= coef
+#     Adam.step()                             -- torch/optim/adam.py::_single_tensor_adam (weight_decay 0, amsgrad off)
+#   exp/comm/comm_model_utils.py:99-121 EMA.update: target = target * decay + source * (1 - decay), skipped while
+#     itr < start_itr.
+# In place on the given lists of tensors; `step` is the count AFTER the increment (1 for the first update).
+# Pinned against torch.optim.Adam + torch.nn.utils.clip_grad_norm_ + the reference's EMA class in
+# tests/test_oracle_vs_reference.py::test_optimiser_tail_vs_torch_and_reference_ema.
+# --------------------------------------------------------------------------------------
+def clip_adam_ema_step(params, grads, exp_avg, exp_avg_sq, ema=None, *, step, lr, betas, eps=1e-8,
+                       max_norm=None, ema_decay=None):
+    total_norm = None
+    if max_norm is not None:
+        norms = [torch.linalg.vector_norm(g, 2.0) for g in grads]
+        total_norm = torch.linalg.vector_norm(torch.stack(norms), 2.0)
+        clip_coef = max_norm / (total_norm + 1e-6)
+        clip_coef_clamped = torch.clamp(clip_coef, max=1.0)
+        for g in grads:
+            g.mul_(clip_coef_clamped)
+    beta1, beta2 = betas
+    bias_correction1 = 1 - beta1 ** step
+    bias_correction2 = 1 - beta2 ** step
+    step_size = lr / bias_correction1
+    bias_correction2_sqrt = bias_correction2 ** 0.5
+    for i, (p, g, m, v) in enumerate(zip(params, grads, exp_avg, exp_avg_sq)):
+        m.lerp_(g, 1 - beta1)
+        v.mul_(beta2).addcmul_(g, g, value=1 - beta2)
+        denom = (v.sqrt() / bias_correction2_sqrt).add_(eps)
+        p.addcdiv_(m, denom, value=-step_size)
+        if ema is not None and ema_decay is not None:
+            ema[i].copy_(ema[i] * ema_decay + p * (1 - ema_decay))
+    return total_norm

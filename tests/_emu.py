@@ -44,12 +44,12 @@ def emulated(async_mode=2, seed=1, preempt_permille=20, sms=2):
     import cips3d_b200 as pkg
     lib = emu_lib()
     lib.c3d_emu_configure(async_mode, seed, preempt_permille, sms)
-    L, ops = pkg._lib, pkg.ops
-    saved = (L._lib, L.ptr, L.stream_ptr, ops.ptr, ops.stream_ptr)
+    L, ops, optim = pkg._lib, pkg.ops, pkg.optim
+    saved = (L._lib, L.ptr, L.stream_ptr, ops.ptr, ops.stream_ptr, optim.ptr, optim.stream_ptr)
     L._lib = L.bind(lib)
-    L.ptr = ops.ptr = _cpu_ptr
-    L.stream_ptr = ops.stream_ptr = lambda: None
+    L.ptr = ops.ptr = optim.ptr = _cpu_ptr
+    L.stream_ptr = ops.stream_ptr = optim.stream_ptr = lambda: None
     try:
         yield pkg
     finally:
-        L._lib, L.ptr, L.stream_ptr, ops.ptr, ops.stream_ptr = saved
+        L._lib, L.ptr, L.stream_ptr, ops.ptr, ops.stream_ptr, optim.ptr, optim.stream_ptr = saved

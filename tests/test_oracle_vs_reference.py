@@ -65,3 +65,35 @@ def test_discriminator_vs_reference():
         a = D(x, use_aux_disc=True, alpha=0.6)[0]
         b = O.discriminator_forward(sd, x, use_aux_disc=True, alpha=0.6)
     assert (a - b).abs().max().item() < 1e-6
+
+
+def test_optimiser_tail_vs_torch_and_reference_ema():
+    """oracle.clip_adam_ema_step == clip_grad_norm_ + torch.optim.Adam.step + the reference's EMA.update, bit for bit."""
+    import copy
+    ref_shim.install()
+    from exp.comm import comm_model_utils
+    torch.manual_seed(0)
+    net = torch.nn.Sequential(torch.nn.Linear(19, 33), torch.nn.Tanh(), torch.nn.Linear(33, 7))
+    net_ema = copy.deepcopy(net)
+    ema = comm_model_utils.EMA(source=net, target=net_ema, decay=0.999, start_itr=2)
+    opt = torch.optim.Adam(params=[{'params': net.parameters(), 'initial_lr': 2e-3}], lr=2e-3, betas=(0.0, 0.999),
+                           weight_decay=0, foreach=False)
+    P = [p.detach().clone() for p in net.parameters()]
+    M = [torch.zeros_like(p) for p in P]
+    V = [torch.zeros_like(p) for p in P]
+    E = [p.clone() for p in P]
+    for it in range(5):
+        x = torch.randn(8, 19)
+        opt.zero_grad()
+        net(x).square().mean().mul(1e3).backward()
+        grads = [p.grad.detach().clone() for p in net.parameters()]
+        n_ref = torch.nn.utils.clip_grad_norm_(net.parameters(), 10.0)
+        opt.step()
+        ema.update(itr=it, source_dict=net.state_dict())
+        n = O.clip_adam_ema_step(P, grads, M, V, E, step=it + 1, lr=2e-3, betas=(0.0, 0.999), max_norm=10.0,
+                                 ema_decay=0.999 if it >= 2 else None)
+        assert torch.equal(n, n_ref)
+        for a, b in zip(P, net.parameters()):
+            assert torch.equal(a, b.detach())
+        for a, b in zip(E, net_ema.parameters()):
+            assert torch.equal(a, b.detach())

@@ -116,6 +116,7 @@ struct WaitRec {
 struct Warp {
   uint32_t arrived = 0, exited = 0, gen = 0;
   uint32_t vals[32];
+  uint32_t shfl[32];
   uint32_t result = 0;
   int nthreads = 32;
   std::unordered_map<void*, WaitRec> waits;
@@ -596,15 +597,14 @@ inline uint32_t ballot_sync(uint32_t mask, int pred) {
   return warp_collective(mask, pred ? 1u : 0u, [](const uint32_t* v, uint32_t m) {
     uint32_t r = 0; for (int i = 0; i < 32; ++i) if ((m >> i & 1u) && v[i]) r |= 1u << i; return r; }, "__ballot_sync");
 }
-// shuffles: two collectives (publish, then read) -- the value table is per warp
+// shuffles: publish into a dedicated per-warp table, rendezvous, read, rendezvous (so nobody republishes early)
 inline uint32_t shfl_idx(uint32_t mask, uint32_t v, int src) {
   Fiber* f = cur();
   Warp* w = f->warp;
-  static thread_local uint32_t snap[32];
-  warp_collective(mask, v, [w](const uint32_t* vals, uint32_t) { (void)w; return 0u; }, "__shfl_sync");
-  const uint32_t r = w->vals[src & 31];
-  (void)snap;
-  syncwarp(mask);     // nobody overwrites vals before everyone has read
+  w->shfl[f->lane] = v;
+  syncwarp(mask);
+  const uint32_t r = w->shfl[src & 31];
+  syncwarp(mask);
   return r;
 }
 
@@ -857,6 +857,8 @@ inline void bulk_copy(std::vector<std::pair<void*, void*>> dst_bar, const void* 
 #undef __shared__
 #define __shared__ static
 #undef __launch_bounds__
+#undef __grid_constant__
+#define __grid_constant__
 #define __launch_bounds__(...)
 #define C3D_DYN_SMEM_ALIGNED(type, name, al) C3D_DYN_SMEM(type, name)
 #define C3D_DYN_SMEM(type, name) type* name = reinterpret_cast<type*>(emu::cur()->cta->smem)
