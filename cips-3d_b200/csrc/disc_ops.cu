@@ -153,6 +153,122 @@ __global__ void __launch_bounds__(256) blur_tile_kernel(const float* __restrict_
   }
 }
 
+// ---- Blur, streaming form (C3D_BLUR_TMA=1; opt-in until timed on hardware).
+// A persistent CTA walks strips of kStripH output rows of one plane.  The strip's input rows (kStripH + 3 of them,
+// each a contiguous, 16-byte aligned run of W floats) are staged into shared memory by the TMA engine -- one
+// cp.async.bulk per row into a padded row (zero margins = the FIR's zero padding in x), rows above / below the plane
+// are zero-filled by the threads -- double buffered behind two mbarriers, so the next strip streams in while the
+// current one is filtered.  Filtering: lane = output column (conflict-free shared reads, fully coalesced stores),
+// 8 output rows per thread from 11 input rows (44 LDS + 128 FMA per 8 outputs), taps in registers.  Columns beyond
+// the last multiple of 32 (the output width is odd: W +- 1) go through a small per-element tail.
+// Bytes: reads H*W (+ 3 halo rows per strip, L2 hits), writes OH*OW per plane.
+constexpr int kStripH = 32, kMargin = 4, kRowPad = 16, kBlurThreads = 256;
+
+struct BlurArgs {
+  const float* x;
+  const float* kernel;
+  float* y;
+  int planes, in_h, in_w, out_h, out_w, pad_x0, pad_y0, strips_per_plane;
+  long long total_strips;
+};
+
+__global__ void __launch_bounds__(kBlurThreads) blur_tma_kernel(const BlurArgs a) {
+  C3D_DYN_SMEM(float, sm);
+  __shared__ uint64_t full[2];
+  const int pitch = a.in_w + kRowPad;                 // floats per staged row: [4 zeros][W data][12 zeros]
+  const int rows = kStripH + 3;
+  auto buf_of = [&](int b) { return sm + (size_t)b * rows * pitch; };
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  float w[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) w[i] = __ldg(a.kernel + (3 - i / 4) * 4 + (3 - i % 4));    // flipped taps (correlation form)
+  if (tid == 0) {
+    mbar_init(&full[0], 1);
+    mbar_init(&full[1], 1);
+    fence_mbar_init();
+  }
+  for (int i = tid; i < 2 * rows * pitch; i += kBlurThreads) sm[i] = 0.f;               // margins stay zero for good
+  fence_proxy_async();
+  __syncthreads();
+
+  // stage strip `s` into buffer b: TMA for the rows inside the plane (thread 0), zero-fill for the others (all threads)
+  auto stage = [&](long long s, int b) {
+    const int plane = (int)(s / a.strips_per_plane), oy0 = (int)(s % a.strips_per_plane) * kStripH;
+    const float* xp = a.x + (size_t)plane * a.in_h * a.in_w;
+    const int iy0 = oy0 - a.pad_y0;
+    int n_in = 0;
+    for (int r = 0; r < rows; ++r) n_in += (iy0 + r >= 0 && iy0 + r < a.in_h) ? 1 : 0;
+    for (int r = 0; r < rows; ++r) {
+      const int iy = iy0 + r;
+      if (iy >= 0 && iy < a.in_h) continue;
+      for (int c = tid; c < a.in_w; c += kBlurThreads) buf_of(b)[(size_t)r * pitch + kMargin + c] = 0.f;
+    }
+    fence_proxy_async();      // generic writes (zero rows, and the previous consumers' reads) before the async writes
+    __syncthreads();
+    if (tid == 0) {
+      mbar_arrive_expect_tx(&full[b], (uint32_t)(n_in * a.in_w * 4));
+      for (int r = 0; r < rows; ++r) {
+        const int iy = iy0 + r;
+        if (iy >= 0 && iy < a.in_h)
+          bulk_g2s(buf_of(b) + (size_t)r * pitch + kMargin, xp + (size_t)iy * a.in_w, (uint32_t)(a.in_w * 4), &full[b]);
+      }
+    }
+  };
+
+  const long long first = blockIdx.x, step = gridDim.x;
+  if (first < a.total_strips) stage(first, 0);
+  uint32_t par = 0;      // bit b = parity of buffer b's next completion
+  int b = 0;
+  for (long long s = first; s < a.total_strips; s += step, b ^= 1) {
+    if (s + step < a.total_strips) stage(s + step, b ^ 1);      // prefetch the next strip into the other buffer
+    mbar_wait(&full[b], (par >> b) & 1u);
+    par ^= 1u << b;
+    const int plane = (int)(s / a.strips_per_plane), oy0 = (int)(s % a.strips_per_plane) * kStripH;
+    const int nrow = a.out_h - oy0 < kStripH ? a.out_h - oy0 : kStripH;
+    float* yp = a.y + ((size_t)plane * a.out_h + oy0) * a.out_w;
+    const float* sb = buf_of(b) + kMargin - a.pad_x0;      // sb[r*pitch + ox + kx] = input (iy0 + r, ox - pad_x0 + kx)
+    const int q = a.out_w / 32;
+    // ---- main part: warp items (column chunk c, row block rb of 8 rows), lane = column
+    for (int item = warp; item < q * (kStripH / 8); item += kBlurThreads / 32) {
+      const int c = item % q, rb = item / q;
+      if (rb * 8 >= nrow) continue;
+      const int ox = c * 32 + lane;
+      float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+      const float* sp = sb + (size_t)(rb * 8) * pitch + ox;
+#pragma unroll
+      for (int r = 0; r < 11; ++r) {
+        const float v0 = sp[r * pitch], v1 = sp[r * pitch + 1], v2 = sp[r * pitch + 2], v3 = sp[r * pitch + 3];
+#pragma unroll
+        for (int o = 0; o < 8; ++o) {
+          const int ky = r - o;
+          if (ky >= 0 && ky < 4) {      // resolved at compile time
+            acc[o] = fmaf(v0, w[ky * 4 + 0], acc[o]);
+            acc[o] = fmaf(v1, w[ky * 4 + 1], acc[o]);
+            acc[o] = fmaf(v2, w[ky * 4 + 2], acc[o]);
+            acc[o] = fmaf(v3, w[ky * 4 + 3], acc[o]);
+          }
+        }
+      }
+#pragma unroll
+      for (int o = 0; o < 8; ++o)
+        if (rb * 8 + o < nrow) __stcs(yp + (size_t)(rb * 8 + o) * a.out_w + ox, acc[o]);
+    }
+    // ---- tail columns [32 q, out_w): one output per thread and step
+    const int rem = a.out_w - q * 32;
+    for (int i = tid; i < rem * nrow; i += kBlurThreads) {
+      const int oy = i / rem, ox = q * 32 + i % rem;
+      const float* sp = sb + (size_t)oy * pitch + ox;
+      float acc = 0.f;
+#pragma unroll
+      for (int ky = 0; ky < 4; ++ky)
+#pragma unroll
+        for (int kx = 0; kx < 4; ++kx) acc = fmaf(sp[ky * pitch + kx], w[ky * 4 + kx], acc);
+      yp[(size_t)oy * a.out_w + ox] = acc;
+    }
+    __syncthreads();      // everyone is done reading this buffer before it is staged again (next iteration's prefetch)
+  }
+}
+
 }  // namespace c3d
 
 using namespace c3d;
@@ -201,6 +317,29 @@ extern "C" int c3d_upfirdn2d(const float* x, const float* kernel, float* y, int3
   int fw = (kTileW - 1) * down_x + kw, fh = (kTileH - 1) * down_y + kh;
   size_t smem = (size_t)fw * fh * sizeof(float);
   cudaStream_t st = (cudaStream_t)stream;
+  if (up_x == 1 && up_y == 1 && down_x == 1 && down_y == 1 && kh == 4 && kw == 4 && getenv("C3D_BLUR_TMA") &&
+      atoi(getenv("C3D_BLUR_TMA")) != 0 && in_w % 4 == 0 && ((uintptr_t)x & 15u) == 0 && pad_x0 >= 0 && pad_x0 <= kMargin &&
+      pad_x1 >= 0 && pad_x1 <= 4 && pad_y0 >= 0 && pad_y1 >= 0 && in_w <= 1024) {
+    BlurArgs ba;
+    ba.x = x; ba.kernel = kernel; ba.y = y;
+    ba.planes = planes; ba.in_h = in_h; ba.in_w = in_w; ba.out_h = out_h; ba.out_w = out_w;
+    ba.pad_x0 = pad_x0; ba.pad_y0 = pad_y0;
+    ba.strips_per_plane = c3d_div_up(out_h, kStripH);
+    ba.total_strips = (long long)planes * ba.strips_per_plane;
+    const size_t bsm = (size_t)2 * (kStripH + 3) * (in_w + kRowPad) * sizeof(float);
+    int dev = 0;
+    cudaGetDevice(&dev);
+    const int sms = c3d_device_sm_count(dev);
+    int per_sm = (int)((200 * 1024) / (bsm + 1024));
+    if (per_sm < 1) per_sm = 1;
+    if (per_sm > 8) per_sm = 8;
+    long long grid = (long long)sms * per_sm;
+    if (grid > ba.total_strips) grid = ba.total_strips;
+    if (bsm > 48 * 1024) C3D_CUDA(cudaFuncSetAttribute(blur_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bsm));
+    C3D_LAUNCH(blur_tma_kernel, (int)grid, kBlurThreads, bsm, st, ba);
+    C3D_LAUNCH_CHECK();
+    return C3D_OK;
+  }
   if (up_x == 1 && up_y == 1 && down_x == 1 && down_y == 1) {     // the discriminator's Blur
     for (int p0 = 0; p0 < planes; p0 += 65535) {
       int np = planes - p0 < 65535 ? planes - p0 : 65535;

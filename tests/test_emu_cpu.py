@@ -203,3 +203,23 @@ def test_emu_upfirdn2d(shape, up, down, pad):
         y = pkg.ops._upfirdn2d_raw(x, k, up, down, pad)
     ref = O.upfirdn2d(x, k, up, down, pad)
     assert y.shape == ref.shape and (y - ref).abs().max().item() < 1e-5
+
+
+@pytest.mark.parametrize("mode", ["eager", "lazy", "random"])
+@pytest.mark.parametrize("shape,pad", [
+    ((2, 3, 64, 64), (2, 2, 2, 2)), ((1, 2, 256, 256), (1, 1, 1, 1)), ((1, 2, 256, 256), (2, 2, 2, 2)),
+    ((3, 1, 8, 8), (2, 2, 2, 2)), ((1, 5, 4, 4), (1, 1, 1, 1)), ((1, 1, 100, 36), (2, 1, 0, 3)), ((1, 2, 70, 128), (1, 1, 1, 1))])
+def test_emu_blur_tma_streaming_kernel(shape, pad, mode, monkeypatch):
+    """C3D_BLUR_TMA=1: the discriminator's 4x4 blur with TMA row staging (cp.async.bulk per input row into zero-margined
+    shared rows, two mbarrier-guarded buffers, persistent strips).  2 emulated SMs -> every CTA walks several strips, so
+    the prefetch / re-staging protocol runs; shapes cover both paddings D uses at 256^2 (out 257 / 255: main columns +
+    tail), planes smaller than one strip, ragged last strips, asymmetric pads, a non-separable random kernel."""
+    monkeypatch.setenv("C3D_BLUR_TMA", "1")
+    g = torch.Generator().manual_seed(sum(shape))
+    x = torch.randn(*shape, generator=g)
+    k1 = torch.tensor([1., 3., 3., 1.])
+    for k in ((k1[None] * k1[:, None]) / 64, torch.randn(4, 4, generator=g)):
+        with emulated(async_mode=MODES[mode], seed=shape[2], sms=2) as pkg:
+            y = pkg.ops._upfirdn2d_raw(x, k, (1, 1), (1, 1), pad)
+        ref = O.upfirdn2d(x, k, (1, 1), (1, 1), pad)
+        assert y.shape == ref.shape and (y - ref).abs().max().item() < 1e-5

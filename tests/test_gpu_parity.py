@@ -321,6 +321,23 @@ def test_upfirdn2d_matches_oracle(pkg, shape, up, down, pad):
     assert (y.cpu().double() - ref).abs().max() < 1e-5
 
 
+@experimental
+@pytest.mark.parametrize("shape,pad", [((4, 16, 256, 256), (2, 2, 2, 2)), ((4, 16, 256, 256), (1, 1, 1, 1)),
+                                       ((2, 64, 128, 128), (2, 2, 2, 2)), ((3, 5, 8, 8), (1, 1, 1, 1)), ((1, 3, 70, 36), (2, 1, 0, 3))])
+def test_blur_tma_streaming_kernel(pkg, shape, pad, monkeypatch):
+    """C3D_BLUR_TMA=1 against the oracle and against the default blur kernel."""
+    g = torch.Generator().manual_seed(sum(shape))
+    x = torch.randn(*shape, generator=g)
+    k1 = torch.tensor([1., 3., 3., 1.])
+    k = (k1[None] * k1[:, None]) / 64
+    y0 = pkg.ops._upfirdn2d_raw(x.to(DEV), k.to(DEV), (1, 1), (1, 1), pad)
+    monkeypatch.setenv("C3D_BLUR_TMA", "1")
+    y1 = pkg.ops._upfirdn2d_raw(x.to(DEV), k.to(DEV), (1, 1), (1, 1), pad)
+    torch.cuda.synchronize()
+    ref = O.upfirdn2d(x, k, (1, 1), (1, 1), pad)
+    assert (y1.cpu() - ref).abs().max().item() < 1e-5 and (y1 - y0).abs().max().item() < 1e-6
+
+
 def test_upfirdn2d_autograd(pkg):
     k = O._blur_kernel(torch.float32).to(DEV)
     x = torch.randn(2, 3, 12, 12, device=DEV, requires_grad=True)

@@ -26,6 +26,7 @@ def timeit(fn, reps=20):
 
 out = []
 k = cips3d_b200.discriminator.make_kernel([1, 3, 3, 1]).to(dev)
+VARIANTS = os.environ.get("C3D_BLUR_TMA", "0")
 for (B, C, H) in [(16, 128, 256), (16, 256, 128), (16, 512, 64)]:
     x = torch.randn(B, C, H, H, device=dev)
     b = torch.randn(C, device=dev)
@@ -40,7 +41,7 @@ for (B, C, H) in [(16, 128, 256), (16, 256, 128), (16, 512, 64)]:
         ms = timeit(lambda: ops._upfirdn2d_raw(x, k, (1, 1), (1, 1), (pad[0], pad[1], pad[0], pad[1])))
         Ho = H + pad[0] + pad[1] - 3
         gb = (x.numel() + B * C * Ho * Ho) * 4 / 1e9
-        out.append(dict(op=f"upfirdn2d blur pad{pad}", shape=[B, C, H, H], ms=ms, gbs=gb / ms * 1e3, frac=gb / ms * 1e3 / peak))
+        out.append(dict(op=f"upfirdn2d blur pad{pad} (C3D_BLUR_TMA={VARIANTS})", shape=[B, C, H, H], ms=ms, gbs=gb / ms * 1e3, frac=gb / ms * 1e3 / peak))
 for r in out:
     print(json.dumps(r))
 print(json.dumps(dict(hbm_peak_gbs=peak, note="algorithmic bytes (read x + write y [+ read ref]) / CUDA-event median; L2 flushed between reps")))
