@@ -134,6 +134,14 @@ __device__ __forceinline__ float sample_alpha(float delta, float sigma, float no
   return __fsub_rn(1.f, expf(__fmul_rn(-delta, act)));
 }
 
+// MATH = 0: per-ray math by all 256 threads of the slot on shared-memory arrays, block barriers between the steps (the
+//           kernel measured in round 1).
+// MATH = 1: per-ray math by ONE WARP PER RAY with shuffles (lane = sample): prefix products / sums are warp scans, the
+//           stable rank sort is nS shuffles, compositing shuffles the weights -- the ~10 slot-wide barriers and the
+//           serial shared-memory loops of MATH 0 (28 % of a ray group's time in the round-1 trace) disappear.  Needs
+//           2S <= 32 (hierarchical: two rays share a warp in the resampling step).  C3D_RAY_MATH=warp; emulation-verified,
+//           not yet timed on hardware.
+template <int MATH>
 __global__ void __launch_bounds__(640, 1) ray_siren_tc_kernel(const KArgs a) {
   C3D_DYN_SMEM(uint8_t, smem_raw);
   Smem& s = *reinterpret_cast<Smem*>(smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u));
@@ -227,6 +235,7 @@ __global__ void __launch_bounds__(640, 1) ray_siren_tc_kernel(const KArgs a) {
     const int q = warp & 3;
     const int row = q * 32 + lane;       // point row of the group
     const int stid = half * 128 + row;   // 0..255 within the slot
+    const int tw = q + 4 * half;         // warp 0..7 within the slot's team
     SlotMem& sm = s.slot[sl];
     const uint32_t lane_sel = (uint32_t)(q * 32) << 16;
     const uint32_t a_hi = tmem + (uint32_t)(sl * 256) + lane_sel, a_lo = a_hi + 64, dcol = a_hi + 128;
@@ -405,7 +414,60 @@ __global__ void __launch_bounds__(640, 1) ray_siren_tc_kernel(const KArgs a) {
         slot_sync();
         stamp(10);
         // ---------------- importance resampling, all threads (generator_nerf_inr.py:537-598, pigan_utils.py:164-209)
-        if (pass == 0 && hier) {
+        if (MATH == 1 && pass == 0 && hier) {
+          // ---- warp per ray, two rays per warp (lanes 0-15 / 16-31; S <= 16): lane e = coarse sample e
+          const unsigned full = 0xffffffffu;
+          const int sub = lane >> 4, e = lane & 15, ns = S - 2;
+          for (int g0 = 0; g0 < n_valid; g0 += 16) {
+            const int g = g0 + tw + 8 * sub;
+            const bool act = g < n_valid && e < S;
+            const int r0 = g * S;
+            const size_t ro = (size_t)img * p.n_rays + ray0 + g;
+            const float z = act ? sm.z_c[r0 + e] : 0.f;
+            const float zn = __shfl_down_sync(full, z, 1, 16);
+            float alpha = 0.f, f = 1.f;
+            if (act) {
+              const float delta = e + 1 < S ? __fsub_rn(zn, z) : 1e10f;
+              const float nz = a.io.noise_c ? __fmul_rn(a.io.noise_c[ro * S + e], p.noise_std) : 0.f;
+              alpha = sample_alpha(delta, sm.sig_c[r0 + e], nz, p.clamp_mode);
+              f = __fadd_rn(__fsub_rn(1.f, alpha), 1e-10f);
+            }
+            float P = f;                                  // inclusive product scan over the ray's lanes
+#pragma unroll
+            for (int d = 1; d < 16; d <<= 1) {
+              const float t = __shfl_up_sync(full, P, d, 16);
+              if (e >= d) P = __fmul_rn(P, t);
+            }
+            float T = __shfl_up_sync(full, P, 1, 16);
+            if (e == 0) T = 1.f;
+            const float w = __fmul_rn(alpha, T);          // coarse compositing weight (pigan_utils.py:256-257)
+            const float wn = __shfl_down_sync(full, w, 1, 16);
+            const float wt = e <= S - 3 ? __fadd_rn(__fadd_rn(wn, 1e-5f), 1e-5f) : 0.f;   // (w + 1e-5)[1:-1] + 1e-5
+            float sum = wt;
+#pragma unroll
+            for (int o = 8; o > 0; o >>= 1) sum += __shfl_xor_sync(full, sum, o, 16);
+            const float pdf = __fmul_rn(wt, __fdividef(1.f, sum));
+            float C = pdf;                                // cdf_j = sum_{i<j} pdf_i, j = 0..S-2
+#pragma unroll
+            for (int d = 1; d < 16; d <<= 1) {
+              const float t = __shfl_up_sync(full, C, d, 16);
+              if (e >= d) C = __fadd_rn(C, t);
+            }
+            float cdf = __shfl_up_sync(full, C, 1, 16);
+            if (e == 0) cdf = 0.f;
+            const float uk = act ? a.io.pdf_u[ro * S + e] : 0.f;
+            int i = 0;                                    // searchsorted(cdf, u, right=False): the cdf is non-decreasing
+            for (int j = 0; j <= ns; ++j) i += __shfl_sync(full, cdf, j, 16) < uk ? 1 : 0;
+            const int below = max(i - 1, 0), above = min(i, ns);
+            const float cb = __shfl_sync(full, cdf, below, 16), ca = __shfl_sync(full, cdf, above, 16);
+            const float bb = 0.5f * __fadd_rn(__shfl_sync(full, z, below, 16), __shfl_sync(full, z, below + 1, 16));
+            const float ba = 0.5f * __fadd_rn(__shfl_sync(full, z, above, 16), __shfl_sync(full, z, above + 1, 16));
+            float denom = __fsub_rn(ca, cb);
+            if (denom < 1e-5f) denom = 1.f;
+            if (act) sm.z_f[r0 + e] = __fadd_rn(bb, __fmul_rn(__fdiv_rn(__fsub_rn(uk, cb), denom), __fsub_rn(ba, bb)));
+          }
+          slot_sync();
+        } else if (pass == 0 && hier) {
           const int r0 = g_row * S;
           float alpha = 0.f;
           if (half == 0 && pt_ok) {   // A: alpha_i and (1 - alpha_i + 1e-10)
@@ -449,6 +511,71 @@ __global__ void __launch_bounds__(640, 1) ray_siren_tc_kernel(const KArgs a) {
       }
       stamp(11);
       // ---------------- merge (stable rank sort of the nS depths of each ray), generator.py:1733-1738
+      if (MATH == 1) {
+        // ---- warp per ray: lane e = element e of cat([fine, coarse]) for the sort, lane = channel for the compositing
+        const unsigned full = 0xffffffffu;
+        const float* featf = &sm.feat[0][0][0];
+        for (int g = tw; g < n_valid; g += 8) {          // warp-uniform
+          const int rc0 = g * S, base = g * nS, e = lane;
+          const bool act = e < nS;
+          const size_t ro = (size_t)img * p.n_rays + ray0 + g;
+          const float k = act ? (hier ? (e < S ? sm.z_f[rc0 + e] : sm.z_c[rc0 + e - S]) : sm.z_c[rc0 + e]) : 3.0e38f;
+          int rank = 0;                                   // stable ascending rank (torch.sort over cat([fine, coarse]))
+          for (int j = 0; j < nS; ++j) {
+            const float kj = __shfl_sync(full, k, j);
+            rank += (kj < k || (kj == k && j < e)) ? 1 : 0;
+          }
+          if (act) {
+            sm.skey[base + rank] = k;
+            sm.sidx[base + rank] = hier ? e : S + e;
+          }
+          __syncwarp();
+          const float ks = act ? sm.skey[base + e] : 0.f;
+          const int src = act ? sm.sidx[base + e] : S;
+          const float kn = __shfl_down_sync(full, ks, 1);
+          float alpha = 0.f, f = 1.f;
+          if (act) {
+            const float sg = src < S ? sm.sig_f[rc0 + src] : sm.sig_c[rc0 + src - S];
+            const float delta = e + 1 < nS ? __fsub_rn(kn, ks) : 1e10f;
+            const float nz = a.io.noise_f ? __fmul_rn(a.io.noise_f[ro * nS + e], p.noise_std) : 0.f;
+            alpha = sample_alpha(delta, sg, nz, p.clamp_mode);
+            f = __fadd_rn(__fsub_rn(1.f, alpha), 1e-10f);
+          }
+          float P = f;
+#pragma unroll
+          for (int d = 1; d < 32; d <<= 1) {
+            const float t = __shfl_up_sync(full, P, d);
+            if (e >= d) P = __fmul_rn(P, t);
+          }
+          float T = __shfl_up_sync(full, P, 1);
+          if (e == 0) T = 1.f;
+          float w = __fmul_rn(alpha, T);
+          float wsum = w;
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) wsum += __shfl_xor_sync(full, wsum, o);
+          if (p.last_back && e == nS - 1) w += 1.f - wsum;
+          const int frow = src < S ? rc0 + src : kRows + rc0 + src - S;
+          float acc = 0.f;
+#pragma unroll 4
+          for (int i = 0; i < nS; ++i)
+            acc = fmaf(__shfl_sync(full, w, i), featf[__shfl_sync(full, frow, i) * 33 + lane], acc);
+          if (p.white_back) acc += 1.f - wsum;
+          a.io.pixels_fea[ro * kFeat + lane] = acc;
+          if (act && a.io.weights) a.io.weights[ro * nS + e] = w;
+          if (act && a.io.dbg_all_z) a.io.dbg_all_z[ro * nS + e] = ks;
+          if (a.io.depth) {
+            float d = act ? __fmul_rn(w, ks) : 0.f;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) d += __shfl_xor_sync(full, d, o);
+            if (lane == 0) a.io.depth[ro] = d;
+          }
+          __syncwarp();
+        }
+        slot_sync();
+        stamp(12);
+        stamp(13);
+        continue;
+      }
       const bool el_ok = g_el < n_valid;
       const int rc0 = g_el * S;           // first row of ray g_el
       const int base = g_el * nS;
@@ -623,13 +750,18 @@ int c3d_ray_siren_fwd_tc(const C3dRayParams* p, const C3dSirenWeights* w, const 
   const size_t smem = sizeof(Smem) + 1024;
   static std::atomic<unsigned long long> attr_set{0};     // per device, once
   if (!(attr_set.load() >> (dev & 63) & 1ull)) {
-    C3D_CUDA(cudaFuncSetAttribute(ray_siren_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    C3D_CUDA(cudaFuncSetAttribute(ray_siren_tc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    C3D_CUDA(cudaFuncSetAttribute(ray_siren_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_set.fetch_or(1ull << (dev & 63));
   }
   int grid = (ka.total_groups + 1) / 2;
   if (grid > sms) grid = sms;
   if (grid < 1) grid = 1;
-  C3D_LAUNCH(ray_siren_tc_kernel, grid, 640, smem, st, ka);
+  // C3D_RAY_MATH=warp: warp-per-ray math (needs 2S <= 32 samples per warp); default: the round-1 block-wide form
+  const char* rm = getenv("C3D_RAY_MATH");
+  const bool warp_math = rm && rm[0] == 'w' && p->num_steps * (p->hierarchical ? 2 : 1) <= 32 && (!p->hierarchical || p->num_steps <= 16);
+  if (warp_math) C3D_LAUNCH(ray_siren_tc_kernel<1>, grid, 640, smem, st, ka);
+  else C3D_LAUNCH(ray_siren_tc_kernel<0>, grid, 640, smem, st, ka);
   C3D_LAUNCH_CHECK();
   return C3D_OK;
 }

@@ -88,6 +88,18 @@ def test_emu_ray_siren_tc_matches_reference_golden(name, mode):
     _check_render(out, ref)
 
 
+@pytest.mark.parametrize("mode", ["lazy", "random"])
+@pytest.mark.parametrize("name", GEN_CASES)
+def test_emu_ray_siren_tc_warp_per_ray_math(name, mode, monkeypatch):
+    """C3D_RAY_MATH=warp: resampling / merge / compositing by one warp per ray with shuffles (scans, rank sort) instead of
+    block-wide shared-memory passes.  Same goldens of the real reference, same bounds (noise, softplus, last_back,
+    white_back, non-hierarchical S = 24 are all in the cases).  Not yet timed on hardware."""
+    monkeypatch.setenv("C3D_RAY_MATH", "warp")
+    with emulated(async_mode=MODES[mode], seed=5) as pkg:
+        out, ref = _render(pkg, name, TC)
+    _check_render(out, ref)
+
+
 @pytest.mark.parametrize("name", ["r16_trained_noise", "r8_nohier_s24"])
 def test_emu_ray_siren_simt_matches_reference_golden(name):
     with emulated(async_mode=0) as pkg:

@@ -141,6 +141,19 @@ experimental = pytest.mark.skipif(os.environ.get("C3D_EXPERIMENTAL", "0") != "1"
 
 
 @experimental
+@pytest.mark.parametrize("name", GEN_CASES)
+def test_renderer_warp_per_ray_math_matches_reference_golden(pkg, name, monkeypatch):
+    """C3D_RAY_MATH=warp (warp-per-ray resampling / merge / compositing) against the reference goldens."""
+    monkeypatch.setenv("C3D_RAY_MATH", "warp")
+    out, ref, _, _ = _render_case(pkg, name, pkg._lib.IMPL_TC)
+    assert rel_err(out["coarse"].cpu(), ref["coarse"])[0] < 2e-4
+    assert rel_err(out["all_z"].cpu(), ref["all_z"])[0] < 2e-4
+    frac, worst = close_frac(out["pixels_fea"], ref["pixels_fea"], 1e-3)
+    assert frac >= 0.995, f"only {frac:.4f} of rays within 1e-3 (worst {worst:.3e})"
+    assert close_frac(out["depth"][..., None], ref["depth"][..., None], 1e-3)[0] >= 0.995
+
+
+@experimental
 @pytest.mark.parametrize("B,N", [(1, 256), (2, 512), (3, 200), (4, 4096)])
 def test_cips_cta_pair_matches_oracle(pkg, B, N, monkeypatch):
     """C3D_CIPS_PAIR=1: the cta_group::2 variant of the CIPS kernel against the fp64 oracle and, bit for bit,

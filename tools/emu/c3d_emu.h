@@ -874,9 +874,27 @@ inline void __syncwarp(unsigned mask = 0xffffffffu) { emu::syncwarp(mask); }
 inline int __all_sync(unsigned mask, int pred) { return emu::all_sync(mask, pred); }
 inline int __any_sync(unsigned mask, int pred) { return emu::any_sync(mask, pred); }
 inline unsigned __ballot_sync(unsigned mask, int pred) { return emu::ballot_sync(mask, pred); }
-inline float __shfl_sync(unsigned mask, float v, int src) { uint32_t u; memcpy(&u, &v, 4); u = emu::shfl_idx(mask, u, src); memcpy(&v, &u, 4); return v; }
-inline float __shfl_xor_sync(unsigned mask, float v, int x) { return __shfl_sync(mask, v, emu::cur()->lane ^ x); }
-inline float __shfl_down_sync(unsigned mask, float v, int d) { const int s = emu::cur()->lane + d; return __shfl_sync(mask, v, s < 32 ? s : emu::cur()->lane); }
+// warp shuffles with the CUDA `width` semantics (segments of `width` lanes; out-of-segment sources return the own value)
+template <class T> inline T c3d_emu_shfl_from(unsigned mask, T v, int src_lane) {
+  static_assert(sizeof(T) == 4, "32-bit shuffles only");
+  uint32_t u; memcpy(&u, &v, 4); u = emu::shfl_idx(mask, u, src_lane); memcpy(&v, &u, 4); return v;
+}
+template <class T> inline T __shfl_sync(unsigned mask, T v, int src, int width = 32) {
+  const int lane = emu::cur()->lane;
+  return c3d_emu_shfl_from(mask, v, (lane & ~(width - 1)) | (src & (width - 1)));
+}
+template <class T> inline T __shfl_xor_sync(unsigned mask, T v, int x, int width = 32) {
+  const int lane = emu::cur()->lane, t = lane ^ x;
+  return c3d_emu_shfl_from(mask, v, (t & ~(width - 1)) == (lane & ~(width - 1)) ? t : lane);
+}
+template <class T> inline T __shfl_down_sync(unsigned mask, T v, int d, int width = 32) {
+  const int lane = emu::cur()->lane;
+  return c3d_emu_shfl_from(mask, v, (lane & (width - 1)) + d < width ? lane + d : lane);
+}
+template <class T> inline T __shfl_up_sync(unsigned mask, T v, int d, int width = 32) {
+  const int lane = emu::cur()->lane;
+  return c3d_emu_shfl_from(mask, v, (lane & (width - 1)) >= d ? lane - d : lane);
+}
 inline void __nanosleep(unsigned) { emu::yield(); }
 inline void __trap() { emu::fail("__trap()"); }
 template <class T> inline T __ldg(const T* p) { return *p; }

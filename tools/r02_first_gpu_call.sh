@@ -10,7 +10,7 @@ mkdir -p gpurun_out
 O=gpurun_out
 python __graft_entry__.py > $O/r02a_build.log 2>&1
 timeout 600 python -m pytest tests -m gpu -x -q > $O/r02a_pytest_gpu.log 2>&1; echo "default gpu suite: exit $?" | tee $O/r02a_summary.txt
-for k in "cips_cta_pair" "blur_tma"; do
+for k in "cips_cta_pair" "blur_tma" "warp_per_ray"; do
   C3D_EXPERIMENTAL=1 timeout 300 python -m pytest tests/test_gpu_parity.py -q -k "$k" > $O/r02a_pytest_$k.log 2>&1
   echo "experimental $k: exit $?" | tee -a $O/r02a_summary.txt
 done
@@ -19,12 +19,13 @@ timeout 300 python tools/time_kernels.py > $O/r02a_time_kernels_default.log 2>&1
 C3D_CIPS_PAIR=1 timeout 300 python tools/time_kernels.py > $O/r02a_time_kernels_pair.log 2>&1; echo "pair timing: exit $?" | tee -a $O/r02a_summary.txt
 timeout 300 python tools/time_forward.py 16 > $O/r02a_time_forward_default.log 2>&1
 C3D_CIPS_PAIR=1 timeout 300 python tools/time_forward.py 16 > $O/r02a_time_forward_pair.log 2>&1
+C3D_RAY_MATH=warp timeout 300 python tools/time_forward.py 16 > $O/r02a_time_forward_raywarp.log 2>&1; echo "ray warp-math timing: exit $?" | tee -a $O/r02a_summary.txt
 # HBM-bound ops
 timeout 300 python tools/bench_disc_ops.py > $O/r02a_disc_ops_default.jsonl 2>&1
 C3D_BLUR_TMA=1 timeout 300 python tools/bench_disc_ops.py > $O/r02a_disc_ops_blur_tma.jsonl 2>&1; echo "blur_tma bench: exit $?" | tee -a $O/r02a_summary.txt
 timeout 300 python tools/bench_optim.py > $O/r02a_optim.jsonl 2>&1; echo "optim bench: exit $?" | tee -a $O/r02a_summary.txt
 python bench.py --steps 20 --warmup 5 > $O/r02a_bench.json 2> $O/r02a_bench.err
-tail -n 3 $O/r02a_time_kernels_default.log $O/r02a_time_kernels_pair.log $O/r02a_time_forward_default.log $O/r02a_time_forward_pair.log
+tail -n 3 $O/r02a_time_kernels_default.log $O/r02a_time_kernels_pair.log $O/r02a_time_forward_default.log $O/r02a_time_forward_pair.log $O/r02a_time_forward_raywarp.log
 grep -h "blur" $O/r02a_disc_ops_default.jsonl $O/r02a_disc_ops_blur_tma.jsonl | cut -c1-200
 cat $O/r02a_optim.jsonl | cut -c1-300
 cat $O/r02a_summary.txt
