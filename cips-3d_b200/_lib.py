@@ -15,7 +15,7 @@ CIPS_MAX_LAYERS = 18
 EXPORTS = ("c3d_version", "c3d_last_error", "c3d_device_supported", "c3d_launch_count",
            "c3d_ray_siren_workspace_bytes",
            "c3d_ray_siren_fwd", "c3d_cips_workspace_bytes", "c3d_cips_fwd", "c3d_bias_act",
-           "c3d_upfirdn2d", "c3d_selftest_umma", "c3d_debug_cips_tile_order",
+           "c3d_upfirdn2d", "c3d_selftest_umma", "c3d_selftest_umma_pair", "c3d_debug_cips_tile_order",
            "c3d_optim_workspace_bytes", "c3d_grad_norm", "c3d_adam_ema_step", "c3d_ema_update")
 
 _fp = C.c_void_p  # device pointers travel as integers
@@ -93,6 +93,7 @@ def bind(lib):
                                  C.c_float, C.c_float, _fp]
     lib.c3d_upfirdn2d.argtypes = [_fp, _fp, _fp] + [C.c_int32] * 13 + [_fp]
     lib.c3d_selftest_umma.argtypes = [_fp, _fp, _fp, C.c_int32, C.c_int32, C.c_int32, _fp]
+    lib.c3d_selftest_umma_pair.argtypes = [_fp, _fp, _fp, C.c_int32, C.c_int32, _fp]
     if hasattr(lib, 'c3d_debug_cips_trace'):      # only in -DC3D_TRACE debug builds
         lib.c3d_debug_cips_trace.argtypes = [C.c_void_p, C.c_int]
     return lib

@@ -287,3 +287,13 @@ def selftest_umma(a, b, a_in_tmem=False):
     check(lib.c3d_selftest_umma(ptr(a), ptr(b), ptr(d), b.shape[0], a.shape[1], int(a_in_tmem), stream_ptr()),
           "c3d_selftest_umma")
     return d
+
+
+def selftest_umma_pair(a, b):
+    """D = A @ B^T through one tcgen05 cta_group::2 tile (cluster of two CTAs, M = 256; fp16 operands, fp32 accumulate)."""
+    lib = load()
+    a, b = _f32c(a, "a"), _f32c(b, "b")
+    assert a.shape[0] == 256 and a.shape[1] == b.shape[1]
+    d = torch.empty((256, b.shape[0]), device=a.device, dtype=torch.float32)
+    check(lib.c3d_selftest_umma_pair(ptr(a), ptr(b), ptr(d), b.shape[0], a.shape[1], stream_ptr()), "c3d_selftest_umma_pair")
+    return d

@@ -205,6 +205,10 @@ int c3d_ema_update(const C3dOptTensor* tensors, int32_t n_tensors, double decay,
 int c3d_selftest_umma(const float* a, const float* b, float* d, int32_t n, int32_t k,
                       int32_t a_in_tmem, void* stream);
 
+/* Same for the CTA-pair form (tcgen05 cta_group::2, cluster of two CTAs): D[256,N] = A[256,K] * B[N,K]^T, N a
+ * multiple of 32.  Isolates what the CTA-pair CIPS kernel (C3D_CIPS_PAIR=1) relies on. */
+int c3d_selftest_umma_pair(const float* a, const float* b, float* d, int32_t n, int32_t k, void* stream);
+
 /* ------------------------------------------------------------------------------------
  * Introspection for the CPU-side protocol test (host only, no GPU work): the order in which
  * c3d_cips_fwd's kernel issues the 32 (K64 x N128) weight tiles of a 512x512 layer and the 4

@@ -53,6 +53,17 @@ def test_emu_umma_selftest(mode, n, k, a_in_tmem):
     assert (d.double() - ref).abs().max().item() < 1e-5 * ref.abs().max().item()
 
 
+@pytest.mark.parametrize("mode", ["eager", "lazy", "random"])
+@pytest.mark.parametrize("n,k", [(32, 16), (128, 64), (256, 256), (96, 128)])
+def test_emu_umma_pair_selftest(mode, n, k):
+    g = torch.Generator().manual_seed(n * 1000 + k)
+    a, b = torch.randn(256, k, generator=g), torch.randn(n, k, generator=g)
+    with emulated(async_mode=MODES[mode], seed=n + k) as pkg:
+        d = pkg.ops.selftest_umma_pair(a, b)
+    ref = a.half().double() @ b.half().double().T
+    assert (d.double() - ref).abs().max().item() < 1e-5 * ref.abs().max().item()
+
+
 def _render(pkg, name, impl):
     sd, zs, draws, kw, meta, ref = load_gen_case(name)
     G = build_generator("cpu", sd)

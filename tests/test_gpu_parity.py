@@ -141,6 +141,19 @@ experimental = pytest.mark.skipif(os.environ.get("C3D_EXPERIMENTAL", "0") != "1"
 
 
 @experimental
+@pytest.mark.parametrize("n,k", [(32, 16), (128, 64), (256, 256), (96, 128)])
+def test_umma_pair_selftest(pkg, n, k):
+    """tcgen05 cta_group::2 in isolation (run this BEFORE the CTA-pair CIPS kernel: it pins the operand partitioning,
+    the multicast commit and the cluster-scope barrier hand-off the emulator assumes)."""
+    g = torch.Generator().manual_seed(n * 1000 + k)
+    a = torch.randn(256, k, generator=g).to(DEV)
+    b = torch.randn(n, k, generator=g).to(DEV)
+    d = pkg.ops.selftest_umma_pair(a, b)
+    ref = a.half().double() @ b.half().double().T
+    assert (d.double() - ref).abs().max().item() < 1e-3 * ref.abs().max().item()
+
+
+@experimental
 @pytest.mark.parametrize("name", GEN_CASES)
 def test_renderer_warp_per_ray_math_matches_reference_golden(pkg, name, monkeypatch):
     """C3D_RAY_MATH=warp (warp-per-ray resampling / merge / compositing) against the reference goldens."""

@@ -10,7 +10,7 @@ mkdir -p gpurun_out
 O=gpurun_out
 python __graft_entry__.py > $O/r02a_build.log 2>&1
 timeout 600 python -m pytest tests -m gpu -x -q > $O/r02a_pytest_gpu.log 2>&1; echo "default gpu suite: exit $?" | tee $O/r02a_summary.txt
-for k in "cips_cta_pair" "blur_tma" "warp_per_ray"; do
+for k in "umma_pair_selftest" "cips_cta_pair" "blur_tma" "warp_per_ray"; do
   C3D_EXPERIMENTAL=1 timeout 300 python -m pytest tests/test_gpu_parity.py -q -k "$k" > $O/r02a_pytest_$k.log 2>&1
   echo "experimental $k: exit $?" | tee -a $O/r02a_summary.txt
 done
