@@ -216,11 +216,11 @@ def sample_pdf(bins, weights, u, eps=1e-5):
     return bin_b + (u - cdf_b) / denom * (bin_a - bin_b)
 
 
-def fine_z_vals(coarse, z, noise_c, pdf_u, clamp_mode="relu"):
+def fine_z_vals(coarse, z, noise_c, pdf_u, clamp_mode="relu", dim_rgb=32):
     """get_fine_points_and_direction  exp/dev/nerf_inr/models/generator_nerf_inr.py:537-598
     coarse (B,N,S,33), z (B,N,S), noise_c (B,N,S)|None, pdf_u (B*N,S) -> fine z (B,N,S)"""
     B, N, S = z.shape
-    _, _, w = integrate(coarse, z, noise_c, clamp_mode=clamp_mode)
+    _, _, w = integrate(coarse, z, noise_c, clamp_mode=clamp_mode, dim_rgb=dim_rgb)
     w = w.reshape(B * N, S) + 1e-5
     zz = z.reshape(B * N, S)
     mid = 0.5 * (zz[:, :-1] + zz[:, 1:])
@@ -540,6 +540,12 @@ def synthetic_state_dict(template, seed=1234, sigma_bias=0.0, dtype=torch.float3
             if "siren.network" in key and ".linear." in key or "color_layer_sine.linear" in key:
                 fan = shape[-1]
                 val = u * math.sqrt(6 / fan) / 25
+            elif key == "siren.network.0.layer.weight":              # piGAN first_layer_film_sine_init (siren.py:36-40)
+                val = u / shape[-1]
+            elif ".layer.weight" in key or (key.startswith("siren.color_layer_linear") and shape[0] == 3):
+                val = u * math.sqrt(6 / shape[-1]) / 25              # piGAN frequency_init(25) (siren.py:75-81)
+            elif key.startswith("siren.mapping_network.network.6"):   # last mapping layer * 0.25 (siren.py:66-67)
+                val = 0.25 * v * math.sqrt(2 / (1 + 0.2 ** 2) / shape[-1])
             elif "gain_fc" in key or "bias_fc" in key:
                 val = 0.25 * u / math.sqrt(shape[-1])
             elif "inr_net.network" in key and len(shape) == 3:       # (1,in,out) SinStyleMod
@@ -652,3 +658,104 @@ def clip_adam_ema_step(params, grads, exp_avg, exp_avg_sq, ema=None, *, step, lr
         if ema is not None and ema_decay is not None:
             ema[i].copy_(ema[i] * ema_decay + p * (1 - ema_decay))
     return total_norm
+
+
+# --------------------------------------------------------------------------------------
+# pi-GAN surface: piGAN_lib/siren/siren.py:47-73 CustomMappingNetwork, :83-94 FiLMLayer,
+# :97-152 TALLSIREN, :160-215 SPATIALSIRENBASELINE; piGAN_lib/generators/generators.py:12-96 ImplicitGenerator3d.forward,
+# :110-204 staged_forward; piGAN_lib/generators/volumetric_rendering.py (same ray / camera / integration math as
+# exp/comm/comm_utils.py + exp/pigan/pigan_utils.py restated above, with 3 colour channels).
+# state_dict keys: siren.network.<i>.layer.{weight,bias}, siren.final_layer.*, siren.color_layer_sine.layer.*,
+# siren.color_layer_linear.0.*, siren.mapping_network.network.{0,2,4,6}.*
+# --------------------------------------------------------------------------------------
+PIGAN_KWARGS = dict(fov=12, ray_start=0.88, ray_end=1.12, num_steps=12, h_stddev=0.3, v_stddev=0.155,
+                    h_mean=math.pi * 0.5, v_mean=math.pi * 0.5, hierarchical_sample=True, sample_dist="gaussian",
+                    clamp_mode="relu", last_back=False, white_back=False)        # curriculums.py CelebA, stage 0
+
+
+def pigan_template(z_dim=256, hidden_dim=256, n_layers=8, map_hidden=256):
+    t = OrderedDict()
+    i = 3
+    for l in range(n_layers):
+        t[f"siren.network.{l}.layer.weight"], t[f"siren.network.{l}.layer.bias"] = (hidden_dim, i), (hidden_dim,)
+        i = hidden_dim
+    t["siren.final_layer.weight"], t["siren.final_layer.bias"] = (1, hidden_dim), (1,)
+    t["siren.color_layer_sine.layer.weight"], t["siren.color_layer_sine.layer.bias"] = (hidden_dim, hidden_dim + 3), (hidden_dim,)
+    t["siren.color_layer_linear.0.weight"], t["siren.color_layer_linear.0.bias"] = (3, hidden_dim), (3,)
+    d = z_dim
+    for j, idx in enumerate((0, 2, 4, 6)):
+        o = map_hidden if j < 3 else (n_layers + 1) * hidden_dim * 2
+        t[f"siren.mapping_network.network.{idx}.weight"], t[f"siren.mapping_network.network.{idx}.bias"] = (o, d), (o,)
+        d = map_hidden
+    return t
+
+
+def pigan_mapping(sd, z):
+    """CustomMappingNetwork.forward (siren.py:69-73): -> frequencies, phase_shifts (B, 9*256) each (raw, before *15+30)"""
+    x = z
+    for j, idx in enumerate((0, 2, 4, 6)):
+        x = F.linear(x, sd[f"siren.mapping_network.network.{idx}.weight"], sd[f"siren.mapping_network.network.{idx}.bias"])
+        if j < 3:
+            x = F.leaky_relu(x, 0.2)
+    h = x.shape[-1] // 2
+    return x[..., :h], x[..., h:]
+
+
+def pigan_siren(sd, points, ray_directions, frequencies, phase_shifts, gridwarp=True):
+    """SPATIALSIRENBASELINE / TALLSIREN .forward_with_frequencies_phase_shifts (siren.py:133-152, 196-215):
+    points, ray_directions (B,P,3), raw frequencies / phase shifts (B, 9*H) -> (B,P,4) = [sigmoid rgb(3), sigma]"""
+    H = sd["siren.final_layer.weight"].shape[1]
+    n_layers = sum(1 for k in sd if k.startswith("siren.network.") and k.endswith(".layer.weight"))
+    freq = frequencies * 15 + 30
+    x = points * (2 / 0.24) if gridwarp else points
+
+    def film(prefix, x, f, ph):
+        y = F.linear(x, sd[f"{prefix}.layer.weight"], sd[f"{prefix}.layer.bias"])
+        return torch.sin(f.unsqueeze(1) * y + ph.unsqueeze(1))
+    for i in range(n_layers):
+        x = film(f"siren.network.{i}", x, freq[..., i * H:(i + 1) * H], phase_shifts[..., i * H:(i + 1) * H])
+    sigma = F.linear(x, sd["siren.final_layer.weight"], sd["siren.final_layer.bias"])
+    rgb = film("siren.color_layer_sine", torch.cat([ray_directions, x], -1), freq[..., -H:], phase_shifts[..., -H:])
+    rgb = torch.sigmoid(F.linear(rgb, sd["siren.color_layer_linear.0.weight"], sd["siren.color_layer_linear.0.bias"]))
+    return torch.cat([rgb, sigma], -1)
+
+
+def pigan_forward(sd, z, draws, *, img_size, fov, ray_start, ray_end, num_steps, h_stddev, v_stddev,
+                  h_mean=math.pi * 0.5, v_mean=math.pi * 0.5, hierarchical_sample=True, sample_dist="gaussian",
+                  lock_view_dependence=False, clamp_mode="relu", nerf_noise=0.0, white_back=False, last_back=False,
+                  gridwarp=True, freq_phase=None, return_all=False, **_):
+    """ImplicitGenerator3d.forward (generators.py:26-96); freq_phase=(frequencies, phase_shifts) overrides the mapping
+    network (staged_forward's truncation, generators.py:121-126).  -> pixels (B,3,R,R) in [-1,1], pitch_yaw (B,2)"""
+    assert sample_dist in ("gaussian", "normal")
+    B, R, S = z.shape[0], img_size, num_steps
+    dt = z.dtype
+    dirs_cam, z_vals = initial_rays(R, fov, ray_start, ray_end, S, dtype=dt)
+    origin, pitch, yaw = camera_origin(draws["yaw_n"].to(dt), draws["pitch_n"].to(dt), h_stddev, v_stddev, h_mean, v_mean)
+    c2w = cam2world(-origin, origin)
+    pts, zc, dirs_w, t = world_points(dirs_cam, z_vals, draws["jitter_u"].to(dt), c2w)   # (B,HW,S,3), (B,HW,S), (B,HW,3), (B,3)
+    origins = t[:, None, :].expand(-1, R * R, -1)
+    dirs_exp = dirs_w[:, :, None, :].expand(-1, -1, S, -1).reshape(B, R * R * S, 3)
+    if lock_view_dependence:
+        dirs_exp = torch.zeros_like(dirs_exp)
+        dirs_exp[..., -1] = -1
+    fr, ph = freq_phase if freq_phase is not None else pigan_mapping(sd, z)
+    coarse = pigan_siren(sd, pts.reshape(B, -1, 3), dirs_exp, fr, ph, gridwarp).reshape(B, R * R, S, 4)
+    noise_c = draws["noise_c"].to(dt) * nerf_noise if (draws.get("noise_c") is not None) else None
+    if hierarchical_sample:
+        fz = fine_z_vals(coarse, zc, noise_c, draws["pdf_u"].to(dt), clamp_mode=clamp_mode, dim_rgb=3)
+        fpts = origins[:, :, None, :] + dirs_w[:, :, None, :] * fz[..., None]
+        fine = pigan_siren(sd, fpts.reshape(B, -1, 3), dirs_exp, fr, ph, gridwarp).reshape(B, R * R, S, 4)
+        all_out = torch.cat([fine, coarse], -2)
+        all_z = torch.cat([fz, zc], -1)
+        all_z, idx = torch.sort(all_z, dim=-1)
+        all_out = torch.gather(all_out, -2, idx[..., None].expand(-1, -1, -1, 4))
+    else:
+        all_out, all_z = coarse, zc
+    noise_f = draws["noise_f"].to(dt) * nerf_noise
+    rgb, depth, w = integrate(all_out, all_z, noise_f, clamp_mode=clamp_mode, last_back=last_back, white_back=white_back,
+                              dim_rgb=3)
+    pixels = rgb.reshape(B, R, R, 3).permute(0, 3, 1, 2).contiguous() * 2 - 1
+    py = torch.cat([pitch, yaw], -1)
+    if return_all:
+        return pixels, py, dict(coarse=coarse, all_z=all_z, rgb=rgb, depth=depth, weights=w)
+    return pixels, py

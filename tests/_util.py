@@ -91,3 +91,33 @@ def build_generator(device, sd=None, frozen=False):
     if sd is not None:
         G.load_state_dict(sd)
     return G
+
+
+# ------------------------------------------------------------------ pi-GAN surface goldens (tools/make_golden_pigan.py)
+PIGAN_CASES = ("spatial_r8", "spatial_r8_noise_backs", "tall_r6_lockview", "spatial_r6_nohier_s24", "spatial_r6_staged_psi07")
+
+
+def load_pigan_case(name, dtype=torch.float32):
+    g = np.load(os.path.join(GOLDEN, f"pigan_{name}.npz"))
+    kw = ast.literal_eval(str(g["kwargs_json"]))
+    sd = O.synthetic_state_dict(O.pigan_template(), seed=int(g["seed"]), sigma_bias=float(g["sigma_bias"]), dtype=dtype)
+    z = torch.from_numpy(g["z"]).to(dtype)
+    draws = {k[5:]: torch.from_numpy(g[k]).to(dtype) for k in g.files if k.startswith("draw_")}
+    draws.setdefault("noise_c", None)
+    draws.setdefault("pdf_u", None)
+    meta = dict(B=int(g["B"]), img_size=int(g["img_size"]), nerf_noise=float(g["nerf_noise"]), siren_cls=str(g["siren_cls"]),
+                staged_psi=float(g["staged_psi"]))
+    if meta["staged_psi"] >= 0:
+        meta["avg"] = (torch.from_numpy(g["avg_frequencies"]).to(dtype), torch.from_numpy(g["avg_phase_shifts"]).to(dtype))
+    ref = {k: torch.from_numpy(g[k]) for k in ("img", "pitch_yaw", "coarse", "all_z", "rgb", "depth")}
+    return sd, z, draws, kw, meta, ref
+
+
+def pigan_freq_phase(sd, z, meta):
+    """mapping network output, truncated towards the stored averages for the staged_forward case (generators.py:121-126)"""
+    fr, ph = O.pigan_mapping(sd, z)
+    if meta["staged_psi"] >= 0:
+        af, ap = meta["avg"]
+        psi = meta["staged_psi"]
+        fr, ph = af + psi * (fr - af), ap + psi * (ph - ap)
+    return fr, ph
