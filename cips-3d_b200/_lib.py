@@ -16,7 +16,8 @@ EXPORTS = ("c3d_version", "c3d_last_error", "c3d_device_supported", "c3d_launch_
            "c3d_ray_siren_workspace_bytes",
            "c3d_ray_siren_fwd", "c3d_cips_workspace_bytes", "c3d_cips_fwd", "c3d_bias_act",
            "c3d_upfirdn2d", "c3d_selftest_umma", "c3d_selftest_umma_pair", "c3d_debug_cips_tile_order",
-           "c3d_optim_workspace_bytes", "c3d_grad_norm", "c3d_adam_ema_step", "c3d_ema_update")
+           "c3d_optim_workspace_bytes", "c3d_grad_norm", "c3d_adam_ema_step", "c3d_ema_update",
+           "c3d_pigan_workspace_bytes", "c3d_pigan_render_fwd")
 
 _fp = C.c_void_p  # device pointers travel as integers
 
@@ -37,6 +38,15 @@ class SirenWeights(C.Structure):
 class RayIO(C.Structure):
     _fields_ = [(n, _fp) for n in ("cam2world", "ray_idx", "jitter_u", "noise_c", "pdf_u", "noise_f",
                                    "pixels_fea", "depth", "weights", "dbg_coarse", "dbg_fine", "dbg_all_z")]
+
+
+PIGAN_MAX_LAYERS = 8
+
+
+class PiganWeights(C.Structure):
+    _fields_ = [("w", _fp * PIGAN_MAX_LAYERS), ("b", _fp * PIGAN_MAX_LAYERS), ("freq", _fp * (PIGAN_MAX_LAYERS + 1)),
+                ("phase", _fp * (PIGAN_MAX_LAYERS + 1)), ("w_sigma", _fp), ("b_sigma", _fp), ("wc", _fp), ("bc", _fp),
+                ("wl", _fp), ("bl", _fp), ("n_layers", C.c_int32), ("hidden", C.c_int32), ("gridwarp", C.c_int32)]
 
 
 class CipsParams(C.Structure):
@@ -94,6 +104,10 @@ def bind(lib):
     lib.c3d_upfirdn2d.argtypes = [_fp, _fp, _fp] + [C.c_int32] * 13 + [_fp]
     lib.c3d_selftest_umma.argtypes = [_fp, _fp, _fp, C.c_int32, C.c_int32, C.c_int32, _fp]
     lib.c3d_selftest_umma_pair.argtypes = [_fp, _fp, _fp, C.c_int32, C.c_int32, _fp]
+    lib.c3d_pigan_workspace_bytes.restype = C.c_size_t
+    lib.c3d_pigan_workspace_bytes.argtypes = [C.POINTER(RayParams)]
+    lib.c3d_pigan_render_fwd.argtypes = [C.POINTER(RayParams), C.POINTER(PiganWeights), C.POINTER(RayIO), C.c_int32, _fp,
+                                         C.c_size_t, _fp]
     if hasattr(lib, 'c3d_debug_cips_trace'):      # only in -DC3D_TRACE debug builds
         lib.c3d_debug_cips_trace.argtypes = [C.c_void_p, C.c_int]
     return lib

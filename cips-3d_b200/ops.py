@@ -9,7 +9,7 @@ import torch
 from torch.autograd import Function
 
 from . import _lib
-from ._lib import CipsParams, CipsWeights, RayIO, RayParams, SirenWeights, check, load, ptr, stream_ptr
+from ._lib import CipsParams, CipsWeights, PiganWeights, RayIO, RayParams, SirenWeights, check, load, ptr, stream_ptr
 
 CLAMP_MODES = {"relu": 0, "softplus": 1}
 # bench.py sets this to a dict to collect CUDA-event pairs around the two hot entry points
@@ -297,3 +297,80 @@ def selftest_umma_pair(a, b):
     d = torch.empty((256, b.shape[0]), device=a.device, dtype=torch.float32)
     check(lib.c3d_selftest_umma_pair(ptr(a), ptr(b), ptr(d), b.shape[0], a.shape[1], stream_ptr()), "c3d_selftest_umma_pair")
     return d
+
+
+# --------------------------------------------------------------------------------------
+# pi-GAN renderer (piGAN_lib ImplicitGenerator3d + TALLSIREN / SPATIALSIRENBASELINE)
+# --------------------------------------------------------------------------------------
+def pigan_render(siren, cam2world, jitter_u, pdf_u=None, noise_c=None, noise_f=None, *, img_size, fov, ray_start, ray_end,
+                 num_steps, hierarchical_sample=True, clamp_mode="relu", noise_std=0.0, white_back=False, last_back=False,
+                 lock_view=False, ray_idx=None, ray_offset=0, n_rays=None, debug=False, want_depth=False, want_weights=False):
+    """rays -> 8-layer FiLM-SIREN (hidden 256, view-dependent colour) -> resample -> composite (c3d_pigan_render_fwd).
+    siren: dict from pigan._Siren.kernel_weights (w, b: lists per layer; freq, phase: lists of (B,hidden) incl. the colour
+    layer; w_sigma, b_sigma, wc, bc, wl, bl; hidden; gridwarp).  Returns dict(rgb (B,N,3) in [0,1][, depth, weights, coarse,
+    fine, all_z])."""
+    lib = load()
+    if clamp_mode not in CLAMP_MODES:
+        raise AssertionError("Need to choose clamp mode")
+    B = cam2world.shape[0]
+    S = int(num_steps)
+    HW = img_size * img_size
+    if ray_idx is not None:
+        ray_idx = ray_idx.to(torch.int32).contiguous()
+        N = ray_idx.numel()
+    else:
+        N = HW - ray_offset if n_rays is None else int(n_rays)
+    nS = 2 * S if hierarchical_sample else S
+    dev = cam2world.device
+    H, L = int(siren["hidden"]), len(siren["w"])
+    p = RayParams(batch=B, img_size=img_size, num_steps=S, n_rays=N, ray_offset=int(ray_offset),
+                  hierarchical=int(bool(hierarchical_sample)), clamp_mode=CLAMP_MODES[clamp_mode],
+                  white_back=int(bool(white_back)), last_back=int(bool(last_back)), impl=_lib.IMPL_SIMT,
+                  z_cam=z_cam_from_fov(fov), ray_start=float(ray_start), ray_end=float(ray_end), noise_std=float(noise_std))
+    keep = []
+
+    def dp(t, name, shape=None):
+        t = _f32c(t, name)
+        if t is not None:
+            if shape is not None and tuple(t.shape) != tuple(shape):
+                raise _lib.C3dError(f"{name}: expected shape {tuple(shape)}, got {tuple(t.shape)}")
+            keep.append(t)
+        return ptr(t)
+
+    w = PiganWeights(n_layers=L, hidden=H, gridwarp=int(bool(siren["gridwarp"])))
+    for l in range(L):
+        w.w[l] = dp(siren["w"][l], f"w[{l}]", (H, 3 if l == 0 else H))
+        w.b[l] = dp(siren["b"][l], f"b[{l}]", (H,))
+    for l in range(L + 1):
+        w.freq[l] = dp(siren["freq"][l], f"freq[{l}]", (B, H))
+        w.phase[l] = dp(siren["phase"][l], f"phase[{l}]", (B, H))
+    w.w_sigma, w.b_sigma = dp(siren["w_sigma"], "w_sigma", (1, H)), dp(siren["b_sigma"], "b_sigma", (1,))
+    w.wc, w.bc = dp(siren["wc"], "wc", (H, H + 3)), dp(siren["bc"], "bc", (H,))
+    w.wl, w.bl = dp(siren["wl"], "wl", (3, H)), dp(siren["bl"], "bl", (3,))
+    out = {"rgb": torch.empty((B, N, 3), device=dev, dtype=torch.float32)}
+    if want_depth or debug:
+        out["depth"] = torch.empty((B, N), device=dev, dtype=torch.float32)
+    if want_weights or debug:
+        out["weights"] = torch.empty((B, N, nS), device=dev, dtype=torch.float32)
+    if debug:
+        out["coarse"] = torch.empty((B, N, S, 4), device=dev, dtype=torch.float32)
+        out["all_z"] = torch.empty((B, N, nS), device=dev, dtype=torch.float32)
+        if hierarchical_sample:
+            out["fine"] = torch.empty((B, N, S, 4), device=dev, dtype=torch.float32)
+    if ray_idx is not None:
+        keep.append(ray_idx)
+    io = RayIO(
+        cam2world=dp(cam2world, "cam2world", (B, 4, 4)), ray_idx=ptr(ray_idx) if ray_idx is not None else None,
+        jitter_u=dp(jitter_u, "jitter_u", (B, HW, S)),
+        noise_c=dp(noise_c, "noise_c", (B, N, S)) if (noise_c is not None and noise_std != 0) else None,
+        pdf_u=dp(pdf_u, "pdf_u", (B * N, S)) if hierarchical_sample else None,
+        noise_f=dp(noise_f, "noise_f", (B, N, nS)) if (noise_f is not None and noise_std != 0) else None,
+        pixels_fea=ptr(out["rgb"]), depth=ptr(out.get("depth")), weights=ptr(out.get("weights")),
+        dbg_coarse=ptr(out.get("coarse")), dbg_fine=ptr(out.get("fine")), dbg_all_z=ptr(out.get("all_z")))
+    wsb = lib.c3d_pigan_workspace_bytes(C.byref(p))
+    ws = torch.empty((max(wsb, 4) + 3) // 4, device=dev, dtype=torch.float32)
+    ev = _prof_begin("pigan")
+    check(lib.c3d_pigan_render_fwd(C.byref(p), C.byref(w), C.byref(io), int(bool(lock_view)), ptr(ws), wsb, stream_ptr()),
+          "c3d_pigan_render_fwd")
+    _prof_end("pigan", ev)
+    return out

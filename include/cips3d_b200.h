@@ -160,6 +160,34 @@ int c3d_upfirdn2d(const float* x, const float* kernel, float* y, int32_t planes,
                   int32_t pad_y1, void* stream);
 
 /* ------------------------------------------------------------------------------------
+ * pi-GAN renderer: rays -> FiLM-SIREN (hidden 256 x 8, view-dependent colour) ->
+ * hierarchical resampling -> compositing of (rgb, sigma).  Replaces
+ *   piGAN_lib/generators/generators.py:26-96 ImplicitGenerator3d.forward, :110-204 staged_forward,
+ *   piGAN_lib/siren/siren.py:133-152 TALLSIREN / :196-215 SPATIALSIRENBASELINE .forward_with_frequencies_phase_shifts,
+ *   piGAN_lib/generators/volumetric_rendering.py (rays, perturbation, camera transform, sample_pdf, fancy_integration).
+ * Uses C3dRayParams / C3dRayIO with 4-channel samples: io->pixels_fea is (B,N,3) = integrated rgb in [0,1] (the caller
+ * applies *2-1), dbg_coarse / dbg_fine are (B,N,S,4) = [rgb(3), sigma].  Random draws come from the caller as above.
+ * ---------------------------------------------------------------------------------- */
+#define C3D_PIGAN_MAX_LAYERS 8
+typedef struct C3dPiganWeights {
+  const float* w[C3D_PIGAN_MAX_LAYERS];        /* network.<i>.layer.weight (hidden, in_i), in_0 = 3         */
+  const float* b[C3D_PIGAN_MAX_LAYERS];        /* network.<i>.layer.bias (hidden)                           */
+  const float* freq[C3D_PIGAN_MAX_LAYERS + 1];  /* (B,hidden) per FiLM layer: frequencies*15+30 (siren.py:134, 197); slot n_layers = colour layer */
+  const float* phase[C3D_PIGAN_MAX_LAYERS + 1]; /* (B,hidden) phase shifts                                   */
+  const float* w_sigma; const float* b_sigma;  /* final_layer (1,hidden) (1)                                */
+  const float* wc; const float* bc;            /* color_layer_sine.layer (hidden, hidden+3) (hidden): input = [ray direction, h] */
+  const float* wl; const float* bl;            /* color_layer_linear.0 (3,hidden) (3); sigmoid applied here */
+  int32_t n_layers;                            /* 8                                                         */
+  int32_t hidden;                              /* 256                                                       */
+  int32_t gridwarp;                            /* 1: SPATIALSIRENBASELINE's UniformBoxWarp(0.24), 0: TALLSIREN */
+} C3dPiganWeights;
+
+size_t c3d_pigan_workspace_bytes(const C3dRayParams* p);
+/* lock_view: ray directions fed to the colour layer are (0,0,-1) (generators.py:43-45) */
+int c3d_pigan_render_fwd(const C3dRayParams* p, const C3dPiganWeights* w, const C3dRayIO* io, int32_t lock_view,
+                         void* workspace, size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------
  * Optimiser tail of the training step, multi-tensor, HBM-bound.
  * Replaces, per optimiser (exp/cips3d/scripts/train.py:417-438 for D, :468-491 for G):
  *   torch.nn.utils.clip_grad_norm_(params, grad_clip)         -> c3d_grad_norm
