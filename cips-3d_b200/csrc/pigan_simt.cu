@@ -226,10 +226,22 @@ static long long pg_chunk_images(const C3dRayParams* p) {
   return nb;
 }
 
+// tcgen05 form (pigan_tc.cu): C3D_PIGAN_IMPL=tc, emulation-verified, opt-in until it has run on hardware
+size_t c3d_pigan_tc_workspace_bytes(const C3dRayParams* p);
+bool c3d_pigan_tc_supported(const C3dRayParams* p, const C3dPiganWeights* w);
+int c3d_pigan_render_fwd_tc(const C3dRayParams* p, const C3dPiganWeights* w, const C3dRayIO* io, int lock_view, void* workspace,
+                            size_t workspace_bytes, cudaStream_t st);
+static bool pg_want_tc() {
+  const char* e = getenv("C3D_PIGAN_IMPL");
+  return e && (e[0] == 't' || e[0] == 'T');
+}
+
 extern "C" size_t c3d_pigan_workspace_bytes(const C3dRayParams* p) {
   if (!p) return 0;
   const long long P = pg_chunk_images(p) * p->n_rays * p->num_steps;
-  return (size_t)P * (1 + 1 + 2 * kLd + 4 + 4) * sizeof(float);      // z, fine z, two activation buffers, coarse4, fine4
+  const size_t simt = (size_t)P * (1 + 1 + 2 * kLd + 4 + 4) * sizeof(float);      // z, fine z, two activation buffers, coarse4, fine4
+  const size_t tc = c3d_pigan_tc_workspace_bytes(p);
+  return simt > tc ? simt : tc;
 }
 
 // evaluate the field on the P points whose [dir | h0] rows are in actA; result rows (rgb, sigma) -> out4
@@ -281,6 +293,7 @@ extern "C" int c3d_pigan_render_fwd(const C3dRayParams* p, const C3dPiganWeights
     return C3D_EWORKSPACE;
   }
   cudaStream_t st = (cudaStream_t)stream;
+  if (pg_want_tc() && c3d_pigan_tc_supported(p, w)) return c3d_pigan_render_fwd_tc(p, w, io, lock_view, workspace, workspace_bytes, st);
   const int S = p->num_steps, N = p->n_rays;
   const long long cb = pg_chunk_images(p), Pmax = cb * N * S;
   float* zbuf = (float*)workspace;

@@ -249,13 +249,17 @@ def test_emu_blur_tma_streaming_kernel(shape, pad, mode, monkeypatch):
         assert y.shape == ref.shape and (y - ref).abs().max().item() < 1e-5
 
 
+@pytest.mark.parametrize("impl,mode", [("simt", "eager"), ("tc", "lazy"), ("tc", "random")])
 @pytest.mark.parametrize("name", PIGAN_CASES)
-def test_emu_pigan_renderer_matches_reference_golden(name):
+def test_emu_pigan_renderer_matches_reference_golden(name, impl, mode, monkeypatch):
     """c3d_pigan_render_fwd (rays -> 8 x 256 FiLM-SIREN with view-dependent colour -> resampling -> rgb compositing) against
     the REAL piGAN_lib ImplicitGenerator3d + SPATIALSIRENBASELINE / TALLSIREN: forward, noise + softplus + backs,
     lock_view_dependence, non-hierarchical S = 24, staged_forward's truncated frequencies."""
+    # impl "tc": pigan_tc.cu -- one fused tcgen05 kernel (streamed 256x256 hi/lo weight tiles, A operand in TMEM, 3-pass
+    # split precision, heads and the view-direction columns in the epilogues, warp-per-ray math); "simt": pigan_simt.cu
+    monkeypatch.setenv("C3D_PIGAN_IMPL", impl)
     sd, z, draws, kw, meta, ref = load_pigan_case(name)
-    with emulated(async_mode=0) as pkg:
+    with emulated(async_mode=MODES[mode], seed=9) as pkg:
         cls = pkg.pigan.SPATIALSIRENBASELINE if meta["siren_cls"] == "SPATIALSIRENBASELINE" else pkg.pigan.TALLSIREN
         G = pkg.pigan.ImplicitGenerator3d(cls, z_dim=256)
         G.load_state_dict(sd)

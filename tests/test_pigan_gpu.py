@@ -1,6 +1,8 @@
 """GPU parity of the pi-GAN surface (cips3d_b200.pigan on c3d_pigan_render_fwd) against the goldens of the REAL piGAN_lib
 classes, through the public class surface with the random draws replayed in the reference's order.  File order: runs after
 the CIPS-3D parity suites."""
+import os
+
 import pytest
 import torch
 
@@ -74,3 +76,17 @@ def test_pigan_training_graph_backprops_and_matches_native(pkg):
         img2, _ = G(z.to(DEV), img_size=meta["img_size"], nerf_noise=0.0, **kw)      # native kernels
     frac, _ = close_frac(img.detach().permute(0, 2, 3, 1).reshape(-1, 3), img2.permute(0, 2, 3, 1).reshape(-1, 3), 1e-3)
     assert frac >= 0.99
+
+
+@pytest.mark.skipif(os.environ.get("C3D_EXPERIMENTAL", "0") != "1", reason="hardware-unvalidated kernel: set C3D_EXPERIMENTAL=1")
+@pytest.mark.parametrize("name", [c for c in PIGAN_CASES if "staged" not in c])
+def test_pigan_tc_kernel_matches_reference_golden(pkg, name, monkeypatch):
+    """C3D_PIGAN_IMPL=tc: the fused tcgen05 pi-GAN renderer (pigan_tc.cu) through the class surface."""
+    monkeypatch.setenv("C3D_PIGAN_IMPL", "tc")
+    sd, z, draws, kw, meta, ref = load_pigan_case(name)
+    G = _build(pkg, sd, meta)
+    with torch.no_grad(), replay_draws(_draw_seq(draws, kw["hierarchical_sample"]), DEV):
+        img, py = G(z.to(DEV), img_size=meta["img_size"], nerf_noise=meta["nerf_noise"], **kw)
+    torch.cuda.synchronize()
+    frac, worst = close_frac(img.permute(0, 2, 3, 1).reshape(-1, 3), ref["img"].permute(0, 2, 3, 1).reshape(-1, 3), 1e-3)
+    assert frac >= 0.99, f"only {frac:.4f} of pixels within 1e-3 (worst {worst:.3e})"

@@ -23,9 +23,11 @@ C3D_RAY_MATH=warp timeout 300 python tools/time_forward.py 16 > $O/r02a_time_for
 # HBM-bound ops
 timeout 300 python tools/bench_disc_ops.py > $O/r02a_disc_ops_default.jsonl 2>&1
 C3D_BLUR_TMA=1 timeout 300 python tools/bench_disc_ops.py > $O/r02a_disc_ops_blur_tma.jsonl 2>&1; echo "blur_tma bench: exit $?" | tee -a $O/r02a_summary.txt
+C3D_EXPERIMENTAL=1 timeout 300 python -m pytest tests/test_pigan_gpu.py -q > $O/r02a_pytest_pigan.log 2>&1; echo "pigan (simt + tc): exit $?" | tee -a $O/r02a_summary.txt
+timeout 300 python tools/time_pigan.py 64 4 > $O/r02a_time_pigan.jsonl 2>&1; echo "pigan timing: exit $?" | tee -a $O/r02a_summary.txt
 timeout 300 python tools/bench_optim.py > $O/r02a_optim.jsonl 2>&1; echo "optim bench: exit $?" | tee -a $O/r02a_summary.txt
 python bench.py --steps 20 --warmup 5 > $O/r02a_bench.json 2> $O/r02a_bench.err
 tail -n 3 $O/r02a_time_kernels_default.log $O/r02a_time_kernels_pair.log $O/r02a_time_forward_default.log $O/r02a_time_forward_pair.log $O/r02a_time_forward_raywarp.log
 grep -h "blur" $O/r02a_disc_ops_default.jsonl $O/r02a_disc_ops_blur_tma.jsonl | cut -c1-200
-cat $O/r02a_optim.jsonl | cut -c1-300
+cat $O/r02a_optim.jsonl $O/r02a_time_pigan.jsonl | cut -c1-300
 cat $O/r02a_summary.txt
