@@ -261,7 +261,10 @@ def main():
                                f"{B} images/GPU/step, 12 coarse + 12 fine samples/ray, nerf_noise 0",
                    "resolution": res, "batch_per_gpu": B, "global_batch": B * world, "samples_per_ray": 24,
                    "kernel_impl": args.kernel_impl, "parallelism": f"dp{world} (no data-path collective)",
-                   "l2": "per-step inputs (random draws ~%.0f MB) exceed the 126 MB L2" % (B * res * res * 48 * 4 / 1e6)},
+                   "l2": "per-step inputs (random draws ~%.0f MB) exceed the 126 MB L2" % (B * res * res * 48 * 4 / 1e6),
+                   # opt-in kernel variants in effect for this run (all unset = the round-1 measured kernels)
+                   "variants": {k: os.environ[k] for k in ("C3D_CIPS_PAIR", "C3D_CIPS_CLUSTER", "C3D_RAY_MATH", "C3D_BLUR_TMA")
+                                if os.environ.get(k)}},
         "e2e": {"value": e2e, "unit": "images/s", "h2d_bytes_per_step": int(B * (256 + 512) * 4),
                 "d2h_bytes_per_step": int(B * 3 * res * res * 4), "ms_per_step": ms_e2e / args.steps},
         "gpu_launches": int(launches),

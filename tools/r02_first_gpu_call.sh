@@ -27,6 +27,8 @@ C3D_EXPERIMENTAL=1 timeout 300 python -m pytest tests/test_pigan_gpu.py -q > $O/
 timeout 300 python tools/time_pigan.py 64 4 > $O/r02a_time_pigan.jsonl 2>&1; echo "pigan timing: exit $?" | tee -a $O/r02a_summary.txt
 timeout 300 python tools/bench_optim.py > $O/r02a_optim.jsonl 2>&1; echo "optim bench: exit $?" | tee -a $O/r02a_summary.txt
 python bench.py --steps 20 --warmup 5 > $O/r02a_bench.json 2> $O/r02a_bench.err
+# the same contract line with the variants that passed above (only meaningful if their tests exited 0)
+C3D_CIPS_PAIR=1 C3D_RAY_MATH=warp timeout 600 python bench.py --steps 20 --warmup 5 --no-cpu-baseline --no-eager > $O/r02a_bench_variants.json 2> $O/r02a_bench_variants.err
 tail -n 3 $O/r02a_time_kernels_default.log $O/r02a_time_kernels_pair.log $O/r02a_time_forward_default.log $O/r02a_time_forward_pair.log $O/r02a_time_forward_raywarp.log
 grep -h "blur" $O/r02a_disc_ops_default.jsonl $O/r02a_disc_ops_blur_tma.jsonl | cut -c1-200
 cat $O/r02a_optim.jsonl $O/r02a_time_pigan.jsonl | cut -c1-300
