@@ -327,6 +327,17 @@ __device__ __forceinline__ void umma_ss_w_cg2(uint32_t d_tmem, uint32_t a_lo, ui
       ::"r"(d_tmem), "r"(a_lo), "r"(b_lo), "r"(desc_hi), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// A operand from tensor memory (each CTA of the pair reads ITS OWN TMEM columns a_tmem), B from shared memory as above
+__device__ __forceinline__ void umma_ts_w_cg2(uint32_t d_tmem, uint32_t a_tmem, uint32_t b_lo, uint32_t desc_hi, uint32_t idesc,
+                                              uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 db;\n\t"
+      "setp.ne.b32 p, %5, 0;\n\t"
+      "mov.b64 db, {%2, %3};\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], [%1], db, %4, p;\n\t}"
+      ::"r"(d_tmem), "r"(a_tmem), "r"(b_lo), "r"(desc_hi), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
 // completion of this thread's earlier cta_group::2 MMAs -> arrive on the barrier at this offset in every CTA of `mask`
 __device__ __forceinline__ void tc_commit_cg2_mc(uint64_t* bar, uint16_t mask) {
   asm volatile(

@@ -10,7 +10,11 @@
 //     memory: they stream as 32 KB tiles (N 256 x K 64) through a 4-stage ring filled by bulk async copies, hi and lo tile
 //     of each K chunk in turn; every layer is the split-precision sum A_hi*B_hi + A_lo*B_hi + A_hi*B_lo (as in
 //     ray_siren_tc.cu: FiLM gains ~30 amplify the pre-activation error of a single fp16 pass beyond the 1e-3 bar);
-//   * layer 0 (3 -> 256) is a K = 16 MMA on [x, y, z, 1] against per-image folded weights (gain, box warp, bias, phase);
+//   * layer 0 (3 -> 256) is three FMAs per unit in the epilogue threads against per-image folded constants (gain, box
+//     warp, bias, phase) -- no MMA phase, and every B operand is image independent (needed for the CTA-pair form);
+//   * PAIR (C3D_PIGAN_PAIR=1): the two CTAs of a cluster form a tcgen05 cta_group::2 pair -- M = 256 = two ray groups,
+//     each CTA streams half of every weight tile (N rows 128 r .. +127), the leader issues, the protocol is the CIPS pair
+//     kernel's (relayed fills, workers of both CTAs report to the leader's a_ready, multicast commits);
 //   * the sigma head and the colour linear (256 -> 3) are dot products in the epilogues of layer 7 / the colour layer
 //     (partial sums per 64-column thread, reduced through shared memory), the ray direction's 3 input columns of the colour
 //     layer are added there too (no K = 259 MMA);
@@ -29,22 +33,29 @@ constexpr int kRows = 128, kH = 256, kLayers = 8;          // hidden width, FiLM
 constexpr int kKC = 64;                                    // K per streamed weight tile
 constexpr int kTileBytes = kH * kKC * 2;                   // 32 KB: B tile (N = 256) x (K = 64) fp16
 constexpr int kStages = 4;
+constexpr int kRingBytes = kStages * kTileBytes;
+template <bool PAIR> struct Ring {                         // PAIR: each CTA holds N/2 = 128 rows of every tile
+  static constexpr int kStageBytes = PAIR ? kTileBytes / 2 : kTileBytes;
+  static constexpr int kNS = PAIR ? 2 * kStages : kStages;
+  static constexpr int kLBO_B = PAIR ? (kH / 2) * 16 : kH * 16;
+};
 constexpr int kTilesPerLayer = 2 * (kH / kKC);             // (hi, lo) x 4 K chunks
 constexpr int kStreamLayers = kLayers;                     // layers 1..7 and the colour layer
 constexpr int kLBO = kH * 16;                              // K-direction core-matrix stride of a 256-row operand
-constexpr int kW0Bytes = kH * 16 * 2;                      // layer-0 B operand (N = 256, K = 16) per hi / lo
 constexpr float kWScale = 256.f, kWInv = 1.f / 256.f;
 constexpr int kThreads = 640, kWorkers = 512;
 
 struct ImgConsts {                    // per image, written by the prep kernel
-  uint8_t w0[2 * kW0Bytes];           // [f0*s*W0[j][0..2], f0*b0[j] + ph0[j], 0..] fp16 hi then lo, UMMA K-major layout
+  float4 w0f[kH];                     // layer 0 folded: (f0*s*W0[j][0..2], f0*b0[j] + ph0[j])
   float2 film[kLayers][kH];           // layers 1..7 and colour (index 7): (f / 256, f * b + ph)
   float4 wdir[kH];                    // f_colour * Wc[:, 0:3]  (the ray direction's input columns)
 };
 
-struct Smem {
-  alignas(1024) uint8_t ring[kStages][kTileBytes];
-  alignas(128) uint8_t w0[2 * kW0Bytes];
+template <bool PAIR>
+struct SmemT {
+  static constexpr int NS = Ring<PAIR>::kNS;
+  alignas(1024) uint8_t ring[kRingBytes];
+  alignas(128) float4 w0f[kH];
   float2 film[kLayers][kH];
   float4 wdir[kH];
   float4 wl4[kH];                     // (Wl[0][k], Wl[1][k], Wl[2][k], Wsigma[k])
@@ -54,8 +65,9 @@ struct Smem {
   float4 part_rgb[4][kRows];
   float skey[2 * kRows];
   int sidx[2 * kRows];
-  alignas(8) uint64_t full[kStages];
-  uint64_t empty[kStages];
+  alignas(8) uint64_t full[NS];
+  uint64_t empty[NS];
+  uint64_t peer_full[NS];             // PAIR, leader only: the peer's half of stage s has landed
   uint64_t a_ready, d_ready;
   uint32_t tmem_base;
 };
@@ -85,10 +97,16 @@ __device__ __forceinline__ float sample_alpha(float delta, float sigma, float no
   return __fsub_rn(1.f, expf(__fmul_rn(-delta, act)));
 }
 
+template <bool PAIR>
 __global__ void __launch_bounds__(kThreads, 1) pigan_tc_kernel(const KArgs a) {
+  using Smem = SmemT<PAIR>;
+  using RC = Ring<PAIR>;
+  constexpr int NS = RC::kNS;
   C3D_DYN_SMEM(uint8_t, smem_raw);
   Smem& s = *reinterpret_cast<Smem*>(smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u));
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t crank = PAIR ? cluster_ctarank() : 0;
+  const bool leader = !PAIR || crank == 0;
   const C3dRayParams& p = a.p;
   const int S = p.num_steps, G = a.G;
   const bool hier = p.hierarchical != 0;
@@ -96,20 +114,31 @@ __global__ void __launch_bounds__(kThreads, 1) pigan_tc_kernel(const KArgs a) {
   const int passes = hier ? 2 : 1;
 
   if (threadIdx.x == 0) {
-    for (int i = 0; i < kStages; ++i) {
+    for (int i = 0; i < NS; ++i) {
       mbar_init(&s.full[i], 1);
       mbar_init(&s.empty[i], 1);
+      mbar_init(&s.peer_full[i], 1);
     }
-    mbar_init(&s.a_ready, kWorkers / 32);
+    mbar_init(&s.a_ready, PAIR ? 2 * (kWorkers / 32) : kWorkers / 32);     // PAIR: the leader's barrier collects both CTAs
     mbar_init(&s.d_ready, 1);
     fence_mbar_init();
   }
-  if (warp == 2) tmem_alloc<512>(&s.tmem_base);
+  if (warp == 2) {
+    if (PAIR) tmem_alloc_cg2<512>(&s.tmem_base);
+    else tmem_alloc<512>(&s.tmem_base);
+  }
   tc_fence_before();
   __syncthreads();
+  if (PAIR) cluster_sync_all();
   tc_fence_after();
   const uint32_t tmem = s.tmem_base;
-  const int iters = (a.total_groups + (int)gridDim.x - 1) / (int)gridDim.x;
+  // group walked in iteration `it`: PAIR -> the cluster takes two consecutive groups
+  const int grid_units = PAIR ? (int)gridDim.x / 2 : (int)gridDim.x;
+  const int total_units = PAIR ? (a.total_groups + 1) / 2 : a.total_groups;
+  const int iters = (total_units + grid_units - 1) / grid_units;
+  auto group_of = [&](int it) {
+    return PAIR ? (it * grid_units + (int)blockIdx.x / 2) * 2 + (int)crank : it * (int)gridDim.x + (int)blockIdx.x;
+  };
 
   if (warp < 4) {
     reg_dec<56>();
@@ -121,70 +150,85 @@ __global__ void __launch_bounds__(kThreads, 1) pigan_tc_kernel(const KArgs a) {
         for (int pass = 0; pass < passes; ++pass)
           for (int t = 0; t < n_tiles; ++t) {
             mbar_wait(&s.empty[stage], phase ^ 1);
-            if (elect_one()) {
-              mbar_arrive_expect_tx(&s.full[stage], kTileBytes);
-              bulk_g2s(s.ring[stage], a.wtiles + (size_t)t * kTileBytes, kTileBytes, &s.full[stage]);
+            if (elect_one()) {       // PAIR: this CTA's half (N rows 128*rank .. +127) of the tile
+              mbar_arrive_expect_tx(&s.full[stage], RC::kStageBytes);
+              bulk_g2s(s.ring + stage * RC::kStageBytes, a.wtiles + (size_t)t * kTileBytes + crank * RC::kStageBytes, RC::kStageBytes,
+                       &s.full[stage]);
             }
             __syncwarp();
-            if (++stage == kStages) { stage = 0; phase ^= 1; }
+            if (++stage == NS) { stage = 0; phase ^= 1; }
           }
+    } else if (PAIR && !leader) {
+      // ---------------------------------------------------------- peer CTA of a pair: warp 1 relays its fills to the leader
+      if (warp == 1) {
+        uint32_t stage = 0, phase = 0;
+        const int n_tiles = kStreamLayers * kTilesPerLayer;
+        for (int it = 0; it < iters; ++it)
+          for (int pass = 0; pass < passes; ++pass)
+#pragma unroll 1
+            for (int t = 0; t < n_tiles; ++t) {
+              mbar_wait(&s.full[stage], phase);
+              if (elect_one()) mbar_arrive_cluster(&s.peer_full[stage], 0);
+              __syncwarp();
+              if (++stage == NS) { stage = 0; phase ^= 1; }
+            }
+      }
     } else if (warp == 1) {
       // ---------------------------------------------------------- MMA issuer (converged warp, one elected lane issues)
-      const uint32_t idesc = umma_idesc_f16(kRows, kH);
+      const uint32_t idesc = umma_idesc_f16(PAIR ? 2 * kRows : kRows, kH);
       const uint32_t dhi = umma_desc_hi(128);
       const uint32_t a_hi = tmem, a_lo = tmem + 128, d = tmem + 256;
-      const uint32_t ring_lo0 = umma_desc_lo(smem_u32(s.ring[0]), kLBO);
-      constexpr uint32_t kStepK16 = (2 * kLBO) >> 4;      // one K = 16 step = 2 core-matrix columns of the B tile
-      constexpr uint32_t kStepStage = kTileBytes >> 4;
+      const uint32_t ring_lo0 = umma_desc_lo(smem_u32(s.ring), RC::kLBO_B);
+      constexpr uint32_t kStepK16 = (2 * RC::kLBO_B) >> 4;      // one K = 16 step = 2 core-matrix columns of the B tile
+      constexpr uint32_t kStepStage = RC::kStageBytes >> 4;
+      auto mma = [&](uint32_t a_col, uint32_t b_lo, uint32_t acc) {
+        if (PAIR) umma_ts_w_cg2(d, a_col, b_lo, dhi, idesc, acc);
+        else umma_ts_w(d, a_col, b_lo, dhi, idesc, acc);
+      };
+      auto wait_tile = [&](uint32_t stage, uint32_t phase) {
+        mbar_wait(&s.full[stage], phase);
+        if (PAIR) mbar_wait_cluster(&s.peer_full[stage], phase);
+        tc_fence_after();
+      };
+      auto release = [&](uint64_t* bar) {
+        if (PAIR) tc_commit_cg2_mc(bar, 3);
+        else tc_commit(bar);
+      };
       uint32_t stage = 0, phase = 0, apar = 0;
       for (int it = 0; it < iters; ++it)
-        for (int pass = 0; pass < passes; ++pass) {
-          // layer 0: K = 16 against the image's folded weights (in shared memory, not streamed)
-          mbar_wait(&s.a_ready, apar);
-          apar ^= 1;
-          tc_fence_after();
-          if (elect_one()) {
-            const uint32_t b0h = umma_desc_lo(smem_u32(s.w0), kLBO), b0l = b0h + (kW0Bytes >> 4);
-            umma_ts_w(d, a_hi, b0h, dhi, idesc, 0);
-            umma_ts_w(d, a_lo, b0h, dhi, idesc, 1);
-            umma_ts_w(d, a_hi, b0l, dhi, idesc, 1);
-            tc_commit(&s.d_ready);
-          }
-          __syncwarp();
+        for (int pass = 0; pass < passes; ++pass)
           for (int l = 0; l < kStreamLayers; ++l) {
-            mbar_wait(&s.a_ready, apar);
+            if (PAIR) mbar_wait_cluster(&s.a_ready, apar);
+            else mbar_wait(&s.a_ready, apar);
             apar ^= 1;
             tc_fence_after();
 #pragma unroll 1
             for (int kc = 0; kc < kH / kKC; ++kc) {
               // hi tile: A_hi * B_hi + A_lo * B_hi
-              mbar_wait(&s.full[stage], phase);
-              tc_fence_after();
+              wait_tile(stage, phase);
               if (elect_one()) {
                 const uint32_t b = ring_lo0 + stage * kStepStage;
 #pragma unroll
-                for (int k = 0; k < kKC / 16; ++k) umma_ts_w(d, a_hi + (uint32_t)(kc * 4 + k) * 8, b + k * kStepK16, dhi, idesc, (kc | k) != 0);
+                for (int k = 0; k < kKC / 16; ++k) mma(a_hi + (uint32_t)(kc * 4 + k) * 8, b + k * kStepK16, (kc | k) != 0);
 #pragma unroll
-                for (int k = 0; k < kKC / 16; ++k) umma_ts_w(d, a_lo + (uint32_t)(kc * 4 + k) * 8, b + k * kStepK16, dhi, idesc, 1);
-                tc_commit(&s.empty[stage]);
+                for (int k = 0; k < kKC / 16; ++k) mma(a_lo + (uint32_t)(kc * 4 + k) * 8, b + k * kStepK16, 1);
+                release(&s.empty[stage]);
               }
               __syncwarp();
-              if (++stage == kStages) { stage = 0; phase ^= 1; }
+              if (++stage == NS) { stage = 0; phase ^= 1; }
               // lo tile: A_hi * B_lo
-              mbar_wait(&s.full[stage], phase);
-              tc_fence_after();
+              wait_tile(stage, phase);
               if (elect_one()) {
                 const uint32_t b = ring_lo0 + stage * kStepStage;
 #pragma unroll
-                for (int k = 0; k < kKC / 16; ++k) umma_ts_w(d, a_hi + (uint32_t)(kc * 4 + k) * 8, b + k * kStepK16, dhi, idesc, 1);
-                tc_commit(&s.empty[stage]);
-                if (kc == kH / kKC - 1) tc_commit(&s.d_ready);
+                for (int k = 0; k < kKC / 16; ++k) mma(a_hi + (uint32_t)(kc * 4 + k) * 8, b + k * kStepK16, 1);
+                release(&s.empty[stage]);
+                if (kc == kH / kKC - 1) release(&s.d_ready);
               }
               __syncwarp();
-              if (++stage == kStages) { stage = 0; phase ^= 1; }
+              if (++stage == NS) { stage = 0; phase ^= 1; }
             }
           }
-        }
     }
   } else {
     // ------------------------------------------------------------ workers: epilogues + per-ray math
@@ -202,7 +246,10 @@ __global__ void __launch_bounds__(kThreads, 1) pigan_tc_kernel(const KArgs a) {
       tc_wait_st();
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&s.a_ready);
+      if (lane == 0) {
+        if (PAIR) mbar_arrive_cluster(&s.a_ready, 0);
+        else mbar_arrive(&s.a_ready);
+      }
     };
     auto wait_d = [&]() {
       mbar_wait(&s.d_ready, dpar);
@@ -215,7 +262,7 @@ __global__ void __launch_bounds__(kThreads, 1) pigan_tc_kernel(const KArgs a) {
     int cur_img = -1;
 
     for (int it = 0; it < iters; ++it) {
-      const int grp = it * (int)gridDim.x + (int)blockIdx.x;
+      const int grp = group_of(it);
       const bool grp_ok = grp < a.total_groups;
       const int img = grp_ok ? grp / a.groups_per_img : 0;
       const int ray0 = grp_ok ? (grp % a.groups_per_img) * G : 0;
@@ -226,10 +273,9 @@ __global__ void __launch_bounds__(kThreads, 1) pigan_tc_kernel(const KArgs a) {
       const float* M = a.io.cam2world + (size_t)img * 16;
       if (img != cur_img) {      // (CTA-uniform) stage the image's folded constants
         const uint4* src = reinterpret_cast<const uint4*>(&a.consts[img]);
-        uint4* dst = reinterpret_cast<uint4*>(s.w0);     // w0, film, wdir are contiguous in both structs
+        uint4* dst = reinterpret_cast<uint4*>(s.w0f);    // w0f, film, wdir are contiguous in both structs
         for (int i = wtid; i < (int)(sizeof(ImgConsts) / 16); i += kWorkers) dst[i] = __ldg(src + i);
         cur_img = img;
-        fence_proxy_async();     // w0 is read by the tensor core
         wsync();
       }
       RayFrame fr;
@@ -242,7 +288,7 @@ __global__ void __launch_bounds__(kThreads, 1) pigan_tc_kernel(const KArgs a) {
       }
 
       for (int pass = 0; pass < passes; ++pass) {
-        // ---------------- L0: A = [x, y, z, 1, 0...] (K = 16)
+        // ---------------- layer 0 in the epilogue threads: h0 = sin(f0 (W0 (p s) + b0) + ph0), folded per image -> A
         float px = 0.f, py = 0.f, pz = 0.f;
         if (pt_ok) {
           if (pass == 0) {
@@ -254,24 +300,15 @@ __global__ void __launch_bounds__(kThreads, 1) pigan_tc_kernel(const KArgs a) {
             fine_sample(fr, s.z_f[row], px, py, pz);
           }
         }
-        if (cq == 0) {
-          const float v[16] = {px, py, pz, 1.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-          store_a16(a_hi, a_lo, v);
-        }
-        signal_a();
-        // ---------------- E0: sin of the folded layer-0 pre-activation -> A (h0)
-        wait_d();
-        {
-          uint32_t acc[16];
 #pragma unroll 1
-          for (int c = 0; c < 4; ++c) {
-            tmem_ld16(dcol + (uint32_t)(c * 16), acc);
-            tc_wait_ld();
-            float v[16];
+        for (int c = 0; c < 4; ++c) {
+          float v[16];
 #pragma unroll
-            for (int j = 0; j < 16; ++j) v[j] = __sinf(__uint_as_float(acc[j]));
-            store_a16(a_hi + (uint32_t)(cq * 32 + c * 8), a_lo + (uint32_t)(cq * 32 + c * 8), v);
+          for (int j = 0; j < 16; ++j) {
+            const float4 w4 = s.w0f[cq * 64 + c * 16 + j];
+            v[j] = __sinf(fmaf(w4.x, px, fmaf(w4.y, py, fmaf(w4.z, pz, w4.w))));
           }
+          store_a16(a_hi + (uint32_t)(cq * 32 + c * 8), a_lo + (uint32_t)(cq * 32 + c * 8), v);
         }
         signal_a();
         // ---------------- E1..E7: FiLM + sin -> A; E7 also accumulates the sigma head
@@ -460,11 +497,17 @@ __global__ void __launch_bounds__(kThreads, 1) pigan_tc_kernel(const KArgs a) {
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 2) tmem_dealloc<512>(tmem);
+  if (PAIR) cluster_sync_all();
+  if (warp == 2) {
+    if (PAIR) tmem_dealloc_cg2<512>(tmem);
+    else tmem_dealloc<512>(tmem);
+  }
 }
 
 // ---- prep: weights -> scaled fp16 (hi, lo) UMMA-B tiles in stream order; per-image folded constants
-// tile index = (l * 4 + kc) * 2 + (0 hi | 1 lo); element (n, k) of a tile at (n%8)*16 + (n/8)*128 + (k/8)*kLBO + (k%8)*2
+// tile index = (l * 4 + kc) * 2 + (0 hi | 1 lo); element (n, k) of a tile at (n%8)*16 + (n/8)*128 + (k/8)*LBO + (k%8)*2;
+// PAIR: the tile is two 16 KB halves (N rows 0..127 | 128..255), each in the layout of a 128-row operand
+template <bool PAIR>
 __global__ void pigan_prep_weights_kernel(const C3dPiganWeights w, uint8_t* __restrict__ tiles, float4* __restrict__ wl4) {
   const int t = blockIdx.x;                       // (l, kc) pair
   const int l = t / (kH / kKC), kc = t % (kH / kKC);
@@ -477,7 +520,8 @@ __global__ void pigan_prep_weights_kernel(const C3dPiganWeights w, uint8_t* __re
     const int n = i / kKC, k = i % kKC;
     const float v = W[(size_t)n * ldw + k_off + kc * kKC + k] * kWScale;
     const __half h = __float2half_rn(v);
-    const int e = ((n % 8) * 16 + (n / 8) * 128 + (k / 8) * kLBO) / 2 + (k % 8);
+    const int nh = PAIR ? n % (kH / 2) : n;
+    const int e = ((PAIR ? (n / (kH / 2)) * (kTileBytes / 2) : 0) + (nh % 8) * 16 + (nh / 8) * 128 + (k / 8) * Ring<PAIR>::kLBO_B) / 2 + (k % 8);
     hi[e] = h;
     lo[e] = __float2half_rn(v - __half2float(h));
   }
@@ -493,15 +537,8 @@ __global__ void pigan_prep_consts_kernel(const C3dPiganWeights w, int B, ImgCons
   const float sc = w.gridwarp ? 2.f / 0.24f : 1.f;
   for (int j = threadIdx.x; j < kH; j += blockDim.x) {
     const float f0 = w.freq[0][(size_t)b * kH + j];
-    const float c4[4] = {f0 * sc * w.w[0][j * 3], f0 * sc * w.w[0][j * 3 + 1], f0 * sc * w.w[0][j * 3 + 2],
-                         fmaf(f0, w.b[0][j], w.phase[0][(size_t)b * kH + j])};
-    for (int k = 0; k < 16; ++k) {
-      const float v = k < 4 ? c4[k] : 0.f;
-      const __half h = __float2half_rn(v);
-      const int e = ((j % 8) * 16 + (j / 8) * 128 + (k / 8) * kLBO) / 2 + (k % 8);
-      reinterpret_cast<__half*>(ic.w0)[e] = h;
-      reinterpret_cast<__half*>(ic.w0 + kW0Bytes)[e] = __float2half_rn(v - __half2float(h));
-    }
+    ic.w0f[j] = make_float4(f0 * sc * w.w[0][j * 3], f0 * sc * w.w[0][j * 3 + 1], f0 * sc * w.w[0][j * 3 + 2],
+                            fmaf(f0, w.b[0][j], w.phase[0][(size_t)b * kH + j]));
     for (int l = 1; l <= kLayers; ++l) {      // layers 1..7 and the colour layer (slot kLayers)
       const float f = w.freq[l][(size_t)b * kH + j];
       const float bias = l < kLayers ? w.b[l][j] : w.bc[j];
@@ -518,7 +555,8 @@ __global__ void pigan_prep_consts_kernel(const C3dPiganWeights w, int B, ImgCons
 using namespace c3d;
 using namespace c3d::pgt;
 
-static_assert(offsetof(Smem, film) - offsetof(Smem, w0) == offsetof(ImgConsts, film) && offsetof(Smem, wdir) - offsetof(Smem, w0) == offsetof(ImgConsts, wdir),
+static_assert(offsetof(SmemT<false>, film) - offsetof(SmemT<false>, w0f) == offsetof(ImgConsts, film) &&
+                  offsetof(SmemT<false>, wdir) - offsetof(SmemT<false>, w0f) == offsetof(ImgConsts, wdir),
               "the staged image constants are copied as one block");
 
 struct PgWs {
@@ -555,7 +593,12 @@ int c3d_pigan_render_fwd_tc(const C3dRayParams* p, const C3dPiganWeights* w, con
     return C3D_EARCH;
   }
   uint8_t* base = (uint8_t*)workspace;
-  C3D_LAUNCH(pigan_prep_weights_kernel, kStreamLayers * (kH / kKC), 256, 0, st, *w, base + ws.tiles, (float4*)(base + ws.wl4));
+  const int sms = c3d_device_sm_count(dev);
+  // C3D_PIGAN_PAIR=1: tcgen05 CTA pairs (two ray groups per weight stream).  Opt-in until timed on hardware.
+  bool pair = false;
+  if (const char* e = getenv("C3D_PIGAN_PAIR")) pair = atoi(e) != 0 && sms >= 2;
+  if (pair) C3D_LAUNCH(pigan_prep_weights_kernel<true>, kStreamLayers * (kH / kKC), 256, 0, st, *w, base + ws.tiles, (float4*)(base + ws.wl4));
+  else C3D_LAUNCH(pigan_prep_weights_kernel<false>, kStreamLayers * (kH / kKC), 256, 0, st, *w, base + ws.tiles, (float4*)(base + ws.wl4));
   C3D_LAUNCH_CHECK();
   C3D_LAUNCH(pigan_prep_consts_kernel, p->batch, 256, 0, st, *w, p->batch, (ImgConsts*)(base + ws.consts));
   C3D_LAUNCH_CHECK();
@@ -571,17 +614,38 @@ int c3d_pigan_render_fwd_tc(const C3dRayParams* p, const C3dPiganWeights* w, con
   ka.total_groups = p->batch * ka.groups_per_img;
   ka.b_sigma = w->b_sigma;
   ka.bl = w->bl;
-  const size_t smem = sizeof(Smem) + 1024;
-  static std::atomic<unsigned long long> attr_set{0};
-  if (!(attr_set.load() >> (dev & 63) & 1ull)) {
-    C3D_CUDA(cudaFuncSetAttribute(pigan_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_set.fetch_or(1ull << (dev & 63));
+  if (pair) {
+    const size_t smem = sizeof(SmemT<true>) + 1024;
+    auto kern = pigan_tc_kernel<true>;
+    C3D_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int grid = (ka.total_groups + 1) / 2 * 2;
+    if (grid > sms / 2 * 2) grid = sms / 2 * 2;
+    c3d_count_launch();
+#ifdef C3D_EMU
+    C3D_CUDA(C3D_LAUNCH_CLUSTER(kern, grid, kThreads, smem, st, 2, ka));
+#else
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    C3D_CUDA(cudaLaunchKernelEx(&cfg, kern, ka));
+#endif
+    return C3D_OK;
   }
+  const size_t smem = sizeof(SmemT<false>) + 1024;
+  C3D_CUDA(cudaFuncSetAttribute(pigan_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int grid = ka.total_groups;
-  const int sms = c3d_device_sm_count(dev);
   if (grid > sms) grid = sms;
   if (grid < 1) grid = 1;
-  C3D_LAUNCH(pigan_tc_kernel, grid, kThreads, smem, st, ka);
+  C3D_LAUNCH(pigan_tc_kernel<false>, grid, kThreads, smem, st, ka);
   C3D_LAUNCH_CHECK();
   return C3D_OK;
 }

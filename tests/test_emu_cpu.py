@@ -249,7 +249,7 @@ def test_emu_blur_tma_streaming_kernel(shape, pad, mode, monkeypatch):
         assert y.shape == ref.shape and (y - ref).abs().max().item() < 1e-5
 
 
-@pytest.mark.parametrize("impl,mode", [("simt", "eager"), ("tc", "lazy"), ("tc", "random")])
+@pytest.mark.parametrize("impl,mode", [("simt", "eager"), ("tc", "lazy"), ("tc", "random"), ("tc-pair", "lazy"), ("tc-pair", "random")])
 @pytest.mark.parametrize("name", PIGAN_CASES)
 def test_emu_pigan_renderer_matches_reference_golden(name, impl, mode, monkeypatch):
     """c3d_pigan_render_fwd (rays -> 8 x 256 FiLM-SIREN with view-dependent colour -> resampling -> rgb compositing) against
@@ -257,7 +257,9 @@ def test_emu_pigan_renderer_matches_reference_golden(name, impl, mode, monkeypat
     lock_view_dependence, non-hierarchical S = 24, staged_forward's truncated frequencies."""
     # impl "tc": pigan_tc.cu -- one fused tcgen05 kernel (streamed 256x256 hi/lo weight tiles, A operand in TMEM, 3-pass
     # split precision, heads and the view-direction columns in the epilogues, warp-per-ray math); "simt": pigan_simt.cu
-    monkeypatch.setenv("C3D_PIGAN_IMPL", impl)
+    # "tc-pair": the same kernel as a tcgen05 cta_group::2 CTA pair (two ray groups per weight stream, A from each CTA's TMEM)
+    monkeypatch.setenv("C3D_PIGAN_IMPL", impl.split("-")[0])
+    monkeypatch.setenv("C3D_PIGAN_PAIR", "1" if impl.endswith("pair") else "0")
     sd, z, draws, kw, meta, ref = load_pigan_case(name)
     with emulated(async_mode=MODES[mode], seed=9) as pkg:
         cls = pkg.pigan.SPATIALSIRENBASELINE if meta["siren_cls"] == "SPATIALSIRENBASELINE" else pkg.pigan.TALLSIREN
@@ -277,3 +279,27 @@ def test_emu_pigan_renderer_matches_reference_golden(name, impl, mode, monkeypat
     assert rel_err(out["all_z"], ref["all_z"])[0] < 5e-4      # inverse CDF over bins down to 1e-5 wide: conditioning ~1e-4
     assert close_frac(out["rgb"], ref["rgb"], 1e-3)[0] >= 0.995
     assert close_frac(out["depth"][..., None], ref["depth"][..., None], 1e-3)[0] >= 0.995
+
+
+@pytest.mark.parametrize("n_rays", [25, 7])
+def test_emu_pigan_tc_pair_with_a_dummy_partner_group_equals_the_single_cta_kernel(n_rays, monkeypatch):
+    """Odd group counts: the last pair runs with a dummy partner group.  Ray-subset renders of the pair kernel must equal the
+    full render of the single-CTA kernel bit for bit (same MMA operands, same K order)."""
+    sd, z, draws, kw, meta, ref = load_pigan_case("tall_r6_lockview")
+    monkeypatch.setenv("C3D_PIGAN_IMPL", "tc")
+
+    def run(n, pair, mode):
+        monkeypatch.setenv("C3D_PIGAN_PAIR", "1" if pair else "0")
+        with emulated(async_mode=mode, seed=2, sms=2) as pkg:
+            G = pkg.pigan.ImplicitGenerator3d(pkg.pigan.TALLSIREN, z_dim=256)
+            G.load_state_dict(sd)
+            with torch.no_grad():
+                fr, ph = pigan_freq_phase(sd, z, meta)
+                origin, _, _ = O.camera_origin(draws["yaw_n"], draws["pitch_n"], kw["h_stddev"], kw["v_stddev"], kw["h_mean"], kw["v_mean"])
+                return pkg.ops.pigan_render(G.siren.kernel_weights(fr, ph), O.cam2world(-origin, origin), draws["jitter_u"], draws["pdf_u"][:n],
+                                            draws["noise_c"][:, :n], draws["noise_f"][:, :n], img_size=meta["img_size"], fov=kw["fov"],
+                                            ray_start=kw["ray_start"], ray_end=kw["ray_end"], num_steps=kw["num_steps"],
+                                            hierarchical_sample=True, clamp_mode="relu", noise_std=0.0, lock_view=True, n_rays=n, want_depth=True)
+    full = run(36, False, 0)
+    sub = run(n_rays, True, 2)
+    assert torch.equal(sub["rgb"], full["rgb"][:, :n_rays]) and torch.equal(sub["depth"], full["depth"][:, :n_rays])

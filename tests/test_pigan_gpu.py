@@ -79,10 +79,12 @@ def test_pigan_training_graph_backprops_and_matches_native(pkg):
 
 
 @pytest.mark.skipif(os.environ.get("C3D_EXPERIMENTAL", "0") != "1", reason="hardware-unvalidated kernel: set C3D_EXPERIMENTAL=1")
+@pytest.mark.parametrize("pair", ["0", "1"])
 @pytest.mark.parametrize("name", [c for c in PIGAN_CASES if "staged" not in c])
-def test_pigan_tc_kernel_matches_reference_golden(pkg, name, monkeypatch):
-    """C3D_PIGAN_IMPL=tc: the fused tcgen05 pi-GAN renderer (pigan_tc.cu) through the class surface."""
+def test_pigan_tc_kernel_matches_reference_golden(pkg, name, pair, monkeypatch):
+    """C3D_PIGAN_IMPL=tc: the fused tcgen05 pi-GAN renderer (pigan_tc.cu) through the class surface; pair = CTA-pair form."""
     monkeypatch.setenv("C3D_PIGAN_IMPL", "tc")
+    monkeypatch.setenv("C3D_PIGAN_PAIR", pair)
     sd, z, draws, kw, meta, ref = load_pigan_case(name)
     G = _build(pkg, sd, meta)
     with torch.no_grad(), replay_draws(_draw_seq(draws, kw["hierarchical_sample"]), DEV):

@@ -775,7 +775,7 @@ inline void mma_issue_cg1(uint32_t d_tmem, bool a_from_tmem, uint64_t a_desc_or_
 // cta_group::2: D_v[128 x N] (+)= A_v[128 x 16] * [B_0; B_1][N x 16]^T in each CTA v of the pair; CTA v holds rows
 // [v*N/2, (v+1)*N/2) of B at the descriptor's address in ITS shared memory (cute MMA_Traits<SM100_MMA_F16BF16_2x1SM_SS>:
 // ALayout / BLayout / CLayout split M, N and M across the two CTAs).
-inline void mma_issue_cg2(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+inline void mma_issue_cg2(uint32_t d_tmem, bool a_from_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
   Fiber* f = cur();
   Launch& l = L();
   if (l.ctas.size() != 2) fail("tcgen05.mma.cta_group::2 needs a 2-CTA cluster (have %zu)", l.ctas.size());
@@ -783,16 +783,22 @@ inline void mma_issue_cg2(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uin
   const InstrDesc id = decode_idesc(idesc, 2);
   if (d_tmem >> 16) fail("tcgen05.mma: D address names lane %u", d_tmem >> 16);
   const int d_col = (int)(d_tmem & 0xFFFF), N = id.N, NH = id.N / 2;
-  const SmemDesc ad = decode_desc(a_desc, "tcgen05.mma A"), bd = decode_desc(b_desc, "tcgen05.mma B");
+  const SmemDesc ad = a_from_tmem ? SmemDesc{} : decode_desc(a_desc, "tcgen05.mma A"), bd = decode_desc(b_desc, "tcgen05.mma B");
+  const int a_col = a_from_tmem ? (int)(a_desc & 0xFFFF) : -1;
+  if (a_from_tmem) {
+    if ((uint32_t)a_desc >> 16) fail("tcgen05.mma: A (TMEM) address names lane %u", (uint32_t)a_desc >> 16);
+    if (a_col < d_col + N && d_col < a_col + 8) fail("tcgen05.mma: A (TMEM cols %d..%d) overlaps D (%d..%d)", a_col, a_col + 7, d_col, d_col + N - 1);
+  }
   uint8_t* a_base[2];
   uint8_t* b_base[2];
   uint64_t ha[2], hb[2];
   for (int v = 0; v < 2; ++v) {
     Cta* c = l.ctas[v];
     if (d_col + N > c->tmem_allocated) fail("tcgen05.mma: D columns %d..%d outside CTA %d's allocation", d_col, d_col + N - 1, v);
-    a_base[v] = desc_ptr(c, ad.addr, canon_span(ad, 128), "tcgen05.mma A");
+    a_base[v] = a_from_tmem ? nullptr : desc_ptr(c, ad.addr, canon_span(ad, 128), "tcgen05.mma A");
+    if (a_from_tmem && a_col + 8 > c->tmem_allocated) fail("tcgen05.mma: A columns outside CTA %d's allocation", v);
     b_base[v] = desc_ptr(c, bd.addr, canon_span(bd, NH), "tcgen05.mma B");
-    ha[v] = hash_operand(a_base[v], ad, 128);
+    ha[v] = a_from_tmem ? 0 : hash_operand(a_base[v], ad, 128);
     hb[v] = hash_operand(b_base[v], bd, NH);
   }
   Cta* c0 = l.ctas[0];
@@ -801,11 +807,12 @@ inline void mma_issue_cg2(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uin
   AsyncOp op;
   op.what = "tcgen05.mma.cta_group::2";
   op.d_col0 = d_col; op.d_col1 = d_col + N;
+  if (a_from_tmem) { op.a_col0 = a_col; op.a_col1 = a_col + 8; }
   op.both_ctas = true;
   op.run = [=]() {
     Cta* cs[2] = {c0, c1};
     for (int v = 0; v < 2; ++v) {
-      if (hash_operand(a_base[v], ad, 128) != ha[v]) fail("race: CTA %d's A operand of a cta_group::2 MMA changed between issue and execution", v);
+      if (!a_from_tmem && hash_operand(a_base[v], ad, 128) != ha[v]) fail("race: CTA %d's A operand of a cta_group::2 MMA changed between issue and execution", v);
       if (hash_operand(b_base[v], bd, NH) != hb[v]) fail("race: CTA %d's half of the B operand of a cta_group::2 MMA changed between issue and execution", v);
     }
     std::vector<float> B((size_t)N * 16);
@@ -814,7 +821,14 @@ inline void mma_issue_cg2(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uin
     for (int v = 0; v < 2; ++v)
       for (int r = 0; r < 128; ++r) {
         float a[16];
-        for (int k = 0; k < 16; ++k) a[k] = h2f(canon_elem(a_base[v], ad, r, k));
+        for (int k = 0; k < 16; ++k) {
+          if (a_from_tmem) {
+            const uint32_t w = cs[v]->T(r, a_col + k / 2);
+            a[k] = h2f((uint16_t)((k & 1) ? (w >> 16) : (w & 0xFFFF)));
+          } else {
+            a[k] = h2f(canon_elem(a_base[v], ad, r, k));
+          }
+        }
         for (int n = 0; n < N; ++n) {
           uint32_t& dw = cs[v]->T(r, d_col + n);
           float accv = 0.f;

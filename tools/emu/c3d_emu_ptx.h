@@ -102,7 +102,10 @@ inline void tmem_alloc_cg2(uint32_t* smem_result) { emu::tmem_do_alloc(smem_resu
 template <int kCols>
 inline void tmem_dealloc_cg2(uint32_t taddr) { emu::tmem_do_dealloc(taddr, kCols); }
 inline void umma_ss_w_cg2(uint32_t d_tmem, uint32_t a_lo, uint32_t b_lo, uint32_t desc_hi, uint32_t idesc, uint32_t accumulate) {
-  emu::mma_issue_cg2(d_tmem, (uint64_t)a_lo | (uint64_t)desc_hi << 32, (uint64_t)b_lo | (uint64_t)desc_hi << 32, idesc, accumulate);
+  emu::mma_issue_cg2(d_tmem, false, (uint64_t)a_lo | (uint64_t)desc_hi << 32, (uint64_t)b_lo | (uint64_t)desc_hi << 32, idesc, accumulate);
+}
+inline void umma_ts_w_cg2(uint32_t d_tmem, uint32_t a_tmem, uint32_t b_lo, uint32_t desc_hi, uint32_t idesc, uint32_t accumulate) {
+  emu::mma_issue_cg2(d_tmem, true, a_tmem, (uint64_t)b_lo | (uint64_t)desc_hi << 32, idesc, accumulate);
 }
 inline void tc_commit_cg2_mc(uint64_t* bar, uint16_t mask) {
   if (emu::cur()->cta->rank != 0) emu::fail("tcgen05.commit.cta_group::2 issued by CTA rank %d", emu::cur()->cta->rank);

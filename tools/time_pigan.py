@@ -19,8 +19,9 @@ kw = dict(O.PIGAN_KWARGS)
 z = torch.randn(B, 256, device=dev)
 mac_per_point = 3 * 256 + 7 * 256 * 256 + 256 + 259 * 256 + 3 * 256
 flop = 2.0 * mac_per_point * 2 * kw["num_steps"] * R * R * B
-for impl in ("simt", "tc"):
-    os.environ["C3D_PIGAN_IMPL"] = impl
+for impl in ("simt", "tc", "tc-pair"):
+    os.environ["C3D_PIGAN_IMPL"] = impl.split("-")[0]
+    os.environ["C3D_PIGAN_PAIR"] = "1" if impl.endswith("pair") else "0"
     with torch.no_grad():
         for _ in range(3):
             G(z, img_size=R, nerf_noise=0.0, **kw)
