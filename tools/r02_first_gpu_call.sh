@@ -26,10 +26,15 @@ C3D_BLUR_TMA=1 timeout 300 python tools/bench_disc_ops.py > $O/r02a_disc_ops_blu
 C3D_EXPERIMENTAL=1 timeout 300 python -m pytest tests/test_pigan_gpu.py -q > $O/r02a_pytest_pigan.log 2>&1; echo "pigan (simt + tc): exit $?" | tee -a $O/r02a_summary.txt
 timeout 300 python tools/time_pigan.py 64 4 > $O/r02a_time_pigan.jsonl 2>&1; echo "pigan timing: exit $?" | tee -a $O/r02a_summary.txt
 timeout 300 python tools/bench_optim.py > $O/r02a_optim.jsonl 2>&1; echo "optim bench: exit $?" | tee -a $O/r02a_summary.txt
+# train-step configurations of BASELINE.json (3: r128 non-frozen + aux, 5: r256 finetune recipe), fused vs torch optimiser tail
+for c in 3 5; do for o in fused torch; do
+  timeout 600 python tools/bench_train_step.py --config $c --optim $o > $O/r02a_train_c${c}_$o.json 2> $O/r02a_train_c${c}_$o.err; echo "train step config $c optim $o: exit $?" | tee -a $O/r02a_summary.txt
+done; done
 python bench.py --steps 20 --warmup 5 > $O/r02a_bench.json 2> $O/r02a_bench.err
 # the same contract line with the variants that passed above (only meaningful if their tests exited 0)
 C3D_CIPS_PAIR=1 C3D_RAY_MATH=warp timeout 600 python bench.py --steps 20 --warmup 5 --no-cpu-baseline --no-eager > $O/r02a_bench_variants.json 2> $O/r02a_bench_variants.err
 tail -n 3 $O/r02a_time_kernels_default.log $O/r02a_time_kernels_pair.log $O/r02a_time_forward_default.log $O/r02a_time_forward_pair.log $O/r02a_time_forward_raywarp.log
 grep -h "blur" $O/r02a_disc_ops_default.jsonl $O/r02a_disc_ops_blur_tma.jsonl | cut -c1-200
 cat $O/r02a_optim.jsonl $O/r02a_time_pigan.jsonl | cut -c1-300
+cat $O/r02a_train_c*.json 2>/dev/null | cut -c1-400
 cat $O/r02a_summary.txt
