@@ -1,6 +1,6 @@
 #!/bin/bash
-# Round-2 opening GPU call (one gpurun, ~8-10 GPU-minutes):
-#   /usr/local/graft/bin/gpurun --timeout 900 -- 'bash tools/r02_first_gpu_call.sh'
+# Round-2 opening GPU call (one gpurun, ~25 GPU-minutes; every item has its own timeout):
+#   /usr/local/graft/bin/gpurun --timeout 2400 -- 'bash tools/r02_first_gpu_call.sh'
 # 1. the default GPU suite (must stay green), 2. the hardware-unvalidated variants that passed the CPU emulation, each
 # in its own process under `timeout` (a protocol error traps the context: it must not take the other checks along),
 # 3. A/B timings of every variant against the default, 4. roofline benches of the HBM-bound ops.  Everything lands in
