@@ -303,3 +303,21 @@ def test_emu_pigan_tc_pair_with_a_dummy_partner_group_equals_the_single_cta_kern
     full = run(36, False, 0)
     sub = run(n_rays, True, 2)
     assert torch.equal(sub["rgb"], full["rgb"][:, :n_rays]) and torch.equal(sub["depth"], full["depth"][:, :n_rays])
+
+
+# ------------------------------------------------------------------ the emulator must report broken kernels (tools/emu/emu_faults.cpp)
+@pytest.mark.parametrize("case,mode,needle", [
+    (1, "random", "deadlock"), (3, "random", "may only access TMEM lanes"),
+    (4, "lazy", "changed between issue and execution"), (5, "lazy", "while a queued tcgen05.mma still writes"),
+    (6, "random", "outside the allocation")])
+def test_emu_reports_broken_micro_kernels(case, mode, needle, capfd):
+    """One deliberately wrong micro-kernel per failure class the emulator claims to detect: a wait nobody satisfies, a
+    TMEM lane-quarter violation, an MMA operand overwritten before the MMA ran, a tcgen05.ld of an
+    accumulator with the MMA still in flight, an access outside the TMEM allocation.  Case 0 (the same kernel, correct) passes."""
+    lib = _emu.emu_lib()
+    lib.c3d_emu_fault_case.argtypes = [C.c_int, C.c_void_p]
+    out = torch.zeros(128)
+    lib.c3d_emu_configure(MODES[mode], 3, 20, 2)
+    assert lib.c3d_emu_fault_case(0, out.data_ptr()) == 0 and float(out.abs().sum()) > 0
+    assert lib.c3d_emu_fault_case(case, out.data_ptr()) != 0
+    assert needle in capfd.readouterr().err

@@ -25,7 +25,7 @@ def build(force=False, extra_defs=(), tag=""):
 def _build(OUT_DIR, force, extra_defs):
     LIB = os.path.join(OUT_DIR, "libcips3d_b200_emu.so")
     os.makedirs(OUT_DIR, exist_ok=True)
-    srcs = sorted(glob.glob(os.path.join(CSRC, "*.cu"))) + [os.path.join(HERE, "emu_impl.cpp")]
+    srcs = sorted(glob.glob(os.path.join(CSRC, "*.cu"))) + [os.path.join(HERE, "emu_impl.cpp"), os.path.join(HERE, "emu_faults.cpp")]
     deps = srcs + glob.glob(os.path.join(CSRC, "*.cuh")) + glob.glob(os.path.join(HERE, "*.h")) + \
         glob.glob(os.path.join(ROOT, "include", "*.h")) + [os.path.abspath(__file__)]
     newest = max(os.path.getmtime(d) for d in deps)
