@@ -51,7 +51,11 @@ def main():
     ap.add_argument("--warmup", type=int, default=2)
     ap.add_argument("--optim", default="fused", choices=["fused", "torch"])
     ap.add_argument("--batch", type=int, default=None)
+    ap.add_argument("--tf32", action="store_true", help="allow TF32 in the torch autograd GEMMs / cuDNN convs of the training graph "
+                    "(NOT the reference's numerics: torch defaults to fp32 matmuls); measures what the library path can give")
     args = ap.parse_args()
+    torch.backends.cuda.matmul.allow_tf32 = bool(args.tf32)
+    torch.backends.cudnn.allow_tf32 = bool(args.tf32)
     cfg = dict(CONFIGS[args.config])
     if args.aux:
         cfg["aux"] = True
@@ -161,7 +165,7 @@ def main():
             metric="train step (D step + G step) images/s", value=B * world / ms.item() * 1e3, unit="images/s", ms_per_step=ms.item(),
             n_gpus=world, steps=args.steps, warmup=args.warmup,
             config=dict(baseline_config=args.config, resolution=R, batch_per_gpu=B, generator=G_cls.__name__, train_aux_img=cfg["aux"],
-                        diffaug=cfg["diffaug"], grad_points=cfg["grad_points"], optim=args.optim,
+                        diffaug=cfg["diffaug"], grad_points=cfg["grad_points"], optim=args.optim, tf32_autograd=bool(args.tf32),
                         note="G forward under no_grad runs the fused kernels; the G step's autograd graph runs as torch CUDA ops "
                              "(backward kernels: DESIGN.md section 9); D convs are cuDNN as in the reference; D's bias_act / blur are native"),
             d_loss=float(dl), g_loss=float(gl), finite=bool(math.isfinite(float(dl)) and math.isfinite(float(gl))))))
