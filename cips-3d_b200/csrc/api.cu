@@ -25,7 +25,7 @@ int c3d_cips_fwd_simt(const C3dCipsParams*, const C3dCipsWeights*, const float*,
 size_t c3d_ray_siren_tc_workspace_bytes(const C3dRayParams* p);
 int c3d_ray_siren_fwd_tc(const C3dRayParams*, const C3dSirenWeights*, const C3dRayIO*, void*, size_t, cudaStream_t);
 size_t c3d_cips_tc_workspace_bytes(const C3dCipsParams* p);
-int c3d_cips_fwd_tc(const C3dCipsParams*, const C3dCipsWeights*, const float*, float*, float*, void*, size_t, cudaStream_t);
+int c3d_cips_fwd_tc(const C3dCipsParams*, const C3dCipsWeights*, const float*, float*, float*, void*, size_t, cudaStream_t, void* acts_f16, void* zsign_u16);
 
 extern "C" int c3d_version(void) { return 100; }
 extern "C" const char* c3d_last_error(void) { return g_err; }
@@ -109,7 +109,18 @@ extern "C" int c3d_cips_fwd(const C3dCipsParams* p, const C3dCipsWeights* w, con
   if (p->batch == 0 || p->n_pix == 0) return C3D_OK;
   C3D_CHECK_ARG(workspace || c3d_cips_workspace_bytes(p) == 0, "cips: null workspace");
   if (p->impl == C3D_IMPL_SIMT) return c3d_cips_fwd_simt(p, w, x, rgb, hidden_out, workspace, workspace_bytes, (cudaStream_t)stream);
-  if (p->impl == C3D_IMPL_TC) return c3d_cips_fwd_tc(p, w, x, rgb, hidden_out, workspace, workspace_bytes, (cudaStream_t)stream);
+  if (p->impl == C3D_IMPL_TC) return c3d_cips_fwd_tc(p, w, x, rgb, hidden_out, workspace, workspace_bytes, (cudaStream_t)stream, nullptr, nullptr);
   c3d_set_error("cips: unknown impl %d", p->impl);
   return C3D_EINVAL;
+}
+
+// training forward: c3d_cips_fwd + the activation stash the backward pass needs (see include/cips3d_b200.h)
+extern "C" int c3d_cips_fwd_train(const C3dCipsParams* p, const C3dCipsWeights* w, const float* x, float* rgb, void* acts_f16,
+                                  void* zsign_u16, void* workspace, size_t workspace_bytes, void* stream) {
+  if (int e = check_cips_args(p, w, x, rgb)) return e;
+  C3D_CHECK_ARG(acts_f16 && zsign_u16, "cips_fwd_train: null activation / sign stash");
+  C3D_CHECK_ARG(p->impl == C3D_IMPL_TC, "cips_fwd_train: tensor-core kernels only");
+  if (p->batch == 0 || p->n_pix == 0) return C3D_OK;
+  C3D_CHECK_ARG(workspace, "cips_fwd_train: null workspace");
+  return c3d_cips_fwd_tc(p, w, x, rgb, nullptr, workspace, workspace_bytes, (cudaStream_t)stream, acts_f16, zsign_u16);
 }

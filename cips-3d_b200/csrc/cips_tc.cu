@@ -90,6 +90,14 @@ struct KArgs {
   // this order so the producer streams linearly.
   uint16_t order_full[32];
   uint16_t order_in[4];
+  // training (DUMP instantiation only): every layer's output y_l (after LeakyReLU and residual) as the fp16 values the next
+  // layer consumed, (n_layers, B, N, 512) row-major, for the backward pass (cips_bwd_tc.cu).  Appended: the offsets of the
+  // fields above are those of the round-1 kernel.
+  __half* acts;
+  size_t acts_layer_stride;      // elements between consecutive layers = B * N * 512
+  // sign bits of z_l for the layers that add a residual (there y_l - y_{l-2} cannot recover the sign of a small lrelu(z_l)
+  // from two fp16-rounded stashes): (n_layers, B, N, 32) uint16, bit i of word c = (z_l[16 c + i] > 0)
+  uint16_t* zsign;
 };
 
 template <int CL>
@@ -146,13 +154,19 @@ struct EpiFlags {
 //   rp: residual scratch (float4 index c/4, this row).
 //   first layer of a block : a = lrelu(acc)
 //   second layer of a block: y = lrelu(acc) (+ residual); ToRGB += y.Wrgb; a = y
-template <bool SECOND>
+template <bool SECOND, bool DUMP = false>
 __device__ __forceinline__ void epi16(const uint32_t (&acc)[16], const float4 (&rs)[4], const float4* __restrict__ rwp,
                                       uint8_t* xp, float4* rp, const EpiFlags f, float& rgb0, float& rgb1, float& rgb2,
-                                      float* hid_out) {
+                                      float* hid_out, uint4* dump = nullptr, uint16_t* zsign = nullptr) {
   float y[16];
 #pragma unroll
   for (int i = 0; i < 16; ++i) y[i] = lrelu02(__uint_as_float(acc[i]));
+  if (DUMP && SECOND && zsign && f.add_res) {
+    uint32_t m = 0;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) m |= (__uint_as_float(acc[i]) > 0.f ? 1u : 0u) << i;
+    *zsign = (uint16_t)m;
+  }
   if (SECOND) {
     if (f.add_res) {
 #pragma unroll
@@ -179,6 +193,13 @@ __device__ __forceinline__ void epi16(const uint32_t (&acc)[16], const float4 (&
         for (int g = 0; g < 4; ++g)
           reinterpret_cast<float4*>(hid_out)[g] = make_float4(y[4 * g], y[4 * g + 1], y[4 * g + 2], y[4 * g + 3]);
       }
+      if (DUMP && dump) {
+        uint32_t pl[8];
+#pragma unroll
+        for (int g = 0; g < 8; ++g) pl[g] = pack_f16(y[2 * g], y[2 * g + 1]);
+        dump[0] = make_uint4(pl[0], pl[1], pl[2], pl[3]);
+        dump[1] = make_uint4(pl[4], pl[5], pl[6], pl[7]);
+      }
       return;
     }
   }
@@ -187,6 +208,10 @@ __device__ __forceinline__ void epi16(const uint32_t (&acc)[16], const float4 (&
   for (int g = 0; g < 8; ++g) pk[g] = pack_f16(y[2 * g], y[2 * g + 1]);
   *reinterpret_cast<uint4*>(xp) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
   *reinterpret_cast<uint4*>(xp + kLBO) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+  if (DUMP && dump) {
+    dump[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+    dump[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+  }
 }
 
 // PAIR (CL == 2 only): the two CTAs of a cluster form a tcgen05 CTA pair.  Only the leader (cluster rank 0) issues MMAs
@@ -194,7 +219,7 @@ __device__ __forceinline__ void epi16(const uint32_t (&acc)[16], const float4 (&
 // streams HALF of every weight tile into its own ring; the peer relays "my half landed" to the leader (peer_full);
 // both CTAs' epilogue warps report to the leader's epi_done barriers; the leader's commits are multicast to the
 // empty / acc_ready barriers of both CTAs.  Everything else (tile order, staircase, epilogue) is the single-CTA kernel.
-template <int CL, bool PAIR = false>
+template <int CL, bool PAIR = false, bool DUMP = false>
 __global__ void __launch_bounds__(kThreads, 1) cips_tc_kernel(const KArgs a) {
   static_assert(!PAIR || CL == 2, "a CTA pair is a cluster of two");
   using SM = SmemT<PAIR>;
@@ -445,6 +470,12 @@ __global__ void __launch_bounds__(kThreads, 1) cips_tc_kernel(const KArgs a) {
         uint8_t* xp = s.x + (size_t)(cw / 8) * kLBO + row * 16;
         const float4* rwp = s.rgbw + cw;
         float* hp = hid ? hid + cw : nullptr;
+        // DUMP: this row's 16-byte units of layer l's output in the activation stash (two per 16-column slice)
+        uint4* dp = (DUMP && a.acts && row_ok)
+                        ? reinterpret_cast<uint4*>(a.acts + (size_t)l * a.acts_layer_stride + ((size_t)img * a.N + pix) * kH + cw)
+                        : nullptr;
+        uint16_t* zp = (DUMP && a.zsign && row_ok) ? a.zsign + ((size_t)l * a.acts_layer_stride + ((size_t)img * a.N + pix) * kH + cw) / 16
+                                                   : nullptr;
         auto load_res = [&](float4 (&rs)[4], const float4* p) {
 #pragma unroll
           for (int g = 0; g < 4; ++g) rs[g] = p[g * kTileM];
@@ -465,8 +496,8 @@ __global__ void __launch_bounds__(kThreads, 1) cips_tc_kernel(const KArgs a) {
           tc_wait_ld();
           tmem_ld16(tcol + 16, accB);
           if (f.add_res) load_res(rsB, rp + 4 * kTileM);
-          if (second) epi16<true>(accA, rsA, rwp, xp, rp, f, rgb0, rgb1, rgb2, hp);
-          else epi16<false>(accA, rsA, rwp, xp, rp, f, rgb0, rgb1, rgb2, hp);
+          if (second) epi16<true, DUMP>(accA, rsA, rwp, xp, rp, f, rgb0, rgb1, rgb2, hp, dp, zp);
+          else epi16<false, DUMP>(accA, rsA, rwp, xp, rp, f, rgb0, rgb1, rgb2, hp, dp);
           tc_wait_ld();
           have = false;
           if (j < 3) {
@@ -477,8 +508,8 @@ __global__ void __launch_bounds__(kThreads, 1) cips_tc_kernel(const KArgs a) {
             }
             if (f.add_res) load_res(rsA, rp + 32 * kTileM);
           }
-          if (second) epi16<true>(accB, rsB, rwp + 16, xp + 2 * kLBO, rp + 4 * kTileM, f, rgb0, rgb1, rgb2, hp ? hp + 16 : nullptr);
-          else epi16<false>(accB, rsB, rwp + 16, xp + 2 * kLBO, rp + 4 * kTileM, f, rgb0, rgb1, rgb2, hp ? hp + 16 : nullptr);
+          if (second) epi16<true, DUMP>(accB, rsB, rwp + 16, xp + 2 * kLBO, rp + 4 * kTileM, f, rgb0, rgb1, rgb2, hp ? hp + 16 : nullptr, dp ? dp + 2 : nullptr, zp ? zp + 1 : nullptr);
+          else epi16<false, DUMP>(accB, rsB, rwp + 16, xp + 2 * kLBO, rp + 4 * kTileM, f, rgb0, rgb1, rgb2, hp ? hp + 16 : nullptr, dp ? dp + 2 : nullptr);
           // chunk j of this epilogue is complete for this warp
           if (PAIR) fence_proxy_async_all();
           else fence_proxy_async();
@@ -491,6 +522,8 @@ __global__ void __launch_bounds__(kThreads, 1) cips_tc_kernel(const KArgs a) {
           if (lane == 0) TRACE(it, 9, (uint32_t)(l << 8 | (warp - 4) << 2 | j));   // warp finished chunk j
           tcol += 128; rp += 32 * kTileM; xp += 16 * kLBO; rwp += 128;
           if (hp) hp += 128;
+          if (dp) dp += 16;
+          if (zp) zp += 8;
         }
       }
       named_bar_sync_c<1, kNumEpiWarps * 32>();   // rgbw (aliased) no longer read
@@ -636,13 +669,13 @@ extern "C" int c3d_debug_cips_trace(unsigned long long* out, int cap) {
 }
 #endif
 
-template <int CL, bool PAIR = false>
+template <int CL, bool PAIR = false, bool DUMP = false>
 static int launch_cips(const KArgs& ka, int grid, cudaStream_t st) {
   const size_t smem = sizeof(SmemT<PAIR>) + 1024;
   static std::atomic<unsigned long long> attr_set{0};     // per device, once
   int dev = 0;
   cudaGetDevice(&dev);
-  auto kern = cips_tc_kernel<CL, PAIR>;
+  auto kern = cips_tc_kernel<CL, PAIR, DUMP>;
   if (!(attr_set.load() >> (dev & 63) & 1ull)) {
     C3D_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_set.fetch_or(1ull << (dev & 63));
@@ -717,7 +750,7 @@ extern "C" int c3d_debug_cips_tile_order(uint16_t* order_full32, uint16_t* order
 }
 
 int c3d_cips_fwd_tc(const C3dCipsParams* p, const C3dCipsWeights* w, const float* x, float* rgb, float* hidden_out,
-                    void* workspace, size_t workspace_bytes, cudaStream_t st) {
+                    void* workspace, size_t workspace_bytes, cudaStream_t st, void* acts_f16, void* zsign_u16) {
   C3D_CHECK_ARG(p->hidden == kH, "cips(tc): hidden must be 512, got %d", p->hidden);
   C3D_CHECK_ARG(p->in_dim >= 1 && p->in_dim <= kKC, "cips(tc): in_dim must be <= 64, got %d", p->in_dim);
   C3D_CHECK_ARG(p->skip_from >= 1, "cips(tc): skip_from must be >= 1 (block 0 changes width)");
@@ -736,6 +769,9 @@ int c3d_cips_fwd_tc(const C3dCipsParams* p, const C3dCipsWeights* w, const float
   const int L = 2 * p->n_blocks;
   KArgs ka = {};
   ka.x = x; ka.rgb = rgb; ka.hidden_out = hidden_out;
+  ka.acts = (__half*)acts_f16;
+  ka.zsign = (uint16_t*)zsign_u16;
+  ka.acts_layer_stride = (size_t)p->batch * p->n_pix * kH;
   ka.wtiles = (const __half*)(base + ws.wtiles);
   ka.rgbw = (const float4*)(base + ws.rgbw);
   ka.rgbb = (const float*)(base + ws.rgbb);
@@ -779,6 +815,10 @@ int c3d_cips_fwd_tc(const C3dCipsParams* p, const C3dCipsWeights* w, const float
   C3D_LAUNCH(cips_prep_consts_kernel, p->n_blocks, 256, 0, st, *w, p->n_blocks, p->rgb_from, (float4*)(base + ws.rgbw),
              (float*)(base + ws.rgbb));
   C3D_LAUNCH_CHECK();
+  if (acts_f16) {       // training forward: single-CTA kernel with the activation stash
+    int g1 = ka.total_tiles < c3d_device_sm_count(dev) ? ka.total_tiles : c3d_device_sm_count(dev);
+    return launch_cips<1, false, true>(ka, g1 < 1 ? 1 : g1, st);
+  }
   if (pair) return launch_cips<2, true>(ka, grid, st);
   if (cl == 1) return launch_cips<1>(ka, grid, st);
   if (cl == 2) return launch_cips<2>(ka, grid, st);

@@ -333,10 +333,23 @@ class CIPSNet(nn.Module):                       # generator.py:1009-1154
             rb.append(self.to_rgbs[name].linear.bias)
         return ws, s1ps, ds, rw, rb
 
+    # 'torch': the autograd graph is built from torch CUDA ops (round-1 behaviour).  'fused': forward and backward chain on the
+    # native kernels, weight gradients as fp16 library GEMMs (ops.CipsMLPFunction) -- opt-in, emulation-verified, gradients
+    # agree with fp32 autograd to fp16-operand accuracy (~1e-3 relative), not bit for bit.
+    train_backend = 'torch'
+
+    def forward_fused_train(self, input, style_dict, img_size=1024):
+        n_blocks = self._n_blocks(img_size)
+        ws, s1ps, ds, rw, rb = self.kernel_inputs(style_dict, n_blocks)     # s1p / demod stay in the torch graph (-> modulation, W)
+        tensors = list(ws) + list(s1ps) + list(ds) + list(rw[3:n_blocks]) + list(rb[3:n_blocks])
+        return ops.CipsMLPFunction.apply(input, n_blocks, 4, 3, *tensors)
+
     def forward(self, input, style_dict, img_size=1024, **kwargs):
         """input (b, n, in) -> (b, n, 3)"""
         _require_cuda(input, "CIPSNet.forward")
         needs_graph = torch.is_grad_enabled() and (input.requires_grad or any(p.requires_grad for p in self.parameters()))
+        if needs_graph and self.train_backend == 'fused' and self.fused_supported() and input.dim() == 3 and self._n_blocks(img_size) > 3:
+            return self.forward_fused_train(input, style_dict, img_size)
         if needs_graph or not self.fused_supported() or input.dim() != 3:
             return self.forward_torch(input, style_dict, img_size)
         n_blocks = self._n_blocks(img_size)

@@ -374,3 +374,119 @@ def pigan_render(siren, cam2world, jitter_u, pdf_u=None, noise_c=None, noise_f=N
           "c3d_pigan_render_fwd")
     _prof_end("pigan", ev)
     return out
+
+
+# --------------------------------------------------------------------------------------
+# CIPS MLP with a native backward (first part): fused forward that stashes the activations,
+# gradient chain on tcgen05 (c3d_cips_bwd), weight gradients as library GEMMs over the two stashes
+# --------------------------------------------------------------------------------------
+def _cips_structs(x, weights, style1p, demod, rgb_w, rgb_b, n_blocks, skip_from, rgb_from):
+    x = _f32c(x, "x")
+    B, N, in_dim = x.shape
+    hidden = weights[0].shape[1]
+    p = CipsParams(batch=B, n_pix=N, in_dim=in_dim, hidden=hidden, n_blocks=n_blocks, skip_from=skip_from, rgb_from=rgb_from,
+                   impl=_lib.IMPL_TC)
+    keep = [x]
+    cw = CipsWeights()
+    for l in range(2 * n_blocks):
+        for arr, src, nm in ((cw.w, weights, "w"), (cw.style1p, style1p, "style1p"), (cw.demod, demod, "demod")):
+            t = _f32c(src[l].detach(), f"{nm}[{l}]")
+            keep.append(t)
+            arr[l] = ptr(t)
+    for b in range(n_blocks):
+        if b >= rgb_from:
+            tw = _f32c(rgb_w[b].detach(), "rgb_w")
+            keep.append(tw)
+            cw.rgb_w[b] = ptr(tw)
+            if rgb_b is not None:
+                tb = _f32c(rgb_b[b].detach(), "rgb_b")
+                keep.append(tb)
+                cw.rgb_b[b] = ptr(tb)
+    return x, p, cw, keep
+
+
+def cips_forward_train(x, weights, style1p, demod, rgb_w, rgb_b, *, n_blocks=9, skip_from=4, rgb_from=3):
+    """c3d_cips_fwd_train: -> rgb (B,N,3), acts (2*n_blocks, B, N, hidden) fp16 (every layer's output as the next layer consumed
+    it), zsign (2*n_blocks, B, N, hidden/16) int16 (sign bits of z_l on the residual layers)"""
+    lib = load()
+    x, p, cw, keep = _cips_structs(x, weights, style1p, demod, rgb_w, rgb_b, n_blocks, skip_from, rgb_from)
+    B, N, _ = x.shape
+    rgb = torch.empty((B, N, 3), device=x.device, dtype=torch.float32)
+    acts = torch.empty((2 * n_blocks, B, N, p.hidden), device=x.device, dtype=torch.float16)
+    zsign = torch.empty((2 * n_blocks, B, N, p.hidden // 16), device=x.device, dtype=torch.int16)
+    wsb = lib.c3d_cips_workspace_bytes(C.byref(p))
+    ws = torch.empty((max(wsb, 4) + 3) // 4, device=x.device, dtype=torch.float32)
+    check(lib.c3d_cips_fwd_train(C.byref(p), C.byref(cw), ptr(x), ptr(rgb), ptr(acts), ptr(zsign), ptr(ws), wsb, stream_ptr()),
+          "c3d_cips_fwd_train")
+    return rgb, acts, zsign
+
+
+def cips_backward_chain(x, acts, zsign, g_pre_scaled, weights, style1p, demod, rgb_w, *, n_blocks=9, skip_from=4, rgb_from=3, want_dx=True):
+    """c3d_cips_bwd: g_pre_scaled (B,N,3) = S * dL/d(rgb before tanh) -> dz (2*n_blocks,B,N,hidden) fp16 = S*dZ_l, dx (B,N,in) = S*dL/dx"""
+    lib = load()
+    x, p, cw, keep = _cips_structs(x, weights, style1p, demod, rgb_w, None, n_blocks, skip_from, rgb_from)
+    B, N, in_dim = x.shape
+    g = _f32c(g_pre_scaled, "g")
+    dz = torch.empty_like(acts)
+    dx = torch.empty((B, N, in_dim), device=x.device, dtype=torch.float32) if want_dx else None
+    wsb = lib.c3d_cips_bwd_workspace_bytes(C.byref(p))
+    ws = torch.empty((max(wsb, 4) + 3) // 4, device=x.device, dtype=torch.float32)
+    check(lib.c3d_cips_bwd(C.byref(p), C.byref(cw), ptr(acts), ptr(zsign), ptr(g), ptr(dz), ptr(dx), ptr(ws), wsb, stream_ptr()), "c3d_cips_bwd")
+    return dz, dx
+
+
+def _bmm_f32(a16, b16):
+    """fp16 x fp16 -> fp32 batched GEMM (tensor cores on the GPU: plain library GEMM)"""
+    if a16.is_cuda:
+        return torch.bmm(a16, b16, out_dtype=torch.float32)
+    return torch.bmm(a16.float(), b16.float())
+
+
+class CipsMLPFunction(Function):
+    """y = CIPSNet core (generator.py:1107-1154) with a native backward.  Inputs: x (B,N,in); per layer W (in,out), s1p (B,in),
+    demod (B,out); per ToRGB block w (3,512), b (3).  forward = c3d_cips_fwd_train, backward = c3d_cips_bwd + library GEMMs:
+        T_l[b]  = X_l[b]^T dZ_l[b]                      (dL/dW''_l, W''[k][n] = s1p[k] W[k][n] d[n])
+        dW_l    = sum_b s1p[b,k] T_l[b,k,n] d[b,n],   d s1p[b,k] = sum_n T W d,   d demod[b,n] = sum_k T W s1p
+    (the dependence of demod on W and s1p is differentiated by torch outside, where demod is computed)."""
+
+    @staticmethod
+    def forward(ctx, x, n_blocks, skip_from, rgb_from, *tensors):
+        L = 2 * n_blocks
+        W, S1, D = list(tensors[:L]), list(tensors[L:2 * L]), list(tensors[2 * L:3 * L])
+        n_rgb = n_blocks - rgb_from
+        RW = [None] * rgb_from + list(tensors[3 * L:3 * L + n_rgb])
+        RB = [None] * rgb_from + list(tensors[3 * L + n_rgb:3 * L + 2 * n_rgb])
+        rgb, acts, zsign = cips_forward_train(x, W, S1, D, RW, RB, n_blocks=n_blocks, skip_from=skip_from, rgb_from=rgb_from)
+        ctx.cfg = (n_blocks, skip_from, rgb_from)
+        ctx.save_for_backward(x, rgb, acts, zsign, *tensors)
+        return rgb
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        n_blocks, skip_from, rgb_from = ctx.cfg
+        L = 2 * n_blocks
+        x, rgb, acts, zsign, *tensors = ctx.saved_tensors
+        W, S1, D = list(tensors[:L]), list(tensors[L:2 * L]), list(tensors[2 * L:3 * L])
+        n_rgb = n_blocks - rgb_from
+        RW = [None] * rgb_from + list(tensors[3 * L:3 * L + n_rgb])
+        g_pre = grad_out * (1 - rgb * rgb)                                   # through tanh
+        scale = 1024.0 / g_pre.abs().max().clamp_min(1e-30)                  # device scalar: fp16 range management, no sync
+        g_s = (g_pre * scale).contiguous()
+        dz, dx = cips_backward_chain(x, acts, zsign, g_s, W, S1, D, RW, n_blocks=n_blocks, skip_from=skip_from, rgb_from=rgb_from,
+                                     want_dx=ctx.needs_input_grad[0])
+        inv = 1.0 / scale
+        gW, gS, gD = [], [], []
+        x16 = x.to(torch.float16)
+        for l in range(L):
+            X = x16 if l == 0 else acts[l - 1]
+            T = _bmm_f32(X.transpose(1, 2), dz[l]) * inv                       # (B, in_l, out)
+            gW.append(torch.einsum("bk,bkn,bn->kn", S1[l], T, D[l]))
+            TW = T * W[l].unsqueeze(0)
+            gS.append(torch.einsum("bkn,bn->bk", TW, D[l]))
+            gD.append(torch.einsum("bkn,bk->bn", TW, S1[l]))
+        g16 = g_s.to(torch.float16)
+        gRW, gRB = [], []
+        for b in range(rgb_from, n_blocks):
+            gRW.append(_bmm_f32(g16.transpose(1, 2), acts[2 * b + 1]).sum(0) * inv)      # (3, 512)
+            gRB.append(g_pre.sum((0, 1)))
+        return (dx * inv if dx is not None else None, None, None, None, *gW, *gS, *gD, *gRW, *gRB)

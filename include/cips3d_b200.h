@@ -137,6 +137,21 @@ size_t c3d_cips_workspace_bytes(const C3dCipsParams* p);
 int c3d_cips_fwd(const C3dCipsParams* p, const C3dCipsWeights* w, const float* x, float* rgb,
                  float* hidden_out, void* workspace, size_t workspace_bytes, void* stream);
 
+/* Training forward and the backward CHAIN of the fused CIPS MLP (first part).
+ *   c3d_cips_fwd_train: c3d_cips_fwd that also writes every layer's output y_l (after LeakyReLU / residual) as the fp16
+ *       values the next layer consumed: acts_f16 (n_layers, B, N, hidden), and the sign bits of z_l for the layers that add a
+ *       residual (where y_l - y_{l-2} of two fp16 stashes cannot recover them): zsign_u16 (n_layers, B, N, hidden/16).
+ *   c3d_cips_bwd: given g = dL/d(rgb before tanh) (B,N,3), PRE-MULTIPLIED by a scale S the caller chooses so that fp16
+ *       gradients neither underflow nor overflow, runs dZ_l = dL/dy_l * lrelu'(z_l), dX_l = dZ_l W''_l^T for l = L-1..0 on
+ *       chip and writes dz_f16 (n_layers, B, N, hidden) = S dZ_l and dx (B,N,in_dim) = S dL/dx (or NULL).
+ *   The weight gradients are plain K = pixels GEMMs over the two stashes, dW''_l[b] = X_l[b]^T dZ_l[b] (X_0 = x, X_l = y_{l-1}),
+ *   left to the library; cips3d_b200/ops.py folds them into dW, d style1p, d demod and the ToRGB gradients. */
+int c3d_cips_fwd_train(const C3dCipsParams* p, const C3dCipsWeights* w, const float* x, float* rgb, void* acts_f16,
+                       void* zsign_u16, void* workspace, size_t workspace_bytes, void* stream);
+size_t c3d_cips_bwd_workspace_bytes(const C3dCipsParams* p);
+int c3d_cips_bwd(const C3dCipsParams* p, const C3dCipsWeights* w, const void* acts_f16, const void* zsign_u16,
+                 const float* g_rgb_pre, void* dz_f16, float* dx, void* workspace, size_t workspace_bytes, void* stream);
+
 /* ------------------------------------------------------------------------------------
  * Discriminator ops.  Same semantics as the reference's two pybind11 modules:
  *   fused.fused_bias_act(input, bias, refer, act, grad, alpha, scale)

@@ -141,6 +141,32 @@ experimental = pytest.mark.skipif(os.environ.get("C3D_EXPERIMENTAL", "0") != "1"
 
 
 @experimental
+@pytest.mark.parametrize("B,N", [(1, 128), (2, 200), (2, 4096)])
+def test_cips_backward_chain_and_fused_training(pkg, B, N):
+    """c3d_cips_fwd_train + c3d_cips_bwd on the GPU: the fused training path (CIPSNet.train_backend = 'fused') against the
+    torch autograd graph of the same module on the same device (see tests/test_emu_cpu.py for the tolerances' rationale)."""
+    sd = O.synthetic_state_dict(O.generator_template(), seed=31)
+    G = build_generator(DEV, sd).train()
+    net = G.inr_net
+    g = torch.Generator().manual_seed(B * 7 + N)
+    x = torch.randn(B, N, 32, generator=g).to(DEV)
+    w = torch.randn(B, 512, generator=g).to(DEV)
+    gout = torch.randn(B, N, 3, generator=g).to(DEV)
+    style = {k: w for k in net.style_dim_dict}
+    xa = x.clone().requires_grad_()
+    (net.forward_torch(xa, style) * gout).sum().backward()
+    ref = {n: p.grad.clone() for n, p in net.named_parameters() if p.grad is not None}
+    net.zero_grad()
+    xb = x.clone().requires_grad_()
+    (net.forward_fused_train(xb, style) * gout).sum().backward()
+    torch.cuda.synchronize()
+    assert rel_err(xb.grad.cpu(), xa.grad.cpu())[1] < 8e-2
+    for n, p in net.named_parameters():
+        if n in ref and float(ref[n].abs().max()) > 0:
+            assert rel_err(p.grad.cpu(), ref[n].cpu())[1] < (2e-3 if n.startswith("to_rgbs") else 8e-2), n
+
+
+@experimental
 @pytest.mark.parametrize("n,k", [(32, 16), (128, 64), (256, 256), (96, 128)])
 def test_umma_pair_selftest(pkg, n, k):
     """tcgen05 cta_group::2 in isolation (run this BEFORE the CTA-pair CIPS kernel: it pins the operand partitioning,

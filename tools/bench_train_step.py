@@ -51,6 +51,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=2)
     ap.add_argument("--optim", default="fused", choices=["fused", "torch"])
     ap.add_argument("--batch", type=int, default=None)
+    ap.add_argument("--cips-backend", default="torch", choices=["torch", "fused"],
+                    help="fused: CIPSNet.train_backend = 'fused' (native forward + backward chain, fp16 library GEMMs for dW)")
     ap.add_argument("--tf32", action="store_true", help="allow TF32 in the torch autograd GEMMs / cuDNN convs of the training graph "
                     "(NOT the reference's numerics: torch defaults to fp32 matmuls); measures what the library path can give")
     args = ap.parse_args()
@@ -75,6 +77,7 @@ def main():
     G.load_state_dict(O.synthetic_state_dict(O.generator_template(), seed=1234, sigma_bias=0.3))
     D = cips3d_b200.Discriminator_MultiScale_Aux(diffaug=cfg["diffaug"], max_size=1024, channel_multiplier=2, first_downsample=False,
                                                  stddev_group=0).to(dev)
+    G.inr_net.train_backend = args.cips_backend
     G_ema = copy.deepcopy(G)
     G_run, D_run = G, D
     if ddp:
@@ -165,7 +168,7 @@ def main():
             metric="train step (D step + G step) images/s", value=B * world / ms.item() * 1e3, unit="images/s", ms_per_step=ms.item(),
             n_gpus=world, steps=args.steps, warmup=args.warmup,
             config=dict(baseline_config=args.config, resolution=R, batch_per_gpu=B, generator=G_cls.__name__, train_aux_img=cfg["aux"],
-                        diffaug=cfg["diffaug"], grad_points=cfg["grad_points"], optim=args.optim, tf32_autograd=bool(args.tf32),
+                        diffaug=cfg["diffaug"], grad_points=cfg["grad_points"], optim=args.optim, tf32_autograd=bool(args.tf32), cips_backend=args.cips_backend,
                         note="G forward under no_grad runs the fused kernels; the G step's autograd graph runs as torch CUDA ops "
                              "(backward kernels: DESIGN.md section 9); D convs are cuDNN as in the reference; D's bias_act / blur are native"),
             d_loss=float(dl), g_loss=float(gl), finite=bool(math.isfinite(float(dl)) and math.isfinite(float(gl))))))

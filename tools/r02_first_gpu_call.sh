@@ -10,7 +10,7 @@ mkdir -p gpurun_out
 O=gpurun_out
 python __graft_entry__.py > $O/r02a_build.log 2>&1
 timeout 600 python -m pytest tests -m gpu -x -q > $O/r02a_pytest_gpu.log 2>&1; echo "default gpu suite: exit $?" | tee $O/r02a_summary.txt
-for k in "umma_pair_selftest" "cips_cta_pair" "blur_tma" "warp_per_ray"; do
+for k in "umma_pair_selftest" "cips_cta_pair" "blur_tma" "warp_per_ray" "cips_backward_chain"; do
   C3D_EXPERIMENTAL=1 timeout 300 python -m pytest tests/test_gpu_parity.py -q -k "$k" > $O/r02a_pytest_$k.log 2>&1
   echo "experimental $k: exit $?" | tee -a $O/r02a_summary.txt
 done
@@ -30,6 +30,7 @@ timeout 300 python tools/bench_optim.py > $O/r02a_optim.jsonl 2>&1; echo "optim 
 for c in 3 5; do for o in fused torch; do
   timeout 600 python tools/bench_train_step.py --config $c --optim $o > $O/r02a_train_c${c}_$o.json 2> $O/r02a_train_c${c}_$o.err; echo "train step config $c optim $o: exit $?" | tee -a $O/r02a_summary.txt
 done; done
+timeout 600 python tools/bench_train_step.py --config 5 --optim fused --cips-backend fused > $O/r02a_train_c5_fused_cipsbwd.json 2> $O/r02a_train_c5_fused_cipsbwd.err
 timeout 600 python tools/bench_train_step.py --config 5 --optim fused --tf32 > $O/r02a_train_c5_fused_tf32.json 2> $O/r02a_train_c5_fused_tf32.err
 python bench.py --steps 20 --warmup 5 > $O/r02a_bench.json 2> $O/r02a_bench.err
 # the same contract line with the variants that passed above (only meaningful if their tests exited 0)
