@@ -25,6 +25,9 @@ def build(force=False, extra_defs=(), tag=""):
 def _build(OUT_DIR, force, extra_defs):
     LIB = os.path.join(OUT_DIR, "libcips3d_b200_emu.so")
     os.makedirs(OUT_DIR, exist_ok=True)
+    base_dir = globals()["OUT_DIR"]
+    if extra_defs and OUT_DIR != base_dir:
+        _build(base_dir, False, ())        # a variant only recompiles the sources that mention one of its defines
     srcs = sorted(glob.glob(os.path.join(CSRC, "*.cu"))) + [os.path.join(HERE, "emu_impl.cpp"), os.path.join(HERE, "emu_faults.cpp")]
     deps = srcs + glob.glob(os.path.join(CSRC, "*.cuh")) + glob.glob(os.path.join(HERE, "*.h")) + \
         glob.glob(os.path.join(ROOT, "include", "*.h")) + [os.path.abspath(__file__)]
@@ -35,6 +38,8 @@ def _build(OUT_DIR, force, extra_defs):
 
     def compile_one(src):
         obj = os.path.join(OUT_DIR, os.path.basename(src) + ".o")
+        if extra_defs and OUT_DIR != base_dir and not any(d.split("=")[0] in open(src).read() for d in extra_defs):
+            return os.path.join(base_dir, os.path.basename(src) + ".o")
         cmd = [gxx] + FLAGS + [f"-D{d}" for d in extra_defs] + ["-x", "c++", "-c", src, "-o", obj]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
