@@ -263,7 +263,7 @@ def main():
                    "kernel_impl": args.kernel_impl, "parallelism": f"dp{world} (no data-path collective)",
                    "l2": "per-step inputs (random draws ~%.0f MB) exceed the 126 MB L2" % (B * res * res * 48 * 4 / 1e6),
                    # opt-in kernel variants in effect for this run (all unset = the round-1 measured kernels)
-                   "variants": {k: os.environ[k] for k in ("C3D_CIPS_PAIR", "C3D_CIPS_CLUSTER", "C3D_RAY_MATH", "C3D_BLUR_TMA")
+                   "variants": {k: os.environ[k] for k in ("C3D_CIPS_PAIR", "C3D_CIPS_CLUSTER", "C3D_RAY_MATH", "C3D_BLUR_TMA", "C3D_STYLE_PREP")
                                 if os.environ.get(k)}},
         "e2e": {"value": e2e, "unit": "images/s", "h2d_bytes_per_step": int(B * (256 + 512) * 4),
                 "d2h_bytes_per_step": int(B * 3 * res * res * 4), "ms_per_step": ms_e2e / args.steps},

@@ -270,3 +270,63 @@ extern "C" int c3d_ema_update(const C3dOptTensor* tensors, int32_t n_tensors, do
   }
   return C3D_OK;
 }
+
+// ------------------------------------------------------------------------------------------------
+// Style prep of the CIPS MLP in one launch (exp/comm/models/mod_conv_fc.py:452-496, the per-image vectors the fused kernel
+// needs): for every layer l and image b
+//     s1p[l][b][k]   = modulation_l(w_b)[k] + 1 = sum_j Wm_l[k][j] w_b[j] + bm_l[k] + 1                       (k < in_l)
+//     demod[l][b][n] = rsqrt(sum_k (W_l[k][n] s1p[l][b][k])^2 + eps)                                            (n < 512)
+// The module computes this with ~7 torch launches per layer (126 per forward, 5 % of the step with the other glue);
+// here: grid (layers, B), one CTA per (layer, image).  C3D_STYLE_PREP=fused, opt-in until it has run on hardware.
+namespace c3d {
+namespace sprep {
+constexpr int kH = 512;
+__global__ void __launch_bounds__(512) style_prep_kernel(const C3dStylePrep a) {
+  __shared__ float wv[kH];
+  __shared__ float s1[kH];
+  const int l = blockIdx.x, b = blockIdx.y;
+  const int in_l = a.in_dim[l];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const float* w = a.style[l] + (size_t)b * a.style_dim;
+  for (int j = tid; j < a.style_dim; j += blockDim.x) wv[j] = w[j];
+  __syncthreads();
+  // s1p: one warp per output k, lanes over the style dimension (coalesced rows of the Linear weight (in_l, style_dim))
+  for (int k = warp; k < in_l; k += blockDim.x / 32) {
+    const float* row = a.mod_w[l] + (size_t)k * a.style_dim;
+    float acc = 0.f;
+    for (int j = lane; j < a.style_dim; j += 32) acc = fmaf(row[j], wv[j], acc);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (lane == 0) {
+      const float v = acc + a.mod_b[l][k] + 1.f;
+      s1[k] = v;
+      a.s1p[l][(size_t)b * in_l + k] = v;
+    }
+  }
+  __syncthreads();
+  // demod: thread per output column n, loop over k (coalesced rows of W (in_l, 512))
+  for (int n = tid; n < kH; n += blockDim.x) {
+    const float* W = a.w[l];
+    float acc = 0.f;
+    for (int k = 0; k < in_l; ++k) {
+      const float t = W[(size_t)k * kH + n] * s1[k];
+      acc = fmaf(t, t, acc);
+    }
+    a.demod[l][(size_t)b * kH + n] = rsqrtf(acc + a.eps);
+  }
+}
+}  // namespace sprep
+}  // namespace c3d
+
+extern "C" int c3d_cips_style_prep(const C3dStylePrep* a, int32_t batch, void* stream) {
+  C3D_CHECK_ARG(a, "style_prep: null argument");
+  C3D_CHECK_ARG(a->n_layers >= 1 && a->n_layers <= C3D_CIPS_MAX_LAYERS && a->style_dim >= 1 && a->style_dim <= 512, "style_prep: bad sizes");
+  for (int l = 0; l < a->n_layers; ++l) {
+    C3D_CHECK_ARG(a->style[l] && a->mod_w[l] && a->mod_b[l] && a->w[l] && a->s1p[l] && a->demod[l], "style_prep: null pointer for layer %d", l);
+    C3D_CHECK_ARG(a->in_dim[l] >= 1 && a->in_dim[l] <= 512, "style_prep: in_dim of layer %d", l);
+  }
+  if (batch == 0) return C3D_OK;
+  C3D_LAUNCH(c3d::sprep::style_prep_kernel, dim3(a->n_layers, batch), 512, 0, (cudaStream_t)stream, *a);
+  C3D_LAUNCH_CHECK();
+  return C3D_OK;
+}

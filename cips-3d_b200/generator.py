@@ -15,6 +15,7 @@ every entry point refuses non-CUDA tensors.
 """
 import logging
 import math
+import os
 from collections import OrderedDict
 
 import numpy as np
@@ -320,6 +321,9 @@ class CIPSNet(nn.Module):                       # generator.py:1009-1154
         return self.tanh(rgb) if not isinstance(rgb, int) else self.tanh(torch.zeros_like(input[..., :3]))
 
     def kernel_inputs(self, style_dict, n_blocks):
+        if (os.environ.get("C3D_STYLE_PREP", "torch") == "fused" and not torch.is_grad_enabled()
+                and all(b.mod1.use_style_fc and b.mod1.demodulate for b in self.network.values())):
+            return self.kernel_inputs_fused(style_dict, n_blocks)
         ws, s1ps, ds, rw, rb = [], [], [], [], []
         for idx, (name, block) in enumerate(self.network.items()):
             if idx >= n_blocks:
@@ -343,6 +347,22 @@ class CIPSNet(nn.Module):                       # generator.py:1009-1154
         ws, s1ps, ds, rw, rb = self.kernel_inputs(style_dict, n_blocks)     # s1p / demod stay in the torch graph (-> modulation, W)
         tensors = list(ws) + list(s1ps) + list(ds) + list(rw[3:n_blocks]) + list(rb[3:n_blocks])
         return ops.CipsMLPFunction.apply(input, n_blocks, 4, 3, *tensors)
+
+    def kernel_inputs_fused(self, style_dict, n_blocks):
+        """kernel_inputs with s1p / demod of all layers from one native launch (inference only; C3D_STYLE_PREP=fused)"""
+        mods, styles, rw, rb = [], [], [], []
+        for idx, (name, block) in enumerate(self.network.items()):
+            if idx >= n_blocks:
+                break
+            for j, mod in enumerate((block.mod1, block.mod2)):
+                mods.append(mod)
+                styles.append(style_dict[f'{block.name_prefix}_{j}'])
+            rw.append(self.to_rgbs[name].linear.weight)
+            rb.append(self.to_rgbs[name].linear.bias)
+        ws = [m.weight[0] for m in mods]
+        s1ps, ds = ops.cips_style_prep(styles, [m.modulation.weight for m in mods], [m.modulation.bias for m in mods], ws,
+                                       eps=mods[0].eps)
+        return ws, s1ps, ds, rw, rb
 
     def forward(self, input, style_dict, img_size=1024, **kwargs):
         """input (b, n, in) -> (b, n, 3)"""

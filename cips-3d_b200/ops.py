@@ -490,3 +490,24 @@ class CipsMLPFunction(Function):
             gRW.append(_bmm_f32(g16.transpose(1, 2), acts[2 * b + 1]).sum(0) * inv)      # (3, 512)
             gRB.append(g_pre.sum((0, 1)))
         return (dx * inv if dx is not None else None, None, None, None, *gW, *gS, *gD, *gRW, *gRB)
+
+
+def cips_style_prep(styles, mod_w, mod_b, weights, eps=1e-8):
+    """c3d_cips_style_prep: per layer l style (B,style_dim), modulation weight (in_l,style_dim) / bias (in_l), W (in_l,512)
+    -> lists s1p[l] (B,in_l), demod[l] (B,512) in ONE launch."""
+    lib = load()
+    L = len(weights)
+    B = styles[0].shape[0]
+    dev = styles[0].device
+    a = _lib.StylePrep(n_layers=L, style_dim=styles[0].shape[1], eps=float(eps))
+    keep, s1p, demod = [], [], []
+    for l in range(L):
+        ts = [_f32c(styles[l], "style"), _f32c(mod_w[l].detach(), "mod_w"), _f32c(mod_b[l].detach(), "mod_b"), _f32c(weights[l].detach(), "w")]
+        keep += ts
+        in_l = ts[3].shape[0]
+        s1p.append(torch.empty((B, in_l), device=dev, dtype=torch.float32))
+        demod.append(torch.empty((B, ts[3].shape[1]), device=dev, dtype=torch.float32))
+        a.style[l], a.mod_w[l], a.mod_b[l], a.w[l] = (ptr(t) for t in ts)
+        a.s1p[l], a.demod[l], a.in_dim[l] = ptr(s1p[l]), ptr(demod[l]), in_l
+    check(lib.c3d_cips_style_prep(C.byref(a), B, stream_ptr()), "c3d_cips_style_prep")
+    return s1p, demod

@@ -137,6 +137,22 @@ size_t c3d_cips_workspace_bytes(const C3dCipsParams* p);
 int c3d_cips_fwd(const C3dCipsParams* p, const C3dCipsWeights* w, const float* x, float* rgb,
                  float* hidden_out, void* workspace, size_t workspace_bytes, void* stream);
 
+/* Per-image vectors of c3d_cips_fwd for all layers in one launch (the module computes them with ~7 torch launches per layer):
+ * s1p[l] (B,in_l) = modulation_l(style_l) + 1, demod[l] (B,hidden) = rsqrt(sum_k (W_l[k][n] s1p[l][b][k])^2 + eps)
+ * (SinStyleMod, exp/comm/models/mod_conv_fc.py:452-496).  hidden = 512. */
+typedef struct C3dStylePrep {
+  const float* style[C3D_CIPS_MAX_LAYERS];  /* (B, style_dim) style vector of layer l                       */
+  const float* mod_w[C3D_CIPS_MAX_LAYERS];  /* modulation.weight (in_l, style_dim)                          */
+  const float* mod_b[C3D_CIPS_MAX_LAYERS];  /* modulation.bias (in_l)                                       */
+  const float* w[C3D_CIPS_MAX_LAYERS];      /* SinStyleMod.weight[0] (in_l, hidden)                         */
+  float* s1p[C3D_CIPS_MAX_LAYERS];          /* out (B, in_l)                                                */
+  float* demod[C3D_CIPS_MAX_LAYERS];        /* out (B, hidden)                                              */
+  int32_t in_dim[C3D_CIPS_MAX_LAYERS];
+  int32_t n_layers, style_dim;
+  float eps;                                /* 1e-8                                                         */
+} C3dStylePrep;
+int c3d_cips_style_prep(const C3dStylePrep* a, int32_t batch, void* stream);
+
 /* Training forward and the backward CHAIN of the fused CIPS MLP (first part).
  *   c3d_cips_fwd_train: c3d_cips_fwd that also writes every layer's output y_l (after LeakyReLU / residual) as the fp16
  *       values the next layer consumed: acts_f16 (n_layers, B, N, hidden), and the sign bits of z_l for the layers that add a

@@ -398,3 +398,23 @@ def test_emu_cips_fused_training_gradients():
             assert p.grad is None or float(p.grad.abs().max()) == 0, n
         else:
             assert rel_err(p.grad, gref.float())[1] < (2e-3 if n.startswith("to_rgbs") else 8e-2), n
+
+
+def test_emu_fused_style_prep_matches_the_module(monkeypatch):
+    """C3D_STYLE_PREP=fused: s1p / demod of all 18 layers from one launch (c3d_cips_style_prep) vs the module's torch ops, and
+    the fused forward fed by either."""
+    sd = O.synthetic_state_dict(O.generator_template(), seed=31)
+    g = torch.Generator().manual_seed(3)
+    w, x = torch.randn(3, 512, generator=g), torch.randn(3, 128, 32, generator=g)
+    with emulated(async_mode=2, sms=2) as pkg, torch.no_grad():
+        net = build_generator("cpu", sd).inr_net
+        style = {k: w for k in net.style_dim_dict}
+        a = net.kernel_inputs(style, 9)
+        monkeypatch.setenv("C3D_STYLE_PREP", "fused")
+        b = net.kernel_inputs(style, 9)
+        ra = pkg.ops.cips_forward(x, *a, impl=TC)
+        rb = pkg.ops.cips_forward(x, *b, impl=TC)
+    for l in range(18):
+        assert a[1][l].shape == b[1][l].shape and a[2][l].shape == b[2][l].shape
+        assert rel_err(b[1][l], a[1][l])[0] < 1e-5 and rel_err(b[2][l], a[2][l])[0] < 1e-5, l
+    assert rel_err(rb, ra)[0] < 1e-4

@@ -19,6 +19,7 @@ timeout 300 python tools/time_kernels.py > $O/r02a_time_kernels_default.log 2>&1
 C3D_CIPS_PAIR=1 timeout 300 python tools/time_kernels.py > $O/r02a_time_kernels_pair.log 2>&1; echo "pair timing: exit $?" | tee -a $O/r02a_summary.txt
 timeout 300 python tools/time_forward.py 16 > $O/r02a_time_forward_default.log 2>&1
 C3D_CIPS_PAIR=1 timeout 300 python tools/time_forward.py 16 > $O/r02a_time_forward_pair.log 2>&1
+C3D_STYLE_PREP=fused timeout 300 python tools/time_forward.py 16 > $O/r02a_time_forward_styleprep.log 2>&1
 C3D_RAY_MATH=warp timeout 300 python tools/time_forward.py 16 > $O/r02a_time_forward_raywarp.log 2>&1; echo "ray warp-math timing: exit $?" | tee -a $O/r02a_summary.txt
 # HBM-bound ops
 timeout 300 python tools/bench_disc_ops.py > $O/r02a_disc_ops_default.jsonl 2>&1
@@ -35,7 +36,7 @@ timeout 600 python tools/bench_train_step.py --config 5 --optim fused --tf32 > $
 python bench.py --steps 20 --warmup 5 > $O/r02a_bench.json 2> $O/r02a_bench.err
 # the same contract line with the variants that passed above (only meaningful if their tests exited 0)
 C3D_CIPS_PAIR=1 C3D_RAY_MATH=warp timeout 600 python bench.py --steps 20 --warmup 5 --no-cpu-baseline --no-eager > $O/r02a_bench_variants.json 2> $O/r02a_bench_variants.err
-tail -n 3 $O/r02a_time_kernels_default.log $O/r02a_time_kernels_pair.log $O/r02a_time_forward_default.log $O/r02a_time_forward_pair.log $O/r02a_time_forward_raywarp.log
+tail -n 3 $O/r02a_time_kernels_default.log $O/r02a_time_kernels_pair.log $O/r02a_time_forward_default.log $O/r02a_time_forward_pair.log $O/r02a_time_forward_raywarp.log $O/r02a_time_forward_styleprep.log
 grep -h "blur" $O/r02a_disc_ops_default.jsonl $O/r02a_disc_ops_blur_tma.jsonl | cut -c1-200
 cat $O/r02a_optim.jsonl $O/r02a_time_pigan.jsonl | cut -c1-300
 cat $O/r02a_train_c*.json 2>/dev/null | cut -c1-400
