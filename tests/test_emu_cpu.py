@@ -417,4 +417,4 @@ def test_emu_fused_style_prep_matches_the_module(monkeypatch):
     for l in range(18):
         assert a[1][l].shape == b[1][l].shape and a[2][l].shape == b[2][l].shape
         assert rel_err(b[1][l], a[1][l])[0] < 1e-5 and rel_err(b[2][l], a[2][l])[0] < 1e-5, l
-    assert rel_err(rb, ra)[0] < 1e-4
+    assert rel_err(rb, ra)[0] < 1e-3        # 1e-7 differences in s1p / demod flip fp16 roundings of the per-image weight tiles
