@@ -15,7 +15,7 @@ CIPS_MAX_LAYERS = 18
 EXPORTS = ("c3d_version", "c3d_last_error", "c3d_device_supported", "c3d_launch_count",
            "c3d_ray_siren_workspace_bytes",
            "c3d_ray_siren_fwd", "c3d_cips_workspace_bytes", "c3d_cips_fwd", "c3d_bias_act",
-           "c3d_upfirdn2d", "c3d_selftest_umma", "c3d_selftest_umma_pair", "c3d_debug_cips_tile_order",
+           "c3d_upfirdn2d", "c3d_selftest_umma", "c3d_selftest_umma_pair", "c3d_debug_cips_tile_order", "c3d_debug_ray_math_mode",
            "c3d_optim_workspace_bytes", "c3d_grad_norm", "c3d_adam_ema_step", "c3d_ema_update",
            "c3d_pigan_workspace_bytes", "c3d_pigan_render_fwd", "c3d_cips_fwd_train", "c3d_cips_bwd_workspace_bytes", "c3d_cips_bwd", "c3d_cips_style_prep")
 

@@ -85,6 +85,7 @@ struct KArgs {
   const float* bl;            // (32) color_layer_linear bias
   int G;                      // rays per group
   int groups_per_img, total_groups;
+  const float* w_sigma;       // (128) final_layer weight, fp32 (MATH = 2 only: sigma head in the E1 epilogue)
 };
 
 __device__ __forceinline__ float fast_sin(float x) { return __sinf(x); }
@@ -127,6 +128,19 @@ __device__ __forceinline__ void mma_split3(uint32_t d_tmem, uint32_t a_hi, uint3
   for (int k = 0; k < K / 16; ++k) umma_ts_w(d_tmem, a_hi + 8 * k, b_lo_lo + kstep * k, dhi, idesc, 1);
 }
 
+// s1.14 fixed point through the float adder: x + 1.5*2^9 has ulp 2^-14 for |x| <= 1, so the low 16 bits of its pattern
+// relative to 0x44400000 are round(x * 2^14) as an int16 (RN-even, like the adder)
+__device__ __forceinline__ uint32_t pack_q14(float x0, float x1) {
+  const uint32_t b0 = __float_as_uint(__fadd_rn(x0, 768.f)), b1 = __float_as_uint(__fadd_rn(x1, 768.f));
+  return (b0 & 0xFFFFu) | (b1 << 16);
+}
+__device__ __forceinline__ float unpack_q14_lo(uint32_t u) {
+  return __fsub_rn(__uint_as_float(0x44400000u + (uint32_t)((int32_t)(u << 16) >> 16)), 768.f);
+}
+__device__ __forceinline__ float unpack_q14_hi(uint32_t u) {
+  return __fsub_rn(__uint_as_float(0x44400000u + (uint32_t)((int32_t)u >> 16)), 768.f);
+}
+
 // alpha of one sample (pigan_utils.py:246-251): 1 - exp(-delta * clamp(sigma + noise))
 __device__ __forceinline__ float sample_alpha(float delta, float sigma, float noise, int clamp_mode) {
   const float sn = __fadd_rn(sigma, noise);
@@ -141,6 +155,14 @@ __device__ __forceinline__ float sample_alpha(float delta, float sigma, float no
 //           serial shared-memory loops of MATH 0 (28 % of a ray group's time in the round-1 trace) disappear.  Needs
 //           2S <= 32 (hierarchical: two rays share a warp in the resampling step).  C3D_RAY_MATH=warp; emulation-verified,
 //           not yet timed on hardware.
+// MATH = 2: MATH 1 plus the two heads taken off the tensor-core chain.  sigma = final_layer(h1) is a 128-term fp32 dot
+//           product accumulated in the layer-1 epilogue while the sines are still in registers (two threads per row, 64
+//           columns each), so the colour MMA shrinks from N = 80 to N = 64.  color_layer_linear (64 -> 32) is linear, so it
+//           commutes with compositing: the 64 colour sines of every sample stay in shared memory (s1.14 fixed point) and
+//           the per-ray warp composites them and applies Wl once per RAY instead of once per SAMPLE -- the fourth MMA phase
+//           and its epilogue (a d_ready round trip per pass on the serial per-slot chain) are gone.  The per-point debug
+//           outputs do not exist in this form (the host falls back to MATH 1).  C3D_RAY_MATH=fold; emulation-verified,
+//           not yet timed on hardware.
 template <int MATH>
 __global__ void __launch_bounds__(640, 1) ray_siren_tc_kernel(const KArgs a) {
   C3D_DYN_SMEM(uint8_t, smem_raw);
@@ -150,7 +172,10 @@ __global__ void __launch_bounds__(640, 1) ray_siren_tc_kernel(const KArgs a) {
   const int S = p.num_steps, G = a.G;
   const bool hier = p.hierarchical != 0;
   const int nS = hier ? 2 * S : S;
-  const int mma_phases = hier ? 8 : 4;     // per pass: layer 0, layer 1, colour+sigma, colour linear
+  constexpr bool WARP = MATH >= 1, FOLD = MATH == 2;
+  constexpr int kPassPhases = FOLD ? 3 : 4;  // per pass: layer 0, layer 1, colour(+sigma), [colour linear]
+  constexpr int kNc = FOLD ? 64 : kN2;       // N of the colour-sine MMA
+  const int mma_phases = hier ? 2 * kPassPhases : kPassPhases;
 
   if (threadIdx.x == 0) {
     mbar_init(&s.w_full, 1);
@@ -182,7 +207,7 @@ __global__ void __launch_bounds__(640, 1) ray_siren_tc_kernel(const KArgs a) {
       const uint32_t wb = smem_u32(s.w);
       const uint32_t dhi = umma_desc_hi(128);
       const uint32_t w1h = umma_desc_lo(wb + kOffW1h, 128 * 16), w1l = umma_desc_lo(wb + kOffW1l, 128 * 16);
-      const uint32_t w2h = umma_desc_lo(wb + kOffW2h, kN2 * 16), w2l = umma_desc_lo(wb + kOffW2l, kN2 * 16);
+      const uint32_t w2h = umma_desc_lo(wb + kOffW2h, kNc * 16), w2l = umma_desc_lo(wb + kOffW2l, kNc * 16);
       const uint32_t w3h = umma_desc_lo(wb + kOffW3h, 32 * 16), w3l = umma_desc_lo(wb + kOffW3l, 32 * 16);
       uint32_t par[2] = {0, 0};
       int done[2] = {0, 0};
@@ -200,7 +225,7 @@ __global__ void __launch_bounds__(640, 1) ray_siren_tc_kernel(const KArgs a) {
           if (done[sl] < total && __all_sync(0xffffffffu, mbar_test(&s.a_ready[sl], par[sl]))) {
             par[sl] ^= 1;
             tc_fence_after();
-            const int layer = done[sl] & 3;
+            const int layer = FOLD ? done[sl] % 3 : (done[sl] & 3);
             if (lane == 0) RTRACE(done[sl] / mma_phases, 1, (uint32_t)(sl << 8 | (done[sl] % mma_phases)));
             if (elect_one()) {
               uint32_t a_hi = tmem + (uint32_t)(sl * 256), a_lo = a_hi + 64;
@@ -213,8 +238,8 @@ __global__ void __launch_bounds__(640, 1) ray_siren_tc_kernel(const KArgs a) {
               asm volatile("" : "+r"(bh), "+r"(bl), "+r"(a_hi), "+r"(a_lo));
               if (layer == 0) mma_split3<128, 16>(d, a_hi, a_lo, bh, bl, dhi);
               else if (layer == 1) mma_split3<128, 128>(d, a_hi, a_lo, bh, bl, dhi);
-              else if (layer == 2) mma_split3<kN2, 128>(d, a_hi, a_lo, bh, bl, dhi);
-              else mma_split3<32, 64>(d, a_hi, a_lo, bh, bl, dhi);
+              else if (layer == 2) mma_split3<kNc, 128>(d, a_hi, a_lo, bh, bl, dhi);
+              else if (!FOLD) mma_split3<32, 64>(d, a_hi, a_lo, bh, bl, dhi);
               tc_commit(&s.d_ready[sl]);
             }
             __syncwarp();
@@ -259,6 +284,8 @@ __global__ void __launch_bounds__(640, 1) ray_siren_tc_kernel(const KArgs a) {
     const bool row_in_group = g_row < G;
     const int g_el = stid / nS, e_el = stid - g_el * nS;  // (ray, element) view used by the merge phases
     int cur_img = -1;
+    if (FOLD && stid < 128) sm.abuf[stid] = __ldg(a.w_sigma + stid);   // visible after the first image-constants barrier
+    if (FOLD) mbar_wait(&s.w_full, 0);   // the workers read Wl^T from the bulk-loaded blob themselves: observe its barrier
 #ifdef C3D_RAY_STAGGER_NS   // start slot 1 half a pass late so its MMA phases fall into slot 0's worker phases
     if (sl == 1) __nanosleep(C3D_RAY_STAGGER_NS);
 #endif
@@ -341,12 +368,14 @@ __global__ void __launch_bounds__(640, 1) ray_siren_tc_kernel(const KArgs a) {
         stamp(5);
         {
           uint32_t accA[16], accB[16];
+          float psig = 0.f;       // MATH 2: this thread's 64 columns of final_layer (fp32, before the fp16 split)
           auto e1 = [&](const uint32_t (&acc)[16], int c) {
             float v[16];
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
               const float2 g2 = sm.l1[half * 64 + c + j];
               v[j] = fast_sin(fmaf(__uint_as_float(acc[j]), g2.x, g2.y));
+              if (FOLD) psig = fmaf(v[j], sm.abuf[half * 64 + c + j], psig);
             }
             store_a16(a_hi + (uint32_t)(half * 32 + c / 2), a_lo + (uint32_t)(half * 32 + c / 2), v);
           };
@@ -362,6 +391,7 @@ __global__ void __launch_bounds__(640, 1) ray_siren_tc_kernel(const KArgs a) {
           e1(accA, 32);
           tc_wait_ld();
           e1(accB, 48);
+          if (FOLD) sm.fbuf[half * kRows + row] = psig;   // read by the row's other thread after the next d_ready
         }
         stamp(6);
         signal_a();
@@ -369,8 +399,34 @@ __global__ void __launch_bounds__(640, 1) ray_siren_tc_kernel(const KArgs a) {
         wait_d();
         stamp(7);
         float sigma = 0.f;
-        {
-          uint32_t accA[16], accB[16], accS[16];
+        if (FOLD) {
+          // colour sines stay in shared memory as s1.14 fixed point (the feat area viewed as [2*kRows][33] pairs:
+          // |error| <= 2^-15, eight times tighter than fp16 near +-1 where sines spend their time); the 64 -> 32
+          // color_layer_linear is applied once per ray to the composited sines (linear in the features)
+          uint32_t accA[16], accB[16];
+          tmem_ld16(dcol + (uint32_t)(half * 32), accA);
+          tmem_ld16(dcol + (uint32_t)(half * 32 + 16), accB);
+          tc_wait_ld();
+          if (half == 1) {
+            sigma = __fadd_rn(__fadd_rn(sm.fbuf[row], sm.fbuf[kRows + row]), __ldg(a.b_sigma));
+            (pass == 0 ? sm.sig_c : sm.sig_f)[row] = sigma;
+          }
+          uint32_t* crow = reinterpret_cast<uint32_t*>(&sm.feat[0][0][0]) + ((pass == 0 ? kRows : 0) + row) * 33 + half * 16;
+          auto e2 = [&](const uint32_t (&acc)[16], int c) {
+#pragma unroll
+            for (int j = 0; j < 16; j += 2) {
+              const float2 g0 = sm.lc[half * 32 + c + j], g1 = sm.lc[half * 32 + c + j + 1];
+              crow[(c + j) >> 1] = pack_q14(fast_sin(fmaf(__uint_as_float(acc[j]), g0.x, g0.y)),
+                                            fast_sin(fmaf(__uint_as_float(acc[j + 1]), g1.x, g1.y)));
+            }
+          };
+          e2(accA, 0);
+          e2(accB, 16);
+          stamp(8);
+          stamp(9);
+        } else {
+          uint32_t accS[16];
+          uint32_t accA[16], accB[16];
           auto e2 = [&](const uint32_t (&acc)[16], int c) {
             float v[16];
 #pragma unroll
@@ -391,6 +447,7 @@ __global__ void __launch_bounds__(640, 1) ray_siren_tc_kernel(const KArgs a) {
           e2(accA, 0);
           e2(accB, 16);
         }
+        if (!FOLD) {
         stamp(8);
         signal_a();
         // ---------------- E3: D(32) -> + bias -> features to shared memory
@@ -410,11 +467,12 @@ __global__ void __launch_bounds__(640, 1) ray_siren_tc_kernel(const KArgs a) {
           }
           if (dbg && pt_ok && half == 1) dbg[(ro_row * S + s_row) * kOutC + kFeat] = sigma;
         }
+        }  // !FOLD
         tc_fence_before();
         slot_sync();
         stamp(10);
         // ---------------- importance resampling, all threads (generator_nerf_inr.py:537-598, pigan_utils.py:164-209)
-        if (MATH == 1 && pass == 0 && hier) {
+        if (WARP && pass == 0 && hier) {
           // ---- warp per ray, two rays per warp (lanes 0-15 / 16-31; S <= 16): lane e = coarse sample e
           const unsigned full = 0xffffffffu;
           const int sub = lane >> 4, e = lane & 15, ns = S - 2;
@@ -511,7 +569,7 @@ __global__ void __launch_bounds__(640, 1) ray_siren_tc_kernel(const KArgs a) {
       }
       stamp(11);
       // ---------------- merge (stable rank sort of the nS depths of each ray), generator.py:1733-1738
-      if (MATH == 1) {
+      if (WARP) {
         // ---- warp per ray: lane e = element e of cat([fine, coarse]) for the sort, lane = channel for the compositing
         const unsigned full = 0xffffffffu;
         const float* featf = &sm.feat[0][0][0];
@@ -556,9 +614,30 @@ __global__ void __launch_bounds__(640, 1) ray_siren_tc_kernel(const KArgs a) {
           if (p.last_back && e == nS - 1) w += 1.f - wsum;
           const int frow = src < S ? rc0 + src : kRows + rc0 + src - S;
           float acc = 0.f;
+          if (FOLD) {
+            // composite the 64 colour sines (lane = sine pair), then color_layer_linear once per ray:
+            //   sum_i w_i (Wl c_i + bl) = Wl (sum_i w_i c_i) + bl sum_i w_i
+            const uint32_t* cq = reinterpret_cast<const uint32_t*>(featf);
+            float a0 = 0.f, a1 = 0.f;
 #pragma unroll 4
-          for (int i = 0; i < nS; ++i)
-            acc = fmaf(__shfl_sync(full, w, i), featf[__shfl_sync(full, frow, i) * 33 + lane], acc);
+            for (int i = 0; i < nS; ++i) {
+              const float wi = __shfl_sync(full, w, i);
+              const uint32_t u = cq[__shfl_sync(full, frow, i) * 33 + lane];
+              a0 = fmaf(wi, unpack_q14_lo(u), a0);
+              a1 = fmaf(wi, unpack_q14_hi(u), a1);
+            }
+            const float* wlt = reinterpret_cast<const float*>(s.w + kOffW3h);   // fp32 Wl^T [64][32] (prep, fold mode)
+            acc = __ldg(a.bl + lane) * (p.last_back ? 1.f : wsum);
+#pragma unroll 8
+            for (int k2 = 0; k2 < 32; ++k2) {
+              acc = fmaf(wlt[(2 * k2) * 32 + lane], __shfl_sync(full, a0, k2), acc);
+              acc = fmaf(wlt[(2 * k2 + 1) * 32 + lane], __shfl_sync(full, a1, k2), acc);
+            }
+          } else {
+#pragma unroll 4
+            for (int i = 0; i < nS; ++i)
+              acc = fmaf(__shfl_sync(full, w, i), featf[__shfl_sync(full, frow, i) * 33 + lane], acc);
+          }
           if (p.white_back) acc += 1.f - wsum;
           a.io.pixels_fea[ro * kFeat + lane] = acc;
           if (act && a.io.weights) a.io.weights[ro * nS + e] = w;
@@ -661,15 +740,21 @@ __device__ __forceinline__ void put_split(uint8_t* blob, int off_hi, int off_lo,
   reinterpret_cast<__half*>(blob + off_lo)[e] = l;
 }
 
-__global__ void ray_prep_kernel(C3dSirenWeights w, int B, uint8_t* blob, ImgConsts* consts) {
+// fold != 0 (MATH 2): the colour-sine matrix alone as N = 64, and fp32 Wl^T [64][32] where the W3 tiles would be
+__global__ void ray_prep_kernel(C3dSirenWeights w, int B, uint8_t* blob, ImgConsts* consts, int fold) {
   const int tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
   for (int i = tid; i < 128 * 128; i += nth) put_split(blob, kOffW1h, kOffW1l, 128, i / 128, i % 128, w.w1[i] * kWScale);
-  for (int i = tid; i < kN2 * 128; i += nth) {
-    const int n = i / 128, k = i % 128;
-    const float v = n < 64 ? w.wc[n * 128 + k] : (n == 64 ? w.w_sigma[k] : 0.f);
-    put_split(blob, kOffW2h, kOffW2l, kN2, n, k, v * kWScale);
+  if (fold) {
+    for (int i = tid; i < 64 * 128; i += nth) put_split(blob, kOffW2h, kOffW2l, 64, i / 128, i % 128, w.wc[i] * kWScale);
+    for (int i = tid; i < 32 * 64; i += nth) reinterpret_cast<float*>(blob + kOffW3h)[(i % 64) * 32 + i / 64] = w.wl[i];
+  } else {
+    for (int i = tid; i < kN2 * 128; i += nth) {
+      const int n = i / 128, k = i % 128;
+      const float v = n < 64 ? w.wc[n * 128 + k] : (n == 64 ? w.w_sigma[k] : 0.f);
+      put_split(blob, kOffW2h, kOffW2l, kN2, n, k, v * kWScale);
+    }
+    for (int i = tid; i < 32 * 64; i += nth) put_split(blob, kOffW3h, kOffW3l, 32, i / 64, i % 64, w.wl[i] * kWScale);
   }
-  for (int i = tid; i < 32 * 64; i += nth) put_split(blob, kOffW3h, kOffW3l, 32, i / 64, i % 64, w.wl[i] * kWScale);
   const float sc = 2.f / 0.24f;
   for (int i = tid; i < B * 128; i += nth) {
     const int b = i / 128, j = i % 128;
@@ -691,6 +776,9 @@ __global__ void ray_prep_kernel(C3dSirenWeights w, int B, uint8_t* blob, ImgCons
 
 using namespace c3d;
 using namespace c3d::rtc;
+
+static std::atomic<int> g_ray_math_mode{-1};
+extern "C" int c3d_debug_ray_math_mode(void) { return g_ray_math_mode.load(); }
 
 struct RayWs {
   size_t blob, consts, total;
@@ -735,7 +823,14 @@ int c3d_ray_siren_fwd_tc(const C3dRayParams* p, const C3dSirenWeights* w, const 
   }
   const int sms = c3d_device_sm_count(dev);
   uint8_t* base = (uint8_t*)workspace;
-  C3D_LAUNCH(ray_prep_kernel, 64, 256, 0, st, *w, p->batch, base + ws.blob, (ImgConsts*)(base + ws.consts));
+  // C3D_RAY_MATH=warp: warp-per-ray math (needs 2S <= 32 samples per warp); =fold: warp math + the sigma head in the E1
+  // epilogue and color_layer_linear applied after compositing (3 MMA phases per pass instead of 4; not with the
+  // per-point debug outputs); default: the round-1 block-wide form
+  const char* rm = getenv("C3D_RAY_MATH");
+  const bool warp_ok = p->num_steps * (p->hierarchical ? 2 : 1) <= 32 && (!p->hierarchical || p->num_steps <= 16);
+  const bool fold_math = rm && rm[0] == 'f' && warp_ok && !io->dbg_coarse && !io->dbg_fine;
+  const bool warp_math = rm && (rm[0] == 'w' || rm[0] == 'f') && warp_ok;
+  C3D_LAUNCH(ray_prep_kernel, 64, 256, 0, st, *w, p->batch, base + ws.blob, (ImgConsts*)(base + ws.consts), fold_math ? 1 : 0);
   C3D_LAUNCH_CHECK();
   KArgs ka = {};
   ka.p = *p;
@@ -747,20 +842,21 @@ int c3d_ray_siren_fwd_tc(const C3dRayParams* p, const C3dSirenWeights* w, const 
   ka.groups_per_img = (p->n_rays + ka.G - 1) / ka.G;
   ka.total_groups = p->batch * ka.groups_per_img;
   ka.b_sigma = w->b_sigma;
+  ka.w_sigma = w->w_sigma;
   const size_t smem = sizeof(Smem) + 1024;
   static std::atomic<unsigned long long> attr_set{0};     // per device, once
   if (!(attr_set.load() >> (dev & 63) & 1ull)) {
     C3D_CUDA(cudaFuncSetAttribute(ray_siren_tc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     C3D_CUDA(cudaFuncSetAttribute(ray_siren_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    C3D_CUDA(cudaFuncSetAttribute(ray_siren_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_set.fetch_or(1ull << (dev & 63));
   }
   int grid = (ka.total_groups + 1) / 2;
   if (grid > sms) grid = sms;
   if (grid < 1) grid = 1;
-  // C3D_RAY_MATH=warp: warp-per-ray math (needs 2S <= 32 samples per warp); default: the round-1 block-wide form
-  const char* rm = getenv("C3D_RAY_MATH");
-  const bool warp_math = rm && rm[0] == 'w' && p->num_steps * (p->hierarchical ? 2 : 1) <= 32 && (!p->hierarchical || p->num_steps <= 16);
-  if (warp_math) C3D_LAUNCH(ray_siren_tc_kernel<1>, grid, 640, smem, st, ka);
+  g_ray_math_mode.store(fold_math ? 2 : (warp_math ? 1 : 0));
+  if (fold_math) C3D_LAUNCH(ray_siren_tc_kernel<2>, grid, 640, smem, st, ka);
+  else if (warp_math) C3D_LAUNCH(ray_siren_tc_kernel<1>, grid, 640, smem, st, ka);
   else C3D_LAUNCH(ray_siren_tc_kernel<0>, grid, 640, smem, st, ka);
   C3D_LAUNCH_CHECK();
   return C3D_OK;

@@ -278,6 +278,12 @@ int c3d_selftest_umma_pair(const float* a, const float* b, float* d, int32_t n, 
  * ---------------------------------------------------------------------------------- */
 int c3d_debug_cips_tile_order(uint16_t* order_full32, uint16_t* order_in4);
 
+/* Which form of the fused renderer kernel the last c3d_ray_siren_fwd call on this process launched:
+ * 0 block-wide ray math (default), 1 C3D_RAY_MATH=warp, 2 C3D_RAY_MATH=fold; -1 before the first call.
+ * The opt-in forms fall back (S too large, per-point debug outputs requested); tests use this to make sure they
+ * exercised the form they name. */
+int c3d_debug_ray_math_mode(void);
+
 #ifdef __cplusplus
 }
 #endif

@@ -65,7 +65,7 @@ def test_emu_umma_pair_selftest(mode, n, k):
     assert (d.double() - ref).abs().max().item() < 1e-5 * ref.abs().max().item()
 
 
-def _render(pkg, name, impl):
+def _render(pkg, name, impl, debug=True, **extra):
     sd, zs, draws, kw, meta, ref = load_gen_case(name)
     G = build_generator("cpu", sd)
     R, S, hier = meta["img_size"], kw["num_steps"], kw["hierarchical_sample"]
@@ -78,7 +78,7 @@ def _render(pkg, name, impl):
             draws["pdf_u"] if hier else None, draws["noise_c"] if hier else None, draws["noise_f"],
             img_size=R, fov=kw["fov"], ray_start=kw["ray_start"], ray_end=kw["ray_end"], num_steps=S,
             hierarchical_sample=hier, clamp_mode=kw.get("clamp_mode", "relu"), noise_std=meta["nerf_noise"],
-            white_back=kw.get("white_back", False), last_back=kw.get("last_back", False), impl=impl, debug=True)
+            white_back=kw.get("white_back", False), last_back=kw.get("last_back", False), impl=impl, debug=debug, **extra)
     return out, ref
 
 
@@ -110,6 +110,22 @@ def test_emu_ray_siren_tc_warp_per_ray_math(name, mode, monkeypatch):
     with emulated(async_mode=MODES[mode], seed=5) as pkg:
         out, ref = _render(pkg, name, TC)
     _check_render(out, ref)
+
+
+@pytest.mark.parametrize("mode", ["lazy", "random"])
+@pytest.mark.parametrize("name", GEN_CASES)
+def test_emu_ray_siren_tc_fold_math(name, mode, monkeypatch):
+    """C3D_RAY_MATH=fold: warp-per-ray math, the sigma head as an fp32 dot product in the layer-1 epilogue and
+    color_layer_linear applied once per ray to the composited colour sines (3 MMA phases per pass instead of 4).  The
+    per-point debug outputs do not exist in this form (the library falls back to warp math when they are requested), so
+    the check is on the outputs a caller sees: pixel features, depth, weights.  Not yet timed on hardware."""
+    monkeypatch.setenv("C3D_RAY_MATH", "fold")
+    with emulated(async_mode=MODES[mode], seed=7) as pkg:
+        out, ref = _render(pkg, name, TC, debug=False, want_depth=True, want_weights=True)
+        assert _emu.emu_lib().c3d_debug_ray_math_mode() == 2      # the fold form ran, not a fallback
+    frac, worst = close_frac(out["pixels_fea"], ref["pixels_fea"], 1e-3)
+    assert frac >= 0.995, (frac, worst)
+    assert close_frac(out["depth"][..., None], ref["depth"][..., None], 1e-3)[0] >= 0.995
 
 
 @pytest.mark.parametrize("name", ["r16_trained_noise", "r8_nohier_s24"])

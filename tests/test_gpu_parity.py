@@ -52,7 +52,7 @@ def test_umma_selftest(pkg, n, k, a_in_tmem):
 
 
 # ------------------------------------------------------------------ renderer vs reference goldens
-def _render_case(pkg, name, impl, dtype_oracle=None):
+def _render_case(pkg, name, impl, dtype_oracle=None, debug=True):
     sd, zs, draws, kw, meta, ref = load_gen_case(name)
     G = build_generator(DEV, sd)
     G.impl = impl
@@ -68,7 +68,8 @@ def _render_case(pkg, name, impl, dtype_oracle=None):
             draws["noise_c"].to(DEV) if hier else None, draws["noise_f"].to(DEV),
             img_size=R, fov=kw["fov"], ray_start=kw["ray_start"], ray_end=kw["ray_end"], num_steps=S,
             hierarchical_sample=hier, clamp_mode=kw.get("clamp_mode", "relu"), noise_std=meta["nerf_noise"],
-            white_back=kw.get("white_back", False), last_back=kw.get("last_back", False), impl=impl, debug=True)
+            white_back=kw.get("white_back", False), last_back=kw.get("last_back", False), impl=impl, debug=debug,
+            want_depth=True)
     return out, ref, G, style
 
 
@@ -187,6 +188,19 @@ def test_renderer_warp_per_ray_math_matches_reference_golden(pkg, name, monkeypa
     out, ref, _, _ = _render_case(pkg, name, pkg._lib.IMPL_TC)
     assert rel_err(out["coarse"].cpu(), ref["coarse"])[0] < 2e-4
     assert rel_err(out["all_z"].cpu(), ref["all_z"])[0] < 2e-4
+    frac, worst = close_frac(out["pixels_fea"], ref["pixels_fea"], 1e-3)
+    assert frac >= 0.995, f"only {frac:.4f} of rays within 1e-3 (worst {worst:.3e})"
+    assert close_frac(out["depth"][..., None], ref["depth"][..., None], 1e-3)[0] >= 0.995
+
+
+@experimental
+@pytest.mark.parametrize("name", GEN_CASES)
+def test_renderer_fold_math_matches_reference_golden(pkg, name, monkeypatch):
+    """C3D_RAY_MATH=fold (sigma head in the layer-1 epilogue, color_layer_linear after compositing) against the
+    reference goldens; caller-visible outputs only (the form has no per-point debug outputs)."""
+    monkeypatch.setenv("C3D_RAY_MATH", "fold")
+    out, ref, _, _ = _render_case(pkg, name, pkg._lib.IMPL_TC, debug=False)
+    assert pkg._lib.load().c3d_debug_ray_math_mode() == 2
     frac, worst = close_frac(out["pixels_fea"], ref["pixels_fea"], 1e-3)
     assert frac >= 0.995, f"only {frac:.4f} of rays within 1e-3 (worst {worst:.3e})"
     assert close_frac(out["depth"][..., None], ref["depth"][..., None], 1e-3)[0] >= 0.995

@@ -10,7 +10,7 @@ mkdir -p gpurun_out
 O=gpurun_out
 python __graft_entry__.py > $O/r02a_build.log 2>&1
 timeout 600 python -m pytest tests -m gpu -x -q > $O/r02a_pytest_gpu.log 2>&1; echo "default gpu suite: exit $?" | tee $O/r02a_summary.txt
-for k in "umma_pair_selftest" "cips_cta_pair" "blur_tma" "warp_per_ray" "cips_backward_chain"; do
+for k in "umma_pair_selftest" "cips_cta_pair" "blur_tma" "warp_per_ray" "fold_math" "cips_backward_chain"; do
   C3D_EXPERIMENTAL=1 timeout 300 python -m pytest tests/test_gpu_parity.py -q -k "$k" > $O/r02a_pytest_$k.log 2>&1
   echo "experimental $k: exit $?" | tee -a $O/r02a_summary.txt
 done
@@ -21,6 +21,7 @@ timeout 300 python tools/time_forward.py 16 > $O/r02a_time_forward_default.log 2
 C3D_CIPS_PAIR=1 timeout 300 python tools/time_forward.py 16 > $O/r02a_time_forward_pair.log 2>&1
 C3D_STYLE_PREP=fused timeout 300 python tools/time_forward.py 16 > $O/r02a_time_forward_styleprep.log 2>&1
 C3D_RAY_MATH=warp timeout 300 python tools/time_forward.py 16 > $O/r02a_time_forward_raywarp.log 2>&1; echo "ray warp-math timing: exit $?" | tee -a $O/r02a_summary.txt
+C3D_RAY_MATH=fold timeout 300 python tools/time_forward.py 16 > $O/r02a_time_forward_rayfold.log 2>&1; echo "ray fold-math timing: exit $?" | tee -a $O/r02a_summary.txt
 # HBM-bound ops
 timeout 300 python tools/bench_disc_ops.py > $O/r02a_disc_ops_default.jsonl 2>&1
 C3D_BLUR_TMA=1 timeout 300 python tools/bench_disc_ops.py > $O/r02a_disc_ops_blur_tma.jsonl 2>&1; echo "blur_tma bench: exit $?" | tee -a $O/r02a_summary.txt
@@ -36,7 +37,7 @@ timeout 600 python tools/bench_train_step.py --config 5 --optim fused --tf32 > $
 python bench.py --steps 20 --warmup 5 > $O/r02a_bench.json 2> $O/r02a_bench.err
 # the same contract line with the variants that passed above (only meaningful if their tests exited 0)
 C3D_CIPS_PAIR=1 C3D_RAY_MATH=warp timeout 600 python bench.py --steps 20 --warmup 5 --no-cpu-baseline --no-eager > $O/r02a_bench_variants.json 2> $O/r02a_bench_variants.err
-tail -n 3 $O/r02a_time_kernels_default.log $O/r02a_time_kernels_pair.log $O/r02a_time_forward_default.log $O/r02a_time_forward_pair.log $O/r02a_time_forward_raywarp.log $O/r02a_time_forward_styleprep.log
+tail -n 3 $O/r02a_time_kernels_default.log $O/r02a_time_kernels_pair.log $O/r02a_time_forward_default.log $O/r02a_time_forward_pair.log $O/r02a_time_forward_raywarp.log $O/r02a_time_forward_rayfold.log $O/r02a_time_forward_styleprep.log
 grep -h "blur" $O/r02a_disc_ops_default.jsonl $O/r02a_disc_ops_blur_tma.jsonl | cut -c1-200
 cat $O/r02a_optim.jsonl $O/r02a_time_pigan.jsonl | cut -c1-300
 cat $O/r02a_train_c*.json 2>/dev/null | cut -c1-400

@@ -19,3 +19,4 @@ cap cips_default  cips_tc_kernel      C3D_X=0            -- python tools/prof_ci
 cap cips_pair     cips_tc_kernel      C3D_CIPS_PAIR=1    -- python tools/prof_cips.py cips 16 256
 cap ray_default   ray_siren_tc_kernel C3D_X=0            -- python tools/prof_cips.py ray 16 256
 cap ray_warpmath  ray_siren_tc_kernel C3D_RAY_MATH=warp  -- python tools/prof_cips.py ray 16 256
+cap ray_foldmath  ray_siren_tc_kernel C3D_RAY_MATH=fold  -- python tools/prof_cips.py ray 16 256
