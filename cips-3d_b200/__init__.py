@@ -9,12 +9,14 @@ Layout:
   comm_utils.py    camera sampling / look-at matrices (host-side mirror, tiny)
   generator.py     GeneratorNerfINR, GeneratorNerfINR_freeze_NeRF, NeRFNetwork, CIPSNet, ...
   discriminator.py Discriminator_MultiScale(_Aux) and its layers
+  inference.py     gen_images / to_pil / tensor_to_PIL: uint8 leaves the GPU (one native conversion kernel, pinned double buffer)
 """
 from . import _lib  # noqa: F401
 from . import ops  # noqa: F401
 from . import optim  # noqa: F401
 from .optim import EMA, FusedAdam  # noqa: F401
 from . import pigan  # noqa: F401
+from . import inference  # noqa: F401
 from .pigan import ImplicitGenerator3d, SPATIALSIRENBASELINE, TALLSIREN  # noqa: F401
 from .generator import (CIPSNet, FiLMLayer, GeneratorNerfINR, GeneratorNerfINR_freeze_NeRF,  # noqa: F401
                         MultiHeadMappingNetwork, NeRFNetwork, SinBlock, SinStyleMod, ToRGB)

@@ -511,3 +511,31 @@ def cips_style_prep(styles, mod_w, mod_b, weights, eps=1e-8):
         a.s1p[l], a.demod[l], a.in_dim[l] = ptr(s1p[l]), ptr(demod[l]), in_l
     check(lib.c3d_cips_style_prep(C.byref(a), B, stream_ptr()), "c3d_cips_style_prep")
     return s1p, demod
+
+
+_U8_MODES = {"save_image": 0, "tensor_to_pil": 1, "to_pil": 2}
+
+
+def image_to_u8(img, mode="save_image", value_range=(-1, 1)):
+    """(B, C, H, W) or (C, H, W) fp32 generator output -> (B, H, W, C) / (H, W, C) uint8 on the device, bit-identical to
+    what the reference's inference scripts hand to PIL (include/cips3d_b200.h, c3d_image_to_u8):
+      'save_image'     torchvision save_image(img, path, normalize=True, value_range=value_range)  gen_images.py:64
+      'tensor_to_pil'  st_web.py:44-46          'to_pil'  comm_utils.py:21-24
+    The result is what `Image.fromarray(...)` takes after a `.cpu().numpy()` of 1 byte per sample."""
+    lib = load()
+    if mode not in _U8_MODES:
+        raise ValueError(f"image_to_u8: unknown mode {mode!r} (one of {sorted(_U8_MODES)})")
+    if img.dtype != torch.float32:
+        raise _lib.C3dError(f"img: expected float32, got {img.dtype}")
+    if img.dim() not in (3, 4):
+        raise ValueError(f"image_to_u8: expected (B, C, H, W) or (C, H, W), got {tuple(img.shape)}")
+    x4 = img if img.dim() == 4 else img[None]
+    B, Cn, H, W = x4.shape
+    # the generator returns an NCHW *view* of the CIPS kernel's (B, H*W, 3) output: convert it in place of a re-layout
+    cl = x4.permute(0, 2, 3, 1).is_contiguous() and not x4.is_contiguous()
+    src = x4.permute(0, 2, 3, 1) if cl else x4.contiguous()
+    out = torch.empty((B, H, W, Cn), device=img.device, dtype=torch.uint8)
+    lo, hi = value_range
+    check(lib.c3d_image_to_u8(ptr(src), ptr(out), B, Cn, H, W, int(cl), _U8_MODES[mode], float(lo), float(hi),
+                              stream_ptr()), "c3d_image_to_u8")
+    return out if img.dim() == 4 else out[0]

@@ -169,6 +169,26 @@ int c3d_cips_bwd(const C3dCipsParams* p, const C3dCipsWeights* w, const void* ac
                  const float* g_rgb_pre, void* dz_f16, float* dx, void* workspace, size_t workspace_bytes, void* stream);
 
 /* ------------------------------------------------------------------------------------
+ * Image export for the inference paths: generator output (batch, channels, height, width)
+ * fp32 -> (batch, height, width, channels) uint8 on the device, bit-identical to what the reference's scripts hand to
+ * PIL, so an inference batch leaves the GPU as 1 byte per sample.  mode:
+ *   C3D_U8_SAVE_IMAGE    torchvision save_image(img, path, normalize=True, value_range=(lo, hi)) on ONE image per file --
+ *                        exp/cips3d/scripts/gen_images.py:64, sample_images.py:73:
+ *                        y = (clamp(x, lo, hi) - lo) / max(hi - lo, 1e-5); u8 = trunc(clamp(y * 255 + 0.5, 0, 255)).
+ *                        The division is a true fp32 division (torch CPU); torch CUDA multiplies by the fp32 reciprocal,
+ *                        identical for power-of-two ranges such as the reference's (-1, 1).
+ *   C3D_U8_TENSOR_TO_PIL exp/cips3d/models/st_web.py:44-46: y = x * 0.5 + 0.5; u8 = trunc(clamp(y * 255 + 0.5, 0, 255))
+ *   C3D_U8_TO_PIL        exp/comm/comm_utils.py:21-24 + torchvision to_pil_image: u8 = trunc(((x + 1) * 0.5) * 255);
+ *                        inputs outside [-1, 1] saturate here (numpy's float -> uint8 cast is undefined there)
+ * channels_last != 0: img is already (batch, height, width, channels) in memory -- the layout the CIPS kernel writes, of
+ * which the generator returns an NCHW view -- and the conversion is a flat stream.
+ * lo / hi are read by mode 0 only.  NaN -> 0.  channels 1..4.  Empty batches / images are a no-op.
+ * ---------------------------------------------------------------------------------- */
+enum { C3D_U8_SAVE_IMAGE = 0, C3D_U8_TENSOR_TO_PIL = 1, C3D_U8_TO_PIL = 2 };
+int c3d_image_to_u8(const float* img, uint8_t* out, int32_t batch, int32_t channels, int32_t height, int32_t width,
+                    int32_t channels_last, int32_t mode, double lo, double hi, void* stream);
+
+/* ------------------------------------------------------------------------------------
  * Discriminator ops.  Same semantics as the reference's two pybind11 modules:
  *   fused.fused_bias_act(input, bias, refer, act, grad, alpha, scale)
  *       exp/comm/op/fused_bias_act.cpp:11-20, fused_bias_act_kernel.cu:19-50

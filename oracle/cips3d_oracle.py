@@ -759,3 +759,35 @@ def pigan_forward(sd, z, draws, *, img_size, fov, ray_start, ray_end, num_steps,
     if return_all:
         return pixels, py, dict(coarse=coarse, all_z=all_z, rgb=rgb, depth=depth, weights=w)
     return pixels, py
+
+
+# --------------------------------------------------------------------------------------
+# Image export of the inference paths: fp32 image(s) in [-1, 1] -> uint8, channels last.
+#   'save_image'     exp/cips3d/scripts/gen_images.py:64, sample_images.py:73:
+#                    torchvision.utils.save_image(img, path, normalize=True, value_range=(-1, 1)) on one image:
+#                    make_grid.norm_ip  img.clamp_(low, high); img.sub_(low).div_(max(high - low, 1e-5))
+#                    save_image         grid.mul(255).add_(0.5).clamp_(0, 255).permute(1, 2, 0).to("cpu", torch.uint8)
+#                    (torchvision is a dependency of the reference, not vendored in it; pinned to the installed
+#                    torchvision 0.26 through a lossless PNG round trip in tests/test_image_export_cpu.py)
+#   'tensor_to_pil'  exp/cips3d/models/st_web.py:44-46:  img * 0.5 + 0.5, then the same mul / add / clamp / cast
+#   'to_pil'         exp/comm/comm_utils.py:21-24: (frame + 1) * 0.5, then torchvision to_pil_image:
+#                    (npimg * 255).astype(np.uint8)  -- a truncation without rounding or clamping
+# Accepts (C, H, W) or (B, C, H, W); returns (H, W, C) or (B, H, W, C).
+# --------------------------------------------------------------------------------------
+def image_to_u8(img, mode="save_image", value_range=(-1, 1)):
+    x = img.detach().to("cpu", torch.float32).clone()
+    if mode == "save_image":
+        low, high = value_range
+        x.clamp_(min=low, max=high)
+        x.sub_(low).div_(max(high - low, 1e-5))
+        y = x.mul(255).add_(0.5).clamp_(0, 255)
+    elif mode == "tensor_to_pil":
+        x = x * 0.5 + 0.5
+        y = x.mul(255).add_(0.5).clamp_(0, 255)
+    elif mode == "to_pil":
+        x = (x + 1) * 0.5
+        y = torch.from_numpy(x.numpy() * 255).clamp_(0, 255)      # in range for tanh outputs; the cast alone is undefined outside
+    else:
+        raise ValueError(mode)
+    perm = (1, 2, 0) if y.dim() == 3 else (0, 2, 3, 1)
+    return y.permute(*perm).to(torch.uint8).contiguous()

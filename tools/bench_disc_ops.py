@@ -42,6 +42,22 @@ for (B, C, H) in [(16, 128, 256), (16, 256, 128), (16, 512, 64)]:
         Ho = H + pad[0] + pad[1] - 3
         gb = (x.numel() + B * C * Ho * Ho) * 4 / 1e9
         out.append(dict(op=f"upfirdn2d blur pad{pad} (C3D_BLUR_TMA={VARIANTS})", shape=[B, C, H, H], ms=ms, gbs=gb / ms * 1e3, frac=gb / ms * 1e3 / peak))
+# image export: 4*C bytes read + C written per pixel; the torch-op chain the reference runs beside it
+for (B, H) in [(16, 256), (64, 256), (16, 512)]:
+    nhwc = torch.tanh(torch.randn(B, H, H, 3, device=dev))
+    for name, x in (("generator layout (NCHW view of NHWC)", nhwc.permute(0, 3, 1, 2)), ("NCHW", nhwc.permute(0, 3, 1, 2).contiguous())):
+        ms = timeit(lambda: ops.image_to_u8(x))
+        gb = x.numel() * 5 / 1e9
+        out.append(dict(op=f"image_to_u8 save_image, {name}", shape=[B, 3, H, H], ms=ms, gbs=gb / ms * 1e3, frac=gb / ms * 1e3 / peak))
+
+    def torch_chain():      # make_grid.norm_ip + save_image's conversion, batched (the reference does it image by image)
+        t = x.clone()
+        t.clamp_(min=-1, max=1)
+        t.sub_(-1).div_(2)
+        return t.mul(255).add_(0.5).clamp_(0, 255).permute(0, 2, 3, 1).to(torch.uint8)
+    ms = timeit(torch_chain)
+    out.append(dict(op="image_to_u8: torch op chain (clone, clamp_, sub_, div_, mul, add_, clamp_, permute+to)", shape=[B, 3, H, H], ms=ms,
+                    gbs=x.numel() * 5 / 1e9 / ms * 1e3, frac=x.numel() * 5 / 1e9 / ms * 1e3 / peak))
 for r in out:
     print(json.dumps(r))
 print(json.dumps(dict(hbm_peak_gbs=peak, note="algorithmic bytes (read x + write y [+ read ref]) / CUDA-event median; L2 flushed between reps")))

@@ -920,6 +920,19 @@ inline float __fadd_rn(float a, float b) { return a + b; }
 inline float __fsub_rn(float a, float b) { return a - b; }
 inline float __fmul_rn(float a, float b) { return a * b; }
 inline float __fdiv_rn(float a, float b) { return a / b; }
+inline unsigned __float2uint_rz(float a) { return a != a || a <= 0.f ? 0u : (a >= 4294967040.f ? 0xFFFFFFFFu : (unsigned)a); }
+inline float __fadd_rz(float a, float b) {      // exact in double for the magnitudes used here, then truncate toward zero
+  const double d = (double)a + (double)b;
+  float f = (float)d;
+  if (fabs((double)f) > fabs(d)) f = nextafterf(f, 0.f);
+  return f;
+}
+inline unsigned __byte_perm(unsigned x, unsigned y, unsigned s) {
+  const unsigned long long v = ((unsigned long long)y << 32) | x;
+  unsigned r = 0;
+  for (int i = 0; i < 4; ++i) r |= (unsigned)((v >> (8 * ((s >> (4 * i)) & 7))) & 0xFF) << (8 * i);
+  return r;
+}
 inline float __fsqrt_rn(float a) { return sqrtf(a); }
 inline float __fdividef(float a, float b) { return a / b; }
 inline float __sinf(float a) { return sinf(a); }
