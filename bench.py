@@ -140,6 +140,7 @@ def main():
     ap.add_argument("--res", type=int, default=R)
     ap.add_argument("--kernel-impl", default=os.environ.get("C3D_IMPL", "tc"), choices=["tc", "simt"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-u8", action="store_true", help="skip the uint8-delivery end-to-end leg")
     ap.add_argument("--no-eager", action="store_true", help="skip the eager-torch-on-the-same-GPU comparison")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
@@ -299,6 +300,33 @@ def main():
         finally:
             G.force_torch_path = False
             torch.cuda.empty_cache()
+    if world == 1 and not args.no_u8:
+        # the evaluation-dump form of the same end-to-end step (inference.gen_images: SURVEY 8(f) rank 4): the images leave
+        # the GPU as uint8, converted by c3d_image_to_u8 -- 1 byte per sample over PCIe instead of 4.  Extra information,
+        # measured after every contract number above is already taken.
+        try:
+            u8_host = torch.empty((B, res, res, 3), dtype=torch.uint8).pin_memory()
+
+            def step_u8():
+                with torch.no_grad():
+                    z = {k: v.to(dev, non_blocking=True) for k, v in zs_host.items()}
+                    img, _ = G(z, img_size=res, nerf_noise=0.0, **kw)
+                    u8_host.copy_(ops.image_to_u8(img), non_blocking=True)
+
+            for _ in range(2):
+                step_u8()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(args.steps):
+                step_u8()
+            e1.record()
+            torch.cuda.synchronize()
+            line["e2e_uint8"] = {"value": B * args.steps / (e0.elapsed_time(e1) / 1e3), "unit": "images/s",
+                                 "h2d_bytes_per_step": int(B * (256 + 512) * 4), "d2h_bytes_per_step": int(B * 3 * res * res),
+                                 "note": "same step, result delivered as (B, H, W, 3) uint8 = save_image's bytes"}
+        except Exception as ex:
+            line["e2e_uint8"] = {"unavailable": str(ex)[:120]}
     if world == 1 and not args.no_cpu_baseline:
         v, cores, sample = cpu_reference_rate(20.0)
         line["cpu_baseline"] = {"value": v, "unit": "images/s", "cores": cores, "kind": "port", "sample": sample}

@@ -59,3 +59,47 @@ def test_two_rank_gloo_sharding():
     res = out.get()
     assert res["same_weights"] and res["distinct_latents"]
     assert res["tmax"] == 11.0 and res["global_batch"] == 8
+
+
+class _StubG:                       # eval / get_zs / __call__ -> (imgs, pitch_yaw), like GeneratorNerfINR in gen_images
+    def eval(self):
+        return self
+
+    def get_zs(self, b):
+        return {"z": torch.randn(b, 4)}
+
+    def __call__(self, zs, forward_points=None, **kw):
+        b, r = zs["z"].shape[0], kw["img_size"]
+        return torch.tanh(torch.randn(b, r, r, 3)).permute(0, 3, 1, 2), torch.zeros(b, 2)
+
+
+def _gen_worker(rank, world, port, fake_dir, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from _emu import emulated
+    import cips3d_b200.inference as inf
+    torch.manual_seed(50 + rank)
+    with emulated(async_mode=0):    # the uint8 conversion kernel runs on the CPU emulation; the sharding logic is what is tested
+        n = inf.gen_images(rank, world, _StubG(), {"fov": 12}, fake_dir, num_imgs=10, img_size=8, batch_size=4, ext="png")
+    out.put((rank, n))
+    dist.destroy_process_group()
+
+
+def test_two_rank_gen_images_shards_the_dump(tmp_path):
+    """gen_images.py:30-73 under world_size 2: rank 0 creates the directory, both ranks pass the barrier, every rank writes
+    its interleaved share (idx_b * batch_size + idx_i * world_size + rank) and together they cover 0..N-1 exactly once."""
+    ctx = mp.get_context("spawn")
+    out = ctx.SimpleQueue()
+    port = _free_port()
+    fake = str(tmp_path / "fake")
+    procs = [ctx.Process(target=_gen_worker, args=(r, 2, port, fake, out)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(timeout=300)
+        assert p.exitcode == 0
+    counts = dict(out.get() for _ in range(2))
+    assert counts == {0: 6, 1: 6}                       # ceil(10 / 4) = 3 iterations x (4 // 2) images per rank
+    assert sorted(os.listdir(fake)) == [f"{i:0>5}.png" for i in range(12)]
