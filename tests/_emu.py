@@ -11,6 +11,8 @@ import importlib.util
 import os
 import sys
 
+import torch
+
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 _spec = importlib.util.spec_from_file_location("c3d_build_emu", os.path.join(ROOT, "tools", "emu", "build_emu.py"))
 build_emu = importlib.util.module_from_spec(_spec)
@@ -36,6 +38,25 @@ def _cpu_ptr(t):
     return t.data_ptr()
 
 
+_POISON = os.environ.get("C3D_EMU_POISON", "1") != "0"
+
+
+def _poisoned(alloc):
+    """torch.empty / empty_like inside the emulation context return POISONED memory (NaN for floating types, 0x7B bytes
+    otherwise): fresh CPU pages are zero, a GPU caching allocator's are not -- a kernel that reads workspace or output
+    memory it never wrote (relying on zeros) must fail its parity check here, as compute-sanitizer's initcheck would flag it."""
+    def wrapper(*a, **k):
+        t = alloc(*a, **k)
+        if t.device.type == "cpu" and t.numel() and not t.is_quantized and t.layout == torch.strided:
+            with torch.no_grad():
+                if t.is_floating_point():
+                    t.fill_(float("nan"))
+                elif t.dtype in (torch.uint8, torch.int8, torch.int16, torch.int32, torch.int64):
+                    t.fill_(0x7B)
+        return t
+    return wrapper
+
+
 @contextlib.contextmanager
 def emulated(async_mode=2, seed=1, preempt_permille=20, sms=2):
     """async_mode: 0 = asynchronous ops complete at issue, 1 = as late as possible, 2 = random (seeded)."""
@@ -49,7 +70,11 @@ def emulated(async_mode=2, seed=1, preempt_permille=20, sms=2):
     L._lib = L.bind(lib)
     L.ptr = ops.ptr = optim.ptr = _cpu_ptr
     L.stream_ptr = ops.stream_ptr = optim.stream_ptr = lambda: None
+    allocs = (torch.empty, torch.empty_like)
+    if _POISON:
+        torch.empty, torch.empty_like = _poisoned(torch.empty), _poisoned(torch.empty_like)
     try:
         yield pkg
     finally:
+        torch.empty, torch.empty_like = allocs
         L._lib, L.ptr, L.stream_ptr, ops.ptr, ops.stream_ptr, optim.ptr, optim.stream_ptr = saved

@@ -471,7 +471,11 @@ inline int launch(const char* name, dim3 grid, dim3 block, size_t dyn_smem, int 
   const int nthreads = (int)(block.x * block.y * block.z);
   const long long nblocks = (long long)grid.x * grid.y * grid.z;
   if (grid.x % l.cluster) { fprintf(stderr, "c3d_emu: grid.x %% cluster != 0\n"); abort(); }
+#if defined(__SANITIZE_ADDRESS__)
+  const size_t smem_alloc = dyn_smem ? dyn_smem : 1;      // exact: the first byte past the request is an ASan redzone
+#else
   const size_t smem_alloc = ((dyn_smem + 1023) / 1024 + 1) * 1024;
+#endif
   std::vector<Cta> ctas(l.cluster);
   for (int r = 0; r < l.cluster; ++r) {
     uint8_t* raw;

@@ -11,7 +11,10 @@ ARGS=("$@")
 [ ${#ARGS[@]} -eq 0 ] && ARGS=(tests/test_emu_cpu.py tests/test_optim_cpu.py tests/test_image_export_cpu.py)
 ASAN=$(/usr/bin/gcc -print-file-name=libasan.so)
 echo "== alignment"
-C3D_EMU_SANITIZE=alignment python -m pytest "${ARGS[@]}" -x -q 2>&1 | tail -3
+# the fault-injection tests are excluded: the emulator's error path unwinds across fiber stacks, which the sanitizer runtime
+# does not survive
+SKIP="not detects and not reports_broken"
+C3D_EMU_SANITIZE=alignment python -m pytest "${ARGS[@]}" -x -q -k "$SKIP" 2>&1 | tail -3
 echo "== address"
 LD_PRELOAD=$(readlink -f "$ASAN") ASAN_OPTIONS=detect_leaks=0:detect_stack_use_after_return=0:halt_on_error=1 \
-  C3D_EMU_SANITIZE=address python -m pytest "${ARGS[@]}" -x -q 2>&1 | tail -30
+  C3D_EMU_SANITIZE=address python -m pytest "${ARGS[@]}" -x -q -k "$SKIP" 2>&1 | tail -30
