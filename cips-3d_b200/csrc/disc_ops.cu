@@ -285,7 +285,9 @@ extern "C" int c3d_bias_act(const float* x, const float* bias, const float* ref,
   cudaStream_t st = (cudaStream_t)stream;
   bool vec = size_x % 4 == 0 && (!bias || step_b % 4 == 0) && ((uintptr_t)x % 16 == 0) &&
              ((uintptr_t)y % 16 == 0) && (!ref || (uintptr_t)ref % 16 == 0);
-  const int sms = 148;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  const int sms = c3d_device_sm_count(dev);
   if (vec) {
     long long nv = size_x / 4;
     int grid = (int)(nv / 256 + 1 < (long long)sms * 16 ? nv / 256 + 1 : (long long)sms * 16);

@@ -1,0 +1,73 @@
+"""The whole training step of the reference (exp/cips3d/scripts/train.py:326-491: D step with R1 through the double backward
+of the native D ops, G step, gradient clipping, Adam, EMA) as tools/bench_train_step.py builds it, executed on the CPU
+emulation of the kernels at 16 x 16 -- the same closure the GPU benchmark times.  It pins, inside a real step rather than
+on isolated tensors:
+  * the fused optimiser tail against torch.optim.Adam + clip_grad_norm_ + the EMA loop (next-step losses agree to 1e-5),
+  * the native CIPS training path (stash forward + tcgen05 backward chain + GEMM weight gradients) against torch autograd
+    (the weights it produces give the same next-step losses to 1e-4),
+  * that the non-frozen recipe (aux images, NeRF gradients through the torch restatement) runs and moves the NeRF weights."""
+import importlib.util
+import math
+import os
+
+import pytest
+import torch
+
+from _emu import emulated
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def bts():
+    spec = importlib.util.spec_from_file_location("c3d_bench_train_step", os.path.join(ROOT, "tools", "bench_train_step.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+@pytest.fixture()
+def cpu_modules(monkeypatch):
+    """The modules refuse CPU tensors by design (no CPU fallback in the product); the emulated library takes host pointers."""
+    import cips3d_b200
+    monkeypatch.setattr(cips3d_b200.generator, "_require_cuda", lambda *a, **k: None)
+    monkeypatch.setattr(cips3d_b200.discriminator, "_require_cuda", lambda *a, **k: None)
+    return cips3d_b200
+
+
+def _run(bts, frozen, optim, backend, steps=2):
+    cfg = dict(res=16, batch=2, frozen=frozen, aux=not frozen, diffaug=frozen, grad_points=256, forward_points=256,
+               warmup_D=frozen)
+    torch.manual_seed(0)
+    with emulated(async_mode=0, sms=2):
+        step, mods = bts.build_step(cfg, torch.device("cpu"), optim, backend)
+        before = {k: v.detach().clone() for k, v in mods["G"].named_parameters()}
+        ema_before = {k: v.detach().clone() for k, v in mods["G_ema"].state_dict().items()}
+        losses = [tuple(float(x) for x in step(it)) for it in range(steps)]
+    moved = {k for k, v in mods["G"].named_parameters() if not torch.equal(v, before[k])}
+    ema_moved = any(not torch.equal(v, ema_before[k]) for k, v in mods["G_ema"].state_dict().items())
+    return losses, moved, ema_moved
+
+
+def test_train_step_frozen_recipe_fused_vs_torch_paths(bts, cpu_modules):
+    """configs 4-5 (GeneratorNerfINR_freeze_NeRF + diffaug D): three ways through the same two steps."""
+    base, moved, ema_moved = _run(bts, True, "fused", "torch")
+    assert all(math.isfinite(x) for pair in base for x in pair)
+    assert moved and all(not k.startswith(("siren.", "mapping_network_nerf.")) for k in moved), "frozen NeRF parameters moved"
+    assert any(k.startswith("inr_net.") for k in moved) and ema_moved
+    ref, moved_ref, _ = _run(bts, True, "torch", "torch")
+    assert moved_ref == moved
+    assert base[0] == pytest.approx(ref[0], rel=1e-6)               # same graph, same draws
+    assert base[1] == pytest.approx(ref[1], rel=1e-5)               # after one FusedAdam vs torch Adam update of D and G
+    nat, moved_nat, _ = _run(bts, True, "fused", "fused")
+    assert moved_nat == moved
+    assert nat[0] == pytest.approx(base[0], rel=1e-5)
+    assert nat[1] == pytest.approx(base[1], rel=1e-4)               # after an update from the native CIPS backward
+
+
+def test_train_step_full_recipe_with_aux_images(bts, cpu_modules):
+    """config 3 (GeneratorNerfINR, train_aux_img, nerf_noise schedule): NeRF and mapping weights receive gradients."""
+    losses, moved, ema_moved = _run(bts, False, "fused", "torch", steps=1)
+    assert all(math.isfinite(x) for x in losses[0]) and ema_moved
+    for prefix in ("siren.", "mapping_network_nerf.", "inr_net.", "mapping_network_inr.", "aux_to_rbg."):
+        assert any(k.startswith(prefix) for k in moved), prefix

@@ -43,40 +43,19 @@ def requires_grad(model, flag):
         p.requires_grad_(flag)
 
 
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--config", type=int, default=3, choices=sorted(CONFIGS))
-    ap.add_argument("--aux", action="store_true", help="config 4 with train_aux_img / aux discriminator on (BASELINE's wording)")
-    ap.add_argument("--steps", type=int, default=5)
-    ap.add_argument("--warmup", type=int, default=2)
-    ap.add_argument("--optim", default="fused", choices=["fused", "torch"])
-    ap.add_argument("--batch", type=int, default=None)
-    ap.add_argument("--cips-backend", default="torch", choices=["torch", "fused"],
-                    help="fused: CIPSNet.train_backend = 'fused' (native forward + backward chain, fp16 library GEMMs for dW)")
-    ap.add_argument("--tf32", action="store_true", help="allow TF32 in the torch autograd GEMMs / cuDNN convs of the training graph "
-                    "(NOT the reference's numerics: torch defaults to fp32 matmuls); measures what the library path can give")
-    args = ap.parse_args()
-    torch.backends.cuda.matmul.allow_tf32 = bool(args.tf32)
-    torch.backends.cudnn.allow_tf32 = bool(args.tf32)
-    cfg = dict(CONFIGS[args.config])
-    if args.aux:
-        cfg["aux"] = True
-    if args.batch:
-        cfg["batch"] = args.batch
-    rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
-    dev = torch.device("cuda", local)
-    torch.cuda.set_device(dev)
-    ddp = world > 1
-    if ddp:
-        torch.distributed.init_process_group("nccl")
-    torch.manual_seed(1234 + rank)
-
+def build_step(cfg, dev, optim="fused", cips_backend="torch", ddp=False, local=0, g_cfg=None, d_kwargs=None):
+    """Modules, optimisers and the step closure of one configuration on device `dev`.  Separate from main() so that
+    tests/test_train_step_cpu.py can execute the very same step on the CPU emulation of the kernels (tiny sizes)."""
+    class _A:        # the two switches the step reads
+        pass
+    args = _A()
+    args.optim, args.cips_backend = optim, cips_backend
     G_cls = cips3d_b200.GeneratorNerfINR_freeze_NeRF if cfg["frozen"] else cips3d_b200.GeneratorNerfINR
-    gcfg = {k: (dict(v) if isinstance(v, dict) else v) for k, v in O.G_CFG.items()}
+    gcfg = {k: (dict(v) if isinstance(v, dict) else v) for k, v in (g_cfg or O.G_CFG).items()}
     G = G_cls(**gcfg, device=dev).to(dev)
     G.load_state_dict(O.synthetic_state_dict(O.generator_template(), seed=1234, sigma_bias=0.3))
-    D = cips3d_b200.Discriminator_MultiScale_Aux(diffaug=cfg["diffaug"], max_size=1024, channel_multiplier=2, first_downsample=False,
-                                                 stddev_group=0).to(dev)
+    D = cips3d_b200.Discriminator_MultiScale_Aux(**dict(dict(diffaug=cfg["diffaug"], max_size=1024, channel_multiplier=2,
+                                                             first_downsample=False, stddev_group=0), **(d_kwargs or {}))).to(dev)
     G.inr_net.train_backend = args.cips_backend
     G_ema = copy.deepcopy(G)
     G_run, D_run = G, D
@@ -148,6 +127,40 @@ def main():
                 for k in sd:
                     td[k].data.copy_(td[k].data * 0.999 + sd[k].data * (1 - 0.999))
         return d_loss.detach(), g_loss.detach()
+
+    return step, dict(G=G, D=D, G_ema=G_ema, opt_G=opt_G, opt_D=opt_D, G_cls=G_cls)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--config", type=int, default=3, choices=sorted(CONFIGS))
+    ap.add_argument("--aux", action="store_true", help="config 4 with train_aux_img / aux discriminator on (BASELINE's wording)")
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=2)
+    ap.add_argument("--optim", default="fused", choices=["fused", "torch"])
+    ap.add_argument("--batch", type=int, default=None)
+    ap.add_argument("--cips-backend", default="torch", choices=["torch", "fused"],
+                    help="fused: CIPSNet.train_backend = 'fused' (native forward + backward chain, fp16 library GEMMs for dW)")
+    ap.add_argument("--tf32", action="store_true", help="allow TF32 in the torch autograd GEMMs / cuDNN convs of the training graph "
+                    "(NOT the reference's numerics: torch defaults to fp32 matmuls); measures what the library path can give")
+    args = ap.parse_args()
+    torch.backends.cuda.matmul.allow_tf32 = bool(args.tf32)
+    torch.backends.cudnn.allow_tf32 = bool(args.tf32)
+    cfg = dict(CONFIGS[args.config])
+    if args.aux:
+        cfg["aux"] = True
+    if args.batch:
+        cfg["batch"] = args.batch
+    rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
+    dev = torch.device("cuda", local)
+    torch.cuda.set_device(dev)
+    ddp = world > 1
+    if ddp:
+        torch.distributed.init_process_group("nccl")
+    torch.manual_seed(1234 + rank)
+    step, mods = build_step(cfg, dev, args.optim, args.cips_backend, ddp, local)
+    G_cls = mods["G_cls"]
+    R, B = cfg["res"], cfg["batch"]
 
     for it in range(args.warmup):
         step(it)
