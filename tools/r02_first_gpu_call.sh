@@ -26,7 +26,9 @@ C3D_RAY_MATH=fold timeout 300 python tools/time_forward.py 16 > $O/r02a_time_for
 timeout 300 python tools/bench_disc_ops.py > $O/r02a_disc_ops_default.jsonl 2>&1
 C3D_BLUR_TMA=1 timeout 300 python tools/bench_disc_ops.py > $O/r02a_disc_ops_blur_tma.jsonl 2>&1; echo "blur_tma bench: exit $?" | tee -a $O/r02a_summary.txt
 C3D_EXPERIMENTAL=1 timeout 300 python -m pytest tests/test_pigan_gpu.py -q > $O/r02a_pytest_pigan.log 2>&1; echo "pigan (simt + tc): exit $?" | tee -a $O/r02a_summary.txt
-timeout 300 python tools/time_pigan.py 64 4 > $O/r02a_time_pigan.jsonl 2>&1; echo "pigan timing: exit $?" | tee -a $O/r02a_summary.txt
+for impl in simt tc tc-pair; do
+  timeout 300 python tools/time_pigan.py 64 4 $impl >> $O/r02a_time_pigan.jsonl 2>> $O/r02a_time_pigan.err; echo "pigan timing $impl: exit $?" | tee -a $O/r02a_summary.txt
+done
 timeout 300 python tools/bench_optim.py > $O/r02a_optim.jsonl 2>&1; echo "optim bench: exit $?" | tee -a $O/r02a_summary.txt
 # train-step configurations of BASELINE.json (3: r128 non-frozen + aux, 5: r256 finetune recipe), fused vs torch optimiser tail
 for c in 3 5; do for o in fused torch; do

@@ -19,7 +19,10 @@ kw = dict(O.PIGAN_KWARGS)
 z = torch.randn(B, 256, device=dev)
 mac_per_point = 3 * 256 + 7 * 256 * 256 + 256 + 259 * 256 + 3 * 256
 flop = 2.0 * mac_per_point * 2 * kw["num_steps"] * R * R * B
-for impl in ("simt", "tc", "tc-pair"):
+# argv[3]: comma-separated subset -- run the hardware-unvalidated tcgen05 forms in their own processes (a protocol error
+# traps the CUDA context and would take the remaining timings along)
+impls = sys.argv[3].split(",") if len(sys.argv) > 3 else ("simt", "tc", "tc-pair")
+for impl in impls:
     os.environ["C3D_PIGAN_IMPL"] = impl.split("-")[0]
     os.environ["C3D_PIGAN_PAIR"] = "1" if impl.endswith("pair") else "0"
     with torch.no_grad():
