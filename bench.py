@@ -33,8 +33,12 @@ def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
         d = json.load(open(p))
-        return d["bf16_tflops"], d["hbm_gbs"], "measured (MEASURED_PEAKS.json, burst bf16)"
-    return 1590.0, 6650.0, "fallback (B200_PROFILING.md)"
+        # the kernels are timed by events inside the long timed step loop (power-limited regime): the contract's denominator
+        # for that is the SUSTAINED dense-bf16 figure; the burst figure rides along as peak_burst / frac_of_burst
+        if d.get("bf16_tflops_sustained"):
+            return d["bf16_tflops_sustained"], d["hbm_gbs"], "measured (MEASURED_PEAKS.json, sustained bf16: kernel timed inside a long step)", d["bf16_tflops"]
+        return d["bf16_tflops"], d["hbm_gbs"], "measured (MEASURED_PEAKS.json, burst bf16)", d["bf16_tflops"]
+    return 1590.0, 6650.0, "fallback (B200_PROFILING.md)", 1590.0
 
 
 class ClockSampler(threading.Thread):
@@ -232,7 +236,7 @@ def main():
     imgs = B * world * args.steps
     value = imgs / (ms / 1e3)
     e2e = imgs / (ms_e2e / 1e3)
-    peak_tf, peak_hbm, peak_src = peaks()
+    peak_tf, peak_hbm, peak_src, peak_burst = peaks()
     roof = {}
     for key, flop_unit, units in (("cips", CIPS_FLOP_PER_PIXEL, B * res * res), ("ray", NERF_FLOP_PER_RAY, B * res * res)):
         evs = (prof or {}).get(key, [])
@@ -241,7 +245,8 @@ def main():
             ach = flop_unit * units / (t_ms * 1e-3) / 1e12
             roof[key] = {"bound": "tensor", "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach / peak_tf,
                          "traffic": None, "kernel_ms": t_ms, "launches_timed": len(evs),
-                         "algorithmic_flop_per_launch": flop_unit * units, "peak_source": peak_src}
+                         "algorithmic_flop_per_launch": flop_unit * units, "peak_source": peak_src,
+                         "peak_burst": peak_burst, "frac_of_burst": ach / peak_burst}
     # DRAM traffic per launch from the committed ncu --set full capture of this workload (profiles/traffic.json)
     tpath = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tpath):
