@@ -283,6 +283,15 @@ __global__ void __launch_bounds__(640, 1) ray_siren_tc_kernel(const KArgs a) {
     const int g_row = row / S, s_row = row - g_row * S;   // ray within the group, sample index
     const bool row_in_group = g_row < G;
     const int g_el = stid / nS, e_el = stid - g_el * nS;  // (ray, element) view used by the merge phases
+    // sigma of a coarse / fine row: MATH 2 keeps the two half-row partial sums of the layer-1 epilogue (see E1)
+    const float bsig = FOLD ? __ldg(a.b_sigma) : 0.f;
+    auto sig_at = [&](bool fine, int r) -> float {
+      if (FOLD) {
+        const float* ps = fine ? sm.w_all : sm.fbuf;
+        return __fadd_rn(__fadd_rn(ps[r], ps[kRows + r]), bsig);
+      }
+      return (fine ? sm.sig_f : sm.sig_c)[r];
+    };
     int cur_img = -1;
     if (FOLD && stid < 128) sm.abuf[stid] = __ldg(a.w_sigma + stid);   // visible after the first image-constants barrier
     if (FOLD) mbar_wait(&s.w_full, 0);   // the workers read Wl^T from the bulk-loaded blob themselves: observe its barrier
@@ -391,7 +400,9 @@ __global__ void __launch_bounds__(640, 1) ray_siren_tc_kernel(const KArgs a) {
           e1(accA, 32);
           tc_wait_ld();
           e1(accB, 48);
-          if (FOLD) sm.fbuf[half * kRows + row] = psig;   // read by the row's other thread after the next d_ready
+          // partial sums of the two column halves, per pass; combined where sigma is used, i.e. after the slot-wide barrier
+          // that ends the pass (fbuf / w_all are free in the warp-math forms)
+          if (FOLD) (pass == 0 ? sm.fbuf : sm.w_all)[half * kRows + row] = psig;
         }
         stamp(6);
         signal_a();
@@ -407,10 +418,6 @@ __global__ void __launch_bounds__(640, 1) ray_siren_tc_kernel(const KArgs a) {
           tmem_ld16(dcol + (uint32_t)(half * 32), accA);
           tmem_ld16(dcol + (uint32_t)(half * 32 + 16), accB);
           tc_wait_ld();
-          if (half == 1) {
-            sigma = __fadd_rn(__fadd_rn(sm.fbuf[row], sm.fbuf[kRows + row]), __ldg(a.b_sigma));
-            (pass == 0 ? sm.sig_c : sm.sig_f)[row] = sigma;
-          }
           uint32_t* crow = reinterpret_cast<uint32_t*>(&sm.feat[0][0][0]) + ((pass == 0 ? kRows : 0) + row) * 33 + half * 16;
           auto e2 = [&](const uint32_t (&acc)[16], int c) {
 #pragma unroll
@@ -487,7 +494,7 @@ __global__ void __launch_bounds__(640, 1) ray_siren_tc_kernel(const KArgs a) {
             if (act) {
               const float delta = e + 1 < S ? __fsub_rn(zn, z) : 1e10f;
               const float nz = a.io.noise_c ? __fmul_rn(a.io.noise_c[ro * S + e], p.noise_std) : 0.f;
-              alpha = sample_alpha(delta, sm.sig_c[r0 + e], nz, p.clamp_mode);
+              alpha = sample_alpha(delta, sig_at(false, r0 + e), nz, p.clamp_mode);
               f = __fadd_rn(__fsub_rn(1.f, alpha), 1e-10f);
             }
             float P = f;                                  // inclusive product scan over the ray's lanes
@@ -593,7 +600,7 @@ __global__ void __launch_bounds__(640, 1) ray_siren_tc_kernel(const KArgs a) {
           const float kn = __shfl_down_sync(full, ks, 1);
           float alpha = 0.f, f = 1.f;
           if (act) {
-            const float sg = src < S ? sm.sig_f[rc0 + src] : sm.sig_c[rc0 + src - S];
+            const float sg = src < S ? sig_at(true, rc0 + src) : sig_at(false, rc0 + src - S);
             const float delta = e + 1 < nS ? __fsub_rn(kn, ks) : 1e10f;
             const float nz = a.io.noise_f ? __fmul_rn(a.io.noise_f[ro * nS + e], p.noise_std) : 0.f;
             alpha = sample_alpha(delta, sg, nz, p.clamp_mode);
