@@ -44,3 +44,4 @@ grep -h "blur" $O/r02a_disc_ops_default.jsonl $O/r02a_disc_ops_blur_tma.jsonl | 
 cat $O/r02a_optim.jsonl $O/r02a_time_pigan.jsonl | cut -c1-300
 cat $O/r02a_train_c*.json 2>/dev/null | cut -c1-400
 cat $O/r02a_summary.txt
+python tools/r02_report.py $O > $O/r02a_report.md 2>&1   # copy to profiles/r02a_summary.md after reading it
