@@ -78,6 +78,8 @@ class FiLMLayer(nn.Module):                     # film_layer.py:41-107
         self.linear = which_linear(in_dim, out_dim)
         self.linear.apply(frequency_init(25))
         self.gain_scale = LinearScale(scale=15, bias=30)
+        # opt-in until timed on hardware: FiLM + sine of the autograd graph as the native op (ops.FilmSinFunction)
+        self.fused_film = False
         if use_style_fc:
             self.gain_fc = which_linear(style_dim, out_dim)
             self.bias_fc = which_linear(style_dim, out_dim)
@@ -99,6 +101,11 @@ class FiLMLayer(nn.Module):                     # film_layer.py:41-107
             gain, bias = gain.unsqueeze(1), bias.unsqueeze(1)
         elif x.dim() != 2:
             assert 0
+        if self.fused_film and x.dim() == 3:
+            z = self.linear(x)
+            if ops.film_sin_supported(z, gain, bias):
+                return ops.film_sin(z, gain, bias)      # one native pass forward, one backward (csrc/film_ops.cu)
+            return torch.sin(gain * z + bias)
         return torch.sin(gain * self.linear(x) + bias)
 
 

@@ -7,6 +7,7 @@ import math
 import numpy as np
 import torch
 from torch.autograd import Function
+from torch.autograd.function import once_differentiable
 
 from . import _lib
 from ._lib import CipsParams, CipsWeights, PiganWeights, RayIO, RayParams, SirenWeights, check, load, ptr, stream_ptr
@@ -539,3 +540,49 @@ def image_to_u8(img, mode="save_image", value_range=(-1, 1)):
     check(lib.c3d_image_to_u8(ptr(src), ptr(out), B, Cn, H, W, int(cl), _U8_MODES[mode], float(lo), float(hi),
                               stream_ptr()), "c3d_image_to_u8")
     return out if img.dim() == 4 else out[0]
+
+
+def film_sin_supported(z, gain, bias):
+    """Shapes the native FiLM-sine takes: z (B, P, C) fp32, gain / bias (B, C) or (B, 1, C), C % 4 == 0 and 256 % (C / 4) == 0."""
+    if z.dim() != 3 or z.dtype != torch.float32 or gain.dtype != torch.float32 or bias.dtype != torch.float32:
+        return False
+    B, _, Cn = z.shape
+    ok = lambda t: t.numel() == B * Cn and t.shape[0] == B and t.shape[-1] == Cn       # noqa: E731
+    return Cn >= 4 and Cn % 4 == 0 and 256 % (Cn // 4) == 0 and ok(gain) and ok(bias)
+
+
+class FilmSinFunction(Function):
+    """y = sin(gain * z + bias) with per-image gain / bias (film_layer.py:94-107): one native pass forward, one backward
+    (dz and the per-image reductions dgain, dbias together); saves z only.  No double backward (the generator's graph
+    needs none: R1 differentiates the discriminator)."""
+
+    @staticmethod
+    def forward(ctx, z, gain, bias):
+        lib = load()
+        z = z.contiguous()
+        B, P, Cn = z.shape
+        g2, b2 = gain.reshape(B, Cn).contiguous(), bias.reshape(B, Cn).contiguous()
+        y = torch.empty_like(z)
+        check(lib.c3d_film_sin_fwd(ptr(z), ptr(g2), ptr(b2), ptr(y), B, P, Cn, stream_ptr()), "c3d_film_sin_fwd")
+        ctx.save_for_backward(z, g2, b2)
+        ctx.shapes = (gain.shape, bias.shape)
+        return y
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dy):
+        lib = load()
+        z, g2, b2 = ctx.saved_tensors
+        B, P, Cn = z.shape
+        dy = dy.contiguous()
+        dz = torch.empty_like(z)
+        dg, db = torch.empty_like(g2), torch.empty_like(b2)
+        nbytes = lib.c3d_film_sin_bwd_workspace_bytes(B, P, Cn)
+        ws = torch.empty(max(nbytes, 16), dtype=torch.uint8, device=z.device)
+        check(lib.c3d_film_sin_bwd(ptr(z), ptr(g2), ptr(b2), ptr(dy), ptr(dz), ptr(dg), ptr(db), B, P, Cn, ptr(ws), nbytes,
+                                   stream_ptr()), "c3d_film_sin_bwd")
+        return dz, dg.view(ctx.shapes[0]), db.view(ctx.shapes[1])
+
+
+def film_sin(z, gain, bias):
+    return FilmSinFunction.apply(z, gain, bias)

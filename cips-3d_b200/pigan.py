@@ -73,9 +73,12 @@ class FiLMLayer(nn.Module):                                  # siren.py:83-94
     def __init__(self, input_dim, hidden_dim):
         super().__init__()
         self.layer = nn.Linear(input_dim, hidden_dim)
+        self.fused_film = False      # opt-in: the native FiLM + sine autograd op (ops.FilmSinFunction, csrc/film_ops.cu)
 
     def forward(self, x, freq, phase_shift):
         x = self.layer(x)
+        if self.fused_film and x.dim() == 3 and ops.film_sin_supported(x, freq, phase_shift):
+            return ops.film_sin(x, freq, phase_shift)
         return torch.sin(freq.unsqueeze(1).expand_as(x) * x + phase_shift.unsqueeze(1).expand_as(x))
 
 

@@ -169,6 +169,22 @@ int c3d_cips_bwd(const C3dCipsParams* p, const C3dCipsWeights* w, const void* ac
                  const float* g_rgb_pre, void* dz_f16, float* dx, void* workspace, size_t workspace_bytes, void* stream);
 
 /* ------------------------------------------------------------------------------------
+ * FiLM + sine of the NeRF branch's AUTOGRAD graph (the torch training path of configs 1-3):
+ *   y = sin(gain * z + bias)     exp/cips3d/models/film_layer.py:94-107, piGAN_lib/siren/siren.py:83-94
+ * z, y, dy, dz: (batch, points, channels) fp32 contiguous; gain, bias, dgain, dbias: (batch, channels).
+ * Forward is one pass; backward is one pass that also produces the per-image reductions
+ *   dz = dy * cos(gain * z + bias) * gain,  dbias = sum_p dy * cos(.),  dgain = sum_p dy * cos(.) * z
+ * (deterministic: fixed-order partial sums through `workspace`).  channels: a multiple of 4 with 256 % (channels / 4) == 0.
+ * All pointers 16-byte aligned.  Only z has to be kept for the backward.
+ * ---------------------------------------------------------------------------------- */
+int c3d_film_sin_fwd(const float* z, const float* gain, const float* bias, float* y, int32_t batch, int64_t points,
+                     int32_t channels, void* stream);
+size_t c3d_film_sin_bwd_workspace_bytes(int32_t batch, int64_t points, int32_t channels);
+int c3d_film_sin_bwd(const float* z, const float* gain, const float* bias, const float* dy, float* dz, float* dgain,
+                     float* dbias, int32_t batch, int64_t points, int32_t channels, void* workspace, size_t workspace_bytes,
+                     void* stream);
+
+/* ------------------------------------------------------------------------------------
  * Image export for the inference paths: generator output (batch, channels, height, width)
  * fp32 -> (batch, height, width, channels) uint8 on the device, bit-identical to what the reference's scripts hand to
  * PIL, so an inference batch leaves the GPU as 1 byte per sample.  mode:

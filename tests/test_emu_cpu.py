@@ -434,3 +434,47 @@ def test_emu_fused_style_prep_matches_the_module(monkeypatch):
         assert a[1][l].shape == b[1][l].shape and a[2][l].shape == b[2][l].shape
         assert rel_err(b[1][l], a[1][l])[0] < 1e-5 and rel_err(b[2][l], a[2][l])[0] < 1e-5, l
     assert rel_err(rb, ra)[0] < 1e-3        # 1e-7 differences in s1p / demod flip fp16 roundings of the per-image weight tiles
+
+
+@pytest.mark.parametrize("B,P,Cn,shape3", [(2, 300, 128, True), (1, 5000, 64, False), (3, 17, 256, True), (2, 1, 128, False)])
+def test_emu_film_sin_forward_and_backward_match_torch_autograd(B, P, Cn, shape3):
+    """csrc/film_ops.cu against the expression it replaces, torch.sin(gain * z + bias) (film_layer.py:94-107), forward and all
+    three gradients (dz; dgain / dbias are per-image reductions over the points: partial sums across several chunks)."""
+    g = torch.Generator().manual_seed(B * 1000 + P)
+    z = torch.randn(B, P, Cn, generator=g).requires_grad_()
+    gshape = (B, 1, Cn) if shape3 else (B, Cn)
+    gain = (torch.randn(*gshape, generator=g) * 5 + 30).requires_grad_()
+    bias = torch.randn(*gshape, generator=g).requires_grad_()
+    dy = torch.randn(B, P, Cn, generator=g)
+    ref = torch.sin(gain.view(B, 1, Cn).double() * z.double() + bias.view(B, 1, Cn).double())
+    rz, rg, rb = torch.autograd.grad(ref, (z, gain, bias), dy.double())
+    with emulated(async_mode=0) as pkg:
+        assert pkg.ops.film_sin_supported(z, gain, bias)
+        y = pkg.ops.film_sin(z, gain, bias)
+        dz, dg, db = torch.autograd.grad(y, (z, gain, bias), dy)
+    assert dg.shape == gain.shape and db.shape == bias.shape
+    assert (y.double() - ref).abs().max().item() < 2e-5               # fp32 argument of magnitude ~30-100: |d arg| ~ 4e-6
+    assert (dz.double() - rz).abs().max().item() < 2e-5 * rz.abs().max().item() + 1e-6
+    assert (dg.double() - rg).abs().max().item() < 1e-4 * rg.abs().max().item() + 1e-5
+    assert (db.double() - rb).abs().max().item() < 1e-4 * rb.abs().max().item() + 1e-5
+
+
+def test_emu_film_layer_fused_flag_matches_torch_path():
+    """FiLMLayer.fused_film: same module, same parameters; outputs and parameter gradients of the native op vs the torch ops."""
+    import cips3d_b200
+    torch.manual_seed(3)
+    layer = cips3d_b200.FiLMLayer(3, 128, 64)
+    x, style = torch.randn(2, 257, 3), torch.randn(2, 64)
+    out = {}
+    for fused in (False, True):
+        layer.fused_film = fused
+        layer.zero_grad()
+        with emulated(async_mode=0):
+            y = layer(x, style)
+            y.square().sum().backward()
+        out[fused] = (y.detach().clone(), {k: v.grad.clone() for k, v in layer.named_parameters()})
+    assert (out[True][0] - out[False][0]).abs().max().item() < 2e-5
+    for k, gr in out[False][1].items():
+        assert (out[True][1][k] - gr).abs().max().item() < 2e-4 * gr.abs().max().item() + 1e-5, k
+    with emulated(async_mode=0) as pkg:     # unsupported widths fall back to the torch expression
+        assert not pkg.ops.film_sin_supported(torch.zeros(1, 4, 6), torch.zeros(1, 6), torch.zeros(1, 6))

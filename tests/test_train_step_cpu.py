@@ -35,12 +35,12 @@ def cpu_modules(monkeypatch):
     return cips3d_b200
 
 
-def _run(bts, frozen, optim, backend, steps=2):
+def _run(bts, frozen, optim, backend, steps=2, film="torch"):
     cfg = dict(res=16, batch=2, frozen=frozen, aux=not frozen, diffaug=frozen, grad_points=256, forward_points=256,
                warmup_D=frozen)
     torch.manual_seed(0)
     with emulated(async_mode=0, sms=2):
-        step, mods = bts.build_step(cfg, torch.device("cpu"), optim, backend)
+        step, mods = bts.build_step(cfg, torch.device("cpu"), optim, backend, film_backend=film)
         before = {k: v.detach().clone() for k, v in mods["G"].named_parameters()}
         ema_before = {k: v.detach().clone() for k, v in mods["G_ema"].state_dict().items()}
         losses = [tuple(float(x) for x in step(it)) for it in range(steps)]
@@ -71,3 +71,9 @@ def test_train_step_full_recipe_with_aux_images(bts, cpu_modules):
     assert all(math.isfinite(x) for x in losses[0]) and ema_moved
     for prefix in ("siren.", "mapping_network_nerf.", "inr_net.", "mapping_network_inr.", "aux_to_rbg."):
         assert any(k.startswith(prefix) for k in moved), prefix
+    # the same two steps with the NeRF branch's FiLM + sine as the native autograd op (csrc/film_ops.cu)
+    ref2, _, _ = _run(bts, False, "fused", "torch", steps=2)
+    nat2, moved2, _ = _run(bts, False, "fused", "torch", steps=2, film="fused")
+    assert any(k.startswith("siren.") for k in moved2)
+    assert nat2[0] == pytest.approx(ref2[0], rel=1e-5)
+    assert nat2[1] == pytest.approx(ref2[1], rel=1e-4)               # after an update that went through the native backward

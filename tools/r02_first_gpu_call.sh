@@ -34,6 +34,7 @@ timeout 300 python tools/bench_optim.py > $O/r02a_optim.jsonl 2>&1; echo "optim 
 for c in 3 5; do for o in fused torch; do
   timeout 600 python tools/bench_train_step.py --config $c --optim $o > $O/r02a_train_c${c}_$o.json 2> $O/r02a_train_c${c}_$o.err; echo "train step config $c optim $o: exit $?" | tee -a $O/r02a_summary.txt
 done; done
+timeout 600 python tools/bench_train_step.py --config 3 --optim fused --film-backend fused > $O/r02a_train_c3_fused_film.json 2> $O/r02a_train_c3_fused_film.err
 timeout 600 python tools/bench_train_step.py --config 5 --optim fused --cips-backend fused > $O/r02a_train_c5_fused_cipsbwd.json 2> $O/r02a_train_c5_fused_cipsbwd.err
 timeout 600 python tools/bench_train_step.py --config 5 --optim fused --tf32 > $O/r02a_train_c5_fused_tf32.json 2> $O/r02a_train_c5_fused_tf32.err
 python bench.py --steps 20 --warmup 5 > $O/r02a_bench.json 2> $O/r02a_bench.err

@@ -87,7 +87,7 @@ for p in sorted(glob.glob(os.path.join(D, "r02a_train_*.json"))):
         c = j.get("config") or {}
         print(f"| {os.path.basename(p)} | {num(j.get('value'), '.2f')} | {num(j.get('ms_per_step'), '.1f')} | "
               f"config {c.get('baseline_config')} r{c.get('resolution')} b{c.get('batch_per_gpu')} optim={c.get('optim')} "
-              f"cips={c.get('cips_backend')} tf32={c.get('tf32_autograd')} | {j.get('finite')} |")
+              f"cips={c.get('cips_backend')} film={c.get('film_backend')} tf32={c.get('tf32_autograd')} | {j.get('finite')} |")
     if not rows:
         err = (read(os.path.basename(p).replace(".json", ".err")) or "").strip().splitlines()
         print(f"| {os.path.basename(p)} | no result | | {err[-1][:120] if err else ''} | |")
