@@ -58,6 +58,24 @@ for (B, H) in [(16, 256), (64, 256), (16, 512)]:
     ms = timeit(torch_chain)
     out.append(dict(op="image_to_u8: torch op chain (clone, clamp_, sub_, div_, mul, add_, clamp_, permute+to)", shape=[B, 3, H, H], ms=ms,
                     gbs=x.numel() * 5 / 1e9 / ms * 1e3, frac=x.numel() * 5 / 1e9 / ms * 1e3 / peak))
+# FiLM + sine of the NeRF autograd graph (csrc/film_ops.cu): forward 8 B/element, backward 12 B/element, against the torch ops
+for (B, P, Cn) in [(16, 16384 * 24, 128), (16, 16384 * 24, 64)]:
+    z = torch.randn(B, P, Cn, device=dev)
+    gain, bias = torch.randn(B, 1, Cn, device=dev) * 5 + 30, torch.randn(B, 1, Cn, device=dev)
+    dy = torch.randn(B, P, Cn, device=dev)
+    ms = timeit(lambda: ops.film_sin(z, gain, bias), reps=10)
+    out.append(dict(op="film_sin fwd", shape=[B, P, Cn], ms=ms, gbs=z.numel() * 8 / 1e9 / ms * 1e3, frac=z.numel() * 8 / 1e9 / ms * 1e3 / peak))
+    ms_t = timeit(lambda: torch.sin(gain * z + bias), reps=10)
+    out.append(dict(op="film_sin fwd: torch (mul, add, sin)", shape=[B, P, Cn], ms=ms_t, gbs=z.numel() * 8 / 1e9 / ms_t * 1e3, frac=z.numel() * 8 / 1e9 / ms_t * 1e3 / peak))
+    zr, gr, br = z.clone().requires_grad_(), gain.clone().requires_grad_(), bias.clone().requires_grad_()
+    y = ops.film_sin(zr, gr, br)
+    ms = timeit(lambda: torch.autograd.grad(y, (zr, gr, br), dy, retain_graph=True), reps=10)
+    out.append(dict(op="film_sin bwd (dz + dgain + dbias)", shape=[B, P, Cn], ms=ms, gbs=z.numel() * 12 / 1e9 / ms * 1e3, frac=z.numel() * 12 / 1e9 / ms * 1e3 / peak))
+    yt = torch.sin(gr * zr + br)
+    ms_t = timeit(lambda: torch.autograd.grad(yt, (zr, gr, br), dy, retain_graph=True), reps=10)
+    out.append(dict(op="film_sin bwd: torch autograd", shape=[B, P, Cn], ms=ms_t, gbs=z.numel() * 12 / 1e9 / ms_t * 1e3, frac=z.numel() * 12 / 1e9 / ms_t * 1e3 / peak))
+    del z, dy, zr, y, yt
+    torch.cuda.empty_cache()
 for r in out:
     print(json.dumps(r))
 print(json.dumps(dict(hbm_peak_gbs=peak, note="algorithmic bytes (read x + write y [+ read ref]) / CUDA-event median; L2 flushed between reps")))

@@ -20,3 +20,17 @@ cap cips_pair     cips_tc_kernel      C3D_CIPS_PAIR=1    -- python tools/prof_ci
 cap ray_default   ray_siren_tc_kernel C3D_X=0            -- python tools/prof_cips.py ray 16 256
 cap ray_warpmath  ray_siren_tc_kernel C3D_RAY_MATH=warp  -- python tools/prof_cips.py ray 16 256
 cap ray_foldmath  ray_siren_tc_kernel C3D_RAY_MATH=fold  -- python tools/prof_cips.py ray 16 256
+# HBM-bound kernels: dram bytes vs the algorithmic bytes in DESIGN.md (5th launch of each = past the warm-up)
+capskip() {   # like cap, but skips the first launches of the kernel
+  local tag=$1 rx=$2; shift 2
+  local envs=()
+  while [ "$1" != "--" ]; do envs+=("$1"); shift; done; shift
+  env "${envs[@]}" timeout 600 ncu --set full --clock-control none --import-source on -k "regex:$rx" --launch-skip 4 -c 1 -o $O/r02b_$tag -f "$@" > $O/r02b_$tag.log 2>&1
+  ncu -i $O/r02b_$tag.ncu-rep --page raw --csv > $O/r02b_${tag}_raw.csv 2>/dev/null
+  python tools/ncu_summary.py $O/r02b_${tag}_raw.csv "" > $O/r02b_${tag}_summary.md 2>/dev/null
+  echo "$tag: $(grep -m1 'gpu__time_duration' $O/r02b_${tag}_summary.md)"
+}
+capskip adam_ema   adam_ema_kernel        C3D_X=0         -- python tools/bench_optim.py
+capskip blur_tma   blur_tma_kernel        C3D_BLUR_TMA=1  -- python tools/bench_disc_ops.py
+capskip image_u8   image_u8_flat4_kernel  C3D_X=0         -- python tools/bench_disc_ops.py
+capskip film_bwd   film_sin_bwd_kernel    C3D_X=0         -- python tools/bench_disc_ops.py
