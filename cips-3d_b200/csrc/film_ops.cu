@@ -14,21 +14,24 @@ namespace film {
 constexpr int kThreads = 256;
 constexpr int kIters = 128;      // rows per chunk = kIters * (kThreads / (channels / 4))
 
+// grid (blocks, batch).  channels / 4 divides the block size (a power of two), so a thread keeps ONE channel quad for the whole
+// grid-stride loop: gain / bias live in registers and the loop has no integer division.
 __global__ void __launch_bounds__(kThreads) film_sin_fwd_kernel(const float4* __restrict__ z, const float4* __restrict__ gain,
                                                                 const float4* __restrict__ bias, float4* __restrict__ y,
-                                                                long long points, int quads, long long total) {
-  const long long stride = (long long)gridDim.x * blockDim.x;
-  const long long per_img = points * quads;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
-    const long long b = i / per_img;
-    const int q = (int)(i % quads);
-    const float4 g = __ldg(gain + b * quads + q), s = __ldg(bias + b * quads + q), v = __ldcs(z + i);
+                                                                long long per_img, int quads) {
+  const long long b = blockIdx.y, stride = (long long)gridDim.x * blockDim.x;
+  const int q = threadIdx.x & (quads - 1);
+  const float4 g = __ldg(gain + b * quads + q), s = __ldg(bias + b * quads + q);
+  const float4* zi = z + b * per_img;
+  float4* yi = y + b * per_img;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < per_img; i += stride) {
+    const float4 v = __ldcs(zi + i);
     float4 o;
     o.x = sinf(__fadd_rn(__fmul_rn(g.x, v.x), s.x));
     o.y = sinf(__fadd_rn(__fmul_rn(g.y, v.y), s.y));
     o.z = sinf(__fadd_rn(__fmul_rn(g.z, v.z), s.z));
     o.w = sinf(__fadd_rn(__fmul_rn(g.w, v.w), s.w));
-    y[i] = o;                    // read again by the next linear layer: default caching
+    yi[i] = o;                   // read again by the next linear layer: default caching
   }
 }
 
@@ -103,7 +106,7 @@ using namespace c3d;
 using namespace c3d::film;
 
 static bool film_shape_ok(int32_t batch, int64_t points, int32_t channels) {
-  return batch >= 0 && points >= 0 && channels >= 4 && channels % 4 == 0 && kThreads % (channels / 4) == 0;
+  return batch >= 0 && batch <= 65535 && points >= 0 && channels >= 4 && channels % 4 == 0 && kThreads % (channels / 4) == 0;
 }
 
 extern "C" int c3d_film_sin_fwd(const float* z, const float* gain, const float* bias, float* y, int32_t batch, int64_t points,
@@ -116,11 +119,12 @@ extern "C" int c3d_film_sin_fwd(const float* z, const float* gain, const float* 
   int dev = 0;
   cudaGetDevice(&dev);
   const int sms = c3d_device_sm_count(dev), quads = channels / 4;
-  const long long total = (long long)batch * points * quads;
-  long long blocks = (total + kThreads - 1) / kThreads;
-  if (blocks > (long long)sms * 16) blocks = (long long)sms * 16;
-  C3D_LAUNCH(film_sin_fwd_kernel, (int)blocks, kThreads, 0, (cudaStream_t)stream, (const float4*)z, (const float4*)gain,
-             (const float4*)bias, (float4*)y, (long long)points, quads, total);
+  const long long per_img = (long long)points * quads;
+  long long blocks = (per_img + kThreads - 1) / kThreads;
+  const long long cap = ((long long)sms * 16 + batch - 1) / batch;      // ~16 blocks per SM over the whole grid
+  if (blocks > cap) blocks = cap;
+  C3D_LAUNCH(film_sin_fwd_kernel, dim3((unsigned)blocks, (unsigned)batch), kThreads, 0, (cudaStream_t)stream, (const float4*)z,
+             (const float4*)gain, (const float4*)bias, (float4*)y, per_img, quads);
   C3D_LAUNCH_CHECK();
   return C3D_OK;
 }
