@@ -792,6 +792,10 @@ int c3d_cips_fwd_tc(const C3dCipsParams* p, const C3dCipsWeights* w, const float
   int cl = 1;
   bool pair = false;
   const int grid = cips_grid(p, &cl, &pair);
+  if (acts_f16) {       // the training forward is the single-CTA kernel: its weight tiles must be laid out for it
+    pair = false;
+    cl = 1;
+  }
   // ---- prep: weights -> fp16 tiles (one launch), per-image epilogue vectors
   {
     PrepArgs pa = {};

@@ -386,14 +386,18 @@ def test_emu_cips_backward_chain_matches_fp64_chain_from_the_same_stash(B, N, mo
     assert rel_err(dx, dX.float())[1] < 2e-3
 
 
-def test_emu_cips_fused_training_gradients():
+@pytest.mark.parametrize("pair_env", ["0", "1"])
+def test_emu_cips_fused_training_gradients(pair_env, monkeypatch):
     """CIPSNet.train_backend = 'fused' (ops.CipsMLPFunction: native forward + backward chain, weight gradients as fp16 GEMMs
     over the stashes, chain rule into W / modulation / ToRGB in torch) against fp64 autograd of the oracle.  The ToRGB
     gradients (no gate in between) agree to fp16 accuracy; the layer gradients differ by a few per cent in L2 because the
     LeakyReLU gates of the fp16-operand forward differ from the fp64 forward's on the ~0.1 % of units with |z| ~ 0 (each flips
     a gradient factor between 1 and 0.2) -- a property of any reduced-precision forward, not of the backward (the test above
-    pins the backward itself at 1e-3)."""
-    B, N = 2, 200
+    pins the backward itself at 1e-3).  pair_env = "1": with C3D_CIPS_PAIR set the training forward must still prepare the
+    single-CTA kernel's weight tiles (N = 256: two tiles per image, so the inference path WOULD pick the pair kernel) -- a
+    mismatch found by dry-running the GPU suite with every variant switched on."""
+    monkeypatch.setenv("C3D_CIPS_PAIR", pair_env)
+    B, N = 2, 256 if pair_env == "1" else 200
     sd = O.synthetic_state_dict(O.generator_template(), seed=31)
     g = torch.Generator().manual_seed(5)
     x, w, gout = torch.randn(B, N, 32, generator=g), torch.randn(B, 512, generator=g), torch.randn(B, N, 3, generator=g)
