@@ -3,6 +3,8 @@
 Mirrors, with the reference's names, arguments and file naming:
   gen_images(rank, world_size, generator, G_kwargs, fake_dir, num_imgs, img_size, batch_size)
       exp/cips3d/scripts/gen_images.py:30-73 -- the FID-evaluation image dump (2 048 - 50 000 images per evaluation)
+  sample_images(rank, world_size, generator, G_kwargs, fake_dir, num_imgs, img_size)
+      exp/cips3d/scripts/sample_images.py:30-83 -- one frontal-ish image per random seed, named by the seed
   to_pil(frame)            exp/comm/comm_utils.py:21-24
   tensor_to_PIL(img)       exp/cips3d/models/st_web.py:44-46
 The reference clamps / rescales / rounds / permutes the fp32 batch with five torch ops, copies 4 bytes per sample to the
@@ -11,8 +13,10 @@ host image by image and encodes there.  Here the generator's output goes through
 as 1 byte per sample into pinned memory on a copy stream, and the host encodes batch k while the GPU renders batch k+1.
 The files are written by the same PIL call torchvision's save_image ends in, so equal images give equal files."""
 import copy
+import math
 import os
 
+import numpy as np
 import torch
 
 from . import ops
@@ -133,3 +137,46 @@ def gen_images(rank, world_size, generator, G_kwargs, fake_dir, num_imgs, img_si
         bar.close()
     _synchronize()
     return written
+
+
+def sample_images(rank, world_size, generator, G_kwargs, fake_dir, num_imgs, img_size, ext="jpg", forward_points=256 ** 2, **kwargs):
+    """sample_images.py:30-83: every rank draws a seed (`np.random.randint(0, 1e8)`), seeds torch with it, renders ONE image with
+    the camera fixed at h_mean = pi/2 + 0.15 (h_stddev = v_stddev = 0, psi = 1) and writes f"{fake_dir}/{seed:0>10}.{ext}".
+    Returns the seeds this rank used."""
+    if rank == 0:
+        os.makedirs(fake_dir, exist_ok=True)
+    _synchronize()
+    metadata = copy.deepcopy(G_kwargs)
+    batch_size = world_size                       # batch_gpu = 1
+    metadata['img_size'] = img_size
+    metadata['batch_size'] = 1
+    metadata['psi'] = 1
+    metadata['h_stddev'] = 0
+    metadata['v_stddev'] = 0
+    metadata['h_mean'] = math.pi * 0.5 + 0.15
+    generator.eval()
+    Image = _pil()
+    ring, pending, seeds = None, None, []
+
+    def flush(p):
+        seed, slot = p
+        Image.fromarray(_squeeze_gray(ring.wait(slot)[0])).save(f"{fake_dir}/{seed:0>10}.{ext}")
+
+    with torch.no_grad():
+        for _ in range((num_imgs + batch_size - 1) // batch_size):
+            seed = np.random.randint(0, 1e8)
+            torch.manual_seed(seed)
+            zs = generator.get_zs(metadata['batch_size'])
+            generated_imgs = generator(zs, forward_points=forward_points, **metadata)[0]
+            u8 = ops.image_to_u8(generated_imgs, mode="save_image", value_range=(-1, 1))
+            if ring is None:
+                ring = _HostRing(u8.device)
+            slot = ring.push(u8)
+            if pending is not None:
+                flush(pending)
+            pending = (seed, slot)
+            seeds.append(int(seed))
+        if pending is not None:
+            flush(pending)
+    _synchronize()
+    return seeds

@@ -149,3 +149,24 @@ def test_to_pil_and_tensor_to_PIL_match_the_reference_helpers():
     img = x.squeeze() * 0.5 + 0.5
     want = Image.fromarray(img.mul(255).add_(0.5).clamp_(0, 255).permute(1, 2, 0).to('cpu', torch.uint8).numpy())
     assert np.array_equal(np.array(b), np.array(want)) and b.mode == want.mode == "RGB"
+
+
+def test_sample_images_names_files_by_seed_and_fixes_the_camera(tmp_path):
+    """sample_images.py:30-83: seed drawn from numpy, torch seeded with it, one image per seed, the reference's camera metadata."""
+    tv = pytest.importorskip("torchvision.utils")
+    import cips3d_b200.inference as inf
+    G = _StubG()
+    np.random.seed(123)
+    with emulated(async_mode=0):
+        seeds = inf.sample_images(0, 1, G, {"fov": 12, "h_stddev": 0.3, "psi": 0.5}, str(tmp_path / "s"), num_imgs=3, img_size=8)
+    np.random.seed(123)
+    assert seeds == [int(np.random.randint(0, 1e8)) for _ in range(3)]
+    for c in G.calls:
+        assert c["h_stddev"] == 0 and c["v_stddev"] == 0 and c["psi"] == 1 and c["batch_size"] == 1
+        assert c["h_mean"] == pytest.approx(np.pi * 0.5 + 0.15) and c["forward_points"] == 256 ** 2
+    for seed, img in zip(seeds, G.images):
+        torch.manual_seed(seed)
+        assert torch.equal(G.get_zs(1)["z"], torch.randn(1, 4, generator=torch.Generator().manual_seed(seed)))   # torch was seeded
+        ref = tmp_path / f"ref_{seed}.jpg"
+        tv.save_image(img.squeeze(), str(ref), normalize=True, value_range=(-1, 1))
+        assert (tmp_path / "s" / f"{seed:0>10}.jpg").read_bytes() == ref.read_bytes()
