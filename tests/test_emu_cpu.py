@@ -482,3 +482,72 @@ def test_emu_film_layer_fused_flag_matches_torch_path():
         assert (out[True][1][k] - gr).abs().max().item() < 2e-4 * gr.abs().max().item() + 1e-5, k
     with emulated(async_mode=0) as pkg:     # unsupported widths fall back to the torch expression
         assert not pkg.ops.film_sin_supported(torch.zeros(1, 4, 6), torch.zeros(1, 6), torch.zeros(1, 6))
+
+
+def _pigan_render(pkg, name):
+    sd, z, draws, kw, meta, ref = load_pigan_case(name)
+    cls = pkg.pigan.SPATIALSIRENBASELINE if meta["siren_cls"] == "SPATIALSIRENBASELINE" else pkg.pigan.TALLSIREN
+    G = pkg.pigan.ImplicitGenerator3d(cls, z_dim=256)
+    G.load_state_dict(sd)
+    hier = kw["hierarchical_sample"]
+    with torch.no_grad():
+        fr, ph = pigan_freq_phase(sd, z, meta)
+        origin, _, _ = O.camera_origin(draws["yaw_n"], draws["pitch_n"], kw["h_stddev"], kw["v_stddev"], kw["h_mean"], kw["v_mean"])
+        out = pkg.ops.pigan_render(
+            G.siren.kernel_weights(fr, ph), O.cam2world(-origin, origin), draws["jitter_u"], draws["pdf_u"] if hier else None,
+            draws["noise_c"] if hier else None, draws["noise_f"], img_size=meta["img_size"], fov=kw["fov"],
+            ray_start=kw["ray_start"], ray_end=kw["ray_end"], num_steps=kw["num_steps"], hierarchical_sample=hier,
+            clamp_mode=kw["clamp_mode"], noise_std=meta["nerf_noise"], white_back=kw["white_back"], last_back=kw["last_back"],
+            lock_view=kw.get("lock_view_dependence", False), debug=True)
+    return out, ref
+
+
+_SCHEDULES = [dict(async_mode=0, seed=1, preempt_permille=0), dict(async_mode=1, seed=2, preempt_permille=100),
+              dict(async_mode=2, seed=99, preempt_permille=300, sms=3)]
+
+
+def _bits(tensors):
+    import hashlib
+    return tuple(hashlib.sha1(t.detach().contiguous().numpy().tobytes()).hexdigest() for t in tensors)
+
+
+@pytest.mark.parametrize("what,env", [("ray", {}), ("ray", {"C3D_RAY_MATH": "fold"}), ("cips", {"C3D_CIPS_PAIR": "1"}),
+                                      ("cips_train", {}), ("pigan", {"C3D_PIGAN_IMPL": "tc", "C3D_PIGAN_PAIR": "1"})])
+def test_emu_outputs_are_bit_identical_across_schedules(what, env, monkeypatch):
+    """A race that stays inside the parity tolerances would still make the output depend on WHEN asynchronous operations
+    complete, which thread runs first and which CTA gets which tile.  Three very different schedules (eager / latest-possible /
+    random completion, 0-30 % random preemption, 2 or 3 SMs) must give the same bits -- for every kernel family, default and
+    opt-in forms.  (It also shows the CTA-pair CIPS kernel equal to the single-CTA kernel bit for bit: see the assertion.)"""
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    sd = O.synthetic_state_dict(O.generator_template(), seed=31)
+    g = torch.Generator().manual_seed(3)
+    x, w = torch.randn(2, 512, 32, generator=g), torch.randn(2, 512, generator=g)
+
+    def run(pkg):
+        if what == "ray":
+            out, _ = _render(pkg, "r16_trained_noise", TC, debug=False, want_depth=True, want_weights=True)
+            return out["pixels_fea"], out["depth"], out["weights"]
+        if what == "cips":
+            G = build_generator("cpu", sd)
+            with torch.no_grad():
+                ws, s1p, dm, rw, rb = G.inr_net.kernel_inputs({k: w for k in G.inr_net.style_dim_dict}, 9)
+                return pkg.ops.cips_forward(x, ws, s1p, dm, rw, rb, impl=TC, return_hidden=True)
+        if what == "cips_train":
+            net = build_generator("cpu", sd).train().inr_net
+            xr = x.clone().requires_grad_()
+            y = net.forward_fused_train(xr, {k: w for k in net.style_dim_dict})
+            y.square().sum().backward()
+            return (y, xr.grad) + tuple(p.grad for p in net.parameters() if p.grad is not None)
+        out, _ = _pigan_render(pkg, "spatial_r8_noise_backs")
+        return tuple(out[k] for k in sorted(out) if torch.is_tensor(out[k]))
+
+    seen = []
+    for s in _SCHEDULES:
+        with emulated(**s) as pkg:
+            seen.append(_bits(run(pkg)))
+    assert seen[0] == seen[1] == seen[2]
+    if what == "cips":          # and the pair form computes exactly what the default form computes
+        monkeypatch.setenv("C3D_CIPS_PAIR", "0")
+        with emulated(**_SCHEDULES[0]) as pkg:
+            assert _bits(run(pkg)) == seen[0]
