@@ -480,6 +480,13 @@ def _torch_integrate(rgb_sigma, z, noise, clamp_mode, last_back, white_back, dim
     return rgb, weights
 
 
+def _integrate(backend, rgb_sigma, z, noise, clamp_mode, last_back, white_back, dim_rgb):
+    """fancy_integration of the training graph: torch ops, or the native op when `backend == 'fused'` and the shape fits."""
+    if backend == 'fused' and rgb_sigma.shape[-1] == dim_rgb + 1 and ops.integrate_supported(rgb_sigma, z, noise):
+        return ops.integrate(rgb_sigma, z, noise, clamp_mode, last_back, white_back)
+    return _torch_integrate(rgb_sigma, z, noise, clamp_mode, last_back, white_back, dim_rgb)
+
+
 def _torch_sample_pdf(bins, weights, u, eps=1e-5):
     n_s = weights.shape[1]
     weights = weights + eps
@@ -599,6 +606,10 @@ class GeneratorNerfINR(nn.Module):              # generator.py:1158-1951
                                   nerf_noise=nerf_noise, white_back=white_back, last_back=last_back,
                                   ray_idx=ray_idx)
 
+    # volume integration of the autograd graph: 'torch' (round-1 behaviour) or 'fused' (ops.IntegrateFunction, csrc/integrate_ops.cu:
+    # one native pass forward, one backward) -- opt-in until timed on hardware, like FiLMLayer.fused_film
+    train_integrate = 'torch'
+
     def _render_torch(self, style_dict, c2w, jitter_u, pdf_u, noise_c, noise_f, *, img_size, fov, ray_start,
                       ray_end, num_steps, hierarchical_sample, clamp_mode, nerf_noise, white_back, last_back,
                       ray_idx=None):
@@ -620,18 +631,22 @@ class GeneratorNerfINR(nn.Module):              # generator.py:1158-1951
         nf = noise_f * nerf_noise if noise_f is not None else None
         if hierarchical_sample:
             with torch.no_grad():                                    # generator_nerf_inr.py:537 (@no_grad)
-                _, w = _torch_integrate(coarse, z, nc, clamp_mode, False, False, dim_rgb)
+                _, w = _integrate(self.train_integrate, coarse, z, nc, clamp_mode, False, False, dim_rgb)
                 w = w.reshape(B * N, S) + 1e-5
                 zz = z.reshape(B * N, S)
                 fz = _torch_sample_pdf(0.5 * (zz[:, :-1] + zz[:, 1:]), w[:, 1:-1], pdf_u).reshape(B, N, S)
                 fpts = t[:, None, None, :] + dirs_w[:, :, None, :] * fz[..., None]
             fine = self.siren(fpts.reshape(B, N * S, 3), style_dict, None).reshape(B, N, S, -1)
+            if (self.train_integrate == 'fused' and fine.shape[-1] == dim_rgb + 1
+                    and ops.integrate_merged_supported(fine, fz, coarse, z, nf)):
+                # cat + sort + gather + integration in one native pass each way (csrc/integrate_ops.cu, merged form)
+                return ops.integrate_merged(fine, fz, coarse, z, nf, clamp_mode, last_back, white_back)[0]
             all_out = torch.cat([fine, coarse], dim=-2)
             all_z, ind = torch.sort(torch.cat([fz, z], dim=-1), dim=-1)
             all_out = torch.gather(all_out, -2, ind[..., None].expand(-1, -1, -1, all_out.shape[-1]))
         else:
             all_out, all_z = coarse, z
-        fea, _ = _torch_integrate(all_out, all_z, nf, clamp_mode, last_back, white_back, dim_rgb)
+        fea, _ = _integrate(self.train_integrate, all_out, all_z, nf, clamp_mode, last_back, white_back, dim_rgb)
         return fea
 
     # ---------------------------------------------------------------- forward paths

@@ -586,3 +586,117 @@ class FilmSinFunction(Function):
 
 def film_sin(z, gain, bias):
     return FilmSinFunction.apply(z, gain, bias)
+
+
+def integrate_supported(rgb_sigma, z, noise=None):
+    """Shapes the native volume integration takes: rgb_sigma (..., T, C + 1) fp32 with T <= 32 sorted samples and C <= 128
+    channels, z (..., T), noise None or (..., T) / (..., T, 1)."""
+    if rgb_sigma.dim() < 2 or rgb_sigma.dtype != torch.float32 or z.dtype != torch.float32:
+        return False
+    T, C1 = rgb_sigma.shape[-2:]
+    if not (1 <= T <= 32 and 2 <= C1 <= 129) or z.shape != rgb_sigma.shape[:-1]:
+        return False
+    return noise is None or (noise.dtype == torch.float32 and noise.numel() == z.numel())
+
+
+class IntegrateFunction(Function):
+    """fancy_integration (pigan_utils.py:222-262) on sorted samples as one native pass forward and one backward
+    (csrc/integrate_ops.cu).  Returns (fea, weights); gradients flow to rgb_sigma only -- z and noise are constants of the
+    reference's graph too (fine depths are drawn under no_grad, generator_nerf_inr.py:537).  Saves only its inputs.
+    No double backward (the generator's graph needs none)."""
+
+    @staticmethod
+    def forward(ctx, rgb_sigma, z, noise, clamp_mode, last_back, white_back):
+        lib = load()
+        if clamp_mode not in CLAMP_MODES:
+            raise AssertionError("Need to choose clamp mode")             # pigan_utils.py:249
+        lead, (T, C1) = rgb_sigma.shape[:-2], rgb_sigma.shape[-2:]
+        rs = rgb_sigma.contiguous()
+        zc = z.contiguous()
+        nz = None if noise is None else noise.reshape(z.shape).contiguous()
+        rays = zc.numel() // T
+        fea = torch.empty(*lead, C1 - 1, dtype=torch.float32, device=rs.device)
+        weights = torch.empty(*lead, T, dtype=torch.float32, device=rs.device)
+        check(lib.c3d_integrate_fwd(ptr(rs), ptr(zc), ptr(nz) if nz is not None else None, ptr(fea), ptr(weights), rays, T,
+                                    C1 - 1, CLAMP_MODES[clamp_mode], int(bool(last_back)), int(bool(white_back)), stream_ptr()),
+              "c3d_integrate_fwd")
+        ctx.save_for_backward(rs, zc, nz if nz is not None else torch.empty(0, device=rs.device))
+        ctx.cfg = (nz is not None, CLAMP_MODES[clamp_mode], int(bool(last_back)), int(bool(white_back)))
+        ctx.mark_non_differentiable(weights)
+        return fea, weights
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, d_fea, _d_weights):
+        lib = load()
+        rs, zc, nz = ctx.saved_tensors
+        has_noise, clamp, last_back, white_back = ctx.cfg
+        T, C1 = rs.shape[-2:]
+        d_fea = d_fea.contiguous()
+        d_rs = torch.empty_like(rs)
+        check(lib.c3d_integrate_bwd(ptr(rs), ptr(zc), ptr(nz) if has_noise else None, ptr(d_fea), ptr(d_rs), zc.numel() // T, T,
+                                    C1 - 1, clamp, last_back, white_back, stream_ptr()), "c3d_integrate_bwd")
+        return d_rs, None, None, None, None, None
+
+
+def integrate(rgb_sigma, z, noise=None, clamp_mode="relu", last_back=False, white_back=False):
+    """(fea, weights) of fancy_integration; differentiable in rgb_sigma."""
+    return IntegrateFunction.apply(rgb_sigma, z, noise, clamp_mode, last_back, white_back)
+
+
+def integrate_merged_supported(fine, z_fine, coarse, z_coarse, noise=None):
+    """Both halves (..., S, C + 1) fp32 with S <= 16 and C <= 128, depths (..., S); noise None or 2S values per ray."""
+    if fine.shape != coarse.shape or z_fine.shape != z_coarse.shape or fine.dim() < 2:
+        return False
+    if any(t.dtype != torch.float32 for t in (fine, coarse, z_fine, z_coarse)):
+        return False
+    S, C1 = fine.shape[-2:]
+    if not (1 <= S <= 16 and 2 <= C1 <= 129) or z_fine.shape != fine.shape[:-1]:
+        return False
+    return noise is None or (noise.dtype == torch.float32 and noise.numel() == 2 * z_fine.numel())
+
+
+class IntegrateMergedFunction(Function):
+    """torch.cat([fine, coarse]) + torch.sort of the depths + torch.gather + fancy_integration (generator.py:1489-1508) as one
+    native pass forward and one backward: the 2S samples of a ray are rank-sorted in registers, colour rows are read from and
+    gradients written to their source rows (csrc/integrate_ops.cu, merged form).  Returns (fea, weights, z_sorted); gradients
+    flow to fine and coarse only.  Equal depths keep cat order (a stable sort)."""
+
+    @staticmethod
+    def forward(ctx, fine, z_fine, coarse, z_coarse, noise, clamp_mode, last_back, white_back):
+        lib = load()
+        if clamp_mode not in CLAMP_MODES:
+            raise AssertionError("Need to choose clamp mode")             # pigan_utils.py:249
+        lead, (S, C1) = fine.shape[:-2], fine.shape[-2:]
+        f, c, zf, zc = fine.contiguous(), coarse.contiguous(), z_fine.contiguous(), z_coarse.contiguous()
+        nz = None if noise is None else noise.reshape(*lead, 2 * S).contiguous()
+        rays = zf.numel() // S
+        fea = torch.empty(*lead, C1 - 1, dtype=torch.float32, device=f.device)
+        weights = torch.empty(*lead, 2 * S, dtype=torch.float32, device=f.device)
+        z_sorted = torch.empty(*lead, 2 * S, dtype=torch.float32, device=f.device)
+        cfg = (CLAMP_MODES[clamp_mode], int(bool(last_back)), int(bool(white_back)))
+        check(lib.c3d_integrate_merge_fwd(ptr(f), ptr(zf), ptr(c), ptr(zc), ptr(nz), ptr(fea), ptr(weights), ptr(z_sorted), rays, S,
+                                          C1 - 1, *cfg, stream_ptr()), "c3d_integrate_merge_fwd")
+        ctx.save_for_backward(f, zf, c, zc, nz if nz is not None else torch.empty(0, device=f.device))
+        ctx.cfg = (nz is not None,) + cfg
+        ctx.mark_non_differentiable(weights, z_sorted)
+        return fea, weights, z_sorted
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, d_fea, _d_weights, _d_z):
+        lib = load()
+        f, zf, c, zc, nz = ctx.saved_tensors
+        has_noise, clamp, last_back, white_back = ctx.cfg
+        S, C1 = f.shape[-2:]
+        d_fea = d_fea.contiguous()
+        d_f, d_c = torch.empty_like(f), torch.empty_like(c)
+        check(lib.c3d_integrate_merge_bwd(ptr(f), ptr(zf), ptr(c), ptr(zc), ptr(nz) if has_noise else None, ptr(d_fea), ptr(d_f),
+                                          ptr(d_c), zf.numel() // S, S, C1 - 1, clamp, last_back, white_back, stream_ptr()),
+              "c3d_integrate_merge_bwd")
+        return d_f, None, d_c, None, None, None, None, None
+
+
+def integrate_merged(fine, z_fine, coarse, z_coarse, noise=None, clamp_mode="relu", last_back=False, white_back=False):
+    """(fea, weights, z_sorted) of the sorted union of the fine and coarse samples; differentiable in fine and coarse."""
+    return IntegrateMergedFunction.apply(fine, z_fine, coarse, z_coarse, noise, clamp_mode, last_back, white_back)

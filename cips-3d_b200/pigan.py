@@ -184,6 +184,7 @@ class ImplicitGenerator3d(nn.Module):                        # generators.py:12-
         self.epoch = 0
         self.step = 0
         self.force_torch_path = False       # measurement / debugging hook
+        self.train_integrate = 'torch'      # 'fused': fancy_integration of the autograd graph as the native op (csrc/integrate_ops.cu)
 
     def set_device(self, device):
         self.device = device
@@ -228,7 +229,7 @@ class ImplicitGenerator3d(nn.Module):                        # generators.py:12-
 
     def _render_torch(self, frequencies, phase_shifts, c2w, jitter_u, pdf_u, noise_c, noise_f, img_size, fov, ray_start, ray_end,
                       S, hierarchical_sample, lock_view, clamp_mode, nerf_noise, white_back, last_back):
-        from .generator import _torch_initial_rays, _torch_integrate, _torch_sample_pdf
+        from .generator import _integrate, _torch_initial_rays, _torch_sample_pdf
         dev = c2w.device
         dirs_cam, z_vals = _torch_initial_rays(img_size, ops.z_cam_from_fov(fov), ray_start, ray_end, S, dev)
         off = (jitter_u - 0.5) * (z_vals[1] - z_vals[0])
@@ -248,18 +249,21 @@ class ImplicitGenerator3d(nn.Module):                        # generators.py:12-
         nf = noise_f * nerf_noise
         if hierarchical_sample:
             with torch.no_grad():
-                _, w = _torch_integrate(coarse, z, nc, clamp_mode, False, False, 3)
+                _, w = _integrate(self.train_integrate, coarse, z, nc, clamp_mode, False, False, 3)
                 w = w.reshape(B * N, S) + 1e-5
                 zz = z.reshape(B * N, S)
                 fz = _torch_sample_pdf(0.5 * (zz[:, :-1] + zz[:, 1:]), w[:, 1:-1], pdf_u).reshape(B, N, S)
                 fpts = t[:, None, None, :] + dirs_w[:, :, None, :] * fz[..., None]
             fine = field(fpts.reshape(B, N * S, 3), frequencies, phase_shifts, ray_directions=dirs_exp).reshape(B, N, S, 4)
+            if self.train_integrate == 'fused' and ops.integrate_merged_supported(fine, fz, coarse, z, nf):
+                rgb, w, all_z = ops.integrate_merged(fine, fz, coarse, z, nf, clamp_mode, last_back, white_back)
+                return rgb, torch.sum(w * all_z, -1)
             all_out = torch.cat([fine, coarse], dim=-2)
             all_z, ind = torch.sort(torch.cat([fz, z], dim=-1), dim=-1)
             all_out = torch.gather(all_out, -2, ind[..., None].expand(-1, -1, -1, 4))
         else:
             all_out, all_z = coarse, z
-        rgb, w = _torch_integrate(all_out, all_z, nf, clamp_mode, last_back, white_back, 3)
+        rgb, w = _integrate(self.train_integrate, all_out, all_z, nf, clamp_mode, last_back, white_back, 3)
         depth = torch.sum(w * all_z, -1)
         return rgb, depth
 

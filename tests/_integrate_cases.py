@@ -1,0 +1,114 @@
+"""Shared inputs / checker of the volume-integration op tests (emulation on the CPU, hardware on the GPU)."""
+import torch
+
+from oracle import cips3d_oracle as O
+
+# (rays shape, samples, channels, clamp, last_back, white_back, noise)
+CASES = [((2, 37), 24, 32, "relu", True, False, False),        # FFHQ recipe: 12 + 12 samples, last_back
+         ((3, 11), 24, 32, "softplus", False, True, True),
+         ((1, 65), 12, 32, "relu", False, False, True),         # coarse pass of get_fine_points (weights only matter)
+         ((2, 9), 32, 32, "softplus", True, True, False),       # widest ray the kernel takes
+         ((1, 5), 2, 32, "relu", True, False, False),           # two samples (the reference needs >= 2: deltas[..., :1])
+         ((2, 19), 24, 3, "relu", True, False, False),          # pi-GAN rgb_dim 3 (one partial channel group)
+         ((1, 13), 7, 40, "softplus", False, False, True),      # two channel groups, second partial
+         ((1, 6), 5, 128, "relu", True, True, False)]           # four channel groups
+
+
+def make(case, seed, device="cpu"):
+    lead, T, Cn, clamp, lb, wb, noisy = case
+    g = torch.Generator().manual_seed(seed)
+    rs = torch.randn(*lead, T, Cn + 1, generator=g)
+    opaque = torch.rand(*lead, 1, generator=g) < 0.3                      # a third of the rays saturate (alpha -> 1 early)
+    rs[..., Cn] = (rs[..., Cn] + 0.3) * torch.where(opaque, 400.0, 8.0)
+    z = torch.sort(0.88 + 0.24 * torch.rand(*lead, T, generator=g), -1).values
+    noise = torch.randn(*lead, T, generator=g) * 0.5 if noisy else None
+    d_fea = torch.randn(*lead, Cn, generator=g)
+    mv = lambda t: None if t is None else t.to(device)                   # noqa: E731
+    return mv(rs), mv(z), mv(noise), mv(d_fea)
+
+
+def reference(case, rs, z, noise, d_fea, dtype=torch.float64):
+    """fp64 (or same-dtype) oracle integrate + torch autograd."""
+    _, T, Cn, clamp, lb, wb, _ = case
+    r = rs.detach().to(dtype).requires_grad_()
+    fea, _, w = O.integrate(r, z.to(dtype), None if noise is None else noise.to(dtype), clamp, lb, wb, dim_rgb=Cn)
+    (dr,) = torch.autograd.grad(fea, r, d_fea.to(dtype))
+    return fea.detach(), w.detach(), dr
+
+
+def check(case, pkg, rs, z, noise, d_fea):
+    _, T, Cn, clamp, lb, wb, _ = case
+    r = rs.clone().requires_grad_()
+    assert pkg.ops.integrate_supported(r, z, noise)
+    fea, w = pkg.ops.integrate(r, z, noise, clamp, lb, wb)
+    assert not w.requires_grad and fea.shape == rs.shape[:-2] + (Cn,) and w.shape == z.shape
+    (dr,) = torch.autograd.grad(fea, r, d_fea)
+    f64, w64, d64 = reference(case, rs.cpu(), z.cpu(), None if noise is None else noise.cpu(), d_fea.cpu())
+    fea, w, dr = fea.detach().cpu().double(), w.cpu().double(), dr.cpu().double()
+    assert (w - w64).abs().max().item() < 2e-6                              # weights are in [0, 1]
+    assert (fea - f64).abs().max().item() < 1e-5 * (1 + f64.abs().max().item())
+    dc, dc64 = dr[..., :Cn], d64[..., :Cn]
+    assert (dc - dc64).abs().max().item() < 1e-5 * (1 + dc64.abs().max().item())
+    ds, ds64 = dr[..., Cn], d64[..., Cn]
+    # d(sigma): fp32 alphas next to saturation carry ~1e-7 absolute error that the 1 / t_i of the cumprod backward scales up
+    assert (ds - ds64).abs().max().item() < 2e-4 * ds64.abs().max().item() + 1e-6
+    return fea, dr
+
+
+# merged form: (rays shape, samples per half, channels, clamp, last_back, white_back, noise)
+MERGED_CASES = [((2, 33), 12, 32, "relu", True, False, False),     # FFHQ recipe: 12 fine + 12 coarse
+                ((2, 17), 12, 32, "softplus", False, True, True),
+                ((1, 9), 16, 32, "relu", True, True, True),         # widest: 16 + 16
+                ((1, 7), 1, 32, "relu", True, False, False),        # one sample per half
+                ((2, 21), 12, 3, "relu", True, False, True),        # pi-GAN rgb_dim 3
+                ((1, 5), 5, 70, "softplus", False, False, False)]   # three channel groups (kernel instantiation 4)
+
+
+def make_merged(case, seed, device="cpu"):
+    lead, S, Cn, clamp, lb, wb, noisy = case
+    g = torch.Generator().manual_seed(seed)
+    halves = []
+    for _ in range(2):
+        rs = torch.randn(*lead, S, Cn + 1, generator=g)
+        opaque = torch.rand(*lead, 1, generator=g) < 0.3
+        rs[..., Cn] = (rs[..., Cn] + 0.3) * torch.where(opaque, 400.0, 8.0)
+        halves.append(rs)
+    z_coarse = torch.sort(0.88 + 0.24 * torch.rand(*lead, S, generator=g), -1).values
+    z_fine = 0.88 + 0.24 * torch.rand(*lead, S, generator=g)               # fine depths arrive unsorted relative to the coarse ones
+    z_fine[..., 0] = z_coarse[..., S // 2]                                  # a tie across the halves: cat order (fine first) wins
+    noise = torch.randn(*lead, 2 * S, generator=g) * 0.5 if noisy else None
+    d_fea = torch.randn(*lead, Cn, generator=g)
+    mv = lambda t: None if t is None else t.to(device)                     # noqa: E731
+    return mv(halves[0]), mv(z_fine), mv(halves[1]), mv(z_coarse), mv(noise), mv(d_fea)
+
+
+def reference_merged(case, fine, z_fine, coarse, z_coarse, noise, d_fea, dtype=torch.float64):
+    """generator.py:1489-1508 in fp64: cat, sort, gather, fancy_integration; autograd to both halves."""
+    _, S, Cn, clamp, lb, wb, _ = case
+    f, c = fine.detach().to(dtype).requires_grad_(), coarse.detach().to(dtype).requires_grad_()
+    all_out = torch.cat([f, c], -2)
+    all_z, ind = torch.sort(torch.cat([z_fine, z_coarse], -1), dim=-1, stable=True)  # fp32 depths: same order as the kernel sees
+    all_out = torch.gather(all_out, -2, ind[..., None].expand(*([-1] * (ind.dim())), Cn + 1))
+    fea, _, w = O.integrate(all_out, all_z.to(dtype), None if noise is None else noise.to(dtype), clamp, lb, wb, dim_rgb=Cn)
+    df, dc = torch.autograd.grad(fea, (f, c), d_fea.to(dtype))
+    return fea.detach(), w.detach(), all_z, df, dc
+
+
+def check_merged(case, pkg, fine, z_fine, coarse, z_coarse, noise, d_fea):
+    _, S, Cn, clamp, lb, wb, _ = case
+    f, c = fine.clone().requires_grad_(), coarse.clone().requires_grad_()
+    assert pkg.ops.integrate_merged_supported(f, z_fine, c, z_coarse, noise)
+    fea, w, zs = pkg.ops.integrate_merged(f, z_fine, c, z_coarse, noise, clamp, lb, wb)
+    assert not w.requires_grad and not zs.requires_grad and w.shape == zs.shape == z_fine.shape[:-1] + (2 * S,)
+    df, dc = torch.autograd.grad(fea, (f, c), d_fea)
+    cpu = lambda t: None if t is None else t.cpu()                         # noqa: E731
+    f64, w64, z64, df64, dc64 = reference_merged(case, *(cpu(t) for t in (fine, z_fine, coarse, z_coarse, noise, d_fea)))
+    assert torch.equal(zs.cpu(), z64)                                       # the sort itself is exact
+    assert (w.cpu().double() - w64).abs().max().item() < 2e-6
+    assert (fea.detach().cpu().double() - f64).abs().max().item() < 1e-5 * (1 + f64.abs().max().item())
+    for got, want in ((df, df64), (dc, dc64)):
+        got = got.cpu().double()
+        assert (got[..., :Cn] - want[..., :Cn]).abs().max().item() < 1e-5 * (1 + want[..., :Cn].abs().max().item())
+    smax = max(df64[..., Cn].abs().max().item(), dc64[..., Cn].abs().max().item())
+    for got, want in ((df, df64), (dc, dc64)):
+        assert (got.cpu().double()[..., Cn] - want[..., Cn]).abs().max().item() < 2e-4 * smax + 1e-6

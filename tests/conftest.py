@@ -21,11 +21,27 @@ def pytest_configure(config):
 EMU_DRYRUN = os.environ.get("C3D_GPU_TESTS_ON_EMU", "0") == "1"
 
 
+# GPU test files whose kernels have run on a B200 and passed there (profiles/r01*): these stay hard failures and run FIRST,
+# so that `pytest -m gpu -x` always reports the section 8(a) path before anything newer.
+HW_VALIDATED_FILES = ("test_gpu_parity.py",)
+# GPU test files written after the round's GPU minutes were spent (DESIGN.md status table: "not yet run on hardware").
+# Their first execution on a B200 is informative, not yet a parity claim: unless C3D_HW_STRICT=1 a failure there is reported
+# as XFAIL (and a pass as XPASS) instead of stopping a `-x` run -- a crash in one of them cannot take the validated results
+# down with it because those have already run.  tools/r02_first_gpu_call.sh runs them with C3D_HW_STRICT=1.
+HW_FIRST_RUN_FILES = ("test_film_gpu.py", "test_inference_gpu.py", "test_integrate_gpu.py", "test_optim_gpu.py", "test_pigan_gpu.py")
+HW_STRICT = os.environ.get("C3D_HW_STRICT", "0") == "1"
+
+
 def pytest_collection_modifyitems(config, items):
     import torch
     has_gpu = torch.cuda.is_available()
     skip_gpu = pytest.mark.skip(reason="no CUDA device")
+    items.sort(key=lambda it: 0 if os.path.basename(str(it.fspath)) in HW_VALIDATED_FILES else 1)   # stable sort
+    first_run = pytest.mark.xfail(strict=False, reason="first run on hardware (emulation-verified only): recorded, not yet "
+                                                        "a parity claim; C3D_HW_STRICT=1 makes it a hard failure")
     for item in items:
+        if "gpu" in item.keywords and has_gpu and not HW_STRICT and os.path.basename(str(item.fspath)) in HW_FIRST_RUN_FILES:
+            item.add_marker(first_run)
         if "gpu" in item.keywords and not has_gpu:
             if EMU_DRYRUN:
                 if hasattr(item.module, "DEV"):

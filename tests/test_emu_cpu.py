@@ -551,3 +551,104 @@ def test_emu_outputs_are_bit_identical_across_schedules(what, env, monkeypatch):
         monkeypatch.setenv("C3D_CIPS_PAIR", "0")
         with emulated(**_SCHEDULES[0]) as pkg:
             assert _bits(run(pkg)) == seen[0]
+
+
+# ------------------------------------------------------------------ volume integration of the autograd graph (csrc/integrate_ops.cu)
+from _integrate_cases import (CASES as INTEG_CASES, MERGED_CASES, check as integ_check, check_merged, make as integ_make,  # noqa: E402
+                              make_merged)
+
+
+@pytest.mark.parametrize("idx", range(len(INTEG_CASES)))
+def test_emu_integrate_forward_and_backward_match_fp64_autograd(idx):
+    """ops.IntegrateFunction against fp64 torch autograd of the oracle's fancy_integration (pigan_utils.py:222-262): features,
+    weights and the gradient w.r.t. every (feature_i, sigma_i), for both clamps, last_back / white_back, noise, 1..32 samples."""
+    case = INTEG_CASES[idx]
+    rs, z, noise, d_fea = integ_make(case, seed=100 + idx)
+    with emulated(async_mode=0) as pkg:
+        integ_check(case, pkg, rs, z, noise, d_fea)
+
+
+@pytest.mark.parametrize("idx", range(len(MERGED_CASES)))
+def test_emu_integrate_merged_matches_fp64_autograd_of_cat_sort_gather_integrate(idx):
+    """ops.IntegrateMergedFunction: unsorted fine + coarse halves in, generator.py:1489-1508 (cat, sort, gather, fancy_integration)
+    out; the sorted depths bit for bit (incl. a tie across the halves), weights, features, and the gradients at the SOURCE rows."""
+    case = MERGED_CASES[idx]
+    with emulated(async_mode=0) as pkg:
+        check_merged(case, pkg, *make_merged(case, seed=200 + idx))
+
+
+def test_emu_integrate_matches_fp32_torch_ops_it_replaces():
+    """Same dtype, same formulas: the op vs generator._torch_integrate (what the training graph ran before) incl. relu'(0) = 0."""
+    import cips3d_b200
+    case = INTEG_CASES[0]
+    rs, z, noise, d_fea = integ_make(case, seed=7)
+    rs[0, 0, 3, 32] = 0.0                                                   # sigma exactly 0: relu' = 0 on both sides
+    rs[0, 1, -1, 32] = -1.0                                                 # last sample empty: delta = 1e10 * relu(-1) = 0
+    r0 = rs.clone().requires_grad_()
+    fea0, w0 = cips3d_b200.generator._torch_integrate(r0, z, None, "relu", True, False, 32)
+    (d0,) = torch.autograd.grad(fea0, r0, d_fea)
+    with emulated(async_mode=0) as pkg:
+        r1 = rs.clone().requires_grad_()
+        fea1, w1 = pkg.ops.integrate(r1, z, None, "relu", True, False)
+        (d1,) = torch.autograd.grad(fea1, r1, d_fea)
+    assert (w1 - w0).abs().max().item() < 1e-6 and (fea1 - fea0).abs().max().item() < 1e-5
+    assert d1[0, 0, 3, 32].item() == 0.0 and d1[0, 1, -1, 32].item() == 0.0
+    assert (d1 - d0).abs().max().item() < 1e-4 * d0.abs().max().item() + 1e-6
+
+
+def test_emu_integrate_rejects_unsupported_shapes_and_generator_flag(monkeypatch):
+    """More than 32 samples per ray: integrate_supported says no and the generator keeps the torch ops; the flag on the real
+    generator's training graph gives the same image and the same parameter gradients as the torch ops."""
+    import cips3d_b200
+    from oracle import cips3d_oracle as O2
+    monkeypatch.setattr(cips3d_b200.generator, "_require_cuda", lambda *a, **k: None)
+    with emulated(async_mode=0) as pkg:
+        assert not pkg.ops.integrate_supported(torch.zeros(2, 3, 33, 33), torch.zeros(2, 3, 33))
+        assert not pkg.ops.integrate_supported(torch.zeros(2, 3, 8, 33), torch.zeros(2, 3, 9))
+        with pytest.raises(pkg._lib.C3dError, match="samples per ray"):
+            pkg.ops.integrate(torch.zeros(1, 2, 40, 33), torch.zeros(1, 2, 40))
+        G = build_generator("cpu", O2.synthetic_state_dict(O2.generator_template(), seed=5, sigma_bias=0.3)).train()
+        kw = dict(O2.G_KWARGS)
+        kw["num_steps"] = 6
+        res = {}
+        for backend in ("torch", "fused"):
+            G.train_integrate = backend
+            G.zero_grad()
+            torch.manual_seed(11)
+            img, _ = G(G.get_zs(2), img_size=8, nerf_noise=0.5, **kw)
+            img.square().mean().backward()
+            res[backend] = (img.detach().clone(), {k: p.grad.clone() for k, p in G.named_parameters() if p.grad is not None})
+    assert (res["fused"][0] - res["torch"][0]).abs().max().item() < 1e-4
+    assert res["fused"][1].keys() == res["torch"][1].keys() and any(k.startswith("siren.") for k in res["fused"][1])
+    for k, gr in res["torch"][1].items():
+        assert (res["fused"][1][k] - gr).abs().max().item() < 1e-3 * gr.abs().max().item() + 1e-7, k
+
+
+@pytest.mark.parametrize("name", ["spatial_r8", "spatial_r8_noise_backs", "tall_r6_lockview", "spatial_r6_nohier_s24"])
+def test_emu_pigan_training_graph_with_native_integration_matches_reference_golden(name):
+    """ImplicitGenerator3d.train_integrate = 'fused' (rgb_dim 3: one partial channel group; coarse weights under no_grad and the
+    final compositing): the image of the REAL piGAN_lib classes' golden, and the field gradients of the torch-op graph."""
+    import cips3d_b200
+    sd, z, draws, kw, meta, ref = load_pigan_case(name)
+    cls = cips3d_b200.pigan.SPATIALSIRENBASELINE if meta["siren_cls"] == "SPATIALSIRENBASELINE" else cips3d_b200.pigan.TALLSIREN
+    G = cips3d_b200.pigan.ImplicitGenerator3d(cls, z_dim=256)
+    G.load_state_dict(sd)
+    hier = kw["hierarchical_sample"]
+    origin, _, _ = O.camera_origin(draws["yaw_n"], draws["pitch_n"], kw["h_stddev"], kw["v_stddev"], kw["h_mean"], kw["v_mean"])
+    res = {}
+    for backend in ("torch", "fused"):
+        G.train_integrate = backend
+        G.zero_grad()
+        with emulated(async_mode=0):
+            fr, ph = G.siren.mapping_network(z)
+            rgb, depth = G._render_torch(fr, ph, O.cam2world(-origin, origin), draws["jitter_u"], draws["pdf_u"] if hier else None,
+                                         draws["noise_c"] if hier else None, draws["noise_f"], meta["img_size"], kw["fov"],
+                                         kw["ray_start"], kw["ray_end"], kw["num_steps"], hier, kw.get("lock_view_dependence", False),
+                                         kw["clamp_mode"], meta["nerf_noise"], kw["white_back"], kw["last_back"])
+            img = G._to_img(rgb, meta["img_size"])
+            img.square().mean().backward()
+        res[backend] = (img.detach().clone(), depth.detach().clone(), {k: p.grad.clone() for k, p in G.named_parameters()})
+    assert rel_err(res["fused"][0], ref["img"])[0] < 1e-4 and rel_err(res["fused"][1], ref["depth"])[0] < 1e-4
+    assert (res["fused"][0] - res["torch"][0]).abs().max().item() < 2e-5
+    for k, gr in res["torch"][2].items():
+        assert (res["fused"][2][k] - gr).abs().max().item() < 1e-3 * gr.abs().max().item() + 1e-8, k

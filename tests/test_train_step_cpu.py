@@ -35,12 +35,12 @@ def cpu_modules(monkeypatch):
     return cips3d_b200
 
 
-def _run(bts, frozen, optim, backend, steps=2, film="torch"):
+def _run(bts, frozen, optim, backend, steps=2, film="torch", integ="torch"):
     cfg = dict(res=16, batch=2, frozen=frozen, aux=not frozen, diffaug=frozen, grad_points=256, forward_points=256,
                warmup_D=frozen)
     torch.manual_seed(0)
     with emulated(async_mode=0, sms=2):
-        step, mods = bts.build_step(cfg, torch.device("cpu"), optim, backend, film_backend=film)
+        step, mods = bts.build_step(cfg, torch.device("cpu"), optim, backend, film_backend=film, integrate_backend=integ)
         before = {k: v.detach().clone() for k, v in mods["G"].named_parameters()}
         ema_before = {k: v.detach().clone() for k, v in mods["G_ema"].state_dict().items()}
         losses = [tuple(float(x) for x in step(it)) for it in range(steps)]
@@ -77,3 +77,8 @@ def test_train_step_full_recipe_with_aux_images(bts, cpu_modules):
     assert any(k.startswith("siren.") for k in moved2)
     assert nat2[0] == pytest.approx(ref2[0], rel=1e-5)
     assert nat2[1] == pytest.approx(ref2[1], rel=1e-4)               # after an update that went through the native backward
+    # ... and with the volume integration as the native autograd op on top (csrc/integrate_ops.cu; nerf_noise > 0 in this recipe)
+    nat3, moved3, _ = _run(bts, False, "fused", "torch", steps=2, film="fused", integ="fused")
+    assert any(k.startswith("siren.") for k in moved3)
+    assert nat3[0] == pytest.approx(ref2[0], rel=1e-5)
+    assert nat3[1] == pytest.approx(ref2[1], rel=1e-4)

@@ -76,6 +76,46 @@ for (B, P, Cn) in [(16, 16384 * 24, 128), (16, 16384 * 24, 64)]:
     out.append(dict(op="film_sin bwd: torch autograd", shape=[B, P, Cn], ms=ms_t, gbs=z.numel() * 12 / 1e9 / ms_t * 1e3, frac=z.numel() * 12 / 1e9 / ms_t * 1e3 / peak))
     del z, dy, zr, y, yt
     torch.cuda.empty_cache()
+# volume integration of the NeRF autograd graph (csrc/integrate_ops.cu): per sample forward reads C + 2 floats (+ C / T written per
+# ray), backward reads the same + d_fea and writes C + 1 -- against the torch ops of generator._torch_integrate
+for (B, N, T, Cn) in [(16, 16384, 24, 32), (8, 65536, 24, 32)]:
+    rs = torch.randn(B, N, T, Cn + 1, device=dev)
+    zs = torch.sort(0.88 + 0.24 * torch.rand(B, N, T, device=dev), -1).values
+    dfe = torch.randn(B, N, Cn, device=dev)
+    fwd_bytes = 4 * B * N * (T * (Cn + 2) + Cn + T)
+    bwd_bytes = 4 * B * N * (T * (Cn + 2) + Cn + T * (Cn + 1))
+    ms = timeit(lambda: ops.integrate(rs, zs, None, "relu", True, False), reps=10)
+    out.append(dict(op="integrate fwd", shape=[B, N, T, Cn + 1], ms=ms, gbs=fwd_bytes / 1e9 / ms * 1e3, frac=fwd_bytes / 1e9 / ms * 1e3 / peak))
+    ms_t = timeit(lambda: cips3d_b200.generator._torch_integrate(rs, zs, None, "relu", True, False, Cn), reps=10)
+    out.append(dict(op="integrate fwd: torch ops", shape=[B, N, T, Cn + 1], ms=ms_t, gbs=fwd_bytes / 1e9 / ms_t * 1e3, frac=fwd_bytes / 1e9 / ms_t * 1e3 / peak))
+    rr = rs.clone().requires_grad_()
+    fea, _ = ops.integrate(rr, zs, None, "relu", True, False)
+    ms = timeit(lambda: torch.autograd.grad(fea, rr, dfe, retain_graph=True), reps=10)
+    out.append(dict(op="integrate bwd", shape=[B, N, T, Cn + 1], ms=ms, gbs=bwd_bytes / 1e9 / ms * 1e3, frac=bwd_bytes / 1e9 / ms * 1e3 / peak))
+    fea_t, _ = cips3d_b200.generator._torch_integrate(rr, zs, None, "relu", True, False, Cn)
+    ms_t = timeit(lambda: torch.autograd.grad(fea_t, rr, dfe, retain_graph=True), reps=10)
+    out.append(dict(op="integrate bwd: torch autograd", shape=[B, N, T, Cn + 1], ms=ms_t, gbs=bwd_bytes / 1e9 / ms_t * 1e3, frac=bwd_bytes / 1e9 / ms_t * 1e3 / peak))
+    # merged form against torch's cat + sort + gather + integrate graph (what the hierarchical recipes run)
+    S = T // 2
+    fi, co = torch.randn(B, N, S, Cn + 1, device=dev).requires_grad_(), torch.randn(B, N, S, Cn + 1, device=dev).requires_grad_()
+    zf, zc = 0.88 + 0.24 * torch.rand(B, N, S, device=dev), torch.sort(0.88 + 0.24 * torch.rand(B, N, S, device=dev), -1).values
+
+    def torch_graph():
+        all_z, ind = torch.sort(torch.cat([zf, zc], -1), dim=-1)
+        all_out = torch.gather(torch.cat([fi, co], -2), -2, ind[..., None].expand(-1, -1, -1, Cn + 1))
+        return cips3d_b200.generator._torch_integrate(all_out, all_z, None, "relu", True, False, Cn)[0]
+    ms = timeit(lambda: ops.integrate_merged(fi, zf, co, zc, None, "relu", True, False), reps=10)
+    out.append(dict(op="integrate_merged fwd", shape=[B, N, T, Cn + 1], ms=ms, gbs=fwd_bytes / 1e9 / ms * 1e3, frac=fwd_bytes / 1e9 / ms * 1e3 / peak))
+    ms_t = timeit(torch_graph, reps=10)
+    out.append(dict(op="integrate_merged fwd: torch cat + sort + gather + integrate", shape=[B, N, T, Cn + 1], ms=ms_t, gbs=fwd_bytes / 1e9 / ms_t * 1e3, frac=fwd_bytes / 1e9 / ms_t * 1e3 / peak))
+    fm = ops.integrate_merged(fi, zf, co, zc, None, "relu", True, False)[0]
+    ms = timeit(lambda: torch.autograd.grad(fm, (fi, co), dfe, retain_graph=True), reps=10)
+    out.append(dict(op="integrate_merged bwd", shape=[B, N, T, Cn + 1], ms=ms, gbs=bwd_bytes / 1e9 / ms * 1e3, frac=bwd_bytes / 1e9 / ms * 1e3 / peak))
+    ft = torch_graph()
+    ms_t = timeit(lambda: torch.autograd.grad(ft, (fi, co), dfe, retain_graph=True), reps=10)
+    out.append(dict(op="integrate_merged bwd: torch autograd", shape=[B, N, T, Cn + 1], ms=ms_t, gbs=bwd_bytes / 1e9 / ms_t * 1e3, frac=bwd_bytes / 1e9 / ms_t * 1e3 / peak))
+    del rs, zs, dfe, rr, fea, fea_t, fi, co, zf, zc, fm, ft
+    torch.cuda.empty_cache()
 for r in out:
     print(json.dumps(r))
 print(json.dumps(dict(hbm_peak_gbs=peak, note="algorithmic bytes (read x + write y [+ read ref]) / CUDA-event median; L2 flushed between reps")))

@@ -43,7 +43,8 @@ def requires_grad(model, flag):
         p.requires_grad_(flag)
 
 
-def build_step(cfg, dev, optim="fused", cips_backend="torch", ddp=False, local=0, g_cfg=None, d_kwargs=None, film_backend="torch"):
+def build_step(cfg, dev, optim="fused", cips_backend="torch", ddp=False, local=0, g_cfg=None, d_kwargs=None, film_backend="torch",
+               integrate_backend="torch"):
     """Modules, optimisers and the step closure of one configuration on device `dev`.  Separate from main() so that
     tests/test_train_step_cpu.py can execute the very same step on the CPU emulation of the kernels (tiny sizes)."""
     class _A:        # the two switches the step reads
@@ -57,6 +58,7 @@ def build_step(cfg, dev, optim="fused", cips_backend="torch", ddp=False, local=0
     D = cips3d_b200.Discriminator_MultiScale_Aux(**dict(dict(diffaug=cfg["diffaug"], max_size=1024, channel_multiplier=2,
                                                              first_downsample=False, stddev_group=0), **(d_kwargs or {}))).to(dev)
     G.inr_net.train_backend = args.cips_backend
+    G.train_integrate = integrate_backend      # volume integration of the autograd graph as the native op (csrc/integrate_ops.cu)
     for m in G.modules():           # FiLM + sine of the NeRF branch's autograd graph as the native op (csrc/film_ops.cu)
         if isinstance(m, cips3d_b200.FiLMLayer):
             m.fused_film = film_backend == "fused"
@@ -146,6 +148,8 @@ def main():
                     help="fused: CIPSNet.train_backend = 'fused' (native forward + backward chain, fp16 library GEMMs for dW)")
     ap.add_argument("--film-backend", default="torch", choices=["torch", "fused"],
                     help="fused: FiLMLayer.fused_film = True (native FiLM+sine forward/backward in the NeRF autograd graph; configs with NeRF gradients)")
+    ap.add_argument("--integrate-backend", default="torch", choices=["torch", "fused"],
+                    help="fused: GeneratorNerfINR.train_integrate = 'fused' (native fancy_integration forward/backward in the NeRF autograd graph)")
     ap.add_argument("--tf32", action="store_true", help="allow TF32 in the torch autograd GEMMs / cuDNN convs of the training graph "
                     "(NOT the reference's numerics: torch defaults to fp32 matmuls); measures what the library path can give")
     args = ap.parse_args()
@@ -163,7 +167,7 @@ def main():
     if ddp:
         torch.distributed.init_process_group("nccl")
     torch.manual_seed(1234 + rank)
-    step, mods = build_step(cfg, dev, args.optim, args.cips_backend, ddp, local, film_backend=args.film_backend)
+    step, mods = build_step(cfg, dev, args.optim, args.cips_backend, ddp, local, film_backend=args.film_backend, integrate_backend=args.integrate_backend)
     G_cls = mods["G_cls"]
     R, B = cfg["res"], cfg["batch"]
 
@@ -186,7 +190,7 @@ def main():
             metric="train step (D step + G step) images/s", value=B * world / ms.item() * 1e3, unit="images/s", ms_per_step=ms.item(),
             n_gpus=world, steps=args.steps, warmup=args.warmup,
             config=dict(baseline_config=args.config, resolution=R, batch_per_gpu=B, generator=G_cls.__name__, train_aux_img=cfg["aux"],
-                        diffaug=cfg["diffaug"], grad_points=cfg["grad_points"], optim=args.optim, tf32_autograd=bool(args.tf32), cips_backend=args.cips_backend, film_backend=args.film_backend,
+                        diffaug=cfg["diffaug"], grad_points=cfg["grad_points"], optim=args.optim, tf32_autograd=bool(args.tf32), cips_backend=args.cips_backend, film_backend=args.film_backend, integrate_backend=args.integrate_backend,
                         note="G forward under no_grad runs the fused kernels; the G step's autograd graph runs as torch CUDA ops "
                              "(backward kernels: DESIGN.md section 9); D convs are cuDNN as in the reference; D's bias_act / blur are native"),
             d_loss=float(dl), g_loss=float(gl), finite=bool(math.isfinite(float(dl)) and math.isfinite(float(gl))))))
