@@ -1,5 +1,5 @@
 // Volume integration of the training graph (HBM-bound): fancy_integration of the sorted samples of a ray --
-// exp/pigan/pigan_utils.py:222-262 (called from exp/cips3d/models/generator.py:1499-1508 and, under no_grad, from
+// exp/pigan/pigan_utils.py:212-273 (called from exp/cips3d/models/generator.py:1744-1752 and, under no_grad, from
 // get_fine_points_and_direction, generator_nerf_inr.py:537-598).  The fused inference kernel composites in registers; this
 // is the same arithmetic as a differentiable op for the autograd graph of the NeRF branch (configs 1-3) and step (B) of the
 // ray-SIREN backward plan: d(loss)/d(pixels_fea) -> d(loss)/d(sigma_i), d(loss)/d(feature_i).
@@ -10,7 +10,7 @@
 //
 // Merged form (c3d_integrate_merge_*): the samples arrive as the two unsorted halves the renderer produces -- fine (rays, S, C + 1)
 // with depths z_fine, coarse (rays, S, C + 1) with depths z -- and the op does torch.cat + torch.sort + torch.gather
-// (generator.py:1489-1497) in registers: a stable rank sort of the 2S depths by warp shuffles; colour rows are then read from, and
+// (generator.py:1733-1738) in registers: a stable rank sort of the 2S depths by warp shuffles; colour rows are then read from, and
 // gradients written to, their SOURCE rows, so the cat / gather copies and the scatter of their backward never touch HBM.
 //
 // One warp per ray: lane i owns sample i (samples <= 32) for the per-sample scalars and channel(s) lane, lane + 32, ... for

@@ -600,7 +600,7 @@ def integrate_supported(rgb_sigma, z, noise=None):
 
 
 class IntegrateFunction(Function):
-    """fancy_integration (pigan_utils.py:222-262) on sorted samples as one native pass forward and one backward
+    """fancy_integration (pigan_utils.py:212-273) on sorted samples as one native pass forward and one backward
     (csrc/integrate_ops.cu).  Returns (fea, weights); gradients flow to rgb_sigma only -- z and noise are constants of the
     reference's graph too (fine depths are drawn under no_grad, generator_nerf_inr.py:537).  Saves only its inputs.
     No double backward (the generator's graph needs none)."""
@@ -609,7 +609,7 @@ class IntegrateFunction(Function):
     def forward(ctx, rgb_sigma, z, noise, clamp_mode, last_back, white_back):
         lib = load()
         if clamp_mode not in CLAMP_MODES:
-            raise AssertionError("Need to choose clamp mode")             # pigan_utils.py:249
+            raise AssertionError("Need to choose clamp mode")             # pigan_utils.py:252-253
         lead, (T, C1) = rgb_sigma.shape[:-2], rgb_sigma.shape[-2:]
         rs = rgb_sigma.contiguous()
         zc = z.contiguous()
@@ -657,7 +657,7 @@ def integrate_merged_supported(fine, z_fine, coarse, z_coarse, noise=None):
 
 
 class IntegrateMergedFunction(Function):
-    """torch.cat([fine, coarse]) + torch.sort of the depths + torch.gather + fancy_integration (generator.py:1489-1508) as one
+    """torch.cat([fine, coarse]) + torch.sort of the depths + torch.gather + fancy_integration (generator.py:1733-1752) as one
     native pass forward and one backward: the 2S samples of a ray are rank-sorted in registers, colour rows are read from and
     gradients written to their source rows (csrc/integrate_ops.cu, merged form).  Returns (fea, weights, z_sorted); gradients
     flow to fine and coarse only.  Equal depths keep cat order (a stable sort)."""
@@ -666,7 +666,7 @@ class IntegrateMergedFunction(Function):
     def forward(ctx, fine, z_fine, coarse, z_coarse, noise, clamp_mode, last_back, white_back):
         lib = load()
         if clamp_mode not in CLAMP_MODES:
-            raise AssertionError("Need to choose clamp mode")             # pigan_utils.py:249
+            raise AssertionError("Need to choose clamp mode")             # pigan_utils.py:252-253
         lead, (S, C1) = fine.shape[:-2], fine.shape[-2:]
         f, c, zf, zc = fine.contiguous(), coarse.contiguous(), z_fine.contiguous(), z_coarse.contiguous()
         nz = None if noise is None else noise.reshape(*lead, 2 * S).contiguous()
@@ -700,3 +700,27 @@ class IntegrateMergedFunction(Function):
 def integrate_merged(fine, z_fine, coarse, z_coarse, noise=None, clamp_mode="relu", last_back=False, white_back=False):
     """(fea, weights, z_sorted) of the sorted union of the fine and coarse samples; differentiable in fine and coarse."""
     return IntegrateMergedFunction.apply(fine, z_fine, coarse, z_coarse, noise, clamp_mode, last_back, white_back)
+
+
+def fancy_integration(rgb_sigma, z_vals, device=None, dim_rgb=3, noise_std=0.5, last_back=False, white_back=False,
+                      clamp_mode=None, fill_mode=None):
+    """Drop-in for exp/pigan/pigan_utils.py:212-273 (same argument meaning, return shapes, RNG draw and error behaviour):
+    rgb_sigma (b, rays, samples, dim_rgb + 1), z_vals (b, rays, samples, 1) sorted ->
+    (rgb_final (b, rays, dim_rgb), depth_final (b, rays, 1), weights (b, rays, samples, 1)), on the native op.
+    The noise is drawn exactly as the reference draws it (one torch.randn of sigma's shape, scaled by noise_std).  Gradients
+    flow to rgb_sigma through rgb_final; weights and depth_final are outputs without a graph (the reference's training loop
+    never differentiates them: the weights feed sample_pdf under no_grad, generator_nerf_inr.py:537, depth is inference-only).
+    fill_mode 'debug' / 'weight' (reference debugging aids) are not on the native path."""
+    if clamp_mode not in CLAMP_MODES:
+        assert 0, "Need to choose clamp mode"                                # pigan_utils.py:252-253
+    if fill_mode is not None:
+        raise _lib.C3dError("fancy_integration: fill_mode is a debugging aid of the reference and is not supported natively")
+    if rgb_sigma.shape[-1] != dim_rgb + 1:
+        raise _lib.C3dError(f"fancy_integration: expected dim_rgb + 1 = {dim_rgb + 1} channels, got {rgb_sigma.shape[-1]}")
+    z = z_vals.reshape(rgb_sigma.shape[:-1])
+    noise = torch.randn(rgb_sigma.shape[:-1] + (1,), device=rgb_sigma.device if device is None else device) * noise_std
+    if not integrate_supported(rgb_sigma, z, noise):
+        raise _lib.C3dError(f"fancy_integration: unsupported shape {tuple(rgb_sigma.shape)} (samples <= 32, dim_rgb <= 128, fp32)")
+    rgb_final, weights = integrate(rgb_sigma, z, noise, clamp_mode, last_back, white_back)
+    depth_final = torch.sum(weights * z, -1, keepdim=True)
+    return rgb_final, depth_final, weights.unsqueeze(-1)

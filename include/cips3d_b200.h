@@ -186,8 +186,8 @@ int c3d_film_sin_bwd(const float* z, const float* gain, const float* bias, const
 
 /* ------------------------------------------------------------------------------------
  * Volume integration of the NeRF branch's AUTOGRAD graph (SURVEY section 8(a) R14-R15 as a differentiable op; section 8(f)
- * rank 1, step (B) of the ray-SIREN backward): fancy_integration, exp/pigan/pigan_utils.py:222-262, as called from
- * exp/cips3d/models/generator.py:1499-1508 and generator_nerf_inr.py:537-598 (coarse pass, no_grad).
+ * rank 1, step (B) of the ray-SIREN backward): fancy_integration, exp/pigan/pigan_utils.py:212-273, as called from
+ * exp/cips3d/models/generator.py:1744-1752 and generator_nerf_inr.py:537-598 (coarse pass, no_grad).
  *   rgb_sigma (rays, samples, channels + 1) fp32, sigma in the last column, samples SORTED by depth; z (rays, samples);
  *   noise (rays, samples) already multiplied by nerf_noise, or NULL; softplus: 0 = relu clamp, 1 = softplus clamp.
  *   fwd: fea (rays, channels) = sum_i w_i c_i (+ 1 - sum w with white_back); weights (rays, samples) or NULL (w after last_back).
@@ -199,7 +199,7 @@ int c3d_integrate_fwd(const float* rgb_sigma, const float* z, const float* noise
 int c3d_integrate_bwd(const float* rgb_sigma, const float* z, const float* noise, const float* d_fea, float* d_rgb_sigma,
                       int64_t rays, int32_t samples, int32_t channels, int32_t softplus, int32_t last_back, int32_t white_back,
                       void* stream);
-/* Merged form: exp/cips3d/models/generator.py:1489-1508 -- torch.cat([fine, coarse]) + torch.sort of the depths + torch.gather +
+/* Merged form: exp/cips3d/models/generator.py:1733-1752 -- torch.cat([fine, coarse]) + torch.sort of the depths + torch.gather +
  * fancy_integration -- without the concatenated / gathered copies.  fine, coarse: (rays, samples_each, channels + 1) as the field
  * produced them (unsorted relative to each other); z_fine, z_coarse: (rays, samples_each).  The 2 * samples_each depths of a ray are
  * sorted in registers (stable: on equal depths the fine sample, first in cat order, comes first); noise (rays, 2 * samples_each)

@@ -83,7 +83,7 @@ def make_merged(case, seed, device="cpu"):
 
 
 def reference_merged(case, fine, z_fine, coarse, z_coarse, noise, d_fea, dtype=torch.float64):
-    """generator.py:1489-1508 in fp64: cat, sort, gather, fancy_integration; autograd to both halves."""
+    """generator.py:1733-1752 in fp64: cat, sort, gather, fancy_integration; autograd to both halves."""
     _, S, Cn, clamp, lb, wb, _ = case
     f, c = fine.detach().to(dtype).requires_grad_(), coarse.detach().to(dtype).requires_grad_()
     all_out = torch.cat([f, c], -2)
@@ -112,3 +112,45 @@ def check_merged(case, pkg, fine, z_fine, coarse, z_coarse, noise, d_fea):
     smax = max(df64[..., Cn].abs().max().item(), dc64[..., Cn].abs().max().item())
     for got, want in ((df, df64), (dc, dc64)):
         assert (got.cpu().double()[..., Cn] - want[..., Cn]).abs().max().item() < 2e-4 * smax + 1e-6
+
+
+# ------------------------------------------------------------------ goldens of the REAL pigan_utils.fancy_integration
+# (tests/golden/fancy_integration.npz, written by tools/make_golden_integrate.py from the unmodified reference)
+GOLDEN_CASES = ("relu_lastback", "softplus_white_noise", "coarse_relu_noise", "pigan_rgb3_backs", "merged_relu_lastback",
+                "merged_softplus_noise")
+
+
+def load_golden(name):
+    import os
+    import numpy as np
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "fancy_integration.npz"))
+    d = {k.split("/", 1)[1]: g[k] for k in g.files if k.startswith(name + "/")}
+    cfg = [int(v) for v in d.pop("cfg")]
+    d = {k: torch.from_numpy(v) if getattr(v, "ndim", 0) else float(v) for k, v in d.items()}
+    return cfg, d
+
+
+def check_golden(name, pkg, device="cpu"):
+    """The native op on the stored inputs and the stored noise draw vs what the real function returned (values and gradient)."""
+    (B, N, T, Cn, softplus, lb, wb, merged), d = load_golden(name)
+    clamp = "softplus" if softplus else "relu"
+    mv = lambda t: t.to(device)                                            # noqa: E731
+    noise = mv(d["noise"][..., 0]) if d["noise_std"] != 0 else None
+    leaf = mv(d["rgb_sigma"]).requires_grad_()
+    if merged:
+        S = T // 2
+        fea, w, zs = pkg.ops.integrate_merged(leaf[:, :, :S], mv(d["z_fine"][..., 0]), leaf[:, :, S:], mv(d["z_coarse"][..., 0]),
+                                              noise, clamp, bool(lb), bool(wb))
+        assert torch.equal(zs.cpu(), d["z"][..., 0])                       # the reference's sorted depths, bit for bit
+    else:
+        zs = mv(d["z"][..., 0])
+        fea, w = pkg.ops.integrate(leaf, zs, noise, clamp, bool(lb), bool(wb))
+    (grad,) = torch.autograd.grad(fea, leaf, mv(d["d_rgb"]))
+    depth = torch.sum(w * zs, -1, keepdim=True)
+    assert (w.cpu() - d["weights"][..., 0]).abs().max().item() < 1e-6
+    assert (fea.detach().cpu() - d["rgb"]).abs().max().item() < 1e-5 * (1 + d["rgb"].abs().max().item())
+    assert (depth.cpu() - d["depth"]).abs().max().item() < 1e-5
+    g_ref = d["grad"]
+    assert (grad.cpu()[..., :Cn] - g_ref[..., :Cn]).abs().max().item() < 1e-5 * (1 + g_ref[..., :Cn].abs().max().item())
+    # fp32 on both sides: the reference's own d(sigma) carries the rounding of 1 / t_i next to saturated samples
+    assert (grad.cpu()[..., Cn] - g_ref[..., Cn]).abs().max().item() < 1e-3 * g_ref[..., Cn].abs().max().item() + 1e-6

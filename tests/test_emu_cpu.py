@@ -554,13 +554,21 @@ def test_emu_outputs_are_bit_identical_across_schedules(what, env, monkeypatch):
 
 
 # ------------------------------------------------------------------ volume integration of the autograd graph (csrc/integrate_ops.cu)
-from _integrate_cases import (CASES as INTEG_CASES, MERGED_CASES, check as integ_check, check_merged, make as integ_make,  # noqa: E402
-                              make_merged)
+from _integrate_cases import (CASES as INTEG_CASES, GOLDEN_CASES as INTEG_GOLDEN, MERGED_CASES, check as integ_check,  # noqa: E402
+                              check_golden, check_merged, make as integ_make, make_merged)
+
+
+@pytest.mark.parametrize("name", INTEG_GOLDEN)
+def test_emu_integrate_matches_golden_of_the_real_fancy_integration(name):
+    """tests/golden/fancy_integration.npz holds what the UNMODIFIED pigan_utils.fancy_integration returned (and its autograd
+    gradient) -- for the merged cases after the reference's own cat + sort + gather; the native op must reproduce it."""
+    with emulated(async_mode=0) as pkg:
+        check_golden(name, pkg)
 
 
 @pytest.mark.parametrize("idx", range(len(INTEG_CASES)))
 def test_emu_integrate_forward_and_backward_match_fp64_autograd(idx):
-    """ops.IntegrateFunction against fp64 torch autograd of the oracle's fancy_integration (pigan_utils.py:222-262): features,
+    """ops.IntegrateFunction against fp64 torch autograd of the oracle's fancy_integration (pigan_utils.py:212-273): features,
     weights and the gradient w.r.t. every (feature_i, sigma_i), for both clamps, last_back / white_back, noise, 1..32 samples."""
     case = INTEG_CASES[idx]
     rs, z, noise, d_fea = integ_make(case, seed=100 + idx)
@@ -570,7 +578,7 @@ def test_emu_integrate_forward_and_backward_match_fp64_autograd(idx):
 
 @pytest.mark.parametrize("idx", range(len(MERGED_CASES)))
 def test_emu_integrate_merged_matches_fp64_autograd_of_cat_sort_gather_integrate(idx):
-    """ops.IntegrateMergedFunction: unsorted fine + coarse halves in, generator.py:1489-1508 (cat, sort, gather, fancy_integration)
+    """ops.IntegrateMergedFunction: unsorted fine + coarse halves in, generator.py:1733-1752 (cat, sort, gather, fancy_integration)
     out; the sorted depths bit for bit (incl. a tie across the halves), weights, features, and the gradients at the SOURCE rows."""
     case = MERGED_CASES[idx]
     with emulated(async_mode=0) as pkg:

@@ -3,7 +3,7 @@ tests), against the torch CUDA ops it replaces at a training-sized batch, and in
 import pytest
 import torch
 
-from _integrate_cases import CASES, MERGED_CASES, check, check_merged, make, make_merged
+from _integrate_cases import CASES, GOLDEN_CASES, MERGED_CASES, check, check_golden, check_merged, make, make_merged
 
 pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
@@ -14,6 +14,11 @@ def pkg():
     import cips3d_b200
     cips3d_b200._lib.load()
     return cips3d_b200
+
+
+@pytest.mark.parametrize("name", GOLDEN_CASES)
+def test_integrate_matches_golden_of_the_real_fancy_integration(pkg, name):
+    check_golden(name, pkg, DEV)
 
 
 @pytest.mark.parametrize("idx", range(len(CASES)))

@@ -142,3 +142,45 @@ def test_pigan_surface_constructor_state_dict_and_field_vs_reference(cls_name):
     torch.manual_seed(7)
     a_m = mine.generate_avg_frequencies()
     assert torch.equal(a_r[0], a_m[0]) and torch.equal(a_r[1], a_m[1])
+
+
+@pytest.mark.parametrize("clamp,last_back,white_back,noise_std,T,Cn", [
+    ("relu", True, False, 0.0, 24, 32), ("softplus", False, True, 0.5, 24, 32), ("relu", False, False, 0.7, 12, 32),
+    ("relu", True, True, 0.3, 24, 3)])
+def test_native_fancy_integration_vs_the_real_function(clamp, last_back, white_back, noise_std, T, Cn):
+    """ops.fancy_integration (csrc/integrate_ops.cu on the CPU emulation) against the UNMODIFIED exp/pigan/pigan_utils.py
+    function: same signature, same RNG draw (identical seed -> identical noise), same three outputs, same gradient."""
+    from _emu import emulated
+    ref_shim.install()
+    from exp.pigan import pigan_utils as ref_utils
+    g = torch.Generator().manual_seed(T * 100 + Cn)
+    rs = torch.randn(2, 29, T, Cn + 1, generator=g)
+    rs[..., Cn] = (rs[..., Cn] + 0.3) * 8
+    z = torch.sort(0.88 + 0.24 * torch.rand(2, 29, T, 1, generator=g), -2).values
+    d_rgb = torch.randn(2, 29, Cn, generator=g)
+    r0 = rs.clone().requires_grad_()
+    torch.manual_seed(77)
+    rgb0, depth0, w0 = ref_utils.fancy_integration(r0, z, device="cpu", dim_rgb=Cn, noise_std=noise_std, last_back=last_back,
+                                                   white_back=white_back, clamp_mode=clamp)
+    (g0,) = torch.autograd.grad(rgb0, r0, d_rgb)
+    with emulated(async_mode=0) as pkg:
+        r1 = rs.clone().requires_grad_()
+        torch.manual_seed(77)
+        rgb1, depth1, w1 = pkg.ops.fancy_integration(r1, z, device="cpu", dim_rgb=Cn, noise_std=noise_std, last_back=last_back,
+                                                     white_back=white_back, clamp_mode=clamp)
+        (g1,) = torch.autograd.grad(rgb1, r1, d_rgb)
+        with pytest.raises(AssertionError):
+            pkg.ops.fancy_integration(r1, z, device="cpu", dim_rgb=Cn, clamp_mode=None)       # pigan_utils.py:252-253
+    assert rgb1.shape == rgb0.shape and depth1.shape == depth0.shape and w1.shape == w0.shape
+    assert (w1 - w0.detach()).abs().max().item() < 1e-6
+    assert (rgb1.detach() - rgb0.detach()).abs().max().item() < 1e-5
+    assert (depth1 - depth0.detach()).abs().max().item() < 1e-5
+    assert (g1 - g0).abs().max().item() < 1e-4 * g0.abs().max().item() + 1e-6
+    torch.manual_seed(77)
+    ref_utils.fancy_integration(rs, z, device="cpu", dim_rgb=Cn, noise_std=noise_std, clamp_mode=clamp)
+    a = torch.rand(4)
+    with emulated(async_mode=0) as pkg:
+        torch.manual_seed(77)
+        pkg.ops.fancy_integration(rs, z, device="cpu", dim_rgb=Cn, noise_std=noise_std, clamp_mode=clamp)
+        b = torch.rand(4)
+    assert torch.equal(a, b)                     # both consumed the same amount of the torch RNG stream

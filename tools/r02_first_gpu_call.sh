@@ -42,7 +42,7 @@ timeout 600 python tools/bench_train_step.py --config 3 --optim fused --film-bac
 timeout 600 python tools/bench_train_step.py --config 3 --optim fused --film-backend fused --integrate-backend fused > $O/r02a_train_c3_fused_film_integ.json 2> $O/r02a_train_c3_fused_film_integ.err
 timeout 600 python tools/bench_train_step.py --config 5 --optim fused --cips-backend fused > $O/r02a_train_c5_fused_cipsbwd.json 2> $O/r02a_train_c5_fused_cipsbwd.err
 timeout 600 python tools/bench_train_step.py --config 5 --optim fused --tf32 > $O/r02a_train_c5_fused_tf32.json 2> $O/r02a_train_c5_fused_tf32.err
-python bench.py --steps 20 --warmup 5 > $O/r02a_bench.json 2> $O/r02a_bench.err
+python bench.py --steps 20 --warmup 5 --u8 > $O/r02a_bench.json 2> $O/r02a_bench.err
 # the same contract line with the variants that passed above (only meaningful if their tests exited 0)
 C3D_CIPS_PAIR=1 C3D_RAY_MATH=warp timeout 600 python bench.py --steps 20 --warmup 5 --no-cpu-baseline --no-eager > $O/r02a_bench_variants.json 2> $O/r02a_bench_variants.err
 tail -n 3 $O/r02a_time_kernels_default.log $O/r02a_time_kernels_pair.log $O/r02a_time_forward_default.log $O/r02a_time_forward_pair.log $O/r02a_time_forward_raywarp.log $O/r02a_time_forward_rayfold.log $O/r02a_time_forward_styleprep.log

@@ -34,3 +34,5 @@ capskip adam_ema   adam_ema_kernel        C3D_X=0         -- python tools/bench_
 capskip blur_tma   blur_tma_kernel        C3D_BLUR_TMA=1  -- python tools/bench_disc_ops.py
 capskip image_u8   image_u8_flat4_kernel  C3D_X=0         -- python tools/bench_disc_ops.py
 capskip film_bwd   film_sin_bwd_kernel    C3D_X=0         -- python tools/bench_disc_ops.py
+capskip integ_fwd  integrate_fwd_kernel   C3D_X=0         -- python tools/bench_disc_ops.py
+capskip integ_bwd  integrate_bwd_kernel   C3D_X=0         -- python tools/bench_disc_ops.py
