@@ -19,7 +19,7 @@ EXPORTS = ("c3d_version", "c3d_last_error", "c3d_device_supported", "c3d_launch_
            "c3d_optim_workspace_bytes", "c3d_grad_norm", "c3d_adam_ema_step", "c3d_ema_update",
            "c3d_pigan_workspace_bytes", "c3d_pigan_render_fwd", "c3d_cips_fwd_train", "c3d_cips_bwd_workspace_bytes", "c3d_cips_bwd", "c3d_cips_style_prep", "c3d_image_to_u8",
            "c3d_film_sin_fwd", "c3d_film_sin_bwd_workspace_bytes", "c3d_film_sin_bwd",
-           "c3d_integrate_fwd", "c3d_integrate_bwd", "c3d_integrate_merge_fwd", "c3d_integrate_merge_bwd")
+           "c3d_integrate_fwd", "c3d_integrate_bwd", "c3d_integrate_merge_fwd", "c3d_integrate_merge_bwd", "c3d_sample_pdf")
 
 _fp = C.c_void_p  # device pointers travel as integers
 
@@ -121,6 +121,7 @@ def bind(lib):
     lib.c3d_integrate_bwd.argtypes = [_fp] * 5 + [C.c_int64] + [C.c_int32] * 5 + [_fp]
     lib.c3d_integrate_merge_fwd.argtypes = [_fp] * 8 + [C.c_int64] + [C.c_int32] * 5 + [_fp]
     lib.c3d_integrate_merge_bwd.argtypes = [_fp] * 8 + [C.c_int64] + [C.c_int32] * 5 + [_fp]
+    lib.c3d_sample_pdf.argtypes = [_fp] * 4 + [C.c_int64, C.c_int32, C.c_int32, C.c_float, _fp]
     lib.c3d_image_to_u8.argtypes = [_fp, _fp] + [C.c_int32] * 6 + [C.c_double, C.c_double, _fp]
     lib.c3d_cips_fwd_train.argtypes = [C.POINTER(CipsParams), C.POINTER(CipsWeights), _fp, _fp, _fp, _fp, _fp, C.c_size_t, _fp]
     lib.c3d_cips_bwd_workspace_bytes.restype = C.c_size_t

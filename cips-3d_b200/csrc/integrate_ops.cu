@@ -311,3 +311,68 @@ extern "C" int c3d_integrate_merge_bwd(const float* fine, const float* z_fine, c
   C3D_INTEG_DISPATCH(integrate_bwd_kernel, a, (cudaStream_t)stream);
   return C3D_OK;
 }
+
+// ------------------------------------------------------------------------------------------------------------------
+// sample_pdf, exp/pigan/pigan_utils.py:164-209 (inverse-CDF resampling of the coarse weights; called under no_grad from
+// get_fine_points_and_direction, generator_nerf_inr.py:570-581), as a standalone op with the reference function's boundary:
+// bins (rays, n + 1), weights (rays, n), u (rays, k) -> samples (rays, k).  One warp per ray: lane j owns weight j (n <= 32):
+//   pdf = (w + eps) / sum(w + eps);  cdf = [0, cumsum(pdf)]  (left-to-right, as torch.cumsum);
+//   i = searchsorted(cdf, u) (first cdf[i] >= u), below = max(i - 1, 0), above = min(i, n);
+//   denom = cdf[above] - cdf[below], denom < eps -> 1;  sample = bins[below] + (u - cdf[below]) / denom * (bins[above] - bins[below]).
+// Same rounding sequence as ray_math.cuh sample_pdf_ray (the fused renderer's form, validated on hardware against the reference).
+namespace c3d {
+namespace integ {
+
+__global__ void __launch_bounds__(kThreads) sample_pdf_kernel(const float* __restrict__ bins, const float* __restrict__ weights,
+                                                              const float* __restrict__ u, float* __restrict__ samples,
+                                                              long long rays, int n, int k, float eps) {
+  const int lane = threadIdx.x & 31;
+  const long long warps = (long long)gridDim.x * (kThreads / 32);
+  for (long long ray = (long long)blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5); ray < rays; ray += warps) {
+    const float w = lane < n ? __fadd_rn(__ldg(weights + ray * n + lane), eps) : 0.f;
+    float sum = 0.f;
+    for (int j = 0; j < n; ++j) sum = __fadd_rn(sum, __shfl_sync(0xffffffffu, w, j));
+    const float pdf = __fdiv_rn(w, sum);
+    // lane j holds cdf[j] (j = 0..n): exclusive running sum, built left to right; lane n's value is the total
+    float run = 0.f, cdf = 0.f;
+    for (int j = 0; j <= n && j < 32; ++j) {
+      if (lane == j) cdf = run;
+      run = __fadd_rn(run, __shfl_sync(0xffffffffu, pdf, j));
+    }
+    const float cdf_n = run;                       // cdf[n] when n == 32 (no lane left to hold it)
+    const float bin = lane <= n && lane < 32 ? __ldg(bins + ray * (n + 1) + lane) : 0.f;
+    const float bin_n = __ldg(bins + ray * (n + 1) + n);
+    for (int k0 = 0; k0 < k; k0 += 32) {
+      const int kk = k0 + lane;
+      const float uk = kk < k ? __ldg(u + ray * k + kk) : 0.f;
+      int i = 0;                                   // first i in [0, n] with cdf[i] >= u, else n + 1
+      for (int j = 0; j <= n; ++j) {
+        const float cj = j < 32 ? __shfl_sync(0xffffffffu, cdf, j) : cdf_n;
+        i += cj < uk ? 1 : 0;                      // cdf is non-decreasing: the count of entries below u is that index
+      }
+      const int below = max(i - 1, 0), above = min(i, n);
+      const float cb0 = __shfl_sync(0xffffffffu, cdf, below & 31), ca0 = __shfl_sync(0xffffffffu, cdf, above & 31);
+      const float bb0 = __shfl_sync(0xffffffffu, bin, below & 31), ba0 = __shfl_sync(0xffffffffu, bin, above & 31);
+      const float cb = below < 32 ? cb0 : cdf_n, ca = above < 32 ? ca0 : cdf_n;
+      const float bb = below < 32 ? bb0 : bin_n, ba = above < 32 ? ba0 : bin_n;
+      float denom = __fsub_rn(ca, cb);
+      if (denom < eps) denom = 1.f;
+      if (kk < k) samples[ray * k + kk] = __fadd_rn(bb, __fmul_rn(__fdiv_rn(__fsub_rn(uk, cb), denom), __fsub_rn(ba, bb)));
+    }
+  }
+}
+
+}  // namespace integ
+}  // namespace c3d
+
+extern "C" int c3d_sample_pdf(const float* bins, const float* weights, const float* u, float* samples, int64_t rays,
+                              int32_t n_weights, int32_t n_importance, float eps, void* stream) {
+  C3D_CHECK_ARG(rays >= 0 && n_weights >= 1 && n_weights <= 32 && n_importance >= 0,
+                "sample_pdf: 1..32 weights per ray, got %d (rays %lld, samples %d)", n_weights, (long long)rays, n_importance);
+  if (rays == 0 || n_importance == 0) return C3D_OK;
+  C3D_CHECK_ARG(bins && weights && u && samples, "sample_pdf: null pointer");
+  C3D_LAUNCH(sample_pdf_kernel, grid_for(rays), kThreads, 0, (cudaStream_t)stream, bins, weights, u, samples, (long long)rays,
+             n_weights, n_importance, eps);
+  C3D_LAUNCH_CHECK();
+  return C3D_OK;
+}

@@ -487,6 +487,13 @@ def _integrate(backend, rgb_sigma, z, noise, clamp_mode, last_back, white_back, 
     return _torch_integrate(rgb_sigma, z, noise, clamp_mode, last_back, white_back, dim_rgb)
 
 
+def _sample_pdf(backend, bins, weights, u, eps=1e-5):
+    """sample_pdf of the (no_grad) resampling step: torch ops, or one native launch when `backend == 'fused'`."""
+    if backend == 'fused' and ops.sample_pdf_supported(bins, weights):
+        return ops.sample_pdf_from_u(bins, weights, u, eps)
+    return _torch_sample_pdf(bins, weights, u, eps)
+
+
 def _torch_sample_pdf(bins, weights, u, eps=1e-5):
     n_s = weights.shape[1]
     weights = weights + eps
@@ -634,7 +641,7 @@ class GeneratorNerfINR(nn.Module):              # generator.py:1158-1951
                 _, w = _integrate(self.train_integrate, coarse, z, nc, clamp_mode, False, False, dim_rgb)
                 w = w.reshape(B * N, S) + 1e-5
                 zz = z.reshape(B * N, S)
-                fz = _torch_sample_pdf(0.5 * (zz[:, :-1] + zz[:, 1:]), w[:, 1:-1], pdf_u).reshape(B, N, S)
+                fz = _sample_pdf(self.train_integrate, 0.5 * (zz[:, :-1] + zz[:, 1:]), w[:, 1:-1], pdf_u).reshape(B, N, S)
                 fpts = t[:, None, None, :] + dirs_w[:, :, None, :] * fz[..., None]
             fine = self.siren(fpts.reshape(B, N * S, 3), style_dict, None).reshape(B, N, S, -1)
             if (self.train_integrate == 'fused' and fine.shape[-1] == dim_rgb + 1

@@ -724,3 +724,32 @@ def fancy_integration(rgb_sigma, z_vals, device=None, dim_rgb=3, noise_std=0.5, 
     rgb_final, weights = integrate(rgb_sigma, z, noise, clamp_mode, last_back, white_back)
     depth_final = torch.sum(weights * z, -1, keepdim=True)
     return rgb_final, depth_final, weights.unsqueeze(-1)
+
+
+def sample_pdf_supported(bins, weights):
+    return (weights.dim() == 2 and bins.dim() == 2 and weights.dtype == torch.float32 and bins.dtype == torch.float32
+            and 1 <= weights.shape[1] <= 32 and bins.shape == (weights.shape[0], weights.shape[1] + 1))
+
+
+def sample_pdf_from_u(bins, weights, u, eps=1e-5):
+    """The arithmetic of pigan_utils.sample_pdf (L181-209) for given uniforms u (N_rays, N_importance): one native launch."""
+    lib = load()
+    if not sample_pdf_supported(bins, weights) or u.dim() != 2 or u.shape[0] != weights.shape[0] or u.dtype != torch.float32:
+        raise _lib.C3dError(f"sample_pdf: unsupported shapes bins {tuple(bins.shape)} weights {tuple(weights.shape)} u {tuple(u.shape)} "
+                            "(fp32, 1..32 weights per ray, bins one longer)")
+    b, w, uu = bins.detach().contiguous(), weights.detach().contiguous(), u.detach().contiguous()
+    out = torch.empty_like(uu)
+    check(lib.c3d_sample_pdf(ptr(b), ptr(w), ptr(uu), ptr(out), w.shape[0], w.shape[1], uu.shape[1], float(eps), stream_ptr()),
+          "c3d_sample_pdf")
+    return out
+
+
+def sample_pdf(bins, weights, N_importance, det=False, eps=1e-5):
+    """Drop-in for exp/pigan/pigan_utils.py:164-209: same arguments, the same torch.rand / torch.linspace draw, same output
+    (N_rays, N_importance).  No gradient (the reference calls it under no_grad and detaches the result)."""
+    N_rays = weights.shape[0]
+    if det:
+        u = torch.linspace(0, 1, N_importance, device=bins.device).expand(N_rays, N_importance)       # pigan_utils.py:188-190
+    else:
+        u = torch.rand(N_rays, N_importance, device=bins.device)                                       # pigan_utils.py:192
+    return sample_pdf_from_u(bins, weights, u.contiguous(), eps)

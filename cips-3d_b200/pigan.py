@@ -229,7 +229,7 @@ class ImplicitGenerator3d(nn.Module):                        # generators.py:12-
 
     def _render_torch(self, frequencies, phase_shifts, c2w, jitter_u, pdf_u, noise_c, noise_f, img_size, fov, ray_start, ray_end,
                       S, hierarchical_sample, lock_view, clamp_mode, nerf_noise, white_back, last_back):
-        from .generator import _integrate, _torch_initial_rays, _torch_sample_pdf
+        from .generator import _integrate, _sample_pdf, _torch_initial_rays
         dev = c2w.device
         dirs_cam, z_vals = _torch_initial_rays(img_size, ops.z_cam_from_fov(fov), ray_start, ray_end, S, dev)
         off = (jitter_u - 0.5) * (z_vals[1] - z_vals[0])
@@ -252,7 +252,7 @@ class ImplicitGenerator3d(nn.Module):                        # generators.py:12-
                 _, w = _integrate(self.train_integrate, coarse, z, nc, clamp_mode, False, False, 3)
                 w = w.reshape(B * N, S) + 1e-5
                 zz = z.reshape(B * N, S)
-                fz = _torch_sample_pdf(0.5 * (zz[:, :-1] + zz[:, 1:]), w[:, 1:-1], pdf_u).reshape(B, N, S)
+                fz = _sample_pdf(self.train_integrate, 0.5 * (zz[:, :-1] + zz[:, 1:]), w[:, 1:-1], pdf_u).reshape(B, N, S)
                 fpts = t[:, None, None, :] + dirs_w[:, :, None, :] * fz[..., None]
             fine = field(fpts.reshape(B, N * S, 3), frequencies, phase_shifts, ray_directions=dirs_exp).reshape(B, N, S, 4)
             if self.train_integrate == 'fused' and ops.integrate_merged_supported(fine, fz, coarse, z, nf):

@@ -212,6 +212,13 @@ int c3d_integrate_merge_bwd(const float* fine, const float* z_fine, const float*
                             const float* d_fea, float* d_fine, float* d_coarse, int64_t rays, int32_t samples_each, int32_t channels,
                             int32_t softplus, int32_t last_back, int32_t white_back, void* stream);
 
+/* sample_pdf, exp/pigan/pigan_utils.py:164-209 (called under no_grad from generator_nerf_inr.py:570-581), for given uniforms:
+ * bins (rays, n_weights + 1), weights (rays, n_weights), u (rays, n_importance) -> samples (rays, n_importance);
+ * pdf = (w + eps) / sum, cdf = [0, cumsum(pdf)], searchsorted (left), linear inverse CDF with denom < eps -> 1.
+ * n_weights <= 32.  The caller draws u (torch.rand, or linspace in the reference's det mode).                              */
+int c3d_sample_pdf(const float* bins, const float* weights, const float* u, float* samples, int64_t rays, int32_t n_weights,
+                   int32_t n_importance, float eps, void* stream);
+
 /* ------------------------------------------------------------------------------------
  * Image export for the inference paths: generator output (batch, channels, height, width)
  * fp32 -> (batch, height, width, channels) uint8 on the device, bit-identical to what the reference's scripts hand to

@@ -154,3 +154,15 @@ def check_golden(name, pkg, device="cpu"):
     assert (grad.cpu()[..., :Cn] - g_ref[..., :Cn]).abs().max().item() < 1e-5 * (1 + g_ref[..., :Cn].abs().max().item())
     # fp32 on both sides: the reference's own d(sigma) carries the rounding of 1 / t_i next to saturated samples
     assert (grad.cpu()[..., Cn] - g_ref[..., Cn]).abs().max().item() < 1e-3 * g_ref[..., Cn].abs().max().item() + 1e-6
+
+
+PDF_GOLDEN_CASES = ("pdf_s12", "pdf_n32_k40", "pdf_det", "pdf_peaky")
+
+
+def check_pdf_golden(name, pkg, device="cpu"):
+    """ops.sample_pdf_from_u on the stored bins / weights / uniforms vs what the real pigan_utils.sample_pdf returned."""
+    (rays, n, k, det), d = load_golden(name)
+    got = pkg.ops.sample_pdf_from_u(d["bins"].to(device), d["weights"].to(device), d["u"].to(device))
+    assert got.shape == (rays, k)
+    # an index that flips on a 1-ulp difference of the cdf moves the sample continuously; the bins span 0.24
+    assert (got.cpu() - d["samples"]).abs().max().item() < 2e-6

@@ -554,8 +554,19 @@ def test_emu_outputs_are_bit_identical_across_schedules(what, env, monkeypatch):
 
 
 # ------------------------------------------------------------------ volume integration of the autograd graph (csrc/integrate_ops.cu)
-from _integrate_cases import (CASES as INTEG_CASES, GOLDEN_CASES as INTEG_GOLDEN, MERGED_CASES, check as integ_check,  # noqa: E402
-                              check_golden, check_merged, make as integ_make, make_merged)
+from _integrate_cases import (CASES as INTEG_CASES, GOLDEN_CASES as INTEG_GOLDEN, MERGED_CASES, PDF_GOLDEN_CASES,  # noqa: E402
+                              check as integ_check, check_golden, check_merged, check_pdf_golden, make as integ_make,
+                              make_merged)
+
+
+@pytest.mark.parametrize("name", PDF_GOLDEN_CASES)
+def test_emu_sample_pdf_matches_golden_of_the_real_function(name):
+    """c3d_sample_pdf against outputs of the UNMODIFIED pigan_utils.sample_pdf (12 / 32 / 22 bins, 12 / 40 / 24 draws, det mode,
+    empty bins that hit the denom < eps branch)."""
+    with emulated(async_mode=0) as pkg:
+        check_pdf_golden(name, pkg)
+        with pytest.raises(pkg._lib.C3dError, match="unsupported shapes"):
+            pkg.ops.sample_pdf_from_u(torch.zeros(2, 35), torch.zeros(2, 34), torch.zeros(2, 4))
 
 
 @pytest.mark.parametrize("name", INTEG_GOLDEN)

@@ -3,7 +3,8 @@ tests), against the torch CUDA ops it replaces at a training-sized batch, and in
 import pytest
 import torch
 
-from _integrate_cases import CASES, GOLDEN_CASES, MERGED_CASES, check, check_golden, check_merged, make, make_merged
+from _integrate_cases import (CASES, GOLDEN_CASES, MERGED_CASES, PDF_GOLDEN_CASES, check, check_golden, check_merged,
+                              check_pdf_golden, make, make_merged)
 
 pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
@@ -19,6 +20,11 @@ def pkg():
 @pytest.mark.parametrize("name", GOLDEN_CASES)
 def test_integrate_matches_golden_of_the_real_fancy_integration(pkg, name):
     check_golden(name, pkg, DEV)
+
+
+@pytest.mark.parametrize("name", PDF_GOLDEN_CASES)
+def test_sample_pdf_matches_golden_of_the_real_function(pkg, name):
+    check_pdf_golden(name, pkg, DEV)
 
 
 @pytest.mark.parametrize("idx", range(len(CASES)))

@@ -184,3 +184,24 @@ def test_native_fancy_integration_vs_the_real_function(clamp, last_back, white_b
         pkg.ops.fancy_integration(rs, z, device="cpu", dim_rgb=Cn, noise_std=noise_std, clamp_mode=clamp)
         b = torch.rand(4)
     assert torch.equal(a, b)                     # both consumed the same amount of the torch RNG stream
+
+
+@pytest.mark.parametrize("n,k,det", [(10, 12, False), (10, 12, True), (32, 40, False)])
+def test_native_sample_pdf_vs_the_real_function(n, k, det):
+    """ops.sample_pdf (emulation): the reference function's signature, its torch.rand / linspace draw and its output."""
+    from _emu import emulated
+    ref_shim.install()
+    from exp.pigan import pigan_utils as ref_utils
+    g = torch.Generator().manual_seed(n * 10 + k)
+    w = torch.rand(41, n, generator=g) + 1e-5
+    edges = torch.sort(0.88 + 0.24 * torch.rand(41, n + 2, generator=g), -1).values
+    bins = 0.5 * (edges[:, :-1] + edges[:, 1:])
+    torch.manual_seed(3)
+    want = ref_utils.sample_pdf(bins, w, k, det=det)
+    a = torch.rand(2)
+    with emulated(async_mode=0) as pkg:
+        torch.manual_seed(3)
+        got = pkg.ops.sample_pdf(bins, w, k, det=det)
+        b = torch.rand(2)
+    assert got.shape == want.shape and (got - want).abs().max().item() < 2e-6
+    assert torch.equal(a, b)                      # same RNG consumption (none in det mode)

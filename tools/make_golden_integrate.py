@@ -1,4 +1,5 @@
 """Generate tests/golden/fancy_integration.npz from the UNMODIFIED reference function exp/pigan/pigan_utils.py:212-273
+and, for the pdf_* cases, from sample_pdf (pigan_utils.py:164-209)
 (needs /root/reference; imported through tools/ref_shim.py):
 
     python tools/make_golden_integrate.py
@@ -67,6 +68,22 @@ def main():
             out[f"{name}/{k}"] = v.numpy()
         out[f"{name}/cfg"] = np.array([B, N, T, Cn, int(clamp == "softplus"), int(lb), int(wb), int(merged)], dtype=np.int64)
         out[f"{name}/noise_std"] = np.float32(nstd)
+    # sample_pdf (pigan_utils.py:164-209): weights as at its call site (coarse weights + 1e-5, inner slice), bins = midpoints
+    for idx, (name, (rays, n, k, det)) in enumerate({"pdf_s12": (37, 10, 12, False), "pdf_n32_k40": (9, 32, 40, False),
+                                                      "pdf_det": (11, 10, 12, True), "pdf_peaky": (23, 22, 24, False)}.items()):
+        rng = np.random.Generator(np.random.PCG64(7700 + idx))
+        w = torch.from_numpy(rng.random((rays, n)).astype(np.float32)) ** (8 if "peaky" in name else 1) + 1e-5
+        if "peaky" in name:
+            w[:, ::3] = 1e-5                                                                  # empty bins (alpha = 0 samples)
+        edges = torch.sort(torch.from_numpy((0.88 + 0.24 * rng.random((rays, n + 2))).astype(np.float32)), -1).values
+        bins = 0.5 * (edges[:, :-1] + edges[:, 1:])
+        torch.manual_seed(500 + idx)
+        samples = ref_utils.sample_pdf(bins, w, k, det=det)
+        torch.manual_seed(500 + idx)
+        u = torch.linspace(0, 1, k).expand(rays, k).contiguous() if det else torch.rand(rays, k)
+        for key, v in dict(bins=bins, weights=w, u=u, samples=samples).items():
+            out[f"{name}/{key}"] = v.numpy()
+        out[f"{name}/cfg"] = np.array([rays, n, k, int(det)], dtype=np.int64)
     np.savez_compressed(OUT, **out)
     print("wrote", OUT, os.path.getsize(OUT), "bytes")
 
