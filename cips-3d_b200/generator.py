@@ -714,6 +714,67 @@ class GeneratorNerfINR(nn.Module):              # generator.py:1158-1951
     def _aux(self, pixels_fea):
         return self.aux_to_rbg(pixels_fea)
 
+    # ---------------------------------------------------------------- explicit-points entry (generator.py:1659-1762)
+    def _field(self, points, style_dict, ray_directions):
+        """the NeRF field on explicit points; subclasses decide whether it carries a graph"""
+        return self.siren(input=points, style_dict=style_dict, ray_directions=ray_directions)
+
+    @torch.no_grad()
+    def get_fine_points_and_direction(self, coarse_output, z_vals, dim_rgb, clamp_mode, nerf_noise, num_steps,
+                                      transformed_ray_origins, transformed_ray_directions):
+        """generator_nerf_inr.py:537-598: coarse weights -> sample_pdf over the bin mid-points -> fine points, all without a
+        graph.  Same draws in the same order as the reference (randn of sigma's shape, then rand(rays, num_steps))."""
+        b = coarse_output.shape[0]
+        z = z_vals.reshape(coarse_output.shape[:-1])
+        noise = torch.randn(coarse_output.shape[:-1] + (1,), device=coarse_output.device)[..., 0] * nerf_noise   # pigan_utils.py:246
+        _, weights = _integrate(self.train_integrate, coarse_output, z, noise, clamp_mode, False, False, dim_rgb)
+        weights = weights.reshape(-1, num_steps) + 1e-5
+        zz = z.reshape(-1, num_steps)
+        u = torch.rand(zz.shape[0], num_steps, device=zz.device)                                              # pigan_utils.py:192
+        fine_z = _sample_pdf(self.train_integrate, 0.5 * (zz[:, :-1] + zz[:, 1:]), weights[:, 1:-1], u).detach()
+        fine_z = fine_z.reshape(b, -1, num_steps, 1)
+        fine_points = transformed_ray_origins.unsqueeze(2) + transformed_ray_directions.unsqueeze(2) * fine_z.expand(-1, -1, -1, 3)
+        return fine_points.reshape(b, -1, 3), fine_z
+
+    def points_forward(self, style_dict, transformed_points, transformed_ray_directions_expanded, num_steps, hierarchical_sample,
+                       z_vals, clamp_mode, nerf_noise, transformed_ray_origins, transformed_ray_directions, white_back, last_back,
+                       return_aux_img, idx_grad=None):
+        """generator.py:1659-1762 (reference signature): field on the given points (b, n, s, 3) -> resampling -> merge ->
+        fancy_integration -> CIPS MLP [-> aux head]; returns (inr_img (b, n, 3), aux_img (b, n, 3) or None).  The points are
+        the caller's, so this is the differentiable form of the path: the field runs as torch ops, integration / resampling /
+        merge on the native ops when `train_integrate == 'fused'`, the CIPS MLP on the fused kernels when no graph is needed.
+        `forward` itself never comes through here: it renders from the cameras with the fused kernels."""
+        _require_cuda(transformed_points, "GeneratorNerfINR.points_forward")
+        if idx_grad is not None:
+            pick = lambda t: t.index_select(1, idx_grad)                   # comm_utils.gather_points, L262-282  # noqa: E731
+            transformed_points, transformed_ray_directions_expanded, z_vals = (
+                pick(transformed_points), pick(transformed_ray_directions_expanded), pick(z_vals))
+            transformed_ray_origins, transformed_ray_directions = pick(transformed_ray_origins), pick(transformed_ray_directions)
+        b, n = transformed_points.shape[:2]
+        dim_rgb = self.siren.rgb_dim
+        dirs = transformed_ray_directions_expanded.reshape(b, n * num_steps, 3)
+        coarse = self._field(transformed_points.reshape(b, n * num_steps, 3), style_dict, dirs).reshape(b, n, num_steps, -1)
+        z = z_vals.reshape(b, n, num_steps)
+        if hierarchical_sample:
+            fine_points, fine_z = self.get_fine_points_and_direction(
+                coarse_output=coarse, z_vals=z_vals, dim_rgb=dim_rgb, clamp_mode=clamp_mode, nerf_noise=nerf_noise,
+                num_steps=num_steps, transformed_ray_origins=transformed_ray_origins,
+                transformed_ray_directions=transformed_ray_directions)
+            fine = self._field(fine_points, style_dict, dirs).reshape(b, n, num_steps, -1)
+            fz = fine_z[..., 0]
+            noise = torch.randn(b, n, 2 * num_steps, 1, device=coarse.device)[..., 0] * nerf_noise            # pigan_utils.py:246
+            if self.train_integrate == 'fused' and ops.integrate_merged_supported(fine, fz, coarse, z, noise):
+                pixels_fea = ops.integrate_merged(fine, fz, coarse, z, noise, clamp_mode, last_back, white_back)[0]
+            else:
+                all_z, ind = torch.sort(torch.cat([fz, z], -1), dim=-1)                                        # L1733-1738
+                all_out = torch.gather(torch.cat([fine, coarse], -2), -2, ind[..., None].expand(-1, -1, -1, coarse.shape[-1]))
+                pixels_fea, _ = _torch_integrate(all_out, all_z, noise, clamp_mode, last_back, white_back, dim_rgb)
+        else:
+            noise = torch.randn(b, n, num_steps, 1, device=coarse.device)[..., 0] * nerf_noise
+            pixels_fea, _ = _integrate(self.train_integrate, coarse, z, noise, clamp_mode, last_back, white_back, dim_rgb)
+        inr_img = self.inr_net(pixels_fea, style_dict)
+        return inr_img, (self._aux(pixels_fea) if return_aux_img else None)
+
     def whole_grad_forward(self, style_dict, img_size, fov, ray_start, ray_end, num_steps, h_stddev, v_stddev,
                            h_mean, v_mean, hierarchical_sample, sample_dist=None, lock_view_dependence=False,
                            clamp_mode='relu', nerf_noise=0., white_back=False, last_back=False,
@@ -848,3 +909,7 @@ class GeneratorNerfINR_freeze_NeRF(GeneratorNerfINR):      # generator.py:1954-2
     def _aux(self, pixels_fea):
         with torch.no_grad():
             return self.aux_to_rbg(pixels_fea)
+
+    def _field(self, points, style_dict, ray_directions):                   # generator.py:2013-2044: the field under no_grad
+        with torch.no_grad():
+            return self.siren(input=points, style_dict=style_dict, ray_directions=ray_directions)

@@ -205,3 +205,55 @@ def test_native_sample_pdf_vs_the_real_function(n, k, det):
         b = torch.rand(2)
     assert got.shape == want.shape and (got - want).abs().max().item() < 2e-6
     assert torch.equal(a, b)                      # same RNG consumption (none in det mode)
+
+
+_PF_HIER = (True, 0.4, dict(clamp_mode="relu", white_back=False, last_back=True))
+_PF_FLAT = (False, 0.0, dict(clamp_mode="softplus", white_back=True, last_back=False))
+
+
+@pytest.mark.parametrize("frozen,backend,case", [(False, "torch", _PF_HIER), (False, "fused", _PF_HIER), (True, "fused", _PF_HIER),
+                                                 (False, "fused", _PF_FLAT)])
+def test_points_forward_vs_reference(monkeypatch, frozen, backend, case):
+    """GeneratorNerfINR[_freeze_NeRF].points_forward (generator.py:1659-1762 / 1972-2078; reference signature) against the
+    UNMODIFIED method on identical weights, points and seed -- same three RNG draws, same images, same parameter gradients;
+    with the torch ops and with the native integration / resampling / merge ops (CPU emulation)."""
+    import cips3d_b200
+    from _emu import emulated
+    from _util import build_generator
+    hier, noise, kw = case
+    monkeypatch.setattr(cips3d_b200.generator, "_require_cuda", lambda *a, **k: None)
+    torch.manual_seed(21)
+    Gr = ref_shim.build_reference_generator(frozen=frozen).train()
+    G = build_generator("cpu", {k: v.clone() for k, v in Gr.state_dict().items()}, frozen=frozen).train()
+    G.train_integrate = backend
+    b, n, s = 2, 37, 12
+    g = torch.Generator().manual_seed(5)
+    origins = torch.randn(b, n, 3, generator=g) * 0.05 + torch.tensor([0., 0., 1.])
+    dirs = torch.nn.functional.normalize(torch.randn(b, n, 3, generator=g) * 0.05 + torch.tensor([0., 0., -1.]), dim=-1)
+    z_vals = torch.sort(0.88 + 0.24 * torch.rand(b, n, s, 1, generator=g), -2).values
+    points = origins[:, :, None] + dirs[:, :, None] * z_vals
+    dirs_exp = dirs[:, :, None].expand(-1, -1, s, -1).contiguous()
+    idx = torch.randperm(n, generator=g)[:29]
+    zs = {"z_nerf": torch.randn(b, 256, generator=g), "z_inr": torch.randn(b, 512, generator=g)}
+    args = dict(transformed_points=points, transformed_ray_directions_expanded=dirs_exp, num_steps=s, hierarchical_sample=hier,
+                z_vals=z_vals, nerf_noise=noise, transformed_ray_origins=origins, transformed_ray_directions=dirs,
+                return_aux_img=True, idx_grad=idx, **kw)
+    out = {}
+    for name, model in (("ref", Gr), ("new", G)):
+        model.zero_grad()
+        with emulated(async_mode=0):
+            style = model.mapping_network(**zs)
+            torch.manual_seed(99)
+            inr, aux = model.points_forward(style_dict=style, **args)
+            after = torch.rand(3)
+            (inr.square().mean() + (aux.square().mean() if aux.requires_grad else 0)).backward()
+        out[name] = (inr.detach(), aux.detach(), after, {k: p.grad.clone() for k, p in model.named_parameters() if p.grad is not None})
+    assert torch.equal(out["new"][2], out["ref"][2])                        # same RNG consumption
+    assert (out["new"][0] - out["ref"][0]).abs().max().item() < 2e-5 and (out["new"][1] - out["ref"][1]).abs().max().item() < 2e-5
+    assert out["new"][3].keys() == out["ref"][3].keys()
+    assert any(k.startswith("siren.") for k in out["ref"][3]) == (not frozen)
+    for k, gr in out["ref"][3].items():
+        if backend == "torch":                  # identical arithmetic to the reference's
+            assert (out["new"][3][k] - gr).abs().max().item() < 1e-3 * gr.abs().max().item() + 1e-7, k
+        else:   # ~1e-6 differences of pixels_fea flip LeakyReLU gates of |z| ~ 0 units in the CIPS MLP (29 pixels): compare in L2
+            assert (out["new"][3][k] - gr).norm().item() < 1e-2 * gr.norm().item() + 1e-7, k
