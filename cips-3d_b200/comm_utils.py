@@ -94,3 +94,15 @@ def scatter_points(idx_grad, points_grad, idx_no_grad, points_no_grad, num_point
     out = points_grad.new_zeros(points_grad.shape[0], num_points, points_grad.shape[-1])
     out = out.index_copy(1, idx_grad, points_grad)
     return out.index_copy(1, idx_no_grad, points_no_grad.to(out.dtype))
+
+
+def get_world_points_and_direction(*args, **kwargs):
+    """comm_utils.py:682-763 (reference signature); implemented next to the other ray helpers in generator.py"""
+    from .generator import get_world_points_and_direction as impl
+    return impl(*args, **kwargs)
+
+
+def gather_points(points, idx_grad):
+    """comm_utils.py:262-282: rays `idx_grad` of (b, n, c) or (b, n, s, c)"""
+    assert points.dim() in (3, 4)
+    return points.index_select(1, idx_grad)

@@ -457,6 +457,33 @@ def _torch_initial_rays(img_size, z_cam, ray_start, ray_end, num_steps, device):
     return comm_utils.normalize_vecs(d), torch.linspace(ray_start, ray_end, num_steps, device=device)
 
 
+def get_world_points_and_direction(batch_size, num_steps, img_size, fov, ray_start, ray_end, h_stddev, v_stddev, h_mean, v_mean,
+                                   sample_dist, lock_view_dependence, device='cuda', camera_pos=None, camera_lookup=None,
+                                   up_vector=None):
+    """exp/comm/comm_utils.py:682-763 with the reference's signature, return tuple and RNG order (jitter rand(b, hw, s, 1), then
+    the camera draws): (transformed_points (b, hw*s, 3), transformed_ray_directions_expanded (b, hw*s, 3), transformed_ray_origins
+    (b, hw, 3), transformed_ray_directions (b, hw, 3), z_vals (b, hw, s, 1), pitch (b, 1), yaw (b, 1)).  O(points) elementwise
+    work as torch ops on `device`: the explicit-points form of rows R2-R7, which the fused renderer computes in registers;
+    it feeds `points_forward`."""
+    dirs_cam, z_lin = _torch_initial_rays(img_size, ops.z_cam_from_fov(fov), ray_start, ray_end, num_steps, device)
+    n = dirs_cam.shape[0]
+    jitter_u = torch.rand((batch_size, n, num_steps, 1), device=device)[..., 0]                 # perturb_points, L416-437
+    off = (jitter_u - 0.5) * (z_lin[1] - z_lin[0])
+    z_vals = z_lin[None, None, :] + off
+    p_cam = dirs_cam[None, :, None, :] * z_lin[None, None, :, None] + off[..., None] * dirs_cam[None, :, None, :]
+    c2w, pitch, yaw = comm_utils.sample_cam2world(batch_size, device, h_stddev, v_stddev, h_mean, v_mean, sample_dist,
+                                                  camera_pos=camera_pos, camera_lookup=camera_lookup, up_vector=up_vector)
+    Rm, t = c2w[:, :3, :3], c2w[:, :3, 3]
+    pts = torch.einsum("bij,bnsj->bnsi", Rm, p_cam) + t[:, None, None, :]                        # transform_sampled_points, L584-679
+    dirs_w = torch.einsum("bij,nj->bni", Rm, dirs_cam)
+    origins = t[:, None, :].expand(-1, n, -1).contiguous()
+    dirs_exp = dirs_w[:, :, None, :].expand(-1, -1, num_steps, -1).reshape(batch_size, n * num_steps, 3)
+    if lock_view_dependence:
+        dirs_exp = torch.zeros_like(dirs_exp)
+        dirs_exp[..., -1] = -1
+    return pts.reshape(batch_size, n * num_steps, 3), dirs_exp, origins, dirs_w, z_vals[..., None], pitch, yaw
+
+
 def _torch_integrate(rgb_sigma, z, noise, clamp_mode, last_back, white_back, dim_rgb):
     rgbs, sig = rgb_sigma[..., :dim_rgb], rgb_sigma[..., dim_rgb]
     deltas = z[..., 1:] - z[..., :-1]

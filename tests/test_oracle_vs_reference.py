@@ -257,3 +257,27 @@ def test_points_forward_vs_reference(monkeypatch, frozen, backend, case):
             assert (out["new"][3][k] - gr).abs().max().item() < 1e-3 * gr.abs().max().item() + 1e-7, k
         else:   # ~1e-6 differences of pixels_fea flip LeakyReLU gates of |z| ~ 0 units in the CIPS MLP (29 pixels): compare in L2
             assert (out["new"][3][k] - gr).norm().item() < 1e-2 * gr.norm().item() + 1e-7, k
+
+
+@pytest.mark.parametrize("lock,cam", [(False, False), (True, False), (False, True)])
+def test_get_world_points_and_direction_vs_reference(lock, cam):
+    """cips3d_b200.comm_utils.get_world_points_and_direction against exp/comm/comm_utils.py:682-763: same signature, the same
+    seven outputs, the same RNG order (jitter, then the camera draws), also with a given camera and lock_view_dependence."""
+    import cips3d_b200
+    ref_shim.install()
+    from exp.comm import comm_utils as ref_cu
+    kw = dict(batch_size=2, num_steps=12, img_size=9, fov=12, ray_start=0.88, ray_end=1.12, h_stddev=0.3, v_stddev=0.155,
+              h_mean=1.5707963, v_mean=1.5707963, sample_dist="gaussian", lock_view_dependence=lock, device="cpu")
+    if cam:
+        kw.update(camera_pos=torch.tensor([[0.1, 0.2, 0.97], [-0.2, 0.0, 0.98]]), camera_lookup=torch.tensor([[-0.1, -0.2, -0.97], [0.2, 0.0, -0.98]]))
+    torch.manual_seed(8)
+    want = ref_cu.get_world_points_and_direction(**kw)
+    a = torch.rand(3)
+    torch.manual_seed(8)
+    got = cips3d_b200.comm_utils.get_world_points_and_direction(**kw)
+    b = torch.rand(3)
+    assert torch.equal(a, b) and len(got) == len(want) == 7
+    for i, (g_, w_) in enumerate(zip(got, want)):
+        assert g_.shape == w_.shape, i
+        assert (g_ - w_).abs().max().item() < 2e-6, i
+    assert torch.equal(cips3d_b200.comm_utils.gather_points(got[2], torch.tensor([3, 1])), ref_cu.gather_points(got[2], torch.tensor([3, 1])))
