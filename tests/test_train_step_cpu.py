@@ -66,19 +66,14 @@ def test_train_step_frozen_recipe_fused_vs_torch_paths(bts, cpu_modules):
 
 
 def test_train_step_full_recipe_with_aux_images(bts, cpu_modules):
-    """config 3 (GeneratorNerfINR, train_aux_img, nerf_noise schedule): NeRF and mapping weights receive gradients."""
-    losses, moved, ema_moved = _run(bts, False, "fused", "torch", steps=1)
-    assert all(math.isfinite(x) for x in losses[0]) and ema_moved
+    """config 3 (GeneratorNerfINR, train_aux_img, nerf_noise schedule): NeRF and mapping weights receive gradients; then the
+    same two steps with the NeRF branch's FiLM + sine (csrc/film_ops.cu) and its volume integration / resampling / merge
+    (csrc/integrate_ops.cu; nerf_noise > 0 in this recipe) as the native autograd ops."""
+    ref2, moved, ema_moved = _run(bts, False, "fused", "torch", steps=2)
+    assert all(math.isfinite(x) for pair in ref2 for x in pair) and ema_moved
     for prefix in ("siren.", "mapping_network_nerf.", "inr_net.", "mapping_network_inr.", "aux_to_rbg."):
         assert any(k.startswith(prefix) for k in moved), prefix
-    # the same two steps with the NeRF branch's FiLM + sine as the native autograd op (csrc/film_ops.cu)
-    ref2, _, _ = _run(bts, False, "fused", "torch", steps=2)
-    nat2, moved2, _ = _run(bts, False, "fused", "torch", steps=2, film="fused")
-    assert any(k.startswith("siren.") for k in moved2)
-    assert nat2[0] == pytest.approx(ref2[0], rel=1e-5)
-    assert nat2[1] == pytest.approx(ref2[1], rel=1e-4)               # after an update that went through the native backward
-    # ... and with the volume integration as the native autograd op on top (csrc/integrate_ops.cu; nerf_noise > 0 in this recipe)
-    nat3, moved3, _ = _run(bts, False, "fused", "torch", steps=2, film="fused", integ="fused")
-    assert any(k.startswith("siren.") for k in moved3)
-    assert nat3[0] == pytest.approx(ref2[0], rel=1e-5)
-    assert nat3[1] == pytest.approx(ref2[1], rel=1e-4)
+    nat, moved_nat, _ = _run(bts, False, "fused", "torch", steps=2, film="fused", integ="fused")
+    assert any(k.startswith("siren.") for k in moved_nat)
+    assert nat[0] == pytest.approx(ref2[0], rel=1e-5)
+    assert nat[1] == pytest.approx(ref2[1], rel=1e-4)               # after an update that went through the native backwards
