@@ -106,3 +106,53 @@ def gather_points(points, idx_grad):
     """comm_utils.py:262-282: rays `idx_grad` of (b, n, c) or (b, n, s, c)"""
     assert points.dim() in (3, 4)
     return points.index_select(1, idx_grad)
+
+
+# ---------------------------------------------------------------- host-side helpers of the inference / finetune scripts
+def inr_layer_swapping(swapped_net, target_net, gamma_target, swapped_layers, verbose=True):
+    """comm_utils.py:28-51 (finetune / interpolation demos): blend the CIPS blocks `network.<name>` and `to_rgbs.<name>` of
+    `swapped_net` towards `target_net` in place: p <- (1 - gamma) p + gamma p_target."""
+    import logging
+    prefixes = tuple(f"{kind}.{name}" for name in swapped_layers for kind in ("network", "to_rgbs"))
+    if verbose:
+        logging.getLogger('tl').info(f"Layer swapping: {prefixes}")
+    target = target_net.state_dict()
+    with torch.no_grad():
+        for name, p in swapped_net.named_parameters():
+            if prefixes and name.startswith(prefixes):
+                p.copy_(p * (1 - gamma_target) + target[name].to(p.device) * gamma_target)
+
+
+def get_yaw_pitch_by_xyz(x, y, z):
+    """comm_utils.py:82-85"""
+    return math.atan2(z, x), math.atan2(math.sqrt(x ** 2 + z ** 2), y)
+
+
+def _trajectory(xyz):
+    """(xyz float32 (n, 3), lookup = -xyz, yaws, pitchs float64) -- the return convention of comm_utils.py:87-110, 219-238"""
+    import numpy as np
+    xyz = np.asarray(xyz, dtype=np.float32)
+    # the rows are iterated as float32 scalars, as the reference does: x ** 2 + z ** 2 is then rounded in float32
+    yp = np.array([get_yaw_pitch_by_xyz(x, y, z) for x, y, z in xyz], dtype=np.float64).reshape(-1, 2)
+    return xyz, -xyz, yp[:, 0].copy(), yp[:, 1].copy()
+
+
+def get_circle_camera_pos_and_lookup(r=1, alpha=3.141592 / 6, num_samples=36, periods=2):
+    """comm_utils.py:87-110: `periods` turns around the z axis on the cone of half-angle alpha (camera path of the videos)"""
+    import numpy as np
+    n = num_samples * periods
+    xyz = np.zeros((n, 3), dtype=np.float32)
+    rho = r * math.sin(alpha)
+    for i, t in enumerate(np.linspace(1, 0, n)):
+        beta = t * 2 * math.pi * periods
+        xyz[i] = (rho * math.cos(beta), rho * math.sin(beta), r * math.cos(alpha))
+    return _trajectory(xyz)
+
+
+def get_yaw_camera_pos_and_lookup(r=1, num_samples=36):
+    """comm_utils.py:219-238: a yaw sweep in the y = 0 plane, theta from 1 to pi - 1"""
+    import numpy as np
+    xyz = np.zeros((num_samples, 3), dtype=np.float32)
+    for i, theta in enumerate(np.linspace(1, math.pi - 1, num_samples)):
+        xyz[i] = (r * math.cos(theta), 0, r * math.sin(theta))
+    return _trajectory(xyz)

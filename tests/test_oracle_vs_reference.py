@@ -281,3 +281,29 @@ def test_get_world_points_and_direction_vs_reference(lock, cam):
         assert g_.shape == w_.shape, i
         assert (g_ - w_).abs().max().item() < 2e-6, i
     assert torch.equal(cips3d_b200.comm_utils.gather_points(got[2], torch.tensor([3, 1])), ref_cu.gather_points(got[2], torch.tensor([3, 1])))
+
+
+def test_host_helpers_of_the_inference_scripts_vs_reference():
+    """comm_utils camera trajectories (bit for bit) and inr_layer_swapping (same parameters touched, same blend)."""
+    import copy
+    import numpy as np
+    import cips3d_b200
+    from _util import build_generator
+    ref_shim.install()
+    from exp.comm import comm_utils as ref_cu
+    cu = cips3d_b200.comm_utils
+    for a, b in ((cu.get_circle_camera_pos_and_lookup(r=1.1, alpha=0.4, num_samples=7, periods=2),
+                  ref_cu.get_circle_camera_pos_and_lookup(r=1.1, alpha=0.4, num_samples=7, periods=2)),
+                 (cu.get_circle_camera_pos_and_lookup(), ref_cu.get_circle_camera_pos_and_lookup()),
+                 (cu.get_yaw_camera_pos_and_lookup(r=1, num_samples=9), ref_cu.get_yaw_camera_pos_and_lookup(r=1, num_samples=9))):
+        for x, y in zip(a, b):
+            assert x.dtype == y.dtype and np.array_equal(x, y)
+    assert cu.get_yaw_pitch_by_xyz(0.3, -0.2, 0.9) == ref_cu.get_yaw_pitch_by_xyz(0.3, -0.2, 0.9)
+    torch.manual_seed(2)
+    A = build_generator("cpu").inr_net
+    B = copy.deepcopy(A)
+    T = build_generator("cpu").inr_net                      # different random init
+    cu.inr_layer_swapping(A, T, 0.3, ["64", "1024"], verbose=False)
+    ref_cu.inr_layer_swapping(B, T, 0.3, ["64", "1024"], verbose=False)
+    for (k, p), q in zip(A.state_dict().items(), B.state_dict().values()):
+        assert torch.equal(p, q), k
