@@ -45,7 +45,8 @@ def check(case, pkg, rs, z, noise, d_fea):
     (dr,) = torch.autograd.grad(fea, r, d_fea)
     f64, w64, d64 = reference(case, rs.cpu(), z.cpu(), None if noise is None else noise.cpu(), d_fea.cpu())
     fea, w, dr = fea.detach().cpu().double(), w.cpu().double(), dr.cpu().double()
-    assert (w - w64).abs().max().item() < 2e-6                              # weights are in [0, 1]
+    # weights are in [0, 1]; a product of up to 32 factors 1 - alpha_j, each carrying expf's rounding (<= 2 ulp on the GPU)
+    assert (w - w64).abs().max().item() < 5e-6
     assert (fea - f64).abs().max().item() < 1e-5 * (1 + f64.abs().max().item())
     dc, dc64 = dr[..., :Cn], d64[..., :Cn]
     assert (dc - dc64).abs().max().item() < 1e-5 * (1 + dc64.abs().max().item())
@@ -104,7 +105,7 @@ def check_merged(case, pkg, fine, z_fine, coarse, z_coarse, noise, d_fea):
     cpu = lambda t: None if t is None else t.cpu()                         # noqa: E731
     f64, w64, z64, df64, dc64 = reference_merged(case, *(cpu(t) for t in (fine, z_fine, coarse, z_coarse, noise, d_fea)))
     assert torch.equal(zs.cpu(), z64)                                       # the sort itself is exact
-    assert (w.cpu().double() - w64).abs().max().item() < 2e-6
+    assert (w.cpu().double() - w64).abs().max().item() < 5e-6
     assert (fea.detach().cpu().double() - f64).abs().max().item() < 1e-5 * (1 + f64.abs().max().item())
     for got, want in ((df, df64), (dc, dc64)):
         got = got.cpu().double()
@@ -147,7 +148,7 @@ def check_golden(name, pkg, device="cpu"):
         fea, w = pkg.ops.integrate(leaf, zs, noise, clamp, bool(lb), bool(wb))
     (grad,) = torch.autograd.grad(fea, leaf, mv(d["d_rgb"]))
     depth = torch.sum(w * zs, -1, keepdim=True)
-    assert (w.cpu() - d["weights"][..., 0]).abs().max().item() < 1e-6
+    assert (w.cpu() - d["weights"][..., 0]).abs().max().item() < 5e-6
     assert (fea.detach().cpu() - d["rgb"]).abs().max().item() < 1e-5 * (1 + d["rgb"].abs().max().item())
     assert (depth.cpu() - d["depth"]).abs().max().item() < 1e-5
     g_ref = d["grad"]
