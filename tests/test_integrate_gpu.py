@@ -90,3 +90,37 @@ def test_generator_flag_in_the_training_graph(pkg):
     assert res["fused"][1].keys() == res["torch"][1].keys() and any(k.startswith("siren.") for k in res["fused"][1])
     for k, gr in res["torch"][1].items():
         assert (res["fused"][1][k] - gr).abs().max().item() < 1e-3 * gr.abs().max().item() + 1e-7, k
+
+
+@pytest.mark.parametrize("frozen", [False, True])
+def test_points_forward_native_ops_match_torch_ops(pkg, frozen):
+    """get_world_points_and_direction -> points_forward (reference entry points, generator.py:1659-1762) on the GPU: the native
+    integration / resampling / merge ops against the torch ops on the same draws -- images, aux images, parameter gradients."""
+    from _util import build_generator
+    from oracle import cips3d_oracle as O
+    G = build_generator(DEV, O.synthetic_state_dict(O.generator_template(), seed=5, sigma_bias=0.3), frozen=frozen).train()
+    torch.manual_seed(3)
+    zs = G.get_zs(2)
+    res = {}
+    for backend in ("torch", "fused"):
+        G.train_integrate = backend
+        G.zero_grad()
+        torch.manual_seed(17)
+        pts, dirs_exp, origins, dirs, z_vals, pitch, yaw = pkg.comm_utils.get_world_points_and_direction(
+            batch_size=2, num_steps=12, img_size=16, fov=12, ray_start=0.88, ray_end=1.12, h_stddev=0.3, v_stddev=0.155,
+            h_mean=1.5707963, v_mean=1.5707963, sample_dist="gaussian", lock_view_dependence=False, device=DEV)
+        style = G.mapping_network(**zs)
+        inr, aux = G.points_forward(style_dict=style, transformed_points=pts.view(2, 256, 12, 3),
+                                    transformed_ray_directions_expanded=dirs_exp.view(2, 256, 12, 3), num_steps=12,
+                                    hierarchical_sample=True, z_vals=z_vals, clamp_mode="relu", nerf_noise=0.3,
+                                    transformed_ray_origins=origins, transformed_ray_directions=dirs, white_back=False,
+                                    last_back=True, return_aux_img=True, idx_grad=torch.arange(0, 256, 2, device=DEV))
+        assert inr.shape == (2, 128, 3) and aux.shape == (2, 128, 3)
+        (inr.square().mean() + (aux.square().mean() if aux.requires_grad else 0)).backward()
+        res[backend] = (inr.detach().clone(), aux.detach().clone(),
+                        {k: p.grad.clone() for k, p in G.named_parameters() if p.grad is not None})
+    assert (res["fused"][0] - res["torch"][0]).abs().max().item() < 1e-4 and (res["fused"][1] - res["torch"][1]).abs().max().item() < 1e-4
+    assert res["fused"][2].keys() == res["torch"][2].keys()
+    assert any(k.startswith("siren.") for k in res["torch"][2]) == (not frozen)
+    for k, gr in res["torch"][2].items():
+        assert (res["fused"][2][k] - gr).norm().item() < 1e-2 * gr.norm().item() + 1e-7, k
