@@ -167,3 +167,39 @@ def check_pdf_golden(name, pkg, device="cpu"):
     assert got.shape == (rays, k)
     # an index that flips on a 1-ulp difference of the cdf moves the sample continuously; the bins span 0.24
     assert (got.cpu() - d["samples"]).abs().max().item() < 2e-6
+
+
+# ------------------------------------------------------------------ goldens of the REAL explicit-points path
+# (tests/golden/points_forward.npz, tools/make_golden_points.py: get_world_points_and_direction -> points_forward)
+POINTS_GOLDEN_CASES = ("hier_noise_lastback", "flat_softplus_white")
+
+
+def check_points_golden(name, pkg, G, device, backend):
+    """Replay the reference's draws through this package's get_world_points_and_direction + points_forward; compare with what
+    the unmodified functions returned."""
+    import os
+    import numpy as np
+    from _util import replay_draws
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "points_forward.npz"))
+    d = {k.split("/", 1)[1]: torch.from_numpy(np.asarray(g[k])) for k in g.files if k.startswith(name + "/")}
+    R, hier, softplus, wb, lb, subset, n_world = (int(v) for v in d["cfg"])
+    draws = [d[k] for k in sorted(k for k in d if k.startswith("draw"))]
+    zs = {k: d[k].to(device) for k in ("z_nerf", "z_inr")}
+    G.train_integrate = backend
+    with torch.no_grad(), replay_draws(draws, device):
+        world = pkg.comm_utils.get_world_points_and_direction(
+            batch_size=2, num_steps=12, img_size=R, fov=12, ray_start=0.88, ray_end=1.12, h_stddev=0.3, v_stddev=0.155,
+            h_mean=np.pi * 0.5, v_mean=np.pi * 0.5, sample_dist="gaussian", lock_view_dependence=False, device=device)
+        for got, key in zip(world, ("points", "dirs_exp", "origins", "dirs", "z_vals", "pitch", "yaw")):
+            assert (got.cpu() - d["world_" + key]).abs().max().item() < 2e-6, key
+        pts, dirs_exp, origins, dirs, z_vals, _, _ = world
+        inr, aux = G.points_forward(
+            style_dict=G.mapping_network(**zs), transformed_points=pts.view(2, R * R, 12, 3),
+            transformed_ray_directions_expanded=dirs_exp.view(2, R * R, 12, 3), num_steps=12, hierarchical_sample=bool(hier),
+            z_vals=z_vals, clamp_mode="softplus" if softplus else "relu", nerf_noise=float(d["nerf_noise"]),
+            transformed_ray_origins=origins, transformed_ray_directions=dirs, white_back=bool(wb), last_back=bool(lb),
+            return_aux_img=True, idx_grad=torch.arange(0, R * R, 2, device=device) if subset else None)
+    # rendered RGB within 1e-3 relative (north_star); the fp32 field through torch ops is far tighter than that
+    assert (inr.cpu() - d["inr"]).abs().max().item() < 1e-3 * d["inr"].abs().max().item()
+    assert (aux.cpu() - d["aux"]).abs().max().item() < 1e-3 * d["aux"].abs().max().item()
+    return (inr.cpu() - d["inr"]).abs().max().item()

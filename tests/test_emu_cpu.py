@@ -671,3 +671,17 @@ def test_emu_pigan_training_graph_with_native_integration_matches_reference_gold
     assert (res["fused"][0] - res["torch"][0]).abs().max().item() < 2e-5
     for k, gr in res["torch"][2].items():
         assert (res["fused"][2][k] - gr).abs().max().item() < 1e-3 * gr.abs().max().item() + 1e-8, k
+
+
+@pytest.mark.parametrize("backend", ["torch", "fused"])
+@pytest.mark.parametrize("name", ["hier_noise_lastback", "flat_softplus_white"])
+def test_emu_points_forward_matches_golden_of_the_real_methods(name, backend, monkeypatch):
+    """comm_utils.get_world_points_and_direction -> GeneratorNerfINR.points_forward with the reference's recorded draws replayed:
+    the seven world tensors and the inr / aux images the UNMODIFIED reference produced (tests/golden/points_forward.npz)."""
+    import cips3d_b200
+    from _integrate_cases import check_points_golden
+    monkeypatch.setattr(cips3d_b200.generator, "_require_cuda", lambda *a, **k: None)
+    G = build_generator("cpu", O.synthetic_state_dict(O.generator_template(), seed=77, sigma_bias=0.3))
+    with emulated(async_mode=0) as pkg:
+        err = check_points_golden(name, pkg, G, "cpu", backend)
+    assert err < 2e-4             # the CIPS MLP runs on the fused fp16 tensor-core kernel here (no graph needed)

@@ -124,3 +124,13 @@ def test_points_forward_native_ops_match_torch_ops(pkg, frozen):
     assert any(k.startswith("siren.") for k in res["torch"][2]) == (not frozen)
     for k, gr in res["torch"][2].items():
         assert (res["fused"][2][k] - gr).norm().item() < 1e-2 * gr.norm().item() + 1e-7, k
+
+
+@pytest.mark.parametrize("backend", ["torch", "fused"])
+@pytest.mark.parametrize("name", ["hier_noise_lastback", "flat_softplus_white"])
+def test_points_forward_matches_golden_of_the_real_methods(pkg, name, backend):
+    from _integrate_cases import check_points_golden
+    from _util import build_generator
+    from oracle import cips3d_oracle as O
+    G = build_generator(DEV, O.synthetic_state_dict(O.generator_template(), seed=77, sigma_bias=0.3))
+    check_points_golden(name, pkg, G, DEV, backend)
