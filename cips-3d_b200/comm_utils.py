@@ -156,3 +156,41 @@ def get_yaw_camera_pos_and_lookup(r=1, num_samples=36):
     for i, theta in enumerate(np.linspace(1, math.pi - 1, num_samples)):
         xyz[i] = (r * math.cos(theta), 0, r * math.sin(theta))
     return _trajectory(xyz)
+
+
+# ---------------------------------------------------------------- camera-space rays as functions (rows R2-R3 of SURVEY 8(a))
+def get_initial_rays_trig(bs, num_steps, fov, resolution, ray_start, ray_end, device):
+    """comm_utils.py:365-413 (reference signature): camera-space sample points (bs, H*W, num_steps, 3), depths
+    (bs, H*W, num_steps, 1) and unit ray directions (bs, H*W, 3); rays row-major, x in [-1, 1], y from +1 down to -1."""
+    W, H = resolution
+    x = torch.linspace(-1, 1, W, device=device)[None, :].expand(H, W).reshape(-1)
+    y = torch.linspace(1, -1, H, device=device)[:, None].expand(H, W).reshape(-1)
+    z = -torch.ones_like(x) / math.tan((2 * math.pi * fov / 360) / 2)
+    rays_d_cam = normalize_vecs(torch.stack([x, y, z], -1))
+    z_vals = torch.linspace(ray_start, ray_end, num_steps, device=device).reshape(1, num_steps, 1).repeat(W * H, 1, 1)
+    points = rays_d_cam[:, None, :] * z_vals
+    rep = lambda t: t.unsqueeze(0).repeat(bs, *([1] * t.dim()))            # noqa: E731
+    return rep(points), rep(z_vals), rep(rays_d_cam)
+
+
+def perturb_points(points, z_vals, ray_directions, device):
+    """comm_utils.py:416-437: one uniform jitter per sample, within the spacing of the first two depths; same draw
+    (torch.rand of z_vals' shape) as the reference."""
+    spacing = z_vals[:, :, 1:2, :] - z_vals[:, :, 0:1, :]
+    offset = (torch.rand(z_vals.shape, device=device) - 0.5) * spacing
+    return points + offset * ray_directions.unsqueeze(2), z_vals + offset
+
+
+def transform_sampled_points(points, z_vals, ray_directions, device, h_stddev=1, v_stddev=1, h_mean=math.pi * 0.5,
+                             v_mean=math.pi * 0.5, mode='normal', camera_pos=None, camera_lookup=None, up_vector=None):
+    """comm_utils.py:584-679 (reference signature): jitter the samples, draw (or take) the camera, map camera space to world
+    space.  -> (points (bs, n, s, 3), z_vals (bs, n, s, 1), ray directions (bs, n, 3), ray origins (bs, n, 3), pitch, yaw)."""
+    bs, n, s, _ = points.shape
+    points, z_vals = perturb_points(points, z_vals, ray_directions, device)
+    c2w, pitch, yaw = sample_cam2world(bs, device, h_stddev, v_stddev, h_mean, v_mean, mode, camera_pos=camera_pos,
+                                       camera_lookup=camera_lookup, up_vector=up_vector)
+    hom = torch.cat([points, torch.ones_like(points[..., :1])], -1).reshape(bs, n * s, 4)
+    world = torch.bmm(c2w, hom.transpose(1, 2)).transpose(1, 2).reshape(bs, n, s, 4)[..., :3]
+    dirs = torch.bmm(c2w[:, :3, :3], ray_directions.reshape(bs, n, 3).transpose(1, 2)).transpose(1, 2).reshape(bs, n, 3)
+    origins = c2w[:, :3, 3].unsqueeze(1).expand(bs, n, 3)               # cam2world applied to the camera-space origin
+    return world, z_vals, dirs, origins, pitch, yaw

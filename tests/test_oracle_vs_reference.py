@@ -307,3 +307,44 @@ def test_host_helpers_of_the_inference_scripts_vs_reference():
     ref_cu.inr_layer_swapping(B, T, 0.3, ["64", "1024"], verbose=False)
     for (k, p), q in zip(A.state_dict().items(), B.state_dict().values()):
         assert torch.equal(p, q), k
+
+
+def test_camera_space_ray_functions_vs_reference():
+    """comm_utils.get_initial_rays_trig / perturb_points: reference signatures, bit-identical outputs and RNG consumption."""
+    import cips3d_b200
+    ref_shim.install()
+    from exp.comm import comm_utils as ref_cu
+    cu = cips3d_b200.comm_utils
+    for res in ((7, 7), (6, 9)):
+        a = cu.get_initial_rays_trig(bs=2, num_steps=12, fov=12, resolution=res, ray_start=0.88, ray_end=1.12, device="cpu")
+        b = ref_cu.get_initial_rays_trig(bs=2, num_steps=12, fov=12, resolution=res, ray_start=0.88, ray_end=1.12, device="cpu")
+        for x, y in zip(a, b):
+            assert x.shape == y.shape and torch.equal(x, y)
+    torch.manual_seed(4)
+    p1, z1 = cu.perturb_points(a[0], a[1], a[2], "cpu")
+    r1 = torch.rand(2)
+    torch.manual_seed(4)
+    p2, z2 = ref_cu.perturb_points(b[0], b[1], b[2], "cpu")
+    r2 = torch.rand(2)
+    assert torch.equal(p1, p2) and torch.equal(z1, z2) and torch.equal(r1, r2)
+
+
+@pytest.mark.parametrize("cam", [False, True])
+def test_transform_sampled_points_vs_reference(cam):
+    import cips3d_b200
+    ref_shim.install()
+    from exp.comm import comm_utils as ref_cu
+    cu = cips3d_b200.comm_utils
+    pts, z, d = ref_cu.get_initial_rays_trig(bs=2, num_steps=12, fov=12, resolution=(5, 5), ray_start=0.88, ray_end=1.12, device="cpu")
+    kw = dict(h_stddev=0.3, v_stddev=0.155, h_mean=1.5707963, v_mean=1.5707963, mode="gaussian", device="cpu")
+    if cam:
+        kw.update(camera_pos=torch.tensor([[0.1, 0.2, 0.97], [-0.2, 0.0, 0.98]]), camera_lookup=torch.tensor([[-0.1, -0.2, -0.97], [0.2, 0.0, -0.98]]))
+    torch.manual_seed(6)
+    want = ref_cu.transform_sampled_points(pts, z, d, **kw)
+    r1 = torch.rand(2)
+    torch.manual_seed(6)
+    got = cu.transform_sampled_points(pts, z, d, **kw)
+    r2 = torch.rand(2)
+    assert torch.equal(r1, r2)
+    for i, (g_, w_) in enumerate(zip(got, want)):
+        assert g_.shape == w_.shape and (g_ - w_).abs().max().item() < 1e-6, i
