@@ -318,3 +318,19 @@ class ImplicitGenerator3d(nn.Module):                        # generators.py:12-
                                             kwargs.get('white_back', False), kwargs.get('last_back', False), False)
             B = rgb.shape[0]
             return self._to_img(rgb, img_size).cpu(), depth.reshape(B, img_size, img_size).contiguous().cpu()
+
+
+# ---------------------------------------------------------------- function surface of piGAN_lib/generators/volumetric_rendering.py
+def fancy_integration(rgb_sigma, z_vals, device, noise_std=0.5, last_back=False, white_back=False, clamp_mode=None, fill_mode=None):
+    """volumetric_rendering.py:18-55 (rgb in channels 0-2, sigma in channel 3) on the native op (csrc/integrate_ops.cu):
+    same arguments, the same torch.randn draw, (rgb_final (b, rays, 3), depth_final (b, rays, 1), weights (b, rays, s, 1)).
+    An unknown clamp_mode raises (the reference raises too: `raise "Need to choose clamp mode"`)."""
+    if clamp_mode not in ops.CLAMP_MODES:
+        raise TypeError("Need to choose clamp mode")          # what `raise <str>` amounts to in the reference
+    return ops.fancy_integration(rgb_sigma, z_vals, device=device, dim_rgb=3, noise_std=noise_std, last_back=last_back,
+                                 white_back=white_back, clamp_mode=clamp_mode, fill_mode=fill_mode)
+
+
+def sample_pdf(bins, weights, N_importance, det=False, eps=1e-5):
+    """volumetric_rendering.py:205-240 (the same function as exp/pigan/pigan_utils.py:164-209) on c3d_sample_pdf"""
+    return ops.sample_pdf(bins, weights, N_importance, det=det, eps=eps)

@@ -348,3 +348,31 @@ def test_transform_sampled_points_vs_reference(cam):
     assert torch.equal(r1, r2)
     for i, (g_, w_) in enumerate(zip(got, want)):
         assert g_.shape == w_.shape and (g_ - w_).abs().max().item() < 1e-6, i
+
+
+def test_pigan_lib_function_surface_vs_reference():
+    """cips3d_b200.pigan.fancy_integration / sample_pdf against piGAN_lib/generators/volumetric_rendering.py (emulation)."""
+    import cips3d_b200
+    import make_golden_pigan
+    from _emu import emulated
+    _, VR, _ = make_golden_pigan.import_reference_pigan()
+    g = torch.Generator().manual_seed(12)
+    rs = torch.randn(2, 21, 24, 4, generator=g)
+    rs[..., 3] = (rs[..., 3] + 0.3) * 8
+    z = torch.sort(0.88 + 0.24 * torch.rand(2, 21, 24, 1, generator=g), -2).values
+    torch.manual_seed(1)
+    want = VR.fancy_integration(rs, z, device="cpu", noise_std=0.4, last_back=True, white_back=True, clamp_mode="relu")
+    w = torch.rand(19, 10, generator=g) + 1e-5
+    bins = torch.sort(0.88 + 0.24 * torch.rand(19, 11, generator=g), -1).values
+    want_pdf = VR.sample_pdf(bins, w, 12, det=False)
+    with emulated(async_mode=0):
+        torch.manual_seed(1)
+        got = cips3d_b200.pigan.fancy_integration(rs, z, device="cpu", noise_std=0.4, last_back=True, white_back=True, clamp_mode="relu")
+        got_pdf = cips3d_b200.pigan.sample_pdf(bins, w, 12, det=False)
+        with pytest.raises(TypeError):
+            cips3d_b200.pigan.fancy_integration(rs, z, device="cpu")
+    with pytest.raises(TypeError):
+        VR.fancy_integration(rs, z, device="cpu")
+    for a, b in zip(got, want):
+        assert a.shape == b.shape and (a - b).abs().max().item() < 1e-5
+    assert (got_pdf - want_pdf).abs().max().item() < 2e-6
