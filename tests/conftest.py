@@ -23,12 +23,14 @@ EMU_DRYRUN = os.environ.get("C3D_GPU_TESTS_ON_EMU", "0") == "1"
 
 # GPU test files whose kernels have run on a B200 and passed there (profiles/r01*): these stay hard failures and run FIRST,
 # so that `pytest -m gpu -x` always reports the section 8(a) path before anything newer.
-HW_VALIDATED_FILES = ("test_gpu_parity.py",)
+HW_VALIDATED_FILES = ("test_gpu_parity.py", "test_baseline_sizes_gpu.py")
 # GPU test files written after the round's GPU minutes were spent (DESIGN.md status table: "not yet run on hardware").
 # Their first execution on a B200 is informative, not yet a parity claim: unless C3D_HW_STRICT=1 a failure there is reported
 # as XFAIL (and a pass as XPASS) instead of stopping a `-x` run -- a crash in one of them cannot take the validated results
 # down with it because those have already run.  tools/r02_first_gpu_call.sh runs them with C3D_HW_STRICT=1.
-HW_FIRST_RUN_FILES = ("test_film_gpu.py", "test_inference_gpu.py", "test_integrate_gpu.py", "test_optim_gpu.py", "test_pigan_gpu.py")
+# round 2: the five files that were here (film, inference, integrate, optim, pigan) all passed their first hardware run
+# (GPUTEST_r01: 79 XPASS / 0 XFAIL) and are hard failures now.  New never-run files go here for exactly one round.
+HW_FIRST_RUN_FILES = ()
 HW_STRICT = os.environ.get("C3D_HW_STRICT", "0") == "1"
 
 
