@@ -27,6 +27,41 @@ R, BATCH_PER_GPU, NUM_STEPS = 256, 16, 12
 NERF_FLOP_PER_RAY = 1302528.0      # BASELINE.md section 3 (24 points x 54 272)
 CIPS_FLOP_PER_PIXEL = 8964096.0
 METRIC = "generator fwd images/sec @ FFHQ r256, 24 samples/ray"
+# exp/cips3d/configs/ffhq_exp.yaml:43-81 (G_cfg_3D2D) and :117-126 (G_kwargs)
+G_CFG = dict(
+    z_dim=256,
+    nerf_cfg=dict(in_dim=3, hidden_dim=128, hidden_layers=2, rgb_dim=32, style_dim=128),
+    mapping_nerf_cfg=dict(z_dim=256, hidden_dim=128, base_layers=4, head_layers=0),
+    inr_cfg=dict(input_dim=32, style_dim=512, hidden_dim=512, pre_rgb_dim=3),
+    mapping_inr_cfg=dict(z_dim=512, hidden_dim=512, base_layers=8, head_layers=0, add_norm=True, norm_out=True),
+)
+G_KWARGS = dict(fov=12, ray_start=0.88, ray_end=1.12, num_steps=12, h_stddev=0.3, v_stddev=0.155,
+                hierarchical_sample=True, psi=1., sample_dist="gaussian")
+WEIGHT_SEED = 1234          # ffhq_exp.yaml:146; both arms: the (reference-identical) constructor init under this seed
+REF_ROOT = os.path.join(ROOT, "baseline", "_ref")
+
+
+def bench_config(res, B, world):
+    """the `config` object, identical in both arms (the driver compares them)"""
+    return {"workload": f"FFHQ r{res} generator forward (GeneratorNerfINR, ffhq_exp.yaml G_cfg_3D2D), "
+                        f"{B} images/GPU/step, 12 coarse + 12 fine samples/ray, nerf_noise 0",
+            "resolution": res, "batch_per_gpu": B, "global_batch": B * world, "samples_per_ray": 24,
+            "parallelism": f"dp{world} (no data-path collective)",
+            "l2": "per-step inputs (random draws ~%.0f MB) exceed the 126 MB L2" % (B * res * res * 48 * 4 / 1e6)}
+
+
+def reference_generator(device):
+    """The UNMODIFIED reference GeneratorNerfINR from baseline/_ref (tools/install_reference.py), tl2 satisfied by
+    tools/ref_shim.py; None when the copy is absent."""
+    if not os.path.isdir(os.path.join(REF_ROOT, "exp", "cips3d", "models")):
+        return None
+    os.environ["CIPS3D_REFERENCE"] = REF_ROOT
+    tools = os.path.join(ROOT, "tools")
+    if tools not in sys.path:
+        sys.path.insert(0, tools)
+    import ref_shim
+    torch.manual_seed(WEIGHT_SEED)
+    return ref_shim.build_reference_generator(device).eval()
 
 
 def peaks():
@@ -71,67 +106,117 @@ class ClockSampler(threading.Thread):
                 "reasons": sorted(reasons), "samples": len(self.rows)}
 
 
-def cpu_reference_rate(seconds_budget=20.0, threads=None, img_size=R, batch=1):
-    """The reference algorithm (CPU oracle port of exp/cips3d/models/generator.py) on the host cores."""
-    from oracle import cips3d_oracle as O
-    sd_probe = O.synthetic_state_dict(O.generator_template(), seed=1234)
-    if threads is None:                     # torch-CPU scales badly past a few dozen threads: pick the best
-        best = (0.0, 1)
-        gp = torch.Generator().manual_seed(1)
-        zp = {"z_nerf": torch.randn(1, 256, generator=gp), "z_inr": torch.randn(1, 512, generator=gp)}
-        for th in sorted({min(os.cpu_count(), t) for t in (8, 16, 32, 64, 128)}):
-            torch.set_num_threads(th)
-            dr = O.draw_randoms(1, 64, 12, generator=gp)
-            t0 = time.perf_counter()
-            with torch.no_grad():
-                O.generator_forward(sd_probe, zp, dr, img_size=64, nerf_noise=0.0, **O.G_KWARGS)
-            r = 1.0 / (time.perf_counter() - t0)
-            if r > best[0]:
-                best = (r, th)
-        threads = best[1]
-    torch.set_num_threads(threads)
-    sd = O.synthetic_state_dict(O.generator_template(), seed=1234)
-    kw = dict(O.G_KWARGS)
-    g = torch.Generator().manual_seed(0)
-    zs = {"z_nerf": torch.randn(batch, 256, generator=g), "z_inr": torch.randn(batch, 512, generator=g)}
+class CpuReference:
+    """The reference's generator forward on the host cores: the UNMODIFIED reference modules from baseline/_ref
+    (kind "reference") when tools/install_reference.py has put them there, else the oracle port (kind "port").
+    One `step(b)` = one forward over b images at the bench resolution -- a bounded sample of the B-image bench step."""
 
-    def one():
-        draws = O.draw_randoms(batch, img_size, kw["num_steps"], generator=g)
+    def __init__(self, res=R, threads=None):
+        self.res = res
+        self.G = reference_generator("cpu")
+        if self.G is not None:
+            self.kind = "reference"
+            self.what = "UNMODIFIED reference GeneratorNerfINR.forward (baseline/_ref via tools/ref_shim.py), fp32 torch-CPU"
+        else:
+            from oracle import cips3d_oracle as O       # the one other place bench.py may execute oracle/: the CPU baseline
+            self.O = O
+            self.kind = "port"
+            self.what = "oracle port of GeneratorNerfINR.forward (oracle/cips3d_oracle.py), fp32 torch-CPU"
+            self.sd = O.synthetic_state_dict(O.generator_template(), seed=WEIGHT_SEED)
+        self.gen = torch.Generator().manual_seed(0)
+        self.threads = threads or self._calibrate()
+        torch.set_num_threads(self.threads)
+
+    def step(self, b, res=None):
+        res = res or self.res
+        zs = {"z_nerf": torch.randn(b, 256, generator=self.gen), "z_inr": torch.randn(b, 512, generator=self.gen)}
+        t0 = time.perf_counter()
         with torch.no_grad():
-            O.generator_forward(sd, zs, draws, img_size=img_size, nerf_noise=0.0, **kw)
+            if self.G is not None:
+                self.G(zs, img_size=res, **G_KWARGS)
+            else:
+                draws = self.O.draw_randoms(b, res, G_KWARGS["num_steps"], generator=self.gen)
+                self.O.generator_forward(self.sd, zs, draws, img_size=res, nerf_noise=0.0, **self.O.G_KWARGS)
+        return time.perf_counter() - t0
 
-    t0 = time.perf_counter()
-    one()                                  # warm-up (also sizes the budget)
-    t_one = time.perf_counter() - t0
+    def _calibrate(self):
+        """torch-CPU scales badly past a few dozen threads: take the fastest of a few counts on a small forward"""
+        best = (1e30, 1)
+        self.step(1, 64)
+        for th in sorted({min(os.cpu_count() or 1, t) for t in (8, 16, 32, 64, 128)}):
+            torch.set_num_threads(th)
+            t = min(self.step(1, 64) for _ in range(2))
+            if t < best[0]:
+                best = (t, th)
+        return best[1]
+
+
+def cpu_baseline_leg(seconds_budget=20.0):
+    ref = CpuReference()
+    t_one = ref.step(1)                      # warm-up (also sizes the sample)
     n = max(1, min(8, int(seconds_budget / max(t_one, 1e-3))))
-    t0 = time.perf_counter()
-    for _ in range(n):
-        one()
-    dt = time.perf_counter() - t0
-    return batch * n / dt, threads, f"{n} x (batch {batch}, r{img_size}, 12+12 samples/ray) fp32 torch-CPU oracle port"
+    dt = sum(ref.step(1) for _ in range(n))
+    return {"value": n / dt, "unit": "images/s", "cores": ref.threads, "kind": ref.kind,
+            "sample": f"{n} x (1 image of the step's batch, r{R}, 12+12 samples/ray): {ref.what}"}
 
 
 def run_reference(args, rank, world):
+    """--impl reference: the reference's own CPU implementation on this box's host cores, on our arm's config/metric.
+    A step = the reference forward over ONE image of the B-image step (bounded sample: the full 16-image step takes
+    ~1 min of CPU); value = images / time.  Rank 0 only."""
     if rank != 0:
         return
     t0 = time.perf_counter()
+    ref = CpuReference(res=args.res)
     for _ in range(max(args.warmup, 0)):
-        pass
-    per_step_budget = max(5.0, min(30.0, 150.0 / max(args.steps, 1)))
-    rates = []
-    for _ in range(args.steps):
-        r, cores, sample = cpu_reference_rate(per_step_budget)
-        rates.append(r)
-    val = float(np.mean(rates))
+        ref.step(1)
+    ts = [ref.step(1) for _ in range(args.steps)]
+    val = len(ts) / sum(ts)
+    sample = f"each step = 1 image of the {args.batch}-image step, r{args.res}, 12+12 samples/ray: {ref.what}"
     line = {"metric": METRIC, "value": val, "unit": "images/s", "n_gpus": args.gpus, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": 1000.0 / val, "higher_is_better": True, "scaling": "weak",
+            "warmup": args.warmup, "ms_per_step": 1000.0 * sum(ts) / len(ts), "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic", "impl": "reference",
-            "config": {"workload": f"FFHQ r{R} generator forward, 12 coarse + 12 fine samples/ray, 1 image per step sample",
-                       "resolution": R, "samples_per_ray": 24},
-            "cpu_baseline": {"value": val, "unit": "images/s", "cores": cores, "kind": "port", "sample": sample},
+            "config": bench_config(args.res, args.batch, max(world, args.gpus)),
+            "cpu_baseline": {"value": val, "unit": "images/s", "cores": ref.threads, "kind": ref.kind, "sample": sample},
             "e2e": {"value": val, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0, "wall_s": time.perf_counter() - t0}
     print(json.dumps(line), flush=True)
+
+
+def reference_eager_gpu_leg(dev, res, B):
+    """The unmodified reference GeneratorNerfINR as eager torch CUDA ops on this GPU ("the
+    implementation the new kernels have to beat"), TF32 off (torch default, the reference's setting) and on."""
+    G = reference_generator(dev)
+    if G is None:
+        return {"unavailable": "baseline/_ref absent (tools/install_reference.py not run where /root/reference exists)"}
+    out = {"impl": "UNMODIFIED reference modules (baseline/_ref), eager torch CUDA ops, fp32"}
+    prev = torch.backends.cuda.matmul.allow_tf32
+    try:
+        for name, tf32 in (("tf32_off", False), ("tf32_on", True)):
+            torch.backends.cuda.matmul.allow_tf32 = tf32
+            for b in (B, 4, 1):
+                try:
+                    zs = G.get_zs(b)
+                    with torch.no_grad():
+                        G(zs, img_size=res, **G_KWARGS)
+                        torch.cuda.synchronize()
+                        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                        n = 3
+                        e0.record()
+                        for _ in range(n):
+                            G(zs, img_size=res, **G_KWARGS)
+                        e1.record()
+                        torch.cuda.synchronize()
+                    out[name] = {"value": n * b / (e0.elapsed_time(e1) / 1e3), "unit": "images/s", "batch": b}
+                    break
+                except torch.OutOfMemoryError:
+                    torch.cuda.empty_cache()
+                    out[name] = {"unavailable": f"out of memory at batch {b}"}
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = prev
+        del G
+        torch.cuda.empty_cache()
+    return out
 
 
 def main():
@@ -168,13 +253,12 @@ def main():
     os.environ["C3D_IMPL"] = args.kernel_impl
     import cips3d_b200
     from cips3d_b200 import _lib, ops
-    from oracle import cips3d_oracle as O          # weights recipe only (synthetic_state_dict)
     lib = _lib.load()
     res, B = args.res, args.batch
-    cfg = {k: (dict(v) if isinstance(v, dict) else v) for k, v in O.G_CFG.items()}
-    G = cips3d_b200.GeneratorNerfINR(**cfg, device=dev).to(dev).eval()
-    G.load_state_dict(O.synthetic_state_dict(O.generator_template(), seed=1234))
-    kw = dict(O.G_KWARGS)
+    cfg = {k: (dict(v) if isinstance(v, dict) else v) for k, v in G_CFG.items()}
+    torch.manual_seed(WEIGHT_SEED)          # the constructor reproduces the reference's init bit for bit (test_boundary_cpu)
+    G = cips3d_b200.GeneratorNerfINR(**cfg, device=dev).to(dev).eval()     # parameters are initialised on the CPU, then moved
+    kw = dict(G_KWARGS)
     torch.manual_seed(1000 + rank)
     zs_host = {"z_nerf": torch.randn(B, 256).pin_memory(), "z_inr": torch.randn(B, 512).pin_memory()}
     zs_dev = {k: v.to(dev) for k, v in zs_host.items()}
@@ -264,12 +348,9 @@ def main():
         "vs_baseline": None, "dtype": "f16-split (fp32-equivalent) ray MLP, f16 CIPS MLP, fp32 accumulate"
         if args.kernel_impl == "tc" else "f32",
         "data": "synthetic",
-        "config": {"workload": f"FFHQ r{res} generator forward (GeneratorNerfINR, ffhq_exp.yaml G_cfg_3D2D), "
-                               f"{B} images/GPU/step, 12 coarse + 12 fine samples/ray, nerf_noise 0",
-                   "resolution": res, "batch_per_gpu": B, "global_batch": B * world, "samples_per_ray": 24,
-                   "kernel_impl": args.kernel_impl, "parallelism": f"dp{world} (no data-path collective)",
-                   "l2": "per-step inputs (random draws ~%.0f MB) exceed the 126 MB L2" % (B * res * res * 48 * 4 / 1e6),
-                   # opt-in kernel variants in effect for this run (all unset = the round-1 measured kernels)
+        "config": bench_config(res, B, world),
+        # kernel selection in effect (all unset = the defaults of this build)
+        "kernel": {"impl": args.kernel_impl,
                    "variants": {k: os.environ[k] for k in ("C3D_CIPS_PAIR", "C3D_CIPS_CLUSTER", "C3D_RAY_MATH", "C3D_BLUR_TMA", "C3D_STYLE_PREP")
                                 if os.environ.get(k)}},
         "e2e": {"value": e2e, "unit": "images/s", "h2d_bytes_per_step": int(B * (256 + 512) * 4),
@@ -334,8 +415,13 @@ def main():
         except Exception as ex:
             line["e2e_uint8"] = {"unavailable": str(ex)[:120]}
     if world == 1 and not args.no_cpu_baseline:
-        v, cores, sample = cpu_reference_rate(20.0)
-        line["cpu_baseline"] = {"value": v, "unit": "images/s", "cores": cores, "kind": "port", "sample": sample}
+        line["vs_reference_gpu_eager"] = reference_eager_gpu_leg(dev, res, B) if not args.no_eager else None
+        if isinstance(line["vs_reference_gpu_eager"], dict):
+            for k in ("tf32_off", "tf32_on"):
+                ent = line["vs_reference_gpu_eager"].get(k)
+                if isinstance(ent, dict) and ent.get("value"):
+                    ent["ours_over_reference"] = value / ent["value"]
+        line["cpu_baseline"] = cpu_baseline_leg(20.0)
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
