@@ -13,6 +13,7 @@ needs a graph (training step) the same math runs as differentiable torch CUDA op
 backward kernels are the next hot-path row, not a CPU path:
 every entry point refuses non-CUDA tensors.
 """
+import contextlib
 import logging
 import math
 import os
@@ -24,6 +25,17 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from . import comm_utils, ops
+
+_log = logging.getLogger("cips3d_b200")
+_warned = set()
+
+
+def _note_torch_path(what, why):
+    """The fused sm_100a kernels cover the reference's shipped configurations; any other module shape runs as torch CUDA
+    ops.  That must not happen silently (VERDICT r1 #12): say so once per (module, reason)."""
+    if (what, why) not in _warned:
+        _warned.add((what, why))
+        _log.warning("cips3d_b200: %s runs as eager torch CUDA ops, not the fused kernel: %s", what, why)
 
 try:  # the reference's registry, when the caller runs inside the reference's train.py
     from tl2.proj.fvcore import MODEL_REGISTRY  # type: ignore
@@ -147,8 +159,10 @@ class NeRFNetwork(nn.Module):                   # generator.py:151-376
         self.gridwarper = UniformBoxWarp(0.24)
 
     # ---- what the fused kernel consumes
-    def fused_supported(self):
-        return (self.in_dim == 3 and self.hidden_dim == 128 and self.hidden_layers == 2 and self.rgb_dim == 32)
+    def fused_supported(self, num_steps=None):
+        """mirrors the argument checks of c3d_ray_siren_fwd (include/cips3d_b200.h): ffhq_exp.yaml's NeRF, 3..32 steps"""
+        return (self.in_dim == 3 and self.hidden_dim == 128 and self.hidden_layers == 2 and self.rgb_dim == 32
+                and (num_steps is None or 3 <= num_steps <= 32))
 
     def kernel_weights(self):
         n0, n1 = self.network[0].linear, self.network[1].linear
@@ -285,6 +299,7 @@ class CIPSNet(nn.Module):                       # generator.py:1009-1154
                  **kwargs):
         super().__init__()
         self.device, self.pre_rgb_dim, self.name_prefix = device, pre_rgb_dim, name_prefix
+        self.input_dim, self.hidden_dim = input_dim, hidden_dim
         self.channels = {str(2 ** i): hidden_dim for i in range(2, 11)}
         self.module_name_list = []
         self.style_dim_dict = {}
@@ -314,7 +329,8 @@ class CIPSNet(nn.Module):                       # generator.py:1009-1154
         return names.index(stop) + 1 if stop in names else len(names)
 
     def fused_supported(self):
-        return self.pre_rgb_dim == 3
+        """mirrors the argument checks of c3d_cips_fwd (csrc/cips_tc.cu): hidden 512, <= 64 input features, RGB heads"""
+        return self.pre_rgb_dim == 3 and self.hidden_dim == 512 and self.input_dim <= 64
 
     def forward_torch(self, input, style_dict, img_size=1024):
         x, rgb = input, 0
@@ -374,7 +390,11 @@ class CIPSNet(nn.Module):                       # generator.py:1009-1154
     def forward(self, input, style_dict, img_size=1024, **kwargs):
         """input (b, n, in) -> (b, n, 3)"""
         _require_cuda(input, "CIPSNet.forward")
-        needs_graph = torch.is_grad_enabled() and (input.requires_grad or any(p.requires_grad for p in self.parameters()))
+        needs_graph = torch.is_grad_enabled() and (input.requires_grad or any(p.requires_grad for p in self.parameters())
+                                                   or any(s.requires_grad for s in style_dict.values()))
+        if not needs_graph and (not self.fused_supported() or input.dim() != 3):
+            _note_torch_path("CIPSNet", f"hidden_dim {self.hidden_dim}, input_dim {self.input_dim}, pre_rgb_dim {self.pre_rgb_dim}, "
+                                        f"input rank {input.dim()} (fused: 512 / <= 64 / 3 / rank 3)")
         if needs_graph and self.train_backend == 'fused' and self.fused_supported() and input.dim() == 3 and self._n_blocks(img_size) > 3:
             return self.forward_fused_train(input, style_dict, img_size)
         if needs_graph or not self.fused_supported() or input.dim() != 3:
@@ -571,8 +591,14 @@ class GeneratorNerfINR(nn.Module):              # generator.py:1158-1951
         self.force_torch_path = False
 
     # ---------------------------------------------------------------- small helpers
-    def _nerf_grad_needed(self):
-        return torch.is_grad_enabled() and any(p.requires_grad for p in self.siren.parameters())
+    def _nerf_grad_needed(self, style_dict=None):
+        """does the renderer need an autograd graph?  Through the field's parameters OR through the styles (a frozen siren under a
+        trainable mapping_network_nerf still needs the FiLM gradients)"""
+        if not torch.is_grad_enabled():
+            return False
+        if any(p.requires_grad for p in self.siren.parameters()):
+            return True
+        return style_dict is not None and any(v.requires_grad for k, v in style_dict.items() if k in self.siren.style_dim_dict)
 
     def z_sampler(self, shape, device, dist='gaussian'):
         if dist == 'gaussian':
@@ -627,7 +653,11 @@ class GeneratorNerfINR(nn.Module):              # generator.py:1158-1951
         """rays -> (B,N,32) integrated features.  jitter_u (B,HW,S), noise_c (B,N,S), pdf_u (B*N,S),
         noise_f (B,N,nS); ray_idx: LongTensor ray subset or None."""
         _require_cuda(cam2world, "GeneratorNerfINR")
-        if not grad and not self.force_torch_path and self.siren.fused_supported():
+        fusable = self.siren.fused_supported(num_steps)
+        if not fusable and not grad:
+            _note_torch_path("NeRFNetwork renderer", f"in_dim {self.siren.in_dim}, hidden_dim {self.siren.hidden_dim}, hidden_layers "
+                             f"{self.siren.hidden_layers}, rgb_dim {self.siren.rgb_dim}, num_steps {num_steps} (fused: 3 / 128 / 2 / 32 / 3..32)")
+        if not grad and not self.force_torch_path and fusable:
             out = ops.render_features(
                 self.siren.kernel_weights(), self.siren.kernel_film(style_dict), cam2world, jitter_u, pdf_u,
                 noise_c, noise_f, img_size=img_size, fov=fov, ray_start=ray_start, ray_end=ray_end,
@@ -860,7 +890,7 @@ class GeneratorNerfINR(nn.Module):              # generator.py:1158-1951
         pixels_fea = self.render_pixels_fea(
             style_dict, c2w, jitter_u, pdf_u, noise_c, noise_f, img_size=img_size, fov=fov, ray_start=ray_start,
             ray_end=ray_end, num_steps=S, hierarchical_sample=hierarchical_sample, clamp_mode=clamp_mode,
-            nerf_noise=nerf_noise, white_back=white_back, last_back=last_back, grad=self._nerf_grad_needed())
+            nerf_noise=nerf_noise, white_back=white_back, last_back=last_back, grad=self._nerf_grad_needed(style_dict))
         return self._pixels_to_imgs(pixels_fea, style_dict, return_aux_img, img_size, pitch, yaw)
 
     def part_grad_forward(self, style_dict, img_size, fov, ray_start, ray_end, num_steps, h_stddev, v_stddev,
@@ -889,13 +919,14 @@ class GeneratorNerfINR(nn.Module):              # generator.py:1158-1951
                 pdf_u = self._draw('rand', (B * n, S))
             noise_f = self._draw('randn', (B, n, nS, 1), need_noise)
             noise_f = noise_f.view(B, n, nS) if noise_f is not None else None
-            ctx = torch.enable_grad() if with_grad else torch.no_grad()
+            # the grad half inherits the CALLER's grad mode (the reference does not re-enable it: generator.py:1536-1657)
+            ctx = contextlib.nullcontext() if with_grad else torch.no_grad()
             with ctx:
                 fea = self.render_pixels_fea(
                     style_dict, c2w, jitter_u, pdf_u, noise_c, noise_f, img_size=img_size, fov=fov,
                     ray_start=ray_start, ray_end=ray_end, num_steps=S, hierarchical_sample=hierarchical_sample,
                     clamp_mode=clamp_mode, nerf_noise=nerf_noise, white_back=white_back, last_back=last_back,
-                    ray_idx=idx, grad=with_grad and self._nerf_grad_needed())
+                    ray_idx=idx, grad=with_grad and self._nerf_grad_needed(style_dict))
                 inr = self.inr_net(fea, style_dict)
                 aux = self._aux(fea) if return_aux_img else None
             parts.append((idx, inr, aux))
@@ -925,7 +956,7 @@ class GeneratorNerfINR_freeze_NeRF(GeneratorNerfINR):      # generator.py:1954-2
         style_dict.update(self.mapping_network_inr(z_inr))
         return style_dict
 
-    def _nerf_grad_needed(self):
+    def _nerf_grad_needed(self, style_dict=None):
         return False
 
     def render_pixels_fea(self, *a, **k):

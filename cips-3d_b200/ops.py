@@ -599,10 +599,31 @@ def integrate_supported(rgb_sigma, z, noise=None):
     return noise is None or (noise.dtype == torch.float32 and noise.numel() == z.numel())
 
 
+def _torch_weights_grad(rs, z, noise, clamp, last_back, d_weights):
+    """d(loss)/d(rgb_sigma) through the compositing WEIGHTS (pigan_utils.py:241-262), for the rare caller that differentiates the
+    returned weights / depth (e.g. a depth loss in piGAN_lib/inverse_render-style use).  The training loop never does -- weights feed
+    sample_pdf under no_grad -- so this is a torch-op recompute from the saved inputs, not a kernel."""
+    with torch.enable_grad():
+        rs_ = rs.detach().requires_grad_(True)
+        sig = rs_[..., -1]
+        deltas = torch.cat([z[..., 1:] - z[..., :-1], torch.full_like(z[..., :1], 1e10)], -1)
+        if noise is not None:
+            sig = sig + noise
+        act = torch.nn.functional.softplus(sig) if clamp == CLAMP_MODES["softplus"] else torch.relu(sig)
+        alphas = 1 - torch.exp(-deltas * act)
+        shifted = torch.cat([torch.ones_like(alphas[..., :1]), 1 - alphas + 1e-10], -1)
+        w = alphas * torch.cumprod(shifted, -1)[..., :-1]
+        if last_back:
+            w = torch.cat([w[..., :-1], w[..., -1:] + (1 - w.sum(-1))[..., None]], -1)
+        (g,) = torch.autograd.grad(w, rs_, d_weights)
+    return g
+
+
 class IntegrateFunction(Function):
     """fancy_integration (pigan_utils.py:212-273) on sorted samples as one native pass forward and one backward
-    (csrc/integrate_ops.cu).  Returns (fea, weights); gradients flow to rgb_sigma only -- z and noise are constants of the
+    (csrc/integrate_ops.cu).  Returns (fea, weights); gradients flow to rgb_sigma -- z and noise are constants of the
     reference's graph too (fine depths are drawn under no_grad, generator_nerf_inr.py:537).  Saves only its inputs.
+    A gradient arriving through `weights` (depth / weight losses) is honoured by a torch-op recompute (_torch_weights_grad).
     No double backward (the generator's graph needs none)."""
 
     @staticmethod
@@ -622,20 +643,25 @@ class IntegrateFunction(Function):
               "c3d_integrate_fwd")
         ctx.save_for_backward(rs, zc, nz if nz is not None else torch.empty(0, device=rs.device))
         ctx.cfg = (nz is not None, CLAMP_MODES[clamp_mode], int(bool(last_back)), int(bool(white_back)))
-        ctx.mark_non_differentiable(weights)
+        ctx.set_materialize_grads(False)          # an unused output arrives as None in backward, not as a zero tensor
         return fea, weights
 
     @staticmethod
     @once_differentiable
-    def backward(ctx, d_fea, _d_weights):
+    def backward(ctx, d_fea, d_weights):
         lib = load()
         rs, zc, nz = ctx.saved_tensors
         has_noise, clamp, last_back, white_back = ctx.cfg
         T, C1 = rs.shape[-2:]
-        d_fea = d_fea.contiguous()
-        d_rs = torch.empty_like(rs)
-        check(lib.c3d_integrate_bwd(ptr(rs), ptr(zc), ptr(nz) if has_noise else None, ptr(d_fea), ptr(d_rs), zc.numel() // T, T,
-                                    C1 - 1, clamp, last_back, white_back, stream_ptr()), "c3d_integrate_bwd")
+        d_rs = None
+        if d_fea is not None:
+            d_fea = d_fea.contiguous()
+            d_rs = torch.empty_like(rs)
+            check(lib.c3d_integrate_bwd(ptr(rs), ptr(zc), ptr(nz) if has_noise else None, ptr(d_fea), ptr(d_rs), zc.numel() // T, T,
+                                        C1 - 1, clamp, last_back, white_back, stream_ptr()), "c3d_integrate_bwd")
+        if d_weights is not None:
+            g = _torch_weights_grad(rs, zc, nz if has_noise else None, clamp, last_back, d_weights)
+            d_rs = g if d_rs is None else d_rs + g
         return d_rs, None, None, None, None, None
 
 

@@ -18,6 +18,8 @@ import torch.nn as nn
 from . import _lib, ops
 from .comm_utils import sample_cam2world
 
+_PIGAN_SAMPLE_DISTS = ('uniform', 'normal', 'gaussian', 'hybrid', 'truncated_gaussian', 'spherical_uniform')
+
 
 # ------------------------------------------------------------------------------ siren.py:14-45 init functions
 def sine_init(m):
@@ -209,7 +211,11 @@ class ImplicitGenerator3d(nn.Module):                        # generators.py:12-
         B, S, HW = frequencies.shape[0], num_steps, img_size * img_size
         nS = 2 * S if hierarchical_sample else S
         jitter_u = torch.rand((B, HW, S, 1), device=dev)[..., 0]                      # perturb_points
-        c2w, pitch, yaw = sample_cam2world(B, dev, h_stddev, v_stddev, h_mean, v_mean, sample_dist)
+        # piGAN_lib/generators/volumetric_rendering.py:162-165: every mode it does not know -- None included, the default of
+        # forward / staged_forward and what inverse_render.py passes -- means "use the mean camera" (the CIPS-3D surface
+        # asserts instead, comm_utils.py:451-535)
+        mode = sample_dist if sample_dist in _PIGAN_SAMPLE_DISTS else 'mean'
+        c2w, pitch, yaw = sample_cam2world(B, dev, h_stddev, v_stddev, h_mean, v_mean, mode)
         noise_c = pdf_u = None
         if hierarchical_sample:
             noise_c = torch.randn((B, HW, S, 1), device=dev)[..., 0]                  # coarse fancy_integration

@@ -685,3 +685,21 @@ def test_emu_points_forward_matches_golden_of_the_real_methods(name, backend, mo
     with emulated(async_mode=0) as pkg:
         err = check_points_golden(name, pkg, G, "cpu", backend)
     assert err < 2e-4             # the CIPS MLP runs on the fused fp16 tensor-core kernel here (no graph needed)
+
+
+@pytest.mark.parametrize("sample_dist", [None, "mean", "not_a_mode"])
+def test_emu_pigan_unknown_sample_dist_is_the_mean_camera(sample_dist, monkeypatch):
+    """piGAN_lib/generators/volumetric_rendering.py:162-165: any mode sample_camera_positions does not know -- None included,
+    the default of ImplicitGenerator3d.forward / staged_forward and what inverse_render.py passes -- renders from
+    (h_mean, v_mean).  (The CIPS-3D surface asserts on unknown modes)"""
+    import cips3d_b200
+    monkeypatch.setattr(cips3d_b200.pigan, "_require_cuda", lambda *a, **k: None)
+    torch.manual_seed(3)
+    G = cips3d_b200.pigan.ImplicitGenerator3d(cips3d_b200.pigan.TALLSIREN, z_dim=256).eval()
+    z = torch.randn(2, 256)
+    kw = dict(img_size=4, fov=12, ray_start=0.88, ray_end=1.12, num_steps=4, h_stddev=0.3, v_stddev=0.155, h_mean=1.3, v_mean=1.7,
+              hierarchical_sample=False, clamp_mode="relu", nerf_noise=0.0)
+    with torch.no_grad(), emulated(async_mode=0):
+        img, py = G(z, sample_dist=sample_dist, **kw)
+    assert torch.isfinite(img).all()
+    assert torch.allclose(py, torch.tensor([[1.7, 1.3]]).expand(2, 2), atol=1e-6)       # (pitch, yaw) = (v_mean, h_mean)
