@@ -94,7 +94,7 @@ __device__ __forceinline__ float fast_sin(float x) { return __sinf(x); }
 __device__ unsigned long long g_rtrace[4096];
 __device__ unsigned int g_rtrace_n;
 __device__ __forceinline__ void rtrace(int it, uint32_t tag, uint32_t a0) {
-  if (blockIdx.x == 0 && it == 3) {
+  if (blockIdx.x == 0 && (it == 3 || it == 4)) {
     unsigned int i = atomicAdd(&g_rtrace_n, 1u);
     if (i < 4096) g_rtrace[i] = ((unsigned long long)tag << 56) | ((unsigned long long)(a0 & 0xFFFF) << 40) | (clock64() & 0xFFFFFFFFFFull);
   }
@@ -226,7 +226,7 @@ __global__ void __launch_bounds__(640, 1) ray_siren_tc_kernel(const KArgs a) {
             par[sl] ^= 1;
             tc_fence_after();
             const int layer = FOLD ? done[sl] % 3 : (done[sl] & 3);
-            if (lane == 0) RTRACE(done[sl] / mma_phases, 1, (uint32_t)(sl << 8 | (done[sl] % mma_phases)));
+            if (lane == 0) RTRACE(done[sl] / mma_phases, 1, (uint32_t)(sl << 15 | ((done[sl] / mma_phases) & 1) << 8 | (done[sl] % mma_phases)));
             if (elect_one()) {
               uint32_t a_hi = tmem + (uint32_t)(sl * 256), a_lo = a_hi + 64;
               const uint32_t d = a_hi + 128;
@@ -279,7 +279,8 @@ __global__ void __launch_bounds__(640, 1) ray_siren_tc_kernel(const KArgs a) {
       tc_fence_after();
     };
     int tr_it = 0, tr_ph = 0;
-    auto stamp = [&](uint32_t tag) { if (stid == 0) RTRACE(tr_it, tag, (uint32_t)(sl << 8 | tr_ph)); ++tr_ph; };
+    // trace word: slot << 15 | team warp << 12 | iteration parity << 8 | phase counter (lane 0 of every worker warp stamps)
+    auto stamp = [&](uint32_t tag) { if (lane == 0) RTRACE(tr_it, tag, (uint32_t)(sl << 15 | tw << 12 | (tr_it & 1) << 8 | tr_ph)); ++tr_ph; };
     const int g_row = row / S, s_row = row - g_row * S;   // ray within the group, sample index
     const bool row_in_group = g_row < G;
     const int g_el = stid / nS, e_el = stid - g_el * nS;  // (ray, element) view used by the merge phases

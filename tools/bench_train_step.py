@@ -152,9 +152,12 @@ def main():
                     help="fused: GeneratorNerfINR.train_integrate = 'fused' (native fancy_integration forward/backward in the NeRF autograd graph)")
     ap.add_argument("--tf32", action="store_true", help="allow TF32 in the torch autograd GEMMs / cuDNN convs of the training graph "
                     "(NOT the reference's numerics: torch defaults to fp32 matmuls); measures what the library path can give")
+    ap.add_argument("--no-cudnn-tf32", action="store_true", help="force fp32 cuDNN convolutions (torch's default -- and the reference's, "
+                    "torch >= 1.7 -- is cudnn.allow_tf32 = True, which this tool keeps)")
+    ap.add_argument("--profile", default=None, help="write a torch.profiler kernel table of 2 steps to this file (after the timing)")
     args = ap.parse_args()
     torch.backends.cuda.matmul.allow_tf32 = bool(args.tf32)
-    torch.backends.cudnn.allow_tf32 = bool(args.tf32)
+    torch.backends.cudnn.allow_tf32 = not args.no_cudnn_tf32
     cfg = dict(CONFIGS[args.config])
     if args.aux:
         cfg["aux"] = True
@@ -190,10 +193,19 @@ def main():
             metric="train step (D step + G step) images/s", value=B * world / ms.item() * 1e3, unit="images/s", ms_per_step=ms.item(),
             n_gpus=world, steps=args.steps, warmup=args.warmup,
             config=dict(baseline_config=args.config, resolution=R, batch_per_gpu=B, generator=G_cls.__name__, train_aux_img=cfg["aux"],
-                        diffaug=cfg["diffaug"], grad_points=cfg["grad_points"], optim=args.optim, tf32_autograd=bool(args.tf32), cips_backend=args.cips_backend, film_backend=args.film_backend, integrate_backend=args.integrate_backend,
+                        diffaug=cfg["diffaug"], grad_points=cfg["grad_points"], optim=args.optim, tf32_autograd=bool(args.tf32),
+                        cudnn_tf32=bool(torch.backends.cudnn.allow_tf32), cips_backend=args.cips_backend, film_backend=args.film_backend, integrate_backend=args.integrate_backend,
                         note="G forward under no_grad runs the fused kernels; the G step's autograd graph runs as torch CUDA ops "
                              "(backward kernels: DESIGN.md section 9); D convs are cuDNN as in the reference; D's bias_act / blur are native"),
             d_loss=float(dl), g_loss=float(gl), finite=bool(math.isfinite(float(dl)) and math.isfinite(float(gl))))))
+    if args.profile and rank == 0:
+        from torch.profiler import profile, ProfilerActivity
+        with profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA]) as prof:
+            for it in range(2):
+                step(args.warmup + args.steps + it)
+            torch.cuda.synchronize()
+        with open(args.profile, "w") as f:
+            f.write(prof.key_averages().table(sort_by="cuda_time_total", row_limit=60, max_name_column_width=90))
     if ddp:
         torch.distributed.destroy_process_group()
 
