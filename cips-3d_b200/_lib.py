@@ -12,7 +12,7 @@ LIB_PATH = os.environ.get("C3D_LIB_PATH", os.path.join(_HERE, "libcips3d_b200.so
 IMPL_TC, IMPL_SIMT = 0, 1
 CIPS_MAX_LAYERS = 18
 
-EXPORTS = ("c3d_version", "c3d_last_error", "c3d_device_supported", "c3d_launch_count",
+EXPORTS = ("c3d_reload_options", "c3d_debug_cips_max_clusters", "c3d_version", "c3d_last_error", "c3d_device_supported", "c3d_launch_count",
            "c3d_ray_siren_workspace_bytes",
            "c3d_ray_siren_fwd", "c3d_cips_workspace_bytes", "c3d_cips_fwd", "c3d_bias_act",
            "c3d_upfirdn2d", "c3d_selftest_umma", "c3d_selftest_umma_pair", "c3d_debug_cips_tile_order", "c3d_debug_ray_math_mode",
@@ -80,6 +80,7 @@ def load():
     """Load the shared library (once).  Raises if it has not been built."""
     global _lib
     if _lib is not None:
+        sync_options(_lib)
         return _lib
     if not os.path.exists(LIB_PATH):
         raise C3dError(f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'`. "
@@ -91,6 +92,20 @@ def load():
         raise C3dError(f"{LIB_PATH} is the CPU emulation build (test infrastructure); cips3d_b200 has no CPU path.")
     _lib = bind(lib)
     return _lib
+
+
+# The library snapshots its A/B variant switches from the environment once (csrc/api.cu: c3d_options) -- never on a launch path.
+# The host layer re-reads them only when one of these variables actually changed since the last call (tests and the A/B
+# timing tools flip them inside one process): a dict lookup per variable here, no getenv in the native code.
+_OPTION_VARS = ("C3D_CIPS_CLUSTER", "C3D_CIPS_PAIR", "C3D_BLUR", "C3D_BLUR_TMA", "C3D_PIGAN_IMPL", "C3D_PIGAN_PAIR", "C3D_RAY_MATH")
+_option_snapshot = {}
+
+
+def sync_options(lib):
+    snap = tuple(os.environ.get(k) for k in _OPTION_VARS)
+    if _option_snapshot.get(id(lib)) != snap:
+        lib.c3d_reload_options()
+        _option_snapshot[id(lib)] = snap
 
 
 def bind(lib):

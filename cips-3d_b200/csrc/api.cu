@@ -27,6 +27,37 @@ int c3d_ray_siren_fwd_tc(const C3dRayParams*, const C3dSirenWeights*, const C3dR
 size_t c3d_cips_tc_workspace_bytes(const C3dCipsParams* p);
 int c3d_cips_fwd_tc(const C3dCipsParams*, const C3dCipsWeights*, const float*, float*, float*, void*, size_t, cudaStream_t, void* acts_f16, void* zsign_u16);
 
+// ---- kernel-variant options: one process-wide snapshot of the environment
+#include <mutex>
+#include <stdlib.h>
+static C3dOptions g_opts;
+static std::once_flag g_opts_once;
+static void load_options() {
+  C3dOptions o;
+  auto geti = [](const char* n, int dflt) { const char* e = getenv(n); return e && *e ? atoi(e) : dflt; };
+  o.cips_cluster = geti("C3D_CIPS_CLUSTER", 1);
+  if (o.cips_cluster != 1 && o.cips_cluster != 2 && o.cips_cluster != 4) o.cips_cluster = 1;
+  o.cips_pair = geti("C3D_CIPS_PAIR", 0) != 0;
+  const char* b = getenv("C3D_BLUR");
+  o.blur_impl = !b || !*b ? 2 : (b[0] == 't' && b[1] == 'i' ? 0 : (b[0] == 't' ? 1 : 2));      // tile | tma | stream
+  if (geti("C3D_BLUR_TMA", 0) != 0) o.blur_impl = 1;                                             // round-1 spelling
+  const char* pg = getenv("C3D_PIGAN_IMPL");
+  o.pigan_tc = !(pg && (pg[0] == 's' || pg[0] == 'S'));
+  o.pigan_pair = geti("C3D_PIGAN_PAIR", 0) != 0;
+  const char* rm = getenv("C3D_RAY_MATH");
+  o.ray_math = !rm || !*rm ? C3D_RAY_MATH_DEFAULT : (rm[0] == 'f' ? 2 : (rm[0] == 'w' ? 1 : 0));
+  g_opts = o;
+}
+const C3dOptions& c3d_options() {
+  std::call_once(g_opts_once, load_options);
+  return g_opts;
+}
+// host layer / tests: re-read the environment (not thread-safe against concurrent launches; an A/B hook, not an API)
+extern "C" void c3d_reload_options(void) {
+  std::call_once(g_opts_once, [] {});
+  load_options();
+}
+
 extern "C" int c3d_version(void) { return 100; }
 extern "C" const char* c3d_last_error(void) { return g_err; }
 

@@ -43,6 +43,20 @@ void c3d_count_launch();
   } while (0)
 
 int c3d_device_sm_count(int dev);   // cached (api.cu)
+// Kernel-variant selection (A/B switches of the build, not part of the drop-in contract).  Read from the environment ONCE,
+// at the first use (or when the host layer calls c3d_reload_options()), never on a launch path.
+#ifndef C3D_RAY_MATH_DEFAULT
+#define C3D_RAY_MATH_DEFAULT 0
+#endif
+struct C3dOptions {
+  int cips_cluster;   // C3D_CIPS_CLUSTER: 1 | 2 | 4   weight multicast clusters of the CIPS kernel (default 1)
+  int cips_pair;      // C3D_CIPS_PAIR:    0 | 1       tcgen05 cta_group::2 CTA pairs (default 0: measured 2.3x slower, r02a)
+  int blur_impl;      // C3D_BLUR:         0 tile | 1 tma | 2 stream     4x4 FIR fast path (default: stream)
+  int pigan_tc;       // C3D_PIGAN_IMPL:   simt -> 0 | tc -> 1           pi-GAN renderer (default tc: 9.4x faster, r02a)
+  int pigan_pair;     // C3D_PIGAN_PAIR:   0 | 1 (default 0: measured 4 % slower, r02a)
+  int ray_math;       // C3D_RAY_MATH:     block -> 0 | warp -> 1 | fold -> 2   per-ray math form of the renderer
+};
+const C3dOptions& c3d_options();
 static inline int c3d_div_up(long long a, long long b) { return (int)((a + b - 1) / b); }
 
 // ---------------------------------------------------------------- PTX wrappers (device)

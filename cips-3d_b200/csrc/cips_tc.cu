@@ -616,13 +616,10 @@ static int cips_grid(const C3dCipsParams* p, int* cl_out, bool* pair_out) {
   int dev = 0;
   cudaGetDevice(&dev);
   const int sms = c3d_device_sm_count(dev);
-  int cl = 1;
-  if (const char* e = getenv("C3D_CIPS_CLUSTER")) cl = atoi(e);
-  if (cl != 1 && cl != 2 && cl != 4) cl = 1;
+  int cl = c3d_options().cips_cluster;
   const int tiles_per_img = (p->n_pix + kTileM - 1) / kTileM;
   // C3D_CIPS_PAIR=1: tcgen05 CTA pairs (cta_group::2).  Opt-in until it has been timed on hardware.
-  bool pair = false;
-  if (const char* e = getenv("C3D_CIPS_PAIR")) pair = atoi(e) != 0;
+  bool pair = c3d_options().cips_pair != 0;
   if (pair && (tiles_per_img % 2 || sms < 2)) pair = false;     // a pair works on two tiles of ONE image
   if (pair) cl = 2;
   *pair_out = pair;
@@ -700,6 +697,42 @@ static int launch_cips(const KArgs& ka, int grid, cudaStream_t st) {
   c3d_count_launch();
   C3D_CUDA(cudaLaunchKernelEx(&cfg, kern, ka));
   return C3D_OK;
+#endif
+}
+
+// diagnostic: how many clusters of `cl` CTAs of this kernel can be resident at once on the current device (a persistent
+// kernel whose grid exceeds that runs in WAVES).  pair != 0: the cta_group::2 instantiation.
+extern "C" int c3d_debug_cips_max_clusters(int cl, int pair) {
+#ifdef C3D_EMU
+  return 1 << 20;
+#else
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(148 / cl * cl);
+  cfg.blockDim = dim3(kThreads);
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = cl;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  int n = -1;
+  cudaError_t e;
+  if (pair) {
+    cfg.dynamicSmemBytes = sizeof(SmemT<true>) + 1024;
+    cudaFuncSetAttribute(cips_tc_kernel<2, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cfg.dynamicSmemBytes);
+    e = cudaOccupancyMaxActiveClusters(&n, cips_tc_kernel<2, true, false>, &cfg);
+  } else if (cl == 2) {
+    cfg.dynamicSmemBytes = sizeof(SmemT<false>) + 1024;
+    cudaFuncSetAttribute(cips_tc_kernel<2, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cfg.dynamicSmemBytes);
+    e = cudaOccupancyMaxActiveClusters(&n, cips_tc_kernel<2, false, false>, &cfg);
+  } else {
+    cfg.dynamicSmemBytes = sizeof(SmemT<false>) + 1024;
+    cudaFuncSetAttribute(cips_tc_kernel<1, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cfg.dynamicSmemBytes);
+    e = cudaOccupancyMaxActiveClusters(&n, cips_tc_kernel<1, false, false>, &cfg);
+  }
+  if (e != cudaSuccess) { c3d_set_error("cudaOccupancyMaxActiveClusters: %s", cudaGetErrorString(e)); return -1; }
+  return n;
 #endif
 }
 

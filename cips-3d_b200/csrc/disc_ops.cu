@@ -269,6 +269,62 @@ __global__ void __launch_bounds__(kBlurThreads) blur_tma_kernel(const BlurArgs a
   }
 }
 
+
+// ---- Blur, register-streaming form (default for the 4x4 FIR with up = down = 1: every Blur of the discriminator and its
+// backward).  No shared memory, no barriers: a thread owns ONE output column and marches down a strip of kStreamRows output
+// rows; the 4 x 4 window lives in registers (four rotating accumulators, one per output row in flight).  Per loop trip a
+// thread issues 16 independent 4-byte loads (4 input rows x 4 taps; 3 of the 4 taps of a row are L1 hits on the neighbour
+// lanes' lines) before it touches any of them, so a resident SM keeps ~128 KB of loads in flight -- the bytes-in-flight an
+// HBM-bound kernel needs and the tile / TMA forms (staged through shared memory behind barriers) never had: they measured
+// 15-32 % of the HBM peak (profiles/r02a_first_run.md).  Warp loads and stores are 128-byte coalesced rows (streaming
+// stores).  Bytes: reads H*W (+ 3 halo rows per strip: L2 hits), writes OH*OW per plane.
+constexpr int kStreamRows = 32;
+__global__ void __launch_bounds__(256) blur_stream_kernel(const float* __restrict__ x, const float* __restrict__ kernel,
+                                                          float* __restrict__ y, int in_h, int in_w, int out_h, int out_w,
+                                                          int pad_x0, int pad_y0, int strips_per_plane) {
+  const int ox = blockIdx.y * blockDim.x + threadIdx.x;
+  if (ox >= out_w) return;
+  const long long plane = blockIdx.x / strips_per_plane;
+  const int oy0 = (int)(blockIdx.x % strips_per_plane) * kStreamRows;
+  const int nrow = out_h - oy0 < kStreamRows ? out_h - oy0 : kStreamRows;
+  float kf[4][4];                      // flipped taps (correlation form), as upfirdn2d_kernel.cu:52-139
+#pragma unroll
+  for (int i = 0; i < 16; ++i) kf[i / 4][i % 4] = __ldg(kernel + (3 - i / 4) * 4 + (3 - i % 4));
+  const int ix0 = ox - pad_x0;
+  bool cok[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) cok[k] = ix0 + k >= 0 && ix0 + k < in_w;
+  const float* xp = x + (size_t)plane * in_h * in_w + ix0;
+  float* yp = y + ((size_t)plane * out_h + oy0) * out_w + ox;
+  const int iy0 = oy0 - pad_y0;
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  for (int rb = 0; rb < nrow + 3; rb += 4) {          // four input rows per trip: rows rb .. rb + 3 of the strip's footprint
+    float v[4][4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int iy = iy0 + rb + j;
+      const bool rok = iy >= 0 && iy < in_h && rb + j < nrow + 3;
+      const float* rp = xp + (size_t)(rok ? iy : 0) * in_w;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) v[j][k] = (rok && cok[k]) ? __ldg(rp + k) : 0.f;
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      // input row r = rb + j feeds outputs o = r - ky (ky = 0..3); output o lives in acc[o & 3] = acc[(j - ky) & 3]
+#pragma unroll
+      for (int ky = 0; ky < 4; ++ky) {
+        float a = acc[(j - ky) & 3];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) a = fmaf(v[j][k], kf[ky][k], a);
+        acc[(j - ky) & 3] = a;
+      }
+      const int o = rb + j - 3;          // complete after its fourth row
+      if (o >= 0 && o < nrow) __stcs(yp + (size_t)o * out_w, acc[(j + 1) & 3]);
+      acc[(j + 1) & 3] = 0.f;
+    }
+  }
+}
+
 }  // namespace c3d
 
 using namespace c3d;
@@ -319,8 +375,25 @@ extern "C" int c3d_upfirdn2d(const float* x, const float* kernel, float* y, int3
   int fw = (kTileW - 1) * down_x + kw, fh = (kTileH - 1) * down_y + kh;
   size_t smem = (size_t)fw * fh * sizeof(float);
   cudaStream_t st = (cudaStream_t)stream;
-  if (up_x == 1 && up_y == 1 && down_x == 1 && down_y == 1 && kh == 4 && kw == 4 && getenv("C3D_BLUR_TMA") &&
-      atoi(getenv("C3D_BLUR_TMA")) != 0 && in_w % 4 == 0 && ((uintptr_t)x & 15u) == 0 && pad_x0 >= 0 && pad_x0 <= kMargin &&
+  const int blur_impl = c3d_options().blur_impl;          // 0 tile | 1 tma | 2 stream (default)
+  if (up_x == 1 && up_y == 1 && down_x == 1 && down_y == 1 && kh == 4 && kw == 4 && blur_impl == 2) {
+    const int strips = c3d_div_up(out_h, kStreamRows);
+    const int nw = c3d_div_up(out_w, 32);
+    int bw = nw <= 8 ? nw : 8;                                   // warps per block: a divisor of the column-warp count if there is one
+    for (int d = 8; d >= 2 && nw > 8; --d)
+      if (nw % d == 0) { bw = d; break; }
+    const int col_blocks = c3d_div_up(out_w, bw * 32);
+    const long long max_planes = 2147483647LL / strips;
+    for (long long p0 = 0; p0 < planes; p0 += max_planes) {
+      const long long np = planes - p0 < max_planes ? planes - p0 : max_planes;
+      dim3 grid((unsigned)(np * strips), col_blocks);
+      C3D_LAUNCH(blur_stream_kernel, grid, bw * 32, 0, st, x + (size_t)p0 * in_h * in_w, kernel, y + (size_t)p0 * out_h * out_w,
+                 in_h, in_w, out_h, out_w, pad_x0, pad_y0, strips);
+      C3D_LAUNCH_CHECK();
+    }
+    return C3D_OK;
+  }
+  if (up_x == 1 && up_y == 1 && down_x == 1 && down_y == 1 && kh == 4 && kw == 4 && blur_impl == 1 && in_w % 4 == 0 && ((uintptr_t)x & 15u) == 0 && pad_x0 >= 0 && pad_x0 <= kMargin &&
       pad_x1 >= 0 && pad_x1 <= 4 && pad_y0 >= 0 && pad_y1 >= 0 && in_w <= 1024) {
     BlurArgs ba;
     ba.x = x; ba.kernel = kernel; ba.y = y;

@@ -231,10 +231,7 @@ size_t c3d_pigan_tc_workspace_bytes(const C3dRayParams* p);
 bool c3d_pigan_tc_supported(const C3dRayParams* p, const C3dPiganWeights* w);
 int c3d_pigan_render_fwd_tc(const C3dRayParams* p, const C3dPiganWeights* w, const C3dRayIO* io, int lock_view, void* workspace,
                             size_t workspace_bytes, cudaStream_t st);
-static bool pg_want_tc() {
-  const char* e = getenv("C3D_PIGAN_IMPL");
-  return e && (e[0] == 't' || e[0] == 'T');
-}
+static bool pg_want_tc() { return c3d_options().pigan_tc != 0; }
 
 extern "C" size_t c3d_pigan_workspace_bytes(const C3dRayParams* p) {
   if (!p) return 0;

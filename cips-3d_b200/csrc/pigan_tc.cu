@@ -595,8 +595,7 @@ int c3d_pigan_render_fwd_tc(const C3dRayParams* p, const C3dPiganWeights* w, con
   uint8_t* base = (uint8_t*)workspace;
   const int sms = c3d_device_sm_count(dev);
   // C3D_PIGAN_PAIR=1: tcgen05 CTA pairs (two ray groups per weight stream).  Opt-in until timed on hardware.
-  bool pair = false;
-  if (const char* e = getenv("C3D_PIGAN_PAIR")) pair = atoi(e) != 0 && sms >= 2;
+  const bool pair = c3d_options().pigan_pair != 0 && sms >= 2;
   if (pair) C3D_LAUNCH(pigan_prep_weights_kernel<true>, kStreamLayers * (kH / kKC), 256, 0, st, *w, base + ws.tiles, (float4*)(base + ws.wl4));
   else C3D_LAUNCH(pigan_prep_weights_kernel<false>, kStreamLayers * (kH / kKC), 256, 0, st, *w, base + ws.tiles, (float4*)(base + ws.wl4));
   C3D_LAUNCH_CHECK();

@@ -199,56 +199,49 @@ __global__ void __launch_bounds__(640, 1) ray_siren_tc_kernel(const KArgs a) {
         mbar_arrive_expect_tx(&s.w_full, kWBlobBytes);
         for (int off = 0; off < kWBlobBytes; off += 16384) bulk_g2s(s.w + off, a.wblob + off, 16384, &s.w_full);
       }
-    } else if (warp == 1) {
-      // ---------------------------------------------------------- MMA issuer: the whole warp stays converged
-      // (operands live in uniform registers, no per-MMA lane loop); one elected lane issues for whichever slot
-      // is ready.
+    } else if (warp == 1 || warp == 3) {
+      // ---------------------------------------------------------- MMA issuers: one warp PER SLOT (warp 1 -> slot 0, warp 3 ->
+      // slot 1), each blocking on its slot's a_ready barrier (hardware-suspended try_wait).  Round 1 had ONE issuer polling
+      // both slots with test_wait + __nanosleep(64): the r02b trace (profiles/r02b_ray_trace.md) showed 1.0-1.3 k clk between
+      // the last worker's arrive and the MMA issue -- the sleep granularity, eight times per ray group and slot (a fifth of
+      // the group's critical path).  The whole warp stays converged (operands in uniform registers, no per-MMA lane loop);
+      // one elected lane issues.
+      const int sl = warp == 1 ? 0 : 1;
       mbar_wait(&s.w_full, 0);
       const uint32_t wb = smem_u32(s.w);
       const uint32_t dhi = umma_desc_hi(128);
       const uint32_t w1h = umma_desc_lo(wb + kOffW1h, 128 * 16), w1l = umma_desc_lo(wb + kOffW1l, 128 * 16);
       const uint32_t w2h = umma_desc_lo(wb + kOffW2h, kNc * 16), w2l = umma_desc_lo(wb + kOffW2l, kNc * 16);
       const uint32_t w3h = umma_desc_lo(wb + kOffW3h, 32 * 16), w3l = umma_desc_lo(wb + kOffW3l, 32 * 16);
-      uint32_t par[2] = {0, 0};
-      int done[2] = {0, 0};
+      const uint32_t w0h = umma_desc_lo(smem_u32(s.slot[sl].w0), 128 * 16);
+      uint32_t par = 0;
       const int total = iters * mma_phases;
-      uint32_t idle = 0;
-      unsigned long long idle_t0 = 0;
-      while (done[0] < total || done[1] < total) {
-        if ((++idle & 0xFFFFu) == 0 && (idle_t0 == 0 ? (idle_t0 = c3d_globaltimer(), false)
-                                                      : c3d_globaltimer() - idle_t0 > C3D_WATCHDOG_NS)) {
-          if (lane == 0) printf("c3d watchdog: ray MMA issuer starved (block %d, done %d/%d of %d)\n", (int)blockIdx.x, done[0], done[1], total);
-          __trap();
+#pragma unroll 1
+      for (int done = 0; done < total; ++done) {
+        mbar_wait(&s.a_ready[sl], par);
+        par ^= 1;
+        tc_fence_after();
+        const int layer = FOLD ? done % 3 : (done & 3);
+        if (lane == 0) RTRACE(done / mma_phases, 1, (uint32_t)(sl << 15 | ((done / mma_phases) & 1) << 8 | (done % mma_phases)));
+        if (elect_one()) {
+          uint32_t a_hi = tmem + (uint32_t)(sl * 256), a_lo = a_hi + 64;
+          const uint32_t d = a_hi + 128;
+          uint32_t bh = layer == 0 ? w0h : (layer == 1 ? w1h : (layer == 2 ? w2h : w3h));
+          uint32_t bl = layer == 0 ? w0h + (kW0Bytes >> 4) : (layer == 1 ? w1l : (layer == 2 ? w2l : w3l));
+          // opaque per-iteration copies: keeps the compiler from materialising ~60 loop-invariant descriptor words
+          // outside the loop (they would spill and cost an LDL per MMA)
+          asm volatile("" : "+r"(bh), "+r"(bl), "+r"(a_hi), "+r"(a_lo));
+          if (layer == 0) mma_split3<128, 16>(d, a_hi, a_lo, bh, bl, dhi);
+          else if (layer == 1) mma_split3<128, 128>(d, a_hi, a_lo, bh, bl, dhi);
+          else if (layer == 2) mma_split3<kNc, 128>(d, a_hi, a_lo, bh, bl, dhi);
+          else if (!FOLD) mma_split3<32, 64>(d, a_hi, a_lo, bh, bl, dhi);
+          tc_commit(&s.d_ready[sl]);
         }
-#pragma unroll
-        for (int sl = 0; sl < 2; ++sl) {
-          if (done[sl] < total && __all_sync(0xffffffffu, mbar_test(&s.a_ready[sl], par[sl]))) {
-            par[sl] ^= 1;
-            tc_fence_after();
-            const int layer = FOLD ? done[sl] % 3 : (done[sl] & 3);
-            if (lane == 0) RTRACE(done[sl] / mma_phases, 1, (uint32_t)(sl << 15 | ((done[sl] / mma_phases) & 1) << 8 | (done[sl] % mma_phases)));
-            if (elect_one()) {
-              uint32_t a_hi = tmem + (uint32_t)(sl * 256), a_lo = a_hi + 64;
-              const uint32_t d = a_hi + 128;
-              // opaque per-iteration copies: keeps the compiler from hoisting ~60 loop-invariant descriptor
-              // words out of the loop (they would spill and cost an LDL per MMA)
-              const uint32_t w0h = umma_desc_lo(smem_u32(s.slot[sl].w0), 128 * 16);
-              uint32_t bh = layer == 0 ? w0h : (layer == 1 ? w1h : (layer == 2 ? w2h : w3h));
-              uint32_t bl = layer == 0 ? w0h + (kW0Bytes >> 4) : (layer == 1 ? w1l : (layer == 2 ? w2l : w3l));
-              asm volatile("" : "+r"(bh), "+r"(bl), "+r"(a_hi), "+r"(a_lo));
-              if (layer == 0) mma_split3<128, 16>(d, a_hi, a_lo, bh, bl, dhi);
-              else if (layer == 1) mma_split3<128, 128>(d, a_hi, a_lo, bh, bl, dhi);
-              else if (layer == 2) mma_split3<kNc, 128>(d, a_hi, a_lo, bh, bl, dhi);
-              else if (!FOLD) mma_split3<32, 64>(d, a_hi, a_lo, bh, bl, dhi);
-              tc_commit(&s.d_ready[sl]);
-            }
-            __syncwarp();
-            ++done[sl];
-            idle = 0;
-            idle_t0 = 0;
-          }
-        }
-        if (idle) __nanosleep(64);   // nothing ready: yield the issue port to the workers on this scheduler
+        __syncwarp();
+#ifdef C3D_TRACE      // when does a SPINNING observer see the commit?  (worker D-ready stamp minus this = wake-up latency of the suspended wait)
+        while (!__all_sync(0xffffffffu, mbar_test(&s.d_ready[sl], par ^ 1))) {}
+        if (lane == 0) RTRACE(done / mma_phases, 14, (uint32_t)(sl << 15 | ((done / mma_phases) & 1) << 8 | (done % mma_phases)));
+#endif
       }
     }
   } else {
@@ -834,10 +827,10 @@ int c3d_ray_siren_fwd_tc(const C3dRayParams* p, const C3dSirenWeights* w, const 
   // C3D_RAY_MATH=warp: warp-per-ray math (needs 2S <= 32 samples per warp); =fold: warp math + the sigma head in the E1
   // epilogue and color_layer_linear applied after compositing (3 MMA phases per pass instead of 4; not with the
   // per-point debug outputs); default: the round-1 block-wide form
-  const char* rm = getenv("C3D_RAY_MATH");
+  const int rm = c3d_options().ray_math;
   const bool warp_ok = p->num_steps * (p->hierarchical ? 2 : 1) <= 32 && (!p->hierarchical || p->num_steps <= 16);
-  const bool fold_math = rm && rm[0] == 'f' && warp_ok && !io->dbg_coarse && !io->dbg_fine;
-  const bool warp_math = rm && (rm[0] == 'w' || rm[0] == 'f') && warp_ok;
+  const bool fold_math = rm == 2 && warp_ok && !io->dbg_coarse && !io->dbg_fine;
+  const bool warp_math = rm >= 1 && warp_ok;
   C3D_LAUNCH(ray_prep_kernel, 64, 256, 0, st, *w, p->batch, base + ws.blob, (ImgConsts*)(base + ws.consts), fold_math ? 1 : 0);
   C3D_LAUNCH_CHECK();
   KArgs ka = {};

@@ -34,7 +34,9 @@ class FusedLeakyReLU(nn.Module):
 
 
 class EqualConv2d(nn.Module):
-    """N(0,1) weights with the He constant applied at run time (discriminator.py:20-54); cuDNN conv."""
+    """N(0,1) weights with the He constant applied at run time (discriminator.py:20-54).  The product is the library's implicit
+    GEMM (as in the reference); the autograd structure is ops.conv2d's: fprop / dgrad / wgrad Functions closed under
+    differentiation, so the R1 double backward never takes torch's generic slow path."""
 
     def __init__(self, in_channel, out_channel, kernel_size, stride=1, padding=0, bias=True):
         super().__init__()
@@ -44,7 +46,7 @@ class EqualConv2d(nn.Module):
         self.stride, self.padding = stride, padding
 
     def forward(self, input):
-        return F.conv2d(input, self.weight * self.scale, self.bias, self.stride, self.padding)
+        return ops.conv2d(input, self.weight * self.scale, self.bias, self.stride, self.padding)
 
     def extra_repr(self):
         o, i, k, _ = self.weight.shape

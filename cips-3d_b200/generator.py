@@ -344,7 +344,7 @@ class CIPSNet(nn.Module):                       # generator.py:1009-1154
         return self.tanh(rgb) if not isinstance(rgb, int) else self.tanh(torch.zeros_like(input[..., :3]))
 
     def kernel_inputs(self, style_dict, n_blocks):
-        if (os.environ.get("C3D_STYLE_PREP", "torch") == "fused" and not torch.is_grad_enabled()
+        if (os.environ.get("C3D_STYLE_PREP", "fused") == "fused" and not torch.is_grad_enabled()
                 and all(b.mod1.use_style_fc and b.mod1.demodulate for b in self.network.values())):
             return self.kernel_inputs_fused(style_dict, n_blocks)
         ws, s1ps, ds, rw, rb = [], [], [], [], []

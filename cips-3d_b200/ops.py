@@ -233,6 +233,97 @@ def _upfirdn2d_raw(x, kernel, up, down, pad):
     return y
 
 
+# ---------------------------------------------------------------------------------------------------------------------
+# Discriminator convolution (row D1: exp/cips3d/models/discriminator.py:20-54 calls F.conv2d).  The arithmetic is the library's
+# (cuDNN / CUTLASS implicit GEMM, TF32 as torch and the reference default to), but the AUTOGRAD STRUCTURE is this repo's: the
+# R1 penalty (train.py:379-386) differentiates ||dD/dx||^2, i.e. runs the DOUBLE backward of every convolution, and torch's
+# generic `_convolution_double_backward` evaluates the weight gradient of that pass as a convolution with batch and channel
+# dimensions swapped -- a "kernel" the size of the feature map, which cuDNN serves with a legacy indexed implicit-GEMM:
+# 16 calls of 9.2 ms = 40 % of a whole config-5 train step (profiles/r02b_train_profiles.md).  Here the three primitive
+# products (fprop, dgrad, wgrad) are autograd Functions whose backwards are expressed in terms of each other, so every pass of
+# every order runs one of the three purpose-built kernels.
+def _conv_args(stride, padding):
+    return [stride, stride], [padding, padding], [1, 1], False, [0, 0], 1
+
+
+def _conv_fprop(x, w, b, stride, padding):
+    return torch.ops.aten.convolution(x, w, b, *_conv_args(stride, padding))
+
+
+def _conv_dgrad(gy, w, x_shape, stride, padding):
+    x_like = gy.new_empty(1).expand(x_shape)          # only its sizes are read (torch.nn.grad.conv2d_input does the same)
+    return torch.ops.aten.convolution_backward(gy, x_like, w, None, *_conv_args(stride, padding), (True, False, False))[0]
+
+
+def _conv_wgrad(gy, x, w_shape, stride, padding):
+    w_like = gy.new_empty(1).expand(w_shape)
+    return torch.ops.aten.convolution_backward(gy, x, w_like, None, *_conv_args(stride, padding), (False, True, False))[1]
+
+
+class _Conv2dDgrad(Function):
+    """gx = dgrad(gy, w); its backward (the double backward of the convolution): d gy = fprop(ggx, w), d w = wgrad(gy, ggx)."""
+
+    @staticmethod
+    def forward(ctx, gy, w, x_shape, stride, padding):
+        ctx.save_for_backward(gy, w)
+        ctx.cfg = (tuple(x_shape), stride, padding)
+        return _conv_dgrad(gy, w, x_shape, stride, padding)
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, ggx):
+        gy, w = ctx.saved_tensors
+        x_shape, stride, padding = ctx.cfg
+        ggx = ggx.contiguous()
+        d_gy = _conv_fprop(ggx, w, None, stride, padding) if ctx.needs_input_grad[0] else None
+        d_w = _conv_wgrad(gy, ggx, w.shape, stride, padding) if ctx.needs_input_grad[1] else None
+        return d_gy, d_w, None, None, None
+
+
+class _Conv2dWgrad(Function):
+    """gw = wgrad(gy, x); its backward: d gy = fprop(x, ggw), d x = dgrad(gy, ggw)."""
+
+    @staticmethod
+    def forward(ctx, gy, x, w_shape, stride, padding):
+        ctx.save_for_backward(gy, x)
+        ctx.cfg = (tuple(w_shape), stride, padding)
+        return _conv_wgrad(gy, x, w_shape, stride, padding)
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, ggw):
+        gy, x = ctx.saved_tensors
+        _, stride, padding = ctx.cfg
+        ggw = ggw.contiguous()
+        d_gy = _conv_fprop(x, ggw, None, stride, padding) if ctx.needs_input_grad[0] else None
+        d_x = _conv_dgrad(gy, ggw, x.shape, stride, padding) if ctx.needs_input_grad[1] else None
+        return d_gy, d_x, None, None, None
+
+
+class _Conv2d(Function):
+    @staticmethod
+    def forward(ctx, x, w, b, stride, padding):
+        ctx.save_for_backward(x, w)
+        ctx.cfg = (stride, padding, b is not None)
+        return _conv_fprop(x, w, b, stride, padding)
+
+    @staticmethod
+    def backward(ctx, gy):                     # differentiable again: R1 runs autograd.grad(..., create_graph=True) through it
+        x, w = ctx.saved_tensors
+        stride, padding, has_bias = ctx.cfg
+        gy = gy.contiguous()
+        gx = _Conv2dDgrad.apply(gy, w, x.shape, stride, padding) if ctx.needs_input_grad[0] else None
+        gw = _Conv2dWgrad.apply(gy, x, w.shape, stride, padding) if ctx.needs_input_grad[1] else None
+        gb = gy.sum((0, 2, 3)) if has_bias and ctx.needs_input_grad[2] else None
+        return gx, gw, gb, None, None
+
+
+def conv2d(input, weight, bias=None, stride=1, padding=0):
+    """F.conv2d(input, weight, bias, stride, padding) for the discriminator's EqualConv2d (square stride / padding, groups 1,
+    dilation 1), twice differentiable, with every backward pass of every order on a purpose-built fprop / dgrad / wgrad kernel."""
+    return _Conv2d.apply(input.contiguous(), weight.contiguous(), bias, int(stride), int(padding))
+
+
 class _UpFirDn2dBackward(Function):                 # upfirdn2d.py:18-85
     @staticmethod
     def forward(ctx, grad_output, kernel, grad_kernel, up, down, pad, g_pad, in_size):

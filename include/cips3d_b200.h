@@ -355,6 +355,17 @@ int c3d_debug_cips_tile_order(uint16_t* order_full32, uint16_t* order_in4);
  * exercised the form they name. */
 int c3d_debug_ray_math_mode(void);
 
+/* Kernel-variant switches (A/B hooks of this build, not part of the drop-in contract): C3D_CIPS_CLUSTER, C3D_CIPS_PAIR,
+ * C3D_BLUR, C3D_PIGAN_IMPL, C3D_PIGAN_PAIR, C3D_RAY_MATH are read from the environment ONCE, at the first call into the
+ * library -- never on a launch path.  c3d_reload_options() re-reads them (host layer / tests: the Python binding calls it
+ * only when one of the variables changed).  Not safe against concurrent launches on other threads. */
+void c3d_reload_options(void);
+
+/* Diagnostic (no GPU work): how many thread-block clusters of `cl` CTAs of the CIPS kernel (pair != 0: its cta_group::2
+ * instantiation) can be resident at once on the current device -- a persistent kernel whose grid exceeds that runs in waves.
+ * Negative on error. */
+int c3d_debug_cips_max_clusters(int cl, int pair);
+
 #ifdef __cplusplus
 }
 #endif

@@ -265,6 +265,27 @@ def test_emu_blur_tma_streaming_kernel(shape, pad, mode, monkeypatch):
         assert y.shape == ref.shape and (y - ref).abs().max().item() < 1e-5
 
 
+@pytest.mark.parametrize("impl", ["stream", "tile"])
+@pytest.mark.parametrize("shape,pad", [
+    ((2, 3, 64, 64), (2, 2, 2, 2)), ((1, 2, 256, 256), (1, 1, 1, 1)), ((1, 2, 256, 256), (2, 2, 2, 2)),
+    ((3, 1, 8, 8), (2, 2, 2, 2)), ((1, 5, 4, 4), (1, 1, 1, 1)), ((1, 1, 100, 36), (2, 1, 0, 3)), ((1, 2, 70, 128), (1, 1, 1, 1)),
+    ((1, 1, 33, 300), (1, 2, 2, 1)), ((1, 1, 5, 2), (3, 3, 3, 3)), ((1, 2, 37, 65), (-1, 2, 2, -1))])
+def test_emu_blur_register_streaming_kernel(shape, pad, impl, monkeypatch):
+    """C3D_BLUR=stream (the default 4x4 FIR path: thread = output column marching down a 32-row strip, the window in
+    registers, no shared memory) and the round-1 tile form, against the oracle: both paddings D uses at 256^2 (out 257 / 255),
+    planes smaller than a strip, ragged last strips, more than 8 column warps, asymmetric and NEGATIVE pads (crop), a
+    non-separable random kernel."""
+    monkeypatch.setenv("C3D_BLUR", impl)
+    g = torch.Generator().manual_seed(sum(shape))
+    x = torch.randn(*shape, generator=g)
+    k1 = torch.tensor([1., 3., 3., 1.])
+    for k in ((k1[None] * k1[:, None]) / 64, torch.randn(4, 4, generator=g)):
+        with emulated(async_mode=0, sms=2) as pkg:
+            y = pkg.ops._upfirdn2d_raw(x, k, (1, 1), (1, 1), pad)
+        ref = O.upfirdn2d(x, k, (1, 1), (1, 1), pad)
+        assert y.shape == ref.shape and (y - ref).abs().max().item() < 1e-5
+
+
 @pytest.mark.parametrize("impl,mode", [("simt", "eager"), ("tc", "lazy"), ("tc", "random"), ("tc-pair", "lazy"), ("tc-pair", "random")])
 @pytest.mark.parametrize("name", PIGAN_CASES)
 def test_emu_pigan_renderer_matches_reference_golden(name, impl, mode, monkeypatch):

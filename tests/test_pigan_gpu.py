@@ -78,12 +78,12 @@ def test_pigan_training_graph_backprops_and_matches_native(pkg):
     assert frac >= 0.99
 
 
-@pytest.mark.skipif(os.environ.get("C3D_EXPERIMENTAL", "0") != "1", reason="hardware-unvalidated kernel: set C3D_EXPERIMENTAL=1")
-@pytest.mark.parametrize("pair", ["0", "1"])
+@pytest.mark.parametrize("impl,pair", [("tc", "0"), ("tc", "1"), ("simt", "0")])
 @pytest.mark.parametrize("name", [c for c in PIGAN_CASES if "staged" not in c])
-def test_pigan_tc_kernel_matches_reference_golden(pkg, name, pair, monkeypatch):
-    """C3D_PIGAN_IMPL=tc: the fused tcgen05 pi-GAN renderer (pigan_tc.cu) through the class surface; pair = CTA-pair form."""
-    monkeypatch.setenv("C3D_PIGAN_IMPL", "tc")
+def test_pigan_renderer_variants_match_reference_golden(pkg, name, impl, pair, monkeypatch):
+    """Every native pi-GAN renderer through the class surface: the fused tcgen05 kernel (pigan_tc.cu; the default since its
+    first hardware run, profiles/r02a_first_run.md), its CTA-pair form, and the fp32-FMA per-layer cross-check (pigan_simt.cu)."""
+    monkeypatch.setenv("C3D_PIGAN_IMPL", impl)
     monkeypatch.setenv("C3D_PIGAN_PAIR", pair)
     sd, z, draws, kw, meta, ref = load_pigan_case(name)
     G = _build(pkg, sd, meta)

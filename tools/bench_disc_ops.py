@@ -26,7 +26,7 @@ def timeit(fn, reps=20):
 
 out = []
 k = cips3d_b200.discriminator.make_kernel([1, 3, 3, 1]).to(dev)
-VARIANTS = os.environ.get("C3D_BLUR_TMA", "0")
+VARIANTS = os.environ.get("C3D_BLUR", "stream")
 for (B, C, H) in [(16, 128, 256), (16, 256, 128), (16, 512, 64)]:
     x = torch.randn(B, C, H, H, device=dev)
     b = torch.randn(C, device=dev)
@@ -41,7 +41,7 @@ for (B, C, H) in [(16, 128, 256), (16, 256, 128), (16, 512, 64)]:
         ms = timeit(lambda: ops._upfirdn2d_raw(x, k, (1, 1), (1, 1), (pad[0], pad[1], pad[0], pad[1])))
         Ho = H + pad[0] + pad[1] - 3
         gb = (x.numel() + B * C * Ho * Ho) * 4 / 1e9
-        out.append(dict(op=f"upfirdn2d blur pad{pad} (C3D_BLUR_TMA={VARIANTS})", shape=[B, C, H, H], ms=ms, gbs=gb / ms * 1e3, frac=gb / ms * 1e3 / peak))
+        out.append(dict(op=f"upfirdn2d blur pad{pad} (C3D_BLUR={VARIANTS})", shape=[B, C, H, H], ms=ms, gbs=gb / ms * 1e3, frac=gb / ms * 1e3 / peak))
 # image export: 4*C bytes read + C written per pixel; the torch-op chain the reference runs beside it
 for (B, H) in [(16, 256), (64, 256), (16, 512)]:
     nhwc = torch.tanh(torch.randn(B, H, H, 3, device=dev))

@@ -28,7 +28,7 @@ for v in buf[:n]:
     ev.append((t, tag, a0 >> 15, (a0 >> 12) & 7, (a0 >> 8) & 1, a0 & 0xFF))
 ev.sort()
 t0 = ev[0][0]
-names = {1: "MMA issue", 2: "A0 written", 3: "D0 ready", 4: "E0 done", 5: "D1 ready", 6: "E1 done", 7: "D2 ready", 8: "E2 done",
+names = {14: "MMA done (spin)", 1: "MMA issue", 2: "A0 written", 3: "D0 ready", 4: "E0 done", 5: "D1 ready", 6: "E1 done", 7: "D2 ready", 8: "E2 done",
          9: "D3 ready", 10: "E3+sync", 11: "resample done", 12: "merge done", 13: "composite done"}
 print("events", n, "math mode", lib.c3d_debug_ray_math_mode())
 groups = collections.OrderedDict()
