@@ -279,24 +279,13 @@ __global__ void __launch_bounds__(kBlurThreads) blur_tma_kernel(const BlurArgs a
 // 15-32 % of the HBM peak (profiles/r02a_first_run.md).  Warp loads and stores are 128-byte coalesced rows (streaming
 // stores).  Bytes: reads H*W (+ 3 halo rows per strip: L2 hits), writes OH*OW per plane.
 constexpr int kStreamRows = 32;
-__global__ void __launch_bounds__(256) blur_stream_kernel(const float* __restrict__ x, const float* __restrict__ kernel,
-                                                          float* __restrict__ y, int in_h, int in_w, int out_h, int out_w,
-                                                          int pad_x0, int pad_y0, int strips_per_plane) {
-  const int ox = blockIdx.y * blockDim.x + threadIdx.x;
-  if (ox >= out_w) return;
-  const long long plane = blockIdx.x / strips_per_plane;
-  const int oy0 = (int)(blockIdx.x % strips_per_plane) * kStreamRows;
-  const int nrow = out_h - oy0 < kStreamRows ? out_h - oy0 : kStreamRows;
-  float kf[4][4];                      // flipped taps (correlation form), as upfirdn2d_kernel.cu:52-139
-#pragma unroll
-  for (int i = 0; i < 16; ++i) kf[i / 4][i % 4] = __ldg(kernel + (3 - i / 4) * 4 + (3 - i % 4));
-  const int ix0 = ox - pad_x0;
-  bool cok[4];
-#pragma unroll
-  for (int k = 0; k < 4; ++k) cok[k] = ix0 + k >= 0 && ix0 + k < in_w;
-  const float* xp = x + (size_t)plane * in_h * in_w + ix0;
-  float* yp = y + ((size_t)plane * out_h + oy0) * out_w + ox;
-  const int iy0 = oy0 - pad_y0;
+// SEP: the taps are an outer product ky (x) kx (every Blur of the discriminator: make_kernel([1,3,3,1])): 4 + 4 FMAs per output
+// instead of 16 -- the generic form is issue-bound (26 instructions per 8 bytes of traffic: measured 0.40-0.54 of the HBM peak,
+// profiles/r02c), the separable one needs 16.  Decided per launch, inside the kernel, from the 16 taps every thread holds anyway.
+template <bool SEP>
+__device__ __forceinline__ void blur_stream_strip(const float* __restrict__ xp, float* __restrict__ yp, const float (&kf)[4][4],
+                                                  const float (&kyv)[4], const bool (&cok)[4], int iy0, int in_h, int in_w,
+                                                  int out_w, int nrow) {
   float acc[4] = {0.f, 0.f, 0.f, 0.f};
   for (int rb = 0; rb < nrow + 3; rb += 4) {          // four input rows per trip: rows rb .. rb + 3 of the strip's footprint
     float v[4][4];
@@ -311,18 +300,58 @@ __global__ void __launch_bounds__(256) blur_stream_kernel(const float* __restric
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       // input row r = rb + j feeds outputs o = r - ky (ky = 0..3); output o lives in acc[o & 3] = acc[(j - ky) & 3]
+      if (SEP) {
+        float h = v[j][0] * kf[0][0];
 #pragma unroll
-      for (int ky = 0; ky < 4; ++ky) {
-        float a = acc[(j - ky) & 3];
+        for (int k = 1; k < 4; ++k) h = fmaf(v[j][k], kf[0][k], h);
 #pragma unroll
-        for (int k = 0; k < 4; ++k) a = fmaf(v[j][k], kf[ky][k], a);
-        acc[(j - ky) & 3] = a;
+        for (int ky = 0; ky < 4; ++ky) acc[(j - ky) & 3] = fmaf(h, kyv[ky], acc[(j - ky) & 3]);
+      } else {
+#pragma unroll
+        for (int ky = 0; ky < 4; ++ky) {
+          float a = acc[(j - ky) & 3];
+#pragma unroll
+          for (int k = 0; k < 4; ++k) a = fmaf(v[j][k], kf[ky][k], a);
+          acc[(j - ky) & 3] = a;
+        }
       }
       const int o = rb + j - 3;          // complete after its fourth row
       if (o >= 0 && o < nrow) __stcs(yp + (size_t)o * out_w, acc[(j + 1) & 3]);
       acc[(j + 1) & 3] = 0.f;
     }
   }
+}
+
+__global__ void __launch_bounds__(256) blur_stream_kernel(const float* __restrict__ x, const float* __restrict__ kernel,
+                                                          float* __restrict__ y, int in_h, int in_w, int out_h, int out_w,
+                                                          int pad_x0, int pad_y0, int strips_per_plane) {
+  const int ox = blockIdx.y * blockDim.x + threadIdx.x;
+  if (ox >= out_w) return;
+  const long long plane = blockIdx.x / strips_per_plane;
+  const int oy0 = (int)(blockIdx.x % strips_per_plane) * kStreamRows;
+  const int nrow = out_h - oy0 < kStreamRows ? out_h - oy0 : kStreamRows;
+  float kf[4][4];                      // flipped taps (correlation form), as upfirdn2d_kernel.cu:52-139
+#pragma unroll
+  for (int i = 0; i < 16; ++i) kf[i / 4][i % 4] = __ldg(kernel + (3 - i / 4) * 4 + (3 - i % 4));
+  float kyv[4] = {1.f, 0.f, 0.f, 0.f};
+  bool sep = kf[0][0] != 0.f;
+  if (sep) {
+#pragma unroll
+    for (int i = 1; i < 4; ++i) kyv[i] = kf[i][0] / kf[0][0];
+#pragma unroll
+    for (int i = 1; i < 4; ++i)
+#pragma unroll
+      for (int j = 1; j < 4; ++j) sep = sep && fabsf(kyv[i] * kf[0][j] - kf[i][j]) <= 1e-6f * fabsf(kf[i][j]);
+  }
+  const int ix0 = ox - pad_x0;
+  bool cok[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) cok[k] = ix0 + k >= 0 && ix0 + k < in_w;
+  const float* xp = x + (size_t)plane * in_h * in_w + ix0;
+  float* yp = y + ((size_t)plane * out_h + oy0) * out_w + ox;
+  const int iy0 = oy0 - pad_y0;
+  if (sep) blur_stream_strip<true>(xp, yp, kf, kyv, cok, iy0, in_h, in_w, out_w, nrow);     // block-uniform branch
+  else blur_stream_strip<false>(xp, yp, kf, kyv, cok, iy0, in_h, in_w, out_w, nrow);
 }
 
 }  // namespace c3d

@@ -21,6 +21,7 @@
 // Weights (fp16 hi/lo, scaled by 2^8 to keep the lo parts normal) sit in shared memory for the
 // whole kernel (112 KB, loaded once per CTA by bulk async copies).
 #include <atomic>
+#include <string.h>
 
 #include "c3d_common.cuh"
 #include "ray_math.cuh"
@@ -71,7 +72,8 @@ struct Smem {
   alignas(1024) uint8_t w[kWBlobBytes];
   SlotMem slot[2];
   alignas(8) uint64_t w_full;
-  uint64_t a_ready[2];
+  uint64_t a_ready[2][3];   // [slot][stage]: one barrier per MMA stage of a layer (a warp arrives ONCE per layer on each: arrivals of two
+                            // stages on one barrier would be indistinguishable when a fast warp runs a stage ahead of a slow one)
   uint64_t d_ready[2];
   uint32_t tmem_base;
 };
@@ -86,20 +88,25 @@ struct KArgs {
   int G;                      // rays per group
   int groups_per_img, total_groups;
   const float* w_sigma;       // (128) final_layer weight, fp32 (MATH = 2 only: sigma head in the E1 epilogue)
+  int stagger_ns;             // A/B knob: slot 1 starts this much later than slot 0
 };
 
 __device__ __forceinline__ float fast_sin(float x) { return __sinf(x); }
 
-#ifdef C3D_TRACE   // debug build: block 0 stamps the phases of iteration 3
-__device__ unsigned long long g_rtrace[4096];
-__device__ unsigned int g_rtrace_n;
-__device__ __forceinline__ void rtrace(int it, uint32_t tag, uint32_t a0) {
+#ifdef C3D_TRACE   // debug build: block 0 stamps the phases of iterations 3 and 4.  One fixed slot per (iteration parity, warp,
+// stamp index): a plain fire-and-forget store -- round 2's first trace used an atomic counter whose ~500 clk round trip sat on
+// the critical path of every stamp (issuer wake-up -> atomic -> MMA issue) and inflated each phase by about 1 k clk.
+__device__ unsigned long long g_rtrace[2 * 20 * 64];
+__device__ __forceinline__ void rtrace(int it, uint32_t tag, uint32_t a0, int& n) {
   if (blockIdx.x == 0 && (it == 3 || it == 4)) {
-    unsigned int i = atomicAdd(&g_rtrace_n, 1u);
-    if (i < 4096) g_rtrace[i] = ((unsigned long long)tag << 56) | ((unsigned long long)(a0 & 0xFFFF) << 40) | (clock64() & 0xFFFFFFFFFFull);
+    const int w = threadIdx.x >> 5;
+    if (n < 64) g_rtrace[((it & 1) * 20 + w) * 64 + n] = ((unsigned long long)tag << 56) | ((unsigned long long)(a0 & 0xFFFF) << 40) | (clock64() & 0xFFFFFFFFFFull);
+    ++n;
+  } else if (it != 3 && it != 4) {
+    n = 0;
   }
 }
-#define RTRACE(it, tag, a0) rtrace(it, tag, a0)
+#define RTRACE(it, tag, a0) rtrace(it, tag, a0, tr_n)
 #else
 #define RTRACE(it, tag, a0)
 #endif
@@ -126,6 +133,17 @@ __device__ __forceinline__ void mma_split3(uint32_t d_tmem, uint32_t a_hi, uint3
   for (int k = 0; k < K / 16; ++k) umma_ts_w(d_tmem, a_lo + 8 * k, b_hi_lo + kstep * k, dhi, idesc, 1);
 #pragma unroll
   for (int k = 0; k < K / 16; ++k) umma_ts_w(d_tmem, a_hi + 8 * k, b_lo_lo + kstep * k, dhi, idesc, 1);
+}
+
+// one K = 16 step (index k) of the three-pass split product; `fresh`: first MMA of the layer (overwrites D)
+template <int N>
+__device__ __forceinline__ void mma_k3(uint32_t d_tmem, uint32_t a_hi, uint32_t a_lo, uint32_t b_hi_lo, uint32_t b_lo_lo,
+                                       uint32_t dhi, int k, bool fresh) {
+  constexpr uint32_t idesc = umma_idesc_f16(kRows, N);
+  constexpr uint32_t kstep = (2u * N * 16u) >> 4;
+  umma_ts_w(d_tmem, a_hi + 8 * k, b_hi_lo + kstep * k, dhi, idesc, fresh ? 0u : 1u);
+  umma_ts_w(d_tmem, a_lo + 8 * k, b_hi_lo + kstep * k, dhi, idesc, 1);
+  umma_ts_w(d_tmem, a_hi + 8 * k, b_lo_lo + kstep * k, dhi, idesc, 1);
 }
 
 // s1.14 fixed point through the float adder: x + 1.5*2^9 has ulp 2^-14 for |x| <= 1, so the low 16 bits of its pattern
@@ -180,7 +198,7 @@ __global__ void __launch_bounds__(640, 1) ray_siren_tc_kernel(const KArgs a) {
   if (threadIdx.x == 0) {
     mbar_init(&s.w_full, 1);
     for (int i = 0; i < 2; ++i) {
-      mbar_init(&s.a_ready[i], 8);
+      for (int j = 0; j < 3; ++j) mbar_init(&s.a_ready[i][j], 8);
       mbar_init(&s.d_ready[i], 1);
     }
     fence_mbar_init();
@@ -214,34 +232,63 @@ __global__ void __launch_bounds__(640, 1) ray_siren_tc_kernel(const KArgs a) {
       const uint32_t w2h = umma_desc_lo(wb + kOffW2h, kNc * 16), w2l = umma_desc_lo(wb + kOffW2l, kNc * 16);
       const uint32_t w3h = umma_desc_lo(wb + kOffW3h, 32 * 16), w3l = umma_desc_lo(wb + kOffW3l, 32 * 16);
       const uint32_t w0h = umma_desc_lo(smem_u32(s.slot[sl].w0), 128 * 16);
-      uint32_t par = 0;
+      uint32_t par = 0;     // bit j = parity of a_ready[sl][j]
+      int tr_n = 0;
+      (void)tr_n;
       const int total = iters * mma_phases;
+      // A layer's MMAs are issued in STAGES, each behind one phase of a_ready: the epilogue that produces the layer's A operand
+      // signals as soon as (a) it has drained the previous accumulator out of D and (b) the K-chunks of the stage are in TMEM, so
+      // the tensor pipe works underneath the rest of that epilogue and only the last stage's MMAs stay exposed:
+      //   K = 128 layers: stage 0 = k-steps {0,4,1,5} (chunks 0,1 of both column halves; D drained), stage 1 = {2,6}, stage 2 = {3,7}
+      //   K = 64  layer : stage 0 = {0,2}, stage 1 = {1,3};   K = 16 layer: one stage.
+      auto next_stage = [&](int j) {
+        mbar_wait(&s.a_ready[sl][j], (par >> j) & 1u);
+        par ^= 1u << j;
+        tc_fence_after();
+      };
 #pragma unroll 1
       for (int done = 0; done < total; ++done) {
-        mbar_wait(&s.a_ready[sl], par);
-        par ^= 1;
-        tc_fence_after();
         const int layer = FOLD ? done % 3 : (done & 3);
+        uint32_t a_hi = tmem + (uint32_t)(sl * 256), a_lo = a_hi + 64;
+        const uint32_t d = a_hi + 128;
+        uint32_t bh = layer == 0 ? w0h : (layer == 1 ? w1h : (layer == 2 ? w2h : w3h));
+        uint32_t bl = layer == 0 ? w0h + (kW0Bytes >> 4) : (layer == 1 ? w1l : (layer == 2 ? w2l : w3l));
+        // opaque per-iteration copies: keeps the compiler from materialising ~60 loop-invariant descriptor words
+        // outside the loop (they would spill and cost an LDL per MMA)
+        asm volatile("" : "+r"(bh), "+r"(bl), "+r"(a_hi), "+r"(a_lo));
+        next_stage(0);
         if (lane == 0) RTRACE(done / mma_phases, 1, (uint32_t)(sl << 15 | ((done / mma_phases) & 1) << 8 | (done % mma_phases)));
-        if (elect_one()) {
-          uint32_t a_hi = tmem + (uint32_t)(sl * 256), a_lo = a_hi + 64;
-          const uint32_t d = a_hi + 128;
-          uint32_t bh = layer == 0 ? w0h : (layer == 1 ? w1h : (layer == 2 ? w2h : w3h));
-          uint32_t bl = layer == 0 ? w0h + (kW0Bytes >> 4) : (layer == 1 ? w1l : (layer == 2 ? w2l : w3l));
-          // opaque per-iteration copies: keeps the compiler from materialising ~60 loop-invariant descriptor words
-          // outside the loop (they would spill and cost an LDL per MMA)
-          asm volatile("" : "+r"(bh), "+r"(bl), "+r"(a_hi), "+r"(a_lo));
-          if (layer == 0) mma_split3<128, 16>(d, a_hi, a_lo, bh, bl, dhi);
-          else if (layer == 1) mma_split3<128, 128>(d, a_hi, a_lo, bh, bl, dhi);
-          else if (layer == 2) mma_split3<kNc, 128>(d, a_hi, a_lo, bh, bl, dhi);
-          else if (!FOLD) mma_split3<32, 64>(d, a_hi, a_lo, bh, bl, dhi);
-          tc_commit(&s.d_ready[sl]);
+        if (layer == 0) {
+          if (elect_one()) {
+            mma_split3<128, 16>(d, a_hi, a_lo, bh, bl, dhi);
+            tc_commit(&s.d_ready[sl]);
+          }
+        } else if (layer == 1 || layer == 2) {
+          const bool n128 = layer == 1;
+          auto step = [&](int k, bool fresh) {
+            if (n128) mma_k3<128>(d, a_hi, a_lo, bh, bl, dhi, k, fresh);
+            else mma_k3<kNc>(d, a_hi, a_lo, bh, bl, dhi, k, fresh);
+          };
+          if (elect_one()) { step(0, true); step(4, false); step(1, false); step(5, false); }
+          __syncwarp();
+          next_stage(1);
+          if (elect_one()) { step(2, false); step(6, false); }
+          __syncwarp();
+          next_stage(2);
+          if (elect_one()) {
+            step(3, false); step(7, false);
+            tc_commit(&s.d_ready[sl]);
+          }
+        } else if (!FOLD) {
+          if (elect_one()) { mma_k3<32>(d, a_hi, a_lo, bh, bl, dhi, 0, true); mma_k3<32>(d, a_hi, a_lo, bh, bl, dhi, 2, false); }
+          __syncwarp();
+          next_stage(1);
+          if (elect_one()) {
+            mma_k3<32>(d, a_hi, a_lo, bh, bl, dhi, 1, false); mma_k3<32>(d, a_hi, a_lo, bh, bl, dhi, 3, false);
+            tc_commit(&s.d_ready[sl]);
+          }
         }
         __syncwarp();
-#ifdef C3D_TRACE      // when does a SPINNING observer see the commit?  (worker D-ready stamp minus this = wake-up latency of the suspended wait)
-        while (!__all_sync(0xffffffffu, mbar_test(&s.d_ready[sl], par ^ 1))) {}
-        if (lane == 0) RTRACE(done / mma_phases, 14, (uint32_t)(sl << 15 | ((done / mma_phases) & 1) << 8 | (done % mma_phases)));
-#endif
       }
     }
   } else {
@@ -260,18 +307,19 @@ __global__ void __launch_bounds__(640, 1) ray_siren_tc_kernel(const KArgs a) {
     const int bar_id = 1 + sl;
     auto slot_sync = [&]() { named_bar_sync_n<256>(bar_id); };
     uint32_t dpar = 0;
-    auto signal_a = [&]() {
+    auto signal_a = [&](int stage = 0) {
       tc_wait_st();
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&s.a_ready[sl]);
+      if (lane == 0) mbar_arrive(&s.a_ready[sl][stage]);
     };
     auto wait_d = [&]() {
       mbar_wait(&s.d_ready[sl], dpar);
       dpar ^= 1;
       tc_fence_after();
     };
-    int tr_it = 0, tr_ph = 0;
+    int tr_it = 0, tr_ph = 0, tr_n = 0;
+    (void)tr_n;
     // trace word: slot << 15 | team warp << 12 | iteration parity << 8 | phase counter (lane 0 of every worker warp stamps)
     auto stamp = [&](uint32_t tag) { if (lane == 0) RTRACE(tr_it, tag, (uint32_t)(sl << 15 | tw << 12 | (tr_it & 1) << 8 | tr_ph)); ++tr_ph; };
     const int g_row = row / S, s_row = row - g_row * S;   // ray within the group, sample index
@@ -289,9 +337,11 @@ __global__ void __launch_bounds__(640, 1) ray_siren_tc_kernel(const KArgs a) {
     int cur_img = -1;
     if (FOLD && stid < 128) sm.abuf[stid] = __ldg(a.w_sigma + stid);   // visible after the first image-constants barrier
     if (FOLD) mbar_wait(&s.w_full, 0);   // the workers read Wl^T from the bulk-loaded blob themselves: observe its barrier
-#ifdef C3D_RAY_STAGGER_NS   // start slot 1 half a pass late so its MMA phases fall into slot 0's worker phases
-    if (sl == 1) __nanosleep(C3D_RAY_STAGGER_NS);
-#endif
+    // A/B knob (C3D_RAY_STAGGER_NS): start slot 1 late so that its MMA phases fall into slot 0's epilogue phases
+    if (sl == 1 && a.stagger_ns > 0) {
+      const unsigned long long t0 = c3d_globaltimer();
+      while (c3d_globaltimer() - t0 < (unsigned long long)a.stagger_ns) __nanosleep(200);
+    }
 
     for (int it = 0; it < iters; ++it) {
       tr_it = it; tr_ph = 0;
@@ -320,6 +370,10 @@ __global__ void __launch_bounds__(640, 1) ray_siren_tc_kernel(const KArgs a) {
         gray = a.io.ray_idx ? a.io.ray_idx[nloc] : p.ray_offset + nloc;
         fr = make_ray_frame(M, gray, p.img_size, p.z_cam);
       }
+      // the resampling step's uniform (block-wide form): issued now, consumed a whole MLP pass later -- an HBM-latency load
+      // (~800 clk) that used to sit on the group's critical path between the two passes
+      float uk_pre = 0.f;
+      if (!WARP && hier && half == 0 && pt_ok) uk_pre = a.io.pdf_u[ro_row * S + s_row];
 
       for (int pass = 0; pass < (hier ? 2 : 1); ++pass) {
         // ---------------- L0: point position -> A operand [x, y, z, 1] (K = 16) for the layer-0 MMA
@@ -360,12 +414,14 @@ __global__ void __launch_bounds__(640, 1) ray_siren_tc_kernel(const KArgs a) {
           e0(accB, 16);
           tc_wait_ld();
           tmem_ld16(dcol + (uint32_t)(half * 64 + 48), accB);
+          tc_wait_ld();      // this thread's 64 accumulator columns are out of D
+          signal_a(0);       // stage 0: K-chunks 0, 1 of both halves written, D drained -> layer 1's MMAs start underneath
           e0(accA, 32);
-          tc_wait_ld();
+          signal_a(1);       // stage 1: chunk 2
           e0(accB, 48);
         }
         stamp(4);
-        signal_a();
+        signal_a(2);         // stage 2: chunk 3
         // ---------------- E1: D(128) -> FiLM+sin -> A (h1); TMEM loads double-buffered
         wait_d();
         stamp(5);
@@ -391,15 +447,17 @@ __global__ void __launch_bounds__(640, 1) ray_siren_tc_kernel(const KArgs a) {
           e1(accB, 16);
           tc_wait_ld();
           tmem_ld16(dcol + (uint32_t)(half * 64 + 48), accB);
-          e1(accA, 32);
           tc_wait_ld();
+          signal_a(0);       // stage 0 of the colour / sigma MMA (see the issuer)
+          e1(accA, 32);
+          signal_a(1);       // stage 1
           e1(accB, 48);
           // partial sums of the two column halves, per pass; combined where sigma is used, i.e. after the slot-wide barrier
           // that ends the pass (fbuf / w_all are free in the warp-math forms)
           if (FOLD) (pass == 0 ? sm.fbuf : sm.w_all)[half * kRows + row] = psig;
         }
         stamp(6);
-        signal_a();
+        signal_a(2);
         // ---------------- E2: D(80): cols 0..63 -> FiLM+sin -> A (h2, K=64); col 64 -> sigma
         wait_d();
         stamp(7);
@@ -446,11 +504,12 @@ __global__ void __launch_bounds__(640, 1) ray_siren_tc_kernel(const KArgs a) {
             (pass == 0 ? sm.sig_c : sm.sig_f)[row] = sigma;
           }
           e2(accA, 0);
+          signal_a(0);       // stage 0 of the K = 64 colour-linear MMA: k-steps {0, 2}
           e2(accB, 16);
         }
         if (!FOLD) {
         stamp(8);
-        signal_a();
+        signal_a(1);         // stage 1: k-steps {1, 3}
         // ---------------- E3: D(32) -> + bias -> features to shared memory
         wait_d();
         stamp(9);
@@ -554,7 +613,7 @@ __global__ void __launch_bounds__(640, 1) ray_siren_tc_kernel(const KArgs a) {
           slot_sync();
           if (half == 0 && pt_ok) {   // D: inverse CDF for u_k, k = s_row
             const int ns = S - 2;
-            const float uk = a.io.pdf_u[ro_row * S + s_row];
+            const float uk = uk_pre;
             int i = 0;
             while (i <= ns && sm.cdf[r0 + i] < uk) ++i;         // searchsorted(cdf, u, right=False)
             const int below = max(i - 1, 0), above = min(i, ns);
@@ -797,15 +856,15 @@ size_t c3d_ray_siren_tc_workspace_bytes(const C3dRayParams* p) { return ray_ws_l
 
 #ifdef C3D_TRACE
 extern "C" int c3d_debug_ray_trace(unsigned long long* out, int cap) {
-  unsigned int n = 0;
+  static unsigned long long host[2 * 20 * 64];
   cudaDeviceSynchronize();
-  cudaMemcpyFromSymbol(&n, c3d::rtc::g_rtrace_n, sizeof(n));
-  if ((int)n > cap) n = cap;
-  if (n > 4096) n = 4096;
-  cudaMemcpyFromSymbol(out, c3d::rtc::g_rtrace, n * sizeof(unsigned long long));
-  unsigned int zero = 0;
-  cudaMemcpyToSymbol(c3d::rtc::g_rtrace_n, &zero, sizeof(zero));
-  return (int)n;
+  cudaMemcpyFromSymbol(host, c3d::rtc::g_rtrace, sizeof(host));
+  int n = 0;
+  for (int i = 0; i < 2 * 20 * 64 && n < cap; ++i)
+    if (host[i]) out[n++] = host[i];
+  memset(host, 0, sizeof(host));
+  cudaMemcpyToSymbol(c3d::rtc::g_rtrace, host, sizeof(host));
+  return n;
 }
 #endif
 
@@ -844,6 +903,7 @@ int c3d_ray_siren_fwd_tc(const C3dRayParams* p, const C3dSirenWeights* w, const 
   ka.total_groups = p->batch * ka.groups_per_img;
   ka.b_sigma = w->b_sigma;
   ka.w_sigma = w->w_sigma;
+  ka.stagger_ns = c3d_options().ray_stagger_ns;
   const size_t smem = sizeof(Smem) + 1024;
   static std::atomic<unsigned long long> attr_set{0};     // per device, once
   if (!(attr_set.load() >> (dev & 63) & 1ull)) {

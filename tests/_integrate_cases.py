@@ -32,8 +32,17 @@ def reference(case, rs, z, noise, d_fea, dtype=torch.float64):
     _, T, Cn, clamp, lb, wb, _ = case
     r = rs.detach().to(dtype).requires_grad_()
     fea, _, w = O.integrate(r, z.to(dtype), None if noise is None else noise.to(dtype), clamp, lb, wb, dim_rgb=Cn)
-    (dr,) = torch.autograd.grad(fea, r, d_fea.to(dtype))
+    (dr,) = torch.autograd.grad(fea, r, d_fea.to(dtype), retain_graph=True)
     return fea.detach(), w.detach(), dr
+
+
+def reference_depth_grad(case, rs, z, noise, dtype=torch.float64):
+    """gradient of a depth loss sum(weights * z) -- it reaches rgb_sigma only through the returned weights"""
+    _, T, Cn, clamp, lb, wb, _ = case
+    r = rs.detach().to(dtype).requires_grad_()
+    _, _, w = O.integrate(r, z.to(dtype), None if noise is None else noise.to(dtype), clamp, lb, wb, dim_rgb=Cn)
+    (dr,) = torch.autograd.grad((w * z.to(dtype)).sum(), r)
+    return dr
 
 
 def check(case, pkg, rs, z, noise, d_fea):
@@ -41,8 +50,14 @@ def check(case, pkg, rs, z, noise, d_fea):
     r = rs.clone().requires_grad_()
     assert pkg.ops.integrate_supported(r, z, noise)
     fea, w = pkg.ops.integrate(r, z, noise, clamp, lb, wb)
-    assert not w.requires_grad and fea.shape == rs.shape[:-2] + (Cn,) and w.shape == z.shape
-    (dr,) = torch.autograd.grad(fea, r, d_fea)
+    assert fea.shape == rs.shape[:-2] + (Cn,) and w.shape == z.shape
+    (dr,) = torch.autograd.grad(fea, r, d_fea, retain_graph=True)
+    # a loss on the returned weights (depth = sum w z, as piGAN_lib's depth maps / inverse rendering would use): the reference's
+    # fancy_integration propagates it; here a torch-op recompute inside IntegrateFunction.backward
+    (dw,) = torch.autograd.grad((w * z).sum(), r)
+    dw64 = reference_depth_grad(case, rs.cpu(), z.cpu(), None if noise is None else noise.cpu())
+    assert (dw.cpu().double()[..., :Cn]).abs().max().item() == 0.0
+    assert (dw.cpu().double()[..., Cn] - dw64[..., Cn]).abs().max().item() < 2e-4 * dw64[..., Cn].abs().max().item() + 1e-6
     f64, w64, d64 = reference(case, rs.cpu(), z.cpu(), None if noise is None else noise.cpu(), d_fea.cpu())
     fea, w, dr = fea.detach().cpu().double(), w.cpu().double(), dr.cpu().double()
     # weights are in [0, 1]; a product of up to 32 factors 1 - alpha_j, each carrying expf's rounding (<= 2 ulp on the GPU)
