@@ -76,6 +76,13 @@ struct Smem {
                             // stages on one barrier would be indistinguishable when a fast warp runs a stage ahead of a slow one)
   uint64_t d_ready[2];
   uint32_t tmem_base;
+  // "epilogue turn": at most ONE slot runs a sine epilogue (E0 / E1 / E2) at a time.  Two symmetric slots fall into lock step
+  // (profiles/r02c, r02d): both epilogues then share MUFU / issue slots while the tensor pipe idles, and both MMA batches
+  // queue on the tensor pipe while MUFU idles.  Serialising the epilogues costs no epilogue throughput (they are MUFU /
+  // issue bound) and forces the other slot's MMAs underneath.  e_owner: -1 free, else the slot; e_left[sl]: warps of the
+  // owner still inside the epilogue (the last one releases).
+  int e_owner;
+  int e_left[2];
 };
 
 struct KArgs {
@@ -89,6 +96,7 @@ struct KArgs {
   int groups_per_img, total_groups;
   const float* w_sigma;       // (128) final_layer weight, fp32 (MATH = 2 only: sigma head in the E1 epilogue)
   int stagger_ns;             // A/B knob: slot 1 starts this much later than slot 0
+  int e_turn;                 // serialise the sine epilogues of the two slots (Smem::e_owner)
 };
 
 __device__ __forceinline__ float fast_sin(float x) { return __sinf(x); }
@@ -197,6 +205,8 @@ __global__ void __launch_bounds__(640, 1) ray_siren_tc_kernel(const KArgs a) {
 
   if (threadIdx.x == 0) {
     mbar_init(&s.w_full, 1);
+    s.e_owner = -1;
+    s.e_left[0] = s.e_left[1] = 0;
     for (int i = 0; i < 2; ++i) {
       for (int j = 0; j < 3; ++j) mbar_init(&s.a_ready[i][j], 8);
       mbar_init(&s.d_ready[i], 1);
@@ -318,6 +328,34 @@ __global__ void __launch_bounds__(640, 1) ray_siren_tc_kernel(const KArgs a) {
       dpar ^= 1;
       tc_fence_after();
     };
+    // epilogue turn (see Smem::e_owner): every warp of the team enters once the team owns the turn (the first warp to find it
+    // free takes it for all eight); the eighth warp to leave releases it.  All eight warps of a team pass through every
+    // epilogue, and none can reach the NEXT epilogue before the team's eighth has left this one (the next d_ready needs all
+    // eight a_ready arrivals), so the counter never mixes two epilogues.
+    auto e_enter = [&]() {
+      if (a.e_turn) {
+        if (lane == 0) {
+          volatile int* own = &s.e_owner;
+          for (;;) {
+            const int o = *own;
+            if (o == sl) break;
+            if (o == -1 && atomicCAS(&s.e_owner, -1, sl) == -1) { atomicExch(&s.e_left[sl], 8); break; }
+            __nanosleep(20);
+          }
+        }
+        __syncwarp();
+      }
+    };
+    auto e_leave = [&]() {
+      if (a.e_turn) {
+        __syncwarp();
+        if (lane == 0) {
+          volatile int* left = &s.e_left[sl];
+          while (*left == 0) __nanosleep(20);          // the taker publishes the count right after the owner word
+          if (atomicAdd(&s.e_left[sl], -1) == 1) atomicExch(&s.e_owner, -1);
+        }
+      }
+    };
     int tr_it = 0, tr_ph = 0, tr_n = 0;
     (void)tr_n;
     // trace word: slot << 15 | team warp << 12 | iteration parity << 8 | phase counter (lane 0 of every worker warp stamps)
@@ -396,6 +434,7 @@ __global__ void __launch_bounds__(640, 1) ray_siren_tc_kernel(const KArgs a) {
         signal_a();
         // ---------------- E0: D(128) = g0*(W0 p*s + b0) + beta0  ->  sin  ->  A (h0)
         wait_d();
+        e_enter();
         stamp(3);
         {
           uint32_t accA[16], accB[16];
@@ -422,8 +461,10 @@ __global__ void __launch_bounds__(640, 1) ray_siren_tc_kernel(const KArgs a) {
         }
         stamp(4);
         signal_a(2);         // stage 2: chunk 3
+        e_leave();
         // ---------------- E1: D(128) -> FiLM+sin -> A (h1); TMEM loads double-buffered
         wait_d();
+        e_enter();
         stamp(5);
         {
           uint32_t accA[16], accB[16];
@@ -458,8 +499,10 @@ __global__ void __launch_bounds__(640, 1) ray_siren_tc_kernel(const KArgs a) {
         }
         stamp(6);
         signal_a(2);
+        e_leave();
         // ---------------- E2: D(80): cols 0..63 -> FiLM+sin -> A (h2, K=64); col 64 -> sigma
         wait_d();
+        e_enter();
         stamp(7);
         float sigma = 0.f;
         if (FOLD) {
@@ -481,6 +524,7 @@ __global__ void __launch_bounds__(640, 1) ray_siren_tc_kernel(const KArgs a) {
           };
           e2(accA, 0);
           e2(accB, 16);
+          e_leave();
           stamp(8);
           stamp(9);
         } else {
@@ -510,6 +554,7 @@ __global__ void __launch_bounds__(640, 1) ray_siren_tc_kernel(const KArgs a) {
         if (!FOLD) {
         stamp(8);
         signal_a(1);         // stage 1: k-steps {1, 3}
+        e_leave();
         // ---------------- E3: D(32) -> + bias -> features to shared memory
         wait_d();
         stamp(9);
@@ -904,6 +949,7 @@ int c3d_ray_siren_fwd_tc(const C3dRayParams* p, const C3dSirenWeights* w, const 
   ka.b_sigma = w->b_sigma;
   ka.w_sigma = w->w_sigma;
   ka.stagger_ns = c3d_options().ray_stagger_ns;
+  ka.e_turn = c3d_options().ray_e_turn;
   const size_t smem = sizeof(Smem) + 1024;
   static std::atomic<unsigned long long> attr_set{0};     // per device, once
   if (!(attr_set.load() >> (dev & 63) & 1ull)) {

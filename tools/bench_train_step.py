@@ -188,6 +188,25 @@ def main():
     ms = torch.tensor([e0.elapsed_time(e1) / args.steps], device=dev)
     if ddp:
         torch.distributed.all_reduce(ms, op=torch.distributed.ReduceOp.MAX)
+    nccl = None
+    if args.profile:          # every rank steps (DDP collectives); rank 0 records
+        from torch.profiler import profile, ProfilerActivity
+        import contextlib
+        ctx = profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA]) if rank == 0 else contextlib.nullcontext()
+        with ctx as prof:
+            for it in range(2):
+                step(args.warmup + args.steps + it)
+            torch.cuda.synchronize()
+        if rank == 0:
+            ka = prof.key_averages()
+            with open(args.profile, "w") as f:
+                f.write(ka.table(sort_by="cuda_time_total", row_limit=60, max_name_column_width=90))
+            dt = lambda e: getattr(e, "self_device_time_total", getattr(e, "self_cuda_time_total", 0.0))     # noqa: E731
+            nccl = dict(nccl_kernel_ms_per_step=sum(dt(e) for e in ka if "nccl" in e.key.lower()) / 2e3,
+                        all_gpu_kernel_ms_per_step=sum(dt(e) for e in ka) / 2e3,
+                        note="sum of kernel durations on rank 0 over 2 profiled steps / 2; the all-reduce kernels run on DDP's "
+                             "communication stream concurrently with backward, so their sum is exposed only where it exceeds the "
+                             "step's compute (compare ms_per_step across n_gpus)")
     if rank == 0:
         print(json.dumps(dict(
             metric="train step (D step + G step) images/s", value=B * world / ms.item() * 1e3, unit="images/s", ms_per_step=ms.item(),
@@ -197,15 +216,7 @@ def main():
                         cudnn_tf32=bool(torch.backends.cudnn.allow_tf32), cips_backend=args.cips_backend, film_backend=args.film_backend, integrate_backend=args.integrate_backend,
                         note="G forward under no_grad runs the fused kernels; the G step's autograd graph runs as torch CUDA ops "
                              "(backward kernels: DESIGN.md section 9); D convs are cuDNN as in the reference; D's bias_act / blur are native"),
-            d_loss=float(dl), g_loss=float(gl), finite=bool(math.isfinite(float(dl)) and math.isfinite(float(gl))))))
-    if args.profile and rank == 0:
-        from torch.profiler import profile, ProfilerActivity
-        with profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA]) as prof:
-            for it in range(2):
-                step(args.warmup + args.steps + it)
-            torch.cuda.synchronize()
-        with open(args.profile, "w") as f:
-            f.write(prof.key_averages().table(sort_by="cuda_time_total", row_limit=60, max_name_column_width=90))
+            d_loss=float(dl), g_loss=float(gl), comm=nccl, finite=bool(math.isfinite(float(dl)) and math.isfinite(float(gl))))))
     if ddp:
         torch.distributed.destroy_process_group()
 

@@ -914,6 +914,11 @@ template <class T> inline T __shfl_up_sync(unsigned mask, T v, int d, int width 
   return c3d_emu_shfl_from(mask, v, (lane & (width - 1)) >= d ? lane - d : lane);
 }
 inline void __nanosleep(unsigned) { emu::yield(); }
+// atomics: fibers are cooperative (switches only at preempt points), so plain read-modify-writes are atomic; a preempt point
+// after each one lets the schedules explore the interleavings around it
+inline int atomicCAS(int* p, int cmp, int val) { const int old = *p; if (old == cmp) *p = val; emu::preempt_point(); return old; }
+inline int atomicExch(int* p, int val) { const int old = *p; *p = val; emu::preempt_point(); return old; }
+inline int atomicAdd(int* p, int v) { const int old = *p; *p = old + v; emu::preempt_point(); return old; }
 inline void __trap() { emu::fail("__trap()"); }
 template <class T> inline T __ldg(const T* p) { return *p; }
 template <class T> inline T __ldcs(const T* p) { return *p; }
