@@ -381,8 +381,22 @@ __global__ void __launch_bounds__(640, 1) ray_siren_tc_kernel(const KArgs a) {
       while (c3d_globaltimer() - t0 < (unsigned long long)a.stagger_ns) __nanosleep(200);
     }
 
+    // the coarse jitter of a group (one global load per point) is fetched one group ahead: issued at the start of the previous
+    // group's fine pass, it used to cost ~1 k clk of exposed latency at the head of every group (r02d trace: A0 skew 1000)
+    auto jitter_of = [&](int it_) -> float {
+      const int grp_ = (it_ * (int)gridDim.x + (int)blockIdx.x) * 2 + sl;
+      if (it_ >= iters || grp_ >= a.total_groups || !row_in_group) return 0.f;
+      const int img_ = grp_ / a.groups_per_img, ray0_ = (grp_ % a.groups_per_img) * G;
+      if (g_row >= min(G, p.n_rays - ray0_)) return 0.f;
+      const int nloc_ = ray0_ + g_row;
+      const int gray_ = a.io.ray_idx ? a.io.ray_idx[nloc_] : p.ray_offset + nloc_;
+      return a.io.jitter_u[((size_t)img_ * p.img_size * p.img_size + gray_) * S + s_row];
+    };
+    float u_next = jitter_of(0);
+
     for (int it = 0; it < iters; ++it) {
       tr_it = it; tr_ph = 0;
+      const float u_cur = u_next;
       const int grp = (it * (int)gridDim.x + (int)blockIdx.x) * 2 + sl;
       const bool grp_ok = grp < a.total_groups;
       const int img = grp_ok ? grp / a.groups_per_img : 0;
@@ -418,7 +432,7 @@ __global__ void __launch_bounds__(640, 1) ray_siren_tc_kernel(const KArgs a) {
         float px = 0.f, py = 0.f, pz = 0.f;
         if (pt_ok) {
           if (pass == 0) {
-            const float u = a.io.jitter_u[((size_t)img * p.img_size * p.img_size + gray) * S + s_row];
+            const float u = u_cur;
             float z;
             coarse_sample(fr, M, p.ray_start, p.ray_end, S, s_row, u, z, px, py, pz);
             if (half == 0) sm.z_c[row] = z;
@@ -426,6 +440,7 @@ __global__ void __launch_bounds__(640, 1) ray_siren_tc_kernel(const KArgs a) {
             fine_sample(fr, sm.z_f[row], px, py, pz);
           }
         }
+        if (pass == (hier ? 1 : 0)) u_next = jitter_of(it + 1);
         if (half == 0) {
           float v[16] = {px, py, pz, 1.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
           store_a16(a_hi, a_lo, v);
@@ -642,15 +657,18 @@ __global__ void __launch_bounds__(640, 1) ray_siren_tc_kernel(const KArgs a) {
           slot_sync();
           if (half == 0 && pt_ok) {   // B: T_i = prod_{j<i} f_j (sequential order), w_i = alpha_i * T_i
             float T = 1.f;
+#pragma unroll 4
             for (int j = 0; j < s_row; ++j) T = __fmul_rn(T, sm.fbuf[r0 + j]);
             sm.wc[row] = __fmul_rn(alpha, T);
           }
           slot_sync();
           if (half == 0 && pt_ok && s_row <= S - 2) {   // C: cdf_j, j = 0..S-2, over weights (w+1e-5)[1:-1]+1e-5
             float sum = 0.f;
+#pragma unroll 4
             for (int j = 0; j < S - 2; ++j) sum += __fadd_rn(__fadd_rn(sm.wc[r0 + j + 1], 1e-5f), 1e-5f);
             float c = 0.f;
             const float inv = __fdividef(1.f, sum);      // pdf_j = wt_j / sum (1-2 ulp; cdf only feeds a 2e-4-conditioned inverse)
+#pragma unroll 4
             for (int j = 0; j < s_row; ++j)
               c = __fadd_rn(c, __fmul_rn(__fadd_rn(__fadd_rn(sm.wc[r0 + j + 1], 1e-5f), 1e-5f), inv));
             sm.cdf[r0 + s_row] = c;
@@ -768,6 +786,7 @@ __global__ void __launch_bounds__(640, 1) ray_siren_tc_kernel(const KArgs a) {
         auto key_of = [&](int e) { return hier ? (e < S ? sm.z_f[rc0 + e] : sm.z_c[rc0 + e - S]) : sm.z_c[rc0 + e]; };
         const float k = key_of(e_el);
         int rank = 0;
+#pragma unroll 4
         for (int e = 0; e < nS; ++e) {
           const float ke = key_of(e);
           rank += (ke < k || (ke == k && e < e_el)) ? 1 : 0;
@@ -790,19 +809,23 @@ __global__ void __launch_bounds__(640, 1) ray_siren_tc_kernel(const KArgs a) {
       slot_sync();
       if (el_ok) {       // transmittance in the reference's cumprod order, weight
         float T = 1.f;
+#pragma unroll 4
         for (int j = 0; j < e_el; ++j) T = __fmul_rn(T, sm.fbuf[base + j]);
         sm.w_all[base + e_el] = __fmul_rn(alpha_el, T);
       }
       slot_sync();
       stamp(12);
       // ---------------- composite: pixels_fea[ray][c] = sum_i w_i * feature_i[c]  (pigan_utils.py:255-266)
-      if (el_ok && e_el == 0) {      // per ray: weight sum in the reference's order, last_back folded into the last weight
-        float wsum = 0.f;
-        for (int i = 0; i < nS; ++i) wsum += sm.w_all[base + i];
-        sm.wsum[g_el] = wsum;
-        if (p.last_back) sm.w_all[base + nS - 1] += 1.f - wsum;
+      if (p.last_back || p.white_back) {     // (slot-uniform) the weight sum is only needed for the two background modes
+        if (el_ok && e_el == 0) {    // per ray: weight sum in the reference's order, last_back folded into the last weight
+          float wsum = 0.f;
+#pragma unroll 4
+          for (int i = 0; i < nS; ++i) wsum += sm.w_all[base + i];
+          sm.wsum[g_el] = wsum;
+          if (p.last_back) sm.w_all[base + nS - 1] += 1.f - wsum;
+        }
+        slot_sync();
       }
-      slot_sync();
       {
         const int c = stid & 31;
         const float* featf = &sm.feat[0][0][0];

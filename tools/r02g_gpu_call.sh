@@ -1,0 +1,15 @@
+#!/bin/bash
+# Round-2 GPU call G: renderer variants on ONE box (box-to-box variance is ~5 %): round-1 kernel vs staged + per-slot issuers
+# (+ epilogue turn, + stagger), after the jitter prefetch / loop unrolling.
+set -u
+mkdir -p gpurun_out
+O=gpurun_out
+python __graft_entry__.py > $O/r02g_build.log 2>&1
+run() { echo "$1: $(env $2 timeout 300 python tools/time_forward.py 16 2>&1 | tail -1 | cut -c1-200)"; }
+for rep in 1 2; do
+  run "r01 renderer (rep $rep)" "C3D_LIB_PATH=$PWD/cips-3d_b200/libcips3d_b200_r01ray.so"
+  run "staged, e_turn 0 (rep $rep)" "C3D_RAY_E_TURN=0"
+  run "staged, e_turn 1 (rep $rep)" "C3D_RAY_E_TURN=1"
+  run "staged, e_turn 0, stagger 10us (rep $rep)" "C3D_RAY_E_TURN=0 C3D_RAY_STAGGER_NS=10000"
+done 2>&1 | tee $O/r02g_ray_variants.txt
+timeout 600 python -m pytest tests/test_gpu_parity.py tests/test_baseline_sizes_gpu.py -m gpu -q -x -p no:cacheprovider > $O/r02g_pytest_gpu.log 2>&1; echo "gpu tests: exit $?"; tail -2 $O/r02g_pytest_gpu.log
