@@ -6,6 +6,8 @@ device is not sm_100, every op raises.
 import ctypes as C
 import os
 
+import torch
+
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("C3D_LIB_PATH", os.path.join(_HERE, "libcips3d_b200.so"))   # override: A/B kernel experiments
 
@@ -15,7 +17,7 @@ CIPS_MAX_LAYERS = 18
 EXPORTS = ("c3d_reload_options", "c3d_debug_cips_max_clusters", "c3d_version", "c3d_last_error", "c3d_device_supported", "c3d_launch_count",
            "c3d_ray_siren_workspace_bytes",
            "c3d_ray_siren_fwd", "c3d_cips_workspace_bytes", "c3d_cips_fwd", "c3d_bias_act",
-           "c3d_upfirdn2d", "c3d_selftest_umma", "c3d_selftest_umma_pair", "c3d_debug_cips_tile_order", "c3d_debug_ray_math_mode",
+           "c3d_upfirdn2d", "c3d_blur_nhwc", "c3d_selftest_umma", "c3d_selftest_umma_pair", "c3d_debug_cips_tile_order", "c3d_debug_ray_math_mode",
            "c3d_optim_workspace_bytes", "c3d_grad_norm", "c3d_adam_ema_step", "c3d_ema_update",
            "c3d_pigan_workspace_bytes", "c3d_pigan_render_fwd", "c3d_cips_fwd_train", "c3d_cips_bwd_workspace_bytes", "c3d_cips_bwd", "c3d_cips_style_prep", "c3d_image_to_u8",
            "c3d_film_sin_fwd", "c3d_film_sin_bwd_workspace_bytes", "c3d_film_sin_bwd",
@@ -125,6 +127,7 @@ def bind(lib):
     lib.c3d_bias_act.argtypes = [_fp, _fp, _fp, _fp, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
                                  C.c_float, C.c_float, _fp]
     lib.c3d_upfirdn2d.argtypes = [_fp, _fp, _fp] + [C.c_int32] * 13 + [_fp]
+    lib.c3d_blur_nhwc.argtypes = [_fp, _fp, _fp] + [C.c_int32] * 8 + [_fp]
     lib.c3d_selftest_umma.argtypes = [_fp, _fp, _fp, C.c_int32, C.c_int32, C.c_int32, _fp]
     lib.c3d_selftest_umma_pair.argtypes = [_fp, _fp, _fp, C.c_int32, C.c_int32, _fp]
     lib.c3d_cips_style_prep.argtypes = [C.POINTER(StylePrep), C.c_int32, _fp]
@@ -162,8 +165,8 @@ def ptr(t):
         return None
     if not t.is_cuda:
         raise C3dError("cips3d_b200 ops need CUDA tensors (there is no CPU path)")
-    if not t.is_contiguous():
-        raise C3dError("cips3d_b200 ops need contiguous tensors")
+    if not (t.is_contiguous() or (t.dim() == 4 and t.is_contiguous(memory_format=torch.channels_last))):
+        raise C3dError("cips3d_b200 ops need dense tensors (NCHW-contiguous, or channels-last where the op says so)")
     return t.data_ptr()
 
 

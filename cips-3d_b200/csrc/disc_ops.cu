@@ -285,7 +285,7 @@ constexpr int kStreamRows = 32;
 template <bool SEP>
 __device__ __forceinline__ void blur_stream_strip(const float* __restrict__ xp, float* __restrict__ yp, const float (&kf)[4][4],
                                                   const float (&kyv)[4], const bool (&cok)[4], int iy0, int in_h, int in_w,
-                                                  int out_w, int nrow) {
+                                                  int out_w, int nrow, int tap) {
   float acc[4] = {0.f, 0.f, 0.f, 0.f};
   for (int rb = 0; rb < nrow + 3; rb += 4) {          // four input rows per trip: rows rb .. rb + 3 of the strip's footprint
     float v[4][4];
@@ -295,7 +295,7 @@ __device__ __forceinline__ void blur_stream_strip(const float* __restrict__ xp, 
       const bool rok = iy >= 0 && iy < in_h && rb + j < nrow + 3;
       const float* rp = xp + (size_t)(rok ? iy : 0) * in_w;
 #pragma unroll
-      for (int k = 0; k < 4; ++k) v[j][k] = (rok && cok[k]) ? __ldg(rp + k) : 0.f;
+      for (int k = 0; k < 4; ++k) v[j][k] = (rok && cok[k]) ? __ldg(rp + k * tap) : 0.f;
     }
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
@@ -322,9 +322,11 @@ __device__ __forceinline__ void blur_stream_strip(const float* __restrict__ xp, 
   }
 }
 
+// `tap` = distance in elements between horizontally adjacent pixels: 1 for NCHW planes; C for channels-last tensors, where a
+// "plane" is a whole image of in_w = W * C / out_w = OW * C interleaved elements and pad_x0 counts PIXELS (c3d_blur_nhwc).
 __global__ void __launch_bounds__(256) blur_stream_kernel(const float* __restrict__ x, const float* __restrict__ kernel,
                                                           float* __restrict__ y, int in_h, int in_w, int out_h, int out_w,
-                                                          int pad_x0, int pad_y0, int strips_per_plane) {
+                                                          int pad_x0, int pad_y0, int strips_per_plane, int tap) {
   const int ox = blockIdx.y * blockDim.x + threadIdx.x;
   if (ox >= out_w) return;
   const long long plane = blockIdx.x / strips_per_plane;
@@ -343,15 +345,15 @@ __global__ void __launch_bounds__(256) blur_stream_kernel(const float* __restric
 #pragma unroll
       for (int j = 1; j < 4; ++j) sep = sep && fabsf(kyv[i] * kf[0][j] - kf[i][j]) <= 1e-6f * fabsf(kf[i][j]);
   }
-  const int ix0 = ox - pad_x0;
+  const int ix0 = ox - pad_x0 * tap;
   bool cok[4];
 #pragma unroll
-  for (int k = 0; k < 4; ++k) cok[k] = ix0 + k >= 0 && ix0 + k < in_w;
+  for (int k = 0; k < 4; ++k) cok[k] = ix0 + k * tap >= 0 && ix0 + k * tap < in_w;
   const float* xp = x + (size_t)plane * in_h * in_w + ix0;
   float* yp = y + ((size_t)plane * out_h + oy0) * out_w + ox;
   const int iy0 = oy0 - pad_y0;
-  if (sep) blur_stream_strip<true>(xp, yp, kf, kyv, cok, iy0, in_h, in_w, out_w, nrow);     // block-uniform branch
-  else blur_stream_strip<false>(xp, yp, kf, kyv, cok, iy0, in_h, in_w, out_w, nrow);
+  if (sep) blur_stream_strip<true>(xp, yp, kf, kyv, cok, iy0, in_h, in_w, out_w, nrow, tap);     // block-uniform branch
+  else blur_stream_strip<false>(xp, yp, kf, kyv, cok, iy0, in_h, in_w, out_w, nrow, tap);
 }
 
 }  // namespace c3d
@@ -417,7 +419,7 @@ extern "C" int c3d_upfirdn2d(const float* x, const float* kernel, float* y, int3
       const long long np = planes - p0 < max_planes ? planes - p0 : max_planes;
       dim3 grid((unsigned)(np * strips), col_blocks);
       C3D_LAUNCH(blur_stream_kernel, grid, bw * 32, 0, st, x + (size_t)p0 * in_h * in_w, kernel, y + (size_t)p0 * out_h * out_w,
-                 in_h, in_w, out_h, out_w, pad_x0, pad_y0, strips);
+                 in_h, in_w, out_h, out_w, pad_x0, pad_y0, strips, 1);
       C3D_LAUNCH_CHECK();
     }
     return C3D_OK;
@@ -468,5 +470,29 @@ extern "C" int c3d_upfirdn2d(const float* x, const float* kernel, float* y, int3
                                               kh, kw, up_x, up_y, down_x, down_y, pad_x0, pad_y0, tiles_x);
     C3D_LAUNCH_CHECK();
   }
+  return C3D_OK;
+}
+
+// The discriminator's 4 x 4 Blur (up = down = 1) on a channels-last tensor: x is (N, H, W, C) in memory, y (N, OH, OW, C) with
+// OH = H + pad_y0 + pad_y1 - 3, OW = W + pad_x0 + pad_x1 - 3 (pads in pixels, may be negative).  Same register-streaming
+// kernel: an image is one "plane" of W * C interleaved elements whose horizontal taps are C elements apart.  Not part of the
+// reference's native boundary (its upfirdn2d op sees (N*C, H, W, 1) planes): it exists so that the whole discriminator can stay
+// in the layout cuDNN's tensor-core convolutions want (no NCHW <-> NHWC transposes around every conv).
+extern "C" int c3d_blur_nhwc(const float* x, const float* kernel, float* y, int32_t n, int32_t in_h, int32_t in_w,
+                             int32_t channels, int32_t pad_x0, int32_t pad_x1, int32_t pad_y0, int32_t pad_y1, void* stream) {
+  C3D_CHECK_ARG(x && kernel && y, "blur_nhwc: null pointer");
+  C3D_CHECK_ARG(n >= 0 && in_h >= 1 && in_w >= 1 && channels >= 1, "blur_nhwc: bad sizes");
+  const int out_h = in_h + pad_y0 + pad_y1 - 3, out_w = in_w + pad_x0 + pad_x1 - 3;
+  C3D_CHECK_ARG(out_h > 0 && out_w > 0, "blur_nhwc: empty output");
+  C3D_CHECK_ARG((long long)in_w * channels < 2147483647LL && (long long)out_w * channels < 2147483647LL, "blur_nhwc: row too long");
+  if (n == 0) return C3D_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int strips = c3d_div_up(out_h, kStreamRows);
+  const int ew = out_w * channels;                               // elements per output row
+  const int col_blocks = c3d_div_up(ew, 256);
+  C3D_CHECK_ARG(col_blocks <= 65535, "blur_nhwc: row too long for one launch");
+  dim3 grid((unsigned)((long long)n * strips), col_blocks);
+  C3D_LAUNCH(blur_stream_kernel, grid, 256, 0, st, x, kernel, y, in_h, in_w * channels, out_h, ew, pad_x0, pad_y0, strips, channels);
+  C3D_LAUNCH_CHECK();
   return C3D_OK;
 }

@@ -256,13 +256,21 @@ class Discriminator_MultiScale(nn.Module):
         """discriminator.py:545-556"""
         n, c, h, w = out.shape
         g = min(n, self.stddev_group)
-        y = out.view(g, -1, self.stddev_feat, c // self.stddev_feat, h, w)
+        y = out.contiguous().view(g, -1, self.stddev_feat, c // self.stddev_feat, h, w)
         y = torch.sqrt(y.var(0, unbiased=False) + 1e-8).mean([2, 3, 4], keepdims=True).squeeze(2)
         return torch.cat([out, y.repeat(g, 1, h, w)], 1)
+
+    # Internal activation layout.  True: channels-last (N, H, W, C in memory) from the stem to the 4x4 head -- the layout the
+    # tensor-core convolutions use natively, so no NCHW <-> NHWC transposes around them (15 % of a config-5 train step,
+    # profiles/r02c); bias_act and the blur keep whatever layout they are given (ops.bias_act, c3d_blur_nhwc).  The module's
+    # contract is unchanged: NCHW-shaped input, (N, 1) output.
+    channels_last = True
 
     def forward(self, input, alpha, summary_ddict=None):
         _require_cuda(input, "Discriminator_MultiScale.forward")
         x = self.diff_aug_img(input) if self.diffaug else input
+        if self.channels_last:
+            x = x.contiguous(memory_format=torch.channels_last)
         res = 2 ** int(math.log(x.shape[-1], 2))
         out = self.convs[str(res)](self.conv_in[str(res)](x))
         if alpha < 1:

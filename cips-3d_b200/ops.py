@@ -40,6 +40,19 @@ def _f32c(t, name):
     return t.contiguous()
 
 
+def _is_cl(t):
+    """4-D tensor stored channels-last (N, H, W, C in memory) and not at the same time NCHW-contiguous"""
+    return t is not None and t.dim() == 4 and not t.is_contiguous() and t.is_contiguous(memory_format=torch.channels_last)
+
+
+def _like(t, ref):
+    """t in the memory format of ref (channels-last or NCHW-contiguous): the discriminator's native ops keep whatever layout
+    their input has, so a channels-last discriminator never transposes"""
+    if t is None:
+        return None
+    return t.contiguous(memory_format=torch.channels_last) if _is_cl(ref) else t.contiguous()
+
+
 def z_cam_from_fov(fov):
     """-1 / tan(fov*pi/360) evaluated like exp/comm/comm_utils.py:396 (fp32 division)."""
     return float(np.float32(-1.0) / np.float32(np.tan((2 * math.pi * fov / 360) / 2)))
@@ -167,17 +180,27 @@ def cips_forward(x, weights, style1p, demod, rgb_w, rgb_b, *, n_blocks=9, skip_f
 # discriminator ops (same call surface as exp/comm/op/{fused_act,upfirdn2d}.py)
 # --------------------------------------------------------------------------------------
 def bias_act(x, bias=None, ref=None, act=3, grad=0, alpha=0.2, scale=2 ** 0.5):
-    """fused.fused_bias_act(input, bias, refer, act, grad, alpha, scale) -- fused_bias_act.cpp:11-20."""
+    """fused.fused_bias_act(input, bias, refer, act, grad, alpha, scale) -- fused_bias_act.cpp:11-20.
+    A channels-last input (N, H, W, C in memory) is processed in place of layout: the bias index is then i % C (step 1)."""
     lib = load()
-    x = _f32c(x, "x")
-    y = torch.empty_like(x)
+    if x.dtype != torch.float32:
+        raise _lib.C3dError(f"x: expected float32, got {x.dtype}")
+    cl = _is_cl(x)
+    if not cl:
+        x = x.contiguous()
+    y = torch.empty_like(x)                       # keeps x's strides
     if x.numel() == 0:
         return y
     b = _f32c(bias, "bias") if bias is not None and bias.numel() else None
-    r = _f32c(ref, "ref") if ref is not None and ref.numel() else None
+    r = None
+    if ref is not None and ref.numel():
+        if ref.dtype != torch.float32:
+            raise _lib.C3dError(f"ref: expected float32, got {ref.dtype}")
+        r = _like(ref, x)
     step_b = 1
-    for i in range(2, x.dim()):
-        step_b *= x.size(i)                                     # fused_bias_act_kernel.cu:67-69
+    if not cl:
+        for i in range(2, x.dim()):
+            step_b *= x.size(i)                                 # fused_bias_act_kernel.cu:67-69
     check(lib.c3d_bias_act(ptr(x), ptr(b), ptr(r), ptr(y), x.numel(), step_b,
                            b.numel() if b is not None else 1, act, grad, alpha, scale, stream_ptr()),
           "c3d_bias_act")
@@ -196,7 +219,7 @@ class _FusedLeakyReLUBackward(Function):            # fused_act.py:19-49
     @staticmethod
     def backward(ctx, gradgrad_input, gradgrad_bias):
         out, = ctx.saved_tensors
-        return bias_act(gradgrad_input.contiguous(), gradgrad_bias, out, 3, 1, ctx.negative_slope,
+        return bias_act(_like(gradgrad_input, out), gradgrad_bias, out, 3, 1, ctx.negative_slope,
                         ctx.scale), None, None, None
 
 
@@ -211,7 +234,7 @@ class _FusedLeakyReLU(Function):                    # fused_act.py:52-70
     @staticmethod
     def backward(ctx, grad_output):
         out, = ctx.saved_tensors
-        gi, gb = _FusedLeakyReLUBackward.apply(grad_output.contiguous(), out, ctx.negative_slope, ctx.scale)
+        gi, gb = _FusedLeakyReLUBackward.apply(_like(grad_output, out), out, ctx.negative_slope, ctx.scale)
         return gi, gb, None, None
 
 
@@ -221,10 +244,17 @@ def fused_leaky_relu(input, bias, negative_slope=0.2, scale=2 ** 0.5):
 
 def _upfirdn2d_raw(x, kernel, up, down, pad):
     lib = load()
-    x = _f32c(x, "x")
     kernel = _f32c(kernel, "kernel")
-    B, Cc, H, W = x.shape
     kh, kw = kernel.shape
+    if _is_cl(x) and x.dtype == torch.float32 and up == (1, 1) and down == (1, 1) and (kh, kw) == (4, 4):
+        # channels-last blur (every Blur of the discriminator and its backward): c3d_blur_nhwc, output channels-last too
+        B, Cc, H, W = x.shape
+        out_h, out_w = H + pad[2] + pad[3] - 3, W + pad[0] + pad[1] - 3
+        y = torch.empty((B, Cc, out_h, out_w), device=x.device, dtype=torch.float32, memory_format=torch.channels_last)
+        check(lib.c3d_blur_nhwc(ptr(x), ptr(kernel), ptr(y), B, H, W, Cc, pad[0], pad[1], pad[2], pad[3], stream_ptr()), "c3d_blur_nhwc")
+        return y
+    x = _f32c(x, "x")
+    B, Cc, H, W = x.shape
     out_h = (H * up[1] + pad[2] + pad[3] - kh) // down[1] + 1
     out_w = (W * up[0] + pad[0] + pad[1] - kw) // down[0] + 1
     y = torch.empty((B, Cc, out_h, out_w), device=x.device, dtype=torch.float32)
@@ -274,7 +304,7 @@ class _Conv2dDgrad(Function):
     def backward(ctx, ggx):
         gy, w = ctx.saved_tensors
         x_shape, stride, padding = ctx.cfg
-        ggx = ggx.contiguous()
+        ggx = _like(ggx, gy)
         d_gy = _conv_fprop(ggx, w, None, stride, padding) if ctx.needs_input_grad[0] else None
         d_w = _conv_wgrad(gy, ggx, w.shape, stride, padding) if ctx.needs_input_grad[1] else None
         return d_gy, d_w, None, None, None
@@ -294,7 +324,7 @@ class _Conv2dWgrad(Function):
     def backward(ctx, ggw):
         gy, x = ctx.saved_tensors
         _, stride, padding = ctx.cfg
-        ggw = ggw.contiguous()
+        ggw = _like(ggw, x)
         d_gy = _conv_fprop(x, ggw, None, stride, padding) if ctx.needs_input_grad[0] else None
         d_x = _conv_dgrad(gy, ggw, x.shape, stride, padding) if ctx.needs_input_grad[1] else None
         return d_gy, d_x, None, None, None
@@ -311,7 +341,7 @@ class _Conv2d(Function):
     def backward(ctx, gy):                     # differentiable again: R1 runs autograd.grad(..., create_graph=True) through it
         x, w = ctx.saved_tensors
         stride, padding, has_bias = ctx.cfg
-        gy = gy.contiguous()
+        gy = _like(gy, x)
         gx = _Conv2dDgrad.apply(gy, w, x.shape, stride, padding) if ctx.needs_input_grad[0] else None
         gw = _Conv2dWgrad.apply(gy, x, w.shape, stride, padding) if ctx.needs_input_grad[1] else None
         gb = gy.sum((0, 2, 3)) if has_bias and ctx.needs_input_grad[2] else None
@@ -321,6 +351,8 @@ class _Conv2d(Function):
 def conv2d(input, weight, bias=None, stride=1, padding=0):
     """F.conv2d(input, weight, bias, stride, padding) for the discriminator's EqualConv2d (square stride / padding, groups 1,
     dilation 1), twice differentiable, with every backward pass of every order on a purpose-built fprop / dgrad / wgrad kernel."""
+    if _is_cl(input):      # channels-last activations: channels-last weights too, and cuDNN's NHWC kernels run without transposes
+        return _Conv2d.apply(input, weight.contiguous(memory_format=torch.channels_last), bias, int(stride), int(padding))
     return _Conv2d.apply(input.contiguous(), weight.contiguous(), bias, int(stride), int(padding))
 
 
@@ -329,15 +361,15 @@ class _UpFirDn2dBackward(Function):                 # upfirdn2d.py:18-85
     def forward(ctx, grad_output, kernel, grad_kernel, up, down, pad, g_pad, in_size):
         grad_input = _upfirdn2d_raw(grad_output, grad_kernel, down, up, g_pad)
         ctx.save_for_backward(kernel)
-        ctx.up, ctx.down, ctx.pad = up, down, pad
+        ctx.up, ctx.down, ctx.pad, ctx.cl = up, down, pad, _is_cl(grad_output)
         assert tuple(grad_input.shape) == tuple(in_size)
         return grad_input
 
     @staticmethod
     def backward(ctx, gradgrad_input):
         kernel, = ctx.saved_tensors
-        return _upfirdn2d_raw(gradgrad_input.contiguous(), kernel, ctx.up, ctx.down, ctx.pad), \
-            None, None, None, None, None, None, None
+        gg = gradgrad_input.contiguous(memory_format=torch.channels_last) if ctx.cl else gradgrad_input.contiguous()
+        return _upfirdn2d_raw(gg, kernel, ctx.up, ctx.down, ctx.pad), None, None, None, None, None, None, None
 
 
 class _UpFirDn2d(Function):                         # upfirdn2d.py:88-141
@@ -352,6 +384,7 @@ class _UpFirDn2d(Function):                         # upfirdn2d.py:88-141
         out_h, out_w = out.shape[2:]
         ctx.save_for_backward(kernel, torch.flip(kernel, [0, 1]))
         ctx.in_size = tuple(input.shape)
+        ctx.cl = _is_cl(input)
         ctx.up, ctx.down, ctx.pad = up, down, pad
         ctx.g_pad = (kw - pad_x0 - 1, in_w * up_x - out_w * down_x + pad_x0 - up_x + 1,
                      kh - pad_y0 - 1, in_h * up_y - out_h * down_y + pad_y0 - up_y + 1)
@@ -360,8 +393,8 @@ class _UpFirDn2d(Function):                         # upfirdn2d.py:88-141
     @staticmethod
     def backward(ctx, grad_output):
         kernel, grad_kernel = ctx.saved_tensors
-        gi = _UpFirDn2dBackward.apply(grad_output.contiguous(), kernel, grad_kernel, ctx.up, ctx.down, ctx.pad,
-                                      ctx.g_pad, ctx.in_size)
+        go = grad_output.contiguous(memory_format=torch.channels_last) if ctx.cl else grad_output.contiguous()
+        gi = _UpFirDn2dBackward.apply(go, kernel, grad_kernel, ctx.up, ctx.down, ctx.pad, ctx.g_pad, ctx.in_size)
         return gi, None, None, None, None
 
 

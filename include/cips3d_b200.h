@@ -339,6 +339,14 @@ int c3d_selftest_umma(const float* a, const float* b, float* d, int32_t n, int32
  * multiple of 32.  Isolates what the CTA-pair CIPS kernel (C3D_CIPS_PAIR=1) relies on. */
 int c3d_selftest_umma_pair(const float* a, const float* b, float* d, int32_t n, int32_t k, void* stream);
 
+/* The discriminator's 4 x 4 Blur (upfirdn2d with up = down = 1; exp/cips3d/models/discriminator.py:67-82) on a CHANNELS-LAST
+ * tensor: x (n, in_h, in_w, channels) in memory -> y (n, in_h + pad_y0 + pad_y1 - 3, in_w + pad_x0 + pad_x1 - 3, channels);
+ * kernel: 4 x 4 taps (device), applied as c3d_upfirdn2d applies them (flipped: true convolution); pads in pixels, negative =
+ * crop.  An extension beside the reference's native boundary (whose op sees (N*C, H, W, 1) planes): it lets the discriminator
+ * stay in the layout the tensor-core convolutions use.  Returns 0 or a negative C3D_E* code. */
+int c3d_blur_nhwc(const float* x, const float* kernel, float* y, int32_t n, int32_t in_h, int32_t in_w, int32_t channels,
+                  int32_t pad_x0, int32_t pad_x1, int32_t pad_y0, int32_t pad_y1, void* stream);
+
 /* ------------------------------------------------------------------------------------
  * Introspection for the CPU-side protocol test (host only, no GPU work): the order in which
  * c3d_cips_fwd's kernel issues the 32 (K64 x N128) weight tiles of a 512x512 layer and the 4

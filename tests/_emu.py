@@ -34,7 +34,7 @@ def emu_lib():
 def _cpu_ptr(t):
     if t is None:
         return None
-    assert not t.is_cuda and t.is_contiguous()
+    assert not t.is_cuda and (t.is_contiguous() or (t.dim() == 4 and t.is_contiguous(memory_format=torch.channels_last)))
     return t.data_ptr()
 
 

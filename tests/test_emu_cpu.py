@@ -724,3 +724,39 @@ def test_emu_pigan_unknown_sample_dist_is_the_mean_camera(sample_dist, monkeypat
         img, py = G(z, sample_dist=sample_dist, **kw)
     assert torch.isfinite(img).all()
     assert torch.allclose(py, torch.tensor([[1.7, 1.3]]).expand(2, 2), atol=1e-6)       # (pitch, yaw) = (v_mean, h_mean)
+
+
+@pytest.mark.parametrize("shape,pad", [((2, 8, 16, 16), (2, 2, 2, 2)), ((1, 128, 9, 7), (1, 1, 1, 1)), ((2, 40, 33, 5), (2, 1, 0, 3)),
+                                       ((1, 3, 4, 4), (3, 3, 3, 3)), ((1, 16, 37, 65), (-1, 2, 2, -1))])
+def test_emu_channels_last_discriminator_ops_match_nchw(shape, pad):
+    """ops.bias_act and the 4x4 blur on channels-last tensors (c3d_blur_nhwc: the register-streaming kernel with the taps C
+    elements apart) equal the NCHW results element for element, keep the layout, and differentiate twice the same way."""
+    g = torch.Generator().manual_seed(sum(shape))
+    x = torch.randn(*shape, generator=g)
+    b = torch.randn(shape[1], generator=g)
+    k1 = torch.tensor([1., 3., 3., 1.])
+    xcl = x.contiguous(memory_format=torch.channels_last)
+    for k in ((k1[None] * k1[:, None]) / 64, torch.randn(4, 4, generator=g)):
+        with emulated(async_mode=0, sms=2) as pkg:
+            y0 = pkg.ops._upfirdn2d_raw(x, k, (1, 1), (1, 1), pad)
+            y1 = pkg.ops._upfirdn2d_raw(xcl, k, (1, 1), (1, 1), pad)
+            a0 = pkg.ops.bias_act(x, b)
+            a1 = pkg.ops.bias_act(xcl, b)
+            g0 = pkg.ops.bias_act(x, None, a0, 3, 1)
+            g1 = pkg.ops.bias_act(xcl, None, a0, 3, 1)          # NCHW ref against a channels-last input: converted inside
+        assert y1.shape == y0.shape and (shape[1] == 1 or y1.is_contiguous(memory_format=torch.channels_last))
+        assert torch.equal(a1, a0) and torch.equal(g1, g0) and a1.stride() == xcl.stride()
+        assert (y1 - y0).abs().max().item() < 1e-6
+        assert (y0 - O.upfirdn2d(x, k, (1, 1), (1, 1), pad)).abs().max().item() < 1e-5
+    with emulated(async_mode=0, sms=2) as pkg:          # autograd through both ops, R1 pattern, both layouts
+        kk = (k1[None] * k1[:, None]) / 64
+        res = []
+        for inp in (x, xcl):
+            xi = inp.clone().requires_grad_()
+            bi = b.clone().requires_grad_()
+            y = pkg.ops.fused_leaky_relu(pkg.ops.upfirdn2d(xi, kk, pad=(max(pad[0], 0), max(pad[1], 0))), bi)
+            gx, = torch.autograd.grad(y.square().sum(), xi, create_graph=True)
+            gx.square().sum().backward()
+            res.append((y.detach(), gx.detach(), xi.grad, bi.grad))
+        for a, c in zip(*res):
+            assert (a - c).abs().max().item() <= 1e-5 * max(1.0, c.abs().max().item())

@@ -84,6 +84,11 @@ def main():
     os.makedirs(OUT, exist_ok=True)
     torch.manual_seed(1234)
     G = ref_shim.build_reference_generator().eval()
+    if "r8_hier_s24" in sys.argv[1:]:
+        # the web-demo sampling (ffhq_exp.yaml:244-278: num_steps 24, hierarchical G_kwargs -> 24 coarse + 24 fine = 48 sorted
+        # samples per ray), added in round 2 without regenerating the other fixtures
+        gen_case(G, "r8_hier_s24", seed=79, sigma_bias=0.25, B=2, img_size=8, nerf_noise=0.0, z_seed=11, num_steps=24)
+        return
     tmpl = {k: list(v.shape) for k, v in G.state_dict().items()}
     # state_dict contract (key order + shapes) of the reference G and D
     D = ref_shim.build_reference_discriminator().eval()

@@ -13,3 +13,10 @@ for rep in 1 2; do
   run "staged, e_turn 0, stagger 10us (rep $rep)" "C3D_RAY_E_TURN=0 C3D_RAY_STAGGER_NS=10000"
 done 2>&1 | tee $O/r02g_ray_variants.txt
 timeout 600 python -m pytest tests/test_gpu_parity.py tests/test_baseline_sizes_gpu.py -m gpu -q -x -p no:cacheprovider > $O/r02g_pytest_gpu.log 2>&1; echo "gpu tests: exit $?"; tail -2 $O/r02g_pytest_gpu.log
+# channels-last discriminator: tests + train step
+timeout 400 python -m pytest tests/test_conv2d_cpu.py -q -p no:cacheprovider > $O/r02g_pytest_conv.log 2>&1; echo "conv2d tests: exit $?"
+for c in 5 4 3; do
+  extra=""; [ $c = 3 ] && extra="--film-backend fused --integrate-backend fused"
+  timeout 500 python tools/bench_train_step.py --config $c --cips-backend fused $extra > $O/r02g_train_c$c.json 2> $O/r02g_train_c$c.err; echo "train c$c: $?"; cut -c1-130 $O/r02g_train_c$c.json
+done
+timeout 500 python tools/bench_train_step.py --config 5 --cips-backend fused --profile $O/r02g_prof_c5.txt > /dev/null 2>&1; head -30 $O/r02g_prof_c5.txt | cut -c1-200
