@@ -8,7 +8,7 @@ import torch
 from oracle import cips3d_oracle as O
 
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
-GEN_CASES = ("r16_synth", "r16_trained_noise", "r8_softplus_backs", "r8_nohier_s24")
+GEN_CASES = ("r16_synth", "r16_trained_noise", "r8_softplus_backs", "r8_nohier_s24", "r8_hier_s24")
 
 
 def load_gen_case(name, dtype=torch.float32):

@@ -88,7 +88,7 @@ def test_renderer_matches_reference_golden(pkg, name, impl_name):
     assert frac_d >= 0.995
 
 
-@pytest.mark.parametrize("name", ["r16_synth", "r16_trained_noise", "r8_softplus_backs", "r8_nohier_s24"])
+@pytest.mark.parametrize("name", ["r16_synth", "r16_trained_noise", "r8_softplus_backs", "r8_nohier_s24", "r8_hier_s24"])
 @pytest.mark.parametrize("impl_name", ["simt", "tc"])
 def test_generator_forward_matches_reference_golden(pkg, name, impl_name):
     """Whole GeneratorNerfINR.forward through the public class surface, draws replayed."""
@@ -198,7 +198,7 @@ def test_renderer_fold_math_matches_reference_golden(pkg, name, monkeypatch):
     reference goldens; caller-visible outputs only (the form has no per-point debug outputs)."""
     monkeypatch.setenv("C3D_RAY_MATH", "fold")
     out, ref, _, _ = _render_case(pkg, name, pkg._lib.IMPL_TC, debug=False)
-    assert pkg._lib.load().c3d_debug_ray_math_mode() == 2
+    assert pkg._lib.load().c3d_debug_ray_math_mode() == (0 if name == "r8_hier_s24" else 2)    # 24 + 24 samples: block form only
     frac, worst = close_frac(out["pixels_fea"], ref["pixels_fea"], 1e-3)
     assert frac >= 0.995, f"only {frac:.4f} of rays within 1e-3 (worst {worst:.3e})"
     assert close_frac(out["depth"][..., None], ref["depth"][..., None], 1e-3)[0] >= 0.995
