@@ -17,7 +17,7 @@ CIPS_MAX_LAYERS = 18
 EXPORTS = ("c3d_reload_options", "c3d_debug_cips_max_clusters", "c3d_version", "c3d_last_error", "c3d_device_supported", "c3d_launch_count",
            "c3d_ray_siren_workspace_bytes",
            "c3d_ray_siren_fwd", "c3d_cips_workspace_bytes", "c3d_cips_fwd", "c3d_bias_act",
-           "c3d_upfirdn2d", "c3d_blur_nhwc", "c3d_selftest_umma", "c3d_selftest_umma_pair", "c3d_debug_cips_tile_order", "c3d_debug_ray_math_mode",
+           "c3d_upfirdn2d", "c3d_blur_nhwc", "c3d_points_linear_workspace_bytes", "c3d_points_linear", "c3d_selftest_umma", "c3d_selftest_umma_pair", "c3d_debug_cips_tile_order", "c3d_debug_ray_math_mode",
            "c3d_optim_workspace_bytes", "c3d_grad_norm", "c3d_adam_ema_step", "c3d_ema_update",
            "c3d_pigan_workspace_bytes", "c3d_pigan_render_fwd", "c3d_cips_fwd_train", "c3d_cips_bwd_workspace_bytes", "c3d_cips_bwd", "c3d_cips_style_prep", "c3d_image_to_u8",
            "c3d_film_sin_fwd", "c3d_film_sin_bwd_workspace_bytes", "c3d_film_sin_bwd",
@@ -127,6 +127,9 @@ def bind(lib):
     lib.c3d_bias_act.argtypes = [_fp, _fp, _fp, _fp, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
                                  C.c_float, C.c_float, _fp]
     lib.c3d_upfirdn2d.argtypes = [_fp, _fp, _fp] + [C.c_int32] * 13 + [_fp]
+    lib.c3d_points_linear_workspace_bytes.restype = C.c_size_t
+    lib.c3d_points_linear_workspace_bytes.argtypes = [C.c_int32, C.c_int32]
+    lib.c3d_points_linear.argtypes = [_fp, _fp, _fp, _fp, _fp, C.c_int64, C.c_int32, C.c_int32, C.c_int32, _fp, C.c_size_t, _fp]
     lib.c3d_blur_nhwc.argtypes = [_fp, _fp, _fp] + [C.c_int32] * 8 + [_fp]
     lib.c3d_selftest_umma.argtypes = [_fp, _fp, _fp, C.c_int32, C.c_int32, C.c_int32, _fp]
     lib.c3d_selftest_umma_pair.argtypes = [_fp, _fp, _fp, C.c_int32, C.c_int32, _fp]

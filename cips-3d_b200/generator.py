@@ -90,8 +90,10 @@ class FiLMLayer(nn.Module):                     # film_layer.py:41-107
         self.linear = which_linear(in_dim, out_dim)
         self.linear.apply(frequency_init(25))
         self.gain_scale = LinearScale(scale=15, bias=30)
-        # opt-in until timed on hardware: FiLM + sine of the autograd graph as the native op (ops.FilmSinFunction)
+        # FiLM + sine of the autograd graph as the native op (ops.FilmSinFunction), and its linear as the tcgen05 split-fp16
+        # GEMM (ops.PointsLinearFunction: forward + data gradient native, weight gradient a library reduction)
         self.fused_film = False
+        self.fused_linear = False
         if use_style_fc:
             self.gain_fc = which_linear(style_dim, out_dim)
             self.bias_fc = which_linear(style_dim, out_dim)
@@ -114,7 +116,10 @@ class FiLMLayer(nn.Module):                     # film_layer.py:41-107
         elif x.dim() != 2:
             assert 0
         if self.fused_film and x.dim() == 3:
-            z = self.linear(x)
+            if self.fused_linear and ops.points_linear_supported(x, self.linear.weight):
+                z = ops.points_linear(x, self.linear.weight, self.linear.bias)
+            else:
+                z = self.linear(x)
             if ops.film_sin_supported(z, gain, bias):
                 return ops.film_sin(z, gain, bias)      # one native pass forward, one backward (csrc/film_ops.cu)
             return torch.sin(gain * z + bias)
@@ -157,6 +162,7 @@ class NeRFNetwork(nn.Module):                   # generator.py:151-376
         self.module_name_list.append('color_layer_linear')
         self.dim_styles = sum(self.style_dim_dict.values())
         self.gridwarper = UniformBoxWarp(0.24)
+        self.fused_linear = False      # training graph: color_layer_linear on ops.points_linear (see FiLMLayer.fused_linear)
 
     # ---- what the fused kernel consumes
     def fused_supported(self, num_steps=None):
@@ -183,7 +189,11 @@ class NeRFNetwork(nn.Module):                   # generator.py:151-376
             x = layer(x, style_dict[f'{self.name_prefix}_w{index}'])
         sigma = self.final_layer(x)
         x = self.color_layer_sine(x, style_dict[f'{self.name_prefix}_rgb'])
-        rbg = self.color_layer_linear(x)
+        lin = self.color_layer_linear[0]
+        if self.fused_linear and x.dim() == 3 and ops.points_linear_supported(x, lin.weight):
+            rbg = ops.points_linear(x, lin.weight, lin.bias)      # tcgen05 split-fp16 GEMM, forward and data gradient
+        else:
+            rbg = self.color_layer_linear(x)
         return torch.cat([rbg, sigma], dim=-1)
 
     def forward(self, input, style_dict, ray_directions=None, **kwargs):

@@ -675,6 +675,64 @@ def film_sin_supported(z, gain, bias):
     return Cn >= 4 and Cn % 4 == 0 and 256 % (Cn // 4) == 0 and ok(gain) and ok(bias)
 
 
+# ---------------------------------------------------------------------------------------------------------------------
+# Per-point linear layer of the NeRF training graph (csrc/points_linear_tc.cu)
+# ---------------------------------------------------------------------------------------------------------------------
+def points_linear_supported(x, weight):
+    """x (..., K) fp32 with K in {32, 64, 128}; weight (N, K) with N in {32, 64, 128}"""
+    return (x.dtype == torch.float32 and weight.dtype == torch.float32 and weight.dim() == 2 and x.shape[-1] == weight.shape[1]
+            and weight.shape[0] in (32, 64, 128) and weight.shape[1] in (32, 64, 128) and x.numel() > 0)
+
+
+def _points_linear_raw(x2, w, bias, scale, transposed):
+    """x2 (rows, K) contiguous; w (N, K) [transposed False] or (K, N) [True]; -> (rows, N)"""
+    lib = load()
+    rows, K = x2.shape
+    N = w.shape[1] if transposed else w.shape[0]
+    y = torch.empty((rows, N), device=x2.device, dtype=torch.float32)
+    nbytes = lib.c3d_points_linear_workspace_bytes(N, K)
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=x2.device)
+    check(lib.c3d_points_linear(ptr(x2), ptr(w), ptr(bias) if bias is not None else None, ptr(scale) if scale is not None else None,
+                                ptr(y), rows, K, N, int(bool(transposed)), ptr(ws), nbytes, stream_ptr()), "c3d_points_linear")
+    return y
+
+
+class PointsLinearFunction(Function):
+    """F.linear(x, weight, bias) for the per-point layers of the NeRF field (film_layer.py:78-107, generator.py:236-243) with the
+    forward GEMM and the data-gradient GEMM on the tcgen05 split-fp16 kernel (fp32-equivalent products); the weight gradient
+    dW = dZ^T X (a points-long reduction) and db stay library reductions over the same tensors, as for the CIPS MLP.
+    The gradient operand is pre-scaled to 1024 / max|dZ| on the device (no host sync) so that its fp16 halves stay normal."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias):
+        x2 = x.reshape(-1, x.shape[-1]).contiguous()
+        w = weight.contiguous()
+        y = _points_linear_raw(x2, w, bias.contiguous() if bias is not None else None, None, False)
+        ctx.save_for_backward(x2, w)
+        ctx.has_bias = bias is not None
+        ctx.x_shape = x.shape
+        return y.view(*x.shape[:-1], w.shape[0])
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dy):
+        x2, w = ctx.saved_tensors
+        dy2 = dy.reshape(-1, dy.shape[-1]).contiguous()
+        dx = dw = db = None
+        if ctx.needs_input_grad[0]:
+            scale = (1024.0 / dy2.abs().amax().clamp_min(1e-30)).reshape(1).to(torch.float32)
+            dx = _points_linear_raw(dy2, w, None, scale, True).view(ctx.x_shape)
+        if ctx.needs_input_grad[1]:
+            dw = dy2.t().mm(x2)
+        if ctx.has_bias and ctx.needs_input_grad[2]:
+            db = dy2.sum(0)
+        return dx, dw, db
+
+
+def points_linear(x, weight, bias=None):
+    return PointsLinearFunction.apply(x, weight, bias)
+
+
 class FilmSinFunction(Function):
     """y = sin(gain * z + bias) with per-image gain / bias (film_layer.py:94-107): one native pass forward, one backward
     (dz and the per-image reductions dgain, dbias together); saves z only.  No double backward (the generator's graph

@@ -339,6 +339,21 @@ int c3d_selftest_umma(const float* a, const float* b, float* d, int32_t n, int32
  * multiple of 32.  Isolates what the CTA-pair CIPS kernel (C3D_CIPS_PAIR=1) relies on. */
 int c3d_selftest_umma_pair(const float* a, const float* b, float* d, int32_t n, int32_t k, void* stream);
 
+/* ------------------------------------------------------------------------------------
+ * Per-point linear layer of the NeRF TRAINING graph on tcgen05: replaces the `self.linear(x)` GEMM of
+ * FiLMLayer.forward (exp/comm/models/film_layer.py:78-107) and of color_layer_linear (exp/cips3d/models/generator.py:236-243)
+ * and, with transposed != 0, their data gradient -- fp32-equivalent products (fp16 hi/lo split, three MMA passes), where
+ * torch runs fp32 SIMT sgemm.
+ *   y (rows, n) = x (rows, k) . w^T (+ bias)       w: (n, k) row-major         [transposed == 0: the layer forward]
+ *   y (rows, n) = x (rows, k) . w    (+ bias)       w: (k, n) row-major         [transposed != 0: dX = dZ . W with W as stored]
+ * k, n in {32, 64, 128}; x, y, bias 16-byte aligned fp32; scale: device scalar or NULL -- operands are multiplied by it before
+ * the fp16 split and the result divided by it (pass 1024 / max|x| for small-magnitude gradients).  workspace: at least
+ * c3d_points_linear_workspace_bytes(n, k) bytes of device memory (the prepared weight blob).  Returns 0 or a negative C3D_E* code.
+ * ---------------------------------------------------------------------------------- */
+size_t c3d_points_linear_workspace_bytes(int32_t n, int32_t k);
+int c3d_points_linear(const float* x, const float* w, const float* bias, const float* scale, float* y, int64_t rows, int32_t k,
+                      int32_t n, int32_t transposed, void* workspace, size_t workspace_bytes, void* stream);
+
 /* The discriminator's 4 x 4 Blur (upfirdn2d with up = down = 1; exp/cips3d/models/discriminator.py:67-82) on a CHANNELS-LAST
  * tensor: x (n, in_h, in_w, channels) in memory -> y (n, in_h + pad_y0 + pad_y1 - 3, in_w + pad_x0 + pad_x1 - 3, channels);
  * kernel: 4 x 4 taps (device), applied as c3d_upfirdn2d applies them (flipped: true convolution); pads in pixels, negative =

@@ -761,3 +761,36 @@ def test_emu_channels_last_discriminator_ops_match_nchw(shape, pad):
             res.append((y.detach(), gx.detach(), xi.grad, bi.grad))
         for a, c in zip(*res):
             assert (a - c).abs().max().item() <= 1e-5 * max(1.0, c.abs().max().item())
+
+
+@pytest.mark.parametrize("rows,K,N,bias", [(128, 128, 128, True), (300, 128, 64, True), (77, 64, 32, True), (1, 32, 64, False),
+                                            (513, 64, 128, False), (256, 128, 32, True)])
+@pytest.mark.parametrize("mode", ["eager", "random"])
+def test_emu_points_linear_matches_fp64(rows, K, N, bias, mode):
+    """c3d_points_linear (tcgen05 split-fp16 GEMM: the NeRF field's per-point linears in the training graph) against an fp64
+    product: forward, the transposed form (data gradient) with the device-side gradient scale, ragged last tile, several tiles
+    per CTA (2 emulated SMs), and the autograd Function against torch's linear."""
+    g = torch.Generator().manual_seed(rows * 7 + K + N)
+    x = torch.randn(rows, K, generator=g)
+    w = torch.randn(N, K, generator=g) * 0.3
+    b = torch.randn(N, generator=g) if bias else None
+    with emulated(async_mode=MODES[mode], seed=3, sms=2) as pkg:
+        y = pkg.ops._points_linear_raw(x, w, b, None, False)
+        dz = torch.randn(rows, N, generator=g) * 1e-6                      # gradient-sized operand: needs the scale
+        sc = (1024.0 / dz.abs().amax()).reshape(1)
+        dx = pkg.ops._points_linear_raw(dz, w, None, sc, True)
+        xr = x.view(1, rows, K).clone().requires_grad_()
+        wr, br = w.clone().requires_grad_(), (b.clone().requires_grad_() if bias else None)
+        out = pkg.ops.points_linear(xr, wr, br)
+        out.square().sum().backward()
+    ref = x.double() @ w.double().T + (b.double() if bias else 0)
+    assert (y.double() - ref).abs().max().item() < 2e-6 * ref.abs().max().item()
+    refx = dz.double() @ w.double()
+    assert (dx.double() - refx).abs().max().item() < 2e-6 * refx.abs().max().item()
+    x2 = x.view(1, rows, K).clone().requires_grad_()
+    w2, b2 = w.clone().requires_grad_(), (b.clone().requires_grad_() if bias else None)
+    torch.nn.functional.linear(x2, w2, b2).square().sum().backward()
+    assert (xr.grad - x2.grad).abs().max().item() < 1e-5 * x2.grad.abs().max().item()
+    assert (wr.grad - w2.grad).abs().max().item() < 1e-4 * w2.grad.abs().max().item()
+    if bias:
+        assert (br.grad - b2.grad).abs().max().item() < 1e-4 * b2.grad.abs().max().item()

@@ -52,3 +52,58 @@ def test_film_layer_flag_in_the_generator_training_graph(pkg):
     assert res[True][1].keys() == res[False][1].keys() and any(k.startswith("siren.") for k in res[True][1])
     for k, gr in res[False][1].items():
         assert (res[True][1][k] - gr).abs().max().item() < 1e-3 * gr.abs().max().item() + 1e-7, k
+
+
+@pytest.mark.parametrize("rows,K,N,bias", [(65536 * 24, 128, 128, True), (100003, 128, 64, True), (4097, 64, 32, True), (1, 32, 64, False),
+                                            (70000, 64, 128, False), (513, 32, 32, True)])
+def test_points_linear_matches_fp64(pkg, rows, K, N, bias):
+    """c3d_points_linear (tcgen05 split-fp16 GEMM of the NeRF training graph) against an fp64 product: forward, the transposed
+    (data gradient) form with gradient-sized operands and the device-side scale, and the autograd Function vs torch's linear."""
+    g = torch.Generator().manual_seed(rows % 1000 + K + N)
+    x = torch.randn(rows, K, generator=g).to(DEV)
+    w = (torch.randn(N, K, generator=g) * 0.3).to(DEV)
+    b = torch.randn(N, generator=g).to(DEV) if bias else None
+    y = pkg.ops._points_linear_raw(x, w, b, None, False)
+    n_chk = min(rows, 20000)
+    ref = x[:n_chk].double() @ w.double().T + (b.double() if bias else 0)
+    assert (y[:n_chk].double() - ref).abs().max().item() < 2e-6 * ref.abs().max().item()
+    dz = torch.randn(rows, N, generator=g).to(DEV) * 1e-6
+    sc = (1024.0 / dz.abs().amax()).reshape(1)
+    dx = pkg.ops._points_linear_raw(dz, w, None, sc, True)
+    refx = dz[:n_chk].double() @ w.double()
+    assert (dx[:n_chk].double() - refx).abs().max().item() < 2e-6 * refx.abs().max().item()
+    if rows <= 100003:
+        xr = x.view(1, rows, K).clone().requires_grad_()
+        wr, br = w.clone().requires_grad_(), (b.clone().requires_grad_() if bias else None)
+        pkg.ops.points_linear(xr, wr, br).square().sum().backward()
+        x2 = x.view(1, rows, K).clone().requires_grad_()
+        w2, b2 = w.clone().requires_grad_(), (b.clone().requires_grad_() if bias else None)
+        torch.nn.functional.linear(x2, w2, b2).square().sum().backward()
+        assert (xr.grad - x2.grad).abs().max().item() < 1e-5 * x2.grad.abs().max().item()
+        assert (wr.grad - w2.grad).abs().max().item() < 1e-4 * w2.grad.abs().max().item()
+
+
+def test_points_linear_in_the_generator_training_graph(pkg):
+    """GeneratorNerfINR with every hot op of the NeRF training graph native (FiLM + sine, per-point linears, volume integration):
+    same image and parameter gradients as the torch-op graph."""
+    from _util import build_generator
+    from oracle import cips3d_oracle as O
+    G = build_generator(DEV, O.synthetic_state_dict(O.generator_template(), seed=5, sigma_bias=0.3)).train()
+    kw = dict(O.G_KWARGS)
+    kw["num_steps"] = 6
+    res = {}
+    for fused in (False, True):
+        for m in G.modules():
+            if isinstance(m, pkg.FiLMLayer):
+                m.fused_film = m.fused_linear = fused
+        G.siren.fused_linear = fused
+        G.train_integrate = "fused" if fused else "torch"
+        G.zero_grad()
+        torch.manual_seed(11)
+        img, _ = G(G.get_zs(2), img_size=16, nerf_noise=0.0, **kw)
+        img.square().mean().backward()
+        res[fused] = (img.detach().clone(), {k: p.grad.clone() for k, p in G.named_parameters() if p.grad is not None})
+    assert (res[True][0] - res[False][0]).abs().max().item() < 1e-4
+    assert res[True][1].keys() == res[False][1].keys() and any(k.startswith("siren.") for k in res[True][1])
+    for k, gr in res[False][1].items():
+        assert (res[True][1][k] - gr).abs().max().item() < 1e-3 * gr.abs().max().item() + 1e-7, k

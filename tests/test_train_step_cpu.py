@@ -35,12 +35,13 @@ def cpu_modules(monkeypatch):
     return cips3d_b200
 
 
-def _run(bts, frozen, optim, backend, steps=2, film="torch", integ="torch"):
+def _run(bts, frozen, optim, backend, steps=2, film="torch", integ="torch", linear="torch"):
     cfg = dict(res=16, batch=2, frozen=frozen, aux=not frozen, diffaug=frozen, grad_points=256, forward_points=256,
                warmup_D=frozen)
     torch.manual_seed(0)
     with emulated(async_mode=0, sms=2):
-        step, mods = bts.build_step(cfg, torch.device("cpu"), optim, backend, film_backend=film, integrate_backend=integ)
+        step, mods = bts.build_step(cfg, torch.device("cpu"), optim, backend, film_backend=film, integrate_backend=integ,
+                                    linear_backend=linear)
         before = {k: v.detach().clone() for k, v in mods["G"].named_parameters()}
         ema_before = {k: v.detach().clone() for k, v in mods["G_ema"].state_dict().items()}
         losses = [tuple(float(x) for x in step(it)) for it in range(steps)]
@@ -77,3 +78,9 @@ def test_train_step_full_recipe_with_aux_images(bts, cpu_modules):
     assert any(k.startswith("siren.") for k in moved_nat)
     assert nat[0] == pytest.approx(ref2[0], rel=1e-5)
     assert nat[1] == pytest.approx(ref2[1], rel=1e-4)               # after an update that went through the native backwards
+    # ... and with the field's per-point linears on the tcgen05 split-fp16 GEMM as well (forward + data gradient native):
+    # every hot op of the NeRF training graph is then a kernel of this repo
+    nat2, moved_nat2, _ = _run(bts, False, "fused", "torch", steps=2, film="fused", integ="fused", linear="fused")
+    assert any(k.startswith("siren.") for k in moved_nat2)
+    assert nat2[0] == pytest.approx(ref2[0], rel=1e-5)
+    assert nat2[1] == pytest.approx(ref2[1], rel=1e-4)

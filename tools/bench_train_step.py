@@ -44,7 +44,7 @@ def requires_grad(model, flag):
 
 
 def build_step(cfg, dev, optim="fused", cips_backend="torch", ddp=False, local=0, g_cfg=None, d_kwargs=None, film_backend="torch",
-               integrate_backend="torch"):
+               integrate_backend="torch", linear_backend="torch"):
     """Modules, optimisers and the step closure of one configuration on device `dev`.  Separate from main() so that
     tests/test_train_step_cpu.py can execute the very same step on the CPU emulation of the kernels (tiny sizes)."""
     class _A:        # the two switches the step reads
@@ -62,6 +62,8 @@ def build_step(cfg, dev, optim="fused", cips_backend="torch", ddp=False, local=0
     for m in G.modules():           # FiLM + sine of the NeRF branch's autograd graph as the native op (csrc/film_ops.cu)
         if isinstance(m, cips3d_b200.FiLMLayer):
             m.fused_film = film_backend == "fused"
+            m.fused_linear = linear_backend == "fused"      # needs fused_film (the z -> sin step is the native op then)
+    G.siren.fused_linear = linear_backend == "fused"
     G_ema = copy.deepcopy(G)
     G_run, D_run = G, D
     if ddp:
@@ -150,6 +152,8 @@ def main():
                     help="fused: FiLMLayer.fused_film = True (native FiLM+sine forward/backward in the NeRF autograd graph; configs with NeRF gradients)")
     ap.add_argument("--integrate-backend", default="torch", choices=["torch", "fused"],
                     help="fused: GeneratorNerfINR.train_integrate = 'fused' (native fancy_integration forward/backward in the NeRF autograd graph)")
+    ap.add_argument("--linear-backend", default="torch", choices=["torch", "fused"],
+                    help="fused: the NeRF field's per-point linears (forward + data gradient) on the tcgen05 split-fp16 GEMM (ops.points_linear)")
     ap.add_argument("--tf32", action="store_true", help="allow TF32 in the torch autograd GEMMs / cuDNN convs of the training graph "
                     "(NOT the reference's numerics: torch defaults to fp32 matmuls); measures what the library path can give")
     ap.add_argument("--no-cudnn-tf32", action="store_true", help="force fp32 cuDNN convolutions (torch's default -- and the reference's, "
@@ -170,7 +174,8 @@ def main():
     if ddp:
         torch.distributed.init_process_group("nccl")
     torch.manual_seed(1234 + rank)
-    step, mods = build_step(cfg, dev, args.optim, args.cips_backend, ddp, local, film_backend=args.film_backend, integrate_backend=args.integrate_backend)
+    step, mods = build_step(cfg, dev, args.optim, args.cips_backend, ddp, local, film_backend=args.film_backend, integrate_backend=args.integrate_backend,
+                             linear_backend=args.linear_backend)
     G_cls = mods["G_cls"]
     R, B = cfg["res"], cfg["batch"]
 
@@ -213,7 +218,7 @@ def main():
             n_gpus=world, steps=args.steps, warmup=args.warmup,
             config=dict(baseline_config=args.config, resolution=R, batch_per_gpu=B, generator=G_cls.__name__, train_aux_img=cfg["aux"],
                         diffaug=cfg["diffaug"], grad_points=cfg["grad_points"], optim=args.optim, tf32_autograd=bool(args.tf32),
-                        cudnn_tf32=bool(torch.backends.cudnn.allow_tf32), cips_backend=args.cips_backend, film_backend=args.film_backend, integrate_backend=args.integrate_backend,
+                        cudnn_tf32=bool(torch.backends.cudnn.allow_tf32), cips_backend=args.cips_backend, film_backend=args.film_backend, integrate_backend=args.integrate_backend, linear_backend=args.linear_backend,
                         note="G forward under no_grad runs the fused kernels; the G step's autograd graph runs as torch CUDA ops "
                              "(backward kernels: DESIGN.md section 9); D convs are cuDNN as in the reference; D's bias_act / blur are native"),
             d_loss=float(dl), g_loss=float(gl), comm=nccl, finite=bool(math.isfinite(float(dl)) and math.isfinite(float(gl))))))
