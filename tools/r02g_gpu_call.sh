@@ -20,3 +20,7 @@ for c in 5 4 3; do
   timeout 500 python tools/bench_train_step.py --config $c --cips-backend fused $extra > $O/r02g_train_c$c.json 2> $O/r02g_train_c$c.err; echo "train c$c: $?"; cut -c1-130 $O/r02g_train_c$c.json
 done
 timeout 500 python tools/bench_train_step.py --config 5 --cips-backend fused --profile $O/r02g_prof_c5.txt > /dev/null 2>&1; head -30 $O/r02g_prof_c5.txt | cut -c1-200
+# points_linear (NeRF per-point linears on tcgen05) + the whole default suite
+timeout 600 python -m pytest tests/test_film_gpu.py -m gpu -q -x -p no:cacheprovider > $O/r02g_pytest_film.log 2>&1; echo "film/points_linear gpu tests: exit $?"; tail -3 $O/r02g_pytest_film.log
+timeout 500 python tools/bench_train_step.py --config 3 --cips-backend fused --film-backend fused --integrate-backend fused --linear-backend fused --profile $O/r02g_prof_c3_linear.txt > $O/r02g_train_c3_linear.json 2> $O/r02g_train_c3_linear.err; echo "train c3 + native linears: $?"; cut -c1-130 $O/r02g_train_c3_linear.json
+timeout 900 python -m pytest tests -m gpu -q -p no:cacheprovider > $O/r02g_pytest_all.log 2>&1; echo "whole gpu suite: exit $?"; tail -3 $O/r02g_pytest_all.log
