@@ -53,7 +53,8 @@ struct ImgConsts {
 
 struct SlotMem {
   float feat[2][kRows][33];   // [0] fine pass, [1] coarse pass features (padded rows: conflict-free both ways)
-  float z_c[kRows], sig_c[kRows], z_f[kRows], sig_f[kRows];
+  float z_c[2][kRows];        // coarse depths, double-buffered by group parity: the deferred merge of group g reads them while group g + 1 writes its own
+  float sig_c[kRows], z_f[kRows], sig_f[kRows];
   float wc[kRows];            // coarse compositing weights
   float cdf[kRows];           // per ray: S-1 cdf entries (stride S)
   float fbuf[2 * kRows];      // 1 - alpha + 1e-10 per (sorted) sample
@@ -392,11 +393,114 @@ __global__ void __launch_bounds__(640, 1) ray_siren_tc_kernel(const KArgs a) {
       const int gray_ = a.io.ray_idx ? a.io.ray_idx[nloc_] : p.ray_offset + nloc_;
       return a.io.jitter_u[((size_t)img_ * p.img_size * p.img_size + gray_) * S + s_row];
     };
+    // ---- deferred merge + compositing of the PREVIOUS group of this slot (MATH 0), in three pieces that are slotted into the
+    // MMA waits of the next group's coarse pass.  Hazards: m1 reads the previous group's coarse depths (z_c is double-buffered)
+    // and fine depths (rewritten by the next resampling, after m1); m2 reads sig_c / sig_f (rewritten by the next E2); m3 reads
+    // the feature rows (rewritten by the next E3) -- each piece runs before the epilogue that overwrites what it reads.
+    struct PrevGroup { int img, ray0, n_valid, zbuf; bool valid; } pg = {0, 0, 0, 0, false};
+    auto m1 = [&]() {      // stable rank sort of the nS depths of each ray (generator.py:1733-1738)
+      const int img = pg.img, ray0 = pg.ray0, n_valid = pg.n_valid;
+      const float* zc = sm.z_c[pg.zbuf];
+      const bool el_ok = g_el < n_valid;
+      const int rc0 = g_el * S;           // first row of ray g_el
+      const int base = g_el * nS;
+      const size_t ro_el = (size_t)img * p.n_rays + ray0 + g_el;
+      (void)ro_el; (void)rc0; (void)base; (void)el_ok; (void)zc; (void)img; (void)ray0;
+      if (el_ok) {
+        auto key_of = [&](int e) { return hier ? (e < S ? sm.z_f[rc0 + e] : zc[rc0 + e - S]) : zc[rc0 + e]; };
+        const float k = key_of(e_el);
+        int rank = 0;
+#pragma unroll 4
+        for (int e = 0; e < nS; ++e) {
+          const float ke = key_of(e);
+          rank += (ke < k || (ke == k && e < e_el)) ? 1 : 0;
+        }
+        const int src = hier ? e_el : S + e_el;
+        sm.skey[base + rank] = k;
+        sm.sidx[base + rank] = src;
+        sm.frow[base + rank] = src < S ? rc0 + src : kRows + rc0 + src - S;
+      }
+      slot_sync();
+    };
+    auto m2 = [&]() {      // alphas, transmittance in the reference's cumprod order, weights (pigan_utils.py:241-257)
+      const int img = pg.img, ray0 = pg.ray0, n_valid = pg.n_valid;
+      const float* zc = sm.z_c[pg.zbuf];
+      const bool el_ok = g_el < n_valid;
+      const int rc0 = g_el * S;           // first row of ray g_el
+      const int base = g_el * nS;
+      const size_t ro_el = (size_t)img * p.n_rays + ray0 + g_el;
+      (void)ro_el; (void)rc0; (void)base; (void)el_ok; (void)zc; (void)img; (void)ray0;
+      float alpha_el = 0.f;
+      if (el_ok) {       // alpha of sorted position e_el (pigan_utils.py:241-251)
+        const int src = sm.sidx[base + e_el];
+        const float sg = src < S ? sm.sig_f[rc0 + src] : sm.sig_c[rc0 + src - S];
+        const float delta = e_el + 1 < nS ? __fsub_rn(sm.skey[base + e_el + 1], sm.skey[base + e_el]) : 1e10f;
+        const float nz = a.io.noise_f ? __fmul_rn(a.io.noise_f[ro_el * nS + e_el], p.noise_std) : 0.f;
+        alpha_el = sample_alpha(delta, sg, nz, p.clamp_mode);
+        sm.fbuf[base + e_el] = __fadd_rn(__fsub_rn(1.f, alpha_el), 1e-10f);
+      }
+      slot_sync();
+      if (el_ok) {       // transmittance in the reference's cumprod order, weight
+        float T = 1.f;
+#pragma unroll 4
+        for (int j = 0; j < e_el; ++j) T = __fmul_rn(T, sm.fbuf[base + j]);
+        sm.w_all[base + e_el] = __fmul_rn(alpha_el, T);
+      }
+      slot_sync();
+    };
+    auto m3 = [&]() {      // pixels_fea[ray][c] = sum_i w_i * feature_i[c] (pigan_utils.py:255-266), depth, debug outputs
+      const int img = pg.img, ray0 = pg.ray0, n_valid = pg.n_valid;
+      const float* zc = sm.z_c[pg.zbuf];
+      const bool el_ok = g_el < n_valid;
+      const int rc0 = g_el * S;           // first row of ray g_el
+      const int base = g_el * nS;
+      const size_t ro_el = (size_t)img * p.n_rays + ray0 + g_el;
+      (void)ro_el; (void)rc0; (void)base; (void)el_ok; (void)zc; (void)img; (void)ray0;
+      stamp(12);
+      // ---------------- composite: pixels_fea[ray][c] = sum_i w_i * feature_i[c]  (pigan_utils.py:255-266)
+      if (p.last_back || p.white_back) {     // (slot-uniform) the weight sum is only needed for the two background modes
+        if (el_ok && e_el == 0) {    // per ray: weight sum in the reference's order, last_back folded into the last weight
+          float wsum = 0.f;
+#pragma unroll 4
+          for (int i = 0; i < nS; ++i) wsum += sm.w_all[base + i];
+          sm.wsum[g_el] = wsum;
+          if (p.last_back) sm.w_all[base + nS - 1] += 1.f - wsum;
+        }
+        slot_sync();
+      }
+      {
+        const int c = stid & 31;
+        const float* featf = &sm.feat[0][0][0];
+        for (int g = stid >> 5; g < n_valid; g += 8) {      // warp = ray, lane = channel
+          const int b0 = g * nS;
+          float acc = 0.f;
+#pragma unroll 4
+          for (int i = 0; i < nS; ++i) acc = fmaf(sm.w_all[b0 + i], featf[sm.frow[b0 + i] * 33 + c], acc);
+          if (p.white_back) acc += 1.f - sm.wsum[g];
+          const size_t ro = (size_t)img * p.n_rays + ray0 + g;
+          a.io.pixels_fea[ro * kFeat + c] = acc;
+          if (c < nS && (a.io.weights || a.io.dbg_all_z)) {     // lanes cover the nS <= 32 fast case, loop otherwise
+            for (int i = c; i < nS; i += 32) {
+              if (a.io.weights) a.io.weights[ro * nS + i] = sm.w_all[b0 + i];
+              if (a.io.dbg_all_z) a.io.dbg_all_z[ro * nS + i] = sm.skey[b0 + i];
+            }
+          }
+          if (c == 0 && a.io.depth) {
+            float depth = 0.f;
+            for (int i = 0; i < nS; ++i) depth = fmaf(sm.w_all[b0 + i], sm.skey[b0 + i], depth);
+            a.io.depth[ro] = depth;
+          }
+        }
+      }
+      slot_sync();
+      stamp(13);
+    };
     float u_next = jitter_of(0);
 
     for (int it = 0; it < iters; ++it) {
       tr_it = it; tr_ph = 0;
       const float u_cur = u_next;
+      float* const zc = sm.z_c[WARP ? 0 : (it & 1)];
       const int grp = (it * (int)gridDim.x + (int)blockIdx.x) * 2 + sl;
       const bool grp_ok = grp < a.total_groups;
       const int img = grp_ok ? grp / a.groups_per_img : 0;
@@ -435,7 +539,7 @@ __global__ void __launch_bounds__(640, 1) ray_siren_tc_kernel(const KArgs a) {
             const float u = u_cur;
             float z;
             coarse_sample(fr, M, p.ray_start, p.ray_end, S, s_row, u, z, px, py, pz);
-            if (half == 0) sm.z_c[row] = z;
+            if (half == 0) zc[row] = z;
           } else {
             fine_sample(fr, sm.z_f[row], px, py, pz);
           }
@@ -447,6 +551,7 @@ __global__ void __launch_bounds__(640, 1) ray_siren_tc_kernel(const KArgs a) {
         }
         stamp(2);
         signal_a();
+        if (!WARP && pass == 0 && pg.valid) m1();
         // ---------------- E0: D(128) = g0*(W0 p*s + b0) + beta0  ->  sin  ->  A (h0)
         wait_d();
         e_enter();
@@ -477,6 +582,7 @@ __global__ void __launch_bounds__(640, 1) ray_siren_tc_kernel(const KArgs a) {
         stamp(4);
         signal_a(2);         // stage 2: chunk 3
         e_leave();
+        if (!WARP && pass == 0 && pg.valid) m2();
         // ---------------- E1: D(128) -> FiLM+sin -> A (h1); TMEM loads double-buffered
         wait_d();
         e_enter();
@@ -515,6 +621,7 @@ __global__ void __launch_bounds__(640, 1) ray_siren_tc_kernel(const KArgs a) {
         stamp(6);
         signal_a(2);
         e_leave();
+        if (!WARP && pass == 0 && pg.valid) m3();
         // ---------------- E2: D(80): cols 0..63 -> FiLM+sin -> A (h2, K=64); col 64 -> sigma
         wait_d();
         e_enter();
@@ -601,7 +708,7 @@ __global__ void __launch_bounds__(640, 1) ray_siren_tc_kernel(const KArgs a) {
             const bool act = g < n_valid && e < S;
             const int r0 = g * S;
             const size_t ro = (size_t)img * p.n_rays + ray0 + g;
-            const float z = act ? sm.z_c[r0 + e] : 0.f;
+            const float z = act ? zc[r0 + e] : 0.f;
             const float zn = __shfl_down_sync(full, z, 1, 16);
             float alpha = 0.f, f = 1.f;
             if (act) {
@@ -649,7 +756,7 @@ __global__ void __launch_bounds__(640, 1) ray_siren_tc_kernel(const KArgs a) {
           const int r0 = g_row * S;
           float alpha = 0.f;
           if (half == 0 && pt_ok) {   // A: alpha_i and (1 - alpha_i + 1e-10)
-            const float delta = s_row + 1 < S ? __fsub_rn(sm.z_c[row + 1], sm.z_c[row]) : 1e10f;
+            const float delta = s_row + 1 < S ? __fsub_rn(zc[row + 1], zc[row]) : 1e10f;
             const float nz = a.io.noise_c ? __fmul_rn(a.io.noise_c[ro_row * S + s_row], p.noise_std) : 0.f;
             alpha = sample_alpha(delta, sm.sig_c[row], nz, p.clamp_mode);
             sm.fbuf[row] = __fadd_rn(__fsub_rn(1.f, alpha), 1e-10f);
@@ -681,8 +788,8 @@ __global__ void __launch_bounds__(640, 1) ray_siren_tc_kernel(const KArgs a) {
             while (i <= ns && sm.cdf[r0 + i] < uk) ++i;         // searchsorted(cdf, u, right=False)
             const int below = max(i - 1, 0), above = min(i, ns);
             const float cb = sm.cdf[r0 + below], ca = sm.cdf[r0 + above];
-            const float bb = 0.5f * __fadd_rn(sm.z_c[r0 + below], sm.z_c[r0 + below + 1]);
-            const float ba = 0.5f * __fadd_rn(sm.z_c[r0 + above], sm.z_c[r0 + above + 1]);
+            const float bb = 0.5f * __fadd_rn(zc[r0 + below], zc[r0 + below + 1]);
+            const float ba = 0.5f * __fadd_rn(zc[r0 + above], zc[r0 + above + 1]);
             float denom = __fsub_rn(ca, cb);
             if (denom < 1e-5f) denom = 1.f;
             sm.z_f[row] = __fadd_rn(bb, __fmul_rn(__fdiv_rn(__fsub_rn(uk, cb), denom), __fsub_rn(ba, bb)));
@@ -700,7 +807,7 @@ __global__ void __launch_bounds__(640, 1) ray_siren_tc_kernel(const KArgs a) {
           const int rc0 = g * S, base = g * nS, e = lane;
           const bool act = e < nS;
           const size_t ro = (size_t)img * p.n_rays + ray0 + g;
-          const float k = act ? (hier ? (e < S ? sm.z_f[rc0 + e] : sm.z_c[rc0 + e - S]) : sm.z_c[rc0 + e]) : 3.0e38f;
+          const float k = act ? (hier ? (e < S ? sm.z_f[rc0 + e] : zc[rc0 + e - S]) : zc[rc0 + e]) : 3.0e38f;
           int rank = 0;                                   // stable ascending rank (torch.sort over cat([fine, coarse]))
           for (int j = 0; j < nS; ++j) {
             const float kj = __shfl_sync(full, k, j);
@@ -778,80 +885,15 @@ __global__ void __launch_bounds__(640, 1) ray_siren_tc_kernel(const KArgs a) {
         stamp(13);
         continue;
       }
-      const bool el_ok = g_el < n_valid;
-      const int rc0 = g_el * S;           // first row of ray g_el
-      const int base = g_el * nS;
-      const size_t ro_el = (size_t)img * p.n_rays + ray0 + g_el;
-      if (el_ok) {
-        auto key_of = [&](int e) { return hier ? (e < S ? sm.z_f[rc0 + e] : sm.z_c[rc0 + e - S]) : sm.z_c[rc0 + e]; };
-        const float k = key_of(e_el);
-        int rank = 0;
-#pragma unroll 4
-        for (int e = 0; e < nS; ++e) {
-          const float ke = key_of(e);
-          rank += (ke < k || (ke == k && e < e_el)) ? 1 : 0;
-        }
-        const int src = hier ? e_el : S + e_el;
-        sm.skey[base + rank] = k;
-        sm.sidx[base + rank] = src;
-        sm.frow[base + rank] = src < S ? rc0 + src : kRows + rc0 + src - S;
-      }
-      slot_sync();
-      float alpha_el = 0.f;
-      if (el_ok) {       // alpha of sorted position e_el (pigan_utils.py:241-251)
-        const int src = sm.sidx[base + e_el];
-        const float sg = src < S ? sm.sig_f[rc0 + src] : sm.sig_c[rc0 + src - S];
-        const float delta = e_el + 1 < nS ? __fsub_rn(sm.skey[base + e_el + 1], sm.skey[base + e_el]) : 1e10f;
-        const float nz = a.io.noise_f ? __fmul_rn(a.io.noise_f[ro_el * nS + e_el], p.noise_std) : 0.f;
-        alpha_el = sample_alpha(delta, sg, nz, p.clamp_mode);
-        sm.fbuf[base + e_el] = __fadd_rn(__fsub_rn(1.f, alpha_el), 1e-10f);
-      }
-      slot_sync();
-      if (el_ok) {       // transmittance in the reference's cumprod order, weight
-        float T = 1.f;
-#pragma unroll 4
-        for (int j = 0; j < e_el; ++j) T = __fmul_rn(T, sm.fbuf[base + j]);
-        sm.w_all[base + e_el] = __fmul_rn(alpha_el, T);
-      }
-      slot_sync();
-      stamp(12);
-      // ---------------- composite: pixels_fea[ray][c] = sum_i w_i * feature_i[c]  (pigan_utils.py:255-266)
-      if (p.last_back || p.white_back) {     // (slot-uniform) the weight sum is only needed for the two background modes
-        if (el_ok && e_el == 0) {    // per ray: weight sum in the reference's order, last_back folded into the last weight
-          float wsum = 0.f;
-#pragma unroll 4
-          for (int i = 0; i < nS; ++i) wsum += sm.w_all[base + i];
-          sm.wsum[g_el] = wsum;
-          if (p.last_back) sm.w_all[base + nS - 1] += 1.f - wsum;
-        }
-        slot_sync();
-      }
-      {
-        const int c = stid & 31;
-        const float* featf = &sm.feat[0][0][0];
-        for (int g = stid >> 5; g < n_valid; g += 8) {      // warp = ray, lane = channel
-          const int b0 = g * nS;
-          float acc = 0.f;
-#pragma unroll 4
-          for (int i = 0; i < nS; ++i) acc = fmaf(sm.w_all[b0 + i], featf[sm.frow[b0 + i] * 33 + c], acc);
-          if (p.white_back) acc += 1.f - sm.wsum[g];
-          const size_t ro = (size_t)img * p.n_rays + ray0 + g;
-          a.io.pixels_fea[ro * kFeat + c] = acc;
-          if (c < nS && (a.io.weights || a.io.dbg_all_z)) {     // lanes cover the nS <= 32 fast case, loop otherwise
-            for (int i = c; i < nS; i += 32) {
-              if (a.io.weights) a.io.weights[ro * nS + i] = sm.w_all[b0 + i];
-              if (a.io.dbg_all_z) a.io.dbg_all_z[ro * nS + i] = sm.skey[b0 + i];
-            }
-          }
-          if (c == 0 && a.io.depth) {
-            float depth = 0.f;
-            for (int i = 0; i < nS; ++i) depth = fmaf(sm.w_all[b0 + i], sm.skey[b0 + i], depth);
-            a.io.depth[ro] = depth;
-          }
-        }
-      }
-      slot_sync();
-      stamp(13);
+      // MATH 0: the merge + compositing of this group is DEFERRED into the MMA waits of the next group's coarse pass (m1 / m2 / m3
+      // below): it uses neither the tensor pipe nor MUFU nor TMEM, and was 17 % of a group's critical path (r02d trace)
+      pg.valid = grp_ok;
+      pg.img = img; pg.ray0 = ray0; pg.n_valid = n_valid; pg.zbuf = it & 1;
+    }
+    if (!WARP && pg.valid) {      // the last group of this slot
+      m1();
+      m2();
+      m3();
     }
   }
   tc_fence_before();
