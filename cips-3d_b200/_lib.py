@@ -106,12 +106,22 @@ _option_snapshot = {}
 def sync_options(lib):
     snap = tuple(os.environ.get(k) for k in _OPTION_VARS)
     if _option_snapshot.get(id(lib)) != snap:
-        lib.c3d_reload_options()
+        if not isinstance(lib.c3d_reload_options, _Optional):
+            lib.c3d_reload_options()
         _option_snapshot[id(lib)] = snap
+
+
+class _Optional:
+    """argtypes / restype sink for an entry point a library build does not export (A/B builds of older sources, C3D_LIB_PATH)"""
+    argtypes = restype = None
 
 
 def bind(lib):
     """Declare the C-ABI signatures (include/cips3d_b200.h) on a loaded library."""
+    for name in ("c3d_points_linear_workspace_bytes", "c3d_points_linear", "c3d_blur_nhwc", "c3d_reload_options",
+                 "c3d_debug_cips_max_clusters"):
+        if not hasattr(lib, name):
+            setattr(lib, name, _Optional())
     lib.c3d_version.restype = C.c_int
     lib.c3d_last_error.restype = C.c_char_p
     lib.c3d_device_supported.argtypes = [C.c_int]

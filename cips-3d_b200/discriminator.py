@@ -261,10 +261,12 @@ class Discriminator_MultiScale(nn.Module):
         return torch.cat([out, y.repeat(g, 1, h, w)], 1)
 
     # Internal activation layout.  True: channels-last (N, H, W, C in memory) from the stem to the 4x4 head -- the layout the
-    # tensor-core convolutions use natively, so no NCHW <-> NHWC transposes around them (15 % of a config-5 train step,
-    # profiles/r02c); bias_act and the blur keep whatever layout they are given (ops.bias_act, c3d_blur_nhwc).  The module's
-    # contract is unchanged: NCHW-shaped input, (N, 1) output.
-    channels_last = True
+    # tensor-core convolutions use natively; bias_act, the blur and conv2d keep whatever layout they are given (ops.bias_act,
+    # c3d_blur_nhwc).  Measured NEUTRAL on B200 (profiles/r02g_summary.md: cuDNN's own NCHW <-> NHWC transposes, 15 % of a config-5
+    # step, disappear and its kernels get 24 ms faster per 2 steps, but the same time reappears as layout-conversion copies around
+    # the autograd graph and a slower interleaved blur), so the default stays the NCHW layout of the reference.  The module's contract
+    # is the same either way: NCHW-shaped input, (N, 1) output.
+    channels_last = False
 
     def forward(self, input, alpha, summary_ddict=None):
         _require_cuda(input, "Discriminator_MultiScale.forward")
