@@ -16,7 +16,8 @@ __device__ __forceinline__ float bias_act_one(float x, float ref, int act, int g
   return grad == 2 ? 0.f : x;  // act == 1 (linear)
 }
 
-// VEC = 4: size_x % 4 == 0, step_b % 4 == 0 (a float4 never straddles a bias boundary), 16B-aligned
+// VEC = 4: size_x % 4 == 0 and 16B-aligned, and either step_b % 4 == 0 (a float4 never straddles a bias boundary: NCHW planes)
+// or step_b == 1 with size_b % 4 == 0 (channels-last: the four lanes take four consecutive bias entries)
 template <int VEC>
 __global__ void __launch_bounds__(256) bias_act_kernel(const float* __restrict__ x,
                                                        const float* __restrict__ bias,
@@ -30,12 +31,20 @@ __global__ void __launch_bounds__(256) bias_act_kernel(const float* __restrict__
     if (VEC == 4) {
       float4 v = __ldcs(reinterpret_cast<const float4*>(x) + i);
       float4 r = ref ? __ldcs(reinterpret_cast<const float4*>(ref) + i) : make_float4(0, 0, 0, 0);
-      float b = bias ? __ldg(bias + ((i * 4) / step_b) % size_b) : 0.f;
+      float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (bias) {
+        if (step_b == 1) {
+          b4 = __ldg(reinterpret_cast<const float4*>(bias + (i * 4) % size_b));
+        } else {
+          const float b = __ldg(bias + ((i * 4) / step_b) % size_b);
+          b4 = make_float4(b, b, b, b);
+        }
+      }
       float4 o;
-      o.x = bias_act_one(v.x + b, r.x, act, grad, alpha) * scale;
-      o.y = bias_act_one(v.y + b, r.y, act, grad, alpha) * scale;
-      o.z = bias_act_one(v.z + b, r.z, act, grad, alpha) * scale;
-      o.w = bias_act_one(v.w + b, r.w, act, grad, alpha) * scale;
+      o.x = bias_act_one(v.x + b4.x, r.x, act, grad, alpha) * scale;
+      o.y = bias_act_one(v.y + b4.y, r.y, act, grad, alpha) * scale;
+      o.z = bias_act_one(v.z + b4.z, r.z, act, grad, alpha) * scale;
+      o.w = bias_act_one(v.w + b4.w, r.w, act, grad, alpha) * scale;
       __stcs(reinterpret_cast<float4*>(y) + i, o);
     } else {
       float b = bias ? __ldg(bias + (i / step_b) % size_b) : 0.f;
@@ -370,8 +379,8 @@ extern "C" int c3d_bias_act(const float* x, const float* bias, const float* ref,
   C3D_CHECK_ARG(grad != 1 || ref, "bias_act: grad=1 needs ref");
   if (size_x == 0) return C3D_OK;
   cudaStream_t st = (cudaStream_t)stream;
-  bool vec = size_x % 4 == 0 && (!bias || step_b % 4 == 0) && ((uintptr_t)x % 16 == 0) &&
-             ((uintptr_t)y % 16 == 0) && (!ref || (uintptr_t)ref % 16 == 0);
+  bool vec = size_x % 4 == 0 && (!bias || step_b % 4 == 0 || (step_b == 1 && size_b % 4 == 0 && (uintptr_t)bias % 16 == 0)) &&
+             ((uintptr_t)x % 16 == 0) && ((uintptr_t)y % 16 == 0) && (!ref || (uintptr_t)ref % 16 == 0);
   int dev = 0;
   cudaGetDevice(&dev);
   const int sms = c3d_device_sm_count(dev);

@@ -98,6 +98,7 @@ struct KArgs {
   const float* w_sigma;       // (128) final_layer weight, fp32 (MATH = 2 only: sigma head in the E1 epilogue)
   int stagger_ns;             // A/B knob: slot 1 starts this much later than slot 0
   int e_turn;                 // serialise the sine epilogues of the two slots (Smem::e_owner)
+  int sched;                  // 0: one polling issuer, whole-layer MMA batches; 1: one blocking issuer per slot, staged issue
 };
 
 __device__ __forceinline__ float fast_sin(float x) { return __sinf(x); }
@@ -228,8 +229,62 @@ __global__ void __launch_bounds__(640, 1) ray_siren_tc_kernel(const KArgs a) {
         mbar_arrive_expect_tx(&s.w_full, kWBlobBytes);
         for (int off = 0; off < kWBlobBytes; off += 16384) bulk_g2s(s.w + off, a.wblob + off, 16384, &s.w_full);
       }
-    } else if (warp == 1 || warp == 3) {
-      // ---------------------------------------------------------- MMA issuers: one warp PER SLOT (warp 1 -> slot 0, warp 3 ->
+    } else if (warp == 1 && a.sched == 0) {
+      // ---------------------------------------------------------- scheduling form 0 (default): ONE issuer polls both slots
+      // (test_wait + a short sleep) and issues a whole layer's MMAs per hand-off.  Same-box A/B (profiles/r02i_ray_variants.txt):
+      // 7.37-7.45 ms for this form against 8.37-8.40 ms for form 1 below -- the poll's granularity keeps the two slots out of
+      // phase (one slot's MMAs under the other's epilogue), while two symmetric blocking issuers lock the slots in step.
+      mbar_wait(&s.w_full, 0);
+      const uint32_t wb = smem_u32(s.w);
+      const uint32_t dhi = umma_desc_hi(128);
+      const uint32_t w1h = umma_desc_lo(wb + kOffW1h, 128 * 16), w1l = umma_desc_lo(wb + kOffW1l, 128 * 16);
+      const uint32_t w2h = umma_desc_lo(wb + kOffW2h, kNc * 16), w2l = umma_desc_lo(wb + kOffW2l, kNc * 16);
+      const uint32_t w3h = umma_desc_lo(wb + kOffW3h, 32 * 16), w3l = umma_desc_lo(wb + kOffW3l, 32 * 16);
+      uint32_t par[2] = {0, 0};      // bit j = parity of a_ready[sl][j]
+      int done[2] = {0, 0};
+      int tr_n = 0;
+      (void)tr_n;
+      const int total = iters * mma_phases;
+      uint32_t idle = 0;
+      unsigned long long idle_t0 = 0;
+      while (done[0] < total || done[1] < total) {
+        if ((++idle & 0xFFFFu) == 0 && (idle_t0 == 0 ? (idle_t0 = c3d_globaltimer(), false)
+                                                      : c3d_globaltimer() - idle_t0 > C3D_WATCHDOG_NS)) {
+          if (lane == 0) printf("c3d watchdog: ray MMA issuer starved (block %d, done %d/%d of %d)\n", (int)blockIdx.x, done[0], done[1], total);
+          __trap();
+        }
+#pragma unroll
+        for (int sl = 0; sl < 2; ++sl) {
+          if (done[sl] >= total) continue;
+          const int layer = FOLD ? done[sl] % 3 : (done[sl] & 3);
+          // the workers signal a layer ONCE in this form, on the barrier their last stage uses (0: positions, 2: K = 128 layers, 1: K = 64)
+          const int bar = layer == 0 ? 0 : (layer == 3 ? 1 : 2);
+          if (!__all_sync(0xffffffffu, mbar_test(&s.a_ready[sl][bar], (par[sl] >> bar) & 1u))) continue;
+          par[sl] ^= 1u << bar;
+          tc_fence_after();
+          if (lane == 0) RTRACE(done[sl] / mma_phases, 1, (uint32_t)(sl << 15 | ((done[sl] / mma_phases) & 1) << 8 | (done[sl] % mma_phases)));
+          if (elect_one()) {
+            uint32_t a_hi = tmem + (uint32_t)(sl * 256), a_lo = a_hi + 64;
+            const uint32_t d = a_hi + 128;
+            const uint32_t w0h = umma_desc_lo(smem_u32(s.slot[sl].w0), 128 * 16);
+            uint32_t bh = layer == 0 ? w0h : (layer == 1 ? w1h : (layer == 2 ? w2h : w3h));
+            uint32_t bl = layer == 0 ? w0h + (kW0Bytes >> 4) : (layer == 1 ? w1l : (layer == 2 ? w2l : w3l));
+            asm volatile("" : "+r"(bh), "+r"(bl), "+r"(a_hi), "+r"(a_lo));
+            if (layer == 0) mma_split3<128, 16>(d, a_hi, a_lo, bh, bl, dhi);
+            else if (layer == 1) mma_split3<128, 128>(d, a_hi, a_lo, bh, bl, dhi);
+            else if (layer == 2) mma_split3<kNc, 128>(d, a_hi, a_lo, bh, bl, dhi);
+            else if (!FOLD) mma_split3<32, 64>(d, a_hi, a_lo, bh, bl, dhi);
+            tc_commit(&s.d_ready[sl]);
+          }
+          __syncwarp();
+          ++done[sl];
+          idle = 0;
+          idle_t0 = 0;
+        }
+        if (idle) __nanosleep(64);   // nothing ready: yield the issue port to the workers on this scheduler
+      }
+    } else if ((warp == 1 || warp == 3) && a.sched == 1) {
+      // ---------------------------------------------------------- scheduling form 1 (C3D_RAY_SCHED=1): one issuer warp PER SLOT (warp 1 -> slot 0, warp 3 ->
       // slot 1), each blocking on its slot's a_ready barrier (hardware-suspended try_wait).  Round 1 had ONE issuer polling
       // both slots with test_wait + __nanosleep(64): the r02b trace (profiles/r02b_ray_trace.md) showed 1.0-1.3 k clk between
       // the last worker's arrive and the MMA issue -- the sleep granularity, eight times per ray group and slot (a fifth of
@@ -318,7 +373,8 @@ __global__ void __launch_bounds__(640, 1) ray_siren_tc_kernel(const KArgs a) {
     const int bar_id = 1 + sl;
     auto slot_sync = [&]() { named_bar_sync_n<256>(bar_id); };
     uint32_t dpar = 0;
-    auto signal_a = [&](int stage = 0) {
+    auto signal_a = [&](int stage = 0, bool early = false) {      // early: a stage signal that only scheduling form 1 uses
+      if (early && a.sched == 0) return;
       tc_wait_st();
       tc_fence_before();
       __syncwarp();
@@ -573,10 +629,15 @@ __global__ void __launch_bounds__(640, 1) ray_siren_tc_kernel(const KArgs a) {
           e0(accB, 16);
           tc_wait_ld();
           tmem_ld16(dcol + (uint32_t)(half * 64 + 48), accB);
-          tc_wait_ld();      // this thread's 64 accumulator columns are out of D
-          signal_a(0);       // stage 0: K-chunks 0, 1 of both halves written, D drained -> layer 1's MMAs start underneath
-          e0(accA, 32);
-          signal_a(1);       // stage 1: chunk 2
+          if (a.sched == 1) {
+            tc_wait_ld();      // this thread's 64 accumulator columns are out of D
+            signal_a(0, true); // stage 0: K-chunks 0, 1 of both halves written, D drained -> layer 1's MMAs start underneath
+            e0(accA, 32);
+            signal_a(1, true); // stage 1: chunk 2
+          } else {
+            e0(accA, 32);      // form 0: the last load's latency hides under this chunk
+            tc_wait_ld();
+          }
           e0(accB, 48);
         }
         stamp(4);
@@ -609,10 +670,15 @@ __global__ void __launch_bounds__(640, 1) ray_siren_tc_kernel(const KArgs a) {
           e1(accB, 16);
           tc_wait_ld();
           tmem_ld16(dcol + (uint32_t)(half * 64 + 48), accB);
-          tc_wait_ld();
-          signal_a(0);       // stage 0 of the colour / sigma MMA (see the issuer)
-          e1(accA, 32);
-          signal_a(1);       // stage 1
+          if (a.sched == 1) {
+            tc_wait_ld();
+            signal_a(0, true); // stage 0 of the colour / sigma MMA (see the issuer)
+            e1(accA, 32);
+            signal_a(1, true); // stage 1
+          } else {
+            e1(accA, 32);
+            tc_wait_ld();
+          }
           e1(accB, 48);
           // partial sums of the two column halves, per pass; combined where sigma is used, i.e. after the slot-wide barrier
           // that ends the pass (fbuf / w_all are free in the warp-math forms)
@@ -670,7 +736,7 @@ __global__ void __launch_bounds__(640, 1) ray_siren_tc_kernel(const KArgs a) {
             (pass == 0 ? sm.sig_c : sm.sig_f)[row] = sigma;
           }
           e2(accA, 0);
-          signal_a(0);       // stage 0 of the K = 64 colour-linear MMA: k-steps {0, 2}
+          signal_a(0, true); // stage 0 of the K = 64 colour-linear MMA: k-steps {0, 2}
           e2(accB, 16);
         }
         if (!FOLD) {
@@ -1015,6 +1081,7 @@ int c3d_ray_siren_fwd_tc(const C3dRayParams* p, const C3dSirenWeights* w, const 
   ka.w_sigma = w->w_sigma;
   ka.stagger_ns = c3d_options().ray_stagger_ns;
   ka.e_turn = c3d_options().ray_e_turn;
+  ka.sched = c3d_options().ray_sched;
   const size_t smem = sizeof(Smem) + 1024;
   static std::atomic<unsigned long long> attr_set{0};     // per device, once
   if (!(attr_set.load() >> (dev & 63) & 1ull)) {
