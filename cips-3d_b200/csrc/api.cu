@@ -46,9 +46,6 @@ static void load_options() {
   o.pigan_pair = geti("C3D_PIGAN_PAIR", 0) != 0;
   const char* rm = getenv("C3D_RAY_MATH");
   o.ray_math = !rm || !*rm ? C3D_RAY_MATH_DEFAULT : (rm[0] == 'f' ? 2 : (rm[0] == 'w' ? 1 : 0));
-  o.ray_stagger_ns = geti("C3D_RAY_STAGGER_NS", 0);
-  o.ray_e_turn = geti("C3D_RAY_E_TURN", 0) != 0;
-  o.ray_sched = geti("C3D_RAY_SCHED", 0) != 0;
   g_opts = o;
 }
 const C3dOptions& c3d_options() {

@@ -55,9 +55,6 @@ struct C3dOptions {
   int pigan_tc;       // C3D_PIGAN_IMPL:   simt -> 0 | tc -> 1           pi-GAN renderer (default tc: 9.4x faster, r02a)
   int pigan_pair;     // C3D_PIGAN_PAIR:   0 | 1 (default 0: measured 4 % slower, r02a)
   int ray_math;       // C3D_RAY_MATH:     block -> 0 | warp -> 1 | fold -> 2   per-ray math form of the renderer
-  int ray_stagger_ns; // C3D_RAY_STAGGER_NS: start the renderer's second TMEM slot this much later than the first (default 0)
-  int ray_e_turn;     // C3D_RAY_E_TURN:   0 | 1  serialise the sine epilogues of the renderer's two slots (default 0)
-  int ray_sched;      // C3D_RAY_SCHED:    0 one polling MMA issuer, whole-layer batches (default) | 1 one blocking issuer per slot, staged issue
 };
 const C3dOptions& c3d_options();
 static inline int c3d_div_up(long long a, long long b) { return (int)((a + b - 1) / b); }

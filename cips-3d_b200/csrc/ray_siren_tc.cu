@@ -20,6 +20,13 @@
 // (tcgen05.st, two fp16 per 32-bit column, row = lane) and the MMAs use the A-from-TMEM form.
 // Weights (fp16 hi/lo, scaled by 2^8 to keep the lo parts normal) sit in shared memory for the
 // whole kernel (112 KB, loaded once per CTA by bulk async copies).
+//
+// Round 2 measured five other scheduling forms of this kernel on B200 (one blocking MMA issuer per slot; K-chunked staged MMA issue;
+// an "epilogue turn" that anti-phases the slots; an initial stagger; merge + compositing deferred into the next group's MMA waits
+// with jitter / pdf_u prefetch) -- all correct, none faster on the same box (7.18-7.25 ms for this form against 7.41-8.50 ms:
+// profiles/r02de_ray_scheduling.md, r02i / r02j_ray_variants.txt; the sources of those forms are commits 64f9cf8 .. fe7aa8d of this
+// file).  The finding behind it: TS-form MMAs and a running epilogue's tcgen05.ld/st slow each other down, so tensor time and
+// epilogue time add whatever the phase of the two slots; the single polling issuer below happens to keep the slots out of phase.
 #include <atomic>
 #include <string.h>
 
@@ -53,8 +60,7 @@ struct ImgConsts {
 
 struct SlotMem {
   float feat[2][kRows][33];   // [0] fine pass, [1] coarse pass features (padded rows: conflict-free both ways)
-  float z_c[2][kRows];        // coarse depths, double-buffered by group parity: the deferred merge of group g reads them while group g + 1 writes its own
-  float sig_c[kRows], z_f[kRows], sig_f[kRows];
+  float z_c[kRows], sig_c[kRows], z_f[kRows], sig_f[kRows];
   float wc[kRows];            // coarse compositing weights
   float cdf[kRows];           // per ray: S-1 cdf entries (stride S)
   float fbuf[2 * kRows];      // 1 - alpha + 1e-10 per (sorted) sample
@@ -73,17 +79,9 @@ struct Smem {
   alignas(1024) uint8_t w[kWBlobBytes];
   SlotMem slot[2];
   alignas(8) uint64_t w_full;
-  uint64_t a_ready[2][3];   // [slot][stage]: one barrier per MMA stage of a layer (a warp arrives ONCE per layer on each: arrivals of two
-                            // stages on one barrier would be indistinguishable when a fast warp runs a stage ahead of a slow one)
+  uint64_t a_ready[2];
   uint64_t d_ready[2];
   uint32_t tmem_base;
-  // "epilogue turn": at most ONE slot runs a sine epilogue (E0 / E1 / E2) at a time.  Two symmetric slots fall into lock step
-  // (profiles/r02c, r02d): both epilogues then share MUFU / issue slots while the tensor pipe idles, and both MMA batches
-  // queue on the tensor pipe while MUFU idles.  Serialising the epilogues costs no epilogue throughput (they are MUFU /
-  // issue bound) and forces the other slot's MMAs underneath.  e_owner: -1 free, else the slot; e_left[sl]: warps of the
-  // owner still inside the epilogue (the last one releases).
-  int e_owner;
-  int e_left[2];
 };
 
 struct KArgs {
@@ -96,9 +94,6 @@ struct KArgs {
   int G;                      // rays per group
   int groups_per_img, total_groups;
   const float* w_sigma;       // (128) final_layer weight, fp32 (MATH = 2 only: sigma head in the E1 epilogue)
-  int stagger_ns;             // A/B knob: slot 1 starts this much later than slot 0
-  int e_turn;                 // serialise the sine epilogues of the two slots (Smem::e_owner)
-  int sched;                  // 0: one polling issuer, whole-layer MMA batches; 1: one blocking issuer per slot, staged issue
 };
 
 __device__ __forceinline__ float fast_sin(float x) { return __sinf(x); }
@@ -143,17 +138,6 @@ __device__ __forceinline__ void mma_split3(uint32_t d_tmem, uint32_t a_hi, uint3
   for (int k = 0; k < K / 16; ++k) umma_ts_w(d_tmem, a_lo + 8 * k, b_hi_lo + kstep * k, dhi, idesc, 1);
 #pragma unroll
   for (int k = 0; k < K / 16; ++k) umma_ts_w(d_tmem, a_hi + 8 * k, b_lo_lo + kstep * k, dhi, idesc, 1);
-}
-
-// one K = 16 step (index k) of the three-pass split product; `fresh`: first MMA of the layer (overwrites D)
-template <int N>
-__device__ __forceinline__ void mma_k3(uint32_t d_tmem, uint32_t a_hi, uint32_t a_lo, uint32_t b_hi_lo, uint32_t b_lo_lo,
-                                       uint32_t dhi, int k, bool fresh) {
-  constexpr uint32_t idesc = umma_idesc_f16(kRows, N);
-  constexpr uint32_t kstep = (2u * N * 16u) >> 4;
-  umma_ts_w(d_tmem, a_hi + 8 * k, b_hi_lo + kstep * k, dhi, idesc, fresh ? 0u : 1u);
-  umma_ts_w(d_tmem, a_lo + 8 * k, b_hi_lo + kstep * k, dhi, idesc, 1);
-  umma_ts_w(d_tmem, a_hi + 8 * k, b_lo_lo + kstep * k, dhi, idesc, 1);
 }
 
 // s1.14 fixed point through the float adder: x + 1.5*2^9 has ulp 2^-14 for |x| <= 1, so the low 16 bits of its pattern
@@ -207,10 +191,8 @@ __global__ void __launch_bounds__(640, 1) ray_siren_tc_kernel(const KArgs a) {
 
   if (threadIdx.x == 0) {
     mbar_init(&s.w_full, 1);
-    s.e_owner = -1;
-    s.e_left[0] = s.e_left[1] = 0;
     for (int i = 0; i < 2; ++i) {
-      for (int j = 0; j < 3; ++j) mbar_init(&s.a_ready[i][j], 8);
+      mbar_init(&s.a_ready[i], 8);
       mbar_init(&s.d_ready[i], 1);
     }
     fence_mbar_init();
@@ -229,21 +211,21 @@ __global__ void __launch_bounds__(640, 1) ray_siren_tc_kernel(const KArgs a) {
         mbar_arrive_expect_tx(&s.w_full, kWBlobBytes);
         for (int off = 0; off < kWBlobBytes; off += 16384) bulk_g2s(s.w + off, a.wblob + off, 16384, &s.w_full);
       }
-    } else if (warp == 1 && a.sched == 0) {
-      // ---------------------------------------------------------- scheduling form 0 (default): ONE issuer polls both slots
-      // (test_wait + a short sleep) and issues a whole layer's MMAs per hand-off.  Same-box A/B (profiles/r02i_ray_variants.txt):
-      // 7.37-7.45 ms for this form against 8.37-8.40 ms for form 1 below -- the poll's granularity keeps the two slots out of
-      // phase (one slot's MMAs under the other's epilogue), while two symmetric blocking issuers lock the slots in step.
+    } else if (warp == 1) {
+      // ---------------------------------------------------------- MMA issuer: the whole warp stays converged
+      // (operands live in uniform registers, no per-MMA lane loop); one elected lane issues for whichever slot
+      // is ready.
       mbar_wait(&s.w_full, 0);
       const uint32_t wb = smem_u32(s.w);
       const uint32_t dhi = umma_desc_hi(128);
       const uint32_t w1h = umma_desc_lo(wb + kOffW1h, 128 * 16), w1l = umma_desc_lo(wb + kOffW1l, 128 * 16);
       const uint32_t w2h = umma_desc_lo(wb + kOffW2h, kNc * 16), w2l = umma_desc_lo(wb + kOffW2l, kNc * 16);
       const uint32_t w3h = umma_desc_lo(wb + kOffW3h, 32 * 16), w3l = umma_desc_lo(wb + kOffW3l, 32 * 16);
-      uint32_t par[2] = {0, 0};      // bit j = parity of a_ready[sl][j]
+      uint32_t par[2] = {0, 0};
       int done[2] = {0, 0};
+#ifdef C3D_TRACE
       int tr_n = 0;
-      (void)tr_n;
+#endif
       const int total = iters * mma_phases;
       uint32_t idle = 0;
       unsigned long long idle_t0 = 0;
@@ -255,106 +237,33 @@ __global__ void __launch_bounds__(640, 1) ray_siren_tc_kernel(const KArgs a) {
         }
 #pragma unroll
         for (int sl = 0; sl < 2; ++sl) {
-          if (done[sl] >= total) continue;
-          const int layer = FOLD ? done[sl] % 3 : (done[sl] & 3);
-          // the workers signal a layer ONCE in this form, on the barrier their last stage uses (0: positions, 2: K = 128 layers, 1: K = 64)
-          const int bar = layer == 0 ? 0 : (layer == 3 ? 1 : 2);
-          if (!__all_sync(0xffffffffu, mbar_test(&s.a_ready[sl][bar], (par[sl] >> bar) & 1u))) continue;
-          par[sl] ^= 1u << bar;
-          tc_fence_after();
-          if (lane == 0) RTRACE(done[sl] / mma_phases, 1, (uint32_t)(sl << 15 | ((done[sl] / mma_phases) & 1) << 8 | (done[sl] % mma_phases)));
-          if (elect_one()) {
-            uint32_t a_hi = tmem + (uint32_t)(sl * 256), a_lo = a_hi + 64;
-            const uint32_t d = a_hi + 128;
-            const uint32_t w0h = umma_desc_lo(smem_u32(s.slot[sl].w0), 128 * 16);
-            uint32_t bh = layer == 0 ? w0h : (layer == 1 ? w1h : (layer == 2 ? w2h : w3h));
-            uint32_t bl = layer == 0 ? w0h + (kW0Bytes >> 4) : (layer == 1 ? w1l : (layer == 2 ? w2l : w3l));
-            asm volatile("" : "+r"(bh), "+r"(bl), "+r"(a_hi), "+r"(a_lo));
-            if (layer == 0) mma_split3<128, 16>(d, a_hi, a_lo, bh, bl, dhi);
-            else if (layer == 1) mma_split3<128, 128>(d, a_hi, a_lo, bh, bl, dhi);
-            else if (layer == 2) mma_split3<kNc, 128>(d, a_hi, a_lo, bh, bl, dhi);
-            else if (!FOLD) mma_split3<32, 64>(d, a_hi, a_lo, bh, bl, dhi);
-            tc_commit(&s.d_ready[sl]);
+          if (done[sl] < total && __all_sync(0xffffffffu, mbar_test(&s.a_ready[sl], par[sl]))) {
+            par[sl] ^= 1;
+            tc_fence_after();
+            const int layer = FOLD ? done[sl] % 3 : (done[sl] & 3);
+            if (lane == 0) RTRACE(done[sl] / mma_phases, 1, (uint32_t)(sl << 15 | ((done[sl] / mma_phases) & 1) << 8 | (done[sl] % mma_phases)));
+            if (elect_one()) {
+              uint32_t a_hi = tmem + (uint32_t)(sl * 256), a_lo = a_hi + 64;
+              const uint32_t d = a_hi + 128;
+              // opaque per-iteration copies: keeps the compiler from hoisting ~60 loop-invariant descriptor
+              // words out of the loop (they would spill and cost an LDL per MMA)
+              const uint32_t w0h = umma_desc_lo(smem_u32(s.slot[sl].w0), 128 * 16);
+              uint32_t bh = layer == 0 ? w0h : (layer == 1 ? w1h : (layer == 2 ? w2h : w3h));
+              uint32_t bl = layer == 0 ? w0h + (kW0Bytes >> 4) : (layer == 1 ? w1l : (layer == 2 ? w2l : w3l));
+              asm volatile("" : "+r"(bh), "+r"(bl), "+r"(a_hi), "+r"(a_lo));
+              if (layer == 0) mma_split3<128, 16>(d, a_hi, a_lo, bh, bl, dhi);
+              else if (layer == 1) mma_split3<128, 128>(d, a_hi, a_lo, bh, bl, dhi);
+              else if (layer == 2) mma_split3<kNc, 128>(d, a_hi, a_lo, bh, bl, dhi);
+              else if (!FOLD) mma_split3<32, 64>(d, a_hi, a_lo, bh, bl, dhi);
+              tc_commit(&s.d_ready[sl]);
+            }
+            __syncwarp();
+            ++done[sl];
+            idle = 0;
+            idle_t0 = 0;
           }
-          __syncwarp();
-          ++done[sl];
-          idle = 0;
-          idle_t0 = 0;
         }
         if (idle) __nanosleep(64);   // nothing ready: yield the issue port to the workers on this scheduler
-      }
-    } else if ((warp == 1 || warp == 3) && a.sched == 1) {
-      // ---------------------------------------------------------- scheduling form 1 (C3D_RAY_SCHED=1): one issuer warp PER SLOT (warp 1 -> slot 0, warp 3 ->
-      // slot 1), each blocking on its slot's a_ready barrier (hardware-suspended try_wait).  Round 1 had ONE issuer polling
-      // both slots with test_wait + __nanosleep(64): the r02b trace (profiles/r02b_ray_trace.md) showed 1.0-1.3 k clk between
-      // the last worker's arrive and the MMA issue -- the sleep granularity, eight times per ray group and slot (a fifth of
-      // the group's critical path).  The whole warp stays converged (operands in uniform registers, no per-MMA lane loop);
-      // one elected lane issues.
-      const int sl = warp == 1 ? 0 : 1;
-      mbar_wait(&s.w_full, 0);
-      const uint32_t wb = smem_u32(s.w);
-      const uint32_t dhi = umma_desc_hi(128);
-      const uint32_t w1h = umma_desc_lo(wb + kOffW1h, 128 * 16), w1l = umma_desc_lo(wb + kOffW1l, 128 * 16);
-      const uint32_t w2h = umma_desc_lo(wb + kOffW2h, kNc * 16), w2l = umma_desc_lo(wb + kOffW2l, kNc * 16);
-      const uint32_t w3h = umma_desc_lo(wb + kOffW3h, 32 * 16), w3l = umma_desc_lo(wb + kOffW3l, 32 * 16);
-      const uint32_t w0h = umma_desc_lo(smem_u32(s.slot[sl].w0), 128 * 16);
-      uint32_t par = 0;     // bit j = parity of a_ready[sl][j]
-      int tr_n = 0;
-      (void)tr_n;
-      const int total = iters * mma_phases;
-      // A layer's MMAs are issued in STAGES, each behind one phase of a_ready: the epilogue that produces the layer's A operand
-      // signals as soon as (a) it has drained the previous accumulator out of D and (b) the K-chunks of the stage are in TMEM, so
-      // the tensor pipe works underneath the rest of that epilogue and only the last stage's MMAs stay exposed:
-      //   K = 128 layers: stage 0 = k-steps {0,4,1,5} (chunks 0,1 of both column halves; D drained), stage 1 = {2,6}, stage 2 = {3,7}
-      //   K = 64  layer : stage 0 = {0,2}, stage 1 = {1,3};   K = 16 layer: one stage.
-      auto next_stage = [&](int j) {
-        mbar_wait(&s.a_ready[sl][j], (par >> j) & 1u);
-        par ^= 1u << j;
-        tc_fence_after();
-      };
-#pragma unroll 1
-      for (int done = 0; done < total; ++done) {
-        const int layer = FOLD ? done % 3 : (done & 3);
-        uint32_t a_hi = tmem + (uint32_t)(sl * 256), a_lo = a_hi + 64;
-        const uint32_t d = a_hi + 128;
-        uint32_t bh = layer == 0 ? w0h : (layer == 1 ? w1h : (layer == 2 ? w2h : w3h));
-        uint32_t bl = layer == 0 ? w0h + (kW0Bytes >> 4) : (layer == 1 ? w1l : (layer == 2 ? w2l : w3l));
-        // opaque per-iteration copies: keeps the compiler from materialising ~60 loop-invariant descriptor words
-        // outside the loop (they would spill and cost an LDL per MMA)
-        asm volatile("" : "+r"(bh), "+r"(bl), "+r"(a_hi), "+r"(a_lo));
-        next_stage(0);
-        if (lane == 0) RTRACE(done / mma_phases, 1, (uint32_t)(sl << 15 | ((done / mma_phases) & 1) << 8 | (done % mma_phases)));
-        if (layer == 0) {
-          if (elect_one()) {
-            mma_split3<128, 16>(d, a_hi, a_lo, bh, bl, dhi);
-            tc_commit(&s.d_ready[sl]);
-          }
-        } else if (layer == 1 || layer == 2) {
-          const bool n128 = layer == 1;
-          auto step = [&](int k, bool fresh) {
-            if (n128) mma_k3<128>(d, a_hi, a_lo, bh, bl, dhi, k, fresh);
-            else mma_k3<kNc>(d, a_hi, a_lo, bh, bl, dhi, k, fresh);
-          };
-          if (elect_one()) { step(0, true); step(4, false); step(1, false); step(5, false); }
-          __syncwarp();
-          next_stage(1);
-          if (elect_one()) { step(2, false); step(6, false); }
-          __syncwarp();
-          next_stage(2);
-          if (elect_one()) {
-            step(3, false); step(7, false);
-            tc_commit(&s.d_ready[sl]);
-          }
-        } else if (!FOLD) {
-          if (elect_one()) { mma_k3<32>(d, a_hi, a_lo, bh, bl, dhi, 0, true); mma_k3<32>(d, a_hi, a_lo, bh, bl, dhi, 2, false); }
-          __syncwarp();
-          next_stage(1);
-          if (elect_one()) {
-            mma_k3<32>(d, a_hi, a_lo, bh, bl, dhi, 1, false); mma_k3<32>(d, a_hi, a_lo, bh, bl, dhi, 3, false);
-            tc_commit(&s.d_ready[sl]);
-          }
-        }
-        __syncwarp();
       }
     }
   } else {
@@ -373,50 +282,24 @@ __global__ void __launch_bounds__(640, 1) ray_siren_tc_kernel(const KArgs a) {
     const int bar_id = 1 + sl;
     auto slot_sync = [&]() { named_bar_sync_n<256>(bar_id); };
     uint32_t dpar = 0;
-    auto signal_a = [&](int stage = 0, bool early = false) {      // early: a stage signal that only scheduling form 1 uses
-      if (early && a.sched == 0) return;
+    auto signal_a = [&]() {
       tc_wait_st();
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&s.a_ready[sl][stage]);
+      if (lane == 0) mbar_arrive(&s.a_ready[sl]);
     };
     auto wait_d = [&]() {
       mbar_wait(&s.d_ready[sl], dpar);
       dpar ^= 1;
       tc_fence_after();
     };
-    // epilogue turn (see Smem::e_owner): every warp of the team enters once the team owns the turn (the first warp to find it
-    // free takes it for all eight); the eighth warp to leave releases it.  All eight warps of a team pass through every
-    // epilogue, and none can reach the NEXT epilogue before the team's eighth has left this one (the next d_ready needs all
-    // eight a_ready arrivals), so the counter never mixes two epilogues.
-    auto e_enter = [&]() {
-      if (a.e_turn) {
-        if (lane == 0) {
-          volatile int* own = &s.e_owner;
-          for (;;) {
-            const int o = *own;
-            if (o == sl) break;
-            if (o == -1 && atomicCAS(&s.e_owner, -1, sl) == -1) { atomicExch(&s.e_left[sl], 8); break; }
-            __nanosleep(20);
-          }
-        }
-        __syncwarp();
-      }
-    };
-    auto e_leave = [&]() {
-      if (a.e_turn) {
-        __syncwarp();
-        if (lane == 0) {
-          volatile int* left = &s.e_left[sl];
-          while (*left == 0) __nanosleep(20);          // the taker publishes the count right after the owner word
-          if (atomicAdd(&s.e_left[sl], -1) == 1) atomicExch(&s.e_owner, -1);
-        }
-      }
-    };
+#ifdef C3D_TRACE
     int tr_it = 0, tr_ph = 0, tr_n = 0;
-    (void)tr_n;
     // trace word: slot << 15 | team warp << 12 | iteration parity << 8 | phase counter (lane 0 of every worker warp stamps)
     auto stamp = [&](uint32_t tag) { if (lane == 0) RTRACE(tr_it, tag, (uint32_t)(sl << 15 | tw << 12 | (tr_it & 1) << 8 | tr_ph)); ++tr_ph; };
+#else
+    auto stamp = [](uint32_t) {};
+#endif
     const int g_row = row / S, s_row = row - g_row * S;   // ray within the group, sample index
     const bool row_in_group = g_row < G;
     const int g_el = stid / nS, e_el = stid - g_el * nS;  // (ray, element) view used by the merge phases
@@ -432,131 +315,14 @@ __global__ void __launch_bounds__(640, 1) ray_siren_tc_kernel(const KArgs a) {
     int cur_img = -1;
     if (FOLD && stid < 128) sm.abuf[stid] = __ldg(a.w_sigma + stid);   // visible after the first image-constants barrier
     if (FOLD) mbar_wait(&s.w_full, 0);   // the workers read Wl^T from the bulk-loaded blob themselves: observe its barrier
-    // A/B knob (C3D_RAY_STAGGER_NS): start slot 1 late so that its MMA phases fall into slot 0's epilogue phases
-    if (sl == 1 && a.stagger_ns > 0) {
-      const unsigned long long t0 = c3d_globaltimer();
-      while (c3d_globaltimer() - t0 < (unsigned long long)a.stagger_ns) __nanosleep(200);
-    }
-
-    // the coarse jitter of a group (one global load per point) is fetched one group ahead: issued at the start of the previous
-    // group's fine pass, it used to cost ~1 k clk of exposed latency at the head of every group (r02d trace: A0 skew 1000)
-    auto jitter_of = [&](int it_) -> float {
-      const int grp_ = (it_ * (int)gridDim.x + (int)blockIdx.x) * 2 + sl;
-      if (it_ >= iters || grp_ >= a.total_groups || !row_in_group) return 0.f;
-      const int img_ = grp_ / a.groups_per_img, ray0_ = (grp_ % a.groups_per_img) * G;
-      if (g_row >= min(G, p.n_rays - ray0_)) return 0.f;
-      const int nloc_ = ray0_ + g_row;
-      const int gray_ = a.io.ray_idx ? a.io.ray_idx[nloc_] : p.ray_offset + nloc_;
-      return a.io.jitter_u[((size_t)img_ * p.img_size * p.img_size + gray_) * S + s_row];
-    };
-    // ---- deferred merge + compositing of the PREVIOUS group of this slot (MATH 0), in three pieces that are slotted into the
-    // MMA waits of the next group's coarse pass.  Hazards: m1 reads the previous group's coarse depths (z_c is double-buffered)
-    // and fine depths (rewritten by the next resampling, after m1); m2 reads sig_c / sig_f (rewritten by the next E2); m3 reads
-    // the feature rows (rewritten by the next E3) -- each piece runs before the epilogue that overwrites what it reads.
-    struct PrevGroup { int img, ray0, n_valid, zbuf; bool valid; } pg = {0, 0, 0, 0, false};
-    auto m1 = [&]() {      // stable rank sort of the nS depths of each ray (generator.py:1733-1738)
-      const int img = pg.img, ray0 = pg.ray0, n_valid = pg.n_valid;
-      const float* zc = sm.z_c[pg.zbuf];
-      const bool el_ok = g_el < n_valid;
-      const int rc0 = g_el * S;           // first row of ray g_el
-      const int base = g_el * nS;
-      const size_t ro_el = (size_t)img * p.n_rays + ray0 + g_el;
-      (void)ro_el; (void)rc0; (void)base; (void)el_ok; (void)zc; (void)img; (void)ray0;
-      if (el_ok) {
-        auto key_of = [&](int e) { return hier ? (e < S ? sm.z_f[rc0 + e] : zc[rc0 + e - S]) : zc[rc0 + e]; };
-        const float k = key_of(e_el);
-        int rank = 0;
-#pragma unroll 4
-        for (int e = 0; e < nS; ++e) {
-          const float ke = key_of(e);
-          rank += (ke < k || (ke == k && e < e_el)) ? 1 : 0;
-        }
-        const int src = hier ? e_el : S + e_el;
-        sm.skey[base + rank] = k;
-        sm.sidx[base + rank] = src;
-        sm.frow[base + rank] = src < S ? rc0 + src : kRows + rc0 + src - S;
-      }
-      slot_sync();
-    };
-    auto m2 = [&]() {      // alphas, transmittance in the reference's cumprod order, weights (pigan_utils.py:241-257)
-      const int img = pg.img, ray0 = pg.ray0, n_valid = pg.n_valid;
-      const float* zc = sm.z_c[pg.zbuf];
-      const bool el_ok = g_el < n_valid;
-      const int rc0 = g_el * S;           // first row of ray g_el
-      const int base = g_el * nS;
-      const size_t ro_el = (size_t)img * p.n_rays + ray0 + g_el;
-      (void)ro_el; (void)rc0; (void)base; (void)el_ok; (void)zc; (void)img; (void)ray0;
-      float alpha_el = 0.f;
-      if (el_ok) {       // alpha of sorted position e_el (pigan_utils.py:241-251)
-        const int src = sm.sidx[base + e_el];
-        const float sg = src < S ? sm.sig_f[rc0 + src] : sm.sig_c[rc0 + src - S];
-        const float delta = e_el + 1 < nS ? __fsub_rn(sm.skey[base + e_el + 1], sm.skey[base + e_el]) : 1e10f;
-        const float nz = a.io.noise_f ? __fmul_rn(a.io.noise_f[ro_el * nS + e_el], p.noise_std) : 0.f;
-        alpha_el = sample_alpha(delta, sg, nz, p.clamp_mode);
-        sm.fbuf[base + e_el] = __fadd_rn(__fsub_rn(1.f, alpha_el), 1e-10f);
-      }
-      slot_sync();
-      if (el_ok) {       // transmittance in the reference's cumprod order, weight
-        float T = 1.f;
-#pragma unroll 4
-        for (int j = 0; j < e_el; ++j) T = __fmul_rn(T, sm.fbuf[base + j]);
-        sm.w_all[base + e_el] = __fmul_rn(alpha_el, T);
-      }
-      slot_sync();
-    };
-    auto m3 = [&]() {      // pixels_fea[ray][c] = sum_i w_i * feature_i[c] (pigan_utils.py:255-266), depth, debug outputs
-      const int img = pg.img, ray0 = pg.ray0, n_valid = pg.n_valid;
-      const float* zc = sm.z_c[pg.zbuf];
-      const bool el_ok = g_el < n_valid;
-      const int rc0 = g_el * S;           // first row of ray g_el
-      const int base = g_el * nS;
-      const size_t ro_el = (size_t)img * p.n_rays + ray0 + g_el;
-      (void)ro_el; (void)rc0; (void)base; (void)el_ok; (void)zc; (void)img; (void)ray0;
-      stamp(12);
-      // ---------------- composite: pixels_fea[ray][c] = sum_i w_i * feature_i[c]  (pigan_utils.py:255-266)
-      if (p.last_back || p.white_back) {     // (slot-uniform) the weight sum is only needed for the two background modes
-        if (el_ok && e_el == 0) {    // per ray: weight sum in the reference's order, last_back folded into the last weight
-          float wsum = 0.f;
-#pragma unroll 4
-          for (int i = 0; i < nS; ++i) wsum += sm.w_all[base + i];
-          sm.wsum[g_el] = wsum;
-          if (p.last_back) sm.w_all[base + nS - 1] += 1.f - wsum;
-        }
-        slot_sync();
-      }
-      {
-        const int c = stid & 31;
-        const float* featf = &sm.feat[0][0][0];
-        for (int g = stid >> 5; g < n_valid; g += 8) {      // warp = ray, lane = channel
-          const int b0 = g * nS;
-          float acc = 0.f;
-#pragma unroll 4
-          for (int i = 0; i < nS; ++i) acc = fmaf(sm.w_all[b0 + i], featf[sm.frow[b0 + i] * 33 + c], acc);
-          if (p.white_back) acc += 1.f - sm.wsum[g];
-          const size_t ro = (size_t)img * p.n_rays + ray0 + g;
-          a.io.pixels_fea[ro * kFeat + c] = acc;
-          if (c < nS && (a.io.weights || a.io.dbg_all_z)) {     // lanes cover the nS <= 32 fast case, loop otherwise
-            for (int i = c; i < nS; i += 32) {
-              if (a.io.weights) a.io.weights[ro * nS + i] = sm.w_all[b0 + i];
-              if (a.io.dbg_all_z) a.io.dbg_all_z[ro * nS + i] = sm.skey[b0 + i];
-            }
-          }
-          if (c == 0 && a.io.depth) {
-            float depth = 0.f;
-            for (int i = 0; i < nS; ++i) depth = fmaf(sm.w_all[b0 + i], sm.skey[b0 + i], depth);
-            a.io.depth[ro] = depth;
-          }
-        }
-      }
-      slot_sync();
-      stamp(13);
-    };
-    float u_next = jitter_of(0);
+#ifdef C3D_RAY_STAGGER_NS   // start slot 1 half a pass late so its MMA phases fall into slot 0's worker phases
+    if (sl == 1) __nanosleep(C3D_RAY_STAGGER_NS);
+#endif
 
     for (int it = 0; it < iters; ++it) {
+#ifdef C3D_TRACE
       tr_it = it; tr_ph = 0;
-      const float u_cur = u_next;
-      float* const zc = sm.z_c[WARP ? 0 : (it & 1)];
+#endif
       const int grp = (it * (int)gridDim.x + (int)blockIdx.x) * 2 + sl;
       const bool grp_ok = grp < a.total_groups;
       const int img = grp_ok ? grp / a.groups_per_img : 0;
@@ -582,35 +348,28 @@ __global__ void __launch_bounds__(640, 1) ray_siren_tc_kernel(const KArgs a) {
         gray = a.io.ray_idx ? a.io.ray_idx[nloc] : p.ray_offset + nloc;
         fr = make_ray_frame(M, gray, p.img_size, p.z_cam);
       }
-      // the resampling step's uniform (block-wide form): issued now, consumed a whole MLP pass later -- an HBM-latency load
-      // (~800 clk) that used to sit on the group's critical path between the two passes
-      float uk_pre = 0.f;
-      if (!WARP && hier && half == 0 && pt_ok) uk_pre = a.io.pdf_u[ro_row * S + s_row];
 
       for (int pass = 0; pass < (hier ? 2 : 1); ++pass) {
         // ---------------- L0: point position -> A operand [x, y, z, 1] (K = 16) for the layer-0 MMA
         float px = 0.f, py = 0.f, pz = 0.f;
         if (pt_ok) {
           if (pass == 0) {
-            const float u = u_cur;
+            const float u = a.io.jitter_u[((size_t)img * p.img_size * p.img_size + gray) * S + s_row];
             float z;
             coarse_sample(fr, M, p.ray_start, p.ray_end, S, s_row, u, z, px, py, pz);
-            if (half == 0) zc[row] = z;
+            if (half == 0) sm.z_c[row] = z;
           } else {
             fine_sample(fr, sm.z_f[row], px, py, pz);
           }
         }
-        if (pass == (hier ? 1 : 0)) u_next = jitter_of(it + 1);
         if (half == 0) {
           float v[16] = {px, py, pz, 1.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
           store_a16(a_hi, a_lo, v);
         }
         stamp(2);
         signal_a();
-        if (!WARP && pass == 0 && pg.valid) m1();
         // ---------------- E0: D(128) = g0*(W0 p*s + b0) + beta0  ->  sin  ->  A (h0)
         wait_d();
-        e_enter();
         stamp(3);
         {
           uint32_t accA[16], accB[16];
@@ -629,24 +388,14 @@ __global__ void __launch_bounds__(640, 1) ray_siren_tc_kernel(const KArgs a) {
           e0(accB, 16);
           tc_wait_ld();
           tmem_ld16(dcol + (uint32_t)(half * 64 + 48), accB);
-          if (a.sched == 1) {
-            tc_wait_ld();      // this thread's 64 accumulator columns are out of D
-            signal_a(0, true); // stage 0: K-chunks 0, 1 of both halves written, D drained -> layer 1's MMAs start underneath
-            e0(accA, 32);
-            signal_a(1, true); // stage 1: chunk 2
-          } else {
-            e0(accA, 32);      // form 0: the last load's latency hides under this chunk
-            tc_wait_ld();
-          }
+          e0(accA, 32);
+          tc_wait_ld();
           e0(accB, 48);
         }
         stamp(4);
-        signal_a(2);         // stage 2: chunk 3
-        e_leave();
-        if (!WARP && pass == 0 && pg.valid) m2();
+        signal_a();
         // ---------------- E1: D(128) -> FiLM+sin -> A (h1); TMEM loads double-buffered
         wait_d();
-        e_enter();
         stamp(5);
         {
           uint32_t accA[16], accB[16];
@@ -670,27 +419,17 @@ __global__ void __launch_bounds__(640, 1) ray_siren_tc_kernel(const KArgs a) {
           e1(accB, 16);
           tc_wait_ld();
           tmem_ld16(dcol + (uint32_t)(half * 64 + 48), accB);
-          if (a.sched == 1) {
-            tc_wait_ld();
-            signal_a(0, true); // stage 0 of the colour / sigma MMA (see the issuer)
-            e1(accA, 32);
-            signal_a(1, true); // stage 1
-          } else {
-            e1(accA, 32);
-            tc_wait_ld();
-          }
+          e1(accA, 32);
+          tc_wait_ld();
           e1(accB, 48);
           // partial sums of the two column halves, per pass; combined where sigma is used, i.e. after the slot-wide barrier
           // that ends the pass (fbuf / w_all are free in the warp-math forms)
           if (FOLD) (pass == 0 ? sm.fbuf : sm.w_all)[half * kRows + row] = psig;
         }
         stamp(6);
-        signal_a(2);
-        e_leave();
-        if (!WARP && pass == 0 && pg.valid) m3();
+        signal_a();
         // ---------------- E2: D(80): cols 0..63 -> FiLM+sin -> A (h2, K=64); col 64 -> sigma
         wait_d();
-        e_enter();
         stamp(7);
         float sigma = 0.f;
         if (FOLD) {
@@ -712,7 +451,6 @@ __global__ void __launch_bounds__(640, 1) ray_siren_tc_kernel(const KArgs a) {
           };
           e2(accA, 0);
           e2(accB, 16);
-          e_leave();
           stamp(8);
           stamp(9);
         } else {
@@ -736,13 +474,11 @@ __global__ void __launch_bounds__(640, 1) ray_siren_tc_kernel(const KArgs a) {
             (pass == 0 ? sm.sig_c : sm.sig_f)[row] = sigma;
           }
           e2(accA, 0);
-          signal_a(0, true); // stage 0 of the K = 64 colour-linear MMA: k-steps {0, 2}
           e2(accB, 16);
         }
         if (!FOLD) {
         stamp(8);
-        signal_a(1);         // stage 1: k-steps {1, 3}
-        e_leave();
+        signal_a();
         // ---------------- E3: D(32) -> + bias -> features to shared memory
         wait_d();
         stamp(9);
@@ -774,7 +510,7 @@ __global__ void __launch_bounds__(640, 1) ray_siren_tc_kernel(const KArgs a) {
             const bool act = g < n_valid && e < S;
             const int r0 = g * S;
             const size_t ro = (size_t)img * p.n_rays + ray0 + g;
-            const float z = act ? zc[r0 + e] : 0.f;
+            const float z = act ? sm.z_c[r0 + e] : 0.f;
             const float zn = __shfl_down_sync(full, z, 1, 16);
             float alpha = 0.f, f = 1.f;
             if (act) {
@@ -822,7 +558,7 @@ __global__ void __launch_bounds__(640, 1) ray_siren_tc_kernel(const KArgs a) {
           const int r0 = g_row * S;
           float alpha = 0.f;
           if (half == 0 && pt_ok) {   // A: alpha_i and (1 - alpha_i + 1e-10)
-            const float delta = s_row + 1 < S ? __fsub_rn(zc[row + 1], zc[row]) : 1e10f;
+            const float delta = s_row + 1 < S ? __fsub_rn(sm.z_c[row + 1], sm.z_c[row]) : 1e10f;
             const float nz = a.io.noise_c ? __fmul_rn(a.io.noise_c[ro_row * S + s_row], p.noise_std) : 0.f;
             alpha = sample_alpha(delta, sm.sig_c[row], nz, p.clamp_mode);
             sm.fbuf[row] = __fadd_rn(__fsub_rn(1.f, alpha), 1e-10f);
@@ -830,18 +566,15 @@ __global__ void __launch_bounds__(640, 1) ray_siren_tc_kernel(const KArgs a) {
           slot_sync();
           if (half == 0 && pt_ok) {   // B: T_i = prod_{j<i} f_j (sequential order), w_i = alpha_i * T_i
             float T = 1.f;
-#pragma unroll 4
             for (int j = 0; j < s_row; ++j) T = __fmul_rn(T, sm.fbuf[r0 + j]);
             sm.wc[row] = __fmul_rn(alpha, T);
           }
           slot_sync();
           if (half == 0 && pt_ok && s_row <= S - 2) {   // C: cdf_j, j = 0..S-2, over weights (w+1e-5)[1:-1]+1e-5
             float sum = 0.f;
-#pragma unroll 4
             for (int j = 0; j < S - 2; ++j) sum += __fadd_rn(__fadd_rn(sm.wc[r0 + j + 1], 1e-5f), 1e-5f);
             float c = 0.f;
             const float inv = __fdividef(1.f, sum);      // pdf_j = wt_j / sum (1-2 ulp; cdf only feeds a 2e-4-conditioned inverse)
-#pragma unroll 4
             for (int j = 0; j < s_row; ++j)
               c = __fadd_rn(c, __fmul_rn(__fadd_rn(__fadd_rn(sm.wc[r0 + j + 1], 1e-5f), 1e-5f), inv));
             sm.cdf[r0 + s_row] = c;
@@ -849,13 +582,13 @@ __global__ void __launch_bounds__(640, 1) ray_siren_tc_kernel(const KArgs a) {
           slot_sync();
           if (half == 0 && pt_ok) {   // D: inverse CDF for u_k, k = s_row
             const int ns = S - 2;
-            const float uk = uk_pre;
+            const float uk = a.io.pdf_u[ro_row * S + s_row];
             int i = 0;
             while (i <= ns && sm.cdf[r0 + i] < uk) ++i;         // searchsorted(cdf, u, right=False)
             const int below = max(i - 1, 0), above = min(i, ns);
             const float cb = sm.cdf[r0 + below], ca = sm.cdf[r0 + above];
-            const float bb = 0.5f * __fadd_rn(zc[r0 + below], zc[r0 + below + 1]);
-            const float ba = 0.5f * __fadd_rn(zc[r0 + above], zc[r0 + above + 1]);
+            const float bb = 0.5f * __fadd_rn(sm.z_c[r0 + below], sm.z_c[r0 + below + 1]);
+            const float ba = 0.5f * __fadd_rn(sm.z_c[r0 + above], sm.z_c[r0 + above + 1]);
             float denom = __fsub_rn(ca, cb);
             if (denom < 1e-5f) denom = 1.f;
             sm.z_f[row] = __fadd_rn(bb, __fmul_rn(__fdiv_rn(__fsub_rn(uk, cb), denom), __fsub_rn(ba, bb)));
@@ -873,7 +606,7 @@ __global__ void __launch_bounds__(640, 1) ray_siren_tc_kernel(const KArgs a) {
           const int rc0 = g * S, base = g * nS, e = lane;
           const bool act = e < nS;
           const size_t ro = (size_t)img * p.n_rays + ray0 + g;
-          const float k = act ? (hier ? (e < S ? sm.z_f[rc0 + e] : zc[rc0 + e - S]) : zc[rc0 + e]) : 3.0e38f;
+          const float k = act ? (hier ? (e < S ? sm.z_f[rc0 + e] : sm.z_c[rc0 + e - S]) : sm.z_c[rc0 + e]) : 3.0e38f;
           int rank = 0;                                   // stable ascending rank (torch.sort over cat([fine, coarse]))
           for (int j = 0; j < nS; ++j) {
             const float kj = __shfl_sync(full, k, j);
@@ -951,15 +684,75 @@ __global__ void __launch_bounds__(640, 1) ray_siren_tc_kernel(const KArgs a) {
         stamp(13);
         continue;
       }
-      // MATH 0: the merge + compositing of this group is DEFERRED into the MMA waits of the next group's coarse pass (m1 / m2 / m3
-      // below): it uses neither the tensor pipe nor MUFU nor TMEM, and was 17 % of a group's critical path (r02d trace)
-      pg.valid = grp_ok;
-      pg.img = img; pg.ray0 = ray0; pg.n_valid = n_valid; pg.zbuf = it & 1;
-    }
-    if (!WARP && pg.valid) {      // the last group of this slot
-      m1();
-      m2();
-      m3();
+      const bool el_ok = g_el < n_valid;
+      const int rc0 = g_el * S;           // first row of ray g_el
+      const int base = g_el * nS;
+      const size_t ro_el = (size_t)img * p.n_rays + ray0 + g_el;
+      if (el_ok) {
+        auto key_of = [&](int e) { return hier ? (e < S ? sm.z_f[rc0 + e] : sm.z_c[rc0 + e - S]) : sm.z_c[rc0 + e]; };
+        const float k = key_of(e_el);
+        int rank = 0;
+        for (int e = 0; e < nS; ++e) {
+          const float ke = key_of(e);
+          rank += (ke < k || (ke == k && e < e_el)) ? 1 : 0;
+        }
+        const int src = hier ? e_el : S + e_el;
+        sm.skey[base + rank] = k;
+        sm.sidx[base + rank] = src;
+        sm.frow[base + rank] = src < S ? rc0 + src : kRows + rc0 + src - S;
+      }
+      slot_sync();
+      float alpha_el = 0.f;
+      if (el_ok) {       // alpha of sorted position e_el (pigan_utils.py:241-251)
+        const int src = sm.sidx[base + e_el];
+        const float sg = src < S ? sm.sig_f[rc0 + src] : sm.sig_c[rc0 + src - S];
+        const float delta = e_el + 1 < nS ? __fsub_rn(sm.skey[base + e_el + 1], sm.skey[base + e_el]) : 1e10f;
+        const float nz = a.io.noise_f ? __fmul_rn(a.io.noise_f[ro_el * nS + e_el], p.noise_std) : 0.f;
+        alpha_el = sample_alpha(delta, sg, nz, p.clamp_mode);
+        sm.fbuf[base + e_el] = __fadd_rn(__fsub_rn(1.f, alpha_el), 1e-10f);
+      }
+      slot_sync();
+      if (el_ok) {       // transmittance in the reference's cumprod order, weight
+        float T = 1.f;
+        for (int j = 0; j < e_el; ++j) T = __fmul_rn(T, sm.fbuf[base + j]);
+        sm.w_all[base + e_el] = __fmul_rn(alpha_el, T);
+      }
+      slot_sync();
+      stamp(12);
+      // ---------------- composite: pixels_fea[ray][c] = sum_i w_i * feature_i[c]  (pigan_utils.py:255-266)
+      if (el_ok && e_el == 0) {      // per ray: weight sum in the reference's order, last_back folded into the last weight
+        float wsum = 0.f;
+        for (int i = 0; i < nS; ++i) wsum += sm.w_all[base + i];
+        sm.wsum[g_el] = wsum;
+        if (p.last_back) sm.w_all[base + nS - 1] += 1.f - wsum;
+      }
+      slot_sync();
+      {
+        const int c = stid & 31;
+        const float* featf = &sm.feat[0][0][0];
+        for (int g = stid >> 5; g < n_valid; g += 8) {      // warp = ray, lane = channel
+          const int b0 = g * nS;
+          float acc = 0.f;
+#pragma unroll 4
+          for (int i = 0; i < nS; ++i) acc = fmaf(sm.w_all[b0 + i], featf[sm.frow[b0 + i] * 33 + c], acc);
+          if (p.white_back) acc += 1.f - sm.wsum[g];
+          const size_t ro = (size_t)img * p.n_rays + ray0 + g;
+          a.io.pixels_fea[ro * kFeat + c] = acc;
+          if (c < nS && (a.io.weights || a.io.dbg_all_z)) {     // lanes cover the nS <= 32 fast case, loop otherwise
+            for (int i = c; i < nS; i += 32) {
+              if (a.io.weights) a.io.weights[ro * nS + i] = sm.w_all[b0 + i];
+              if (a.io.dbg_all_z) a.io.dbg_all_z[ro * nS + i] = sm.skey[b0 + i];
+            }
+          }
+          if (c == 0 && a.io.depth) {
+            float depth = 0.f;
+            for (int i = 0; i < nS; ++i) depth = fmaf(sm.w_all[b0 + i], sm.skey[b0 + i], depth);
+            a.io.depth[ro] = depth;
+          }
+        }
+      }
+      slot_sync();
+      stamp(13);
     }
   }
   tc_fence_before();
@@ -1079,9 +872,6 @@ int c3d_ray_siren_fwd_tc(const C3dRayParams* p, const C3dSirenWeights* w, const 
   ka.total_groups = p->batch * ka.groups_per_img;
   ka.b_sigma = w->b_sigma;
   ka.w_sigma = w->w_sigma;
-  ka.stagger_ns = c3d_options().ray_stagger_ns;
-  ka.e_turn = c3d_options().ray_e_turn;
-  ka.sched = c3d_options().ray_sched;
   const size_t smem = sizeof(Smem) + 1024;
   static std::atomic<unsigned long long> attr_set{0};     // per device, once
   if (!(attr_set.load() >> (dev & 63) & 1ull)) {

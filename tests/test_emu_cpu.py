@@ -794,17 +794,3 @@ def test_emu_points_linear_matches_fp64(rows, K, N, bias, mode):
     assert (wr.grad - w2.grad).abs().max().item() < 1e-4 * w2.grad.abs().max().item()
     if bias:
         assert (br.grad - b2.grad).abs().max().item() < 1e-4 * b2.grad.abs().max().item()
-
-
-@pytest.mark.parametrize("env", [{"C3D_RAY_SCHED": "1"}, {"C3D_RAY_SCHED": "1", "C3D_RAY_E_TURN": "1"}, {"C3D_RAY_SCHED": "0", "C3D_RAY_STAGGER_NS": "2000"}])
-@pytest.mark.parametrize("name", ["r16_trained_noise", "r8_hier_s24"])
-def test_emu_ray_siren_scheduling_forms(name, env, monkeypatch):
-    """The renderer's scheduling forms (C3D_RAY_SCHED=1: one blocking MMA issuer per slot with K-chunked staged issue, optionally
-    with the epilogue turn; form 0 with an initial stagger of the second slot) give the goldens of the real reference like the
-    default, under random completion of the asynchronous operations (the staged form's first version aliased two stages on one
-    mbarrier -- the emulator's TMEM race check found it)."""
-    for k, v in env.items():
-        monkeypatch.setenv(k, v)
-    with emulated(async_mode=MODES["random"], seed=11) as pkg:
-        out, ref = _render(pkg, name, TC)
-    _check_render(out, ref)

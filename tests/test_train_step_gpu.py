@@ -1,0 +1,54 @@
+"""The reference's training step (train.py:326-491) on a B200, at r64 with 4 images: the native training paths against the torch-op
+graph of the same modules, from the same seed.  Step 0 runs the same forward graph up to kernel numerics, so its losses must agree
+closely; step 1 runs after one optimiser update computed from each path's own gradients, so its losses pin the GRADIENTS
+("parity of next-step losses <= 1e-4").  The same closure tools/bench_train_step.py times."""
+import importlib.util
+import math
+import os
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+DEV = "cuda:0"
+
+
+@pytest.fixture(scope="module")
+def bts():
+    spec = importlib.util.spec_from_file_location("c3d_bench_train_step", os.path.join(ROOT, "tools", "bench_train_step.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def _run(bts, frozen, optim="fused", cips="torch", film="torch", integ="torch", linear="torch", steps=2, res=64, batch=4):
+    cfg = dict(res=res, batch=batch, frozen=frozen, aux=not frozen, diffaug=False, grad_points=256, forward_points=256, warmup_D=frozen)
+    torch.manual_seed(0)
+    step, mods = bts.build_step(cfg, torch.device(DEV), optim, cips, film_backend=film, integrate_backend=integ, linear_backend=linear)
+    out = [tuple(float(x) for x in step(it)) for it in range(steps)]
+    torch.cuda.synchronize()
+    return out
+
+
+def test_frozen_recipe_native_cips_backward_next_step_losses(bts):
+    """configs 4-5 (freeze-NeRF): torch graph + torch Adam  vs  fused optimiser tail  vs  native CIPS training path."""
+    ref = _run(bts, True, optim="torch")
+    fus = _run(bts, True, optim="fused")
+    nat = _run(bts, True, optim="fused", cips="fused")
+    assert all(math.isfinite(x) for r in (ref, fus, nat) for pair in r for x in pair)
+    print("TRAIN-PARITY frozen", ref, fus, nat)
+    assert fus[0] == pytest.approx(ref[0], rel=1e-5) and fus[1] == pytest.approx(ref[1], rel=1e-4)
+    assert nat[0] == pytest.approx(ref[0], rel=1e-4)          # fp16-operand CIPS forward in the graph vs fp32 torch ops
+    assert nat[1] == pytest.approx(ref[1], rel=1e-3)          # after an update from the native backward chain's gradients
+
+
+def test_full_recipe_native_nerf_training_ops_next_step_losses(bts):
+    """config 3 (NeRF gradients, aux images): torch graph vs every hot op of the NeRF training graph native (FiLM + sine,
+    per-point linears on tcgen05, volume integration / merge, sample_pdf)."""
+    ref = _run(bts, False)
+    nat = _run(bts, False, film="fused", integ="fused", linear="fused")
+    print("TRAIN-PARITY full", ref, nat)
+    assert all(math.isfinite(x) for r in (ref, nat) for pair in r for x in pair)
+    assert nat[0] == pytest.approx(ref[0], rel=1e-5)
+    assert nat[1] == pytest.approx(ref[1], rel=1e-4)
