@@ -65,15 +65,14 @@ def reference_generator(device):
 
 
 def peaks():
+    """-> (peak TFLOP/s used for roofline.frac, HBM GB/s, source string, the other bf16 figure).  The timed region of the default run
+    is a few tenths of a second, not a long sustained step, so `frac` is quoted against the BURST dense-bf16 figure (the stricter
+    denominator; VERDICT r1 weak #11) and the sustained figure rides along as `frac_of_sustained`."""
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
         d = json.load(open(p))
-        # the kernels are timed by events inside the long timed step loop (power-limited regime): the contract's denominator
-        # for that is the SUSTAINED dense-bf16 figure; the burst figure rides along as peak_burst / frac_of_burst
-        if d.get("bf16_tflops_sustained"):
-            return d["bf16_tflops_sustained"], d["hbm_gbs"], "measured (MEASURED_PEAKS.json, sustained bf16: kernel timed inside a long step)", d["bf16_tflops"]
-        return d["bf16_tflops"], d["hbm_gbs"], "measured (MEASURED_PEAKS.json, burst bf16)", d["bf16_tflops"]
-    return 1590.0, 6650.0, "fallback (B200_PROFILING.md)", 1590.0
+        return d["bf16_tflops"], d["hbm_gbs"], "measured (MEASURED_PEAKS.json, burst bf16)", d.get("bf16_tflops_sustained")
+    return 1590.0, 6650.0, "fallback (B200_PROFILING.md)", None
 
 
 class ClockSampler(threading.Thread):
@@ -321,7 +320,7 @@ def main():
     imgs = B * world * args.steps
     value = imgs / (ms / 1e3)
     e2e = imgs / (ms_e2e / 1e3)
-    peak_tf, peak_hbm, peak_src, peak_burst = peaks()
+    peak_tf, peak_hbm, peak_src, peak_sustained = peaks()
     roof = {}
     for key, flop_unit, units in (("cips", CIPS_FLOP_PER_PIXEL, B * res * res), ("ray", NERF_FLOP_PER_RAY, B * res * res)):
         evs = (prof or {}).get(key, [])
@@ -331,7 +330,7 @@ def main():
             roof[key] = {"bound": "tensor", "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach / peak_tf,
                          "traffic": None, "kernel_ms": t_ms, "launches_timed": len(evs),
                          "algorithmic_flop_per_launch": flop_unit * units, "peak_source": peak_src,
-                         "peak_burst": peak_burst, "frac_of_burst": ach / peak_burst}
+                         "peak_sustained": peak_sustained, "frac_of_sustained": (ach / peak_sustained) if peak_sustained else None}
     # DRAM traffic per launch from the committed ncu --set full capture of this workload (profiles/traffic.json)
     tpath = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tpath):
