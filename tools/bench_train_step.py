@@ -219,8 +219,9 @@ def main():
             config=dict(baseline_config=args.config, resolution=R, batch_per_gpu=B, generator=G_cls.__name__, train_aux_img=cfg["aux"],
                         diffaug=cfg["diffaug"], grad_points=cfg["grad_points"], optim=args.optim, tf32_autograd=bool(args.tf32),
                         cudnn_tf32=bool(torch.backends.cudnn.allow_tf32), cips_backend=args.cips_backend, film_backend=args.film_backend, integrate_backend=args.integrate_backend, linear_backend=args.linear_backend,
-                        note="G forward under no_grad runs the fused kernels; the G step's autograd graph runs as torch CUDA ops "
-                             "(backward kernels: DESIGN.md section 9); D convs are cuDNN as in the reference; D's bias_act / blur are native"),
+                        note="G forward under no_grad runs the fused kernels; the G step's graph uses the native training ops the "
+                             "*_backend flags select (DESIGN.md 4.10-4.14), torch CUDA ops otherwise; D convolutions are the library's implicit "
+                             "GEMM behind ops.conv2d's autograd structure; D's bias_act / blur are native"),
             d_loss=float(dl), g_loss=float(gl), comm=nccl, finite=bool(math.isfinite(float(dl)) and math.isfinite(float(gl))))))
     if ddp:
         torch.distributed.destroy_process_group()
