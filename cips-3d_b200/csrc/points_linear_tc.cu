@@ -5,10 +5,12 @@
 // SURVEY 7.2): 42 % of a config-3 train step (profiles/r02b_train_profiles.md).  K, N in {32, 64, 128}.
 //
 // HBM-bound by construction (4 (K + N) bytes per point against 6 K N tensor-core MACs): the structure is the simplest one
-// that keeps the tensor pipe out of the way -- thread = point row (TMEM lane); per 128-row tile the four warps split their rows'
-// fp32 values straight into the TMEM A operand (tcgen05.st, hi and lo halves), one elected thread issues the 3 K/16 MMAs
-// against the weight blob resident in shared memory, and every thread drains its accumulator row to global memory.  Two CTAs
-// per SM (256 TMEM columns and <= 64 KB of shared memory each) overlap one tile's loads with the other's MMAs and stores.
+// that keeps the tensor pipe out of the way -- 256 threads per 128-row tile: thread = (point row = TMEM lane, half): the eight
+// warps split their rows' fp32 values straight into the TMEM A operand (tcgen05.st, hi and lo halves; half h owns the h-th half
+// of K), one elected thread issues the 3 K/16 MMAs against the weight blob resident in shared memory, and every thread drains
+// its half of the accumulator row to global memory.  Two CTAs per SM (256 TMEM columns and <= 64 KB of shared memory each)
+// overlap one tile's loads with the other's MMAs and stores.  (The first version had one thread per row: 0.44 of the HBM peak,
+// too few loads in flight -- profiles/r02h_ncu_plin_summary.md.)
 //
 // `scale` (device scalar, may be null = 1): operands are multiplied by it before the fp16 split and the result divided by it,
 // so that small-magnitude inputs (gradients) stay in fp16's normal range; the caller passes 1024 / max|X|.
@@ -20,6 +22,7 @@ namespace c3d {
 namespace plin {
 
 constexpr int kRows = 128;
+constexpr int kThreads = 256;       // two threads per row
 constexpr float kWScale = 256.f, kWInv = 1.f / 256.f;       // weights are stored x 2^8 so that their lo parts stay normal
 
 struct KArgs {
@@ -58,11 +61,14 @@ __global__ void plin_prep_kernel(const float* __restrict__ w, int N, int K, int 
 }
 
 template <int N, int K>
-__global__ void __launch_bounds__(kRows, 2) plin_kernel(const KArgs a) {
+__global__ void __launch_bounds__(kThreads, 2) plin_kernel(const KArgs a) {
   C3D_DYN_SMEM(uint8_t, smem_raw);
   Smem<N, K>& s = *reinterpret_cast<Smem<N, K>*>(smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u));
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  const int q = warp & 3, half = warp >> 2;      // TMEM lane quarter (fixed by warp % 4), K / N half
+  const int r_in_tile = q * 32 + (threadIdx.x & 31);
   constexpr int kWBytes = 2 * N * K * 2;
+  constexpr int KH = K / 2, NH = N / 2;          // this thread's share of a row (both multiples of 16)
   if (threadIdx.x == 0) {
     mbar_init(&s.w_full, 1);
     mbar_init(&s.d_ready, 1);
@@ -80,7 +86,7 @@ __global__ void __launch_bounds__(kRows, 2) plin_kernel(const KArgs a) {
   }
   const float sc = a.scale ? __ldg(a.scale) : 1.f;
   const float inv = kWInv / sc;
-  const uint32_t lane_sel = (uint32_t)(warp * 32) << 16;
+  const uint32_t lane_sel = (uint32_t)(q * 32) << 16;
   const uint32_t a_hi = tmem + lane_sel, a_lo = a_hi + 64, dcol = a_hi + 128;
   const uint32_t dhi = umma_desc_hi(128);
   const uint32_t b_hi = umma_desc_lo(smem_u32(s.w), N * 16), b_lo = umma_desc_lo(smem_u32(s.w) + N * K * 2, N * 16);
@@ -90,12 +96,12 @@ __global__ void __launch_bounds__(kRows, 2) plin_kernel(const KArgs a) {
   bool w_seen = false;
 
   for (int tile = blockIdx.x; tile < a.tiles; tile += gridDim.x) {
-    const long long row = (long long)tile * kRows + threadIdx.x;
+    const long long row = (long long)tile * kRows + r_in_tile;
     const bool row_ok = row < a.rows;
-    // ---- this thread's row: fp32 -> (hi, lo) fp16 pairs -> TMEM A operand, 16 values per step
-    const float4* xr = reinterpret_cast<const float4*>(a.x + (size_t)(row_ok ? row : 0) * K);
+    // ---- this thread's half row: fp32 -> (hi, lo) fp16 pairs -> TMEM A operand, 16 values per step
+    const float4* xr = reinterpret_cast<const float4*>(a.x + (size_t)(row_ok ? row : 0) * K + half * KH);
 #pragma unroll
-    for (int c = 0; c < K / 16; ++c) {
+    for (int c = 0; c < KH / 16; ++c) {
       float4 v4[4];
 #pragma unroll
       for (int j = 0; j < 4; ++j) v4[j] = row_ok ? __ldg(xr + c * 4 + j) : make_float4(0.f, 0.f, 0.f, 0.f);
@@ -105,8 +111,8 @@ __global__ void __launch_bounds__(kRows, 2) plin_kernel(const KArgs a) {
         split_f16(v4[j].x * sc, v4[j].y * sc, hi[2 * j], lo[2 * j]);
         split_f16(v4[j].z * sc, v4[j].w * sc, hi[2 * j + 1], lo[2 * j + 1]);
       }
-      tmem_st8(a_hi + (uint32_t)(c * 8), hi);
-      tmem_st8(a_lo + (uint32_t)(c * 8), lo);
+      tmem_st8(a_hi + (uint32_t)(half * (KH / 2) + c * 8), hi);
+      tmem_st8(a_lo + (uint32_t)(half * (KH / 2) + c * 8), lo);
     }
     tc_wait_st();
     tc_fence_before();
@@ -136,7 +142,7 @@ __global__ void __launch_bounds__(kRows, 2) plin_kernel(const KArgs a) {
     // ---- accumulator row -> global
     float4* yr = reinterpret_cast<float4*>(a.y + (size_t)(row_ok ? row : 0) * N);
 #pragma unroll
-    for (int n0 = 0; n0 < N; n0 += 16) {
+    for (int n0 = half * NH; n0 < half * NH + NH; n0 += 16) {
       uint32_t acc[16];
       tmem_ld16(dcol + (uint32_t)n0, acc);
       tc_wait_ld();
@@ -178,7 +184,7 @@ static int launch(const KArgs& ka, int grid, cudaStream_t st) {
     attr_set.fetch_or(1ull << (dev & 63));
   }
   auto kern = plin_kernel<N, K>;
-  C3D_LAUNCH(kern, grid, kRows, smem, st, ka);
+  C3D_LAUNCH(kern, grid, kThreads, smem, st, ka);
   C3D_LAUNCH_CHECK();
   return C3D_OK;
 }
