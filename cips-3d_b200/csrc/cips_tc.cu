@@ -26,6 +26,7 @@
 // (they would have to come from shared memory, whose bandwidth the MMA operand fetch already saturates).  Only HBM traffic: x (128 B/pixel) in, rgb (12 B/pixel) out; the residual stream
 // of the skip blocks goes through an L2-resident per-CTA scratch (fp32, 256 KB).
 #include <atomic>
+#include <string.h>
 
 #include "c3d_common.cuh"
 
@@ -131,18 +132,23 @@ __device__ __forceinline__ void load_w_tile(void* dst, const uint8_t* src, uint6
 
 __device__ __forceinline__ float lrelu02(float v) { return fmaxf(v, 0.2f * v); }
 
-#ifdef C3D_TRACE   // debug build: block 0 stamps pipeline events of tile iteration 1 (steady state)
-__device__ unsigned long long g_trace[8192];
-__device__ unsigned int g_trace_n;
-__device__ __forceinline__ void trace_ev(int it, uint32_t tag, uint32_t a0) {
-  if (blockIdx.x == 0 && it == 1) {
-    unsigned int i = atomicAdd(&g_trace_n, 1u);
-    if (i < 8192) g_trace[i] = ((unsigned long long)tag << 56) | ((unsigned long long)(a0 & 0xFFFF) << 40) | (clock64() & 0xFFFFFFFFFFull);
+#ifdef C3D_TRACE   // debug build: blocks 0 and 1 stamp the pipeline events of tile iteration 1 (steady state).  One fixed slot per
+// (block, warp, stamp index): plain stores, no atomics (an atomic per stamp costs ~500 clk on the stamping warp's critical path).
+constexpr int kTraceCap = 3072;
+__device__ unsigned long long g_trace[2 * 20 * kTraceCap];
+__device__ __forceinline__ void trace_ev(int it, uint32_t tag, uint32_t a0, int& n) {
+  if (blockIdx.x < 2 && it == 1) {
+    if (n < kTraceCap)
+      g_trace[((size_t)blockIdx.x * 20 + (threadIdx.x >> 5)) * kTraceCap + n] =
+          ((unsigned long long)tag << 56) | ((unsigned long long)(a0 & 0xFFFF) << 40) | (clock64() & 0xFFFFFFFFFFull);
+    ++n;
   }
 }
-#define TRACE(it, tag, a0) trace_ev(it, tag, a0)
+#define TRACE(it, tag, a0) trace_ev(it, tag, a0, tr_n)
+#define TRACE_DECL int tr_n = 0; (void)tr_n
 #else
 #define TRACE(it, tag, a0)
+#define TRACE_DECL
 #endif
 
 struct EpiFlags {
@@ -269,6 +275,7 @@ __global__ void __launch_bounds__(kThreads, 1) cips_tc_kernel(const KArgs a) {
     reg_dec<56>();
     if (warp == 0) {
       // ---------------------------------------------------------- weight producer (whole warp converged, one lane issues)
+      TRACE_DECL;
       uint32_t stage = 0, phase = 0;
       for (int it = 0; it < iters; ++it) {
         const int tile = tile_of(it);
@@ -279,6 +286,7 @@ __global__ void __launch_bounds__(kThreads, 1) cips_tc_kernel(const KArgs a) {
           const int ntiles = a.layer_kc[l] * 4;
           for (int t = 0; t < ntiles; ++t) {
             mbar_wait(&s.empty[stage], phase ^ 1);
+            if (lane == 0) TRACE(it, 10, (uint32_t)(l << 8 | t));                  // producer: stage free, load issued
             if (elect_one()) {
               if (PAIR) {      // this CTA's half (N rows 64*rank .. +63) of the tile
                 mbar_arrive_expect_tx(&s.full[stage], RC::kStageBytes);
@@ -298,6 +306,7 @@ __global__ void __launch_bounds__(kThreads, 1) cips_tc_kernel(const KArgs a) {
       // ---------------------------------------------------------- peer CTA of a pair: warp 1 relays "my half of stage s
       // has landed" to the leader's peer_full[s] (one remote arrive per fill, in ring order); warp 3 idles.
       if (warp == 1) {
+        TRACE_DECL;
         uint32_t stage = 0, phase = 0;
         for (int it = 0; it < iters; ++it)
           for (int l = 0; l < L; ++l) {
@@ -305,6 +314,7 @@ __global__ void __launch_bounds__(kThreads, 1) cips_tc_kernel(const KArgs a) {
 #pragma unroll 1
             for (int t = 0; t < ntiles; ++t) {
               mbar_wait(&s.full[stage], phase);
+              if (lane == 0) TRACE(it, 11, (uint32_t)(l << 8 | t));                // peer: my half landed, relaying
               if (elect_one()) mbar_arrive_cluster(&s.peer_full[stage], 0);
               __syncwarp();
               if (++stage == NS) { stage = 0; phase ^= 1; }
@@ -316,6 +326,7 @@ __global__ void __launch_bounds__(kThreads, 1) cips_tc_kernel(const KArgs a) {
       // Two issuer warps share the weight ring: issuer i owns accumulator column blocks nc = 2i, 2i+1 (disjoint
       // TMEM columns, so the two instruction streams never touch the same accumulator) -- one thread alone
       // cannot issue 4 MMAs + bookkeeping inside the 256 clk a tile occupies the tensor pipe.
+      TRACE_DECL;
       const uint32_t me = warp == 1 ? 0u : 1u;
       const uint32_t idesc = umma_idesc_f16(PAIR ? 2 * kTileM : kTileM, kNC);
       const uint32_t dhi = umma_desc_hi(kSBO);
@@ -356,6 +367,7 @@ __global__ void __launch_bounds__(kThreads, 1) cips_tc_kernel(const KArgs a) {
             if (mine)
 #endif
             mbar_wait(&s.full[stage], phase);
+            if (PAIR && mine && lane == 0) TRACE(it, 12, (uint32_t)(l << 8 | t));  // own half landed
             if (PAIR) mbar_wait_cluster(&s.peer_full[stage], phase);             // ... and the peer's half
             if (mine) {
               if (lane == 0) TRACE(it, 5 + me, (uint32_t)(l << 8 | t));          // weight tile landed
@@ -402,6 +414,7 @@ __global__ void __launch_bounds__(kThreads, 1) cips_tc_kernel(const KArgs a) {
   } else {
     // ------------------------------------------------------------ epilogue warps
     reg_inc<104>();
+    TRACE_DECL;
     const int ew = warp - 4;
     const int wg = ew >> 2;            // column group 0..3
     const int q = warp & 3;            // TMEM lane quarter
@@ -489,7 +502,7 @@ __global__ void __launch_bounds__(kThreads, 1) cips_tc_kernel(const KArgs a) {
         for (int j = 0; j < 4; ++j) {
           if (!have) {
             mbar_wait(&s.acc_ready[j], apar);
-            if (threadIdx.x == 128) TRACE(it, 8, (uint32_t)(l << 8 | j));       // accumulator block j complete
+            if (lane == 0) TRACE(it, 8, (uint32_t)(l << 8 | j));                 // accumulator block j complete
             tc_fence_after();
             tmem_ld16(tcol, accA);
           }
@@ -653,16 +666,22 @@ static CipsWs cips_ws_layout(const C3dCipsParams* p) {
 size_t c3d_cips_tc_workspace_bytes(const C3dCipsParams* p) { return cips_ws_layout(p).total; }
 
 #ifdef C3D_TRACE
+// out: records of 2 words: [block << 8 | warp, stamp]; returns the number of records
 extern "C" int c3d_debug_cips_trace(unsigned long long* out, int cap) {
-  unsigned int n = 0;
+  static unsigned long long host[2 * 20 * c3d::cips::kTraceCap];
   cudaDeviceSynchronize();
-  cudaMemcpyFromSymbol(&n, c3d::cips::g_trace_n, sizeof(n));
-  if ((int)n > cap) n = cap;
-  if (n > 8192) n = 8192;
-  cudaMemcpyFromSymbol(out, c3d::cips::g_trace, n * sizeof(unsigned long long));
-  unsigned int zero = 0;
-  cudaMemcpyToSymbol(c3d::cips::g_trace_n, &zero, sizeof(zero));
-  return (int)n;
+  cudaMemcpyFromSymbol(host, c3d::cips::g_trace, sizeof(host));
+  int n = 0;
+  for (int w = 0; w < 40; ++w)
+    for (int i = 0; i < c3d::cips::kTraceCap && 2 * n + 1 < cap; ++i)
+      if (host[(size_t)w * c3d::cips::kTraceCap + i]) {
+        out[2 * n] = (unsigned long long)((w / 20) << 8 | (w % 20));
+        out[2 * n + 1] = host[(size_t)w * c3d::cips::kTraceCap + i];
+        ++n;
+      }
+  memset(host, 0, sizeof(host));
+  cudaMemcpyToSymbol(c3d::cips::g_trace, host, sizeof(host));
+  return n;
 }
 #endif
 
