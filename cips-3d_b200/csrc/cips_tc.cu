@@ -99,6 +99,9 @@ struct KArgs {
   // sign bits of z_l for the layers that add a residual (there y_l - y_{l-2} cannot recover the sign of a small lrelu(z_l)
   // from two fp16-rounded stashes): (n_layers, B, N, 32) uint16, bit i of word c = (z_l[16 c + i] > 0)
   uint16_t* zsign;
+  // A/B knob (C3D_CIPS_STAGGER_NS): CTA i starts i * stagger_ns late, so that the 148 CTAs -- identical work on the same image's 9.4 MB
+  // of weights -- do not all stream the same tile at the same moment
+  int stagger_ns;
 };
 
 template <int CL>
@@ -270,6 +273,11 @@ __global__ void __launch_bounds__(kThreads, 1) cips_tc_kernel(const KArgs a) {
     return PAIR ? (it * grid_units + (int)blockIdx.x / 2) * 2 + (int)crank : it * (int)gridDim.x + (int)blockIdx.x;
   };
   const int L = a.n_layers;
+  if (a.stagger_ns > 0) {        // whole CTA, before any pipeline role starts
+    const unsigned long long t_end = c3d_globaltimer() + (unsigned long long)a.stagger_ns * (blockIdx.x / (CL > 1 ? CL : 1));
+    while (c3d_globaltimer() < t_end) __nanosleep(100);
+    __syncthreads();
+  }
 
   if (warp < 4) {
     reg_dec<56>();
@@ -823,6 +831,7 @@ int c3d_cips_fwd_tc(const C3dCipsParams* p, const C3dCipsWeights* w, const float
   ka.x = x; ka.rgb = rgb; ka.hidden_out = hidden_out;
   ka.acts = (__half*)acts_f16;
   ka.zsign = (uint16_t*)zsign_u16;
+  ka.stagger_ns = c3d_options().cips_stagger_ns;
   ka.acts_layer_stride = (size_t)p->batch * p->n_pix * kH;
   ka.wtiles = (const __half*)(base + ws.wtiles);
   ka.rgbw = (const float4*)(base + ws.rgbw);
