@@ -38,7 +38,10 @@ constexpr int kTileM = 128;        // pixels per tile
 constexpr int kKC = 64;            // K per weight tile
 constexpr int kNC = 128;           // N per weight tile
 constexpr int kWTileBytes = kKC * kNC * 2;              // 16 KB
-constexpr int kStages = 5;
+#ifndef C3D_CIPS_STAGES
+#define C3D_CIPS_STAGES 5
+#endif
+constexpr int kStages = C3D_CIPS_STAGES;      // depth of the weight ring (5 x 16 KB is what fits beside the 128 KB activation tile)
 // CTA-pair variant (PAIR, tcgen05 cta_group::2): an MMA is M = 256 (128 pixels in each CTA of the pair) x N = 128 and
 // each CTA holds -- and streams from L2 -- only HALF of every weight tile (64 of its 128 N rows, 8 KB), so the ring
 // has twice the stages in the same 80 KB and the L2 -> SM weight traffic per SM is halved.
