@@ -82,3 +82,24 @@ if rel:
     l, v = sorted(rel)[min(3, len(rel) - 1)]
     ts = [v[i] for i in sorted(v)]
     print(f"peer relay (block 1, layer {l}): gaps between consecutive relays [clk]: " + " ".join(str(b - a) for a, b in zip(ts, ts[1:])))
+
+# per-tile detail of one steady-state layer on the leader: producer load issue -> own half landed -> both landed (MMA issue)
+for L_ in (5,):
+    prod, own, reach = by.get((0, 10, L_), {}), by.get((0, 12, L_), {}), {}
+    issue, dep = {}, {}
+    for me in (0, 1):
+        issue.update(by.get((0, 5 + me, L_), {})); dep.update(by.get((0, 3 + me, L_), {})); reach.update(by.get((0, 1 + me, L_), {}))
+    if prod and issue:
+        print(f"layer {L_}, leader, per tile t: producer issued load | own half landed (+latency) | MMA issued | issuer reached | dep ok   [clk, relative to the layer's first stamp]")
+        base = min(list(prod.values()) + list(issue.values()))
+        for t_idx in sorted(issue):
+            p_, o_, i_ = prod.get(t_idx), own.get(t_idx, issue[t_idx]), issue[t_idx]
+            print(f"  t{t_idx:2d}: load {p_ - base if p_ is not None else -1:7d} | own landed {o_ - base if o_ is not None else -1:7d} "
+                  f"(+{(o_ - p_) if (o_ is not None and p_ is not None) else -1:6d}) | mma {i_ - base:7d} | reached {reach.get(t_idx, base) - base:7d} | dep {dep.get(t_idx, base) - base:7d}")
+    prod1, rel1 = by.get((1, 10, L_), {}), by.get((1, 11, L_), {})
+    if prod1 and rel1:
+        b1 = min(prod1.values())
+        print(f"layer {L_}, peer (block 1; its own clock): producer issued load | its half landed (+latency)")
+        for t_idx in sorted(rel1):
+            if t_idx in prod1:
+                print(f"  t{t_idx:2d}: load {prod1[t_idx] - b1:7d} | landed {rel1[t_idx] - b1:7d} (+{rel1[t_idx] - prod1[t_idx]:6d})")
