@@ -246,7 +246,12 @@ __global__ void __launch_bounds__(kThreads, 1) cips_tc_kernel(const KArgs a) {
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < NS; ++i) {
-      mbar_init(&s.full[i], 1);
+      // PAIR, leader: a fill of stage i is complete when the leader's own half has landed (its producer's arrive + bytes) AND the
+      // peer has relayed "my half landed" with one remote arrive on this SAME barrier -- the issuers then wait on one CTA-local
+      // barrier per tile.  (Round 2's first form kept a separate peer_full barrier that both issuers polled with
+      // try_wait.acquire.cluster: ~350 clk per wait, twice per tile, serialised on the MMA issue path -- 1 370 clk per weight tile,
+      // profiles/r02o_cips_trace_pair.txt.)
+      mbar_init(&s.full[i], (PAIR && leader) ? 2 : 1);
 #ifdef C3D_INJECT_RING_RACE           // test-only (tests/test_emu_cpu.py): re-creates the round-1 parity-aliasing race
       mbar_init(&s.empty[i], CL);
 #else
@@ -326,7 +331,7 @@ __global__ void __launch_bounds__(kThreads, 1) cips_tc_kernel(const KArgs a) {
             for (int t = 0; t < ntiles; ++t) {
               mbar_wait(&s.full[stage], phase);
               if (lane == 0) TRACE(it, 11, (uint32_t)(l << 8 | t));                // peer: my half landed, relaying
-              if (elect_one()) mbar_arrive_cluster(&s.peer_full[stage], 0);
+              if (elect_one()) mbar_arrive_cluster(&s.full[stage], 0);      // second arrival of the leader's full[stage]
               __syncwarp();
               if (++stage == NS) { stage = 0; phase ^= 1; }
             }
@@ -378,8 +383,6 @@ __global__ void __launch_bounds__(kThreads, 1) cips_tc_kernel(const KArgs a) {
             if (mine)
 #endif
             mbar_wait(&s.full[stage], phase);
-            if (PAIR && mine && lane == 0) TRACE(it, 12, (uint32_t)(l << 8 | t));  // own half landed
-            if (PAIR) mbar_wait_cluster(&s.peer_full[stage], phase);             // ... and the peer's half
             if (mine) {
               if (lane == 0) TRACE(it, 5 + me, (uint32_t)(l << 8 | t));          // weight tile landed
               tc_fence_after();
