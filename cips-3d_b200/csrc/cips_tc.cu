@@ -255,7 +255,11 @@ __global__ void __launch_bounds__(kThreads, 1) cips_tc_kernel(const KArgs a) {
 #ifdef C3D_INJECT_RING_RACE           // test-only (tests/test_emu_cpu.py): re-creates the round-1 parity-aliasing race
       mbar_init(&s.empty[i], CL);
 #else
-      mbar_init(&s.empty[i], PAIR ? 2 : 2 * CL);   // both issuers release every stage (see the issuer loop)
+      // both issuers release every stage (see the issuer loop).  PAIR: the leader's stage needs the owner's (multicast) commit and the
+      // non-owner's LOCAL observe; the peer's stage only the multicast commit -- its half is read by the MMA alone, so it may refill as
+      // soon as that MMA is done, and it can never run more than one fill ahead (its next release needs the leader's next MMA, which
+      // needs the leader's own fill).  Round 2's first form sent two release.cluster arrives per non-owned tile from the issue path.
+      mbar_init(&s.empty[i], PAIR ? (leader ? 2 : 1) : 2 * CL);
 #endif
       if (PAIR) mbar_init(&s.peer_full[i], 1);
     }
@@ -416,7 +420,8 @@ __global__ void __launch_bounds__(kThreads, 1) cips_tc_kernel(const KArgs a) {
             }
 #ifndef C3D_INJECT_RING_RACE
             else if (elect_one()) {
-              observe_stage_free<CL>(&s.empty[stage]);      // (PAIR: CL == 2 -> one arrive on the barrier of each CTA)
+              if (PAIR) mbar_arrive(&s.empty[stage]);       // leader-local (see the barrier's initialisation)
+              else observe_stage_free<CL>(&s.empty[stage]);
             }
 #endif
             __syncwarp();
@@ -463,8 +468,7 @@ __global__ void __launch_bounds__(kThreads, 1) cips_tc_kernel(const KArgs a) {
             *reinterpret_cast<uint4*>(s.x + (size_t)(k0 / 8 + g) * kLBO + row * 16) =
                 make_uint4(pk[4 * g], pk[4 * g + 1], pk[4 * g + 2], pk[4 * g + 3]);
         }
-        if (PAIR) fence_proxy_async_all();
-        else fence_proxy_async();
+        fence_proxy_async();      // the A operand in THIS CTA's shared memory is what the tensor core (async proxy) reads; PAIR too
         tc_fence_before();
         __syncwarp();
         if (lane == 0)
@@ -538,8 +542,9 @@ __global__ void __launch_bounds__(kThreads, 1) cips_tc_kernel(const KArgs a) {
           if (second) epi16<true, DUMP>(accB, rsB, rwp + 16, xp + 2 * kLBO, rp + 4 * kTileM, f, rgb0, rgb1, rgb2, hp ? hp + 16 : nullptr, dp ? dp + 2 : nullptr, zp ? zp + 1 : nullptr);
           else epi16<false, DUMP>(accB, rsB, rwp + 16, xp + 2 * kLBO, rp + 4 * kTileM, f, rgb0, rgb1, rgb2, hp ? hp + 16 : nullptr, dp ? dp + 2 : nullptr);
           // chunk j of this epilogue is complete for this warp
-          if (PAIR) fence_proxy_async_all();
-          else fence_proxy_async();
+          // (round 2's first PAIR form used the all-state-spaces proxy fence here: it also waits for this thread's global residual
+          // stores, ~1.4 k clk per chunk -- the epilogue chunks took 2.9 k instead of 1.5 k clk, profiles/r02p_cips_trace_pair.txt)
+          fence_proxy_async();
           tc_fence_before();
           __syncwarp();
           if (lane == 0 && !f.last) {
