@@ -304,11 +304,15 @@ __device__ __forceinline__ void tc_commit_mc(uint64_t* bar, uint16_t mask) {
       "h"(mask)
       : "memory");
 }
-// plain arrive on the barrier at this offset in CTA `rank` of the cluster
+// plain arrive on the barrier at this offset in CTA `rank` of the cluster.  Default semantics (release at CTA scope): the
+// `.release.cluster` form compiles to MEMBAR.ALL.GPU + ERRBAR + CGAERRBAR in front of the arrive, ~1.3 k clk per call
+// (profiles/r02q_cips_trace_pair.txt: the relay warp of the CTA-pair kernel managed one arrive per 1.3 k clk and paced the whole
+// pipeline).  What the remote waiter consumes here is never generic-proxy global data: it is shared memory filled by the
+// TMA engine or written before a fence.proxy.async, and TMEM -- ordered by the fences the callers already issue.
 __device__ __forceinline__ void mbar_arrive_cluster(uint64_t* bar, uint32_t rank) {
   asm volatile(
       "{\n\t.reg .b32 ra;\n\tmapa.shared::cluster.u32 ra, %0, %1;\n\t"
-      "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t}" ::"r"(smem_u32(bar)),
+      "mbarrier.arrive.shared::cluster.b64 _, [ra];\n\t}" ::"r"(smem_u32(bar)),
       "r"(rank)
       : "memory");
 }
@@ -361,12 +365,14 @@ __device__ __forceinline__ void tc_commit_cg2_mc(uint64_t* bar, uint16_t mask) {
       "h"(mask)
       : "memory");
 }
-// wait on a LOCAL barrier whose arrivals come from another CTA of the cluster (acquire at cluster scope)
+// wait on a LOCAL barrier whose arrivals come from another CTA of the cluster.  Same default (CTA-scope acquire) form as the
+// local wait, matching mbar_arrive_cluster above: the cluster-scope acquire costs ~350 clk per successful wait
+// (profiles/r02o_cips_trace_pair.txt) and pairs with nothing once the arrive side is CTA-scope.
 __device__ __forceinline__ bool mbar_try_wait_cluster(uint64_t* bar, uint32_t parity) {
   uint32_t ok;
   asm volatile(
       "{\n\t.reg .pred P;\n\t"
-      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 P, [%1], %2, %3;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 P, [%1], %2, %3;\n\t"
       "selp.u32 %0, 1, 0, P;\n\t}"
       : "=r"(ok)
       : "r"(smem_u32(bar)), "r"(parity), "r"(kSuspendHintNs)
