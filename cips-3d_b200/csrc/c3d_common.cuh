@@ -107,15 +107,17 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t by
 #ifndef C3D_SUSPEND_HINT_NS
 #define C3D_SUSPEND_HINT_NS 20000
 #endif
-constexpr uint32_t kSuspendHintNs = C3D_SUSPEND_HINT_NS;
+constexpr uint32_t kSuspendHintNs = C3D_SUSPEND_HINT_NS > 0 ? C3D_SUSPEND_HINT_NS : 0;
 __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   uint32_t ok;
   asm volatile(
       "{\n\t.reg .pred P;\n\t"
 #if C3D_SUSPEND_HINT_NS > 0
       "mbarrier.try_wait.parity.shared::cta.b64 P, [%1], %2, %3;\n\t"
-#else
+#elif C3D_SUSPEND_HINT_NS == 0
       "mbarrier.try_wait.parity.shared::cta.b64 P, [%1], %2;\n\t"
+#else      /* experiment builds: pure spin */
+      "mbarrier.test_wait.parity.shared::cta.b64 P, [%1], %2;\n\t"
 #endif
       "selp.u32 %0, 1, 0, P;\n\t}"
       : "=r"(ok)

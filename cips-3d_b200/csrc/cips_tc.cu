@@ -94,6 +94,10 @@ struct KArgs {
   // this order so the producer streams linearly.
   uint16_t order_full[32];
   uint16_t order_in[4];
+  // PAIR kernel: the same order split by owner -- issuer i (accumulator blocks 2i, 2i+1) has its OWN weight ring and walks only its
+  // tiles.  Entry = order entry | position in the layer's stream order << 16 (the tile's address in the prepared weights).
+  uint32_t own_full[2][16];
+  uint32_t own_in[2][2];
   // training (DUMP instantiation only): every layer's output y_l (after LeakyReLU and residual) as the fp16 values the next
   // layer consumed, (n_layers, B, N, 512) row-major, for the backward pass (cips_bwd_tc.cu).  Appended: the offsets of the
   // fields above are those of the round-1 kernel.
@@ -105,6 +109,11 @@ struct KArgs {
   // A/B knob (C3D_CIPS_STAGGER_NS): CTA i starts i * stagger_ns late, so that the 148 CTAs -- identical work on the same image's 9.4 MB
   // of weights -- do not all stream the same tile at the same moment
   int stagger_ns;
+  // -DC3D_CIPS_ABLATE builds only (tools/build_ablate_lib.sh; timing experiments, results are garbage): bit 0 = epilogue without its
+  // TMEM reads / math / stores, bit 1 = issuers commit without issuing MMAs, bit 2 = producer signals the stages without loading,
+  // bit 3 (with bit 1, single CTA) = plain mbarrier arrives instead of tcgen05.commit, bit 4 = no epilogue warps at all (the issuers do
+  // not wait for them): the weight ring alone
+  int ablate;
 };
 
 template <int CL>
@@ -138,6 +147,48 @@ __device__ __forceinline__ void load_w_tile(void* dst, const uint8_t* src, uint6
 
 __device__ __forceinline__ float lrelu02(float v) { return fmaxf(v, 0.2f * v); }
 
+// Who probes an mbarrier while a warp waits.  0 (the product): every lane; 1: lane 0 probes, the warp joins it at a __syncwarp;
+// 2: as 1 and the 16 epilogue warps wait for their accumulator block behind ONE probing lane and a named barrier.  Measured
+// (profiles/r02u_cips_poll.txt, r02v_mbar_bench.txt): a hand-off to a single probing lane is 2-3x slower than to a full warp
+// (ping-pong 695 vs 271 clk per round trip; the whole kernel 23.6 vs 11.8 ms), and 16 extra polling warps cost the ring nothing.
+#ifndef C3D_CIPS_POLL
+#define C3D_CIPS_POLL 0
+#endif
+__device__ __forceinline__ void wait_warp(uint64_t* bar, uint32_t parity, int lane) {
+#if C3D_CIPS_POLL == 0
+  mbar_wait(bar, parity);
+#else
+  if (lane == 0) mbar_wait(bar, parity);
+  __syncwarp();
+#endif
+}
+__device__ __forceinline__ void wait_warp_cluster(uint64_t* bar, uint32_t parity, int lane) {
+#if C3D_CIPS_POLL == 0
+  mbar_wait_cluster(bar, parity);
+#else
+  if (lane == 0) mbar_wait_cluster(bar, parity);
+  __syncwarp();
+#endif
+}
+// epilogue: all 16 warps wait for the same barrier
+__device__ __forceinline__ void wait_epilogue(uint64_t* bar, uint32_t parity, int warp, int lane) {
+#if C3D_CIPS_POLL == 2
+  if (warp == 4 && lane == 0) mbar_wait(bar, parity);
+  named_bar_sync_c<2, kNumEpiWarps * 32>();
+#else
+  wait_warp(bar, parity, lane);
+#endif
+}
+__device__ __forceinline__ bool test_warp(uint64_t* bar, uint32_t parity, int lane) {
+#if C3D_CIPS_POLL == 0
+  return __all_sync(0xffffffffu, mbar_test(bar, parity)) != 0;
+#elif C3D_CIPS_POLL == 2
+  return false;      // every warp must reach the named barrier of wait_epilogue
+#else
+  return __shfl_sync(0xffffffffu, lane == 0 ? (int)mbar_test(bar, parity) : 0, 0) != 0;
+#endif
+}
+
 #ifdef C3D_TRACE   // debug build: blocks 0 and 1 stamp the pipeline events of tile iteration 1 (steady state).  One fixed slot per
 // (block, warp, stamp index): plain stores, no atomics (an atomic per stamp costs ~500 clk on the stamping warp's critical path).
 constexpr int kTraceCap = 3072;
@@ -152,9 +203,21 @@ __device__ __forceinline__ void trace_ev(int it, uint32_t tag, uint32_t a0, int&
 }
 #define TRACE(it, tag, a0) trace_ev(it, tag, a0, tr_n)
 #define TRACE_DECL int tr_n = 0; (void)tr_n
+// -DC3D_TRACE=1 ("light"): the per-tile stamps of the producer / issuers only at tiles 0, 18 (first of the tail the previous layer's
+// last epilogue chunk unlocks), 22 and 31, and the epilogue stamps by one warp only -- a stamp costs ~170 clk on the stamping warp, and
+// three per tile make the issuers the bottleneck of the traced CTA (profiles/r02r_cips_trace_pair.txt)
+#if C3D_TRACE + 0 == 1
+#define TRACE_TILE(t) ((t) == 0 || (t) == 18 || (t) == 22 || (t) == 31)
+#define TRACE_EPI_WARP(w) ((w) == 4)
+#else
+#define TRACE_TILE(t) true
+#define TRACE_EPI_WARP(w) true
+#endif
 #else
 #define TRACE(it, tag, a0)
 #define TRACE_DECL
+#define TRACE_TILE(t) false
+#define TRACE_EPI_WARP(w) false
 #endif
 
 struct EpiFlags {
@@ -259,9 +322,9 @@ __global__ void __launch_bounds__(kThreads, 1) cips_tc_kernel(const KArgs a) {
       // non-owner's LOCAL observe; the peer's stage only the multicast commit -- its half is read by the MMA alone, so it may refill as
       // soon as that MMA is done, and it can never run more than one fill ahead (its next release needs the leader's next MMA, which
       // needs the leader's own fill).  Round 2's first form sent two release.cluster arrives per non-owned tile from the issue path.
-      mbar_init(&s.empty[i], PAIR ? (leader ? 2 : 1) : 2 * CL);
+      // PAIR: two rings of NS / 2 stages, one per issuer; a stage is released by its issuer's multicast commit alone.
+      mbar_init(&s.empty[i], PAIR ? 1 : 2 * CL);
 #endif
-      if (PAIR) mbar_init(&s.peer_full[i], 1);
     }
     for (int i = 0; i < 4; ++i) mbar_init(&s.epi_done[i], PAIR ? 2 * kNumEpiWarps : kNumEpiWarps);
     for (int i = 0; i < 4; ++i) mbar_init(&s.acc_ready[i], 2);   // two MMA issuer warps, each commits once per layer and chunk
@@ -285,13 +348,136 @@ __global__ void __launch_bounds__(kThreads, 1) cips_tc_kernel(const KArgs a) {
     return PAIR ? (it * grid_units + (int)blockIdx.x / 2) * 2 + (int)crank : it * (int)gridDim.x + (int)blockIdx.x;
   };
   const int L = a.n_layers;
+#ifdef C3D_CIPS_ABLATE
+  const int abl = a.ablate;
+#else
+  constexpr int abl = 0;
+#endif
   if (a.stagger_ns > 0) {        // whole CTA, before any pipeline role starts
     const unsigned long long t_end = c3d_globaltimer() + (unsigned long long)a.stagger_ns * (blockIdx.x / (CL > 1 ? CL : 1));
     while (c3d_globaltimer() < t_end) __nanosleep(100);
     __syncthreads();
   }
 
-  if (warp < 4) {
+  if (warp < 4 && PAIR) {
+    // ================================================================ CTA pair: one weight ring PER ISSUER.
+    // Ring r (stages r * NR .. r * NR + NR - 1, 8 KB each = this CTA's N-half of a tile) carries the tiles of issuer r
+    // (accumulator blocks 2r, 2r+1) in the layer's stream order: warp 2r streams them in (both CTAs), warp 2r + 1 is the issuer
+    // (leader) or relays "my half landed" to the leader's full barrier (peer).  An issuer therefore walks 16 tiles a layer, not 32:
+    // with ONE ring both issuers had to observe every fill (parity aliasing, see the single-CTA path below), and the ~380 clk a
+    // ring step costs an issuer warp even without any work (profiles/r02s_cips_ablate.txt: 6.6 of the kernel's 10.6 ms) was paid
+    // 32 times a layer by both -- the issue loop, not the tensor pipe (256 clk a tile), set the pace.
+    reg_dec<56>();
+    constexpr int NR = NS / 2;
+    const uint32_t ring = (uint32_t)warp >> 1;
+    uint64_t* const full = s.full + ring * NR;
+    uint64_t* const empty = s.empty + ring * NR;
+    uint8_t* const wring = &s.w[0][0] + ring * NR * RC::kStageBytes;
+    TRACE_DECL;
+    uint32_t stage = 0, phase = 0;
+    if ((warp & 1) == 0) {
+      // ---------------------------------------------------------- weight producer of ring `ring`
+      for (int it = 0; it < iters; ++it) {
+        const int tile = tile_of(it);
+        const int img = tile < a.total_tiles ? tile / a.tiles_per_img : 0;     // dummy tiles stream image 0
+        for (int l = 0; l < L; ++l) {
+          const uint8_t* src = reinterpret_cast<const uint8_t*>(a.wtiles) +
+                               ((size_t)img * a.img_tile_stride + (size_t)a.layer_tile_off[l]) * kWTileBytes + crank * RC::kStageBytes;
+          const bool full_layer = a.layer_kc[l] * 4 == 32;
+          const uint32_t* own = full_layer ? a.own_full[ring] : a.own_in[ring];
+          const int n_own = full_layer ? 16 : 2;
+#pragma unroll 1
+          for (int i = 0; i < n_own; ++i) {
+            const uint32_t t = own[i] >> 16;
+            wait_warp(&empty[stage], phase ^ 1, lane);
+            if (lane == 0 && TRACE_TILE(t)) TRACE(it, 10, (uint32_t)(l << 8 | t));                  // producer: stage free, load issued
+            if (abl & 4) {
+              if (elect_one()) mbar_arrive(&full[stage]);
+            } else if (elect_one()) {      // this CTA's half (N rows 64*rank .. +63) of the tile
+              mbar_arrive_expect_tx(&full[stage], RC::kStageBytes);
+              bulk_g2s(wring + stage * RC::kStageBytes, src + (size_t)t * kWTileBytes, RC::kStageBytes, &full[stage]);
+            }
+            __syncwarp();
+            if (++stage == NR) { stage = 0; phase ^= 1; }
+          }
+        }
+      }
+    } else if (!leader) {
+      // ---------------------------------------------------------- peer CTA: relay "my half of this fill has landed" -- the second
+      // arrival of the leader's full barrier (one remote arrive per fill, in ring order)
+      for (int it = 0; it < iters; ++it)
+        for (int l = 0; l < L; ++l) {
+          const bool full_layer = a.layer_kc[l] * 4 == 32;
+          const uint32_t* own = full_layer ? a.own_full[ring] : a.own_in[ring];
+          const int n_own = full_layer ? 16 : 2;
+#pragma unroll 1
+          for (int i = 0; i < n_own; ++i) {
+            wait_warp(&full[stage], phase, lane);
+            if (lane == 0 && TRACE_TILE(own[i] >> 16)) TRACE(it, 11, (uint32_t)(l << 8 | (own[i] >> 16)));
+            if (elect_one()) mbar_arrive_cluster(&full[stage], 0);
+            __syncwarp();
+            if (++stage == NR) { stage = 0; phase ^= 1; }
+          }
+        }
+    } else {
+      // ---------------------------------------------------------- MMA issuer `ring` (leader CTA; whole warp converged, one lane issues)
+      const uint32_t me = ring;
+      const uint32_t idesc = umma_idesc_f16(2 * kTileM, kNC);
+      const uint32_t dhi = umma_desc_hi(kSBO);
+      const uint32_t a_lo0 = umma_desc_lo(smem_u32(s.x), kLBO);
+      const uint32_t b_lo0 = umma_desc_lo(smem_u32(wring), RC::kLBO_B);
+      constexpr uint32_t kStepK16 = (2 * kLBO) >> 4;       // one K=16 MMA step  = 2 core-matrix columns
+      constexpr uint32_t kStepK16B = (2 * RC::kLBO_B) >> 4;
+      constexpr uint32_t kStepStage = RC::kStageBytes >> 4;
+      for (int it = 0; it < iters; ++it) {
+        for (int l = 0; l < L; ++l) {
+          const uint32_t epar = (uint32_t)(it * L + l) & 1u;   // phase of the epilogue that feeds layer l (staging for l = 0)
+          const bool full_layer = a.layer_kc[l] * 4 == 32;
+          const uint32_t* own = full_layer ? a.own_full[ring] : a.own_in[ring];
+          const int n_own = full_layer ? 16 : 2;
+          int waited = -1;
+          uint32_t e = own[0];
+#pragma unroll 1
+          for (int i = 0; i < n_own; ++i) {
+            const uint32_t e_next = own[i + 1 < n_own ? i + 1 : i];      // fetched ahead of the waits
+            const uint32_t kc = e & 15u, nc = (e >> 4) & 15u, t = e >> 16;
+            const int need = (int)((e >> 8) & 15u);
+            if (lane == 0 && TRACE_TILE(t)) TRACE(it, 1 + me, (uint32_t)(l << 8 | t));          // tile reached
+            if (need > waited && !(abl & 16)) {
+              for (int j = waited + 1; j <= need; ++j) wait_warp_cluster(&s.epi_done[j], epar, lane);     // half of the arrivals come from the peer CTA
+              waited = need;
+            }
+            if (lane == 0 && TRACE_TILE(t)) TRACE(it, 3 + me, (uint32_t)(l << 8 | t));          // epilogue dependency satisfied
+            wait_warp(&full[stage], phase, lane);
+            if (lane == 0 && TRACE_TILE(t)) TRACE(it, 5 + me, (uint32_t)(l << 8 | t));          // weight tile landed (both halves)
+            tc_fence_after();
+            if (elect_one()) {
+              const uint32_t a_lo = a_lo0 + kc * (kStepK16 * (kKC / 16));
+              const uint32_t b_lo = b_lo0 + stage * kStepStage;
+              const uint32_t d = tmem + nc * kNC;
+              if (!(abl & 2)) {
+                umma_ss_w_cg2(d, a_lo, b_lo, dhi, idesc, kc != 0);
+                umma_ss_w_cg2(d, a_lo + kStepK16, b_lo + kStepK16B, dhi, idesc, 1);
+                umma_ss_w_cg2(d, a_lo + 2 * kStepK16, b_lo + 2 * kStepK16B, dhi, idesc, 1);
+                umma_ss_w_cg2(d, a_lo + 3 * kStepK16, b_lo + 3 * kStepK16B, dhi, idesc, 1);
+              }
+              tc_commit_cg2_mc(&empty[stage], 3);      // stage free in BOTH CTAs
+              const uint32_t rdy = (e >> 12) & 15u;    // chunks j for which this is the issuer's last tile of S_j
+              if (rdy) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                  if (rdy & (1u << j)) tc_commit_cg2_mc(&s.acc_ready[j], 3);
+              }
+            }
+            __syncwarp();
+            if (++stage == NR) { stage = 0; phase ^= 1; }
+            e = e_next;
+          }
+        }
+      }
+    }
+  } else if (warp < 4) {
+    // ================================================================ single CTA (and multicast clusters): one ring, two issuers
     reg_dec<56>();
     if (warp == 0) {
       // ---------------------------------------------------------- weight producer (whole warp converged, one lane issues)
@@ -305,9 +491,11 @@ __global__ void __launch_bounds__(kThreads, 1) cips_tc_kernel(const KArgs a) {
                                ((size_t)img * a.img_tile_stride + (size_t)a.layer_tile_off[l]) * kWTileBytes;
           const int ntiles = a.layer_kc[l] * 4;
           for (int t = 0; t < ntiles; ++t) {
-            mbar_wait(&s.empty[stage], phase ^ 1);
-            if (lane == 0) TRACE(it, 10, (uint32_t)(l << 8 | t));                  // producer: stage free, load issued
-            if (elect_one()) {
+            wait_warp(&s.empty[stage], phase ^ 1, lane);
+            if (lane == 0 && TRACE_TILE(t)) TRACE(it, 10, (uint32_t)(l << 8 | t));                  // producer: stage free, load issued
+            if (abl & 4) {
+              if (elect_one()) mbar_arrive(&s.full[stage]);
+            } else if (elect_one()) {
               if (PAIR) {      // this CTA's half (N rows 64*rank .. +63) of the tile
                 mbar_arrive_expect_tx(&s.full[stage], RC::kStageBytes);
                 bulk_g2s(&s.w[0][0] + stage * RC::kStageBytes, src + (size_t)t * kWTileBytes + crank * RC::kStageBytes,
@@ -333,8 +521,8 @@ __global__ void __launch_bounds__(kThreads, 1) cips_tc_kernel(const KArgs a) {
             const int ntiles = a.layer_kc[l] * 4;
 #pragma unroll 1
             for (int t = 0; t < ntiles; ++t) {
-              mbar_wait(&s.full[stage], phase);
-              if (lane == 0) TRACE(it, 11, (uint32_t)(l << 8 | t));                // peer: my half landed, relaying
+              wait_warp(&s.full[stage], phase, lane);
+              if (lane == 0 && TRACE_TILE(t)) TRACE(it, 11, (uint32_t)(l << 8 | t));                // peer: my half landed, relaying
               if (elect_one()) mbar_arrive_cluster(&s.full[stage], 0);      // second arrival of the leader's full[stage]
               __syncwarp();
               if (++stage == NS) { stage = 0; phase ^= 1; }
@@ -370,15 +558,15 @@ __global__ void __launch_bounds__(kThreads, 1) cips_tc_kernel(const KArgs a) {
             const bool mine = (nc >> 1) == me;
             if (mine) {
               const int need = (int)((e >> 8) & 15u);
-              if (lane == 0) TRACE(it, 1 + me, (uint32_t)(l << 8 | t));          // tile reached
-              if (need > waited) {
+              if (lane == 0 && TRACE_TILE(t)) TRACE(it, 1 + me, (uint32_t)(l << 8 | t));          // tile reached
+              if (need > waited && !(abl & 16)) {
                 for (int j = waited + 1; j <= need; ++j) {
-                  if (PAIR) mbar_wait_cluster(&s.epi_done[j], epar);     // half of the arrivals come from the peer CTA
-                  else mbar_wait(&s.epi_done[j], epar);
+                  if (PAIR) wait_warp_cluster(&s.epi_done[j], epar, lane);     // half of the arrivals come from the peer CTA
+                  else wait_warp(&s.epi_done[j], epar, lane);
                 }
                 waited = need;
               }
-              if (lane == 0) TRACE(it, 3 + me, (uint32_t)(l << 8 | t));          // epilogue dependency satisfied
+              if (lane == 0 && TRACE_TILE(t)) TRACE(it, 3 + me, (uint32_t)(l << 8 | t));          // epilogue dependency satisfied
             }
             // BOTH issuers observe every fill of every stage, in ring order, and a stage is released only when
             // both have (empty count 2): an issuer that skipped the phases of tiles it does not own could see
@@ -386,15 +574,23 @@ __global__ void __launch_bounds__(kThreads, 1) cips_tc_kernel(const KArgs a) {
 #ifdef C3D_INJECT_RING_RACE
             if (mine)
 #endif
-            mbar_wait(&s.full[stage], phase);
+            wait_warp(&s.full[stage], phase, lane);
             if (mine) {
-              if (lane == 0) TRACE(it, 5 + me, (uint32_t)(l << 8 | t));          // weight tile landed
+              if (lane == 0 && TRACE_TILE(t)) TRACE(it, 5 + me, (uint32_t)(l << 8 | t));          // weight tile landed
               tc_fence_after();
               if (elect_one()) {
                 const uint32_t a_lo = a_lo0 + kc * (kStepK16 * (kKC / 16));
                 const uint32_t b_lo = b_lo0 + stage * kStepStage;
                 const uint32_t d = tmem + nc * kNC;
-                if (PAIR) {
+                if ((abl & 10) == 10 && !PAIR && CL == 1) {      // no MMAs in flight: plain arrives stand in for the commits
+                  mbar_arrive(&s.empty[stage]);
+                  const uint32_t rdy8 = e >> 12;
+                  for (int j = 0; j < 4; ++j)
+                    if (rdy8 & (1u << j)) mbar_arrive(&s.acc_ready[j]);
+                } else if (abl & 2) {
+                  if (PAIR) tc_commit_cg2_mc(&s.empty[stage], 3);
+                  else commit_stage_free<CL>(&s.empty[stage]);
+                } else if (PAIR) {
                   umma_ss_w_cg2(d, a_lo, b_lo, dhi, idesc, kc != 0);
                   umma_ss_w_cg2(d, a_lo + kStepK16, b_lo + kStepK16B, dhi, idesc, 1);
                   umma_ss_w_cg2(d, a_lo + 2 * kStepK16, b_lo + 2 * kStepK16B, dhi, idesc, 1);
@@ -407,7 +603,7 @@ __global__ void __launch_bounds__(kThreads, 1) cips_tc_kernel(const KArgs a) {
                   umma_ss_w(d, a_lo + 3 * kStepK16, b_lo + 3 * kStepK16, dhi, idesc, 1);
                   commit_stage_free<CL>(&s.empty[stage]);
                 }
-                const uint32_t rdy = e >> 12;    // chunks j for which this is the issuer's last tile of S_j
+                const uint32_t rdy = ((abl & 10) == 10 && !PAIR && CL == 1) ? 0u : e >> 12;    // chunks j for which this is the issuer's last tile of S_j
                 if (rdy) {
 #pragma unroll
                   for (int j = 0; j < 4; ++j)
@@ -440,7 +636,7 @@ __global__ void __launch_bounds__(kThreads, 1) cips_tc_kernel(const KArgs a) {
     const int row = q * 32 + lane;     // row of the tile this thread owns
     const uint32_t trow = tmem + ((uint32_t)(q * 32) << 16);
     float4* resid = a.resid + (size_t)blockIdx.x * (kH / 4) * kTileM;
-    for (int it = 0; it < iters; ++it) {
+    for (int it = 0; it < ((abl & 16) ? 0 : iters); ++it) {
       const int tile = tile_of(it);
       const bool tile_ok = tile < a.total_tiles;
       const int img = tile_ok ? tile / a.tiles_per_img : 0;
@@ -518,9 +714,21 @@ __global__ void __launch_bounds__(kThreads, 1) cips_tc_kernel(const KArgs a) {
         if (f.add_res) load_res(rsA, rp);
 #pragma unroll 1
         for (int j = 0; j < 4; ++j) {
+          if (abl & 1) {
+            wait_epilogue(&s.acc_ready[j], apar, warp, lane);
+            tc_fence_after();
+            fence_proxy_async();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0 && !f.last) {
+              if (PAIR) mbar_arrive_cluster(&s.epi_done[j], 0);
+              else mbar_arrive(&s.epi_done[j]);
+            }
+            continue;
+          }
           if (!have) {
-            mbar_wait(&s.acc_ready[j], apar);
-            if (lane == 0) TRACE(it, 8, (uint32_t)(l << 8 | j));                 // accumulator block j complete
+            wait_epilogue(&s.acc_ready[j], apar, warp, lane);
+            if (lane == 0 && TRACE_EPI_WARP(warp)) TRACE(it, 8, (uint32_t)(l << 8 | j));                 // accumulator block j complete
             tc_fence_after();
             tmem_ld16(tcol, accA);
           }
@@ -532,7 +740,7 @@ __global__ void __launch_bounds__(kThreads, 1) cips_tc_kernel(const KArgs a) {
           tc_wait_ld();
           have = false;
           if (j < 3) {
-            have = __all_sync(0xffffffffu, mbar_test(&s.acc_ready[j + 1], apar)) != 0;
+            have = test_warp(&s.acc_ready[j + 1], apar, lane);
             if (have) {
               tc_fence_after();
               tmem_ld16(tcol + 128, accA);
@@ -551,7 +759,7 @@ __global__ void __launch_bounds__(kThreads, 1) cips_tc_kernel(const KArgs a) {
             if (PAIR) mbar_arrive_cluster(&s.epi_done[j], 0);
             else mbar_arrive(&s.epi_done[j]);
           }
-          if (lane == 0) TRACE(it, 9, (uint32_t)(l << 8 | (warp - 4) << 2 | j));   // warp finished chunk j
+          if (lane == 0 && TRACE_EPI_WARP(warp)) TRACE(it, 9, (uint32_t)(l << 8 | (warp - 4) << 2 | j));   // warp finished chunk j
           tcol += 128; rp += 32 * kTileM; xp += 16 * kLBO; rwp += 128;
           if (hp) hp += 128;
           if (dp) dp += 16;
@@ -843,6 +1051,10 @@ int c3d_cips_fwd_tc(const C3dCipsParams* p, const C3dCipsWeights* w, const float
   ka.acts = (__half*)acts_f16;
   ka.zsign = (uint16_t*)zsign_u16;
   ka.stagger_ns = c3d_options().cips_stagger_ns;
+  ka.ablate = 0;
+#ifdef C3D_CIPS_ABLATE
+  if (const char* e = getenv("C3D_CIPS_ABLATE")) ka.ablate = atoi(e);
+#endif
   ka.acts_layer_stride = (size_t)p->batch * p->n_pix * kH;
   ka.wtiles = (const __half*)(base + ws.wtiles);
   ka.rgbw = (const float4*)(base + ws.rgbw);
@@ -861,6 +1073,14 @@ int c3d_cips_fwd_tc(const C3dCipsParams* p, const C3dCipsWeights* w, const float
   ka.layer_tile_off[L] = off;
   ka.img_tile_stride = (size_t)off;
   build_tile_order(ka.order_full, ka.order_in);
+  for (int me = 0; me < 2; ++me) {      // the same order, split by owner (PAIR kernel: one ring per issuer)
+    int n = 0;
+    for (int t = 0; t < 32; ++t)
+      if ((((ka.order_full[t] >> 4) & 15) >> 1) == me) ka.own_full[me][n++] = (uint32_t)ka.order_full[t] | (uint32_t)t << 16;
+    n = 0;
+    for (int t = 0; t < 4; ++t)
+      if ((((ka.order_in[t] >> 4) & 15) >> 1) == me) ka.own_in[me][n++] = (uint32_t)ka.order_in[t] | (uint32_t)t << 16;
+  }
   int cl = 1;
   bool pair = false;
   const int grid = cips_grid(p, &cl, &pair);
