@@ -42,13 +42,14 @@ constexpr int kWTileBytes = kKC * kNC * 2;              // 16 KB
 #define C3D_CIPS_STAGES 5
 #endif
 constexpr int kStages = C3D_CIPS_STAGES;      // depth of the weight ring (5 x 16 KB is what fits beside the 128 KB activation tile)
-// CTA-pair variant (PAIR, tcgen05 cta_group::2): an MMA is M = 256 (128 pixels in each CTA of the pair) x N = 128 and
-// each CTA holds -- and streams from L2 -- only HALF of every weight tile (64 of its 128 N rows, 8 KB), so the ring
-// has twice the stages in the same 80 KB and the L2 -> SM weight traffic per SM is halved.
+// CTA-pair variant (PAIR, tcgen05 cta_group::2): an MMA is M = 256 (128 pixels in each CTA of the pair) x N = 256, and each CTA
+// holds -- and streams from L2 -- the 128 N rows of its half: a ring stage is again one 16 KB (kc, nc) tile, CTA r holding
+// (kc, 2h + r) of the "big tile" (kc, h).  Per CTA and layer that is half the weight traffic and half the A-operand reads of the
+// single-CTA kernel, and 16 issue steps instead of 32 (see the PAIR branch of the kernel).
 template <bool PAIR> struct RingCfg {
-  static constexpr int kStagesP = PAIR ? 2 * kStages : kStages;
-  static constexpr int kStageBytes = PAIR ? kWTileBytes / 2 : kWTileBytes;
-  static constexpr int kLBO_B = PAIR ? (kNC / 2) * 16 : kNC * 16;     // K-direction core-matrix stride of the B tile
+  static constexpr int kStagesP = kStages;
+  static constexpr int kStageBytes = kWTileBytes;
+  static constexpr int kLBO_B = kNC * 16;     // K-direction core-matrix stride of the B tile (128 rows)
 };
 constexpr int kXBytes = kTileM * kH * 2;                // 128 KB
 constexpr int kLBO = kTileM * 16;                       // 2048: K-direction core-matrix stride (A and B tiles have 128 rows)
@@ -61,7 +62,7 @@ template <bool PAIR>
 struct SmemT {
   static constexpr int NS = RingCfg<PAIR>::kStagesP;
   alignas(1024) uint8_t x[kXBytes];
-  alignas(1024) uint8_t w[kStages][kWTileBytes];   // PAIR: 10 stages of 8 KB in the same bytes
+  alignas(1024) uint8_t w[kStages][kWTileBytes];
   union {                                // ToRGB weights of the current block / per-tile rgb partial sums
     float4 rgbw[kH];
     float rgb_part[4][kTileM][4];
@@ -72,7 +73,6 @@ struct SmemT {
   uint64_t acc_ready[4];   // accumulator block j complete AND A-operand chunk j no longer read by this layer's MMAs
   uint32_t tmem_base;
   uint32_t pad_;
-  uint64_t peer_full[PAIR ? NS : 1];   // PAIR, leader CTA only: the peer CTA's half of stage s has landed (relayed by the peer)
 };
 using Smem = SmemT<false>;
 
@@ -94,10 +94,11 @@ struct KArgs {
   // this order so the producer streams linearly.
   uint16_t order_full[32];
   uint16_t order_in[4];
-  // PAIR kernel: the same order split by owner -- issuer i (accumulator blocks 2i, 2i+1) has its OWN weight ring and walks only its
-  // tiles.  Entry = order entry | position in the layer's stream order << 16 (the tile's address in the prepared weights).
-  uint32_t own_full[2][16];
-  uint32_t own_in[2][2];
+  // PAIR kernel: issue order of the 16 big tiles (kc, h) of a layer -- h = which 256 accumulator columns -- and of the 2 of the
+  // input layer: kc | h << 4 | need << 8 | acc_ready commit mask << 12.  The prepared weights hold them in this order, CTA 0's half
+  // (kc, 2h) followed by CTA 1's (kc, 2h + 1).
+  uint16_t big_full[16];
+  uint16_t big_in[2];
   // training (DUMP instantiation only): every layer's output y_l (after LeakyReLU and residual) as the fp16 values the next
   // layer consumed, (n_layers, B, N, 512) row-major, for the backward pass (cips_bwd_tc.cu).  Appended: the offsets of the
   // fields above are those of the round-1 kernel.
@@ -207,7 +208,7 @@ __device__ __forceinline__ void trace_ev(int it, uint32_t tag, uint32_t a0, int&
 // last epilogue chunk unlocks), 22 and 31, and the epilogue stamps by one warp only -- a stamp costs ~170 clk on the stamping warp, and
 // three per tile make the issuers the bottleneck of the traced CTA (profiles/r02r_cips_trace_pair.txt)
 #if C3D_TRACE + 0 == 1
-#define TRACE_TILE(t) ((t) == 0 || (t) == 18 || (t) == 22 || (t) == 31)
+#define TRACE_TILE(t) ((t) == 0 || (t) == 6 || (t) == 10 || (t) == 15 || (t) == 18 || (t) == 22 || (t) == 31)
 #define TRACE_EPI_WARP(w) ((w) == 4)
 #else
 #define TRACE_TILE(t) true
@@ -290,10 +291,10 @@ __device__ __forceinline__ void epi16(const uint32_t (&acc)[16], const float4 (&
 }
 
 // PAIR (CL == 2 only): the two CTAs of a cluster form a tcgen05 CTA pair.  Only the leader (cluster rank 0) issues MMAs
-// (cta_group::2, M = 256: the leader's 128 pixels and the peer's 128 pixels against the same weight tile); each CTA
-// streams HALF of every weight tile into its own ring; the peer relays "my half landed" to the leader (peer_full);
+// (cta_group::2, M = 256: the leader's 128 pixels and the peer's 128 pixels against the same 256 weight columns); each CTA
+// streams ITS half of every big weight tile into its own ring; the peer relays "my half landed" to the leader's full barrier;
 // both CTAs' epilogue warps report to the leader's epi_done barriers; the leader's commits are multicast to the
-// empty / acc_ready barriers of both CTAs.  Everything else (tile order, staircase, epilogue) is the single-CTA kernel.
+// empty / acc_ready barriers of both CTAs.  The epilogue (4 chunks of 128 columns a layer) is the single-CTA kernel's.
 template <int CL, bool PAIR = false, bool DUMP = false>
 __global__ void __launch_bounds__(kThreads, 1) cips_tc_kernel(const KArgs a) {
   static_assert(!PAIR || CL == 2, "a CTA pair is a cluster of two");
@@ -310,24 +311,17 @@ __global__ void __launch_bounds__(kThreads, 1) cips_tc_kernel(const KArgs a) {
   if (threadIdx.x == 0) {
     for (int i = 0; i < NS; ++i) {
       // PAIR, leader: a fill of stage i is complete when the leader's own half has landed (its producer's arrive + bytes) AND the
-      // peer has relayed "my half landed" with one remote arrive on this SAME barrier -- the issuers then wait on one CTA-local
-      // barrier per tile.  (Round 2's first form kept a separate peer_full barrier that both issuers polled with
-      // try_wait.acquire.cluster: ~350 clk per wait, twice per tile, serialised on the MMA issue path -- 1 370 clk per weight tile,
-      // profiles/r02o_cips_trace_pair.txt.)
+      // peer has relayed "my half landed" with one remote arrive on this SAME barrier -- the issuer waits on one CTA-local barrier.
       mbar_init(&s.full[i], (PAIR && leader) ? 2 : 1);
 #ifdef C3D_INJECT_RING_RACE           // test-only (tests/test_emu_cpu.py): re-creates the round-1 parity-aliasing race
       mbar_init(&s.empty[i], CL);
 #else
-      // both issuers release every stage (see the issuer loop).  PAIR: the leader's stage needs the owner's (multicast) commit and the
-      // non-owner's LOCAL observe; the peer's stage only the multicast commit -- its half is read by the MMA alone, so it may refill as
-      // soon as that MMA is done, and it can never run more than one fill ahead (its next release needs the leader's next MMA, which
-      // needs the leader's own fill).  Round 2's first form sent two release.cluster arrives per non-owned tile from the issue path.
-      // PAIR: two rings of NS / 2 stages, one per issuer; a stage is released by its issuer's multicast commit alone.
+      // both issuers release every stage (see the issuer loop); PAIR: one issuer, whose multicast commit releases the stage in both CTAs
       mbar_init(&s.empty[i], PAIR ? 1 : 2 * CL);
 #endif
     }
     for (int i = 0; i < 4; ++i) mbar_init(&s.epi_done[i], PAIR ? 2 * kNumEpiWarps : kNumEpiWarps);
-    for (int i = 0; i < 4; ++i) mbar_init(&s.acc_ready[i], 2);   // two MMA issuer warps, each commits once per layer and chunk
+    for (int i = 0; i < 4; ++i) mbar_init(&s.acc_ready[i], PAIR ? 1 : 2);   // one commit per issuer warp, layer and chunk (PAIR: one issuer)
     fence_mbar_init();
   }
   if (warp == 2) {
@@ -360,109 +354,102 @@ __global__ void __launch_bounds__(kThreads, 1) cips_tc_kernel(const KArgs a) {
   }
 
   if (warp < 4 && PAIR) {
-    // ================================================================ CTA pair: one weight ring PER ISSUER.
-    // Ring r (stages r * NR .. r * NR + NR - 1, 8 KB each = this CTA's N-half of a tile) carries the tiles of issuer r
-    // (accumulator blocks 2r, 2r+1) in the layer's stream order: warp 2r streams them in (both CTAs), warp 2r + 1 is the issuer
-    // (leader) or relays "my half landed" to the leader's full barrier (peer).  An issuer therefore walks 16 tiles a layer, not 32:
-    // with ONE ring both issuers had to observe every fill (parity aliasing, see the single-CTA path below), and the ~380 clk a
-    // ring step costs an issuer warp even without any work (profiles/r02s_cips_ablate.txt: 6.6 of the kernel's 10.6 ms) was paid
-    // 32 times a layer by both -- the issue loop, not the tensor pipe (256 clk a tile), set the pace.
+    // ================================================================ CTA pair: ONE issuer, N = 256 MMAs.
+    // What the measurements of round 2 say about the issue side (profiles/r02s..r02y): an issuer warp cannot turn a ring step
+    // (wait for the fill, issue, commit) around in less than ~350 clk, whatever the step contains, and the tensor pipe needs
+    // 64 clk per N = 128 MMA -- so with 4 MMAs a step (256 clk of work) the ISSUE LOOP sets the pace, not the tensor pipe
+    // (first pair form, two issuers sharing one ring and observing every fill: 10.6 ms; one ring per issuer: 9.25 ms;
+    // 4.1 ms of either is there with all the work removed).  An N = 256 MMA is 128 clk: 4 of them are 512 clk of work per step,
+    // one issuer thread keeps the pipe full (microbenchmark: 513 clk per step sustained), the layer is 16 steps, and the A operand
+    // is read from shared memory twice per layer instead of four times (the MMA operand reads + the weight stream + the epilogue's
+    // stores are ~144 B/clk of shared-memory traffic at the tensor floor with N = 128, ~112 B/clk with N = 256; the port gives 128).
+    // Roles: warp 0 streams this CTA's half of every big tile (both CTAs), warp 1 issues (leader) or relays "my half landed" to the
+    // leader's full barrier (peer), warp 2 owns the TMEM allocation, warp 3 idles.
     reg_dec<56>();
-    constexpr int NR = NS / 2;
-    const uint32_t ring = (uint32_t)warp >> 1;
-    uint64_t* const full = s.full + ring * NR;
-    uint64_t* const empty = s.empty + ring * NR;
-    uint8_t* const wring = &s.w[0][0] + ring * NR * RC::kStageBytes;
     TRACE_DECL;
     uint32_t stage = 0, phase = 0;
-    if ((warp & 1) == 0) {
-      // ---------------------------------------------------------- weight producer of ring `ring`
+    if (warp == 0) {
+      // ---------------------------------------------------------- weight producer
       for (int it = 0; it < iters; ++it) {
         const int tile = tile_of(it);
         const int img = tile < a.total_tiles ? tile / a.tiles_per_img : 0;     // dummy tiles stream image 0
         for (int l = 0; l < L; ++l) {
           const uint8_t* src = reinterpret_cast<const uint8_t*>(a.wtiles) +
-                               ((size_t)img * a.img_tile_stride + (size_t)a.layer_tile_off[l]) * kWTileBytes + crank * RC::kStageBytes;
-          const bool full_layer = a.layer_kc[l] * 4 == 32;
-          const uint32_t* own = full_layer ? a.own_full[ring] : a.own_in[ring];
-          const int n_own = full_layer ? 16 : 2;
+                               ((size_t)img * a.img_tile_stride + (size_t)a.layer_tile_off[l] + crank) * kWTileBytes;
+          const int n_big = a.layer_kc[l] * 2;
 #pragma unroll 1
-          for (int i = 0; i < n_own; ++i) {
-            const uint32_t t = own[i] >> 16;
-            wait_warp(&empty[stage], phase ^ 1, lane);
-            if (lane == 0 && TRACE_TILE(t)) TRACE(it, 10, (uint32_t)(l << 8 | t));                  // producer: stage free, load issued
+          for (int i = 0; i < n_big; ++i) {
+            wait_warp(&s.empty[stage], phase ^ 1, lane);
+            if (lane == 0 && TRACE_TILE(i)) TRACE(it, 10, (uint32_t)(l << 8 | i));                  // producer: stage free, load issued
             if (abl & 4) {
-              if (elect_one()) mbar_arrive(&full[stage]);
-            } else if (elect_one()) {      // this CTA's half (N rows 64*rank .. +63) of the tile
-              mbar_arrive_expect_tx(&full[stage], RC::kStageBytes);
-              bulk_g2s(wring + stage * RC::kStageBytes, src + (size_t)t * kWTileBytes, RC::kStageBytes, &full[stage]);
+              if (elect_one()) mbar_arrive(&s.full[stage]);
+            } else if (elect_one()) {      // this CTA's half of big tile i: stream tile 2 i + rank
+              mbar_arrive_expect_tx(&s.full[stage], kWTileBytes);
+              bulk_g2s(s.w[stage], src + (size_t)(2 * i) * kWTileBytes, kWTileBytes, &s.full[stage]);
             }
             __syncwarp();
-            if (++stage == NR) { stage = 0; phase ^= 1; }
+            if (++stage == NS) { stage = 0; phase ^= 1; }
           }
         }
       }
-    } else if (!leader) {
+    } else if (warp == 1 && !leader) {
       // ---------------------------------------------------------- peer CTA: relay "my half of this fill has landed" -- the second
       // arrival of the leader's full barrier (one remote arrive per fill, in ring order)
       for (int it = 0; it < iters; ++it)
         for (int l = 0; l < L; ++l) {
-          const bool full_layer = a.layer_kc[l] * 4 == 32;
-          const uint32_t* own = full_layer ? a.own_full[ring] : a.own_in[ring];
-          const int n_own = full_layer ? 16 : 2;
+          const int n_big = a.layer_kc[l] * 2;
 #pragma unroll 1
-          for (int i = 0; i < n_own; ++i) {
-            wait_warp(&full[stage], phase, lane);
-            if (lane == 0 && TRACE_TILE(own[i] >> 16)) TRACE(it, 11, (uint32_t)(l << 8 | (own[i] >> 16)));
-            if (elect_one()) mbar_arrive_cluster(&full[stage], 0);
+          for (int i = 0; i < n_big; ++i) {
+            wait_warp(&s.full[stage], phase, lane);
+            if (lane == 0 && TRACE_TILE(i)) TRACE(it, 11, (uint32_t)(l << 8 | i));
+            if (elect_one()) mbar_arrive_cluster(&s.full[stage], 0);
             __syncwarp();
-            if (++stage == NR) { stage = 0; phase ^= 1; }
+            if (++stage == NS) { stage = 0; phase ^= 1; }
           }
         }
-    } else {
-      // ---------------------------------------------------------- MMA issuer `ring` (leader CTA; whole warp converged, one lane issues)
-      const uint32_t me = ring;
-      const uint32_t idesc = umma_idesc_f16(2 * kTileM, kNC);
+    } else if (warp == 1) {
+      // ---------------------------------------------------------- MMA issuer (leader CTA; whole warp converged, one lane issues)
+      const uint32_t idesc = umma_idesc_f16(2 * kTileM, 2 * kNC);
       const uint32_t dhi = umma_desc_hi(kSBO);
       const uint32_t a_lo0 = umma_desc_lo(smem_u32(s.x), kLBO);
-      const uint32_t b_lo0 = umma_desc_lo(smem_u32(wring), RC::kLBO_B);
+      const uint32_t b_lo0 = umma_desc_lo(smem_u32(s.w[0]), RC::kLBO_B);
       constexpr uint32_t kStepK16 = (2 * kLBO) >> 4;       // one K=16 MMA step  = 2 core-matrix columns
       constexpr uint32_t kStepK16B = (2 * RC::kLBO_B) >> 4;
       constexpr uint32_t kStepStage = RC::kStageBytes >> 4;
       for (int it = 0; it < iters; ++it) {
         for (int l = 0; l < L; ++l) {
           const uint32_t epar = (uint32_t)(it * L + l) & 1u;   // phase of the epilogue that feeds layer l (staging for l = 0)
-          const bool full_layer = a.layer_kc[l] * 4 == 32;
-          const uint32_t* own = full_layer ? a.own_full[ring] : a.own_in[ring];
-          const int n_own = full_layer ? 16 : 2;
+          const bool full_layer = a.layer_kc[l] * 2 == 16;
+          const uint16_t* big = full_layer ? a.big_full : a.big_in;
+          const int n_big = full_layer ? 16 : 2;
           int waited = -1;
-          uint32_t e = own[0];
+          uint32_t e = big[0];
 #pragma unroll 1
-          for (int i = 0; i < n_own; ++i) {
-            const uint32_t e_next = own[i + 1 < n_own ? i + 1 : i];      // fetched ahead of the waits
-            const uint32_t kc = e & 15u, nc = (e >> 4) & 15u, t = e >> 16;
+          for (int i = 0; i < n_big; ++i) {
+            const uint32_t e_next = big[i + 1 < n_big ? i + 1 : i];      // fetched ahead of the waits
+            const uint32_t kc = e & 15u, h = (e >> 4) & 15u;
             const int need = (int)((e >> 8) & 15u);
-            if (lane == 0 && TRACE_TILE(t)) TRACE(it, 1 + me, (uint32_t)(l << 8 | t));          // tile reached
+            if (lane == 0 && TRACE_TILE(i)) TRACE(it, 1, (uint32_t)(l << 8 | i));          // tile reached
             if (need > waited && !(abl & 16)) {
               for (int j = waited + 1; j <= need; ++j) wait_warp_cluster(&s.epi_done[j], epar, lane);     // half of the arrivals come from the peer CTA
               waited = need;
             }
-            if (lane == 0 && TRACE_TILE(t)) TRACE(it, 3 + me, (uint32_t)(l << 8 | t));          // epilogue dependency satisfied
-            wait_warp(&full[stage], phase, lane);
-            if (lane == 0 && TRACE_TILE(t)) TRACE(it, 5 + me, (uint32_t)(l << 8 | t));          // weight tile landed (both halves)
+            if (lane == 0 && TRACE_TILE(i)) TRACE(it, 3, (uint32_t)(l << 8 | i));          // epilogue dependency satisfied
+            wait_warp(&s.full[stage], phase, lane);
+            if (lane == 0 && TRACE_TILE(i)) TRACE(it, 5, (uint32_t)(l << 8 | i));          // weight tile landed (both halves)
             tc_fence_after();
             if (elect_one()) {
               const uint32_t a_lo = a_lo0 + kc * (kStepK16 * (kKC / 16));
               const uint32_t b_lo = b_lo0 + stage * kStepStage;
-              const uint32_t d = tmem + nc * kNC;
+              const uint32_t d = tmem + h * (2 * kNC);
               if (!(abl & 2)) {
                 umma_ss_w_cg2(d, a_lo, b_lo, dhi, idesc, kc != 0);
                 umma_ss_w_cg2(d, a_lo + kStepK16, b_lo + kStepK16B, dhi, idesc, 1);
                 umma_ss_w_cg2(d, a_lo + 2 * kStepK16, b_lo + 2 * kStepK16B, dhi, idesc, 1);
                 umma_ss_w_cg2(d, a_lo + 3 * kStepK16, b_lo + 3 * kStepK16B, dhi, idesc, 1);
               }
-              tc_commit_cg2_mc(&empty[stage], 3);      // stage free in BOTH CTAs
-              const uint32_t rdy = (e >> 12) & 15u;    // chunks j for which this is the issuer's last tile of S_j
+              tc_commit_cg2_mc(&s.empty[stage], 3);      // stage free in BOTH CTAs
+              const uint32_t rdy = (e >> 12) & 15u;    // chunks j whose set S_j this tile completes
               if (rdy) {
 #pragma unroll
                 for (int j = 0; j < 4; ++j)
@@ -470,7 +457,7 @@ __global__ void __launch_bounds__(kThreads, 1) cips_tc_kernel(const KArgs a) {
               }
             }
             __syncwarp();
-            if (++stage == NR) { stage = 0; phase ^= 1; }
+            if (++stage == NS) { stage = 0; phase ^= 1; }
             e = e_next;
           }
         }
@@ -496,38 +483,13 @@ __global__ void __launch_bounds__(kThreads, 1) cips_tc_kernel(const KArgs a) {
             if (abl & 4) {
               if (elect_one()) mbar_arrive(&s.full[stage]);
             } else if (elect_one()) {
-              if (PAIR) {      // this CTA's half (N rows 64*rank .. +63) of the tile
-                mbar_arrive_expect_tx(&s.full[stage], RC::kStageBytes);
-                bulk_g2s(&s.w[0][0] + stage * RC::kStageBytes, src + (size_t)t * kWTileBytes + crank * RC::kStageBytes,
-                         RC::kStageBytes, &s.full[stage]);
-              } else {
-                mbar_arrive_expect_tx(&s.full[stage], kWTileBytes);
-                load_w_tile<CL>(s.w[stage], src + (size_t)t * kWTileBytes, &s.full[stage], crank);
-              }
+              mbar_arrive_expect_tx(&s.full[stage], kWTileBytes);
+              load_w_tile<CL>(s.w[stage], src + (size_t)t * kWTileBytes, &s.full[stage], crank);
             }
             __syncwarp();
             if (++stage == NS) { stage = 0; phase ^= 1; }
           }
         }
-      }
-    } else if (PAIR && !leader) {
-      // ---------------------------------------------------------- peer CTA of a pair: warp 1 relays "my half of stage s
-      // has landed" to the leader's peer_full[s] (one remote arrive per fill, in ring order); warp 3 idles.
-      if (warp == 1) {
-        TRACE_DECL;
-        uint32_t stage = 0, phase = 0;
-        for (int it = 0; it < iters; ++it)
-          for (int l = 0; l < L; ++l) {
-            const int ntiles = a.layer_kc[l] * 4;
-#pragma unroll 1
-            for (int t = 0; t < ntiles; ++t) {
-              wait_warp(&s.full[stage], phase, lane);
-              if (lane == 0 && TRACE_TILE(t)) TRACE(it, 11, (uint32_t)(l << 8 | t));                // peer: my half landed, relaying
-              if (elect_one()) mbar_arrive_cluster(&s.full[stage], 0);      // second arrival of the leader's full[stage]
-              __syncwarp();
-              if (++stage == NS) { stage = 0; phase ^= 1; }
-            }
-          }
       }
     } else if (warp == 1 || warp == 3) {
       // ---------------------------------------------------------- MMA issuers (whole warp converged, one lane issues).
@@ -536,7 +498,7 @@ __global__ void __launch_bounds__(kThreads, 1) cips_tc_kernel(const KArgs a) {
       // cannot issue 4 MMAs + bookkeeping inside the 256 clk a tile occupies the tensor pipe.
       TRACE_DECL;
       const uint32_t me = warp == 1 ? 0u : 1u;
-      const uint32_t idesc = umma_idesc_f16(PAIR ? 2 * kTileM : kTileM, kNC);
+      const uint32_t idesc = umma_idesc_f16(kTileM, kNC);
       const uint32_t dhi = umma_desc_hi(kSBO);
       const uint32_t a_lo0 = umma_desc_lo(smem_u32(s.x), kLBO);
       const uint32_t b_lo0 = umma_desc_lo(smem_u32(s.w[0]), RC::kLBO_B);
@@ -561,8 +523,7 @@ __global__ void __launch_bounds__(kThreads, 1) cips_tc_kernel(const KArgs a) {
               if (lane == 0 && TRACE_TILE(t)) TRACE(it, 1 + me, (uint32_t)(l << 8 | t));          // tile reached
               if (need > waited && !(abl & 16)) {
                 for (int j = waited + 1; j <= need; ++j) {
-                  if (PAIR) wait_warp_cluster(&s.epi_done[j], epar, lane);     // half of the arrivals come from the peer CTA
-                  else wait_warp(&s.epi_done[j], epar, lane);
+                  wait_warp(&s.epi_done[j], epar, lane);
                 }
                 waited = need;
               }
@@ -582,20 +543,13 @@ __global__ void __launch_bounds__(kThreads, 1) cips_tc_kernel(const KArgs a) {
                 const uint32_t a_lo = a_lo0 + kc * (kStepK16 * (kKC / 16));
                 const uint32_t b_lo = b_lo0 + stage * kStepStage;
                 const uint32_t d = tmem + nc * kNC;
-                if ((abl & 10) == 10 && !PAIR && CL == 1) {      // no MMAs in flight: plain arrives stand in for the commits
+                if ((abl & 10) == 10 && CL == 1) {      // no MMAs in flight: plain arrives stand in for the commits
                   mbar_arrive(&s.empty[stage]);
                   const uint32_t rdy8 = e >> 12;
                   for (int j = 0; j < 4; ++j)
                     if (rdy8 & (1u << j)) mbar_arrive(&s.acc_ready[j]);
                 } else if (abl & 2) {
-                  if (PAIR) tc_commit_cg2_mc(&s.empty[stage], 3);
-                  else commit_stage_free<CL>(&s.empty[stage]);
-                } else if (PAIR) {
-                  umma_ss_w_cg2(d, a_lo, b_lo, dhi, idesc, kc != 0);
-                  umma_ss_w_cg2(d, a_lo + kStepK16, b_lo + kStepK16B, dhi, idesc, 1);
-                  umma_ss_w_cg2(d, a_lo + 2 * kStepK16, b_lo + 2 * kStepK16B, dhi, idesc, 1);
-                  umma_ss_w_cg2(d, a_lo + 3 * kStepK16, b_lo + 3 * kStepK16B, dhi, idesc, 1);
-                  tc_commit_cg2_mc(&s.empty[stage], 3);      // stage free in BOTH CTAs
+                  commit_stage_free<CL>(&s.empty[stage]);
                 } else {
                   umma_ss_w(d, a_lo, b_lo, dhi, idesc, kc != 0);
                   umma_ss_w(d, a_lo + kStepK16, b_lo + kStepK16, dhi, idesc, 1);
@@ -603,21 +557,19 @@ __global__ void __launch_bounds__(kThreads, 1) cips_tc_kernel(const KArgs a) {
                   umma_ss_w(d, a_lo + 3 * kStepK16, b_lo + 3 * kStepK16, dhi, idesc, 1);
                   commit_stage_free<CL>(&s.empty[stage]);
                 }
-                const uint32_t rdy = ((abl & 10) == 10 && !PAIR && CL == 1) ? 0u : e >> 12;    // chunks j for which this is the issuer's last tile of S_j
+                const uint32_t rdy = ((abl & 10) == 10 && CL == 1) ? 0u : e >> 12;    // chunks j for which this is the issuer's last tile of S_j
                 if (rdy) {
 #pragma unroll
                   for (int j = 0; j < 4; ++j)
                     if (rdy & (1u << j)) {
-                      if (PAIR) tc_commit_cg2_mc(&s.acc_ready[j], 3);
-                      else tc_commit(&s.acc_ready[j]);
+                      tc_commit(&s.acc_ready[j]);
                     }
                 }
               }
             }
 #ifndef C3D_INJECT_RING_RACE
             else if (elect_one()) {
-              if (PAIR) mbar_arrive(&s.empty[stage]);       // leader-local (see the barrier's initialisation)
-              else observe_stage_free<CL>(&s.empty[stage]);
+              observe_stage_free<CL>(&s.empty[stage]);
             }
 #endif
             __syncwarp();
@@ -804,9 +756,8 @@ struct PrepArgs {
   uint16_t order_full[32];
   uint16_t order_in[4];
 };
-// grid = (tiles per image, B): block = one 16 KB tile of one image, in STREAM order.
-// PAIR: the tile is stored as two 8 KB halves (N rows 0..63, 64..127), each in the canonical layout of a 64-row operand.
-template <bool PAIR>
+// grid = (tiles per image, B): block = one 16 KB tile of one image, in STREAM order.  (The PAIR kernel streams the same tiles in ITS
+// order -- see the host's pair_stream_order: the two halves of a big tile are two ordinary tiles, adjacent.)
 __global__ void cips_prep_weights_kernel(const PrepArgs pa, __half* __restrict__ out) {
   const int gt = blockIdx.x, b = blockIdx.y;
   int l = 0;
@@ -823,13 +774,7 @@ __global__ void cips_prep_weights_kernel(const PrepArgs pa, __half* __restrict__
     const int k = i / kNC, n = i % kNC;    // n fastest -> coalesced reads of W rows
     const int gk = kc * kKC + k;
     const float v = gk < in_dim ? (sv[gk] * W[(size_t)gk * kH + nc * kNC + n]) * dv[n] : 0.f;
-    if (PAIR) {
-      const int nh = n % (kNC / 2);
-      o[((n / (kNC / 2)) * (kWTileBytes / 2) + (nh % 8) * 16 + (nh / 8) * 128 + (k / 8) * RingCfg<true>::kLBO_B) / 2 + (k % 8)] =
-          __float2half_rn(v);
-    } else {
-      o[((n % 8) * 16 + (n / 8) * 128 + (k / 8) * kLBO) / 2 + (k % 8)] = __float2half_rn(v);
-    }
+    o[((n % 8) * 16 + (n / 8) * 128 + (k / 8) * kLBO) / 2 + (k % 8)] = __float2half_rn(v);
   }
 }
 
@@ -1022,6 +967,41 @@ static void build_tile_order(uint16_t* order_full, uint16_t* order_in) {
   mark(order_in, 4);
 }
 
+// PAIR kernel (N = 256 MMAs, one issuer): issue order of the big tiles (kc, h), h = accumulator columns 256 h .. 256 h + 255.
+// Big tile (kc, h) overwrites / accumulates into accumulator blocks 2h and 2h+1 and reads A-operand chunk kc / 2, so it needs the
+// previous layer's epilogue chunks up to max(kc / 2, 2h + 1).  Head: (0..3, 0) after chunk 1, (4, 0)(5, 0) after chunk 2; tail, after
+// chunk 3: (6, 0)(7, 0) then (0..7, 1).  acc_ready[j] (block j complete, A chunk j no longer read) is committed with the last tile of
+// S_j = {h == j / 2 or kc / 2 == j}: (1, 1), (3, 1), (7, 1), (7, 1).  stream_*: the same order as (kc, nc) tiles, the leader's half
+// (nc = 2h) then the peer's (nc = 2h + 1) -- what the prep kernel writes and the two producers read.
+static void build_pair_order(uint16_t* big_full, uint16_t* big_in, uint16_t* stream_full, uint16_t* stream_in) {
+  int n = 0;
+  auto put = [&](int kc, int h) {
+    const int need = kc / 2 > 2 * h + 1 ? kc / 2 : 2 * h + 1;
+    big_full[n++] = (uint16_t)(kc | (h << 4) | (need << 8));
+  };
+  for (int kc = 0; kc < 8; ++kc) put(kc, 0);
+  for (int kc = 0; kc < 8; ++kc) put(kc, 1);
+  big_in[0] = (uint16_t)(0 | (0 << 4) | (1 << 8));
+  big_in[1] = (uint16_t)(0 | (1 << 4) | (3 << 8));
+  auto mark = [&](uint16_t* ord, int cnt) {
+    for (int j = 0; j < 4; ++j) {
+      int at = -1;
+      for (int i = 0; i < cnt; ++i) {
+        const int kc = ord[i] & 15, h = (ord[i] >> 4) & 15;
+        if (h == j / 2 || (kc >> 1) == j) at = i;
+      }
+      if (at < 0) at = 0;
+      ord[at] |= (uint16_t)(1u << (12 + j));
+    }
+  };
+  mark(big_full, 16);
+  mark(big_in, 2);
+  for (int i = 0; i < 16; ++i)
+    for (int r = 0; r < 2; ++r) stream_full[2 * i + r] = (uint16_t)((big_full[i] & 15) | ((2 * ((big_full[i] >> 4) & 15) + r) << 4));
+  for (int i = 0; i < 2; ++i)
+    for (int r = 0; r < 2; ++r) stream_in[2 * i + r] = (uint16_t)((big_in[i] & 15) | ((2 * ((big_in[i] >> 4) & 15) + r) << 4));
+}
+
 extern "C" int c3d_debug_cips_tile_order(uint16_t* order_full32, uint16_t* order_in4) {
   if (!order_full32 || !order_in4) return C3D_EINVAL;
   build_tile_order(order_full32, order_in4);
@@ -1073,14 +1053,8 @@ int c3d_cips_fwd_tc(const C3dCipsParams* p, const C3dCipsWeights* w, const float
   ka.layer_tile_off[L] = off;
   ka.img_tile_stride = (size_t)off;
   build_tile_order(ka.order_full, ka.order_in);
-  for (int me = 0; me < 2; ++me) {      // the same order, split by owner (PAIR kernel: one ring per issuer)
-    int n = 0;
-    for (int t = 0; t < 32; ++t)
-      if ((((ka.order_full[t] >> 4) & 15) >> 1) == me) ka.own_full[me][n++] = (uint32_t)ka.order_full[t] | (uint32_t)t << 16;
-    n = 0;
-    for (int t = 0; t < 4; ++t)
-      if ((((ka.order_in[t] >> 4) & 15) >> 1) == me) ka.own_in[me][n++] = (uint32_t)ka.order_in[t] | (uint32_t)t << 16;
-  }
+  uint16_t pair_full[32], pair_in[4];      // stream order of the PAIR kernel, as (kc, nc) tiles for the prep kernel
+  build_pair_order(ka.big_full, ka.big_in, pair_full, pair_in);
   int cl = 1;
   bool pair = false;
   const int grid = cips_grid(p, &cl, &pair);
@@ -1100,12 +1074,9 @@ int c3d_cips_fwd_tc(const C3dCipsParams* p, const C3dCipsWeights* w, const float
     pa.in_dim0 = p->in_dim;
     pa.n_layers = L;
     pa.B = p->batch;
-    for (int i = 0; i < 32; ++i) pa.order_full[i] = ka.order_full[i];
-    for (int i = 0; i < 4; ++i) pa.order_in[i] = ka.order_in[i];
-    if (pair)
-      C3D_LAUNCH(cips_prep_weights_kernel<true>, dim3(ka.layer_tile_off[L], p->batch), 256, 0, st, pa, (__half*)(base + ws.wtiles));
-    else
-      C3D_LAUNCH(cips_prep_weights_kernel<false>, dim3(ka.layer_tile_off[L], p->batch), 256, 0, st, pa, (__half*)(base + ws.wtiles));
+    for (int i = 0; i < 32; ++i) pa.order_full[i] = pair ? pair_full[i] : ka.order_full[i];
+    for (int i = 0; i < 4; ++i) pa.order_in[i] = pair ? pair_in[i] : ka.order_in[i];
+    C3D_LAUNCH(cips_prep_weights_kernel, dim3(ka.layer_tile_off[L], p->batch), 256, 0, st, pa, (__half*)(base + ws.wtiles));
     C3D_LAUNCH_CHECK();
   }
   C3D_LAUNCH(cips_prep_consts_kernel, p->n_blocks, 256, 0, st, *w, p->n_blocks, p->rgb_from, (float4*)(base + ws.rgbw),
