@@ -113,7 +113,8 @@ struct KArgs {
   // -DC3D_CIPS_ABLATE builds only (tools/build_ablate_lib.sh; timing experiments, results are garbage): bit 0 = epilogue without its
   // TMEM reads / math / stores, bit 1 = issuers commit without issuing MMAs, bit 2 = producer signals the stages without loading,
   // bit 3 (with bit 1, single CTA) = plain mbarrier arrives instead of tcgen05.commit, bit 4 = no epilogue warps at all (the issuers do
-  // not wait for them): the weight ring alone
+  // not wait for them): the weight ring alone; epilogue parts: bit 5 = no TMEM loads, bit 6 = no A-operand stores, bit 7 = no residual
+  // loads, bit 8 = no ToRGB, bit 9 = no residual stores
   int ablate;
 };
 
@@ -223,20 +224,57 @@ __device__ __forceinline__ void trace_ev(int it, uint32_t tag, uint32_t a0, int&
 
 struct EpiFlags {
   bool add_res, keep_res, do_rgb, last;
+  bool no_x = false;      // -DC3D_CIPS_ABLATE timing experiments only: skip the A-operand stores
 };
 
-// One thread, 16 accumulator columns of its row (the per-image scales are already inside the weights).
-//   rwp: ToRGB weights of column c; xp: the thread's 16-byte slot of K-group c/8 in the A operand;
-//   rp: residual scratch (float4 index c/4, this row).
+// One thread, 16 accumulator columns of its row (the per-image scales are already inside the weights), in two phases:
+//   epi16_act : what the NEXT LAYER'S MMAs wait for -- a = fp16(y) into the A operand -- and nothing else;
+//   epi16_tail: everything else (residual store, ToRGB, the last layer's outputs, the training stash), after the chunk has been
+//               handed to the issuer.  It recomputes y from the same registers (a max, a multiply and an add per value), so what
+//               it stores is bit-identical to what epi16_act packed.
+// Why two phases: fence.proxy.async (needed between the A-operand stores and the hand-over) is MEMBAR.ALL.CTA + FENCE.VIEW.ASYNC in
+// SASS and waits for the thread's outstanding GLOBAL stores as well; with the residual stores in front of it a chunk of a
+// residual + ToRGB layer took 4-5 k clk against 1.3 k for a plain one (profiles/r02aa_cips_light_pair_l8.txt), and the epilogue chain
+// is the critical path of a layer.  Removing the residual stores alone: -1.4 ms of 8.9, the ToRGB FMAs: -0.75 ms
+// (profiles/r02ab_cips_pair_residual.txt).
 //   first layer of a block : a = lrelu(acc)
 //   second layer of a block: y = lrelu(acc) (+ residual); ToRGB += y.Wrgb; a = y
-template <bool SECOND, bool DUMP = false>
-__device__ __forceinline__ void epi16(const uint32_t (&acc)[16], const float4 (&rs)[4], const float4* __restrict__ rwp,
-                                      uint8_t* xp, float4* rp, const EpiFlags f, float& rgb0, float& rgb1, float& rgb2,
-                                      float* hid_out, uint4* dump = nullptr, uint16_t* zsign = nullptr) {
-  float y[16];
+//   rwp: ToRGB weights of column c; xp: the thread's 16-byte slot of K-group c/8 in the A operand; rp: residual scratch (float4
+//   index c/4, this row).
+template <bool SECOND>
+__device__ __forceinline__ void epi16_y(const uint32_t (&acc)[16], const float4 (&rs)[4], const EpiFlags f, float (&y)[16]) {
 #pragma unroll
   for (int i = 0; i < 16; ++i) y[i] = lrelu02(__uint_as_float(acc[i]));
+  if (SECOND && f.add_res) {
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+      y[4 * g + 0] += rs[g].x; y[4 * g + 1] += rs[g].y; y[4 * g + 2] += rs[g].z; y[4 * g + 3] += rs[g].w;
+    }
+  }
+}
+template <bool SECOND>
+__device__ __forceinline__ void epi16_act(const uint32_t (&acc)[16], const float4 (&rs)[4], uint8_t* xp, const EpiFlags f) {
+  if (SECOND && f.last) return;      // the last layer feeds no MMA
+  float y[16];
+  epi16_y<SECOND>(acc, rs, f, y);
+  uint32_t pk[8];
+#pragma unroll
+  for (int g = 0; g < 8; ++g) pk[g] = pack_f16(y[2 * g], y[2 * g + 1]);
+#ifdef C3D_CIPS_ABLATE
+  if (!f.no_x)
+#endif
+  {
+    *reinterpret_cast<uint4*>(xp) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+    *reinterpret_cast<uint4*>(xp + kLBO) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+  }
+}
+template <bool SECOND, bool DUMP = false>
+__device__ __forceinline__ void epi16_tail(const uint32_t (&acc)[16], const float4 (&rs)[4], const float4* __restrict__ rwp, float4* rp,
+                                           const EpiFlags f, float& rgb0, float& rgb1, float& rgb2, float* hid_out,
+                                           uint4* dump = nullptr, uint16_t* zsign = nullptr) {
+  if (!SECOND && !DUMP) return;
+  float y[16];
+  epi16_y<SECOND>(acc, rs, f, y);
   if (DUMP && SECOND && zsign && f.add_res) {
     uint32_t m = 0;
 #pragma unroll
@@ -244,12 +282,6 @@ __device__ __forceinline__ void epi16(const uint32_t (&acc)[16], const float4 (&
     *zsign = (uint16_t)m;
   }
   if (SECOND) {
-    if (f.add_res) {
-#pragma unroll
-      for (int g = 0; g < 4; ++g) {
-        y[4 * g + 0] += rs[g].x; y[4 * g + 1] += rs[g].y; y[4 * g + 2] += rs[g].z; y[4 * g + 3] += rs[g].w;
-      }
-    }
     if (f.keep_res) {
 #pragma unroll
       for (int g = 0; g < 4; ++g) rp[g * kTileM] = make_float4(y[4 * g], y[4 * g + 1], y[4 * g + 2], y[4 * g + 3]);
@@ -263,28 +295,16 @@ __device__ __forceinline__ void epi16(const uint32_t (&acc)[16], const float4 (&
         rgb2 = fmaf(y[i], w4.z, rgb2);
       }
     }
-    if (f.last) {
-      if (hid_out) {
+    if (f.last && hid_out) {
 #pragma unroll
-        for (int g = 0; g < 4; ++g)
-          reinterpret_cast<float4*>(hid_out)[g] = make_float4(y[4 * g], y[4 * g + 1], y[4 * g + 2], y[4 * g + 3]);
-      }
-      if (DUMP && dump) {
-        uint32_t pl[8];
-#pragma unroll
-        for (int g = 0; g < 8; ++g) pl[g] = pack_f16(y[2 * g], y[2 * g + 1]);
-        dump[0] = make_uint4(pl[0], pl[1], pl[2], pl[3]);
-        dump[1] = make_uint4(pl[4], pl[5], pl[6], pl[7]);
-      }
-      return;
+      for (int g = 0; g < 4; ++g)
+        reinterpret_cast<float4*>(hid_out)[g] = make_float4(y[4 * g], y[4 * g + 1], y[4 * g + 2], y[4 * g + 3]);
     }
   }
-  uint32_t pk[8];
-#pragma unroll
-  for (int g = 0; g < 8; ++g) pk[g] = pack_f16(y[2 * g], y[2 * g + 1]);
-  *reinterpret_cast<uint4*>(xp) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-  *reinterpret_cast<uint4*>(xp + kLBO) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
   if (DUMP && dump) {
+    uint32_t pk[8];
+#pragma unroll
+    for (int g = 0; g < 8; ++g) pk[g] = pack_f16(y[2 * g], y[2 * g + 1]);
     dump[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
     dump[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
   }
@@ -634,14 +654,17 @@ __global__ void __launch_bounds__(kThreads, 1) cips_tc_kernel(const KArgs a) {
         f.add_res = second && blk >= a.skip_from && blk >= 1;      // block input dim == 512 for blk >= 1
         f.keep_res = second && (blk + 1 >= a.skip_from) && !f.last;  // the next block adds this output
         f.do_rgb = second && blk >= a.rgb_from;
+        if (abl & 64) f.no_x = true;
+        if (abl & 128) f.add_res = false;
+        if (abl & 512) f.keep_res = false;
+        if (abl & 256) f.do_rgb = false;
         if (f.do_rgb) {   // ToRGB weights of this block -> shared memory (overlaps the MMAs)
           s.rgbw[(int)threadIdx.x - 128] = __ldg(a.rgbw + (size_t)blk * kH + ((int)threadIdx.x - 128));
           named_bar_sync_c<1, kNumEpiWarps * 32>();
         }
         float* hid = (f.last && a.hidden_out && row_ok) ? a.hidden_out + ((size_t)img * a.N + pix) * kH : nullptr;
-        // software pipeline over the 8 x 16-column slices this thread owns (chunk j, halves 0/1);
-        // every address advances by a constant per chunk
-        uint32_t accA[16], accB[16];
+        // the 8 x 16-column slices this thread owns (chunk j, halves 0/1); every address advances by a constant per chunk
+        uint32_t accA[16] = {}, accB[16] = {};
         float4 rsA[4], rsB[4];
         const int cw = wg * 32;
         uint32_t tcol = trow + (uint32_t)cw;                    // TMEM column of slice (j, 0)
@@ -662,8 +685,8 @@ __global__ void __launch_bounds__(kThreads, 1) cips_tc_kernel(const KArgs a) {
         // chunk j starts as soon as accumulator block j is complete and no MMA of this layer still reads
         // A-operand chunk j (acc_ready[j]); the rest of the layer's MMAs run underneath.
         const uint32_t apar = (uint32_t)(it * L + l) & 1u;
-        bool have = false;                                      // slice (j, 0) already in flight
-        if (f.add_res) load_res(rsA, rp);
+        bool have = false;                                      // the chunk's accumulators are already on their way to registers
+        if (f.add_res) { load_res(rsA, rp); load_res(rsB, rp + 4 * kTileM); }
 #pragma unroll 1
         for (int j = 0; j < 4; ++j) {
           if (abl & 1) {
@@ -680,38 +703,39 @@ __global__ void __launch_bounds__(kThreads, 1) cips_tc_kernel(const KArgs a) {
           }
           if (!have) {
             wait_epilogue(&s.acc_ready[j], apar, warp, lane);
-            if (lane == 0 && TRACE_EPI_WARP(warp)) TRACE(it, 8, (uint32_t)(l << 8 | j));                 // accumulator block j complete
             tc_fence_after();
-            tmem_ld16(tcol, accA);
+            if (!(abl & 32)) { tmem_ld16(tcol, accA); tmem_ld16(tcol + 16, accB); }
           }
+          if (lane == 0 && TRACE_EPI_WARP(warp)) TRACE(it, 8, (uint32_t)(l << 8 | j));                 // accumulator block j complete
           tc_wait_ld();
-          tmem_ld16(tcol + 16, accB);
-          if (f.add_res) load_res(rsB, rp + 4 * kTileM);
-          if (second) epi16<true, DUMP>(accA, rsA, rwp, xp, rp, f, rgb0, rgb1, rgb2, hp, dp, zp);
-          else epi16<false, DUMP>(accA, rsA, rwp, xp, rp, f, rgb0, rgb1, rgb2, hp, dp);
-          tc_wait_ld();
-          have = false;
-          if (j < 3) {
-            have = test_warp(&s.acc_ready[j + 1], apar, lane);
-            if (have) {
-              tc_fence_after();
-              tmem_ld16(tcol + 128, accA);
-            }
-            if (f.add_res) load_res(rsA, rp + 32 * kTileM);
-          }
-          if (second) epi16<true, DUMP>(accB, rsB, rwp + 16, xp + 2 * kLBO, rp + 4 * kTileM, f, rgb0, rgb1, rgb2, hp ? hp + 16 : nullptr, dp ? dp + 2 : nullptr, zp ? zp + 1 : nullptr);
-          else epi16<false, DUMP>(accB, rsB, rwp + 16, xp + 2 * kLBO, rp + 4 * kTileM, f, rgb0, rgb1, rgb2, hp ? hp + 16 : nullptr, dp ? dp + 2 : nullptr);
-          // chunk j of this epilogue is complete for this warp
-          // (round 2's first PAIR form used the all-state-spaces proxy fence here: it also waits for this thread's global residual
-          // stores, ~1.4 k clk per chunk -- the epilogue chunks took 2.9 k instead of 1.5 k clk, profiles/r02p_cips_trace_pair.txt)
-          fence_proxy_async();
+          // ---- phase 1: the next layer's A operand, then hand the chunk over
+          if (second) { epi16_act<true>(accA, rsA, xp, f); epi16_act<true>(accB, rsB, xp + 2 * kLBO, f); }
+          else { epi16_act<false>(accA, rsA, xp, f); epi16_act<false>(accB, rsB, xp + 2 * kLBO, f); }
+          fence_proxy_async();      // CTA scope: the A operand in THIS CTA's shared memory is what the tensor core (async proxy) reads
           tc_fence_before();
           __syncwarp();
           if (lane == 0 && !f.last) {
             if (PAIR) mbar_arrive_cluster(&s.epi_done[j], 0);
             else mbar_arrive(&s.epi_done[j]);
           }
-          if (lane == 0 && TRACE_EPI_WARP(warp)) TRACE(it, 9, (uint32_t)(l << 8 | (warp - 4) << 2 | j));   // warp finished chunk j
+          if (lane == 0 && TRACE_EPI_WARP(warp)) TRACE(it, 9, (uint32_t)(l << 8 | (warp - 4) << 2 | j));   // warp handed chunk j over
+          // ---- phase 2: residual store, ToRGB, outputs -- under the MMAs the hand-over released
+          if (second) {
+            epi16_tail<true, DUMP>(accA, rsA, rwp, rp, f, rgb0, rgb1, rgb2, hp, dp, zp);
+            epi16_tail<true, DUMP>(accB, rsB, rwp + 16, rp + 4 * kTileM, f, rgb0, rgb1, rgb2, hp ? hp + 16 : nullptr, dp ? dp + 2 : nullptr, zp ? zp + 1 : nullptr);
+          } else if (DUMP) {
+            epi16_tail<false, DUMP>(accA, rsA, rwp, rp, f, rgb0, rgb1, rgb2, hp, dp);
+            epi16_tail<false, DUMP>(accB, rsB, rwp + 16, rp + 4 * kTileM, f, rgb0, rgb1, rgb2, hp ? hp + 16 : nullptr, dp ? dp + 2 : nullptr);
+          }
+          have = false;
+          if (j < 3) {      // the next chunk: its residual a whole chunk ahead, its accumulators if they are complete already
+            if (f.add_res) { load_res(rsA, rp + 32 * kTileM); load_res(rsB, rp + 36 * kTileM); }
+            have = test_warp(&s.acc_ready[j + 1], apar, lane);
+            if (have) {
+              tc_fence_after();
+              if (!(abl & 32)) { tmem_ld16(tcol + 128, accA); tmem_ld16(tcol + 144, accB); }
+            }
+          }
           tcol += 128; rp += 32 * kTileM; xp += 16 * kLBO; rwp += 128;
           if (hp) hp += 128;
           if (dp) dp += 16;
