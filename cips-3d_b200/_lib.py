@@ -99,7 +99,7 @@ def load():
 # The library snapshots its A/B variant switches from the environment once (csrc/api.cu: c3d_options) -- never on a launch path.
 # The host layer re-reads them only when one of these variables actually changed since the last call (tests and the A/B
 # timing tools flip them inside one process): a dict lookup per variable here, no getenv in the native code.
-_OPTION_VARS = ("C3D_CIPS_CLUSTER", "C3D_CIPS_PAIR", "C3D_CIPS_STAGGER_NS", "C3D_BLUR", "C3D_BLUR_TMA", "C3D_PIGAN_IMPL", "C3D_PIGAN_PAIR", "C3D_RAY_MATH")
+_OPTION_VARS = ("C3D_CIPS_CLUSTER", "C3D_CIPS_PAIR", "C3D_CIPS_STAGGER_NS", "C3D_CIPS_RES16", "C3D_BLUR", "C3D_BLUR_TMA", "C3D_PIGAN_IMPL", "C3D_PIGAN_PAIR", "C3D_RAY_MATH")
 _option_snapshot = {}
 
 

@@ -37,8 +37,9 @@ static void load_options() {
   auto geti = [](const char* n, int dflt) { const char* e = getenv(n); return e && *e ? atoi(e) : dflt; };
   o.cips_cluster = geti("C3D_CIPS_CLUSTER", 1);
   if (o.cips_cluster != 1 && o.cips_cluster != 2 && o.cips_cluster != 4) o.cips_cluster = 1;
-  o.cips_pair = geti("C3D_CIPS_PAIR", 0) != 0;
+  o.cips_pair = geti("C3D_CIPS_PAIR", 1) != 0;
   o.cips_stagger_ns = geti("C3D_CIPS_STAGGER_NS", 0);
+  o.cips_res16 = geti("C3D_CIPS_RES16", 1);
   const char* b = getenv("C3D_BLUR");
   o.blur_impl = !b || !*b ? 2 : (b[0] == 't' && b[1] == 'i' ? 0 : (b[0] == 't' ? 1 : 2));      // tile | tma | stream
   if (geti("C3D_BLUR_TMA", 0) != 0) o.blur_impl = 1;                                             // round-1 spelling

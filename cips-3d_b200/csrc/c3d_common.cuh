@@ -51,7 +51,8 @@ int c3d_device_sm_count(int dev);   // cached (api.cu)
 struct C3dOptions {
   int cips_cluster;   // C3D_CIPS_CLUSTER: 1 | 2 | 4   weight multicast clusters of the CIPS kernel (default 1)
   int cips_stagger_ns; // C3D_CIPS_STAGGER_NS: CTA i of the CIPS kernel starts i * this many ns late (default 0)
-  int cips_pair;      // C3D_CIPS_PAIR:    0 | 1       tcgen05 cta_group::2 CTA pairs (default 0: measured 2.3x slower, r02a)
+  int cips_res16;      // C3D_CIPS_RES16: fp16 residual stream in the CIPS kernel when only the image is asked for (default 1)
+  int cips_pair;      // C3D_CIPS_PAIR:    0 | 1       tcgen05 cta_group::2 CTA pairs (default 1 since round 2's N = 256 / one-issuer form)
   int blur_impl;      // C3D_BLUR:         0 tile | 1 tma | 2 stream     4x4 FIR fast path (default: stream)
   int pigan_tc;       // C3D_PIGAN_IMPL:   simt -> 0 | tc -> 1           pi-GAN renderer (default tc: 9.4x faster, r02a)
   int pigan_pair;     // C3D_PIGAN_PAIR:   0 | 1 (default 0: measured 4 % slower, r02a)

@@ -222,6 +222,16 @@ __device__ __forceinline__ void trace_ev(int it, uint32_t tag, uint32_t a0, int&
 #define TRACE_EPI_WARP(w) false
 #endif
 
+// The residual stream y_b (block output, added to the output of block b + 1) between its two layers lives in a per-CTA scratch that
+// stays in L2.  fp32: 512 KB of L2 traffic per CTA and residual layer (256 KB in, 256 KB out) beside the 256 KB of weights -- those
+// layers are L2-bandwidth-bound (a residual layer took ~21 k clk, a plain one ~13 k: profiles/r02ac_cips_light_pair_l8.txt).
+// R16 keeps it as fp16 -- the very bits the next layer's A operand holds, so the skip connection adds what the MMAs saw -- and halves
+// that.  Image error vs the fp64 oracle is unchanged by it (2.8-3.3e-4 against 2.5-3.3e-4 on the CPU emulation), the error of the
+// 512-wide hidden state grows by a quarter (up to 1.2e-3): the launcher uses R16 only when no hidden output / activation stash is asked for.
+template <bool R16> struct ResT;
+template <> struct ResT<false> { using Vec = float4; static constexpr int kVecs = 4; };     // vectors per 16-column slice
+template <> struct ResT<true> { using Vec = uint4; static constexpr int kVecs = 2; };       // 8 halves each
+
 struct EpiFlags {
   bool add_res, keep_res, do_rgb, last;
   bool no_x = false;      // -DC3D_CIPS_ABLATE timing experiments only: skip the A-operand stores
@@ -241,19 +251,42 @@ struct EpiFlags {
 //   second layer of a block: y = lrelu(acc) (+ residual); ToRGB += y.Wrgb; a = y
 //   rwp: ToRGB weights of column c; xp: the thread's 16-byte slot of K-group c/8 in the A operand; rp: residual scratch (float4
 //   index c/4, this row).
-template <bool SECOND>
-__device__ __forceinline__ void epi16_y(const uint32_t (&acc)[16], const float4 (&rs)[4], const EpiFlags f, float (&y)[16]) {
+__device__ __forceinline__ void add_residual(float (&y)[16], const float4 (&rs)[4]) {
 #pragma unroll
-  for (int i = 0; i < 16; ++i) y[i] = lrelu02(__uint_as_float(acc[i]));
-  if (SECOND && f.add_res) {
+  for (int g = 0; g < 4; ++g) {
+    y[4 * g + 0] += rs[g].x; y[4 * g + 1] += rs[g].y; y[4 * g + 2] += rs[g].z; y[4 * g + 3] += rs[g].w;
+  }
+}
+__device__ __forceinline__ void add_residual(float (&y)[16], const uint4 (&rs)[2]) {
 #pragma unroll
-    for (int g = 0; g < 4; ++g) {
-      y[4 * g + 0] += rs[g].x; y[4 * g + 1] += rs[g].y; y[4 * g + 2] += rs[g].z; y[4 * g + 3] += rs[g].w;
+  for (int g = 0; g < 2; ++g) {
+    const uint32_t w[4] = {rs[g].x, rs[g].y, rs[g].z, rs[g].w};
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const float2 v = __half22float2(*reinterpret_cast<const __half2*>(&w[q]));
+      y[8 * g + 2 * q] += v.x;
+      y[8 * g + 2 * q + 1] += v.y;
     }
   }
 }
-template <bool SECOND>
-__device__ __forceinline__ void epi16_act(const uint32_t (&acc)[16], const float4 (&rs)[4], uint8_t* xp, const EpiFlags f) {
+__device__ __forceinline__ void store_residual(float4* rp, const float (&y)[16]) {
+#pragma unroll
+  for (int g = 0; g < 4; ++g) rp[g * kTileM] = make_float4(y[4 * g], y[4 * g + 1], y[4 * g + 2], y[4 * g + 3]);
+}
+__device__ __forceinline__ void store_residual(uint4* rp, const float (&y)[16]) {
+#pragma unroll
+  for (int g = 0; g < 2; ++g)
+    rp[g * kTileM] = make_uint4(pack_f16(y[8 * g], y[8 * g + 1]), pack_f16(y[8 * g + 2], y[8 * g + 3]), pack_f16(y[8 * g + 4], y[8 * g + 5]),
+                                pack_f16(y[8 * g + 6], y[8 * g + 7]));
+}
+template <bool SECOND, typename RV, int NV>
+__device__ __forceinline__ void epi16_y(const uint32_t (&acc)[16], const RV (&rs)[NV], const EpiFlags f, float (&y)[16]) {
+#pragma unroll
+  for (int i = 0; i < 16; ++i) y[i] = lrelu02(__uint_as_float(acc[i]));
+  if (SECOND && f.add_res) add_residual(y, rs);
+}
+template <bool SECOND, typename RV, int NV>
+__device__ __forceinline__ void epi16_act(const uint32_t (&acc)[16], const RV (&rs)[NV], uint8_t* xp, const EpiFlags f) {
   if (SECOND && f.last) return;      // the last layer feeds no MMA
   float y[16];
   epi16_y<SECOND>(acc, rs, f, y);
@@ -268,8 +301,8 @@ __device__ __forceinline__ void epi16_act(const uint32_t (&acc)[16], const float
     *reinterpret_cast<uint4*>(xp + kLBO) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
   }
 }
-template <bool SECOND, bool DUMP = false>
-__device__ __forceinline__ void epi16_tail(const uint32_t (&acc)[16], const float4 (&rs)[4], const float4* __restrict__ rwp, float4* rp,
+template <bool SECOND, bool DUMP, typename RV, int NV>
+__device__ __forceinline__ void epi16_tail(const uint32_t (&acc)[16], const RV (&rs)[NV], const float4* __restrict__ rwp, RV* rp,
                                            const EpiFlags f, float& rgb0, float& rgb1, float& rgb2, float* hid_out,
                                            uint4* dump = nullptr, uint16_t* zsign = nullptr) {
   if (!SECOND && !DUMP) return;
@@ -282,10 +315,7 @@ __device__ __forceinline__ void epi16_tail(const uint32_t (&acc)[16], const floa
     *zsign = (uint16_t)m;
   }
   if (SECOND) {
-    if (f.keep_res) {
-#pragma unroll
-      for (int g = 0; g < 4; ++g) rp[g * kTileM] = make_float4(y[4 * g], y[4 * g + 1], y[4 * g + 2], y[4 * g + 3]);
-    }
+    if (f.keep_res) store_residual(rp, y);
     if (f.do_rgb) {
 #pragma unroll
       for (int i = 0; i < 16; ++i) {
@@ -315,8 +345,10 @@ __device__ __forceinline__ void epi16_tail(const uint32_t (&acc)[16], const floa
 // streams ITS half of every big weight tile into its own ring; the peer relays "my half landed" to the leader's full barrier;
 // both CTAs' epilogue warps report to the leader's epi_done barriers; the leader's commits are multicast to the
 // empty / acc_ready barriers of both CTAs.  The epilogue (4 chunks of 128 columns a layer) is the single-CTA kernel's.
-template <int CL, bool PAIR = false, bool DUMP = false>
+template <int CL, bool PAIR = false, bool DUMP = false, bool R16 = false>
 __global__ void __launch_bounds__(kThreads, 1) cips_tc_kernel(const KArgs a) {
+  using ResVec = typename ResT<R16>::Vec;
+  constexpr int kResVecs = ResT<R16>::kVecs, kResCols = 16 / kResVecs;
   static_assert(!PAIR || CL == 2, "a CTA pair is a cluster of two");
   using SM = SmemT<PAIR>;
   using RC = RingCfg<PAIR>;
@@ -607,7 +639,7 @@ __global__ void __launch_bounds__(kThreads, 1) cips_tc_kernel(const KArgs a) {
     const int q = warp & 3;            // TMEM lane quarter
     const int row = q * 32 + lane;     // row of the tile this thread owns
     const uint32_t trow = tmem + ((uint32_t)(q * 32) << 16);
-    float4* resid = a.resid + (size_t)blockIdx.x * (kH / 4) * kTileM;
+    ResVec* resid = reinterpret_cast<ResVec*>(a.resid) + (size_t)blockIdx.x * (kH / kResCols) * kTileM;
     for (int it = 0; it < ((abl & 16) ? 0 : iters); ++it) {
       const int tile = tile_of(it);
       const bool tile_ok = tile < a.total_tiles;
@@ -665,10 +697,10 @@ __global__ void __launch_bounds__(kThreads, 1) cips_tc_kernel(const KArgs a) {
         float* hid = (f.last && a.hidden_out && row_ok) ? a.hidden_out + ((size_t)img * a.N + pix) * kH : nullptr;
         // the 8 x 16-column slices this thread owns (chunk j, halves 0/1); every address advances by a constant per chunk
         uint32_t accA[16] = {}, accB[16] = {};
-        float4 rsA[4], rsB[4];
+        ResVec rsA[kResVecs], rsB[kResVecs];
         const int cw = wg * 32;
         uint32_t tcol = trow + (uint32_t)cw;                    // TMEM column of slice (j, 0)
-        float4* rp = resid + (size_t)(cw / 4) * kTileM + row;   // residual slot of slice (j, 0), g = 0
+        ResVec* rp = resid + (size_t)(cw / kResCols) * kTileM + row;   // residual slot of slice (j, 0), g = 0
         uint8_t* xp = s.x + (size_t)(cw / 8) * kLBO + row * 16;
         const float4* rwp = s.rgbw + cw;
         float* hp = hid ? hid + cw : nullptr;
@@ -678,15 +710,16 @@ __global__ void __launch_bounds__(kThreads, 1) cips_tc_kernel(const KArgs a) {
                         : nullptr;
         uint16_t* zp = (DUMP && a.zsign && row_ok) ? a.zsign + ((size_t)l * a.acts_layer_stride + ((size_t)img * a.N + pix) * kH + cw) / 16
                                                    : nullptr;
-        auto load_res = [&](float4 (&rs)[4], const float4* p) {
+        auto load_res = [&](ResVec (&rs)[kResVecs], const ResVec* p) {
 #pragma unroll
-          for (int g = 0; g < 4; ++g) rs[g] = p[g * kTileM];
+          for (int g = 0; g < kResVecs; ++g) rs[g] = p[g * kTileM];
         };
+        constexpr int kResSlice = kResVecs * kTileM, kResChunk = (kNC / kResCols) * kTileM;   // pointer steps: 16 / 128 columns
         // chunk j starts as soon as accumulator block j is complete and no MMA of this layer still reads
         // A-operand chunk j (acc_ready[j]); the rest of the layer's MMAs run underneath.
         const uint32_t apar = (uint32_t)(it * L + l) & 1u;
         bool have = false;                                      // the chunk's accumulators are already on their way to registers
-        if (f.add_res) { load_res(rsA, rp); load_res(rsB, rp + 4 * kTileM); }
+        if (f.add_res) { load_res(rsA, rp); load_res(rsB, rp + kResSlice); }
 #pragma unroll 1
         for (int j = 0; j < 4; ++j) {
           if (abl & 1) {
@@ -722,21 +755,21 @@ __global__ void __launch_bounds__(kThreads, 1) cips_tc_kernel(const KArgs a) {
           // ---- phase 2: residual store, ToRGB, outputs -- under the MMAs the hand-over released
           if (second) {
             epi16_tail<true, DUMP>(accA, rsA, rwp, rp, f, rgb0, rgb1, rgb2, hp, dp, zp);
-            epi16_tail<true, DUMP>(accB, rsB, rwp + 16, rp + 4 * kTileM, f, rgb0, rgb1, rgb2, hp ? hp + 16 : nullptr, dp ? dp + 2 : nullptr, zp ? zp + 1 : nullptr);
+            epi16_tail<true, DUMP>(accB, rsB, rwp + 16, rp + kResSlice, f, rgb0, rgb1, rgb2, hp ? hp + 16 : nullptr, dp ? dp + 2 : nullptr, zp ? zp + 1 : nullptr);
           } else if (DUMP) {
             epi16_tail<false, DUMP>(accA, rsA, rwp, rp, f, rgb0, rgb1, rgb2, hp, dp);
-            epi16_tail<false, DUMP>(accB, rsB, rwp + 16, rp + 4 * kTileM, f, rgb0, rgb1, rgb2, hp ? hp + 16 : nullptr, dp ? dp + 2 : nullptr);
+            epi16_tail<false, DUMP>(accB, rsB, rwp + 16, rp + kResSlice, f, rgb0, rgb1, rgb2, hp ? hp + 16 : nullptr, dp ? dp + 2 : nullptr);
           }
           have = false;
           if (j < 3) {      // the next chunk: its residual a whole chunk ahead, its accumulators if they are complete already
-            if (f.add_res) { load_res(rsA, rp + 32 * kTileM); load_res(rsB, rp + 36 * kTileM); }
+            if (f.add_res) { load_res(rsA, rp + kResChunk); load_res(rsB, rp + kResChunk + kResSlice); }
             have = test_warp(&s.acc_ready[j + 1], apar, lane);
             if (have) {
               tc_fence_after();
               if (!(abl & 32)) { tmem_ld16(tcol + 128, accA); tmem_ld16(tcol + 144, accB); }
             }
           }
-          tcol += 128; rp += 32 * kTileM; xp += 16 * kLBO; rwp += 128;
+          tcol += 128; rp += kResChunk; xp += 16 * kLBO; rwp += 128;
           if (hp) hp += 128;
           if (dp) dp += 16;
           if (zp) zp += 8;
@@ -827,8 +860,9 @@ static int cips_grid(const C3dCipsParams* p, int* cl_out, bool* pair_out) {
   const int sms = c3d_device_sm_count(dev);
   int cl = c3d_options().cips_cluster;
   const int tiles_per_img = (p->n_pix + kTileM - 1) / kTileM;
-  // C3D_CIPS_PAIR=1: tcgen05 CTA pairs (cta_group::2).  Opt-in until it has been timed on hardware.
-  bool pair = c3d_options().cips_pair != 0;
+  // tcgen05 CTA pairs (cta_group::2) wherever an image has an even number of tiles: 8.4 ms against the single-CTA kernel's 10.9 ms at
+  // B = 16, r256 (profiles/r02ac_cips_epilogue.txt).  C3D_CIPS_PAIR=0 selects the single-CTA kernel.
+  bool pair = c3d_options().cips_pair != 0 && cl == 1;      // an explicit C3D_CIPS_CLUSTER=2|4 asks for the multicast (non-pair) form
   if (pair && (tiles_per_img % 2 || sms < 2)) pair = false;     // a pair works on two tiles of ONE image
   if (pair) cl = 2;
   *pair_out = pair;
@@ -881,13 +915,13 @@ extern "C" int c3d_debug_cips_trace(unsigned long long* out, int cap) {
 }
 #endif
 
-template <int CL, bool PAIR = false, bool DUMP = false>
+template <int CL, bool PAIR = false, bool DUMP = false, bool R16 = false>
 static int launch_cips(const KArgs& ka, int grid, cudaStream_t st) {
   const size_t smem = sizeof(SmemT<PAIR>) + 1024;
   static std::atomic<unsigned long long> attr_set{0};     // per device, once
   int dev = 0;
   cudaGetDevice(&dev);
-  auto kern = cips_tc_kernel<CL, PAIR, DUMP>;
+  auto kern = cips_tc_kernel<CL, PAIR, DUMP, R16>;
   if (!(attr_set.load() >> (dev & 63) & 1ull)) {
     C3D_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_set.fetch_or(1ull << (dev & 63));
@@ -1110,8 +1144,10 @@ int c3d_cips_fwd_tc(const C3dCipsParams* p, const C3dCipsWeights* w, const float
     int g1 = ka.total_tiles < c3d_device_sm_count(dev) ? ka.total_tiles : c3d_device_sm_count(dev);
     return launch_cips<1, false, true>(ka, g1 < 1 ? 1 : g1, st);
   }
-  if (pair) return launch_cips<2, true>(ka, grid, st);
-  if (cl == 1) return launch_cips<1>(ka, grid, st);
+  // fp16 residual stream (see ResT): only when the caller takes the image alone
+  const bool r16 = c3d_options().cips_res16 != 0 && !hidden_out;
+  if (pair) return r16 ? launch_cips<2, true, false, true>(ka, grid, st) : launch_cips<2, true>(ka, grid, st);
+  if (cl == 1) return r16 ? launch_cips<1, false, false, true>(ka, grid, st) : launch_cips<1>(ka, grid, st);
   if (cl == 2) return launch_cips<2>(ka, grid, st);
   return launch_cips<4>(ka, grid, st);
 }

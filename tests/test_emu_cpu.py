@@ -150,9 +150,10 @@ def _cips_case(pkg, B, N, impl, seed=31, n_blocks=9):
 
 @pytest.mark.parametrize("mode", ["eager", "lazy", "random"])
 @pytest.mark.parametrize("B,N", [(1, 128), (3, 200)])
-def test_emu_cips_tc_matches_oracle(B, N, mode):
-    """The fused CIPS tcgen05 kernel (weight ring, dual issuers, staircase pipeline) on the CPU vs the fp64 oracle;
+def test_emu_cips_tc_matches_oracle(B, N, mode, monkeypatch):
+    """The fused single-CTA CIPS tcgen05 kernel (weight ring, dual issuers, staircase pipeline) on the CPU vs the fp64 oracle;
     (3, 200) has ragged tiles and more tiles than emulated SMs (the persistent loop and the dummy tiles run)."""
+    monkeypatch.setenv("C3D_CIPS_PAIR", "0")
     with emulated(async_mode=MODES[mode], seed=B + N, sms=2) as pkg:
         e_hid, e_rgb = _cips_case(pkg, B, N, TC)
     assert e_hid < 1e-3 and e_rgb < 1e-3, (e_hid, e_rgb)
@@ -184,6 +185,28 @@ def test_emu_cips_tc_cta_pair(B, N, sms, mode, monkeypatch):
     assert e_hid < 1e-3 and e_rgb < 1e-3, (e_hid, e_rgb)
 
 
+@pytest.mark.parametrize("pair", ["0", "1"])
+@pytest.mark.parametrize("B,N", [(2, 256), (1, 384)])
+def test_emu_cips_image_only_call_uses_the_fp16_residual_stream(B, N, pair, monkeypatch):
+    """Without a hidden-state output the kernel keeps the skip connections' stream as fp16 (csrc/cips_tc.cu ResT): same bound against
+    the fp64 oracle as the fp32 stream; C3D_CIPS_RES16=0 gives back the fp32-stream image bit for bit."""
+    monkeypatch.setenv("C3D_CIPS_PAIR", pair)
+    sd = O.synthetic_state_dict(O.generator_template(), seed=31)
+    G = build_generator("cpu", sd)
+    g = torch.Generator().manual_seed(B * 7 + N)
+    x, w = torch.randn(B, N, 32, generator=g), torch.randn(B, 512, generator=g)
+    with torch.no_grad():
+        ref64 = O.cips_net({k: v.double() for k, v in sd.items()}, x.double(), w.double())
+        with emulated(async_mode=2, seed=N, sms=2) as pkg:
+            ws, s1p, dm, rw, rb = G.inr_net.kernel_inputs({k: w for k in G.inr_net.style_dim_dict}, 9)
+            rgb_h, _ = pkg.ops.cips_forward(x, ws, s1p, dm, rw, rb, impl=TC, return_hidden=True)
+            rgb16 = pkg.ops.cips_forward(x, ws, s1p, dm, rw, rb, impl=TC)
+            monkeypatch.setenv("C3D_CIPS_RES16", "0")
+            rgb32 = pkg.ops.cips_forward(x, ws, s1p, dm, rw, rb, impl=TC)
+    assert rel_err(rgb16, ref64.float())[0] < 1e-3
+    assert torch.equal(rgb32, rgb_h) and not torch.equal(rgb16, rgb_h)
+
+
 def test_emu_cips_tc_cta_pair_falls_back_on_odd_tile_counts(monkeypatch):
     monkeypatch.setenv("C3D_CIPS_PAIR", "1")
     with emulated(async_mode=2, sms=2) as pkg:
@@ -197,10 +220,11 @@ def test_emu_cips_simt_matches_oracle():
     assert e_hid < 1e-3 and e_rgb < 1e-3, (e_hid, e_rgb)
 
 
-def test_emu_detects_the_round1_weight_ring_race():
+def test_emu_detects_the_round1_weight_ring_race(monkeypatch):
     """Fault injection: -DC3D_INJECT_RING_RACE restores the round-1 protocol (an MMA issuer skips the fills of the
     tiles it does not own).  On hardware it only failed under ncu's replay timing; the emulator must report it
     whenever asynchronous operations complete late."""
+    monkeypatch.setenv("C3D_CIPS_PAIR", "0")       # the two-issuer ring is the single-CTA kernel's
     path = _emu.build_emu.build(extra_defs=("C3D_INJECT_RING_RACE",), tag="ringrace")
     good = _emu._cdll
     bad = C.CDLL(path)
@@ -388,10 +412,11 @@ def _cips_chain_fp64(B, N, acts, zs, gp, ws, s1ps, ds, rw, L=18, skip_from=4, rg
 
 @pytest.mark.parametrize("mode", ["eager", "lazy", "random"])
 @pytest.mark.parametrize("B,N", [(1, 128), (2, 200)])
-def test_emu_cips_backward_chain_matches_fp64_chain_from_the_same_stash(B, N, mode):
+def test_emu_cips_backward_chain_matches_fp64_chain_from_the_same_stash(B, N, mode, monkeypatch):
     """c3d_cips_fwd_train (forward + fp16 activation stash + sign bits of z on the residual layers) and c3d_cips_bwd (the
     gradient chain dZ_l = dL/dy_l lrelu'(z_l), dX_l = dZ_l W''_l^T on tcgen05, ToRGB and skip-connection gradients injected in
     the epilogues) against an fp64 evaluation of the same chain from the same stash.  (2, 200): ragged tile, two iterations."""
+    monkeypatch.setenv("C3D_CIPS_RES16", "0")       # the training forward keeps the fp32 residual stream; compare like with like
     sd = O.synthetic_state_dict(O.generator_template(), seed=31)
     g = torch.Generator().manual_seed(B * 7 + N)
     x, w, gp = torch.randn(B, N, 32, generator=g), torch.randn(B, 512, generator=g), torch.randn(B, N, 3, generator=g)

@@ -206,9 +206,10 @@ def test_renderer_fold_math_matches_reference_golden(pkg, name, monkeypatch):
 
 @pytest.mark.parametrize("B,N", [(1, 256), (2, 512), (3, 200), (4, 4096)])
 def test_cips_cta_pair_matches_oracle(pkg, B, N, monkeypatch):
-    """C3D_CIPS_PAIR=1: the cta_group::2 variant of the CIPS kernel against the fp64 oracle and, bit for bit,
-    against the default single-CTA kernel (same fp16 operands, same K order -> identical accumulators expected;
-    a tolerance of 1e-6 absorbs a different in-tile summation order of the pair's tensor cores)."""
+    """The cta_group::2 form of the CIPS kernel (the default wherever an image has an even number of tiles) against the fp64
+    oracle and, bit for bit, against the single-CTA kernel (C3D_CIPS_PAIR=0; same fp16 operands, same K order -> identical
+    accumulators expected; a tolerance of 1e-6 absorbs a different in-tile summation order of the pair's tensor cores).
+    Then the image-only call (fp16 residual stream, see csrc/cips_tc.cu ResT) against the oracle and the fp32-residual image."""
     sd = O.synthetic_state_dict(O.generator_template(), seed=31)
     G = build_generator(DEV, sd)
     g = torch.Generator().manual_seed(B * 7 + N)
@@ -218,13 +219,23 @@ def test_cips_cta_pair_matches_oracle(pkg, B, N, monkeypatch):
         ref64, hid64 = O.cips_net({k: v.double() for k, v in sd.items()}, x.double(), w.double(), return_hidden=True)
         style = {k: w.to(DEV) for k in G.inr_net.style_dim_dict}
         ws, s1p, dm, rw, rb = G.inr_net.kernel_inputs(style, 9)
+        monkeypatch.setenv("C3D_CIPS_PAIR", "0")
         rgb1, hid1 = pkg.ops.cips_forward(x.to(DEV), ws, s1p, dm, rw, rb, impl=pkg._lib.IMPL_TC, return_hidden=True)
+        rgb1i = pkg.ops.cips_forward(x.to(DEV), ws, s1p, dm, rw, rb, impl=pkg._lib.IMPL_TC)
         monkeypatch.setenv("C3D_CIPS_PAIR", "1")
         rgb2, hid2 = pkg.ops.cips_forward(x.to(DEV), ws, s1p, dm, rw, rb, impl=pkg._lib.IMPL_TC, return_hidden=True)
+        rgb2i = pkg.ops.cips_forward(x.to(DEV), ws, s1p, dm, rw, rb, impl=pkg._lib.IMPL_TC)
+        monkeypatch.setenv("C3D_CIPS_RES16", "0")
+        rgb2f = pkg.ops.cips_forward(x.to(DEV), ws, s1p, dm, rw, rb, impl=pkg._lib.IMPL_TC)
         torch.cuda.synchronize()
     assert rel_err(hid2.cpu(), hid64.float())[0] < 1e-3
     assert rel_err(rgb2.cpu(), ref64.float())[0] < 1e-3
     assert rel_err(hid2.cpu(), hid1.cpu())[0] < 1e-6 and rel_err(rgb2.cpu(), rgb1.cpu())[0] < 1e-6
+    # image-only calls: fp16 residual stream.  Same bound against the oracle; identical between the two kernels; and with
+    # C3D_CIPS_RES16=0 the image-only call is the fp32-residual image bit for bit.
+    assert rel_err(rgb2i.cpu(), ref64.float())[0] < 1e-3 and rel_err(rgb1i.cpu(), ref64.float())[0] < 1e-3
+    assert rel_err(rgb2i.cpu(), rgb1i.cpu())[0] < 1e-6
+    assert torch.equal(rgb2f.cpu(), rgb2.cpu())
 
 
 @pytest.mark.parametrize("img_size,nb", [(32, 4), (64, 5), (256, 7), (1024, 9)])   # < 32: reference tanh(int 0) raises
