@@ -632,8 +632,10 @@ __global__ void __launch_bounds__(kThreads, 1) cips_tc_kernel(const KArgs a) {
     }
   } else {
     // ------------------------------------------------------------ epilogue warps
-    reg_inc<104>();
     TRACE_DECL;
+    if (lane == 0) TRACE(1, 20, 0);      // trace builds: how long setmaxnreg.inc waits for the control warps' registers
+    reg_inc<104>();
+    if (lane == 0) TRACE(1, 21, 0);
     const int ew = warp - 4;
     const int wg = ew >> 2;            // column group 0..3
     const int q = warp & 3;            // TMEM lane quarter

@@ -36,6 +36,11 @@ for i in range(n):
     blk, warp, tag, a0, t = int(w >> 8), int(w & 0xFF), int((v >> 56) & 0xFF), int((v >> 40) & 0xFFFF), int(v & 0xFFFFFFFFFF)
     ev.append((blk, t, warp, tag, a0 >> 8, a0 & 0xFF))
 print("events", n)
+for blk in (0, 1):      # setmaxnreg.inc wait of the epilogue warps (tags 20 / 21: before / after)
+    t20 = {w: t for b, t, w, tag, l, i in ev if b == blk and tag == 20}
+    t21 = {w: t for b, t, w, tag, l, i in ev if b == blk and tag == 21}
+    if t20 and t21:
+        print(f"block {blk}: setmaxnreg.inc wait per epilogue warp [clk]: " + " ".join(str(t21[w] - t20[w]) for w in sorted(t20) if w in t21))
 for blk in (0, 1):
     rows = sorted(e for e in ev if e[0] == blk and L0 <= e[4] < L0 + NL)
     if not rows:
