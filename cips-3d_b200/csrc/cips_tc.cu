@@ -26,6 +26,7 @@
 // (they would have to come from shared memory, whose bandwidth the MMA operand fetch already saturates).  Only HBM traffic: x (128 B/pixel) in, rgb (12 B/pixel) out; the residual stream
 // of the skip blocks goes through an L2-resident per-CTA scratch (fp32, 256 KB).
 #include <atomic>
+#include <utility>
 #include <string.h>
 
 #include "c3d_common.cuh"
@@ -340,6 +341,83 @@ __device__ __forceinline__ void epi16_tail(const uint32_t (&acc)[16], const RV (
   }
 }
 
+// ---- PAIR kernel: the issue order of a layer as COMPILE-TIME constants.
+// Entry = kc | h << 4 | need << 8 | acc_ready commit mask << 12 (see build_pair_order on the host, which must produce the same tables:
+// checked at library load in c3d_cips_fwd_tc and by tests/test_boundary_cpu.py through c3d_debug_cips_pair_order).  The issuer's step
+// is the kernel's critical instruction stream: it shares its scheduler with four epilogue warps, and at ~110 instructions a step (table
+// look-ups, decoding, generic loops) it stretched from ~500 to 750-900 clk whenever the epilogue was busy (light trace
+// profiles/r02ae_cips_light_pair_l8.txt; in isolation neither the epilogue's TMEM loads, its shared / global stores, its proxy fences
+// nor the weight stream slow the tensor pipe by a single clock: profiles/r02ai_contention_bench.txt).  With every field a template
+// argument a step is a wait, an election, four MMAs and a commit.
+constexpr uint16_t pair_entry(int kc, int h, int rdy) {
+  return (uint16_t)(kc | (h << 4) | ((kc / 2 > 2 * h + 1 ? kc / 2 : 2 * h + 1) << 8) | (rdy << 12));
+}
+constexpr uint16_t kPairFull[16] = {
+    pair_entry(0, 0, 0), pair_entry(1, 0, 0), pair_entry(2, 0, 0), pair_entry(3, 0, 0), pair_entry(4, 0, 0), pair_entry(5, 0, 0),
+    pair_entry(6, 0, 0), pair_entry(7, 0, 0), pair_entry(0, 1, 0), pair_entry(1, 1, 1), pair_entry(2, 1, 0), pair_entry(3, 1, 2),
+    pair_entry(4, 1, 0), pair_entry(5, 1, 0), pair_entry(6, 1, 0), pair_entry(7, 1, 4 | 8)};
+constexpr uint16_t kPairIn[2] = {pair_entry(0, 0, 2), pair_entry(0, 1, 1 | 4 | 8)};
+
+template <bool PAIR>
+struct PairIssuer {      // state of the leader's issuer warp
+  SmemT<PAIR>* s;
+  uint32_t a_lo0, b_lo0, tmem, stage, phase, epar;
+  int lane, it, l, abl;
+#ifdef C3D_TRACE
+  int tr_n;
+#endif
+};
+// One step: big tile E; PREV_NEED = the epilogue chunks of the previous layer already waited for in this layer (-1: none).
+template <uint16_t E, int PREV_NEED, int IDX, bool PAIR>
+__device__ __forceinline__ void pair_step(PairIssuer<PAIR>& c) {
+  constexpr uint32_t kc = E & 15u, h = (E >> 4) & 15u, rdy = (E >> 12) & 15u;
+  constexpr int need = (E >> 8) & 15;
+  constexpr int NS = SmemT<PAIR>::NS;
+  constexpr uint32_t idesc = umma_idesc_f16(2 * kTileM, 2 * kNC);
+  constexpr uint32_t dhi = umma_desc_hi(kSBO);
+  constexpr uint32_t kStepK16 = (2 * kLBO) >> 4;       // one K=16 MMA step  = 2 core-matrix columns
+  constexpr uint32_t kStepStage = kWTileBytes >> 4;
+  SmemT<PAIR>& s = *c.s;
+#ifdef C3D_TRACE
+  int& tr_n = c.tr_n;
+#endif
+  if (c.lane == 0 && TRACE_TILE(IDX)) TRACE(c.it, 1, (uint32_t)(c.l << 8 | IDX));          // tile reached
+  if (need > PREV_NEED && !(c.abl & 16)) {
+#pragma unroll
+    for (int j = PREV_NEED + 1; j <= need; ++j) wait_warp_cluster(&s.epi_done[j], c.epar, c.lane);     // half of the arrivals come from the peer CTA
+  }
+  if (c.lane == 0 && TRACE_TILE(IDX)) TRACE(c.it, 3, (uint32_t)(c.l << 8 | IDX));          // epilogue dependency satisfied
+  wait_warp(&s.full[c.stage], c.phase, c.lane);
+  if (c.lane == 0 && TRACE_TILE(IDX)) TRACE(c.it, 5, (uint32_t)(c.l << 8 | IDX));          // weight tile landed (both halves)
+  tc_fence_after();
+  if (elect_one()) {
+    const uint32_t a_lo = c.a_lo0 + kc * (kStepK16 * (kKC / 16));
+    const uint32_t b_lo = c.b_lo0 + c.stage * kStepStage;
+    const uint32_t d = c.tmem + h * (2 * kNC);
+    if (!(c.abl & 2)) {
+      umma_ss_w_cg2(d, a_lo, b_lo, dhi, idesc, kc != 0);
+      umma_ss_w_cg2(d, a_lo + kStepK16, b_lo + kStepK16, dhi, idesc, 1);
+      umma_ss_w_cg2(d, a_lo + 2 * kStepK16, b_lo + 2 * kStepK16, dhi, idesc, 1);
+      umma_ss_w_cg2(d, a_lo + 3 * kStepK16, b_lo + 3 * kStepK16, dhi, idesc, 1);
+    }
+    tc_commit_cg2_mc(&s.empty[c.stage], 3);      // stage free in BOTH CTAs
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      if (rdy & (1u << j)) tc_commit_cg2_mc(&s.acc_ready[j], 3);      // S_j complete: accumulator block j done, A chunk j no longer read
+  }
+  __syncwarp();
+  if (++c.stage == (uint32_t)NS) { c.stage = 0; c.phase ^= 1; }
+}
+template <bool PAIR, size_t... I>
+__device__ __forceinline__ void pair_layer_full(PairIssuer<PAIR>& c, std::index_sequence<I...>) {
+  (pair_step<kPairFull[I], (I == 0 ? -1 : (int)((kPairFull[I == 0 ? 0 : I - 1] >> 8) & 15)), (int)I, PAIR>(c), ...);
+}
+template <bool PAIR>
+__device__ __forceinline__ void pair_layer_in(PairIssuer<PAIR>& c) {
+  pair_step<kPairIn[0], -1, 0, PAIR>(c);
+  pair_step<kPairIn[1], (int)((kPairIn[0] >> 8) & 15), 1, PAIR>(c);
+}
+
 // PAIR (CL == 2 only): the two CTAs of a cluster form a tcgen05 CTA pair.  Only the leader (cluster rank 0) issues MMAs
 // (cta_group::2, M = 256: the leader's 128 pixels and the peer's 128 pixels against the same 256 weight columns); each CTA
 // streams ITS half of every big weight tile into its own ring; the peer relays "my half landed" to the leader's full barrier;
@@ -460,58 +538,26 @@ __global__ void __launch_bounds__(kThreads, 1) cips_tc_kernel(const KArgs a) {
           }
         }
     } else if (warp == 1) {
-      // ---------------------------------------------------------- MMA issuer (leader CTA; whole warp converged, one lane issues)
-      const uint32_t idesc = umma_idesc_f16(2 * kTileM, 2 * kNC);
-      const uint32_t dhi = umma_desc_hi(kSBO);
-      const uint32_t a_lo0 = umma_desc_lo(smem_u32(s.x), kLBO);
-      const uint32_t b_lo0 = umma_desc_lo(smem_u32(s.w[0]), RC::kLBO_B);
-      constexpr uint32_t kStepK16 = (2 * kLBO) >> 4;       // one K=16 MMA step  = 2 core-matrix columns
-      constexpr uint32_t kStepK16B = (2 * RC::kLBO_B) >> 4;
-      constexpr uint32_t kStepStage = RC::kStageBytes >> 4;
+      // ---------------------------------------------------------- MMA issuer (leader CTA; whole warp converged, one lane issues):
+      // the layer's steps are unrolled with their tile, dependency and commit mask as template arguments (pair_step above)
+      PairIssuer<PAIR> c;
+      c.s = &s;
+      c.a_lo0 = umma_desc_lo(smem_u32(s.x), kLBO);
+      c.b_lo0 = umma_desc_lo(smem_u32(s.w[0]), RC::kLBO_B);
+      c.tmem = tmem;
+      c.stage = 0; c.phase = 0;
+      c.lane = lane; c.abl = abl;
+#ifdef C3D_TRACE
+      c.tr_n = 0;
+#endif
       for (int it = 0; it < iters; ++it) {
-        for (int l = 0; l < L; ++l) {
-          const uint32_t epar = (uint32_t)(it * L + l) & 1u;   // phase of the epilogue that feeds layer l (staging for l = 0)
-          const bool full_layer = a.layer_kc[l] * 2 == 16;
-          const uint16_t* big = full_layer ? a.big_full : a.big_in;
-          const int n_big = full_layer ? 16 : 2;
-          int waited = -1;
-          uint32_t e = big[0];
+        c.it = it;
 #pragma unroll 1
-          for (int i = 0; i < n_big; ++i) {
-            const uint32_t e_next = big[i + 1 < n_big ? i + 1 : i];      // fetched ahead of the waits
-            const uint32_t kc = e & 15u, h = (e >> 4) & 15u;
-            const int need = (int)((e >> 8) & 15u);
-            if (lane == 0 && TRACE_TILE(i)) TRACE(it, 1, (uint32_t)(l << 8 | i));          // tile reached
-            if (need > waited && !(abl & 16)) {
-              for (int j = waited + 1; j <= need; ++j) wait_warp_cluster(&s.epi_done[j], epar, lane);     // half of the arrivals come from the peer CTA
-              waited = need;
-            }
-            if (lane == 0 && TRACE_TILE(i)) TRACE(it, 3, (uint32_t)(l << 8 | i));          // epilogue dependency satisfied
-            wait_warp(&s.full[stage], phase, lane);
-            if (lane == 0 && TRACE_TILE(i)) TRACE(it, 5, (uint32_t)(l << 8 | i));          // weight tile landed (both halves)
-            tc_fence_after();
-            if (elect_one()) {
-              const uint32_t a_lo = a_lo0 + kc * (kStepK16 * (kKC / 16));
-              const uint32_t b_lo = b_lo0 + stage * kStepStage;
-              const uint32_t d = tmem + h * (2 * kNC);
-              if (!(abl & 2)) {
-                umma_ss_w_cg2(d, a_lo, b_lo, dhi, idesc, kc != 0);
-                umma_ss_w_cg2(d, a_lo + kStepK16, b_lo + kStepK16B, dhi, idesc, 1);
-                umma_ss_w_cg2(d, a_lo + 2 * kStepK16, b_lo + 2 * kStepK16B, dhi, idesc, 1);
-                umma_ss_w_cg2(d, a_lo + 3 * kStepK16, b_lo + 3 * kStepK16B, dhi, idesc, 1);
-              }
-              tc_commit_cg2_mc(&s.empty[stage], 3);      // stage free in BOTH CTAs
-              const uint32_t rdy = (e >> 12) & 15u;    // chunks j whose set S_j this tile completes
-              if (rdy) {
-#pragma unroll
-                for (int j = 0; j < 4; ++j)
-                  if (rdy & (1u << j)) tc_commit_cg2_mc(&s.acc_ready[j], 3);
-              }
-            }
-            __syncwarp();
-            if (++stage == NS) { stage = 0; phase ^= 1; }
-            e = e_next;
-          }
+        for (int l = 0; l < L; ++l) {
+          c.l = l;
+          c.epar = (uint32_t)(it * L + l) & 1u;   // phase of the epilogue that feeds layer l (staging for l = 0)
+          if (a.layer_kc[l] * 2 == 16) pair_layer_full<PAIR>(c, std::make_index_sequence<16>{});
+          else pair_layer_in<PAIR>(c);
         }
       }
     }
@@ -1115,6 +1161,11 @@ int c3d_cips_fwd_tc(const C3dCipsParams* p, const C3dCipsWeights* w, const float
   build_tile_order(ka.order_full, ka.order_in);
   uint16_t pair_full[32], pair_in[4];      // stream order of the PAIR kernel, as (kc, nc) tiles for the prep kernel
   build_pair_order(ka.big_full, ka.big_in, pair_full, pair_in);
+  for (int i = 0; i < 16; ++i)      // the kernel's compile-time order (kPairFull / kPairIn) must be the order the weights are prepared in
+    if (ka.big_full[i] != kPairFull[i] || (i < 2 && ka.big_in[i] != kPairIn[i])) {
+      c3d_set_error("cips(tc): pair tile order mismatch at %d (host 0x%x, kernel 0x%x)", i, ka.big_full[i], kPairFull[i]);
+      return C3D_EINVAL;
+    }
   int cl = 1;
   bool pair = false;
   const int grid = cips_grid(p, &cl, &pair);
