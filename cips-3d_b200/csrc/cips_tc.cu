@@ -95,11 +95,6 @@ struct KArgs {
   // this order so the producer streams linearly.
   uint16_t order_full[32];
   uint16_t order_in[4];
-  // PAIR kernel: issue order of the 16 big tiles (kc, h) of a layer -- h = which 256 accumulator columns -- and of the 2 of the
-  // input layer: kc | h << 4 | need << 8 | acc_ready commit mask << 12.  The prepared weights hold them in this order, CTA 0's half
-  // (kc, 2h) followed by CTA 1's (kc, 2h + 1).
-  uint16_t big_full[16];
-  uint16_t big_in[2];
   // training (DUMP instantiation only): every layer's output y_l (after LeakyReLU and residual) as the fp16 values the next
   // layer consumed, (n_layers, B, N, 512) row-major, for the backward pass (cips_bwd_tc.cu).  Appended: the offsets of the
   // fields above are those of the round-1 kernel.
@@ -342,8 +337,8 @@ __device__ __forceinline__ void epi16_tail(const uint32_t (&acc)[16], const RV (
 }
 
 // ---- PAIR kernel: the issue order of a layer as COMPILE-TIME constants.
-// Entry = kc | h << 4 | need << 8 | acc_ready commit mask << 12 (see build_pair_order on the host, which must produce the same tables:
-// checked at library load in c3d_cips_fwd_tc and by tests/test_boundary_cpu.py through c3d_debug_cips_pair_order).  The issuer's step
+// Entry = kc | h << 4 | need << 8 | acc_ready commit mask << 12 (build_pair_order on the host derives the same tables from the dependency
+// rules and lays the weights out in that order; c3d_cips_fwd_tc refuses to launch if the two ever disagree).  The issuer's step
 // is the kernel's critical instruction stream: it shares its scheduler with four epilogue warps, and at ~110 instructions a step (table
 // look-ups, decoding, generic loops) it stretched from ~500 to 750-900 clk whenever the epilogue was busy (light trace
 // profiles/r02ae_cips_light_pair_l8.txt; in isolation neither the epilogue's TMEM loads, its shared / global stores, its proxy fences
@@ -1159,11 +1154,11 @@ int c3d_cips_fwd_tc(const C3dCipsParams* p, const C3dCipsWeights* w, const float
   ka.layer_tile_off[L] = off;
   ka.img_tile_stride = (size_t)off;
   build_tile_order(ka.order_full, ka.order_in);
-  uint16_t pair_full[32], pair_in[4];      // stream order of the PAIR kernel, as (kc, nc) tiles for the prep kernel
-  build_pair_order(ka.big_full, ka.big_in, pair_full, pair_in);
+  uint16_t big_full[16], big_in[2], pair_full[32], pair_in[4];      // PAIR kernel: big-tile order; the same as (kc, nc) tiles for the prep kernel
+  build_pair_order(big_full, big_in, pair_full, pair_in);
   for (int i = 0; i < 16; ++i)      // the kernel's compile-time order (kPairFull / kPairIn) must be the order the weights are prepared in
-    if (ka.big_full[i] != kPairFull[i] || (i < 2 && ka.big_in[i] != kPairIn[i])) {
-      c3d_set_error("cips(tc): pair tile order mismatch at %d (host 0x%x, kernel 0x%x)", i, ka.big_full[i], kPairFull[i]);
+    if (big_full[i] != kPairFull[i] || (i < 2 && big_in[i] != kPairIn[i])) {
+      c3d_set_error("cips(tc): pair tile order mismatch at %d (host 0x%x, kernel 0x%x)", i, big_full[i], kPairFull[i]);
       return C3D_EINVAL;
     }
   int cl = 1;
