@@ -146,7 +146,9 @@ def render_features(siren, film, cam2world, jitter_u, pdf_u=None, noise_c=None, 
 def cips_forward(x, weights, style1p, demod, rgb_w, rgb_b, *, n_blocks=9, skip_from=4, rgb_from=3,
                  impl=None, return_hidden=False):
     """x (B,N,in) -> tanh(rgb) (B,N,3).  weights[l] (in_l,out), style1p[l] (B,in_l),
-    demod[l] (B,out), rgb_w[b] (3,hidden) / rgb_b[b] (3,) (None for blocks < rgb_from)."""
+    demod[l] (B,out), rgb_w[b] (3,hidden) / rgb_b[b] (3,) (None for blocks < rgb_from).
+    return_hidden=False (the image alone) lets the tensor-core kernel keep the skip connections' stream as fp16 (csrc/cips_tc.cu ResT;
+    C3D_CIPS_RES16=0 turns that off); with return_hidden=True the stream is fp32 and the image is bit-identical to that setting's."""
     lib = load()
     x = _f32c(x, "x")
     B, N, in_dim = x.shape
