@@ -1,5 +1,10 @@
 // Fused per-pixel CIPS synthesis MLP on tcgen05 (C3D_IMPL_TC).
 //
+// Two forms of one kernel (template parameter PAIR).  The default wherever an image has an even number of tiles is the CTA PAIR
+// (tcgen05 cta_group::2: M = 256 x N = 256 MMAs issued by one thread of the leader CTA, each CTA streaming its half of the weights;
+// see the PAIR branch and DESIGN.md 4.2b for the measurements that led there); the single-CTA form described next serves odd tile
+// counts and the training forward (activation stash).  Both share the tile walk, the staircase and the two-phase epilogue.
+//
 // One persistent CTA per SM walks 128-pixel tiles (all pixels of a tile belong to one image).
 // For a tile, the whole 18-layer chain  x -> [mod-linear 512x512 + demod + LeakyReLU]x2 (+skip)
 // -> ToRGB ... -> tanh  runs on-chip:
@@ -24,7 +29,7 @@
 // fp16 tiles of  W''[k][n] = s1p[k] * W[k][n] * d[n]  (the reference's modulated + demodulated weight);
 // all 512 pixel tiles of an image stream the same 9.3 MB, so the epilogue needs no per-column constants
 // (they would have to come from shared memory, whose bandwidth the MMA operand fetch already saturates).  Only HBM traffic: x (128 B/pixel) in, rgb (12 B/pixel) out; the residual stream
-// of the skip blocks goes through an L2-resident per-CTA scratch (fp32, 256 KB).
+// of the skip blocks goes through an L2-resident per-CTA scratch (fp32, 256 KB; fp16 when only the image is returned: ResT below).
 #include <atomic>
 #include <utility>
 #include <string.h>
