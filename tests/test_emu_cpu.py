@@ -558,7 +558,7 @@ def _bits(tensors):
     return tuple(hashlib.sha1(t.detach().contiguous().numpy().tobytes()).hexdigest() for t in tensors)
 
 
-@pytest.mark.parametrize("what,env", [("ray", {}), ("ray", {"C3D_RAY_MATH": "fold"}), ("cips", {"C3D_CIPS_PAIR": "1"}),
+@pytest.mark.parametrize("what,env", [("ray", {}), ("ray", {"C3D_RAY_MATH": "fold"}), ("cips", {"C3D_CIPS_PAIR": "1"}), ("cips_image", {"C3D_CIPS_PAIR": "1"}),
                                       ("cips_train", {}), ("pigan", {"C3D_PIGAN_IMPL": "tc", "C3D_PIGAN_PAIR": "1"})])
 def test_emu_outputs_are_bit_identical_across_schedules(what, env, monkeypatch):
     """A race that stays inside the parity tolerances would still make the output depend on WHEN asynchronous operations
@@ -575,10 +575,12 @@ def test_emu_outputs_are_bit_identical_across_schedules(what, env, monkeypatch):
         if what == "ray":
             out, _ = _render(pkg, "r16_trained_noise", TC, debug=False, want_depth=True, want_weights=True)
             return out["pixels_fea"], out["depth"], out["weights"]
-        if what == "cips":
+        if what in ("cips", "cips_image"):     # cips_image: no hidden state asked for -> fp16 residual stream
             G = build_generator("cpu", sd)
             with torch.no_grad():
                 ws, s1p, dm, rw, rb = G.inr_net.kernel_inputs({k: w for k in G.inr_net.style_dim_dict}, 9)
+                if what == "cips_image":
+                    return (pkg.ops.cips_forward(x, ws, s1p, dm, rw, rb, impl=TC),)
                 return pkg.ops.cips_forward(x, ws, s1p, dm, rw, rb, impl=TC, return_hidden=True)
         if what == "cips_train":
             net = build_generator("cpu", sd).train().inr_net
@@ -594,7 +596,7 @@ def test_emu_outputs_are_bit_identical_across_schedules(what, env, monkeypatch):
         with emulated(**s) as pkg:
             seen.append(_bits(run(pkg)))
     assert seen[0] == seen[1] == seen[2]
-    if what == "cips":          # and the pair form computes exactly what the default form computes
+    if what in ("cips", "cips_image"):          # and the pair form computes exactly what the single-CTA form computes
         monkeypatch.setenv("C3D_CIPS_PAIR", "0")
         with emulated(**_SCHEDULES[0]) as pkg:
             assert _bits(run(pkg)) == seen[0]
