@@ -681,7 +681,8 @@ class GeneratorNerfINR(nn.Module):              # generator.py:1158-1951
                                   ray_idx=ray_idx)
 
     # volume integration of the autograd graph: 'torch' (round-1 behaviour) or 'fused' (ops.IntegrateFunction, csrc/integrate_ops.cu:
-    # one native pass forward, one backward) -- opt-in until timed on hardware, like FiLMLayer.fused_film
+    # one native pass forward, one backward) -- opt-in like FiLMLayer.fused_film (validated and timed on a B200 in round 2, DESIGN.md 4.13;
+    # the default stays the torch-op graph of the reference)
     train_integrate = 'torch'
 
     def _render_torch(self, style_dict, c2w, jitter_u, pdf_u, noise_c, noise_f, *, img_size, fov, ray_start,
